@@ -1,0 +1,149 @@
+/* thrl.h — C ABI of the B200-native th_rl training hot path.
+ *
+ * One shared library (libthrl.so, built from th_rl_b200/csrc/) exports the `thrl_*` entry
+ * points declared here.  They replace, batched over R independent runs, the duck-typed Python
+ * protocol the reference's trainer drives once per run (the reference has no FFI; these are the
+ * symbols a ctypes binding of that protocol would bind):
+ *
+ *   thrl_qtable_scan        <- th_rl/trainer.py:45-70   (epoch/step loop)
+ *                              th_rl/agents.py:80-89    (QTable.sample_action)
+ *                              th_rl/agents.py:47-57    (QTable.encode / scale)
+ *                              th_rl/environments.py:18-39 (NoisyPriceState.step)
+ *                              th_rl/buffers.py:12,18-19,28-41 (ReplayBuffer append/replay/empty)
+ *                              th_rl/agents.py:59-78    (QTable.train_net)
+ *                              th_rl/trainer.py:40-41,65-66 (rewards_log / actions_log)
+ *   thrl_qtable_scan_host   <- the same call with HOST buffers (H2D + scan + D2H inside)
+ *   thrl_qtable_init        <- th_rl/agents.py:29,45 (table = 12.5/(1-gamma)+randn, counter = 0)
+ *                              th_rl/environments.py:15-16,50-53 (reset: price ~ U(0,a))
+ *   thrl_greedy_eval        <- th_rl/utils.py:27-47 (play_game) + th_rl/agents.py:91-92 (get_action)
+ *
+ * Conventions: plain C types only; every pointer in ThrlScanArgs is a DEVICE pointer owned by
+ * the caller unless the entry point's name ends in `_host`; nothing is allocated or freed by the
+ * library on the device-pointer path; calls are asynchronous on the caller's cudaStream_t (passed
+ * as void*); the return value is 0 or a negative ThrlStatus, with a message in thrl_last_error().
+ * The reference raises AssertionError/IndexError for bad configs (trainer.py:21-23, agents.py:88);
+ * here those become THRL_ERR_BAD_CONFIG before anything is launched.
+ */
+#ifndef THRL_H_
+#define THRL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define THRL_ABI_VERSION 1
+#define THRL_MAX_AGENTS 16
+#define THRL_MAX_ACTIONS 256 /* greedy-action cache is one byte per table row */
+
+typedef enum ThrlStatus {
+  THRL_OK = 0,
+  THRL_ERR_BAD_CONFIG = -1,  /* reference: AssertionError / IndexError at construction or first step */
+  THRL_ERR_BAD_ARGS = -2,    /* null / inconsistent pointers */
+  THRL_ERR_UNSUPPORTED = -3, /* shape outside what the kernels were built for */
+  THRL_ERR_CUDA = -4,        /* a CUDA runtime call failed; text in thrl_last_error() */
+  THRL_ERR_NO_DEVICE = -5    /* no sm_100 device: there is no CPU fallback */
+} ThrlStatus;
+
+typedef enum ThrlDtype {
+  THRL_F32 = 0, /* fp32 storage, update arithmetic in f64 with one final rounding (fast path) */
+  THRL_F64 = 1  /* the reference's own dtype: bit-exact tables (agents.py:29) */
+} ThrlDtype;
+
+typedef enum ThrlRngMode {
+  THRL_RNG_PHILOX = 0,        /* free running: Philox4x32-10 keyed (seed), counter (run, epoch, step, stream) */
+  THRL_RNG_REPLAY_DRAWS = 1,  /* replay recorded exploration draws u / random action; greedy picked here */
+  THRL_RNG_REPLAY_ACTIONS = 2 /* teacher forcing: every action is taken from replay_ra */
+} ThrlRngMode;
+
+/* One agent.  Field names and defaults follow QTable.__init__ (th_rl/agents.py:13-27). */
+typedef struct ThrlAgentSpec {
+  int32_t states;     /* table has states+1 rows (agents.py:29) */
+  int32_t actions;    /* columns; 1..THRL_MAX_ACTIONS */
+  int32_t min_memory; /* update fires when buffered transitions >= min_memory (agents.py:60) */
+  int32_t capacity;   /* deque(maxlen=capacity) (buffers.py:12) */
+  double action_lo, action_hi; /* action_range */
+  double max_state;
+  double gamma, alpha, eps_end, eps_step; /* used when ThrlScanArgs.hp == NULL */
+  int64_t table_offset;                   /* element offset inside one run's slab; set by thrl_game_layout */
+} ThrlAgentSpec;
+
+/* One game = n agents + NoisyPriceState kwargs (th_rl/environments.py:5-13). */
+typedef struct ThrlGame {
+  int32_t n_agents;
+  int32_t max_steps;
+  double a, b, noise_prob;
+  ThrlAgentSpec agent[THRL_MAX_AGENTS];
+  int64_t run_stride; /* elements per run slab = sum_i (states_i+1)*actions_i; set by thrl_game_layout */
+  int32_t ring_len;   /* transitions a run may hold across an epoch boundary; set by thrl_game_layout */
+  int32_t regular;    /* 1 if every agent's buffer is empty at every epoch boundary (min_memory <= max_steps) */
+} ThrlGame;
+
+/* Fixed-point scales of the cross-run statistics (exact, order-independent integer sums). */
+#define THRL_STATS_K 4 /* sum r, sum r^2, sum x, sum x^2 of the per-epoch means, per (epoch, agent) */
+#define THRL_STATS_SCALE_SUM 4294967296.0 /* 2^32 */
+#define THRL_STATS_SCALE_SQ 16777216.0    /* 2^24 */
+
+typedef struct ThrlScanArgs {
+  const ThrlGame* game; /* HOST pointer */
+  int64_t n_runs;       /* runs held by this call (this GPU's shard) */
+  int64_t run_id0;      /* global id of local run 0: Philox counters use global ids => results do not depend on the sharding */
+  int32_t epoch_begin;  /* epochs [epoch_begin, epoch_end) are played; arrays below are indexed by e - epoch_begin */
+  int32_t epoch_end;
+  int32_t table_dtype; /* ThrlDtype */
+  int32_t rng_mode;    /* ThrlRngMode */
+  uint64_t seed;
+
+  /* per-run state, read and written in place */
+  void* q;           /* [R][run_stride] f32 or f64; agent i's table at table_offset_i, row-major [states_i+1][actions_i] */
+  uint32_t* counter; /* [R][run_stride] visit counts (agents.py:45,76); may be NULL */
+  double* eps;       /* [R][n] current epsilon */
+  double* price;     /* [R] current state = last price (environments.py:36) */
+  const double* hp;  /* NULL or [R][n][4] = alpha, gamma, eps_end, eps_step per run (hyper-parameter sweeps) */
+  void* ring;        /* NULL or [R][thrl_ring_bytes(game)] opaque transition buffer carried between calls;
+                        required when game->regular == 0 */
+
+  /* replay streams (rng_mode != PHILOX); [R][E][T][n] / [R][E][T] */
+  const double* replay_u;     /* recorded random.uniform(0,1) (agents.py:81); REPLAY_DRAWS only */
+  const int32_t* replay_ra;   /* REPLAY_DRAWS: recorded random.choice result, -1 where not drawn (agents.py:82);
+                                 REPLAY_ACTIONS: the action to take */
+  const double* replay_new_a; /* NULL (no noise: new_a = a) or recorded demand intercept per step (environments.py:28-31) */
+
+  /* outputs, all optional */
+  double* rewards_log; /* [n_log_runs][E][n] per-epoch mean reward (trainer.py:65) for runs 0..n_log_runs-1 */
+  double* actions_log; /* [n_log_runs][E][n] per-epoch mean scaled action (trainer.py:66) */
+  int64_t n_log_runs;
+  int64_t* stats;         /* [E][n][THRL_STATS_K] fixed-point sums over the runs of this call, accumulated (+=) */
+  int32_t* trace_actions; /* [R][E][T][n] chosen action indices */
+  double* trace_rewards;  /* [R][E][T][n] */
+  double* trace_prices;   /* [R][E][T] */
+} ThrlScanArgs;
+
+/* Host-side helpers (no device needed). */
+int thrl_abi_version(void);
+const char* thrl_last_error(void);
+/* Validates the game like the reference's constructors would, fills table_offset / run_stride / ring_len / regular. */
+int thrl_game_layout(ThrlGame* game);
+int64_t thrl_ring_bytes(const ThrlGame* game);
+
+/* Device entry points. `stream` is a cudaStream_t. */
+int thrl_qtable_scan(const ThrlScanArgs* args, void* stream);
+/* Same arguments but every pointer in *args is a HOST pointer; copies in, scans, copies back, synchronises. */
+int thrl_qtable_scan_host(const ThrlScanArgs* args, int device);
+/* Fills q (12.5/(1-gamma_i) + N(0,1)), counter (0), eps (eps0[i]), price (U(0,a)) for runs of this shard from
+ * Philox(seed, global run id); eps0 is a HOST array of n doubles. */
+int thrl_qtable_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
+                     const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps, double* price,
+                     void* stream);
+/* Greedy rollout (no exploration, no update): `iters` episodes per run, each starting from price0[r][it];
+ * rewards/actions [R][iters*T][n] as utils.play_game returns them per run. */
+int thrl_greedy_eval(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, int32_t iters,
+                     const double* price0, double* rewards, double* actions, void* stream);
+/* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
+int64_t thrl_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THRL_H_ */

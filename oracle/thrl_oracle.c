@@ -1,0 +1,468 @@
+/* thrl_oracle.c — CPU restatement of the th_rl QTable training hot path.
+ *
+ * TEST INFRASTRUCTURE, NOT PRODUCT.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this file's shared object; the product
+ * (th_rl_b200/) never does and has no CPU fallback.
+ *
+ * Parity status: PINNED.  tests/test_oracle_golden.py checks this restatement bit-for-bit
+ * (actions, rewards, prices, f64 tables, counters, epsilon, per-epoch logs) against streams
+ * recorded from the unmodified reference by oracle/make_goldens.py (tests/golden/*.npz).
+ * The reference ships no tests or golden vectors of its own.
+ *
+ * Everything here is scalar f64/f32 IEEE arithmetic in the reference's operation order; build
+ * with -ffp-contract=off (see oracle/Makefile) so no FMA is formed.
+ *
+ * Reference lines restated (paths relative to /root/reference):
+ *   scan_run()      th_rl/trainer.py:45-70      epoch / step loop, log accumulation :65-66
+ *   act_row()       th_rl/agents.py:47-49,84-88 float32 encode used when acting (trainer.py:53)
+ *   upd_row()       th_rl/agents.py:47-49,62,66 float64 encode used when updating
+ *   scale_action()  th_rl/agents.py:51-57
+ *   env step        th_rl/environments.py:22-39
+ *   buffer          th_rl/buffers.py:12,18-19,28-41 (deque(maxlen=capacity), replay in order, empty)
+ *   train_net()     th_rl/agents.py:59-78
+ * Two modes have no reference counterpart and are specified in DESIGN.md ("fp32 storage",
+ * "Philox streams"); the CUDA kernels must match this file bit-for-bit in those modes too.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/thrl.h"
+#include <pthread.h>
+#include <unistd.h>
+
+/* ---------------------------------------------------------------- Philox4x32-10 (DESIGN.md "Philox streams") */
+#define PHILOX_M0 0xD2511F53u
+#define PHILOX_M1 0xCD9E8D57u
+#define PHILOX_W0 0x9E3779B9u
+#define PHILOX_W1 0xBB67AE85u
+enum { STREAM_ACT = 0, STREAM_ENV = 1, STREAM_INIT_Q = 2, STREAM_INIT_P = 3 };
+
+static void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                          uint32_t out[4]) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += PHILOX_W0; k1 += PHILOX_W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+/* 53-bit uniform in [0,1): 32 bits of hi, top 21 bits of lo */
+static double u53(uint32_t hi, uint32_t lo) {
+  uint64_t m = ((uint64_t)hi << 21) | (lo >> 11);
+  return (double)m * (1.0 / 9007199254740992.0);
+}
+
+/* ---------------------------------------------------------------- deterministic N(0,1) from a 53-bit uniform
+ * (used by thrl_oracle_qtable_init; DESIGN.md "Device init").  Only + - * / and sqrt, in a fixed order, so the
+ * CUDA version (explicit _rn intrinsics) reproduces it bit-for-bit.  log() is our own: frexp + atanh series. */
+static double det_log(double x) {
+  int e;
+  double m = frexp(x, &e); /* m in [0.5,1) */
+  if (m < 0.70710678118654752) { m = m * 2.0; e -= 1; }
+  double s = (m - 1.0) / (m + 1.0), s2 = s * s;
+  double p = 1.0 / 27.0;
+  for (int k = 25; k >= 1; k -= 2) p = p * s2 + 1.0 / (double)k;
+  return (double)e * 0.6931471805599453094 + 2.0 * s * p;
+}
+/* Acklam's rational approximation of the inverse normal CDF (|rel err| < 1.2e-9), p in (0,1) */
+static double det_norminv(double p) {
+  static const double a[6] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                              1.383577518672690e+02, -3.066479806614716e+01, 2.506628277459239e+00};
+  static const double b[5] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                              6.680131188771972e+01, -1.328068155288572e+01};
+  static const double c[6] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                              -2.549732539343734e+00, 4.374664141464968e+00, 2.938163982698783e+00};
+  static const double d[4] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00,
+                              3.754408661907416e+00};
+  const double plow = 0.02425;
+  if (p < plow || p > 1.0 - plow) {
+    double pp = p < plow ? p : 1.0 - p;
+    double q = sqrt(-2.0 * det_log(pp));
+    double num = ((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5];
+    double den = (((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0;
+    double x = num / den;
+    return p < plow ? x : -x;
+  }
+  double q = p - 0.5, r = q * q;
+  double num = (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q;
+  double den = ((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1.0;
+  return num / den;
+}
+
+/* ---------------------------------------------------------------- table access by dtype */
+typedef struct Table {
+  int dtype;
+  void* base; /* this agent's table of this run */
+  int rows, cols;
+} Table;
+static double tget(const Table* t, int64_t row, int64_t col) {
+  int64_t i = row * t->cols + col;
+  return t->dtype == THRL_F64 ? ((const double*)t->base)[i] : (double)((const float*)t->base)[i];
+}
+static void tset(Table* t, int64_t row, int64_t col, double v) {
+  int64_t i = row * t->cols + col;
+  if (t->dtype == THRL_F64) ((double*)t->base)[i] = v;
+  else ((float*)t->base)[i] = (float)v; /* fp32 storage: one rounding, to nearest even */
+}
+/* numpy.argmax(table[[row]]): first maximal index (agents.py:88) */
+static int row_argmax(const Table* t, int64_t row) {
+  int best = 0;
+  double bv = tget(t, row, 0);
+  for (int k = 1; k < t->cols; ++k) {
+    double v = tget(t, row, k);
+    if (v > bv) { bv = v; best = k; }
+  }
+  return best;
+}
+/* numpy.max(table[ns]) (agents.py:71) */
+static double row_max(const Table* t, int64_t row) {
+  double bv = tget(t, row, 0);
+  for (int k = 1; k < t->cols; ++k) {
+    double v = tget(t, row, k);
+    if (v > bv) bv = v;
+  }
+  return bv;
+}
+
+/* agents.py:47-49 on the float32 state trainer.py:53 hands to sample_action */
+static int64_t act_row(double price, const ThrlAgentSpec* s) {
+  float st = (float)price;
+  float x = st / (float)s->max_state;
+  x = x * (float)s->states;
+  return (int64_t)rintf(x); /* numpy.round: half to even */
+}
+/* agents.py:47-49 on the float64 states stored in the buffer (agents.py:62,66) */
+static int64_t upd_row(double price, const ThrlAgentSpec* s) {
+  double x = price / s->max_state;
+  x = x * (double)s->states;
+  return (int64_t)rint(x);
+}
+/* agents.py:51-57 */
+static double scale_action(int k, const ThrlAgentSpec* s) {
+  return (double)k / ((double)s->actions - 1.0) * (s->action_hi - s->action_lo) + s->action_lo;
+}
+
+typedef struct Transition { /* buffers.py Experience(state, action, reward, done, new_state); `done` is never read */
+  double state, reward, new_state;
+  int action;
+} Transition;
+
+typedef struct Buffer { /* deque(maxlen=capacity) */
+  Transition* item;
+  int cap, len, head; /* head = index of the oldest element */
+} Buffer;
+static void buf_append(Buffer* b, Transition t) {
+  if (b->cap <= 0) return;
+  if (b->len < b->cap) {
+    b->item[(b->head + b->len) % b->cap] = t;
+    b->len++;
+  } else { /* full: drop the oldest (deque maxlen) */
+    b->item[b->head] = t;
+    b->head = (b->head + 1) % b->cap;
+  }
+}
+
+static int64_t fx_round(double x) { return (int64_t)llrint(x); }
+
+/* One run, epochs [e0,e1).  Returns 0, or -1 on a row index outside the table (the reference's IndexError). */
+static int scan_run(const ThrlScanArgs* A, int64_t r) {
+  const ThrlGame* G = A->game;
+  const int n = G->n_agents, T = G->max_steps, E = A->epoch_end - A->epoch_begin;
+  Table tab[THRL_MAX_AGENTS];
+  Buffer buf[THRL_MAX_AGENTS];
+  double alpha[THRL_MAX_AGENTS], gamma[THRL_MAX_AGENTS], eps_end[THRL_MAX_AGENTS], eps_step[THRL_MAX_AGENTS];
+  const size_t esz = A->table_dtype == THRL_F64 ? 8 : 4;
+  int rc = 0;
+  for (int i = 0; i < n; ++i) {
+    const ThrlAgentSpec* s = &G->agent[i];
+    tab[i].dtype = A->table_dtype;
+    tab[i].base = (char*)A->q + ((size_t)r * G->run_stride + s->table_offset) * esz;
+    tab[i].rows = s->states + 1;
+    tab[i].cols = s->actions;
+    buf[i].cap = s->capacity;
+    buf[i].len = buf[i].head = 0;
+    buf[i].item = (Transition*)malloc(sizeof(Transition) * (size_t)(s->capacity > 0 ? s->capacity : 1));
+    if (A->hp) {
+      const double* h = A->hp + ((size_t)r * n + i) * 4;
+      alpha[i] = h[0]; gamma[i] = h[1]; eps_end[i] = h[2]; eps_step[i] = h[3];
+    } else {
+      alpha[i] = s->alpha; gamma[i] = s->gamma; eps_end[i] = s->eps_end; eps_step[i] = s->eps_step;
+    }
+  }
+  double* eps = A->eps + (size_t)r * n;
+  double price = A->price[r]; /* trainer.py:45 state = environment.reset(), carried over all epochs */
+  const uint64_t gid = (uint64_t)(A->run_id0 + r);
+  const uint32_t k0 = (uint32_t)A->seed, k1 = (uint32_t)(A->seed >> 32);
+  int act[THRL_MAX_AGENTS];
+  double xs[THRL_MAX_AGENTS], Aq[THRL_MAX_AGENTS], rew[THRL_MAX_AGENTS];
+  double* old_value = NULL;
+  int64_t *st_row = NULL, *ns_row = NULL;
+  int maxcap = 1;
+  for (int i = 0; i < n; ++i) if (G->agent[i].capacity > maxcap) maxcap = G->agent[i].capacity;
+  old_value = (double*)malloc(sizeof(double) * (size_t)maxcap);
+  st_row = (int64_t*)malloc(sizeof(int64_t) * (size_t)maxcap);
+  ns_row = (int64_t*)malloc(sizeof(int64_t) * (size_t)maxcap);
+
+  for (int e = 0; e < E && rc == 0; ++e) {
+    const int eabs = A->epoch_begin + e;
+    double rlog[THRL_MAX_AGENTS], alog[THRL_MAX_AGENTS];
+    for (int i = 0; i < n; ++i) rlog[i] = alog[i] = 0.0; /* trainer.py:40-41 zeros */
+    for (int t = 0; t < T && rc == 0; ++t) { /* trainer.py:50 while not done (episode counts to max_steps) */
+      const size_t sidx = ((size_t)r * E + e) * T + t;
+      /* trainer.py:52-55, agent order 0..n-1; agents.py:80-89 */
+      for (int i = 0; i < n; ++i) {
+        const ThrlAgentSpec* s = &G->agent[i];
+        int k;
+        if (A->rng_mode == THRL_RNG_REPLAY_ACTIONS) {
+          k = A->replay_ra[sidx * n + i];
+        } else {
+          double u;
+          int ra;
+          if (A->rng_mode == THRL_RNG_REPLAY_DRAWS) {
+            u = A->replay_u[sidx * n + i];
+            ra = A->replay_ra[sidx * n + i];
+          } else {
+            uint32_t x[4];
+            philox4x32_10((uint32_t)gid, (uint32_t)eabs, (uint32_t)t, (uint32_t)i | (STREAM_ACT << 16), k0, k1, x);
+            u = u53(x[0], x[1]);
+            ra = (int)(((uint64_t)x[2] * (uint64_t)s->actions) >> 32);
+          }
+          if (u < eps[i]) {
+            k = ra;
+          } else {
+            int64_t row = act_row(price, s);
+            if (row < 0 || row > s->states) { rc = -1; break; }
+            k = row_argmax(&tab[i], row);
+          }
+        }
+        if (k < 0 || k >= s->actions) { rc = -1; break; }
+        act[i] = k;
+        xs[i] = scale_action(k, s); /* trainer.py:56 */
+      }
+      if (rc) break;
+      /* environments.py:25-39 */
+      const double ab = G->a / G->b;
+      double Q = 0.0;
+      for (int i = 0; i < n; ++i) { Aq[i] = ab * xs[i]; Q = Q + Aq[i]; }
+      double new_a;
+      if (A->rng_mode == THRL_RNG_PHILOX) {
+        new_a = G->a;
+        if (G->noise_prob > 0.0) {
+          uint32_t x[4];
+          philox4x32_10((uint32_t)gid, (uint32_t)eabs, (uint32_t)t, (uint32_t)(STREAM_ENV << 16), k0, k1, x);
+          double un = u53(x[0], x[1]);
+          if (un < G->noise_prob) {
+            double lo = G->a * 0.7;
+            new_a = lo + (G->a - lo) * u53(x[2], x[3]); /* numpy uniform(low, high) = low + (high-low)*U */
+          }
+        }
+      } else {
+        new_a = A->replay_new_a ? A->replay_new_a[sidx] : G->a;
+      }
+      double pn = new_a - G->b * Q;
+      double next_price = pn > 0.0 ? pn : 0.0; /* numpy.max([0, x]) */
+      if (pn != pn) next_price = pn;           /* NaN propagates through numpy.max */
+      for (int i = 0; i < n; ++i) rew[i] = next_price * Aq[i];
+      /* trainer.py:61-62 */
+      for (int i = 0; i < n; ++i) {
+        Transition tr = {price, rew[i], next_price, act[i]};
+        buf_append(&buf[i], tr);
+      }
+      /* trainer.py:65-66: divide, then add */
+      for (int i = 0; i < n; ++i) {
+        rlog[i] += rew[i] / (double)T;
+        alog[i] += xs[i] / (double)T;
+      }
+      if (A->trace_actions) for (int i = 0; i < n; ++i) A->trace_actions[sidx * n + i] = act[i];
+      if (A->trace_rewards) for (int i = 0; i < n; ++i) A->trace_rewards[sidx * n + i] = rew[i];
+      if (A->trace_prices) A->trace_prices[sidx] = next_price;
+      price = next_price; /* trainer.py:67 */
+    }
+    if (rc) break;
+    /* trainer.py:70, agents.py:59-78 */
+    for (int i = 0; i < n && rc == 0; ++i) {
+      const ThrlAgentSpec* s = &G->agent[i];
+      Buffer* b = &buf[i];
+      if (b->len >= s->min_memory) {
+        const int L = b->len;
+        for (int j = 0; j < L; ++j) { /* :62,:66 encodes, :67 snapshot */
+          const Transition* tr = &b->item[(b->head + j) % b->cap];
+          st_row[j] = upd_row(tr->state, s);
+          ns_row[j] = upd_row(tr->new_state, s);
+          if (st_row[j] < 0 || st_row[j] > s->states || ns_row[j] < 0 || ns_row[j] > s->states) { rc = -1; break; }
+          old_value[j] = tget(&tab[i], st_row[j], tr->action);
+        }
+        if (rc) break;
+        uint32_t* cnt = A->counter ? A->counter + (size_t)r * G->run_stride + s->table_offset : NULL;
+        for (int j = 0; j < L; ++j) { /* :68-76 */
+          const Transition* tr = &b->item[(b->head + j) % b->cap];
+          double next_max = row_max(&tab[i], ns_row[j]);
+          double new_value = (1.0 - alpha[i]) * old_value[j] + alpha[i] * (tr->reward + gamma[i] * next_max);
+          tset(&tab[i], st_row[j], tr->action, new_value);
+          if (cnt) cnt[st_row[j] * s->actions + tr->action] += 1;
+        }
+        b->len = 0; b->head = 0; /* :77 */
+      }
+      eps[i] = eps_end[i] + (eps[i] - eps_end[i]) * eps_step[i]; /* :78, every epoch */
+    }
+    if (rc) break;
+    if (r < A->n_log_runs) {
+      for (int i = 0; i < n; ++i) {
+        if (A->rewards_log) A->rewards_log[((size_t)r * E + e) * n + i] = rlog[i];
+        if (A->actions_log) A->actions_log[((size_t)r * E + e) * n + i] = alog[i];
+      }
+    }
+    if (A->stats) {
+      for (int i = 0; i < n; ++i) {
+        int64_t* s4 = A->stats + ((size_t)e * n + i) * THRL_STATS_K;
+        int64_t v0 = fx_round(rlog[i] * THRL_STATS_SCALE_SUM), v1 = fx_round(rlog[i] * rlog[i] * THRL_STATS_SCALE_SQ);
+        int64_t v2 = fx_round(alog[i] * THRL_STATS_SCALE_SUM), v3 = fx_round(alog[i] * alog[i] * THRL_STATS_SCALE_SQ);
+        __atomic_fetch_add(&s4[0], v0, __ATOMIC_RELAXED); /* integer sums: exact in any order */
+        __atomic_fetch_add(&s4[1], v1, __ATOMIC_RELAXED);
+        __atomic_fetch_add(&s4[2], v2, __ATOMIC_RELAXED);
+        __atomic_fetch_add(&s4[3], v3, __ATOMIC_RELAXED);
+      }
+    }
+  }
+  A->price[r] = price;
+  for (int i = 0; i < n; ++i) free(buf[i].item);
+  free(old_value); free(st_row); free(ns_row);
+  return rc;
+}
+
+typedef struct Worker {
+  const ThrlScanArgs* args;
+  int64_t* next; /* shared run cursor */
+  int bad;
+} Worker;
+static void* worker_main(void* p) {
+  Worker* w = (Worker*)p;
+  for (;;) {
+    int64_t r0 = __atomic_fetch_add(w->next, 16, __ATOMIC_RELAXED);
+    if (r0 >= w->args->n_runs) break;
+    int64_t r1 = r0 + 16 < w->args->n_runs ? r0 + 16 : w->args->n_runs;
+    for (int64_t r = r0; r < r1; ++r) w->bad |= scan_run(w->args, r) != 0;
+  }
+  return NULL;
+}
+
+/* Same meaning as thrl_qtable_scan (include/thrl.h) on HOST pointers.  Buffers start empty (args->ring is ignored),
+ * so call it once over the whole epoch range.  Runs are independent, so they are spread over n_threads pthreads
+ * (n_threads <= 0: one per online core).  Returns 0 / THRL_ERR_BAD_CONFIG. */
+int thrl_oracle_qtable_scan(const ThrlScanArgs* args, int n_threads) {
+  if (n_threads <= 0) n_threads = (int)sysconf(_SC_NPROCESSORS_ONLN);
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  if ((int64_t)n_threads > args->n_runs) n_threads = (int)(args->n_runs > 0 ? args->n_runs : 1);
+  int64_t next = 0;
+  Worker w[256];
+  pthread_t th[256];
+  for (int i = 0; i < n_threads; ++i) { w[i].args = args; w[i].next = &next; w[i].bad = 0; }
+  for (int i = 1; i < n_threads; ++i) pthread_create(&th[i], NULL, worker_main, &w[i]);
+  worker_main(&w[0]);
+  int bad = w[0].bad;
+  for (int i = 1; i < n_threads; ++i) { pthread_join(th[i], NULL); bad |= w[i].bad; }
+  return bad ? THRL_ERR_BAD_CONFIG : THRL_OK;
+}
+int thrl_oracle_online_cores(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }
+
+/* DESIGN.md "Device init": q = 12.5/(1-gamma) + N(0,1) (agents.py:29), counter = 0 (agents.py:45),
+ * price ~ U(0,a) (environments.py:15-16), eps = eps0. */
+int thrl_oracle_qtable_init(const ThrlGame* G, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
+                            const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps,
+                            double* price) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const int n = G->n_agents;
+  for (int64_t r = 0; r < n_runs; ++r) {
+    const uint64_t gid = (uint64_t)(run_id0 + r);
+    for (int i = 0; i < n; ++i) {
+      const ThrlAgentSpec* s = &G->agent[i];
+      const double gamma = hp ? hp[((size_t)r * n + i) * 4 + 1] : s->gamma;
+      const double base = 12.5 / (1.0 - gamma);
+      const int64_t cells = (int64_t)(s->states + 1) * s->actions;
+      for (int64_t c = 0; c < cells; c += 2) { /* one Philox call -> two normals */
+        uint32_t x[4];
+        philox4x32_10((uint32_t)gid, (uint32_t)(c >> 1), (uint32_t)i, (uint32_t)(STREAM_INIT_Q << 16), k0, k1, x);
+        for (int h = 0; h < 2 && c + h < cells; ++h) {
+          /* (m + 0.5) * 2^-53 lies strictly inside (0,1) */
+          uint64_t m = ((uint64_t)x[2 * h] << 21) | (x[2 * h + 1] >> 11);
+          double p = ((double)m + 0.5) * (1.0 / 9007199254740992.0);
+          double v = base + det_norminv(p);
+          size_t idx = (size_t)r * G->run_stride + s->table_offset + (size_t)(c + h);
+          if (table_dtype == THRL_F64) ((double*)q)[idx] = v;
+          else ((float*)q)[idx] = (float)v;
+          if (counter) counter[idx] = 0;
+        }
+      }
+      eps[(size_t)r * n + i] = eps0[i];
+    }
+    uint32_t x[4];
+    philox4x32_10((uint32_t)gid, 0, 0, (uint32_t)(STREAM_INIT_P << 16), k0, k1, x);
+    price[r] = 0.0 + (G->a - 0.0) * u53(x[0], x[1]);
+  }
+  return THRL_OK;
+}
+
+/* utils.py:27-47 play_game with agents.py:91-92 get_action (float64 encode of the state, no exploration,
+ * no update).  price0[r][it] replaces environment.reset()'s draw.  rewards/actions: [R][iters*T][n]. */
+int thrl_oracle_greedy_eval(const ThrlGame* G, int64_t n_runs, int32_t table_dtype, const void* q, int32_t iters,
+                            const double* price0, double* rewards, double* actions) {
+  const int n = G->n_agents, T = G->max_steps;
+  const size_t esz = table_dtype == THRL_F64 ? 8 : 4;
+  for (int64_t r = 0; r < n_runs; ++r) {
+    for (int it = 0; it < iters; ++it) {
+      double price = price0[(size_t)r * iters + it];
+      for (int t = 0; t < T; ++t) {
+        double xs[THRL_MAX_AGENTS], Aq[THRL_MAX_AGENTS];
+        const double ab = G->a / G->b;
+        double Q = 0.0;
+        for (int i = 0; i < n; ++i) {
+          const ThrlAgentSpec* s = &G->agent[i];
+          Table tb = {table_dtype, (char*)q + ((size_t)r * G->run_stride + s->table_offset) * esz, s->states + 1,
+                      s->actions};
+          int64_t row = upd_row(price, s);
+          if (row < 0 || row > s->states) return THRL_ERR_BAD_CONFIG;
+          xs[i] = scale_action(row_argmax(&tb, row), s);
+          Aq[i] = ab * xs[i];
+          Q = Q + Aq[i];
+        }
+        double pn = G->a - G->b * Q; /* deterministic demand: evaluation is defined for noise_prob == 0 */
+        double next_price = pn > 0.0 ? pn : 0.0;
+        size_t o = (((size_t)r * iters + it) * T + t) * n;
+        for (int i = 0; i < n; ++i) { rewards[o + i] = next_price * Aq[i]; actions[o + i] = xs[i]; }
+        price = next_price;
+      }
+    }
+  }
+  return THRL_OK;
+}
+
+/* Same checks / layout as thrl_game_layout in the product, restated so the oracle stands alone. */
+int thrl_oracle_game_layout(ThrlGame* G) {
+  if (G->n_agents < 1 || G->n_agents > THRL_MAX_AGENTS || G->max_steps < 1) return THRL_ERR_BAD_CONFIG;
+  int64_t off = 0;
+  int ring = 0, regular = 1;
+  for (int i = 0; i < G->n_agents; ++i) {
+    ThrlAgentSpec* s = &G->agent[i];
+    if (s->states < 1 || s->actions < 2 || s->actions > THRL_MAX_ACTIONS || s->capacity < 0 || s->min_memory < 0)
+      return THRL_ERR_BAD_CONFIG;
+    if (!(s->max_state > 0.0) || G->a > s->max_state) return THRL_ERR_BAD_CONFIG; /* row would exceed states: IndexError */
+    s->table_offset = off;
+    off += (int64_t)(s->states + 1) * s->actions;
+    if (s->min_memory <= s->capacity) { /* otherwise the update never fires and the buffer content is irrelevant */
+      int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
+      int64_t need = (int64_t)T * ((mm + T - 1) / T);
+      if (need > s->capacity) need = s->capacity;
+      if (need > ring) ring = (int)need;
+      if (s->min_memory > T) regular = 0;
+    }
+  }
+  G->run_stride = off;
+  G->ring_len = ring;
+  G->regular = regular;
+  return THRL_OK;
+}

@@ -1,0 +1,70 @@
+"""The oracle (oracle/thrl_oracle.c) against streams recorded from the unmodified reference.
+
+Every quantity the hot path produces must be BIT-EXACT in the reference's own dtype (f64 tables):
+chosen actions, rewards, prices, final tables, visit counters, epsilon and both per-epoch logs.
+"""
+import numpy as np
+
+from oracle import oracle
+from th_rl_b200 import abi
+
+
+def run_oracle(g, rng_mode, dtype=np.float64):
+    cfg = g["config"]
+    game = oracle.layout(cfg)
+    n = game.n_agents
+    q0 = oracle.pack_tables(game, [g["q0_%d" % i] for i in range(n)], dtype)
+    E = g["u"].shape[0]
+    ra = g["ra"] if rng_mode == abi.THRL_RNG_REPLAY_DRAWS else g["actions"]
+    noisy = cfg["environment"].get("noise_prob", 0.05) > 0
+    return game, oracle.scan(game, q0, [abi.eps0_from_config(cfg)], [g["p0"]], E, rng_mode=rng_mode,
+                             replay_u=g["u"][None], replay_ra=ra[None],
+                             replay_new_a=g["new_a"][None] if noisy else None, trace=True, stats=True)
+
+
+def check_bit_exact(g, game, res):
+    n = game.n_agents
+    assert np.array_equal(res.trace_actions[0], g["actions"])
+    assert np.array_equal(res.trace_rewards[0], g["rewards"])
+    assert np.array_equal(res.trace_prices[0], g["prices"])
+    tabs = oracle.unpack_tables(game, res.q)
+    cnts = oracle.unpack_tables(game, res.counter)
+    for i in range(n):
+        assert np.array_equal(tabs[i][0], g["q_final_%d" % i]), "table of agent %d" % i
+        assert np.array_equal(cnts[i][0].astype(np.float64), g["counter_final_%d" % i])
+    assert np.array_equal(res.eps[0], g["eps_trace"][-1])
+    # log.csv round-trips through repr(float) -> exact
+    assert np.array_equal(res.rewards_log[0], g["rewards_log"])
+    assert np.array_equal(res.actions_log[0], g["actions_log"])
+    assert res.price[0] == g["prices"][-1, -1]
+
+
+def test_replay_draws_f64_bit_exact(golden):
+    """Exploration draws replayed, greedy actions chosen by the oracle: everything equals the reference."""
+    game, res = run_oracle(golden, abi.THRL_RNG_REPLAY_DRAWS)
+    check_bit_exact(golden, game, res)
+
+
+def test_replay_actions_f64_bit_exact(golden):
+    game, res = run_oracle(golden, abi.THRL_RNG_REPLAY_ACTIONS)
+    check_bit_exact(golden, game, res)
+
+
+def test_replay_actions_f32_storage_tolerance(golden):
+    """fp32 storage + f64 update arithmetic under teacher forcing: rewards/prices exact, Q within 1e-6 relative."""
+    game, res = run_oracle(golden, abi.THRL_RNG_REPLAY_ACTIONS, dtype=np.float32)
+    assert np.array_equal(res.trace_rewards[0], golden["rewards"])
+    assert np.array_equal(res.trace_prices[0], golden["prices"])
+    tabs = oracle.unpack_tables(game, res.q)
+    for i in range(game.n_agents):
+        ref = golden["q_final_%d" % i]
+        rel = np.max(np.abs(tabs[i][0].astype(np.float64) - ref) / np.abs(ref))
+        assert rel < 1e-6, rel
+
+
+def test_stats_are_fixed_point_sums(golden):
+    game, res = run_oracle(golden, abi.THRL_RNG_REPLAY_ACTIONS)
+    want = np.rint(res.rewards_log[0] * abi.THRL_STATS_SCALE_SUM).astype(np.int64)
+    assert np.array_equal(res.stats[:, :, 0], want)
+    want = np.rint(res.actions_log[0] ** 2 * abi.THRL_STATS_SCALE_SQ).astype(np.int64)
+    assert np.array_equal(res.stats[:, :, 3], want)

@@ -1,0 +1,141 @@
+"""ctypes mirror of include/thrl.h (the C ABI of the hot path) plus config -> ThrlGame translation.
+
+Nothing here computes anything: it only describes memory layouts.  Field names, order and defaults follow
+include/thrl.h, which in turn cites the reference lines each field comes from
+(QTable.__init__ th_rl/agents.py:13-27, NoisyPriceState.__init__ th_rl/environments.py:5-13).
+"""
+import ctypes as C
+
+THRL_ABI_VERSION = 1
+THRL_MAX_AGENTS = 16
+THRL_MAX_ACTIONS = 256
+THRL_STATS_K = 4
+THRL_STATS_SCALE_SUM = 4294967296.0
+THRL_STATS_SCALE_SQ = 16777216.0
+
+THRL_OK = 0
+THRL_ERR_BAD_CONFIG = -1
+THRL_ERR_BAD_ARGS = -2
+THRL_ERR_UNSUPPORTED = -3
+THRL_ERR_CUDA = -4
+THRL_ERR_NO_DEVICE = -5
+
+THRL_F32 = 0
+THRL_F64 = 1
+
+THRL_RNG_PHILOX = 0
+THRL_RNG_REPLAY_DRAWS = 1
+THRL_RNG_REPLAY_ACTIONS = 2
+
+
+class ThrlAgentSpec(C.Structure):
+    _fields_ = [
+        ("states", C.c_int32),
+        ("actions", C.c_int32),
+        ("min_memory", C.c_int32),
+        ("capacity", C.c_int32),
+        ("action_lo", C.c_double),
+        ("action_hi", C.c_double),
+        ("max_state", C.c_double),
+        ("gamma", C.c_double),
+        ("alpha", C.c_double),
+        ("eps_end", C.c_double),
+        ("eps_step", C.c_double),
+        ("table_offset", C.c_int64),
+    ]
+
+
+class ThrlGame(C.Structure):
+    _fields_ = [
+        ("n_agents", C.c_int32),
+        ("max_steps", C.c_int32),
+        ("a", C.c_double),
+        ("b", C.c_double),
+        ("noise_prob", C.c_double),
+        ("agent", ThrlAgentSpec * THRL_MAX_AGENTS),
+        ("run_stride", C.c_int64),
+        ("ring_len", C.c_int32),
+        ("regular", C.c_int32),
+    ]
+
+
+class ThrlScanArgs(C.Structure):
+    _fields_ = [
+        ("game", C.POINTER(ThrlGame)),
+        ("n_runs", C.c_int64),
+        ("run_id0", C.c_int64),
+        ("epoch_begin", C.c_int32),
+        ("epoch_end", C.c_int32),
+        ("table_dtype", C.c_int32),
+        ("rng_mode", C.c_int32),
+        ("seed", C.c_uint64),
+        ("q", C.c_void_p),
+        ("counter", C.c_void_p),
+        ("eps", C.c_void_p),
+        ("price", C.c_void_p),
+        ("hp", C.c_void_p),
+        ("ring", C.c_void_p),
+        ("replay_u", C.c_void_p),
+        ("replay_ra", C.c_void_p),
+        ("replay_new_a", C.c_void_p),
+        ("rewards_log", C.c_void_p),
+        ("actions_log", C.c_void_p),
+        ("n_log_runs", C.c_int64),
+        ("stats", C.c_void_p),
+        ("trace_actions", C.c_void_p),
+        ("trace_rewards", C.c_void_p),
+        ("trace_prices", C.c_void_p),
+    ]
+
+
+# QTable.__init__ defaults (th_rl/agents.py:13-27)
+QTABLE_DEFAULTS = dict(states=16, actions=4, action_range=[0, 1], gamma=0.99, buffer="ReplayBuffer", capacity=500,
+                       max_state=10, alpha=0.1, eps_end=2e-2, epsilon=0.5, eps_step=5e-4, min_memory=100)
+# NoisyPriceState.__init__ defaults (th_rl/environments.py:5)
+ENV_DEFAULTS = dict(action_range=[0, 1], a=10, b=1, max_steps=1, noise_prob=0.05)
+
+
+def game_from_config(config):
+    """Translate the reference's JSON schema (th_rl/some_path/configs/example_config.json) into a ThrlGame.
+
+    Only QTable agents are on this path; unknown keys are ignored exactly as the reference's **kwargs does
+    (agents.py:27, environments.py:5).  table_offset / run_stride / ring_len / regular are left for
+    thrl_game_layout to fill.
+    """
+    agents = config["agents"]
+    env = dict(ENV_DEFAULTS)
+    env.update(config["environment"])
+    # trainer.py:21-23
+    assert len(agents) == env["nplayers"], "Bad config. Check number of agents."
+    if len(agents) > THRL_MAX_AGENTS:
+        raise ValueError("at most %d agents per game" % THRL_MAX_AGENTS)
+    g = ThrlGame()
+    g.n_agents = len(agents)
+    g.max_steps = int(env["max_steps"])
+    g.a = float(env["a"])
+    g.b = float(env["b"])
+    g.noise_prob = float(env["noise_prob"])
+    for i, ad in enumerate(agents):
+        if ad.get("name", "QTable") != "QTable":
+            raise NotImplementedError(
+                "agent %d is %r: only QTable agents are on the B200 hot path (DESIGN.md, out of scope: MLP agents)"
+                % (i, ad.get("name")))
+        d = dict(QTABLE_DEFAULTS)
+        d.update(ad)
+        s = g.agent[i]
+        s.states = int(d["states"])
+        s.actions = int(d["actions"])
+        s.min_memory = int(d["min_memory"])
+        s.capacity = int(d["capacity"])
+        s.action_lo = float(d["action_range"][0])
+        s.action_hi = float(d["action_range"][1])
+        s.max_state = float(d["max_state"])
+        s.gamma = float(d["gamma"])
+        s.alpha = float(d["alpha"])
+        s.eps_end = float(d["eps_end"])
+        s.eps_step = float(d["eps_step"])
+    return g
+
+
+def eps0_from_config(config):
+    return [float(dict(QTABLE_DEFAULTS, **ad)["epsilon"]) for ad in config["agents"]]

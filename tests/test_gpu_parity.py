@@ -1,0 +1,213 @@
+"""CUDA path (through the C ABI) against the golden streams of the reference and against the oracle.
+
+Bars: bit-exact for actions, rewards, prices, counters, epsilon, logs and f64 tables; fp32-storage tables within
+1e-6 relative of the reference's f64 tables under teacher forcing, and bit-exact against the oracle's fp32 mode.
+"""
+import numpy as np
+import pytest
+
+from th_rl_b200 import abi
+
+pytestmark = pytest.mark.gpu
+
+
+def _mods():
+    import torch
+    from oracle import oracle
+    from th_rl_b200 import engine
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch, oracle, engine
+
+
+def _cuda_replay(g, rng_mode, dtype):
+    torch, oracle, engine = _mods()
+    cfg = g["config"]
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    b = engine.RunBatch(cfg, 1, dtype=tdt)
+    n = b.game.n_agents
+    q0 = oracle.pack_tables(b.game, [g["q0_%d" % i] for i in range(n)], dtype)
+    b.load_state(q0, [abi.eps0_from_config(cfg)], [g["p0"]])
+    E = g["u"].shape[0]
+    ra = g["ra"] if rng_mode == abi.THRL_RNG_REPLAY_DRAWS else g["actions"]
+    noisy = cfg["environment"].get("noise_prob", 0.05) > 0
+    out = b.scan(E, rng_mode=rng_mode, replay_u=g["u"][None], replay_ra=ra[None],
+                 replay_new_a=g["new_a"][None] if noisy else None, n_log_runs=1, stats=True, trace=True)
+    torch.cuda.synchronize()
+    return b, out
+
+
+def _check_vs_golden(g, b, out, exact_tables=True):
+    n = b.game.n_agents
+    assert np.array_equal(out.trace_actions[0].cpu().numpy(), g["actions"])
+    assert np.array_equal(out.trace_rewards[0].cpu().numpy(), g["rewards"])
+    assert np.array_equal(out.trace_prices[0].cpu().numpy(), g["prices"])
+    tabs, cnts = b.tables(), b.counters()
+    for i in range(n):
+        got = tabs[i][0].cpu().numpy().astype(np.float64)
+        ref = g["q_final_%d" % i]
+        if exact_tables:
+            assert np.array_equal(got, ref), "table of agent %d" % i
+        else:
+            rel = np.max(np.abs(got - ref) / np.abs(ref))
+            assert rel < 1e-6, rel  # fp32 storage tolerance stated in BASELINE.json north_star
+        assert np.array_equal(cnts[i][0].cpu().numpy().astype(np.float64), g["counter_final_%d" % i])
+    assert np.array_equal(b.eps[0].cpu().numpy(), g["eps_trace"][-1])
+    assert np.array_equal(out.rewards_log[0].cpu().numpy(), g["rewards_log"])
+    assert np.array_equal(out.actions_log[0].cpu().numpy(), g["actions_log"])
+    assert b.price[0].item() == g["prices"][-1, -1]
+
+
+def test_replay_draws_f64_matches_reference(golden):
+    """Recorded exploration draws replayed, greedy actions chosen on the GPU: every output equals the reference."""
+    b, out = _cuda_replay(golden, abi.THRL_RNG_REPLAY_DRAWS, np.float64)
+    _check_vs_golden(golden, b, out)
+
+
+def test_replay_actions_f64_matches_reference(golden):
+    b, out = _cuda_replay(golden, abi.THRL_RNG_REPLAY_ACTIONS, np.float64)
+    _check_vs_golden(golden, b, out)
+
+
+def test_replay_actions_f32_within_tolerance(golden):
+    b, out = _cuda_replay(golden, abi.THRL_RNG_REPLAY_ACTIONS, np.float32)
+    _check_vs_golden(golden, b, out, exact_tables=False)
+
+
+def _sweep_hp(rng, R, n):
+    hp = np.empty((R, n, 4))
+    hp[..., 0] = rng.choice([0.05, 0.1, 0.2, 0.5], size=(R, n))
+    hp[..., 1] = rng.choice([0.35, 0.8, 0.95, 0.99], size=(R, n))
+    hp[..., 2] = 0.001
+    hp[..., 3] = rng.choice([0.9, 0.999, 0.9995], size=(R, n))
+    return hp
+
+
+def _philox_case(cfg, R, E, dtype, seed, run_id0=0, hp=False, chunks=None):
+    torch, oracle, engine = _mods()
+    game = oracle.layout(cfg)
+    n = game.n_agents
+    rng = np.random.default_rng(seed)
+    hpa = _sweep_hp(rng, R, n) if hp else None
+    q0, c0, eps0, p0 = oracle.init(game, R, seed=seed, run_id0=run_id0, dtype=dtype, hp=hpa,
+                                   eps0=abi.eps0_from_config(cfg))
+    ref = oracle.scan(game, q0, eps0, p0, E, hp=hpa, seed=seed, run_id0=run_id0, stats=True, trace=True, n_threads=0)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    b = engine.RunBatch(cfg, R, dtype=tdt, seed=seed, run_id0=run_id0, hp=hpa)
+    b.load_state(q0, eps0, p0)
+    outs = [b.scan(e, n_log_runs=R, stats=True, trace=True) for e in (chunks or [E])]
+    torch.cuda.synchronize()
+    cat = lambda f, ax: np.concatenate([getattr(o, f).cpu().numpy() for o in outs], axis=ax)
+    assert np.array_equal(cat("trace_actions", 1), ref.trace_actions)
+    assert np.array_equal(cat("trace_prices", 1), ref.trace_prices)
+    assert np.array_equal(cat("trace_rewards", 1), ref.trace_rewards)
+    assert np.array_equal(b.q.cpu().numpy(), ref.q)
+    assert np.array_equal(b.counter.cpu().numpy().view(np.uint32), ref.counter)
+    assert np.array_equal(b.eps.cpu().numpy(), ref.eps)
+    assert np.array_equal(b.price.cpu().numpy(), ref.price)
+    assert np.array_equal(cat("rewards_log", 1), ref.rewards_log)
+    assert np.array_equal(cat("actions_log", 1), ref.actions_log)
+    assert np.array_equal(cat("stats", 0), ref.stats)
+    return b, ref
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_philox_free_running_matches_oracle(golden, dtype):
+    """Free-running Philox mode, many runs, per-run hyper-parameters: bit-exact against the oracle in both dtypes."""
+    E = 6 if golden["config"]["environment"]["nplayers"] > 2 else 10
+    _philox_case(golden["config"], 96, E, dtype, seed=1234, run_id0=7, hp=True)
+
+
+def test_chunked_scan_equals_single_call(golden):
+    """Splitting the epoch range over several calls (state and pending transitions carried on the device) changes nothing."""
+    _philox_case(golden["config"], 40, 9, np.float32, seed=5, chunks=[1, 3, 5])
+
+
+def test_host_buffer_entry_point(golden):
+    """thrl_qtable_scan_host (host buffers, copies inside the call) == oracle."""
+    torch, oracle, engine = _mods()
+    cfg = golden["config"]
+    game = oracle.layout(cfg)
+    q0, c0, eps0, p0 = oracle.init(game, 33, seed=9, dtype=np.float32, eps0=abi.eps0_from_config(cfg))
+    ref = oracle.scan(game, q0, eps0, p0, 5, seed=9, stats=True)
+    q, eps, p, cnt = q0.copy(), eps0.copy(), p0.copy(), c0.copy()
+    out = engine.scan_host(cfg, q, eps, p, 5, counter=cnt, seed=9, n_log_runs=33, stats=True)
+    assert np.array_equal(q, ref.q) and np.array_equal(cnt, ref.counter)
+    assert np.array_equal(eps, ref.eps) and np.array_equal(p, ref.price)
+    assert np.array_equal(out.rewards_log, ref.rewards_log) and np.array_equal(out.stats, ref.stats)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_device_init_matches_oracle(golden, dtype):
+    torch, oracle, engine = _mods()
+    cfg = golden["config"]
+    game = oracle.layout(cfg)
+    q0, c0, eps0, p0 = oracle.init(game, 50, seed=77, run_id0=1000, dtype=dtype, eps0=abi.eps0_from_config(cfg))
+    b = engine.RunBatch(cfg, 50, dtype=torch.float64 if dtype == np.float64 else torch.float32, seed=77, run_id0=1000)
+    b.init_device()
+    torch.cuda.synchronize()
+    assert np.array_equal(b.q.cpu().numpy(), q0)
+    assert np.array_equal(b.eps.cpu().numpy(), eps0) and np.array_equal(b.price.cpu().numpy(), p0)
+    # agents.py:29: 12.5/(1-gamma) + N(0,1)
+    z = b.tables()[0].cpu().numpy().astype(np.float64) - 12.5 / (1 - game.agent[0].gamma)
+    assert abs(z.mean()) < 0.05 and abs(z.std() - 1.0) < 0.05
+
+
+def test_greedy_eval_matches_oracle(golden):
+    torch, oracle, engine = _mods()
+    cfg = golden["config"]
+    game = oracle.layout(cfg)
+    q0, c0, eps0, p0 = oracle.init(game, 20, seed=3, dtype=np.float64, eps0=abi.eps0_from_config(cfg))
+    price0 = np.random.default_rng(0).uniform(0, game.a, size=(20, 3))
+    ref_a, ref_r = oracle.greedy_eval(game, q0, price0)
+    b = engine.RunBatch(cfg, 20, dtype=torch.float64)
+    b.load_state(q0, eps0, p0)
+    a, r = b.greedy_eval(price0)
+    torch.cuda.synchronize()
+    assert np.array_equal(a.cpu().numpy(), ref_a) and np.array_equal(r.cpu().numpy(), ref_r)
+
+
+def test_sharding_is_invisible():
+    """Philox counters use global run ids: runs [0,R) in one call == the same runs split over two 'ranks'."""
+    torch, oracle, engine = _mods()
+    from conftest import load_golden
+    cfg = load_golden("c1_example_2q_seed0")["config"]
+    R, E = 64, 5
+    whole = engine.RunBatch(cfg, R, seed=11).init_device()
+    ow = whole.scan(E, stats=True)
+    parts = [engine.RunBatch(cfg, R // 2, seed=11, run_id0=k * (R // 2)).init_device() for k in range(2)]
+    op = [p.scan(E, stats=True) for p in parts]
+    torch.cuda.synchronize()
+    assert torch.equal(whole.q, torch.cat([p.q for p in parts]))
+    assert torch.equal(whole.counter, torch.cat([p.counter for p in parts]))
+    assert torch.equal(ow.stats, op[0].stats + op[1].stats)  # what the NCCL all-reduce computes
+
+
+def test_full_size_properties():
+    """BASELINE C2 at full size (65,536 runs): size-independent invariants + run-to-run determinism."""
+    torch, oracle, engine = _mods()
+    from conftest import load_golden
+    cfg = load_golden("c1_example_2q_seed0")["config"]
+    R, E, T = 65536, 4, 100
+    outs = []
+    for rep in range(2):
+        b = engine.RunBatch(cfg, R, seed=2).init_device()
+        o = b.scan(E, n_log_runs=R, stats=True)
+        torch.cuda.synchronize()
+        outs.append((b, o))
+    (b, o), (b2, o2) = outs
+    assert torch.equal(b.q, b2.q) and torch.equal(b.counter, b2.counter) and torch.equal(o.stats, o2.stats)
+    for c in b.counters():  # every transition is counted exactly once (agents.py:76)
+        assert torch.all(c.reshape(R, -1).sum(1) == E * T)
+    e = 0.5
+    for _ in range(E):
+        e = 0.001 + (e - 0.001) * 0.9995
+    assert torch.all(b.eps == e)
+    want = torch.round(o.rewards_log * abi.THRL_STATS_SCALE_SUM).to(torch.int64).sum(0)
+    assert torch.equal(o.stats[:, :, 0], want)
+    # a sample of the full-size batch against the oracle
+    game = oracle.layout(cfg)
+    idx = np.arange(0, R, 4099)
+    q0, c0, eps0, p0 = oracle.init(game, R, seed=2, dtype=np.float32, eps0=abi.eps0_from_config(cfg))
+    for r in idx:
+        ref = oracle.scan(game, q0[r:r + 1], eps0[r:r + 1], p0[r:r + 1], E, seed=2, run_id0=int(r))
+        assert np.array_equal(b.q[r].cpu().numpy(), ref.q[0])

@@ -1,0 +1,336 @@
+// thrl.cu — C ABI (include/thrl.h) of the B200-native th_rl hot path: validation, shared-memory layout, launches.
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a --fmad=false -lineinfo (see th_rl_b200/build.py).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "thrl_device.cuh"
+#include "thrl_scan_generic.cuh"
+#include "thrl_aux_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) return fail(THRL_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(e_));     \
+  } while (0)
+
+inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+struct DeviceInfo {
+  int sms = 0, smem_optin = 0, cc_major = 0;
+};
+int device_info(DeviceInfo* d) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(THRL_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+  CUDA_TRY(cudaDeviceGetAttribute(&d->sms, cudaDevAttrMultiProcessorCount, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&d->cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (d->cc_major != 10) return fail(THRL_ERR_NO_DEVICE, "device is sm_%d0, this library is built for sm_100a only", d->cc_major);
+  return THRL_OK;
+}
+
+int validate_layout(ThrlGame* G) {
+  if (!G) return fail(THRL_ERR_BAD_ARGS, "game is NULL");
+  if (G->n_agents < 1 || G->n_agents > THRL_MAX_AGENTS)
+    return fail(THRL_ERR_BAD_CONFIG, "n_agents=%d outside 1..%d", G->n_agents, THRL_MAX_AGENTS);
+  if (G->max_steps < 1) return fail(THRL_ERR_BAD_CONFIG, "max_steps=%d", G->max_steps);
+  if (!(G->b == G->b) || G->b == 0.0) return fail(THRL_ERR_BAD_CONFIG, "b must be non-zero");
+  long long off = 0;
+  int ring = 0, regular = 1;
+  for (int i = 0; i < G->n_agents; ++i) {
+    ThrlAgentSpec* s = &G->agent[i];
+    if (s->states < 1 || s->states > 65534) return fail(THRL_ERR_BAD_CONFIG, "agent %d: states=%d outside 1..65534", i, s->states);
+    if (s->actions < 2 || s->actions > THRL_MAX_ACTIONS)
+      return fail(THRL_ERR_BAD_CONFIG, "agent %d: actions=%d outside 2..%d", i, s->actions, THRL_MAX_ACTIONS);
+    if (s->capacity < 0 || s->min_memory < 0) return fail(THRL_ERR_BAD_CONFIG, "agent %d: negative capacity/min_memory", i);
+    // the reference raises IndexError on the first encode whose row exceeds `states` (agents.py:88): price <= a
+    if (!(s->max_state > 0.0) || G->a > s->max_state)
+      return fail(THRL_ERR_BAD_CONFIG, "agent %d: a=%g > max_state=%g would index past the table (reference: IndexError)", i,
+                  G->a, s->max_state);
+    s->table_offset = off;
+    off += (long long)(s->states + 1) * s->actions;
+    if (s->min_memory <= s->capacity) {
+      const int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
+      long long need = (long long)T * ((mm + T - 1) / T);
+      if (need > s->capacity) need = s->capacity;
+      if (need > ring) ring = (int)need;
+      if (s->min_memory > T) regular = 0;
+    }
+  }
+  G->run_stride = off;
+  G->ring_len = ring;
+  G->regular = regular;
+  return THRL_OK;
+}
+
+long long ring_bytes(const ThrlGame* G) {
+  const long long Hp = (G->ring_len > 0 ? G->ring_len : 1) + 1;
+  long long b = (long long)sizeof(thrl::RingHeader) + Hp * 8 + (long long)G->n_agents * Hp;
+  return (b + 15) / 16 * 16;
+}
+
+// Fills the shared-memory layout of ScanParams; returns bytes per warp slot.
+void plan_generic(thrl::ScanParams* p, bool smem_tables, size_t elem) {
+  const ThrlGame& G = p->game;
+  const int n = G.n_agents, T = G.max_steps, Hp = p->Hp;
+  int lut = 0, rows = 0;
+  for (int i = 0; i < n; ++i) { lut += G.agent[i].actions; rows += G.agent[i].states + 1; }
+  p->lut_total = lut;
+  p->rows_total = rows;
+  p->cta_bytes = align_up(3 * lut * 8, 16);
+  int o = 0;
+  p->off_tab = o;
+  if (smem_tables) o += align_up((int)(G.run_stride * (long long)elem), 16);
+  p->off_P = o;    o += align_up(Hp * 8, 16);
+  p->off_newa = o; o += p->noisy ? align_up(T * 8, 16) : 0;
+  p->off_hp = o;   o += align_up(n * 5 * 8, 16);
+  p->off_old = o;  o += align_up(Hp * (int)elem, 16);
+  p->off_pre = o;  o += align_up(T * n * 2, 16);
+  p->off_row = o;  o += align_up((Hp + 1) * 2, 16);
+  p->off_act = o;  o += align_up(n * Hp, 16);
+  p->off_g = o;    o += align_up(rows, 16);
+  p->warp_bytes = o;
+}
+
+template <typename T>
+int launch_generic(thrl::ScanParams& p, const DeviceInfo& dev, cudaStream_t stream) {
+  const ThrlGame& G = p.game;
+  const long long tab_bytes = G.run_stride * (long long)sizeof(T);
+  // Tables go to shared memory when at least 4 runs fit next to each other on an SM; otherwise they stay in HBM.
+  bool smem_tables = false;
+  if (tab_bytes < dev.smem_optin / 4) {
+    plan_generic(&p, true, sizeof(T));
+    smem_tables = (dev.smem_optin - p.cta_bytes) / p.warp_bytes >= 4;
+  }
+  if (!smem_tables) plan_generic(&p, false, sizeof(T));
+  int warps = (dev.smem_optin - p.cta_bytes) / p.warp_bytes;
+  if (warps < 1) return fail(THRL_ERR_UNSUPPORTED, "one run needs %d B of shared memory (> %d B)", p.warp_bytes + p.cta_bytes, dev.smem_optin);
+  if (warps > 32) warps = 32;
+  const long long needed_ctas = (p.n_runs + warps - 1) / warps;
+  int grid = dev.sms;
+  if (needed_ctas < grid) {  // few runs: spread them one warp-run per SM first
+    warps = (int)((p.n_runs + dev.sms - 1) / dev.sms);
+    if (warps < 1) warps = 1;
+    grid = (int)((p.n_runs + warps - 1) / warps);
+  }
+  const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
+  auto kern = smem_tables ? thrl::qtable_scan_generic<T, true> : thrl::qtable_scan_generic<T, false>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, warps * 32, smem, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return THRL_OK;
+}
+
+int check_args(const ThrlScanArgs* a) {
+  if (!a || !a->game) return fail(THRL_ERR_BAD_ARGS, "args/game is NULL");
+  if (a->n_runs < 0 || a->epoch_end < a->epoch_begin) return fail(THRL_ERR_BAD_ARGS, "negative run or epoch count");
+  if (a->table_dtype != THRL_F32 && a->table_dtype != THRL_F64) return fail(THRL_ERR_BAD_ARGS, "table_dtype=%d", a->table_dtype);
+  if (a->rng_mode < THRL_RNG_PHILOX || a->rng_mode > THRL_RNG_REPLAY_ACTIONS) return fail(THRL_ERR_BAD_ARGS, "rng_mode=%d", a->rng_mode);
+  if (!a->q || !a->eps || !a->price) return fail(THRL_ERR_BAD_ARGS, "q / eps / price must not be NULL");
+  if (a->rng_mode != THRL_RNG_PHILOX && !a->replay_ra) return fail(THRL_ERR_BAD_ARGS, "replay mode without replay_ra");
+  if (a->rng_mode == THRL_RNG_REPLAY_DRAWS && !a->replay_u) return fail(THRL_ERR_BAD_ARGS, "REPLAY_DRAWS without replay_u");
+  if (a->n_log_runs < 0 || a->n_log_runs > a->n_runs) return fail(THRL_ERR_BAD_ARGS, "n_log_runs=%lld outside 0..n_runs", (long long)a->n_log_runs);
+  return THRL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int thrl_abi_version(void) { return THRL_ABI_VERSION; }
+const char* thrl_last_error(void) { return g_err; }
+int64_t thrl_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int thrl_game_layout(ThrlGame* game) { return validate_layout(game); }
+
+int64_t thrl_ring_bytes(const ThrlGame* game) {
+  ThrlGame g = *game;
+  if (validate_layout(&g) != THRL_OK) return -1;
+  return ring_bytes(&g);
+}
+
+int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
+  int rc = check_args(a);
+  if (rc) return rc;
+  thrl::ScanParams p;
+  memset(&p, 0, sizeof(p));
+  p.game = *a->game;
+  rc = validate_layout(&p.game);
+  if (rc) return rc;
+  if (a->n_runs == 0 || a->epoch_end == a->epoch_begin) return THRL_OK;
+  DeviceInfo dev;
+  rc = device_info(&dev);
+  if (rc) return rc;
+  p.n_runs = a->n_runs;
+  p.run_id0 = a->run_id0;
+  p.epoch_begin = a->epoch_begin;
+  p.E = a->epoch_end - a->epoch_begin;
+  p.rng_mode = a->rng_mode;
+  p.k0 = (uint32_t)a->seed;
+  p.k1 = (uint32_t)(a->seed >> 32);
+  p.q = a->q; p.counter = a->counter; p.eps = a->eps; p.price = a->price; p.hp = a->hp;
+  p.ring = (unsigned char*)a->ring;
+  p.ring_bytes = ring_bytes(&p.game);
+  p.replay_u = a->replay_u; p.replay_ra = a->replay_ra; p.replay_new_a = a->replay_new_a;
+  p.rewards_log = a->rewards_log; p.actions_log = a->actions_log; p.n_log_runs = a->n_log_runs;
+  p.stats = (long long*)a->stats;
+  p.trace_actions = a->trace_actions; p.trace_rewards = a->trace_rewards; p.trace_prices = a->trace_prices;
+  p.Hp = (p.game.ring_len > 0 ? p.game.ring_len : 1) + 1;
+  p.noisy = (a->rng_mode == THRL_RNG_PHILOX) ? (p.game.noise_prob > 0.0) : (a->replay_new_a != nullptr);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  return a->table_dtype == THRL_F64 ? launch_generic<double>(p, dev, stream) : launch_generic<float>(p, dev, stream);
+}
+
+int thrl_qtable_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
+                     const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps, double* price,
+                     void* stream) {
+  if (!game || !eps0 || !q || !eps || !price) return fail(THRL_ERR_BAD_ARGS, "thrl_qtable_init: NULL argument");
+  if (table_dtype != THRL_F32 && table_dtype != THRL_F64) return fail(THRL_ERR_BAD_ARGS, "table_dtype=%d", table_dtype);
+  thrl::InitParams p;
+  memset(&p, 0, sizeof(p));
+  p.game = *game;
+  int rc = validate_layout(&p.game);
+  if (rc) return rc;
+  if (n_runs <= 0) return THRL_OK;
+  DeviceInfo dev;
+  rc = device_info(&dev);
+  if (rc) return rc;
+  p.n_runs = n_runs; p.run_id0 = run_id0;
+  p.k0 = (uint32_t)seed; p.k1 = (uint32_t)(seed >> 32);
+  p.f64 = table_dtype == THRL_F64;
+  p.hp = hp;
+  for (int i = 0; i < p.game.n_agents; ++i) p.eps0[i] = eps0[i];
+  p.q = q; p.counter = counter; p.eps = eps; p.price = price;
+  long long max_cells = 0;
+  for (int i = 0; i < p.game.n_agents; ++i) {
+    const long long c = (long long)(p.game.agent[i].states + 1) * p.game.agent[i].actions;
+    if (c > max_cells) max_cells = c;
+  }
+  dim3 grid((unsigned)((max_cells / 2 + 255) / 256), (unsigned)(n_runs < 65535 ? n_runs : 65535));
+  if (grid.x < 1) grid.x = 1;
+  if (grid.x > 64) grid.x = 64;
+  thrl::qtable_init<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return THRL_OK;
+}
+
+int thrl_greedy_eval(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, int32_t iters,
+                     const double* price0, double* rewards, double* actions, void* stream) {
+  if (!game || !q || !price0 || !rewards || !actions) return fail(THRL_ERR_BAD_ARGS, "thrl_greedy_eval: NULL argument");
+  if (table_dtype != THRL_F32 && table_dtype != THRL_F64) return fail(THRL_ERR_BAD_ARGS, "table_dtype=%d", table_dtype);
+  thrl::EvalParams p;
+  memset(&p, 0, sizeof(p));
+  p.game = *game;
+  int rc = validate_layout(&p.game);
+  if (rc) return rc;
+  if (n_runs <= 0 || iters <= 0) return THRL_OK;
+  DeviceInfo dev;
+  rc = device_info(&dev);
+  if (rc) return rc;
+  p.n_runs = n_runs; p.iters = iters; p.q = q; p.price0 = price0; p.rewards = rewards; p.actions = actions;
+  long long blocks = (n_runs + 7) / 8;
+  if (blocks > dev.sms * 8) blocks = dev.sms * 8;
+  if (table_dtype == THRL_F64) thrl::greedy_eval<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  else thrl::greedy_eval<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return THRL_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ host-buffer call
+namespace {
+struct DevBuf {
+  void* d = nullptr;
+  ~DevBuf() { if (d) cudaFree(d); }
+  int up(const void* h, size_t bytes, cudaStream_t s) {
+    if (!h || bytes == 0) return THRL_OK;
+    CUDA_TRY(cudaMalloc(&d, bytes));
+    CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
+    return THRL_OK;
+  }
+  int zero(size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return THRL_OK;
+    CUDA_TRY(cudaMalloc(&d, bytes));
+    CUDA_TRY(cudaMemsetAsync(d, 0, bytes, s));
+    return THRL_OK;
+  }
+  int down(void* h, size_t bytes, cudaStream_t s) {
+    if (!h || !d || bytes == 0) return THRL_OK;
+    CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
+    return THRL_OK;
+  }
+};
+}  // namespace
+
+extern "C" int thrl_qtable_scan_host(const ThrlScanArgs* a, int device) {
+  int rc = check_args(a);
+  if (rc) return rc;
+  ThrlGame G = *a->game;
+  rc = validate_layout(&G);
+  if (rc) return rc;
+  if (cudaSetDevice(device) != cudaSuccess) return fail(THRL_ERR_NO_DEVICE, "cudaSetDevice(%d) failed (there is no CPU fallback)", device);
+  cudaStream_t s;
+  CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  const size_t R = (size_t)a->n_runs, n = (size_t)G.n_agents, T = (size_t)G.max_steps;
+  const size_t E = (size_t)(a->epoch_end - a->epoch_begin);
+  const size_t esz = a->table_dtype == THRL_F64 ? 8 : 4;
+  const size_t qb = R * (size_t)G.run_stride * esz, cb = R * (size_t)G.run_stride * 4;
+  const size_t logb = (size_t)a->n_log_runs * E * n * 8, statb = E * n * THRL_STATS_K * 8;
+  const size_t rb = (size_t)ring_bytes(&G) * R;
+  DevBuf q, cnt, eps, price, hp, ring, ru, rra, rna, rl, al, st, ta, tr, tp;
+  ThrlScanArgs d = *a;
+  d.game = &G;
+#define TRY(x) do { rc = (x); if (rc) { cudaStreamDestroy(s); return rc; } } while (0)
+  TRY(q.up(a->q, qb, s)); d.q = q.d;
+  TRY(cnt.up(a->counter, cb, s)); d.counter = (uint32_t*)cnt.d;
+  TRY(eps.up(a->eps, R * n * 8, s)); d.eps = (double*)eps.d;
+  TRY(price.up(a->price, R * 8, s)); d.price = (double*)price.d;
+  TRY(hp.up(a->hp, R * n * 32, s)); d.hp = (const double*)hp.d;
+  TRY(ring.up(a->ring, rb, s)); d.ring = ring.d;
+  TRY(ru.up(a->replay_u, R * E * T * n * 8, s)); d.replay_u = (const double*)ru.d;
+  TRY(rra.up(a->replay_ra, R * E * T * n * 4, s)); d.replay_ra = (const int32_t*)rra.d;
+  TRY(rna.up(a->replay_new_a, R * E * T * 8, s)); d.replay_new_a = (const double*)rna.d;
+  if (a->rewards_log) { TRY(rl.zero(logb, s)); } d.rewards_log = (double*)rl.d;
+  if (a->actions_log) { TRY(al.zero(logb, s)); } d.actions_log = (double*)al.d;
+  if (a->stats) { TRY(st.up(a->stats, statb, s)); } d.stats = (int64_t*)st.d;
+  if (a->trace_actions) { TRY(ta.zero(R * E * T * n * 4, s)); } d.trace_actions = (int32_t*)ta.d;
+  if (a->trace_rewards) { TRY(tr.zero(R * E * T * n * 8, s)); } d.trace_rewards = (double*)tr.d;
+  if (a->trace_prices) { TRY(tp.zero(R * E * T * 8, s)); } d.trace_prices = (double*)tp.d;
+  TRY(thrl_qtable_scan(&d, s));
+  TRY(q.down(a->q, qb, s));
+  TRY(cnt.down(a->counter, cb, s));
+  TRY(eps.down(a->eps, R * n * 8, s));
+  TRY(price.down(a->price, R * 8, s));
+  TRY(ring.down(a->ring, rb, s));
+  TRY(rl.down(a->rewards_log, logb, s));
+  TRY(al.down(a->actions_log, logb, s));
+  TRY(st.down(a->stats, statb, s));
+  TRY(ta.down(a->trace_actions, R * E * T * n * 4, s));
+  TRY(tr.down(a->trace_rewards, R * E * T * n * 8, s));
+  TRY(tp.down(a->trace_prices, R * E * T * 8, s));
+#undef TRY
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaStreamDestroy(s);
+  if (e != cudaSuccess) return fail(THRL_ERR_CUDA, "scan failed: %s", cudaGetErrorString(e));
+  return THRL_OK;
+}

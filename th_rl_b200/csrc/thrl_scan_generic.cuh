@@ -1,0 +1,344 @@
+// thrl_scan_generic.cuh — the general warp-per-run scan kernel.
+//
+// One warp plays one run from epoch_begin to epoch_end, then picks up the next run (persistent grid).  It covers
+// every configuration the reference's QTable path accepts: 1..16 heterogeneous agents, demand noise, any
+// min_memory / capacity / max_steps regime, all three RNG modes, fp32 or f64 tables, tables staged in shared
+// memory (kSmemTables) or left in HBM when they do not fit.  The 2-agent noise-free configuration of the headline
+// benchmark has a specialised kernel (thrl_scan_lut2.cuh); this one is its general fallback and the C4 (HBM) path.
+//
+// Restated reference lines: see include/thrl.h; the per-step order is the one in SURVEY.md Appendix A.
+#pragma once
+#include "thrl_device.cuh"
+
+namespace thrl {
+
+struct ScanParams {
+  ThrlGame game;
+  long long n_runs, run_id0;
+  int epoch_begin, E, rng_mode;
+  uint32_t k0, k1;
+  void* q;
+  uint32_t* counter;
+  double* eps;
+  double* price;
+  const double* hp;
+  unsigned char* ring;
+  long long ring_bytes;
+  const double* replay_u;
+  const int32_t* replay_ra;
+  const double* replay_new_a;
+  double* rewards_log;
+  double* actions_log;
+  long long n_log_runs;
+  long long* stats;
+  int32_t* trace_actions;
+  double* trace_rewards;
+  double* trace_prices;
+  // shared-memory layout (bytes): [cta_bytes shared by the CTA][warp 0 slot][warp 1 slot]...
+  int cta_bytes, warp_bytes;
+  int off_tab, off_g, off_pre, off_newa, off_P, off_act, off_row, off_old, off_hp;
+  int lut_total;   // sum of actions_i
+  int rows_total;  // sum of states_i + 1
+  int Hp;          // ring slots = ring_len + 1
+  int noisy;       // new_a varies per step (noise_prob > 0 or replay_new_a given)
+};
+
+// Per-run ring blob carried between calls when the game is not regular (include/thrl.h ThrlScanArgs.ring).
+struct RingHeader {
+  int32_t pos;
+  int32_t pad;
+  int32_t len[THRL_MAX_AGENTS];
+  int32_t pad2[2];
+};
+static_assert(sizeof(RingHeader) == 80, "ring header");
+
+template <typename QT, bool kSmemTables>
+__global__ void __launch_bounds__(1024, 1) qtable_scan_generic(const __grid_constant__ ScanParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ThrlGame& G = p.game;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+  const int n = G.n_agents, T = G.max_steps, E = p.E, Hp = p.Hp;
+  const bool is_agent = lane < n;
+
+  // ---- CTA-shared per-action tables: X[k] = scale(k), AQ[k] = (a/b)*X[k], XT[k] = X[k]/max_steps
+  double* lutX = reinterpret_cast<double*>(smem);
+  double* lutAQ = lutX + p.lut_total;
+  double* lutXT = lutAQ + p.lut_total;
+  {
+    const double ab = __ddiv_rn(G.a, G.b);  // environments.py:23 self.a/self.b
+    int base = 0;
+    for (int i = 0; i < n; ++i) {
+      const ThrlAgentSpec& s = G.agent[i];
+      for (int k = threadIdx.x; k < s.actions; k += blockDim.x) {
+        const double x = scale_action(k, s.actions, s.action_lo, s.action_hi);
+        lutX[base + k] = x;
+        lutAQ[base + k] = __dmul_rn(ab, x);
+        lutXT[base + k] = __ddiv_rn(x, (double)T);  // trainer.py:66 scaled_acts / max_steps
+      }
+      base += s.actions;
+    }
+  }
+  __syncthreads();
+
+  // ---- this warp's slot
+  unsigned char* slot = smem + p.cta_bytes + (size_t)warp * p.warp_bytes;
+  QT* tab_s = reinterpret_cast<QT*>(slot + p.off_tab);
+  uint8_t* Gc = slot + p.off_g;                                    // greedy action per (agent,row)
+  int16_t* pre = reinterpret_cast<int16_t*>(slot + p.off_pre);     // [T][n] forced action or -1 (= greedy)
+  double* newa = reinterpret_cast<double*>(slot + p.off_newa);     // [T] demand intercept (noisy only)
+  double* P = reinterpret_cast<double*>(slot + p.off_P);           // [Hp] price ring
+  uint8_t* act = slot + p.off_act;                                 // [n][Hp] action ring
+  uint16_t* rowbuf = reinterpret_cast<uint16_t*>(slot + p.off_row);  // [Hp] update-encode rows of the batch
+  QT* oldv = reinterpret_cast<QT*>(slot + p.off_old);                // [Hp-1] snapshot (agents.py:67)
+  double* hpw = reinterpret_cast<double*>(slot + p.off_hp);        // [n][5] alpha,gamma,eps_end,eps_step,eps
+
+  // ---- lane i < n keeps agent i's constants in registers
+  int my_states = 1, my_actions = 2, my_cap = 0, my_minmem = 0x7fffffff, my_lut = 0, my_goff = 0;
+  long long my_toff = 0;
+  float my_msf = 1.f, my_sf = 1.f;
+  if (is_agent) {
+    const ThrlAgentSpec& s = G.agent[lane];
+    my_states = s.states; my_actions = s.actions; my_cap = s.capacity; my_minmem = s.min_memory;
+    my_toff = s.table_offset;
+    my_msf = (float)s.max_state;
+    my_sf = (float)s.states;
+    for (int j = 0; j < lane; ++j) { my_lut += G.agent[j].actions; my_goff += G.agent[j].states + 1; }
+  }
+  const bool never_fires = my_minmem > my_cap;  // buffer can never reach min_memory
+
+  const long long total_warps = (long long)gridDim.x * warps_per_cta;
+  for (long long r = (long long)blockIdx.x * warps_per_cta + warp; r < p.n_runs; r += total_warps) {
+    QT* qg = reinterpret_cast<QT*>(p.q) + r * G.run_stride;
+    QT* tab = kSmemTables ? tab_s : qg;
+    uint32_t* cnt = p.counter ? p.counter + r * G.run_stride : nullptr;
+    const uint32_t gid = (uint32_t)(p.run_id0 + r);
+
+    // ---- stage the run: tables, hyper-parameters, greedy cache, ring
+    if (kSmemTables) {
+      for (long long c = lane; c < G.run_stride; c += 32) tab_s[c] = qg[c];
+    }
+    if (is_agent) {
+      const ThrlAgentSpec& s = G.agent[lane];
+      double* h = hpw + lane * 5;
+      if (p.hp) {
+        const double* src = p.hp + (r * n + lane) * 4;
+        h[0] = src[0]; h[1] = src[1]; h[2] = src[2]; h[3] = src[3];
+      } else {
+        h[0] = s.alpha; h[1] = s.gamma; h[2] = s.eps_end; h[3] = s.eps_step;
+      }
+      h[4] = p.eps[r * n + lane];
+    }
+    __syncwarp();
+    for (int i = 0, goff = 0; i < n; ++i) {
+      const ThrlAgentSpec& s = G.agent[i];
+      const QT* tb = tab + s.table_offset;
+      for (int row = 0; row <= s.states; ++row) {
+        const int g = row_argmax(tb + (size_t)row * s.actions, s.actions, lane);
+        if (lane == 0) Gc[goff + row] = (uint8_t)g;
+      }
+      goff += s.states + 1;
+    }
+    double price = p.price[r];
+    int pos = 0, my_len = 0;
+    if (p.ring && !G.regular) {
+      const unsigned char* blob = p.ring + r * p.ring_bytes;
+      const RingHeader* hd = reinterpret_cast<const RingHeader*>(blob);
+      const double* bp = reinterpret_cast<const double*>(blob + sizeof(RingHeader));
+      const uint8_t* ba = blob + sizeof(RingHeader) + (size_t)Hp * 8;
+      pos = hd->pos;
+      if (is_agent) my_len = hd->len[lane];
+      for (int j = lane; j < Hp; j += 32) P[j] = bp[j];
+      for (int j = lane; j < n * Hp; j += 32) act[j] = ba[j];
+    }
+    __syncwarp();
+    if (lane == 0) P[pos] = price;
+    __syncwarp();
+
+    for (int e = 0; e < E; ++e) {
+      const uint32_t eabs = (uint32_t)(p.epoch_begin + e);
+      const long long step0 = (r * E + e) * (long long)T;
+
+      // ---- per-episode draws, lane-parallel (epsilon is frozen within an episode: trainer.py:50-70 only calls
+      //      train_net after the episode).  pre[t][i] = action forced by exploration / replay, or -1 = greedy.
+      for (int idx = lane; idx < T * n; idx += 32) {
+        const int t = idx / n, i = idx - t * n;
+        int v;
+        if (p.rng_mode == THRL_RNG_REPLAY_ACTIONS) {
+          v = p.replay_ra[step0 * n + idx];
+        } else if (p.rng_mode == THRL_RNG_REPLAY_DRAWS) {
+          const double u = p.replay_u[step0 * n + idx];
+          v = u < hpw[i * 5 + 4] ? p.replay_ra[step0 * n + idx] : -1;  // agents.py:81
+        } else {
+          uint32_t x[4];
+          philox4x32_10(gid, eabs, (uint32_t)t, (uint32_t)i | (kStreamAct << 16), p.k0, p.k1, x);
+          const double u = u53(x[0], x[1]);
+          const int ra = (int)__umulhi(x[2], (uint32_t)G.agent[i].actions);
+          v = u < hpw[i * 5 + 4] ? ra : -1;
+        }
+        pre[idx] = (int16_t)v;
+      }
+      if (p.noisy) {
+        for (int t = lane; t < T; t += 32) {
+          double na = G.a;
+          if (p.rng_mode == THRL_RNG_PHILOX) {
+            uint32_t x[4];
+            philox4x32_10(gid, eabs, (uint32_t)t, kStreamEnv << 16, p.k0, p.k1, x);
+            if (u53(x[0], x[1]) < G.noise_prob) {  // environments.py:28
+              const double lo = __dmul_rn(G.a, 0.7);
+              na = __dadd_rn(lo, __dmul_rn(__dsub_rn(G.a, lo), u53(x[2], x[3])));
+            }
+          } else if (p.replay_new_a) {
+            na = p.replay_new_a[step0 + t];
+          }
+          newa[t] = na;
+        }
+      }
+      __syncwarp();
+
+      // ---- the episode (trainer.py:50-67); lane i < n acts for agent i
+      double rlog = 0.0, alog = 0.0;  // trainer.py:40-41
+      for (int t = 0; t < T; ++t) {
+        int k = 0;
+        double aq = 0.0;
+        if (is_agent) {
+          k = pre[t * n + lane];
+          if (k < 0) k = Gc[my_goff + act_row(price, my_msf, my_sf)];  // agents.py:84-88 on the frozen table
+          aq = lutAQ[my_lut + k];
+        }
+        double Q = 0.0;  // environments.py:27 sum(A): ((0 + A0) + A1) + ...
+        for (int i = 0; i < n; ++i) Q = __dadd_rn(Q, shfl_d(aq, i));
+        const double na = p.noisy ? newa[t] : G.a;
+        const double pn = __dsub_rn(na, __dmul_rn(G.b, Q));
+        const double next_price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);  // numpy.max([0, x])
+        const double rew = __dmul_rn(next_price, aq);                       // environments.py:34
+        int nxt = pos + 1;
+        if (nxt == Hp) nxt = 0;
+        if (is_agent) {
+          rlog = __dadd_rn(rlog, __ddiv_rn(rew, (double)T));  // trainer.py:65
+          alog = __dadd_rn(alog, lutXT[my_lut + k]);          // trainer.py:66
+          act[lane * Hp + pos] = (uint8_t)k;                  // trainer.py:61-62 memory.append
+          my_len = my_len < my_cap ? my_len + 1 : my_cap;     // deque(maxlen=capacity)
+          if (p.trace_actions) p.trace_actions[(step0 + t) * n + lane] = k;
+          if (p.trace_rewards) p.trace_rewards[(step0 + t) * n + lane] = rew;
+        }
+        if (lane == 0) {
+          P[nxt] = next_price;
+          if (p.trace_prices) p.trace_prices[step0 + t] = next_price;
+        }
+        pos = nxt;
+        price = next_price;  // trainer.py:67
+      }
+      __syncwarp();
+
+      // ---- train_net for every agent in order (trainer.py:70, agents.py:59-78)
+      for (int i = 0; i < n; ++i) {
+        const int L = __shfl_sync(kFull, my_len, i);
+        const int fires = __shfl_sync(kFull, (int)(!never_fires && my_len >= my_minmem), i);
+        if (fires) {
+          const ThrlAgentSpec& s = G.agent[i];
+          const int A = s.actions;
+          QT* tb = tab + s.table_offset;
+          const double alpha = hpw[i * 5 + 0], gamma = hpw[i * 5 + 1];
+          const double one_m_alpha = __dsub_rn(1.0, alpha);
+          int first = pos - L;
+          if (first < 0) first += Hp;
+          const int goff = __shfl_sync(kFull, my_goff, i), loff = __shfl_sync(kFull, my_lut, i);
+          // encodes (:62,:66) and the stale snapshot (:67), lane-parallel
+          for (int j = lane; j <= L; j += 32) {
+            int sl = first + j;
+            if (sl >= Hp) sl -= Hp;
+            rowbuf[j] = (uint16_t)upd_row(P[sl], s.max_state, (double)s.states);
+          }
+          __syncwarp();
+          for (int j = lane; j < L; j += 32) {
+            int sl = first + j;
+            if (sl >= Hp) sl -= Hp;
+            oldv[j] = tb[(size_t)rowbuf[j] * A + act[i * Hp + sl]];
+          }
+          __syncwarp();
+          // the sequential pass (:68-76); `dirty` marks rows whose greedy action must be recomputed
+          unsigned dirty = 0;  // lane l holds rows 32*l .. 32*l+31 (+1024*w in word w; rows > 1023 fall back below)
+          bool dirty_overflow = false;
+          int sl = first;
+          for (int j = 0; j < L; ++j) {
+            const int st = rowbuf[j], ns = rowbuf[j + 1];
+            const int k = act[i * Hp + sl];
+            int sn = sl + 1;
+            if (sn == Hp) sn = 0;
+            const double reward = __dmul_rn(P[sn], lutAQ[loff + k]);
+            const double next_max = (double)row_max(tb + (size_t)ns * A, A, lane);  // live table (:71)
+            const double nv = __dadd_rn(__dmul_rn(one_m_alpha, (double)oldv[j]),
+                                        __dmul_rn(alpha, __dadd_rn(reward, __dmul_rn(gamma, next_max))));
+            if ((k & 31) == lane) {  // the lane that owns column k
+              tb[(size_t)st * A + k] = (QT)nv;
+              if (cnt) atomicAdd(cnt + s.table_offset + (size_t)st * A + k, 1u);  // :76, fire-and-forget RED
+            }
+            if (st < 1024) {
+              if ((st >> 5) == lane) dirty |= 1u << (st & 31);
+            } else {
+              dirty_overflow = true;
+            }
+            sl = sn;
+          }
+          // refresh the greedy cache of the rows that were written
+          if (dirty_overflow) {
+            for (int row = 1024; row <= s.states; ++row) {
+              const int g = row_argmax(tb + (size_t)row * A, A, lane);
+              if (lane == 0) Gc[goff + row] = (uint8_t)g;
+            }
+          }
+          unsigned any = __ballot_sync(kFull, dirty != 0);
+          while (any) {
+            const int src = __ffs(any) - 1;
+            const unsigned word = __shfl_sync(kFull, dirty, src);
+            const int bit = __ffs(word) - 1;
+            const int row = src * 32 + bit;
+            const int g = row_argmax(tb + (size_t)row * A, A, lane);
+            if (lane == 0) Gc[goff + row] = (uint8_t)g;
+            if (lane == src) dirty &= dirty - 1;
+            any = __ballot_sync(kFull, dirty != 0);
+          }
+          if (lane == i) my_len = 0;  // :77 memory.empty()
+          __syncwarp();
+        }
+      }
+      // epsilon decay, every epoch (:78); logs
+      if (is_agent) {
+        double* h = hpw + lane * 5;
+        h[4] = __dadd_rn(h[2], __dmul_rn(__dsub_rn(h[4], h[2]), h[3]));
+        if (r < p.n_log_runs) {
+          if (p.rewards_log) p.rewards_log[(r * E + e) * n + lane] = rlog;
+          if (p.actions_log) p.actions_log[(r * E + e) * n + lane] = alog;
+        }
+        if (p.stats) {
+          unsigned long long* s4 = reinterpret_cast<unsigned long long*>(p.stats) + ((size_t)e * n + lane) * THRL_STATS_K;
+          atomicAdd(s4 + 0, (unsigned long long)fx_round(__dmul_rn(rlog, THRL_STATS_SCALE_SUM)));
+          atomicAdd(s4 + 1, (unsigned long long)fx_round(__dmul_rn(__dmul_rn(rlog, rlog), THRL_STATS_SCALE_SQ)));
+          atomicAdd(s4 + 2, (unsigned long long)fx_round(__dmul_rn(alog, THRL_STATS_SCALE_SUM)));
+          atomicAdd(s4 + 3, (unsigned long long)fx_round(__dmul_rn(__dmul_rn(alog, alog), THRL_STATS_SCALE_SQ)));
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- write the run back
+    if (kSmemTables) {
+      for (long long c = lane; c < G.run_stride; c += 32) qg[c] = tab_s[c];
+    }
+    if (is_agent) p.eps[r * n + lane] = hpw[lane * 5 + 4];
+    if (lane == 0) p.price[r] = price;
+    if (p.ring && !G.regular) {
+      unsigned char* blob = p.ring + r * p.ring_bytes;
+      RingHeader* hd = reinterpret_cast<RingHeader*>(blob);
+      double* bp = reinterpret_cast<double*>(blob + sizeof(RingHeader));
+      uint8_t* ba = blob + sizeof(RingHeader) + (size_t)Hp * 8;
+      if (lane == 0) hd->pos = pos;
+      if (is_agent) hd->len[lane] = my_len;
+      for (int j = lane; j < Hp; j += 32) bp[j] = P[j];
+      for (int j = lane; j < n * Hp; j += 32) ba[j] = act[j];
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace thrl

@@ -1,0 +1,209 @@
+"""Batched runs of one game on one GPU: device-resident state + calls into the C ABI.
+
+`RunBatch` owns the per-run state as torch CUDA tensors (torch is only the allocator / stream provider here) and
+advances all runs with one `thrl_qtable_scan` launch per call.  This is what `trainer.train_many` / `train_one`
+drive; it replaces the reference's one-run-at-a-time Python loop (th_rl/trainer.py:45-70, th_rl/main.py:19-21).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+from ._lib import check, game_layout, lib
+
+
+def _dp(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class ScanOutput:
+    """What one scan call produced (device tensors unless stated)."""
+    rewards_log = None   # [n_log_runs, E, n] f64 per-epoch mean reward (trainer.py:65)
+    actions_log = None   # [n_log_runs, E, n] f64 per-epoch mean scaled action (trainer.py:66)
+    stats = None         # [E, n, 4] int64 fixed-point cross-run sums (abi.THRL_STATS_*)
+    trace_actions = None
+    trace_rewards = None
+    trace_prices = None
+
+
+class RunBatch:
+    def __init__(self, config, n_runs, *, device="cuda:0", dtype=torch.float32, run_id0=0, seed=0, hp=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("th_rl_b200 needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.config = config
+        self.game = game_layout(config)
+        self.n_runs = int(n_runs)
+        self.device = torch.device(device)
+        assert dtype in (torch.float32, torch.float64)
+        self.dtype = dtype
+        self.table_dtype = abi.THRL_F64 if dtype == torch.float64 else abi.THRL_F32
+        self.run_id0 = int(run_id0)
+        self.seed = int(seed)
+        self.epoch = 0
+        g, R, n = self.game, self.n_runs, self.game.n_agents
+        with torch.cuda.device(self.device):
+            self.q = torch.empty((R, g.run_stride), dtype=dtype, device=self.device)
+            self.counter = torch.zeros((R, g.run_stride), dtype=torch.int32, device=self.device)  # u32 bit pattern
+            self.eps = torch.empty((R, n), dtype=torch.float64, device=self.device)
+            self.price = torch.empty((R,), dtype=torch.float64, device=self.device)
+            self.hp = None if hp is None else torch.as_tensor(np.ascontiguousarray(hp, np.float64)).reshape(R, n, 4).to(self.device)
+            self.ring = None
+            if not g.regular:
+                rb = lib().thrl_ring_bytes(C.byref(g))
+                self.ring = torch.zeros((R, rb), dtype=torch.uint8, device=self.device)
+
+    # ---- initial state -------------------------------------------------------------------------------------------
+    def init_device(self):
+        """QTable.__init__ / environment.reset() for every run, on the device, from Philox(seed, global run id)."""
+        eps0 = (C.c_double * self.game.n_agents)(*abi.eps0_from_config(self.config))
+        with torch.cuda.device(self.device):
+            check(lib().thrl_qtable_init(C.byref(self.game), self.n_runs, self.run_id0, self.seed, self.table_dtype,
+                                         _dp(self.hp), eps0, _dp(self.q), _dp(self.counter), _dp(self.eps),
+                                         _dp(self.price), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        self.epoch = 0
+        return self
+
+    def load_state(self, q, eps, price, counter=None, non_blocking=False):
+        """Initial state provided by the caller as host arrays / tensors (e.g. tables drawn by numpy like the reference)."""
+        def put(dst, src, dt):
+            src = torch.as_tensor(src).reshape(dst.shape)
+            if src.dtype != dt:
+                src = src.to(dt)
+            dst.copy_(src, non_blocking=non_blocking)
+        put(self.q, q, self.dtype)
+        put(self.eps, eps, torch.float64)
+        put(self.price, price, torch.float64)
+        if counter is not None:
+            put(self.counter, torch.as_tensor(np.asarray(counter).astype(np.uint32).view(np.int32)) if not torch.is_tensor(counter) else counter, torch.int32)
+        else:
+            self.counter.zero_()
+        self.epoch = 0
+        return self
+
+    # ---- the hot path --------------------------------------------------------------------------------------------
+    def scan(self, epochs, *, rng_mode=abi.THRL_RNG_PHILOX, replay_u=None, replay_ra=None, replay_new_a=None,
+             n_log_runs=0, stats=False, trace=False, stream=None):
+        """Play `epochs` more epochs for every run with one kernel launch.  Asynchronous on the current stream."""
+        g, R, n, T, E = self.game, self.n_runs, self.game.n_agents, self.game.max_steps, int(epochs)
+        dev = self.device
+        out = ScanOutput()
+        keep = []
+
+        def dev_in(a, dt, shape):
+            if a is None:
+                return None
+            t = torch.as_tensor(a)
+            if t.dtype != dt:
+                t = t.to(dt)
+            t = t.reshape(shape).contiguous().to(dev, non_blocking=True)
+            keep.append(t)
+            return t
+
+        with torch.cuda.device(dev):
+            ru = dev_in(replay_u, torch.float64, (R, E, T, n))
+            rra = dev_in(replay_ra, torch.int32, (R, E, T, n))
+            rna = dev_in(replay_new_a, torch.float64, (R, E, T))
+            if n_log_runs:
+                out.rewards_log = torch.zeros((n_log_runs, E, n), dtype=torch.float64, device=dev)
+                out.actions_log = torch.zeros((n_log_runs, E, n), dtype=torch.float64, device=dev)
+            if stats:
+                out.stats = torch.zeros((E, n, abi.THRL_STATS_K), dtype=torch.int64, device=dev)
+            if trace:
+                out.trace_actions = torch.zeros((R, E, T, n), dtype=torch.int32, device=dev)
+                out.trace_rewards = torch.zeros((R, E, T, n), dtype=torch.float64, device=dev)
+                out.trace_prices = torch.zeros((R, E, T), dtype=torch.float64, device=dev)
+            a = abi.ThrlScanArgs()
+            a.game = C.pointer(g)
+            a.n_runs, a.run_id0 = R, self.run_id0
+            a.epoch_begin, a.epoch_end = self.epoch, self.epoch + E
+            a.table_dtype, a.rng_mode, a.seed = self.table_dtype, rng_mode, self.seed
+            a.q, a.counter, a.eps, a.price = _dp(self.q), _dp(self.counter), _dp(self.eps), _dp(self.price)
+            a.hp, a.ring = _dp(self.hp), _dp(self.ring)
+            a.replay_u, a.replay_ra, a.replay_new_a = _dp(ru), _dp(rra), _dp(rna)
+            a.rewards_log, a.actions_log, a.n_log_runs = _dp(out.rewards_log), _dp(out.actions_log), int(n_log_runs)
+            a.stats = _dp(out.stats)
+            a.trace_actions, a.trace_rewards, a.trace_prices = _dp(out.trace_actions), _dp(out.trace_rewards), _dp(out.trace_prices)
+            s = stream if stream is not None else torch.cuda.current_stream()
+            check(lib().thrl_qtable_scan(C.byref(a), C.c_void_p(s.cuda_stream)))
+            for t in keep:  # inputs must outlive the asynchronous kernel
+                t.record_stream(s)
+        self.epoch += E
+        return out
+
+    # ---- results -------------------------------------------------------------------------------------------------
+    def tables(self, run=None):
+        """Per-agent tables [R, states+1, actions] (views of the packed slab)."""
+        q = self.q if run is None else self.q[run:run + 1]
+        return [q[:, s.table_offset:s.table_offset + (s.states + 1) * s.actions].reshape(-1, s.states + 1, s.actions)
+                for s in (self.game.agent[i] for i in range(self.game.n_agents))]
+
+    def counters(self, run=None):
+        c = self.counter if run is None else self.counter[run:run + 1]
+        return [c[:, s.table_offset:s.table_offset + (s.states + 1) * s.actions].reshape(-1, s.states + 1, s.actions)
+                for s in (self.game.agent[i] for i in range(self.game.n_agents))]
+
+    def greedy_eval(self, price0):
+        """utils.play_game for every run: price0 [R, iters] -> (actions, rewards) [R, iters*T, n] f64 device tensors."""
+        g, R, n, T = self.game, self.n_runs, self.game.n_agents, self.game.max_steps
+        p0 = torch.as_tensor(price0, dtype=torch.float64).reshape(R, -1).contiguous().to(self.device)
+        iters = p0.shape[1]
+        rewards = torch.empty((R, iters * T, n), dtype=torch.float64, device=self.device)
+        actions = torch.empty((R, iters * T, n), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib().thrl_greedy_eval(C.byref(g), R, self.table_dtype, _dp(self.q), iters, _dp(p0), _dp(rewards),
+                                         _dp(actions), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return actions, rewards
+
+
+def scan_host(config, q, eps, price, epochs, *, counter=None, hp=None, rng_mode=abi.THRL_RNG_PHILOX, seed=0, run_id0=0,
+              epoch_begin=0, replay_u=None, replay_ra=None, replay_new_a=None, n_log_runs=0, stats=False, trace=False,
+              device=0):
+    """thrl_qtable_scan_host: HOST numpy buffers in and out, all copies inside the call (the reference-facing
+    boundary; bench.py's e2e leg times exactly this).  q/eps/price(/counter) are updated IN PLACE."""
+    g = game_layout(config)
+    n, T, E = g.n_agents, g.max_steps, int(epochs)
+    R = q.shape[0]
+    assert q.flags.c_contiguous and q.dtype in (np.float32, np.float64) and q.shape == (R, g.run_stride)
+    assert eps.dtype == np.float64 and price.dtype == np.float64 and eps.flags.c_contiguous and price.flags.c_contiguous
+    out = ScanOutput()
+    keep = []
+
+    def inp(a, dt, shape):
+        if a is None:
+            return None
+        a = np.ascontiguousarray(a, dtype=dt).reshape(shape)
+        keep.append(a)
+        return a.ctypes.data_as(C.c_void_p)
+
+    def outp(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    if n_log_runs:
+        out.rewards_log = np.zeros((n_log_runs, E, n), np.float64)
+        out.actions_log = np.zeros((n_log_runs, E, n), np.float64)
+    if stats:
+        out.stats = np.zeros((E, n, abi.THRL_STATS_K), np.int64)
+    if trace:
+        out.trace_actions = np.zeros((R, E, T, n), np.int32)
+        out.trace_rewards = np.zeros((R, E, T, n), np.float64)
+        out.trace_prices = np.zeros((R, E, T), np.float64)
+    a = abi.ThrlScanArgs()
+    a.game = C.pointer(g)
+    a.n_runs, a.run_id0 = R, run_id0
+    a.epoch_begin, a.epoch_end = epoch_begin, epoch_begin + E
+    a.table_dtype = abi.THRL_F64 if q.dtype == np.float64 else abi.THRL_F32
+    a.rng_mode, a.seed = rng_mode, seed
+    a.q, a.eps, a.price = outp(q), outp(eps), outp(price)
+    if counter is not None:
+        assert counter.dtype == np.uint32 and counter.shape == q.shape and counter.flags.c_contiguous
+        a.counter = outp(counter)
+    a.hp = inp(hp, np.float64, (R, n, 4))
+    a.replay_u = inp(replay_u, np.float64, (R, E, T, n))
+    a.replay_ra = inp(replay_ra, np.int32, (R, E, T, n))
+    a.replay_new_a = inp(replay_new_a, np.float64, (R, E, T))
+    a.rewards_log, a.actions_log, a.n_log_runs = outp(out.rewards_log), outp(out.actions_log), int(n_log_runs)
+    a.stats = outp(out.stats)
+    a.trace_actions, a.trace_rewards, a.trace_prices = outp(out.trace_actions), outp(out.trace_rewards), outp(out.trace_prices)
+    check(lib().thrl_qtable_scan_host(C.byref(a), int(device)))
+    return out

@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""bench.py — agent-steps/s of the th_rl training hot path on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path (thrl_qtable_scan) over the whole batch: RUNS_PER_GPU independent runs x
+2 QTable agents x EPOCHS epochs x 100 env steps on every GPU (BASELINE C2 shape; 8 GPUs x 131,072 runs = the
+1,048,576 runs of C3).  Runs are independent, so ranks share nothing on the data path (weak scaling); the only
+collective is the NCCL all-reduce of the per-epoch cross-run statistics, inside the timed region.
+
+value  = agent-steps of all ranks / max-over-ranks CUDA-event time, state resident in HBM.
+e2e    = the same work through the host-facing API: tables start in pinned HOST memory, are copied in, scanned,
+         and tables + counters + statistics are copied back, all inside the timed region.
+--impl reference: the CPU arm = the oracle port of the reference path (oracle/thrl_oracle.c, all host threads) on a
+         bounded sample of the same workload.  The reference itself is pure Python and cannot travel to the GPU box;
+         its measured speed in the build container is quoted in BASELINE.md (2.35e4 agent-steps/s/core).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RUNS_PER_GPU = 131072
+EPOCHS = 200
+MAX_STEPS = 100
+ALGO_BYTES_PER_AGENT_STEP = 184.0  # 8*A + 16 bytes of table traffic per agent-step at A = 21
+
+CONFIG = {
+    "agents": [dict(name="QTable", gamma=0.95, actions=21, states=100, alpha=0.1, eps_end=0.001, epsilon=0.5,
+                    eps_step=0.9995, action_range=[0.2, 0.4]) for _ in range(2)],
+    "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=2, max_steps=MAX_STEPS),
+    "training": dict(print_freq=500, epochs=EPOCHS),
+}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_leg(n_threads, target_seconds=12.0):
+    """Times the oracle port on host cores on a bounded sample of the same workload (same config, fewer runs)."""
+    import numpy as np
+    from oracle import oracle
+    from th_rl_b200 import abi
+    game = oracle.layout(CONFIG)
+    cores = n_threads if n_threads > 0 else oracle.online_cores()
+    eps0 = abi.eps0_from_config(CONFIG)
+    # calibrate on a small sample, then size the timed sample for ~target_seconds
+    R0 = 4 * cores
+    q0, c0, e0, p0 = oracle.init(game, R0, seed=0, dtype=np.float32, eps0=eps0)
+    t = time.perf_counter()
+    oracle.scan(game, q0, e0, p0, 20, n_threads=cores, n_log_runs=0, stats=True)
+    rate = R0 * 2 * 20 * MAX_STEPS / (time.perf_counter() - t)
+    R = int(max(cores, min(4096, target_seconds * rate / (2 * EPOCHS * MAX_STEPS))))
+    q0, c0, e0, p0 = oracle.init(game, R, seed=0, dtype=np.float32, eps0=eps0)
+    t = time.perf_counter()
+    oracle.scan(game, q0, e0, p0, EPOCHS, n_threads=cores, n_log_runs=0, stats=True)
+    dt = time.perf_counter() - t
+    return {"value": R * 2 * EPOCHS * MAX_STEPS / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d runs x %d epochs x %d steps x 2 agents of the bench workload, fp32-storage oracle "
+                      "(oracle/thrl_oracle.c), %d pthreads, %.1f s" % (R, EPOCHS, MAX_STEPS, cores, dt)}, dt
+
+
+def base_line(args, n_gpus):
+    return {
+        "metric": "agent-steps/sec", "unit": "agent-steps/s", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "2-agent QTable iterated Cournot/PD game (example_config hyper-parameters, 101x21 tables, "
+                               "max_steps=100), %d runs/GPU x %d epochs per step (C2 shape; 8 GPUs = the 1,048,576 runs "
+                               "of C3)" % (args.runs_per_gpu, args.epochs),
+                   "runs_per_gpu": args.runs_per_gpu, "global_runs": args.runs_per_gpu * n_gpus, "epochs_per_step": args.epochs,
+                   "max_steps": MAX_STEPS, "agents": 2, "table_storage": "fp32 (f64 update arithmetic)",
+                   "rng": "philox4x32-10", "parallelism": "runs sharded over %d GPU(s), no data-path collective; "
+                                                          "NCCL all-reduce of per-epoch statistics" % n_gpus,
+                   "l2": "per-GPU state (tables+counters %.1f GB) is far larger than the 126 MB L2"
+                         % (args.runs_per_gpu * 4242 * 8 / 1e9)},
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb, dt = cpu_oracle_leg(0, target_seconds=max(2.0, min(10.0, 120.0 / (args.warmup + args.steps))))
+        if i >= args.warmup:
+            vals.append((cb["value"], dt))
+    v = statistics.mean(x for x, _ in vals)
+    line = base_line(args, args.gpus)
+    line.update({"impl": "reference", "value": v, "ms_per_step": 1e3 * statistics.mean(d for _, d in vals),
+                 "cpu_baseline": dict(cb, value=v),
+                 "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    line["config"]["reference_arm"] = ("oracle port of th_rl/trainer.py:45-70 + agents.py:59-89 + environments.py:25-39 on "
+                                       "host cores; the Python reference itself measured 2.35e4 agent-steps/s/core in the "
+                                       "build container (BASELINE.md)")
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from th_rl_b200 import _lib, abi, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    R, E = args.runs_per_gpu, args.epochs
+    agent_steps_rank = R * 2 * E * MAX_STEPS
+
+    batch = engine.RunBatch(CONFIG, R, device=dev, dtype=torch.float32, seed=0, run_id0=rank * R).init_device()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        out = batch.scan(E, stats=True)
+        if world > 1:
+            dist.all_reduce(out.stats)  # exact int64 sums: the result does not depend on the sharding
+        return out
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev[0].record()
+    for i in range(args.steps):
+        kev[i][0].record()
+        out = batch.scan(E, stats=True)
+        kev[i][1].record()
+        if world > 1:
+            dist.all_reduce(out.stats)
+        ev[i + 1].record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kern_ms = t.tolist()
+    value = agent_steps_rank * world * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: host-resident state in, results back to the host, all inside the timed region
+    e2e = measure_e2e(args, torch, np, engine, dev, rank, world, barrier)
+
+    if rank == 0:
+        hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+        smem_peak_gbs = 128.0 * 148 * sm_max_mhz * 1e6 / 1e9  # 128 B/clk/SM x 148 SMs x max SM clock
+        per_gpu_rate = agent_steps_rank / (kern_ms * 1e-3)
+        achieved = per_gpu_rate * ALGO_BYTES_PER_AGENT_STEP / 1e9
+        line = base_line(args, world)
+        line.update({
+            "value": value, "ms_per_step": total_ms / args.steps, "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_peak_gbs, "unit": "GB/s",
+                         "frac": achieved / smem_peak_gbs, "traffic": None,
+                         "kernel": "thrl::qtable_scan (persistent, one launch per step)",
+                         "kernel_ms": kern_ms,
+                         "note": "tables are shared-memory resident, so the bound is SM shared-memory bandwidth "
+                                 "(BASELINE.md 5: 184 algorithmic B per agent-step; peak = 128 B/clk/SM x 148 SMs x "
+                                 "%.0f MHz from MEASURED_PEAKS.json, %s); HBM sees only the one-off table load/store "
+                                 "and the visit counters" % (sm_max_mhz, peak_src),
+                         "hbm": {"achieved": per_gpu_rate * (2 * 4242 * (4 + 4 + 4) / (2.0 * E * MAX_STEPS)) / 1e9,
+                                 "peak": hbm_peak, "unit": "GB/s"}},
+        })
+        if args.no_cpu_baseline:
+            line["cpu_baseline"] = None
+        else:
+            line["cpu_baseline"], _ = cpu_oracle_leg(0)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_e2e(args, torch, np, engine, dev, rank, world, barrier):
+    """Same metric through the host-facing call: pinned host tables -> device -> scan -> tables, counters, epsilon,
+    price and statistics back into pinned host memory.  Runs go through in chunks so copies overlap the kernel."""
+    import torch.distributed as dist
+    R, E = args.runs_per_gpu, args.epochs
+    batch = engine.RunBatch(CONFIG, R, device=dev, dtype=torch.float32, seed=1, run_id0=rank * R).init_device()
+    torch.cuda.synchronize()
+    host = engine.HostState.from_batch(batch)  # pinned host copies of q / counter / eps / price
+    steps = max(1, min(args.steps, 3))
+    h2d = d2h = 0
+    for it in range(1 + steps):  # one warm-up
+        if it == 1:
+            barrier()
+            t0 = time.perf_counter()
+        stats, h2d, d2h = engine.scan_from_host(batch, host, E, n_chunks=args.e2e_chunks)
+        if world > 1:
+            dist.all_reduce(stats)
+        stats_h = stats.cpu()  # the step's result (per-epoch cross-run statistics) is read on the host
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = t.item()
+    return {"value": R * world * 2 * E * MAX_STEPS * steps / dt, "unit": "agent-steps/s",
+            "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h + stats_h.numel() * 8) * world,
+            "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "api": "th_rl_b200.engine.scan_from_host (pinned host state in, tables+counters+eps+price+stats out)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--runs-per-gpu", type=int, default=RUNS_PER_GPU)
+    ap.add_argument("--epochs", type=int, default=EPOCHS)
+    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun
+        port = 29500 + os.getpid() % 1000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(port)] + sys.argv
+        sys.exit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

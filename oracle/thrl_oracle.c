@@ -6,7 +6,7 @@
  *
  * Parity status: PINNED.  tests/test_oracle_golden.py checks this restatement bit-for-bit
  * (actions, rewards, prices, f64 tables, counters, epsilon, per-epoch logs) against streams
- * recorded from the unmodified reference by oracle/make_goldens.py (tests/golden/*.npz).
+ * recorded from the unmodified reference by oracle/make_goldens.py (the .npz files under tests/golden).
  * The reference ships no tests or golden vectors of its own.
  *
  * Everything here is scalar f64/f32 IEEE arithmetic in the reference's operation order; build

@@ -3,9 +3,9 @@ import json, sys, time
 import torch
 sys.path.insert(0, ".")
 from th_rl_b200 import engine
-from tests.conftest import load_golden
+import numpy as np
 
-cfg = load_golden("c1_example_2q_seed0")["config"]
+cfg = json.loads(str(np.load("tests/golden/c1_example_2q_seed0.npz")["config"]))
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 E = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 for dtype in (torch.float32, torch.float64):

@@ -67,7 +67,7 @@ class RunBatch:
     def load_state(self, q, eps, price, counter=None, non_blocking=False):
         """Initial state provided by the caller as host arrays / tensors (e.g. tables drawn by numpy like the reference)."""
         def put(dst, src, dt):
-            src = torch.as_tensor(src).reshape(dst.shape)
+            src = (src if torch.is_tensor(src) else torch.as_tensor(np.asarray(src))).reshape(dst.shape)
             if src.dtype != dt:
                 src = src.to(dt)
             dst.copy_(src, non_blocking=non_blocking)
@@ -83,9 +83,12 @@ class RunBatch:
 
     # ---- the hot path --------------------------------------------------------------------------------------------
     def scan(self, epochs, *, rng_mode=abi.THRL_RNG_PHILOX, replay_u=None, replay_ra=None, replay_new_a=None,
-             n_log_runs=0, stats=False, trace=False, stream=None):
-        """Play `epochs` more epochs for every run with one kernel launch.  Asynchronous on the current stream."""
-        g, R, n, T, E = self.game, self.n_runs, self.game.n_agents, self.game.max_steps, int(epochs)
+             n_log_runs=0, stats=False, trace=False, stream=None, run_range=None, advance=True):
+        """Play `epochs` more epochs for every run (or runs [b, e) with run_range=(b, e)) with one kernel launch.
+        Asynchronous on the current stream.  `stats` may be True (fresh buffer) or an int64 [E, n, 4] tensor to add into."""
+        g, n, T, E = self.game, self.game.n_agents, self.game.max_steps, int(epochs)
+        rb, re_ = (0, self.n_runs) if run_range is None else (int(run_range[0]), int(run_range[1]))
+        R = re_ - rb
         dev = self.device
         out = ScanOutput()
         keep = []
@@ -107,7 +110,9 @@ class RunBatch:
             if n_log_runs:
                 out.rewards_log = torch.zeros((n_log_runs, E, n), dtype=torch.float64, device=dev)
                 out.actions_log = torch.zeros((n_log_runs, E, n), dtype=torch.float64, device=dev)
-            if stats:
+            if torch.is_tensor(stats):
+                out.stats = stats
+            elif stats:
                 out.stats = torch.zeros((E, n, abi.THRL_STATS_K), dtype=torch.int64, device=dev)
             if trace:
                 out.trace_actions = torch.zeros((R, E, T, n), dtype=torch.int32, device=dev)
@@ -115,11 +120,12 @@ class RunBatch:
                 out.trace_prices = torch.zeros((R, E, T), dtype=torch.float64, device=dev)
             a = abi.ThrlScanArgs()
             a.game = C.pointer(g)
-            a.n_runs, a.run_id0 = R, self.run_id0
+            a.n_runs, a.run_id0 = R, self.run_id0 + rb
             a.epoch_begin, a.epoch_end = self.epoch, self.epoch + E
             a.table_dtype, a.rng_mode, a.seed = self.table_dtype, rng_mode, self.seed
-            a.q, a.counter, a.eps, a.price = _dp(self.q), _dp(self.counter), _dp(self.eps), _dp(self.price)
-            a.hp, a.ring = _dp(self.hp), _dp(self.ring)
+            a.q, a.counter, a.eps, a.price = _dp(self.q[rb:re_]), _dp(self.counter[rb:re_]), _dp(self.eps[rb:re_]), _dp(self.price[rb:re_])
+            a.hp = None if self.hp is None else _dp(self.hp[rb:re_])
+            a.ring = None if self.ring is None else _dp(self.ring[rb:re_])
             a.replay_u, a.replay_ra, a.replay_new_a = _dp(ru), _dp(rra), _dp(rna)
             a.rewards_log, a.actions_log, a.n_log_runs = _dp(out.rewards_log), _dp(out.actions_log), int(n_log_runs)
             a.stats = _dp(out.stats)
@@ -128,7 +134,8 @@ class RunBatch:
             check(lib().thrl_qtable_scan(C.byref(a), C.c_void_p(s.cuda_stream)))
             for t in keep:  # inputs must outlive the asynchronous kernel
                 t.record_stream(s)
-        self.epoch += E
+        if advance:
+            self.epoch += E
         return out
 
     # ---- results -------------------------------------------------------------------------------------------------
@@ -154,6 +161,60 @@ class RunBatch:
             check(lib().thrl_greedy_eval(C.byref(g), R, self.table_dtype, _dp(self.q), iters, _dp(p0), _dp(rewards),
                                          _dp(actions), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return actions, rewards
+
+
+class HostState:
+    """Per-run state in pinned host memory (what a host-side caller owns between calls)."""
+
+    def __init__(self, q, counter, eps, price):
+        self.q, self.counter, self.eps, self.price = q, counter, eps, price
+
+    @classmethod
+    def from_batch(cls, batch):
+        def pin(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t)
+            return h
+        return cls(pin(batch.q), pin(batch.counter), pin(batch.eps), pin(batch.price))
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in (self.q, self.counter, self.eps, self.price))
+
+
+def scan_from_host(batch, host, epochs, n_chunks=8):
+    """Host-resident state -> `epochs` more epochs -> host-resident state, plus the cross-run statistics.
+
+    The run range is cut into n_chunks; chunk c+1's host->device copy and chunk c-1's device->host copy run on their
+    own streams while chunk c is in the kernel.  Returns (stats device tensor [E, n, 4], h2d bytes, d2h bytes).
+    """
+    dev, R, E, n = batch.device, batch.n_runs, int(epochs), batch.game.n_agents
+    n_chunks = max(1, min(int(n_chunks), R))
+    bounds = [R * c // n_chunks for c in range(n_chunks + 1)]
+    with torch.cuda.device(dev):
+        if not hasattr(batch, "_streams"):
+            batch._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        up, down = batch._streams
+        cs = torch.cuda.current_stream()
+        stats = torch.zeros((E, n, abi.THRL_STATS_K), dtype=torch.int64, device=dev)
+        up.wait_stream(cs)
+        pairs = ((batch.q, host.q), (batch.counter, host.counter), (batch.eps, host.eps), (batch.price, host.price))
+        for c in range(n_chunks):
+            b, e = bounds[c], bounds[c + 1]
+            with torch.cuda.stream(up):
+                for d, h in pairs:
+                    d[b:e].copy_(h[b:e], non_blocking=True)
+                ev_up = up.record_event()
+            cs.wait_event(ev_up)
+            batch.scan(E, stats=stats, run_range=(b, e), advance=False)
+            ev_k = cs.record_event()
+            down.wait_event(ev_k)
+            with torch.cuda.stream(down):
+                for d, h in pairs:
+                    h[b:e].copy_(d[b:e], non_blocking=True)
+        cs.wait_stream(down)
+    batch.epoch += E
+    nb = host.nbytes()
+    return stats, nb, nb
 
 
 def scan_host(config, q, eps, price, epochs, *, counter=None, hp=None, rng_mode=abi.THRL_RNG_PHILOX, seed=0, run_id0=0,

@@ -226,10 +226,11 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
             u = A->replay_u[sidx * n + i];
             ra = A->replay_ra[sidx * n + i];
           } else {
+            /* one Philox call serves agents 2p and 2p+1: words (0,1) / (2,3) = (uniform, random action) */
             uint32_t x[4];
-            philox4x32_10((uint32_t)gid, (uint32_t)eabs, (uint32_t)t, (uint32_t)i | (STREAM_ACT << 16), k0, k1, x);
-            u = u53(x[0], x[1]);
-            ra = (int)(((uint64_t)x[2] * (uint64_t)s->actions) >> 32);
+            philox4x32_10((uint32_t)gid, (uint32_t)eabs, (uint32_t)t, (uint32_t)(i >> 1) | (STREAM_ACT << 16), k0, k1, x);
+            u = (double)x[2 * (i & 1)] * (1.0 / 4294967296.0);
+            ra = (int)(((uint64_t)x[2 * (i & 1) + 1] * (uint64_t)s->actions) >> 32);
           }
           if (u < eps[i]) {
             k = ra;

@@ -11,6 +11,17 @@ from th_rl_b200 import abi
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["auto", "generic"], autouse=True)
+def kernel_choice(request, monkeypatch):
+    """Every test runs twice: with the default dispatch (specialised 2-agent kernel where it applies) and with the
+    general kernel forced, so both kernels are held to the same bar."""
+    if request.param == "generic":
+        monkeypatch.setenv("THRL_KERNEL", "generic")
+    else:
+        monkeypatch.delenv("THRL_KERNEL", raising=False)
+    return request.param
+
+
 def _mods():
     import torch
     from oracle import oracle

@@ -5,11 +5,19 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <math.h>
+#include <stdlib.h>
+
+#include <array>
 #include <atomic>
+#include <map>
+#include <memory>
+#include <set>
 #include <vector>
 
 #include "thrl_device.cuh"
 #include "thrl_scan_generic.cuh"
+#include "thrl_scan_lut2.cuh"
 #include "thrl_aux_kernels.cuh"
 
 namespace {
@@ -138,6 +146,120 @@ int launch_generic(thrl::ScanParams& p, const DeviceInfo& dev, cudaStream_t stre
   return THRL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ LUT2 planning
+// Host restatement of the per-joint-action price and its encodes; compiled with -ffp-contract=off, every operation is
+// the same IEEE operation the device (and the reference) performs.
+double h_scale(int k, int actions, double lo, double hi) {
+  double d = (double)k / ((double)actions - 1.0);
+  d = d * (hi - lo);
+  return d + lo;
+}
+int h_act_row(double price, double max_state, int states) {
+  float x = (float)price / (float)max_state;
+  x = x * (float)states;
+  return (int)rintf(x);
+}
+int h_upd_row(double price, double max_state, int states) {
+  double x = price / max_state;
+  x = x * (double)states;
+  return (int)rint(x);
+}
+
+// Returns true and fills p (structure + layout) when the specialised kernel applies; *warps = runs resident per CTA.
+bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int* warps) {
+  const ThrlGame& G = p->game;
+  if (G.n_agents != 2 || noisy || !G.regular) return false;
+  const int A0 = G.agent[0].actions, A1 = G.agent[1].actions, T = G.max_steps;
+  if (A0 > 255 || A1 > 255 || A0 * A1 > thrl::kLut2MaxJoint || T > 32767) return false;
+  const int J = A0 * A1;
+  const double ab = G.a / G.b;
+  std::map<std::array<int, 4>, int> ids;
+  std::vector<std::array<int, 4>> tuples;
+  std::vector<int> state_of(J);
+  for (int j = 0; j < J; ++j) {
+    const int k0 = j / A1, k1 = j % A1;
+    const double aq0 = ab * h_scale(k0, A0, G.agent[0].action_lo, G.agent[0].action_hi);
+    const double aq1 = ab * h_scale(k1, A1, G.agent[1].action_lo, G.agent[1].action_hi);
+    double Q = 0.0 + aq0;
+    Q = Q + aq1;
+    const double pn = G.a - G.b * Q;
+    const double price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
+    if (price != price) return false;
+    std::array<int, 4> t = {h_act_row(price, G.agent[0].max_state, G.agent[0].states),
+                            h_upd_row(price, G.agent[0].max_state, G.agent[0].states),
+                            h_act_row(price, G.agent[1].max_state, G.agent[1].states),
+                            h_upd_row(price, G.agent[1].max_state, G.agent[1].states)};
+    auto it = ids.find(t);
+    if (it == ids.end()) {
+      it = ids.emplace(t, (int)tuples.size()).first;
+      tuples.push_back(t);
+    }
+    state_of[j] = it->second;
+  }
+  const int NS = (int)tuples.size();
+  if (NS > thrl::kLut2MaxStates) return false;
+  std::set<int> rows[2];
+  for (auto& t : tuples) { rows[0].insert(t[0]); rows[0].insert(t[1]); rows[1].insert(t[2]); rows[1].insert(t[3]); }
+  std::map<int, int> cidx[2];
+  for (int a = 0; a < 2; ++a) {
+    if ((int)rows[a].size() > thrl::kLut2MaxRows) return false;
+    int c = 0;
+    for (int row : rows[a]) {
+      if (row < 0 || row > G.agent[a].states) return false;
+      p->row_list[a][c] = (uint16_t)row;
+      cidx[a][row] = c++;
+    }
+    p->NR[a] = c;
+    const ThrlAgentSpec& s = G.agent[a];
+    p->L[a] = s.min_memory > s.capacity ? 0 : (T < s.capacity ? T : s.capacity);
+  }
+  p->J = J;
+  p->NS = NS;
+  for (int j = 0; j < J; ++j) p->next_state[j] = (uint8_t)state_of[j];
+  for (int s = 0; s < NS; ++s) {
+    const auto& t = tuples[s];
+    p->state_rows[s] = (uint32_t)cidx[0][t[0]] | ((uint32_t)cidx[0][t[1]] << 8) | ((uint32_t)cidx[1][t[2]] << 16) |
+                       ((uint32_t)cidx[1][t[3]] << 24);
+  }
+  // shared-memory layout
+  int o = 0;
+  p->off_next = o;    o += align_up(J, 16);
+  p->off_rowlist = o; o += align_up(2 * (p->NR[0] + p->NR[1]), 16);
+  p->off_lutr = o;    o += J * 16;
+  p->off_lutlog = o;  o += J * 32;
+  p->cta_bytes = o;
+  o = align_up((p->NR[0] + 2) * A0 * (int)elem, 16);
+  p->off_tab1 = o;    o += align_up((p->NR[1] + 2) * A1 * (int)elem, 16);
+  p->off_grow = o;    o += align_up(p->NR[0] + p->NR[1] + 4, 16);
+  p->off_rows = o;    o += align_up((NS + 1) * 4, 16);
+  p->off_gj = o;      o += align_up((NS + 1) * 4, 16);
+  p->off_seq = o;     o += align_up(T + 1, 16);
+  p->off_rec = o;     o += align_up(2 * T, 16);
+  p->off_scr = o;     o += align_up(2 * T * 4, 16) + 2 * T * 16;
+  p->warp_bytes = o;
+  const int w = (smem_optin - p->cta_bytes) / p->warp_bytes;
+  if (w < 2) return false;
+  *warps = w > thrl::kLut2MaxWarps ? thrl::kLut2MaxWarps : w;
+  return true;
+}
+
+template <typename QT>
+int launch_lut2(thrl::Lut2Params& p, int warps, const DeviceInfo& dev, cudaStream_t stream) {
+  int grid = dev.sms;
+  const long long needed_ctas = (p.n_runs + warps - 1) / warps;
+  if (needed_ctas < grid) {
+    warps = (int)((p.n_runs + dev.sms - 1) / dev.sms);
+    if (warps < 1) warps = 1;
+    grid = (int)((p.n_runs + warps - 1) / warps);
+  }
+  const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
+  CUDA_TRY(cudaFuncSetAttribute(thrl::qtable_scan_lut2<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  thrl::qtable_scan_lut2<QT><<<grid, warps * 32, smem, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return THRL_OK;
+}
+
 int check_args(const ThrlScanArgs* a) {
   if (!a || !a->game) return fail(THRL_ERR_BAD_ARGS, "args/game is NULL");
   if (a->n_runs < 0 || a->epoch_end < a->epoch_begin) return fail(THRL_ERR_BAD_ARGS, "negative run or epoch count");
@@ -195,6 +317,26 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
   p.Hp = (p.game.ring_len > 0 ? p.game.ring_len : 1) + 1;
   p.noisy = (a->rng_mode == THRL_RNG_PHILOX) ? (p.game.noise_prob > 0.0) : (a->replay_new_a != nullptr);
   cudaStream_t stream = (cudaStream_t)stream_;
+  // Kernel choice.  THRL_KERNEL=generic|lut2 forces one (tests exercise both); default: lut2 whenever it applies.
+  const char* force = getenv("THRL_KERNEL");
+  const bool want_generic = force && strcmp(force, "generic") == 0;
+  if (!want_generic) {
+    thrl::Lut2Params* l = new thrl::Lut2Params();
+    std::unique_ptr<thrl::Lut2Params> hold(l);
+    l->game = p.game;
+    int warps = 0;
+    if (plan_lut2(l, p.noisy != 0, a->table_dtype == THRL_F64 ? 8 : 4, dev.smem_optin, &warps)) {
+      l->n_runs = p.n_runs; l->run_id0 = p.run_id0; l->epoch_begin = p.epoch_begin; l->E = p.E; l->rng_mode = p.rng_mode;
+      l->k0 = p.k0; l->k1 = p.k1;
+      l->q = p.q; l->counter = p.counter; l->eps = p.eps; l->price = p.price; l->hp = p.hp;
+      l->replay_u = p.replay_u; l->replay_ra = p.replay_ra;
+      l->rewards_log = p.rewards_log; l->actions_log = p.actions_log; l->n_log_runs = p.n_log_runs; l->stats = p.stats;
+      l->trace_actions = p.trace_actions; l->trace_rewards = p.trace_rewards; l->trace_prices = p.trace_prices;
+      return a->table_dtype == THRL_F64 ? launch_lut2<double>(*l, warps, dev, stream) : launch_lut2<float>(*l, warps, dev, stream);
+    }
+    if (force && strcmp(force, "lut2") == 0)
+      return fail(THRL_ERR_UNSUPPORTED, "THRL_KERNEL=lut2 but the game is not a 2-agent noise-free regular game that fits");
+  }
   return a->table_dtype == THRL_F64 ? launch_generic<double>(p, dev, stream) : launch_generic<float>(p, dev, stream);
 }
 

@@ -12,6 +12,7 @@
 namespace thrl {
 
 constexpr unsigned kFull = 0xffffffffu;
+__host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 
 // ---------------------------------------------------------------- Philox4x32-10 (DESIGN.md "Philox streams")
 enum : uint32_t { kStreamAct = 0, kStreamEnv = 1, kStreamInitQ = 2, kStreamInitP = 3 };
@@ -36,6 +37,9 @@ __device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
   const unsigned long long m = ((unsigned long long)hi << 21) | (unsigned long long)(lo >> 11);
   return __dmul_rn(__ull2double_rn(m), 1.0 / 9007199254740992.0);
 }
+
+// 32-bit uniform in [0,1) for the exploration test (exact: integer < 2^32 times 2^-32)
+__device__ __forceinline__ double u32_unit(uint32_t x) { return __dmul_rn((double)x, 1.0 / 4294967296.0); }
 
 // ---------------------------------------------------------------- state encodes (th_rl/agents.py:47-49)
 // float32 encode of the state handed to sample_action (trainer.py:53): rint_f32(f32(p) / f32(max_state) * f32(states))

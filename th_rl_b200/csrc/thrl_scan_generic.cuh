@@ -170,9 +170,9 @@ __global__ void __launch_bounds__(1024, 1) qtable_scan_generic(const __grid_cons
           v = u < hpw[i * 5 + 4] ? p.replay_ra[step0 * n + idx] : -1;  // agents.py:81
         } else {
           uint32_t x[4];
-          philox4x32_10(gid, eabs, (uint32_t)t, (uint32_t)i | (kStreamAct << 16), p.k0, p.k1, x);
-          const double u = u53(x[0], x[1]);
-          const int ra = (int)__umulhi(x[2], (uint32_t)G.agent[i].actions);
+          philox4x32_10(gid, eabs, (uint32_t)t, (uint32_t)(i >> 1) | (kStreamAct << 16), p.k0, p.k1, x);
+          const double u = u32_unit(x[2 * (i & 1)]);
+          const int ra = (int)__umulhi(x[2 * (i & 1) + 1], (uint32_t)G.agent[i].actions);
           v = u < hpw[i * 5 + 4] ? ra : -1;
         }
         pre[idx] = (int16_t)v;

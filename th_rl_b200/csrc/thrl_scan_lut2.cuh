@@ -1,0 +1,388 @@
+// thrl_scan_lut2.cuh — the headline kernel: 2 QTable agents, noise-free demand, tables resident in shared memory.
+//
+// With noise_prob == 0 the environment step (th_rl/environments.py:25-39) is a pure function of the joint action
+// (k0,k1): the next price, both rewards and every encode of that price (agents.py:47-49, f32 for acting, f64 for the
+// update) are fixed per joint action.  The host groups joint actions by the encodes of their price into NS "states"
+// (41 for the example config) and lists, per agent, the table rows those states can ever address (the *compact rows*);
+// only those rows (plus the rows of the call's initial price) are staged in shared memory, which more than doubles the
+// number of runs resident per SM.  The f64 lookup values themselves (rewards, reward/T, action/T) are computed by every
+// CTA in its prologue with the reference's own formulas.
+//
+// One warp = one run; per epoch:
+//   A  draws      lane-parallel Philox (or replay streams) -> per-step forced actions (epsilon is frozen in an episode)
+//   B  rollout    sequential: state -> greedy pair (cached per state) -> forced override -> joint action -> next state
+//   C  pre-pass   lane-parallel: stale snapshot (agents.py:67), rewards, cell/row addresses, visit counters (RED)
+//   D  update     sequential (agents.py:68-76), both agents' chains interleaved; row max = 1 LDS + 1 CREDUX.MAX
+//   E  refresh    greedy cache of the rows that were written; epsilon decay; logs / statistics
+#pragma once
+#include "thrl_device.cuh"
+
+namespace thrl {
+
+constexpr int kLut2MaxJoint = 1024;  // A0*A1
+constexpr int kLut2MaxStates = 254;  // distinct (encode) states; 255 = the call's initial state at most
+constexpr int kLut2MaxRows = 253;    // compact rows per agent (+2 slots for the initial price's rows)
+
+struct Lut2Params {
+  ThrlGame game;
+  long long n_runs, run_id0;
+  int epoch_begin, E, rng_mode;
+  uint32_t k0, k1;
+  void* q;
+  uint32_t* counter;
+  double* eps;
+  double* price;
+  const double* hp;
+  const double* replay_u;
+  const int32_t* replay_ra;
+  double* rewards_log;
+  double* actions_log;
+  long long n_log_runs;
+  long long* stats;
+  int32_t* trace_actions;
+  double* trace_rewards;
+  double* trace_prices;
+  // host-built structure of the deterministic game
+  int J, NS, NR[2], L[2];             // joint actions, states, compact rows per agent, batch length per agent (0 = never fires)
+  uint8_t next_state[kLut2MaxJoint];  // joint action -> state
+  uint32_t state_rows[kLut2MaxStates];  // state -> compact rows: act0 | upd0<<8 | act1<<16 | upd1<<24
+  uint16_t row_list[2][kLut2MaxRows + 3];  // compact row -> table row
+  // shared-memory layout
+  int cta_bytes, warp_bytes;
+  int off_next, off_rowlist, off_lutr, off_lutlog;  // CTA-shared
+  int off_tab1, off_grow, off_rows, off_gj, off_seq, off_rec, off_scr;  // per warp (tables of agent 0 at 0)
+};
+
+template <typename QT>
+__device__ __forceinline__ QT lut2_row_max(const QT* row, int A, int lane, bool in0) {
+  QT m = in0 ? row[lane] : NegInf<QT>::v();
+  if (A > 32) {
+    for (int k = lane + 32; k < A; k += 32) { const QT v = row[k]; m = v > m ? v : m; }
+  }
+  return warp_max(m);
+}
+
+constexpr int kLut2MaxWarps = 24;
+
+template <typename QT>
+__global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const __grid_constant__ Lut2Params p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ThrlGame& G = p.game;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+  const int T = G.max_steps, E = p.E, J = p.J, NS = p.NS;
+  const int A0 = G.agent[0].actions, A1 = G.agent[1].actions;
+  const int NR0 = p.NR[0], NR1 = p.NR[1];
+
+  // ---------------------------------------------------------------- CTA-shared lookup tables
+  uint8_t* nextS = smem + p.off_next;
+  uint16_t* rowlist = reinterpret_cast<uint16_t*>(smem + p.off_rowlist);  // [2][kLut2MaxRows+3] -> packed [NR0+2][NR1+2]
+  double* lutR = reinterpret_cast<double*>(smem + p.off_lutr);            // [J][2] reward (environments.py:34)
+  double* lutLog = reinterpret_cast<double*>(smem + p.off_lutlog);        // [J][4] r0/T, r1/T, x0/T, x1/T (trainer.py:65-66)
+  {
+    const double ab = __ddiv_rn(G.a, G.b);
+    for (int j = threadIdx.x; j < J; j += blockDim.x) {
+      const int k0 = j / A1, k1 = j - k0 * A1;
+      const double x0 = scale_action(k0, A0, G.agent[0].action_lo, G.agent[0].action_hi);
+      const double x1 = scale_action(k1, A1, G.agent[1].action_lo, G.agent[1].action_hi);
+      const double aq0 = __dmul_rn(ab, x0), aq1 = __dmul_rn(ab, x1);
+      const double Q = __dadd_rn(__dadd_rn(0.0, aq0), aq1);
+      const double pn = __dsub_rn(G.a, __dmul_rn(G.b, Q));
+      const double price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
+      const double r0 = __dmul_rn(price, aq0), r1 = __dmul_rn(price, aq1);
+      lutR[2 * j] = r0;
+      lutR[2 * j + 1] = r1;
+      lutLog[4 * j + 0] = __ddiv_rn(r0, (double)T);
+      lutLog[4 * j + 1] = __ddiv_rn(r1, (double)T);
+      lutLog[4 * j + 2] = __ddiv_rn(x0, (double)T);
+      lutLog[4 * j + 3] = __ddiv_rn(x1, (double)T);
+      nextS[j] = p.next_state[j];
+    }
+    for (int c = threadIdx.x; c < NR0 + NR1; c += blockDim.x)
+      rowlist[c] = c < NR0 ? p.row_list[0][c] : p.row_list[1][c - NR0];
+  }
+  __syncthreads();
+
+  // ---------------------------------------------------------------- this warp's slot
+  unsigned char* slot = smem + p.cta_bytes + (size_t)warp * p.warp_bytes;
+  QT* tab0 = reinterpret_cast<QT*>(slot);
+  QT* tab1 = reinterpret_cast<QT*>(slot + p.off_tab1);
+  uint8_t* grow = slot + p.off_grow;                                // greedy action per compact row: [NR0+2][NR1+2]
+  uint32_t* rowsW = reinterpret_cast<uint32_t*>(slot + p.off_rows);  // [NS+1] state -> compact rows (entry NS = initial state)
+  uint32_t* GJ = reinterpret_cast<uint32_t*>(slot + p.off_gj);       // [NS+1] state -> greedy g0 | g1<<8
+  uint8_t* seq = slot + p.off_seq;                                   // [T+1] state before step t
+  uint16_t* rec = reinterpret_cast<uint16_t*>(slot + p.off_rec);     // [T] k0 | k1<<8
+  uint16_t* pre = reinterpret_cast<uint16_t*>(slot + p.off_scr);     // [T] forced k0 | k1<<8, 0xFF = greedy      (phases A-B)
+  uint32_t* meta = reinterpret_cast<uint32_t*>(slot + p.off_scr);    // [2][T] cell | next-row offset << 16        (phases C-D)
+  double2* rc = reinterpret_cast<double2*>(slot + p.off_scr + align16(2 * T * 4));  // [2][T] (reward, (1-alpha)*old)
+
+  const bool in0 = lane < A0, in1 = lane < A1;
+  const int L0 = p.L[0], L1 = p.L[1];
+
+  const long long total_warps = (long long)gridDim.x * warps_per_cta;
+  for (long long r = (long long)blockIdx.x * warps_per_cta + warp; r < p.n_runs; r += total_warps) {
+    QT* qg0 = reinterpret_cast<QT*>(p.q) + r * G.run_stride;
+    QT* qg1 = qg0 + G.agent[1].table_offset;
+    uint32_t* cnt0 = p.counter ? p.counter + r * G.run_stride : nullptr;
+    uint32_t* cnt1 = cnt0 ? cnt0 + G.agent[1].table_offset : nullptr;
+    const uint32_t gid = (uint32_t)(p.run_id0 + r);
+    double alpha0, gamma0, epsend0, epsstep0, alpha1, gamma1, epsend1, epsstep1;
+    if (p.hp) {
+      const double* h = p.hp + r * 8;
+      alpha0 = h[0]; gamma0 = h[1]; epsend0 = h[2]; epsstep0 = h[3];
+      alpha1 = h[4]; gamma1 = h[5]; epsend1 = h[6]; epsstep1 = h[7];
+    } else {
+      alpha0 = G.agent[0].alpha; gamma0 = G.agent[0].gamma; epsend0 = G.agent[0].eps_end; epsstep0 = G.agent[0].eps_step;
+      alpha1 = G.agent[1].alpha; gamma1 = G.agent[1].gamma; epsend1 = G.agent[1].eps_end; epsstep1 = G.agent[1].eps_step;
+    }
+    const double oma0 = __dsub_rn(1.0, alpha0), oma1 = __dsub_rn(1.0, alpha1);
+    double eps0 = p.eps[r * 2], eps1 = p.eps[r * 2 + 1];
+    const double price_in = p.price[r];
+
+    // ---- the call's initial state: rows of the incoming price, aliased to a compact row when it is one
+    int init_c[4];  // act0, upd0, act1, upd1 compact indices
+    int extra_row0[2] = {-1, -1}, extra_row1[2] = {-1, -1};  // table rows staged in the two extra slots
+    {
+      const int tr[4] = {act_row(price_in, (float)G.agent[0].max_state, (float)G.agent[0].states),
+                         upd_row(price_in, G.agent[0].max_state, (double)G.agent[0].states),
+                         act_row(price_in, (float)G.agent[1].max_state, (float)G.agent[1].states),
+                         upd_row(price_in, G.agent[1].max_state, (double)G.agent[1].states)};
+#pragma unroll
+      for (int w = 0; w < 4; ++w) {
+        const int ag = w >> 1, NRa = ag ? NR1 : NR0;
+        const uint16_t* rl = rowlist + (ag ? NR0 : 0);
+        unsigned found = 0;
+        int base = 0;
+        for (int c0 = 0; c0 < NRa && !found; c0 += 32) {
+          const int c = c0 + lane;
+          found = __ballot_sync(kFull, c < NRa && rl[c] == tr[w]);
+          base = c0;
+        }
+        int ci;
+        if (found) {
+          ci = base + __ffs(found) - 1;
+        } else if ((w & 1) && tr[w] == tr[w - 1] && init_c[w - 1] >= NRa) {
+          ci = init_c[w - 1];  // update row == act row, already in the first extra slot
+        } else {
+          ci = NRa + (w & 1);
+          if (ag) extra_row1[w & 1] = tr[w]; else extra_row0[w & 1] = tr[w];
+        }
+        init_c[w] = ci;
+      }
+    }
+
+    // ---- stage compact rows (plus extra rows) into shared memory, build the caches
+    for (int c = 0; c < NR0 + 2; ++c) {
+      const int row = c < NR0 ? rowlist[c] : extra_row0[c - NR0];
+      if (row >= 0) for (int k = lane; k < A0; k += 32) tab0[c * A0 + k] = qg0[(size_t)row * A0 + k];
+    }
+    for (int c = 0; c < NR1 + 2; ++c) {
+      const int row = c < NR1 ? rowlist[NR0 + c] : extra_row1[c - NR1];
+      if (row >= 0) for (int k = lane; k < A1; k += 32) tab1[c * A1 + k] = qg1[(size_t)row * A1 + k];
+    }
+    for (int s = lane; s < NS; s += 32) rowsW[s] = p.state_rows[s];
+    if (lane == 0) rowsW[NS] = (uint32_t)init_c[0] | ((uint32_t)init_c[1] << 8) | ((uint32_t)init_c[2] << 16) | ((uint32_t)init_c[3] << 24);
+    __syncwarp();
+    for (int c = 0; c < NR0 + 2; ++c) {
+      if (c < NR0 || extra_row0[c - NR0] >= 0) {
+        const int g = row_argmax(tab0 + c * A0, A0, lane);
+        if (lane == 0) grow[c] = (uint8_t)g;
+      }
+    }
+    for (int c = 0; c < NR1 + 2; ++c) {
+      if (c < NR1 || extra_row1[c - NR1] >= 0) {
+        const int g = row_argmax(tab1 + c * A1, A1, lane);
+        if (lane == 0) grow[NR0 + 2 + c] = (uint8_t)g;
+      }
+    }
+    __syncwarp();
+    for (int s = lane; s <= NS; s += 32) {
+      const uint32_t rw = rowsW[s];
+      GJ[s] = (uint32_t)grow[rw & 0xff] | ((uint32_t)grow[NR0 + 2 + ((rw >> 16) & 0xff)] << 8);
+    }
+    __syncwarp();
+
+    int sigma = NS;
+    int last_k = -1;  // k0 | k1<<8 of the most recent step (for the outgoing price)
+
+    for (int e = 0; e < E; ++e) {
+      const uint32_t eabs = (uint32_t)(p.epoch_begin + e);
+      const long long step0 = (r * E + e) * (long long)T;
+
+      // ---- A: draws (agents.py:81-82), lane-parallel over the steps of the episode
+      for (int t = lane; t < T; t += 32) {
+        int f0, f1;
+        if (p.rng_mode == THRL_RNG_REPLAY_ACTIONS) {
+          const int2 v = *reinterpret_cast<const int2*>(p.replay_ra + (step0 + t) * 2);
+          f0 = v.x; f1 = v.y;
+        } else if (p.rng_mode == THRL_RNG_REPLAY_DRAWS) {
+          const double2 u = *reinterpret_cast<const double2*>(p.replay_u + (step0 + t) * 2);
+          const int2 v = *reinterpret_cast<const int2*>(p.replay_ra + (step0 + t) * 2);
+          f0 = u.x < eps0 ? v.x : -1;
+          f1 = u.y < eps1 ? v.y : -1;
+        } else {
+          uint32_t x[4];
+          philox4x32_10(gid, eabs, (uint32_t)t, kStreamAct << 16, p.k0, p.k1, x);
+          f0 = u32_unit(x[0]) < eps0 ? (int)__umulhi(x[1], (uint32_t)A0) : -1;
+          f1 = u32_unit(x[2]) < eps1 ? (int)__umulhi(x[3], (uint32_t)A1) : -1;
+        }
+        pre[t] = (uint16_t)((f0 < 0 ? 0xFF : f0) | ((f1 < 0 ? 0xFF : f1) << 8));
+      }
+      __syncwarp();
+
+      // ---- B: the episode (trainer.py:50-67).  Lanes 0..3 carry the four log accumulators (trainer.py:65-66).
+      double acc = 0.0;
+      const int acc_lane = lane & 3;
+#pragma unroll 4
+      for (int t = 0; t < T; ++t) {
+        const uint32_t f = pre[t];
+        const uint32_t gj = GJ[sigma];
+        const uint32_t f0 = f & 0xff, f1 = f >> 8;
+        const uint32_t k0 = f0 == 0xff ? (gj & 0xff) : f0;
+        const uint32_t k1 = f1 == 0xff ? (gj >> 8) : f1;
+        const int joint = (int)(k0 * (uint32_t)A1 + k1);
+        if (lane == 0) {
+          seq[t] = (uint8_t)sigma;
+          rec[t] = (uint16_t)(k0 | (k1 << 8));
+        }
+        acc = __dadd_rn(acc, lutLog[4 * joint + acc_lane]);
+        sigma = nextS[joint];
+        last_k = (int)(k0 | (k1 << 8));
+      }
+      if (lane == 0) seq[T] = (uint8_t)sigma;
+      __syncwarp();
+
+      // optional per-step traces (parity runs only), lane-parallel
+      if (p.trace_actions || p.trace_rewards || p.trace_prices) {
+        const double ab = __ddiv_rn(G.a, G.b);
+        for (int t = lane; t < T; t += 32) {
+          const int k0 = rec[t] & 0xff, k1 = rec[t] >> 8, joint = k0 * A1 + k1;
+          if (p.trace_actions) { p.trace_actions[(step0 + t) * 2] = k0; p.trace_actions[(step0 + t) * 2 + 1] = k1; }
+          if (p.trace_rewards) { p.trace_rewards[(step0 + t) * 2] = lutR[2 * joint]; p.trace_rewards[(step0 + t) * 2 + 1] = lutR[2 * joint + 1]; }
+          if (p.trace_prices) {
+            const double aq0 = __dmul_rn(ab, scale_action(k0, A0, G.agent[0].action_lo, G.agent[0].action_hi));
+            const double aq1 = __dmul_rn(ab, scale_action(k1, A1, G.agent[1].action_lo, G.agent[1].action_hi));
+            const double pn = __dsub_rn(G.a, __dmul_rn(G.b, __dadd_rn(__dadd_rn(0.0, aq0), aq1)));
+            p.trace_prices[step0 + t] = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
+          }
+        }
+      }
+
+      // ---- C: pre-pass over the batch = the newest L_i transitions of the episode (buffers.py:12, agents.py:61-67)
+      unsigned dirty0[2] = {0, 0}, dirty1[2] = {0, 0};  // written compact rows (bit c of word c>>5 ... up to 64 rows tracked)
+      bool dirty_all0 = false, dirty_all1 = false;
+      for (int j = T - L0 + lane; j < T; j += 32) {
+        const uint32_t rw = rowsW[seq[j]], rn = rowsW[seq[j + 1]];
+        const int k = rec[j] & 0xff, joint = k * A1 + (rec[j] >> 8);
+        const int cu = (rw >> 8) & 0xff, cn = (rn >> 8) & 0xff;
+        const int cell = cu * A0 + k;
+        const int jj = j - (T - L0);
+        meta[jj] = (uint32_t)cell | ((uint32_t)(cn * A0) << 16);
+        rc[jj] = make_double2(lutR[2 * joint], __dmul_rn(oma0, (double)tab0[cell]));
+        if (cnt0) atomicAdd(cnt0 + (size_t)(cu < NR0 ? rowlist[cu] : extra_row0[cu - NR0]) * A0 + k, 1u);  // agents.py:76
+        if (cu < 64) dirty0[cu >> 5] |= 1u << (cu & 31); else dirty_all0 = true;
+      }
+      for (int j = T - L1 + lane; j < T; j += 32) {
+        const uint32_t rw = rowsW[seq[j]], rn = rowsW[seq[j + 1]];
+        const int k = rec[j] >> 8, joint = (rec[j] & 0xff) * A1 + k;
+        const int cu = rw >> 24, cn = rn >> 24;
+        const int cell = cu * A1 + k;
+        const int jj = j - (T - L1);
+        meta[T + jj] = (uint32_t)cell | ((uint32_t)(cn * A1) << 16);
+        rc[T + jj] = make_double2(lutR[2 * joint + 1], __dmul_rn(oma1, (double)tab1[cell]));
+        if (cnt1) atomicAdd(cnt1 + (size_t)(cu < NR1 ? rowlist[NR0 + cu] : extra_row1[cu - NR1]) * A1 + k, 1u);
+        if (cu < 64) dirty1[cu >> 5] |= 1u << (cu & 31); else dirty_all1 = true;
+      }
+      __syncwarp();
+
+      // ---- D: the sequential pass (agents.py:68-76), the two agents' dependency chains interleaved
+      auto upd = [&](QT* tab, int A, bool in, const uint32_t m, const double2 v, double alpha, double gamma) {
+        const double next_max = (double)lut2_row_max(tab + (m >> 16), A, lane, in);  // live table (:71)
+        const double nv = __dadd_rn(v.y, __dmul_rn(alpha, __dadd_rn(v.x, __dmul_rn(gamma, next_max))));  // :72-74
+        if (lane == 0) tab[m & 0xffff] = (QT)nv;                                                          // :75
+      };
+      if (L0 == L1) {
+#pragma unroll 2
+        for (int j = 0; j < L0; ++j) {
+          const uint32_t m0 = meta[j], m1 = meta[T + j];
+          const double2 v0 = rc[j], v1 = rc[T + j];
+          upd(tab0, A0, in0, m0, v0, alpha0, gamma0);
+          upd(tab1, A1, in1, m1, v1, alpha1, gamma1);
+          __syncwarp();
+        }
+      } else {
+        for (int j = 0; j < L0; ++j) { upd(tab0, A0, in0, meta[j], rc[j], alpha0, gamma0); __syncwarp(); }
+        for (int j = 0; j < L1; ++j) { upd(tab1, A1, in1, meta[T + j], rc[T + j], alpha1, gamma1); __syncwarp(); }
+      }
+
+      // ---- E: refresh the greedy cache of written rows, then the per-state greedy pairs
+      {
+        unsigned w0 = __reduce_or_sync(kFull, dirty0[0]), w1 = __reduce_or_sync(kFull, dirty0[1]);
+        if (__any_sync(kFull, dirty_all0)) {
+          for (int c = 64; c < NR0 + 2; ++c) { const int g = row_argmax(tab0 + c * A0, A0, lane); if (lane == 0) grow[c] = (uint8_t)g; }
+        }
+        while (w0 | w1) {
+          const int c = w0 ? __ffs(w0) - 1 : 32 + __ffs(w1) - 1;
+          if (w0) w0 &= w0 - 1; else w1 &= w1 - 1;
+          const int g = row_argmax(tab0 + c * A0, A0, lane);
+          if (lane == 0) grow[c] = (uint8_t)g;
+        }
+        w0 = __reduce_or_sync(kFull, dirty1[0]); w1 = __reduce_or_sync(kFull, dirty1[1]);
+        if (__any_sync(kFull, dirty_all1)) {
+          for (int c = 64; c < NR1 + 2; ++c) { const int g = row_argmax(tab1 + c * A1, A1, lane); if (lane == 0) grow[NR0 + 2 + c] = (uint8_t)g; }
+        }
+        while (w0 | w1) {
+          const int c = w0 ? __ffs(w0) - 1 : 32 + __ffs(w1) - 1;
+          if (w0) w0 &= w0 - 1; else w1 &= w1 - 1;
+          const int g = row_argmax(tab1 + c * A1, A1, lane);
+          if (lane == 0) grow[NR0 + 2 + c] = (uint8_t)g;
+        }
+        __syncwarp();
+        for (int s = lane; s <= NS; s += 32) {
+          const uint32_t rw = rowsW[s];
+          GJ[s] = (uint32_t)grow[rw & 0xff] | ((uint32_t)grow[NR0 + 2 + ((rw >> 16) & 0xff)] << 8);
+        }
+      }
+      // epsilon decay, every epoch (agents.py:78)
+      eps0 = __dadd_rn(epsend0, __dmul_rn(__dsub_rn(eps0, epsend0), epsstep0));
+      eps1 = __dadd_rn(epsend1, __dmul_rn(__dsub_rn(eps1, epsend1), epsstep1));
+      // logs and statistics: lane 0,1 = rewards_log[e, 0..1], lane 2,3 = actions_log[e, 0..1]
+      if (lane < 4) {
+        const int ag = lane & 1;
+        if (r < p.n_log_runs) {
+          double* dst = lane < 2 ? p.rewards_log : p.actions_log;
+          if (dst) dst[(r * E + e) * 2 + ag] = acc;
+        }
+        if (p.stats) {
+          unsigned long long* s4 = reinterpret_cast<unsigned long long*>(p.stats) + ((size_t)e * 2 + ag) * THRL_STATS_K + (lane < 2 ? 0 : 2);
+          atomicAdd(s4 + 0, (unsigned long long)fx_round(__dmul_rn(acc, THRL_STATS_SCALE_SUM)));
+          atomicAdd(s4 + 1, (unsigned long long)fx_round(__dmul_rn(__dmul_rn(acc, acc), THRL_STATS_SCALE_SQ)));
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- write the run back: only the staged rows can have changed
+    for (int c = 0; c < NR0 + 2; ++c) {
+      const int row = c < NR0 ? rowlist[c] : extra_row0[c - NR0];
+      if (row >= 0) for (int k = lane; k < A0; k += 32) qg0[(size_t)row * A0 + k] = tab0[c * A0 + k];
+    }
+    for (int c = 0; c < NR1 + 2; ++c) {
+      const int row = c < NR1 ? rowlist[NR0 + c] : extra_row1[c - NR1];
+      if (row >= 0) for (int k = lane; k < A1; k += 32) qg1[(size_t)row * A1 + k] = tab1[c * A1 + k];
+    }
+    if (lane == 0) {
+      p.eps[r * 2] = eps0;
+      p.eps[r * 2 + 1] = eps1;
+      if (last_k >= 0) {  // environments.py:36 self.state = price of the last step
+        const double ab = __ddiv_rn(G.a, G.b);
+        const double aq0 = __dmul_rn(ab, scale_action(last_k & 0xff, A0, G.agent[0].action_lo, G.agent[0].action_hi));
+        const double aq1 = __dmul_rn(ab, scale_action(last_k >> 8, A1, G.agent[1].action_lo, G.agent[1].action_hi));
+        const double pn = __dsub_rn(G.a, __dmul_rn(G.b, __dadd_rn(__dadd_rn(0.0, aq0), aq1)));
+        p.price[r] = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace thrl

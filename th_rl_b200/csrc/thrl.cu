@@ -223,7 +223,7 @@ bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int
   }
   // shared-memory layout
   int o = 0;
-  p->off_next = o;    o += align_up(J, 16);
+  p->off_next = o;    o += align_up(2 * J, 16);
   p->off_rowlist = o; o += align_up(2 * (p->NR[0] + p->NR[1]), 16);
   p->off_lutr = o;    o += J * 16;
   p->off_lutlog = o;  o += J * 32;
@@ -235,7 +235,7 @@ bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int
   p->off_gj = o;      o += align_up((NS + 1) * 4, 16);
   p->off_seq = o;     o += align_up(T + 1, 16);
   p->off_rec = o;     o += align_up(2 * T, 16);
-  p->off_scr = o;     o += align_up(2 * T * 4, 16) + 2 * T * 16;
+  p->off_scr = o;     o += align_up(2 * T * 8, 16) + 2 * T * 16;
   p->warp_bytes = o;
   const int w = (smem_optin - p->cta_bytes) / p->warp_bytes;
   if (w < 2) return false;
@@ -253,8 +253,10 @@ int launch_lut2(thrl::Lut2Params& p, int warps, const DeviceInfo& dev, cudaStrea
     grid = (int)((p.n_runs + warps - 1) / warps);
   }
   const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
-  CUDA_TRY(cudaFuncSetAttribute(thrl::qtable_scan_lut2<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  thrl::qtable_scan_lut2<QT><<<grid, warps * 32, smem, stream>>>(p);
+  const bool small = p.game.agent[0].actions <= 32 && p.game.agent[1].actions <= 32;
+  auto kern = small ? thrl::qtable_scan_lut2<QT, true> : thrl::qtable_scan_lut2<QT, false>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, warps * 32, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return THRL_OK;

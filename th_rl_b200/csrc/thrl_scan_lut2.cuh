@@ -53,29 +53,40 @@ struct Lut2Params {
   int off_tab1, off_grow, off_rows, off_gj, off_seq, off_rec, off_scr;  // per warp (tables of agent 0 at 0)
 };
 
-template <typename QT>
-__device__ __forceinline__ QT lut2_row_max(const QT* row, int A, int lane, bool in0) {
-  QT m = in0 ? row[lane] : NegInf<QT>::v();
-  if (A > 32) {
-    for (int k = lane + 32; k < A; k += 32) { const QT v = row[k]; m = v > m ? v : m; }
+constexpr int kLut2MaxWarps = 24;
+
+// Row max / first argmax with the column count known to be <= 32 at compile time (kSmallA): one LDS per lane.
+template <typename QT, bool kSmallA>
+__device__ __forceinline__ QT lut2_row_max(const QT* row_lane, int A, int lane, bool in) {
+  QT m = in ? row_lane[0] : NegInf<QT>::v();
+  if (!kSmallA) {
+    for (int k = lane + 32; k < A; k += 32) { const QT v = row_lane[k - lane]; m = v > m ? v : m; }
   }
   return warp_max(m);
 }
+template <typename QT, bool kSmallA>
+__device__ __forceinline__ int lut2_row_argmax(const QT* row, int A, int lane, bool in) {
+  if (!kSmallA) return row_argmax(row, A, lane);
+  const QT v = in ? row[lane] : NegInf<QT>::v();
+  const QT wm = warp_max(v);
+  return (int)__reduce_min_sync(kFull, (in && v == wm) ? (unsigned)lane : 0xffffffffu);
+}
 
-constexpr int kLut2MaxWarps = 24;
-
-template <typename QT>
+template <typename QT, bool kSmallA>
 __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const __grid_constant__ Lut2Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ThrlGame& G = p.game;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
+  const int warp = __shfl_sync(kFull, (int)(threadIdx.x >> 5), 0);  // provably warp-uniform
   const int T = G.max_steps, E = p.E, J = p.J, NS = p.NS;
   const int A0 = G.agent[0].actions, A1 = G.agent[1].actions;
   const int NR0 = p.NR[0], NR1 = p.NR[1];
+  const int rng_mode = p.rng_mode;
+  const uint32_t key0 = p.k0, key1 = p.k1;
 
   // ---------------------------------------------------------------- CTA-shared lookup tables
-  uint8_t* nextS = smem + p.off_next;
-  uint16_t* rowlist = reinterpret_cast<uint16_t*>(smem + p.off_rowlist);  // [2][kLut2MaxRows+3] -> packed [NR0+2][NR1+2]
+  uint16_t* nextS = reinterpret_cast<uint16_t*>(smem + p.off_next);  // joint action -> 4 * next state (byte offset into GJ)
+  uint16_t* rowlist = reinterpret_cast<uint16_t*>(smem + p.off_rowlist);  // compact row -> table row, [NR0][NR1]
   double* lutR = reinterpret_cast<double*>(smem + p.off_lutr);            // [J][2] reward (environments.py:34)
   double* lutLog = reinterpret_cast<double*>(smem + p.off_lutlog);        // [J][4] r0/T, r1/T, x0/T, x1/T (trainer.py:65-66)
   {
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
       lutLog[4 * j + 1] = __ddiv_rn(r1, (double)T);
       lutLog[4 * j + 2] = __ddiv_rn(x0, (double)T);
       lutLog[4 * j + 3] = __ddiv_rn(x1, (double)T);
-      nextS[j] = p.next_state[j];
+      nextS[j] = (uint16_t)(4u * p.next_state[j]);
     }
     for (int c = threadIdx.x; c < NR0 + NR1; c += blockDim.x)
       rowlist[c] = c < NR0 ? p.row_list[0][c] : p.row_list[1][c - NR0];
@@ -106,17 +117,22 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
   unsigned char* slot = smem + p.cta_bytes + (size_t)warp * p.warp_bytes;
   QT* tab0 = reinterpret_cast<QT*>(slot);
   QT* tab1 = reinterpret_cast<QT*>(slot + p.off_tab1);
-  uint8_t* grow = slot + p.off_grow;                                // greedy action per compact row: [NR0+2][NR1+2]
+  uint8_t* grow = slot + p.off_grow;                                 // greedy action per compact row: [NR0+2][NR1+2]
   uint32_t* rowsW = reinterpret_cast<uint32_t*>(slot + p.off_rows);  // [NS+1] state -> compact rows (entry NS = initial state)
-  uint32_t* GJ = reinterpret_cast<uint32_t*>(slot + p.off_gj);       // [NS+1] state -> greedy g0 | g1<<8
-  uint8_t* seq = slot + p.off_seq;                                   // [T+1] state before step t
+  unsigned char* GJb = slot + p.off_gj;                              // [NS+1] u32: state -> greedy g0 | g1<<8
+  uint32_t* GJ = reinterpret_cast<uint32_t*>(GJb);
   uint16_t* rec = reinterpret_cast<uint16_t*>(slot + p.off_rec);     // [T] k0 | k1<<8
-  uint16_t* pre = reinterpret_cast<uint16_t*>(slot + p.off_scr);     // [T] forced k0 | k1<<8, 0xFF = greedy      (phases A-B)
-  uint32_t* meta = reinterpret_cast<uint32_t*>(slot + p.off_scr);    // [2][T] cell | next-row offset << 16        (phases C-D)
-  double2* rc = reinterpret_cast<double2*>(slot + p.off_scr + align16(2 * T * 4));  // [2][T] (reward, (1-alpha)*old)
+  uint8_t* seq = slot + p.off_seq;                                   // [T+1] state before step t (rebuilt lane-parallel)
+  uint2* pre = reinterpret_cast<uint2*>(slot + p.off_scr);           // [T] (keep mask, forced value) byte pairs      (phases A-B)
+  uint2* meta = reinterpret_cast<uint2*>(slot + p.off_scr);          // [2][T] (next-row byte offset, cell byte offset) (phases C-D)
+  double2* rc = reinterpret_cast<double2*>(slot + p.off_scr + align16(2 * T * 8));  // [2][T] (reward, (1-alpha)*old)
 
   const bool in0 = lane < A0, in1 = lane < A1;
   const int L0 = p.L[0], L1 = p.L[1];
+  const uint32_t dp_b = (uint32_t)A1 | (1u << 8);  // joint = dp4a(k0 | k1<<8, A1 | 1<<8)
+  const double* lutLogLane = lutLog + (lane & 3);
+  const QT* tab0_lane = tab0 + lane;
+  const QT* tab1_lane = tab1 + lane;
 
   const long long total_warps = (long long)gridDim.x * warps_per_cta;
   for (long long r = (long long)blockIdx.x * warps_per_cta + warp; r < p.n_runs; r += total_warps) {
@@ -139,58 +155,54 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
     const double price_in = p.price[r];
 
     // ---- the call's initial state: rows of the incoming price, aliased to a compact row when it is one
-    int init_c[4];  // act0, upd0, act1, upd1 compact indices
-    int extra_row0[2] = {-1, -1}, extra_row1[2] = {-1, -1};  // table rows staged in the two extra slots
+    int init_c0, init_c1, init_c2, init_c3;            // act0, upd0, act1, upd1 compact indices
+    int xrow00 = -1, xrow01 = -1, xrow10 = -1, xrow11 = -1;  // table rows staged in the two extra slots of each agent
     {
-      const int tr[4] = {act_row(price_in, (float)G.agent[0].max_state, (float)G.agent[0].states),
-                         upd_row(price_in, G.agent[0].max_state, (double)G.agent[0].states),
-                         act_row(price_in, (float)G.agent[1].max_state, (float)G.agent[1].states),
-                         upd_row(price_in, G.agent[1].max_state, (double)G.agent[1].states)};
-#pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        const int ag = w >> 1, NRa = ag ? NR1 : NR0;
-        const uint16_t* rl = rowlist + (ag ? NR0 : 0);
-        unsigned found = 0;
-        int base = 0;
-        for (int c0 = 0; c0 < NRa && !found; c0 += 32) {
-          const int c = c0 + lane;
-          found = __ballot_sync(kFull, c < NRa && rl[c] == tr[w]);
-          base = c0;
+      auto find = [&](const uint16_t* rl, int NRa, int row) -> int {
+        int res = -1;
+        for (int c0 = 0; c0 < NRa; c0 += 32) {
+          const unsigned f = __ballot_sync(kFull, c0 + lane < NRa && rl[c0 + lane] == row);
+          if (f) { res = c0 + __ffs(f) - 1; break; }
         }
-        int ci;
-        if (found) {
-          ci = base + __ffs(found) - 1;
-        } else if ((w & 1) && tr[w] == tr[w - 1] && init_c[w - 1] >= NRa) {
-          ci = init_c[w - 1];  // update row == act row, already in the first extra slot
-        } else {
-          ci = NRa + (w & 1);
-          if (ag) extra_row1[w & 1] = tr[w]; else extra_row0[w & 1] = tr[w];
-        }
-        init_c[w] = ci;
-      }
+        return res;
+      };
+      const int ta0 = act_row(price_in, (float)G.agent[0].max_state, (float)G.agent[0].states);
+      const int tu0 = upd_row(price_in, G.agent[0].max_state, (double)G.agent[0].states);
+      const int ta1 = act_row(price_in, (float)G.agent[1].max_state, (float)G.agent[1].states);
+      const int tu1 = upd_row(price_in, G.agent[1].max_state, (double)G.agent[1].states);
+      init_c0 = find(rowlist, NR0, ta0);
+      if (init_c0 < 0) { init_c0 = NR0; xrow00 = ta0; }
+      init_c1 = find(rowlist, NR0, tu0);
+      if (init_c1 < 0) { if (tu0 == ta0) init_c1 = init_c0; else { init_c1 = NR0 + 1; xrow01 = tu0; } }
+      init_c2 = find(rowlist + NR0, NR1, ta1);
+      if (init_c2 < 0) { init_c2 = NR1; xrow10 = ta1; }
+      init_c3 = find(rowlist + NR0, NR1, tu1);
+      if (init_c3 < 0) { if (tu1 == ta1) init_c3 = init_c2; else { init_c3 = NR1 + 1; xrow11 = tu1; } }
     }
+    auto table_row0 = [&](int c) { return c < NR0 ? (int)rowlist[c] : (c == NR0 ? xrow00 : xrow01); };
+    auto table_row1 = [&](int c) { return c < NR1 ? (int)rowlist[NR0 + c] : (c == NR1 ? xrow10 : xrow11); };
 
     // ---- stage compact rows (plus extra rows) into shared memory, build the caches
     for (int c = 0; c < NR0 + 2; ++c) {
-      const int row = c < NR0 ? rowlist[c] : extra_row0[c - NR0];
+      const int row = table_row0(c);
       if (row >= 0) for (int k = lane; k < A0; k += 32) tab0[c * A0 + k] = qg0[(size_t)row * A0 + k];
     }
     for (int c = 0; c < NR1 + 2; ++c) {
-      const int row = c < NR1 ? rowlist[NR0 + c] : extra_row1[c - NR1];
+      const int row = table_row1(c);
       if (row >= 0) for (int k = lane; k < A1; k += 32) tab1[c * A1 + k] = qg1[(size_t)row * A1 + k];
     }
     for (int s = lane; s < NS; s += 32) rowsW[s] = p.state_rows[s];
-    if (lane == 0) rowsW[NS] = (uint32_t)init_c[0] | ((uint32_t)init_c[1] << 8) | ((uint32_t)init_c[2] << 16) | ((uint32_t)init_c[3] << 24);
+    if (lane == 0) rowsW[NS] = (uint32_t)init_c0 | ((uint32_t)init_c1 << 8) | ((uint32_t)init_c2 << 16) | ((uint32_t)init_c3 << 24);
     __syncwarp();
     for (int c = 0; c < NR0 + 2; ++c) {
-      if (c < NR0 || extra_row0[c - NR0] >= 0) {
-        const int g = row_argmax(tab0 + c * A0, A0, lane);
+      if (table_row0(c) >= 0) {
+        const int g = lut2_row_argmax<QT, kSmallA>(tab0 + c * A0, A0, lane, in0);
         if (lane == 0) grow[c] = (uint8_t)g;
       }
     }
     for (int c = 0; c < NR1 + 2; ++c) {
-      if (c < NR1 || extra_row1[c - NR1] >= 0) {
-        const int g = row_argmax(tab1 + c * A1, A1, lane);
+      if (table_row1(c) >= 0) {
+        const int g = lut2_row_argmax<QT, kSmallA>(tab1 + c * A1, A1, lane, in1);
         if (lane == 0) grow[NR0 + 2 + c] = (uint8_t)g;
       }
     }
@@ -201,54 +213,62 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
     }
     __syncwarp();
 
-    int sigma = NS;
-    int last_k = -1;  // k0 | k1<<8 of the most recent step (for the outgoing price)
+    uint32_t sig4 = 4u * (uint32_t)NS;  // 4 * current state
+    int last_k = -1;                    // k0 | k1<<8 of the most recent step (for the outgoing price)
 
     for (int e = 0; e < E; ++e) {
       const uint32_t eabs = (uint32_t)(p.epoch_begin + e);
       const long long step0 = (r * E + e) * (long long)T;
 
-      // ---- A: draws (agents.py:81-82), lane-parallel over the steps of the episode
+      // ---- A: draws (agents.py:81-82), lane-parallel over the steps of the episode.
+      //      pre[t] = (keep, forced): action pair = (greedy pair & keep) | forced
       for (int t = lane; t < T; t += 32) {
         int f0, f1;
-        if (p.rng_mode == THRL_RNG_REPLAY_ACTIONS) {
-          const int2 v = *reinterpret_cast<const int2*>(p.replay_ra + (step0 + t) * 2);
-          f0 = v.x; f1 = v.y;
-        } else if (p.rng_mode == THRL_RNG_REPLAY_DRAWS) {
+        if (rng_mode == THRL_RNG_PHILOX) {
+          uint32_t x[4];
+          philox4x32_10(gid, eabs, (uint32_t)t, kStreamAct << 16, key0, key1, x);
+          f0 = u32_unit(x[0]) < eps0 ? (int)__umulhi(x[1], (uint32_t)A0) : -1;
+          f1 = u32_unit(x[2]) < eps1 ? (int)__umulhi(x[3], (uint32_t)A1) : -1;
+        } else if (rng_mode == THRL_RNG_REPLAY_DRAWS) {
           const double2 u = *reinterpret_cast<const double2*>(p.replay_u + (step0 + t) * 2);
           const int2 v = *reinterpret_cast<const int2*>(p.replay_ra + (step0 + t) * 2);
           f0 = u.x < eps0 ? v.x : -1;
           f1 = u.y < eps1 ? v.y : -1;
         } else {
-          uint32_t x[4];
-          philox4x32_10(gid, eabs, (uint32_t)t, kStreamAct << 16, p.k0, p.k1, x);
-          f0 = u32_unit(x[0]) < eps0 ? (int)__umulhi(x[1], (uint32_t)A0) : -1;
-          f1 = u32_unit(x[2]) < eps1 ? (int)__umulhi(x[3], (uint32_t)A1) : -1;
+          const int2 v = *reinterpret_cast<const int2*>(p.replay_ra + (step0 + t) * 2);
+          f0 = v.x; f1 = v.y;
         }
-        pre[t] = (uint16_t)((f0 < 0 ? 0xFF : f0) | ((f1 < 0 ? 0xFF : f1) << 8));
+        pre[t] = make_uint2((f0 < 0 ? 0xffu : 0u) | (f1 < 0 ? 0xff00u : 0u),
+                            (uint32_t)(f0 < 0 ? 0 : f0) | ((uint32_t)(f1 < 0 ? 0 : f1) << 8));
       }
       __syncwarp();
 
       // ---- B: the episode (trainer.py:50-67).  Lanes 0..3 carry the four log accumulators (trainer.py:65-66).
+      const uint32_t sig4_start = sig4;
       double acc = 0.0;
-      const int acc_lane = lane & 3;
+      {
+        const uint2* pp = pre;
+        uint16_t* rp = rec;
+        uint32_t kk = 0;
 #pragma unroll 4
-      for (int t = 0; t < T; ++t) {
-        const uint32_t f = pre[t];
-        const uint32_t gj = GJ[sigma];
-        const uint32_t f0 = f & 0xff, f1 = f >> 8;
-        const uint32_t k0 = f0 == 0xff ? (gj & 0xff) : f0;
-        const uint32_t k1 = f1 == 0xff ? (gj >> 8) : f1;
-        const int joint = (int)(k0 * (uint32_t)A1 + k1);
-        if (lane == 0) {
-          seq[t] = (uint8_t)sigma;
-          rec[t] = (uint16_t)(k0 | (k1 << 8));
+        for (int t = 0; t < T; ++t) {
+          const uint2 f = pp[t];
+          const uint32_t gj = *reinterpret_cast<const uint32_t*>(GJb + sig4);
+          kk = (gj & f.x) | f.y;                               // agents.py:80-89 for both agents
+          const uint32_t joint = __dp4a(kk, dp_b, 0u);         // k0 * A1 + k1
+          rp[t] = (uint16_t)kk;                                // same value from every lane
+          acc = __dadd_rn(acc, lutLogLane[4 * joint]);
+          sig4 = nextS[joint];
         }
-        acc = __dadd_rn(acc, lutLog[4 * joint + acc_lane]);
-        sigma = nextS[joint];
-        last_k = (int)(k0 | (k1 << 8));
+        last_k = (int)kk;
       }
-      if (lane == 0) seq[T] = (uint8_t)sigma;
+      __syncwarp();
+      // states before every step, rebuilt lane-parallel from the action record
+      for (int t = lane; t <= T; t += 32) {
+        uint32_t s4 = sig4_start;
+        if (t > 0) { const uint32_t kk = rec[t - 1]; s4 = nextS[__dp4a(kk, dp_b, 0u)]; }
+        seq[t] = (uint8_t)(s4 >> 2);
+      }
       __syncwarp();
 
       // optional per-step traces (parity runs only), lane-parallel
@@ -268,7 +288,7 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
       }
 
       // ---- C: pre-pass over the batch = the newest L_i transitions of the episode (buffers.py:12, agents.py:61-67)
-      unsigned dirty0[2] = {0, 0}, dirty1[2] = {0, 0};  // written compact rows (bit c of word c>>5 ... up to 64 rows tracked)
+      unsigned dirty0a = 0, dirty0b = 0, dirty1a = 0, dirty1b = 0;  // written compact rows 0..63 of each agent
       bool dirty_all0 = false, dirty_all1 = false;
       for (int j = T - L0 + lane; j < T; j += 32) {
         const uint32_t rw = rowsW[seq[j]], rn = rowsW[seq[j + 1]];
@@ -276,10 +296,10 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
         const int cu = (rw >> 8) & 0xff, cn = (rn >> 8) & 0xff;
         const int cell = cu * A0 + k;
         const int jj = j - (T - L0);
-        meta[jj] = (uint32_t)cell | ((uint32_t)(cn * A0) << 16);
+        meta[jj] = make_uint2((uint32_t)(cn * A0) * (uint32_t)sizeof(QT), (uint32_t)cell * (uint32_t)sizeof(QT));
         rc[jj] = make_double2(lutR[2 * joint], __dmul_rn(oma0, (double)tab0[cell]));
-        if (cnt0) atomicAdd(cnt0 + (size_t)(cu < NR0 ? rowlist[cu] : extra_row0[cu - NR0]) * A0 + k, 1u);  // agents.py:76
-        if (cu < 64) dirty0[cu >> 5] |= 1u << (cu & 31); else dirty_all0 = true;
+        if (cnt0) atomicAdd(cnt0 + (size_t)table_row0(cu) * A0 + k, 1u);  // agents.py:76
+        if (cu < 32) dirty0a |= 1u << cu; else if (cu < 64) dirty0b |= 1u << (cu - 32); else dirty_all0 = true;
       }
       for (int j = T - L1 + lane; j < T; j += 32) {
         const uint32_t rw = rowsW[seq[j]], rn = rowsW[seq[j + 1]];
@@ -287,55 +307,64 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
         const int cu = rw >> 24, cn = rn >> 24;
         const int cell = cu * A1 + k;
         const int jj = j - (T - L1);
-        meta[T + jj] = (uint32_t)cell | ((uint32_t)(cn * A1) << 16);
+        meta[T + jj] = make_uint2((uint32_t)(cn * A1) * (uint32_t)sizeof(QT), (uint32_t)cell * (uint32_t)sizeof(QT));
         rc[T + jj] = make_double2(lutR[2 * joint + 1], __dmul_rn(oma1, (double)tab1[cell]));
-        if (cnt1) atomicAdd(cnt1 + (size_t)(cu < NR1 ? rowlist[NR0 + cu] : extra_row1[cu - NR1]) * A1 + k, 1u);
-        if (cu < 64) dirty1[cu >> 5] |= 1u << (cu & 31); else dirty_all1 = true;
+        if (cnt1) atomicAdd(cnt1 + (size_t)table_row1(cu) * A1 + k, 1u);
+        if (cu < 32) dirty1a |= 1u << cu; else if (cu < 64) dirty1b |= 1u << (cu - 32); else dirty_all1 = true;
       }
       __syncwarp();
 
       // ---- D: the sequential pass (agents.py:68-76), the two agents' dependency chains interleaved
-      auto upd = [&](QT* tab, int A, bool in, const uint32_t m, const double2 v, double alpha, double gamma) {
-        const double next_max = (double)lut2_row_max(tab + (m >> 16), A, lane, in);  // live table (:71)
+      auto upd = [&](QT* tab, const QT* tab_lane, int A, bool in, const uint2 m, const double2 v, double alpha, double gamma) {
+        const QT* row_lane = reinterpret_cast<const QT*>(reinterpret_cast<const unsigned char*>(tab_lane) + m.x);
+        const double next_max = (double)lut2_row_max<QT, kSmallA>(row_lane, A, lane, in);                 // live table (:71)
         const double nv = __dadd_rn(v.y, __dmul_rn(alpha, __dadd_rn(v.x, __dmul_rn(gamma, next_max))));  // :72-74
-        if (lane == 0) tab[m & 0xffff] = (QT)nv;                                                          // :75
+        if (lane == 0) *reinterpret_cast<QT*>(reinterpret_cast<unsigned char*>(tab) + m.y) = (QT)nv;     // :75
       };
       if (L0 == L1) {
+        const uint2* m0p = meta;
+        const uint2* m1p = meta + T;
+        const double2* v0p = rc;
+        const double2* v1p = rc + T;
 #pragma unroll 2
         for (int j = 0; j < L0; ++j) {
-          const uint32_t m0 = meta[j], m1 = meta[T + j];
-          const double2 v0 = rc[j], v1 = rc[T + j];
-          upd(tab0, A0, in0, m0, v0, alpha0, gamma0);
-          upd(tab1, A1, in1, m1, v1, alpha1, gamma1);
+          const uint2 m0 = m0p[j], m1 = m1p[j];
+          const double2 v0 = v0p[j], v1 = v1p[j];
+          upd(tab0, tab0_lane, A0, in0, m0, v0, alpha0, gamma0);
+          upd(tab1, tab1_lane, A1, in1, m1, v1, alpha1, gamma1);
           __syncwarp();
         }
       } else {
-        for (int j = 0; j < L0; ++j) { upd(tab0, A0, in0, meta[j], rc[j], alpha0, gamma0); __syncwarp(); }
-        for (int j = 0; j < L1; ++j) { upd(tab1, A1, in1, meta[T + j], rc[T + j], alpha1, gamma1); __syncwarp(); }
+        for (int j = 0; j < L0; ++j) { upd(tab0, tab0_lane, A0, in0, meta[j], rc[j], alpha0, gamma0); __syncwarp(); }
+        for (int j = 0; j < L1; ++j) { upd(tab1, tab1_lane, A1, in1, meta[T + j], rc[T + j], alpha1, gamma1); __syncwarp(); }
       }
 
       // ---- E: refresh the greedy cache of written rows, then the per-state greedy pairs
       {
-        unsigned w0 = __reduce_or_sync(kFull, dirty0[0]), w1 = __reduce_or_sync(kFull, dirty0[1]);
-        if (__any_sync(kFull, dirty_all0)) {
-          for (int c = 64; c < NR0 + 2; ++c) { const int g = row_argmax(tab0 + c * A0, A0, lane); if (lane == 0) grow[c] = (uint8_t)g; }
-        }
-        while (w0 | w1) {
-          const int c = w0 ? __ffs(w0) - 1 : 32 + __ffs(w1) - 1;
-          if (w0) w0 &= w0 - 1; else w1 &= w1 - 1;
-          const int g = row_argmax(tab0 + c * A0, A0, lane);
-          if (lane == 0) grow[c] = (uint8_t)g;
-        }
-        w0 = __reduce_or_sync(kFull, dirty1[0]); w1 = __reduce_or_sync(kFull, dirty1[1]);
-        if (__any_sync(kFull, dirty_all1)) {
-          for (int c = 64; c < NR1 + 2; ++c) { const int g = row_argmax(tab1 + c * A1, A1, lane); if (lane == 0) grow[NR0 + 2 + c] = (uint8_t)g; }
-        }
-        while (w0 | w1) {
-          const int c = w0 ? __ffs(w0) - 1 : 32 + __ffs(w1) - 1;
-          if (w0) w0 &= w0 - 1; else w1 &= w1 - 1;
-          const int g = row_argmax(tab1 + c * A1, A1, lane);
-          if (lane == 0) grow[NR0 + 2 + c] = (uint8_t)g;
-        }
+        auto refresh = [&](QT* tab, int A, bool in, int NRa, uint8_t* gr, unsigned wa, unsigned wb, bool all) {
+          wa = __reduce_or_sync(kFull, wa);
+          wb = __reduce_or_sync(kFull, wb);
+          if (__any_sync(kFull, all)) {
+            for (int c = 64; c < NRa + 2; ++c) {
+              const int g = lut2_row_argmax<QT, kSmallA>(tab + c * A, A, lane, in);
+              if (lane == 0) gr[c] = (uint8_t)g;
+            }
+          }
+          while (wa) {
+            const int c = __ffs(wa) - 1;
+            wa &= wa - 1;
+            const int g = lut2_row_argmax<QT, kSmallA>(tab + c * A, A, lane, in);
+            if (lane == 0) gr[c] = (uint8_t)g;
+          }
+          while (wb) {
+            const int c = 32 + __ffs(wb) - 1;
+            wb &= wb - 1;
+            const int g = lut2_row_argmax<QT, kSmallA>(tab + c * A, A, lane, in);
+            if (lane == 0) gr[c] = (uint8_t)g;
+          }
+        };
+        refresh(tab0, A0, in0, NR0, grow, dirty0a, dirty0b, dirty_all0);
+        refresh(tab1, A1, in1, NR1, grow + NR0 + 2, dirty1a, dirty1b, dirty_all1);
         __syncwarp();
         for (int s = lane; s <= NS; s += 32) {
           const uint32_t rw = rowsW[s];
@@ -363,11 +392,11 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
 
     // ---- write the run back: only the staged rows can have changed
     for (int c = 0; c < NR0 + 2; ++c) {
-      const int row = c < NR0 ? rowlist[c] : extra_row0[c - NR0];
+      const int row = table_row0(c);
       if (row >= 0) for (int k = lane; k < A0; k += 32) qg0[(size_t)row * A0 + k] = tab0[c * A0 + k];
     }
     for (int c = 0; c < NR1 + 2; ++c) {
-      const int row = c < NR1 ? rowlist[NR0 + c] : extra_row1[c - NR1];
+      const int row = table_row1(c);
       if (row >= 0) for (int k = lane; k < A1; k += 32) qg1[(size_t)row * A1 + k] = tab1[c * A1 + k];
     }
     if (lane == 0) {

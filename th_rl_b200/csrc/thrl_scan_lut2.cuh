@@ -124,15 +124,16 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
   uint16_t* rec = reinterpret_cast<uint16_t*>(slot + p.off_rec);     // [T] k0 | k1<<8
   uint8_t* seq = slot + p.off_seq;                                   // [T+1] state before step t (rebuilt lane-parallel)
   uint2* pre = reinterpret_cast<uint2*>(slot + p.off_scr);           // [T] (keep mask, forced value) byte pairs      (phases A-B)
-  uint2* meta = reinterpret_cast<uint2*>(slot + p.off_scr);          // [2][T] (next-row byte offset, cell byte offset) (phases C-D)
-  double2* rc = reinterpret_cast<double2*>(slot + p.off_scr + align16(2 * T * 8));  // [2][T] (reward, (1-alpha)*old)
+  uint2* meta = reinterpret_cast<uint2*>(slot + p.off_scr);          // [T][2] (next-row byte offset, cell byte offset) (phases C-D)
+  double2* rc = reinterpret_cast<double2*>(slot + p.off_scr + align16(2 * T * 8));  // [T][2] (reward, (1-alpha)*old)
 
   const bool in0 = lane < A0, in1 = lane < A1;
   const int L0 = p.L[0], L1 = p.L[1];
   const uint32_t dp_b = (uint32_t)A1 | (1u << 8);  // joint = dp4a(k0 | k1<<8, A1 | 1<<8)
   const double* lutLogLane = lutLog + (lane & 3);
-  const QT* tab0_lane = tab0 + lane;
-  const QT* tab1_lane = tab1 + lane;
+  // lanes >= A re-read the last column: harmless for a max, and no masked load / select in the hot loop
+  const QT* tab0_lane = tab0 + (kSmallA ? (lane < A0 ? lane : A0 - 1) : lane);
+  const QT* tab1_lane = tab1 + (kSmallA ? (lane < A1 ? lane : A1 - 1) : lane);
 
   const long long total_warps = (long long)gridDim.x * warps_per_cta;
   for (long long r = (long long)blockIdx.x * warps_per_cta + warp; r < p.n_runs; r += total_warps) {
@@ -296,8 +297,8 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
         const int cu = (rw >> 8) & 0xff, cn = (rn >> 8) & 0xff;
         const int cell = cu * A0 + k;
         const int jj = j - (T - L0);
-        meta[jj] = make_uint2((uint32_t)(cn * A0) * (uint32_t)sizeof(QT), (uint32_t)cell * (uint32_t)sizeof(QT));
-        rc[jj] = make_double2(lutR[2 * joint], __dmul_rn(oma0, (double)tab0[cell]));
+        meta[2 * jj] = make_uint2((uint32_t)(cn * A0) * (uint32_t)sizeof(QT), (uint32_t)cell * (uint32_t)sizeof(QT));
+        rc[2 * jj] = make_double2(lutR[2 * joint], __dmul_rn(oma0, (double)tab0[cell]));
         if (cnt0) atomicAdd(cnt0 + (size_t)table_row0(cu) * A0 + k, 1u);  // agents.py:76
         if (cu < 32) dirty0a |= 1u << cu; else if (cu < 64) dirty0b |= 1u << (cu - 32); else dirty_all0 = true;
       }
@@ -307,36 +308,49 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
         const int cu = rw >> 24, cn = rn >> 24;
         const int cell = cu * A1 + k;
         const int jj = j - (T - L1);
-        meta[T + jj] = make_uint2((uint32_t)(cn * A1) * (uint32_t)sizeof(QT), (uint32_t)cell * (uint32_t)sizeof(QT));
-        rc[T + jj] = make_double2(lutR[2 * joint + 1], __dmul_rn(oma1, (double)tab1[cell]));
+        meta[2 * jj + 1] = make_uint2((uint32_t)(cn * A1) * (uint32_t)sizeof(QT), (uint32_t)cell * (uint32_t)sizeof(QT));
+        rc[2 * jj + 1] = make_double2(lutR[2 * joint + 1], __dmul_rn(oma1, (double)tab1[cell]));
         if (cnt1) atomicAdd(cnt1 + (size_t)table_row1(cu) * A1 + k, 1u);
         if (cu < 32) dirty1a |= 1u << cu; else if (cu < 64) dirty1b |= 1u << (cu - 32); else dirty_all1 = true;
       }
       __syncwarp();
 
-      // ---- D: the sequential pass (agents.py:68-76), the two agents' dependency chains interleaved
-      auto upd = [&](QT* tab, const QT* tab_lane, int A, bool in, const uint2 m, const double2 v, double alpha, double gamma) {
-        const QT* row_lane = reinterpret_cast<const QT*>(reinterpret_cast<const unsigned char*>(tab_lane) + m.x);
-        const double next_max = (double)lut2_row_max<QT, kSmallA>(row_lane, A, lane, in);                 // live table (:71)
-        const double nv = __dadd_rn(v.y, __dmul_rn(alpha, __dadd_rn(v.x, __dmul_rn(gamma, next_max))));  // :72-74
-        if (lane == 0) *reinterpret_cast<QT*>(reinterpret_cast<unsigned char*>(tab) + m.y) = (QT)nv;     // :75
+      // ---- D: the sequential pass (agents.py:68-76).  The two agents' chains are independent: both rows are loaded
+      //      before either cell is stored so the two dependency chains overlap.
+      auto load_max = [&](const QT* tab_lane, int A, bool in, uint32_t row_off) -> double {
+        const QT* row_lane = reinterpret_cast<const QT*>(reinterpret_cast<const unsigned char*>(tab_lane) + row_off);
+        if (kSmallA) return (double)warp_max(row_lane[0]);                        // live table (:71)
+        return (double)lut2_row_max<QT, false>(row_lane, A, lane, in);
+      };
+      auto store_cell = [&](QT* tab, uint32_t cell_off, double v, double next_max, double alpha, double gamma, double2 rcv) {
+        (void)v;
+        const double nv = __dadd_rn(rcv.y, __dmul_rn(alpha, __dadd_rn(rcv.x, __dmul_rn(gamma, next_max))));  // :72-74
+        if (lane == 0) *reinterpret_cast<QT*>(reinterpret_cast<unsigned char*>(tab) + cell_off) = (QT)nv;   // :75
       };
       if (L0 == L1) {
-        const uint2* m0p = meta;
-        const uint2* m1p = meta + T;
-        const double2* v0p = rc;
-        const double2* v1p = rc + T;
+        const uint4* mp = reinterpret_cast<const uint4*>(meta);
+        const double2* vp = rc;
 #pragma unroll 2
         for (int j = 0; j < L0; ++j) {
-          const uint2 m0 = m0p[j], m1 = m1p[j];
-          const double2 v0 = v0p[j], v1 = v1p[j];
-          upd(tab0, tab0_lane, A0, in0, m0, v0, alpha0, gamma0);
-          upd(tab1, tab1_lane, A1, in1, m1, v1, alpha1, gamma1);
+          const uint4 m = mp[j];
+          const double2 v0 = vp[2 * j], v1 = vp[2 * j + 1];
+          const double mx0 = load_max(tab0_lane, A0, in0, m.x);
+          const double mx1 = load_max(tab1_lane, A1, in1, m.z);
+          store_cell(tab0, m.y, 0.0, mx0, alpha0, gamma0, v0);
+          store_cell(tab1, m.w, 0.0, mx1, alpha1, gamma1, v1);
           __syncwarp();
         }
       } else {
-        for (int j = 0; j < L0; ++j) { upd(tab0, tab0_lane, A0, in0, meta[j], rc[j], alpha0, gamma0); __syncwarp(); }
-        for (int j = 0; j < L1; ++j) { upd(tab1, tab1_lane, A1, in1, meta[T + j], rc[T + j], alpha1, gamma1); __syncwarp(); }
+        for (int j = 0; j < L0; ++j) {
+          const uint2 m = meta[2 * j];
+          store_cell(tab0, m.y, 0.0, load_max(tab0_lane, A0, in0, m.x), alpha0, gamma0, rc[2 * j]);
+          __syncwarp();
+        }
+        for (int j = 0; j < L1; ++j) {
+          const uint2 m = meta[2 * j + 1];
+          store_cell(tab1, m.y, 0.0, load_max(tab1_lane, A1, in1, m.x), alpha1, gamma1, rc[2 * j + 1]);
+          __syncwarp();
+        }
       }
 
       // ---- E: refresh the greedy cache of written rows, then the per-state greedy pairs

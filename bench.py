@@ -107,7 +107,7 @@ def cpu_oracle_leg(n_threads, target_seconds=12.0):
     t = time.perf_counter()
     oracle.scan(game, q0, e0, p0, 20, n_threads=cores, n_log_runs=0, stats=True)
     rate = R0 * 2 * 20 * MAX_STEPS / (time.perf_counter() - t)
-    R = int(max(cores, min(4096, target_seconds * rate / (2 * EPOCHS * MAX_STEPS))))
+    R = int(max(cores, min(262144, target_seconds * rate / (2 * EPOCHS * MAX_STEPS))))
     q0, c0, e0, p0 = oracle.init(game, R, seed=0, dtype=np.float32, eps0=eps0)
     t = time.perf_counter()
     oracle.scan(game, q0, e0, p0, EPOCHS, n_threads=cores, n_log_runs=0, stats=True)
@@ -228,7 +228,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_peak_gbs, "unit": "GB/s",
                          "frac": achieved / smem_peak_gbs, "traffic": None,
-                         "kernel": "thrl::qtable_scan (persistent, one launch per step)",
+                         "kernel": "thrl::qtable_scan_lut2<float, true> (persistent, one launch per step)",
                          "kernel_ms": kern_ms,
                          "note": "tables are shared-memory resident, so the bound is SM shared-memory bandwidth "
                                  "(BASELINE.md 5: 184 algorithmic B per agent-step; peak = 128 B/clk/SM x 148 SMs x "

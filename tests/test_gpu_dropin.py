@@ -1,0 +1,92 @@
+"""Drop-in behaviour on the GPU: train_one reproduces the reference's artefacts bit for bit under seeded RNGs; the CLI
+writes the reference's runs/ layout; train_many's exported runs agree with its device state."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_train_one_reproduces_reference_files(golden, tmp_path):
+    """Seed python `random` and numpy like the recorded reference run, call train_one: the saved tables, counters and
+    log.csv equal what the unmodified reference wrote (th_rl/trainer.py:101-110)."""
+    from th_rl_b200 import trainer
+    cfg = golden["config"]
+    cpath = tmp_path / "cfg.json"
+    cpath.write_text(json.dumps(cfg))
+    seed = int(golden["seed"])
+    random.seed(seed)
+    np.random.seed(seed)
+    out = tmp_path / "run0"
+    trainer.train_one(str(out), str(cpath), chunk_epochs=5)
+    n = len(cfg["agents"])
+    for i in range(n):
+        assert np.array_equal(np.load(out / ("%d.npy" % i)), golden["q_final_%d" % i])
+        assert np.array_equal(np.load(out / ("%d_counter.npy" % i)), golden["counter_final_%d" % i])
+    lines = (out / "log.csv").read_text().splitlines()
+    assert lines[0] == str(golden["log_header"][0]) and lines[1] == str(golden["log_header"][1])
+    log = np.loadtxt(lines[2:], delimiter=",", ndmin=2)
+    assert np.array_equal(log[:, :n], golden["rewards_log"]) and np.array_equal(log[:, n:], golden["actions_log"])
+    assert json.loads((out / "config.json").read_text()) == cfg
+    assert (out / "config.json").read_text() == json.dumps(cfg, indent=3)
+
+
+def _small_cfg():
+    a = dict(name="QTable", gamma=0.95, actions=21, states=100, alpha=0.1, eps_end=0.001, epsilon=0.5, eps_step=0.9995,
+             action_range=[0.2, 0.4])
+    return {"agents": [dict(a), dict(a)],
+            "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=2, max_steps=100),
+            "training": {"epochs": 12, "print_freq": 5}}
+
+
+def test_cli_writes_reference_layout(tmp_path):
+    from click.testing import CliRunner
+    from th_rl_b200.main import main
+    cdir = tmp_path / "configs"
+    cdir.mkdir()
+    (cdir / "example_config.json").write_text(json.dumps(_small_cfg()))
+    (cdir / "notes.txt").write_text("not a config")
+    r = CliRunner().invoke(main, ["--dir", str(cdir), "--runs", "3"])
+    assert r.exit_code == 0, r.output
+    assert "Skipping example_config.json" in r.output  # the reference's for-else prints this after every config
+    runs = tmp_path / "runs" / "example_config"
+    assert sorted(os.listdir(runs)) == ["0", "1", "2"]
+    for i in range(3):
+        assert sorted(os.listdir(runs / str(i))) == ["0.npy", "0_counter.npy", "1.npy", "1_counter.npy", "config.json", "log.csv"]
+        t = np.load(runs / str(i) / "0.npy")
+        c = np.load(runs / str(i) / "1_counter.npy")
+        assert t.shape == (101, 21) and t.dtype == np.float64 and c.dtype == np.float64
+        assert c.sum() == 12 * 100  # counter.sum() == epochs * max_steps, as in the shipped sample runs
+        lines = (runs / str(i) / "log.csv").read_text().splitlines()
+        assert lines[0] == "rewards,rewards,actions,actions" and lines[1] == "0,1,0,1" and len(lines) == 2 + 12
+    assert not np.array_equal(np.load(runs / "0" / "0.npy"), np.load(runs / "1" / "0.npy"))
+    # second invocation: the config's directory exists -> skipped silently (main.py:16); --cdir is accepted
+    r2 = CliRunner().invoke(main, ["--cdir", str(cdir), "--runs", "3"])
+    assert r2.exit_code == 0 and r2.output == ""
+    # reference mode: one train_one per run, progress lines in the reference's format
+    (cdir / "second.json").write_text(json.dumps(_small_cfg()))
+    r3 = CliRunner().invoke(main, ["--dir", str(cdir), "--runs", "1", "--mode", "reference"])
+    assert r3.exit_code == 0, r3.output
+    assert "| episode:  4 | reward:[" in r3.output and "agents:QTable,QTable" in r3.output
+    assert sorted(os.listdir(tmp_path / "runs" / "second")) == ["0"]
+
+
+def test_train_many_matches_single_batch_and_exports(tmp_path):
+    import torch
+    from th_rl_b200 import abi, engine, trainer
+    cfg = _small_cfg()
+    res = trainer.train_many(cfg, 40, seed=3, log_runs=40, chunk_epochs=5, export_dir=str(tmp_path / "x"), export_runs=2)
+    b = engine.RunBatch(cfg, 40, seed=3).init_device()
+    o = b.scan(12, n_log_runs=40, stats=True)
+    torch.cuda.synchronize()
+    assert torch.equal(res.batch.q, b.q) and torch.equal(res.batch.counter, b.counter)
+    assert np.array_equal(res.rewards_log, o.rewards_log.cpu().numpy())
+    assert np.array_equal(res.stats, o.stats.cpu().numpy())
+    mean_r, sd_r, mean_x, sd_x = res.mean_curves()
+    assert np.allclose(mean_r, res.rewards_log.mean(0), atol=1e-8) and np.allclose(sd_r, res.rewards_log.std(0), atol=1e-4)
+    assert np.array_equal(np.load(tmp_path / "x" / "1" / "0.npy"), b.tables()[0][1].cpu().numpy().astype(np.float64))
+    # learning signal: total reward per step sits between 0 and the cartel level 25 (th_rl/utils.py:91-92)
+    assert 0 < mean_r.sum(1).mean() < 25.0

@@ -1,0 +1,178 @@
+"""Host-side logic that needs no GPU: C-ABI library loads and exports every declared symbol, config translation,
+validation / layout, drop-in class surface, reference random-stream generation, sharding, gloo all-reduce of stats."""
+import ctypes
+import json
+import os
+import random
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from th_rl_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from th_rl_b200 import _lib
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "thrl.h")).read()
+    names = set(re.findall(r"\b(thrl_[a-z0-9_]+)\s*\(", hdr))
+    assert {"thrl_qtable_scan", "thrl_qtable_scan_host", "thrl_qtable_init", "thrl_greedy_eval", "thrl_game_layout",
+            "thrl_ring_bytes", "thrl_last_error", "thrl_abi_version", "thrl_launch_count"} <= names
+    for nm in names:
+        assert hasattr(L, nm), nm
+    assert L.thrl_abi_version() == abi.THRL_ABI_VERSION
+
+
+def test_struct_sizes_match_header():
+    """The ctypes mirror and the C structs must agree byte for byte (checked with a tiny C program)."""
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "thrl.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(ThrlAgentSpec), sizeof(ThrlGame), sizeof(ThrlScanArgs),
+        offsetof(ThrlGame, run_stride), offsetof(ThrlScanArgs, trace_prices)); return 0; }'''
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        got = [int(x) for x in subprocess.check_output([exe]).split()]
+    want = [ctypes.sizeof(abi.ThrlAgentSpec), ctypes.sizeof(abi.ThrlGame), ctypes.sizeof(abi.ThrlScanArgs),
+            abi.ThrlGame.run_stride.offset, abi.ThrlScanArgs.trace_prices.offset]
+    assert got == want
+
+
+def _cfg(**env):
+    a = dict(name="QTable", gamma=0.95, actions=21, states=100, alpha=0.1, eps_end=0.001, epsilon=0.5, eps_step=0.9995,
+             action_range=[0.2, 0.4])
+    e = dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=2, max_steps=100)
+    e.update(env)
+    return {"agents": [dict(a), dict(a)], "environment": e, "training": {"epochs": 3, "print_freq": 500}}
+
+
+def test_layout_matches_oracle_and_validates():
+    from th_rl_b200 import _lib
+    from oracle import oracle
+    for cfg in (_cfg(), _cfg(max_steps=37), _cfg(max_steps=150)):
+        cfg["agents"][1].update(states=50, actions=11, capacity=120, min_memory=60)
+        g, o = _lib.game_layout(cfg), oracle.layout(cfg)
+        assert (g.run_stride, g.ring_len, g.regular) == (o.run_stride, o.ring_len, o.regular)
+        assert [g.agent[i].table_offset for i in range(2)] == [o.agent[i].table_offset for i in range(2)]
+    bad = _cfg(a=20)  # price can exceed max_state: the reference dies with IndexError on the first encode
+    with pytest.raises(ValueError):
+        _lib.game_layout(bad)
+    bad = _cfg()
+    bad["environment"]["nplayers"] = 3  # trainer.py:21-23
+    with pytest.raises(AssertionError):
+        _lib.game_layout(bad)
+    mlp = _cfg()
+    mlp["agents"][1]["name"] = "Reinforce"
+    with pytest.raises(NotImplementedError):
+        _lib.game_layout(mlp)
+
+
+def test_dropin_class_surface():
+    from th_rl_b200 import agents, environments, trainer
+    np.random.seed(3)
+    q = agents.QTable(states=100, actions=21, action_range=[0.2, 0.4], gamma=0.95, unknown_key=1)
+    assert q.table.shape == (101, 21) and q.counter.shape == (101, 21) and q.table.dtype == np.float64
+    np.random.seed(3)
+    assert np.array_equal(q.table, 12.5 / (1 - 0.95) + np.random.randn(101, 21))  # agents.py:29
+    assert q.scale(20) == 20 / 20.0 * (0.4 - 0.2) + 0.2
+    assert q.encode(np.array([3.3])).tolist() == [33]
+    assert q.get_action(np.array([3.3])) == int(np.argmax(q.table[33]))
+    with pytest.raises(NotImplementedError):
+        q.sample_action(None)
+    env = environments.NoisyPriceState(nplayers=2, a=10, b=1, max_steps=100, noise_prob=0)
+    nash, cartel = env.get_optimal()
+    assert abs(nash - 22.2222222) < 1e-6 and cartel == 25.0  # th_rl/utils.py:91-92
+    with pytest.raises(NotImplementedError):
+        env.step([0.3, 0.3])
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "c.json")
+        json.dump(_cfg(), open(p, "w"))
+        config, ags, e = trainer.create_game(p)
+        assert len(ags) == 2 and e.nplayers == 2 and config["training"]["epochs"] == 3
+        q.save(os.path.join(d, "0"))
+        q2 = agents.QTable(states=100, actions=21)
+        q2.load(os.path.join(d, "0"))
+        assert np.array_equal(q2.table, q.table)
+
+
+def test_reference_streams_reproduce_recorded_draws(golden):
+    """trainer.reference_streams consumes python `random` / numpy.random exactly like the reference's loop: seeded like
+    the golden run, it regenerates the recorded u / random-action / demand-intercept streams bit for bit."""
+    from th_rl_b200 import trainer
+    cfg = golden["config"]
+    seed = int(golden["seed"])
+    random.seed(seed)
+    np.random.seed(seed)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "c.json")
+        json.dump(cfg, open(p, "w"))
+        config, ags, env = trainer.create_game(p)
+    n = len(ags)
+    for i in range(n):
+        assert np.array_equal(ags[i].table, golden["q0_%d" % i])
+    state = env.reset()
+    assert state[0] == golden["p0"]
+    E = golden["u"].shape[0]
+    u, ra, new_a = trainer.reference_streams(ags, env, E)
+    assert np.array_equal(u, golden["u"]) and np.array_equal(ra, golden["ra"]) and np.array_equal(new_a, golden["new_a"])
+
+
+def test_shard_bounds_cover_everything():
+    from th_rl_b200.trainer import shard_bounds
+    for total in (1, 7, 65536, 1048576):
+        for world in (1, 2, 3, 8):
+            b = [shard_bounds(total, r, world) for r in range(world)]
+            assert b[0][0] == 0 and b[-1][1] == total and all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = _cfg()
+    game = oracle.layout(cfg)
+    from th_rl_b200.trainer import shard_bounds
+    R, E = 24, 3
+    lo, hi = shard_bounds(R, rank, world)
+    q0, c0, e0, p0 = oracle.init(game, hi - lo, seed=5, run_id0=lo, dtype=np.float32, eps0=abi.eps0_from_config(cfg))
+    res = oracle.scan(game, q0, e0, p0, E, seed=5, run_id0=lo, stats=True)  # stands in for the device scan of this shard
+    stats = torch.from_numpy(res.stats.copy())
+    dist.all_reduce(stats)  # the same call bench.py / train_many make over NCCL
+    if rank == 0:
+        q.put((stats.numpy(), res.q[:2]))
+    dist.destroy_process_group()
+
+
+def test_sharded_stats_allreduce_gloo_world2():
+    """N>1 path on CPU: two ranks own run shards (global ids), all-reduce the fixed-point statistics over gloo; the sum
+    equals the unsharded statistics exactly."""
+    import torch.multiprocessing as mp
+    from oracle import oracle
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    stats, qhead = q.get(timeout=120)
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    cfg = _cfg()
+    game = oracle.layout(cfg)
+    q0, c0, e0, p0 = oracle.init(game, 24, seed=5, dtype=np.float32, eps0=abi.eps0_from_config(cfg))
+    whole = oracle.scan(game, q0, e0, p0, 3, seed=5, stats=True)
+    assert np.array_equal(stats, whole.stats)
+    assert np.array_equal(qhead, whole.q[:2])

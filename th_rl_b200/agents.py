@@ -1,0 +1,67 @@
+"""QTable — host-side mirror of th_rl/agents.py:12-116 for the B200 path.
+
+Same constructor keywords, defaults and attributes as the reference class, so `create_game`, saved artefacts and the
+reference's analysis code (`utils.py` reads .table/.counter/.states/.actions/.action_space/.action_range/.max_state and
+calls load/get_action/scale) keep working.  What differs: acting and learning do not happen per call on the host.
+`sample_action` / `train_net` / `memory.append` are fused into the device scan (csrc/thrl_scan_*.cuh); calling them on the
+host raises, because this package has no CPU implementation of the hot path.
+"""
+import numpy
+
+from .buffers import ReplayBuffer  # noqa: F401  (the reference resolves `buffer` by name)
+
+_FUSED = ("%s is fused into the device scan (th_rl_b200.trainer.train_one / train_many -> thrl_qtable_scan); "
+          "th_rl_b200 has no per-step host implementation of the hot path")
+
+
+class QTable:
+    def __init__(self, states=16, actions=4, action_range=[0, 1], gamma=0.99, buffer="ReplayBuffer", capacity=500,
+                 max_state=10, alpha=0.1, eps_end=2e-2, epsilon=0.5, eps_step=5e-4, min_memory=100, **kwargs):
+        # agents.py:29 — same draw from numpy's global generator, so a seeded script starts from the same table
+        self.table = 12.5 / (1 - gamma) + numpy.random.randn(states + 1, actions)
+        self.gamma = gamma
+        self.alpha = alpha
+        self.action_space = numpy.arange(0, actions)
+        self.action_range = action_range
+        self.actions = actions
+        self.epsilon = epsilon
+        self.eps_step = eps_step
+        self.eps_end = eps_end
+        self.states = states
+        self.max_state = max_state
+        self.min_memory = min_memory
+        self.capacity = capacity
+        if buffer != "ReplayBuffer":
+            raise ValueError("unknown buffer %r (the reference only ships ReplayBuffer)" % (buffer,))
+        self.memory = ReplayBuffer(capacity, None)
+        self.counter = 0 * self.table
+
+    # agents.py:47-49
+    def encode(self, state):
+        return numpy.round(state / self.max_state * self.states).astype("int64")
+
+    # agents.py:51-57
+    def scale(self, actions):
+        return actions / (self.actions - 1.0) * (self.action_range[1] - self.action_range[0]) + self.action_range[0]
+
+    # agents.py:91-92 (evaluation helper used by utils.play_game; batched on the device by RunBatch.greedy_eval)
+    def get_action(self, state):
+        return numpy.argmax(self.table[self.encode(state)])
+
+    def sample_action(self, state):
+        raise NotImplementedError(_FUSED % "QTable.sample_action")
+
+    def train_net(self):
+        raise NotImplementedError(_FUSED % "QTable.train_net")
+
+    # agents.py:110-116
+    def save(self, loc):
+        numpy.save(loc, self.table)
+        numpy.save(loc + "_counter", self.counter)
+
+    def load(self, loc):
+        self.table = numpy.load(loc + ".npy")
+        self.counter = numpy.load(loc + "_counter.npy")
+
+
+AGENTS = {"QTable": QTable}

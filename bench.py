@@ -102,7 +102,7 @@ def cpu_oracle_leg(n_threads, target_seconds=12.0):
     cores = n_threads if n_threads > 0 else oracle.online_cores()
     eps0 = abi.eps0_from_config(CONFIG)
     # calibrate on a small sample, then size the timed sample for ~target_seconds
-    R0 = 4 * cores
+    R0 = 64 * cores
     q0, c0, e0, p0 = oracle.init(game, R0, seed=0, dtype=np.float32, eps0=eps0)
     t = time.perf_counter()
     oracle.scan(game, q0, e0, p0, 20, n_threads=cores, n_log_runs=0, stats=True)

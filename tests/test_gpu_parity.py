@@ -11,14 +11,18 @@ from th_rl_b200 import abi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["auto", "generic"], autouse=True)
+@pytest.fixture(params=["auto", "generic", "lpc", "lpc16"], autouse=True)
 def kernel_choice(request, monkeypatch):
     """Every test runs twice: with the default dispatch (specialised 2-agent kernel where it applies) and with the
     general kernel forced, so both kernels are held to the same bar."""
+    monkeypatch.delenv("THRL_KERNEL", raising=False)
+    monkeypatch.delenv("THRL_LPC_GL", raising=False)
     if request.param == "generic":
         monkeypatch.setenv("THRL_KERNEL", "generic")
-    else:
-        monkeypatch.delenv("THRL_KERNEL", raising=False)
+    elif request.param.startswith("lpc"):
+        monkeypatch.setenv("THRL_KERNEL", "lpc")  # lane-per-chain kernel where it applies (else the general kernel)
+        if request.param == "lpc16":
+            monkeypatch.setenv("THRL_LPC_GL", "16")
     return request.param
 
 

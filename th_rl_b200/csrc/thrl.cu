@@ -18,6 +18,7 @@
 #include "thrl_device.cuh"
 #include "thrl_scan_generic.cuh"
 #include "thrl_scan_lut2.cuh"
+#include "thrl_scan_lpc.cuh"
 #include "thrl_aux_kernels.cuh"
 
 namespace {
@@ -262,6 +263,62 @@ int launch_lut2(thrl::Lut2Params& p, int warps, const DeviceInfo& dev, cudaStrea
   return THRL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ LPC launch
+template <typename QT, int GL>
+int launch_lpc_gl(thrl::Lut2Params& p, const DeviceInfo& dev, cudaStream_t stream) {
+  const ThrlGame& G = p.game;
+  const int T = G.max_steps, esz = (int)sizeof(QT);
+  thrl::LpcLayout lay;
+  lay.cells_max = 0; lay.rows_max = 0;
+  int Lmax = 1;
+  for (int a = 0; a < 2; ++a) {
+    const int cells = (p.NR[a] + 2) * G.agent[a].actions;
+    if (cells > lay.cells_max) lay.cells_max = cells;
+    if (p.NR[a] + 2 > lay.rows_max) lay.rows_max = p.NR[a] + 2;
+    if (p.L[a] > Lmax) Lmax = p.L[a];
+  }
+  int o = 0;
+  lay.off_tab = o;  o += align_up(lay.cells_max * GL * esz, 16);
+  lay.off_old = o;  o += align_up(Lmax * GL * esz, 16);
+  lay.off_rec = o;  o += align_up(T * GL * 4, 16);
+  lay.off_pre = o;  o += align_up(T * GL, 16);
+  lay.off_gj = o;   o += align_up((p.NS + 1) * GL * 4, 16);
+  lay.off_rows = o; o += align_up((p.NS + 1) * GL * 2, 16);
+  lay.off_grow = o; o += align_up(lay.rows_max * GL, 16);
+  lay.off_eps = o;  o += align_up(GL * 8, 16);
+  lay.off_xrow = o; o += align_up(2 * GL * 2, 16);
+  lay.warp_bytes = o;
+  int warps = (dev.smem_optin - p.cta_bytes) / lay.warp_bytes;
+  if (warps < 1) return fail(THRL_ERR_UNSUPPORTED, "lpc: one warp group needs %d B of shared memory", lay.warp_bytes);
+  if (warps > thrl::kLpcMaxWarps) warps = thrl::kLpcMaxWarps;
+  const long long groups = (p.n_runs + GL / 2 - 1) / (GL / 2);
+  int grid = dev.sms;
+  if ((groups + warps - 1) / warps < grid) {
+    warps = (int)((groups + dev.sms - 1) / dev.sms);
+    if (warps < 1) warps = 1;
+    grid = (int)((groups + warps - 1) / warps);
+  }
+  const size_t smem = (size_t)p.cta_bytes + (size_t)warps * lay.warp_bytes;
+  // compile-time action count for the shapes the reference ships (example_config / configs2: 21 actions)
+  const bool a21 = G.agent[0].actions == 21 && G.agent[1].actions == 21;
+  auto kern = a21 ? thrl::qtable_scan_lpc<QT, GL, 21> : thrl::qtable_scan_lpc<QT, GL, 0>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, warps * 32, smem, stream>>>(p, lay);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return THRL_OK;
+}
+template <typename QT>
+int launch_lpc(thrl::Lut2Params& p, const DeviceInfo& dev, cudaStream_t stream) {
+  const char* s = getenv("THRL_LPC_GL");
+  const int gl = s ? atoi(s) : 8;
+  switch (gl) {
+    case 4: return launch_lpc_gl<QT, 4>(p, dev, stream);
+    case 16: return launch_lpc_gl<QT, 16>(p, dev, stream);
+    default: return launch_lpc_gl<QT, 8>(p, dev, stream);
+  }
+}
+
 int check_args(const ThrlScanArgs* a) {
   if (!a || !a->game) return fail(THRL_ERR_BAD_ARGS, "args/game is NULL");
   if (a->n_runs < 0 || a->epoch_end < a->epoch_begin) return fail(THRL_ERR_BAD_ARGS, "negative run or epoch count");
@@ -319,7 +376,8 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
   p.Hp = (p.game.ring_len > 0 ? p.game.ring_len : 1) + 1;
   p.noisy = (a->rng_mode == THRL_RNG_PHILOX) ? (p.game.noise_prob > 0.0) : (a->replay_new_a != nullptr);
   cudaStream_t stream = (cudaStream_t)stream_;
-  // Kernel choice.  THRL_KERNEL=generic|lut2 forces one (tests exercise both); default: lut2 whenever it applies.
+  // Kernel choice.  THRL_KERNEL=generic forces the general kernel, lut2 / lpc pick one of the two specialised kernels
+  // where they apply (tests exercise all three); default: see below.
   const char* force = getenv("THRL_KERNEL");
   const bool want_generic = force && strcmp(force, "generic") == 0;
   if (!want_generic) {
@@ -334,10 +392,10 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
       l->replay_u = p.replay_u; l->replay_ra = p.replay_ra;
       l->rewards_log = p.rewards_log; l->actions_log = p.actions_log; l->n_log_runs = p.n_log_runs; l->stats = p.stats;
       l->trace_actions = p.trace_actions; l->trace_rewards = p.trace_rewards; l->trace_prices = p.trace_prices;
+      if (force && strcmp(force, "lpc") == 0)
+        return a->table_dtype == THRL_F64 ? launch_lpc<double>(*l, dev, stream) : launch_lpc<float>(*l, dev, stream);
       return a->table_dtype == THRL_F64 ? launch_lut2<double>(*l, warps, dev, stream) : launch_lut2<float>(*l, warps, dev, stream);
     }
-    if (force && strcmp(force, "lut2") == 0)
-      return fail(THRL_ERR_UNSUPPORTED, "THRL_KERNEL=lut2 but the game is not a 2-agent noise-free regular game that fits");
   }
   return a->table_dtype == THRL_F64 ? launch_generic<double>(p, dev, stream) : launch_generic<float>(p, dev, stream);
 }

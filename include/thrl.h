@@ -35,7 +35,7 @@ extern "C" {
 
 #define THRL_ABI_VERSION 1
 #define THRL_MAX_AGENTS 16
-#define THRL_MAX_ACTIONS 256 /* greedy-action cache is one byte per table row */
+#define THRL_MAX_ACTIONS 255 /* greedy-action cache is one byte per table row, 0xFF = not cached */
 
 typedef enum ThrlStatus {
   THRL_OK = 0,

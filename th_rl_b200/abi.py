@@ -8,7 +8,7 @@ import ctypes as C
 
 THRL_ABI_VERSION = 1
 THRL_MAX_AGENTS = 16
-THRL_MAX_ACTIONS = 256
+THRL_MAX_ACTIONS = 255
 THRL_STATS_K = 4
 THRL_STATS_SCALE_SUM = 4294967296.0
 THRL_STATS_SCALE_SQ = 16777216.0

@@ -102,16 +102,19 @@ void plan_generic(thrl::ScanParams* p, bool smem_tables, size_t elem) {
   for (int i = 0; i < n; ++i) { lut += G.agent[i].actions; rows += G.agent[i].states + 1; }
   p->lut_total = lut;
   p->rows_total = rows;
-  p->cta_bytes = align_up(3 * lut * 8, 16);
+  p->cta_bytes = align_up(2 * lut * 8, 16);
   int o = 0;
   p->off_tab = o;
   if (smem_tables) o += align_up((int)(G.run_stride * (long long)elem), 16);
   p->off_P = o;    o += align_up(Hp * 8, 16);
   p->off_newa = o; o += p->noisy ? align_up(T * 8, 16) : 0;
   p->off_hp = o;   o += align_up(n * 5 * 8, 16);
-  p->off_old = o;  o += align_up(Hp * (int)elem, 16);
+  p->old_stride = align_up(Hp, 4);
+  p->off_old = o;  o += align_up(n * p->old_stride * (int)elem, 16);
   p->off_pre = o;  o += align_up(T * n * 2, 16);
-  p->off_row = o;  o += align_up((Hp + 1) * 2, 16);
+  p->row_stride = align_up(Hp + 1, 8);
+  p->off_row = o;  o += align_up(n * p->row_stride * 2, 16);
+  p->off_des = o;  o += align_up(n * 4 * 4, 16);
   p->off_act = o;  o += align_up(n * Hp, 16);
   p->off_g = o;    o += align_up(rows, 16);
   p->warp_bytes = o;
@@ -130,7 +133,7 @@ int launch_generic(thrl::ScanParams& p, const DeviceInfo& dev, cudaStream_t stre
   if (!smem_tables) plan_generic(&p, false, sizeof(T));
   int warps = (dev.smem_optin - p.cta_bytes) / p.warp_bytes;
   if (warps < 1) return fail(THRL_ERR_UNSUPPORTED, "one run needs %d B of shared memory (> %d B)", p.warp_bytes + p.cta_bytes, dev.smem_optin);
-  if (warps > 32) warps = 32;
+  if (warps > (smem_tables ? 32 : 16)) warps = smem_tables ? 32 : 16;
   const long long needed_ctas = (p.n_runs + warps - 1) / warps;
   int grid = dev.sms;
   if (needed_ctas < grid) {  // few runs: spread them one warp-run per SM first

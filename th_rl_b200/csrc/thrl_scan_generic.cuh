@@ -36,7 +36,8 @@ struct ScanParams {
   double* trace_prices;
   // shared-memory layout (bytes): [cta_bytes shared by the CTA][warp 0 slot][warp 1 slot]...
   int cta_bytes, warp_bytes;
-  int off_tab, off_g, off_pre, off_newa, off_P, off_act, off_row, off_old, off_hp;
+  int off_tab, off_g, off_pre, off_newa, off_P, off_act, off_row, off_old, off_hp, off_des;
+  int row_stride, old_stride;  // per-agent strides (elements) of the rowbuf / oldv scratch
   int lut_total;   // sum of actions_i
   int rows_total;  // sum of states_i + 1
   int Hp;          // ring slots = ring_len + 1
@@ -53,16 +54,15 @@ struct RingHeader {
 static_assert(sizeof(RingHeader) == 80, "ring header");
 
 template <typename QT, bool kSmemTables>
-__global__ void __launch_bounds__(1024, 1) qtable_scan_generic(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_generic(const __grid_constant__ ScanParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ThrlGame& G = p.game;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
   const int n = G.n_agents, T = G.max_steps, E = p.E, Hp = p.Hp;
   const bool is_agent = lane < n;
 
-  // ---- CTA-shared per-action tables: X[k] = scale(k), AQ[k] = (a/b)*X[k], XT[k] = X[k]/max_steps
-  double* lutX = reinterpret_cast<double*>(smem);
-  double* lutAQ = lutX + p.lut_total;
+  // ---- CTA-shared per-action tables: AQ[k] = (a/b)*scale(k), XT[k] = scale(k)/max_steps
+  double* lutAQ = reinterpret_cast<double*>(smem);
   double* lutXT = lutAQ + p.lut_total;
   {
     const double ab = __ddiv_rn(G.a, G.b);  // environments.py:23 self.a/self.b
@@ -71,7 +71,6 @@ __global__ void __launch_bounds__(1024, 1) qtable_scan_generic(const __grid_cons
       const ThrlAgentSpec& s = G.agent[i];
       for (int k = threadIdx.x; k < s.actions; k += blockDim.x) {
         const double x = scale_action(k, s.actions, s.action_lo, s.action_hi);
-        lutX[base + k] = x;
         lutAQ[base + k] = __dmul_rn(ab, x);
         lutXT[base + k] = __ddiv_rn(x, (double)T);  // trainer.py:66 scaled_acts / max_steps
       }
@@ -88,8 +87,9 @@ __global__ void __launch_bounds__(1024, 1) qtable_scan_generic(const __grid_cons
   double* newa = reinterpret_cast<double*>(slot + p.off_newa);     // [T] demand intercept (noisy only)
   double* P = reinterpret_cast<double*>(slot + p.off_P);           // [Hp] price ring
   uint8_t* act = slot + p.off_act;                                 // [n][Hp] action ring
-  uint16_t* rowbuf = reinterpret_cast<uint16_t*>(slot + p.off_row);  // [Hp] update-encode rows of the batch
-  QT* oldv = reinterpret_cast<QT*>(slot + p.off_old);                // [Hp-1] snapshot (agents.py:67)
+  uint16_t* rowbuf_all = reinterpret_cast<uint16_t*>(slot + p.off_row);  // [n][row_stride] update-encode rows of the batch
+  QT* oldv_all = reinterpret_cast<QT*>(slot + p.off_old);                // [n][old_stride] snapshot (agents.py:67)
+  int* des = reinterpret_cast<int*>(slot + p.off_des);                   // [n][4] per-epoch batch descriptor: L, first slot, fires, j offset
   double* hpw = reinterpret_cast<double*>(slot + p.off_hp);        // [n][5] alpha,gamma,eps_end,eps_step,eps
 
   // ---- lane i < n keeps agent i's constants in registers
@@ -129,15 +129,8 @@ __global__ void __launch_bounds__(1024, 1) qtable_scan_generic(const __grid_cons
       h[4] = p.eps[r * n + lane];
     }
     __syncwarp();
-    for (int i = 0, goff = 0; i < n; ++i) {
-      const ThrlAgentSpec& s = G.agent[i];
-      const QT* tb = tab + s.table_offset;
-      for (int row = 0; row <= s.states; ++row) {
-        const int g = row_argmax(tb + (size_t)row * s.actions, s.actions, lane);
-        if (lane == 0) Gc[goff + row] = (uint8_t)g;
-      }
-      goff += s.states + 1;
-    }
+    // greedy-action cache: 0xFF = not computed; filled on first visit, invalidated when the row is written
+    for (int c = lane; c < p.rows_total; c += 32) Gc[c] = 0xFF;
     double price = p.price[r];
     int pos = 0, my_len = 0;
     if (p.ring && !G.regular) {
@@ -200,11 +193,50 @@ __global__ void __launch_bounds__(1024, 1) qtable_scan_generic(const __grid_cons
       for (int t = 0; t < T; ++t) {
         int k = 0;
         double aq = 0.0;
+        int arow = 0;
         if (is_agent) {
           k = pre[t * n + lane];
-          if (k < 0) k = Gc[my_goff + act_row(price, my_msf, my_sf)];  // agents.py:84-88 on the frozen table
-          aq = lutAQ[my_lut + k];
+          if (k < 0) {  // agents.py:84-88 on the frozen table
+            arow = act_row(price, my_msf, my_sf);
+            const int g = Gc[my_goff + arow];
+            k = g == 0xFF ? -1 : g;
+          }
         }
+        unsigned need = __ballot_sync(kFull, is_agent && k < 0);  // greedy action of that row not cached yet
+        if (need) {
+          do {  // up to four agents per round: all their row loads are issued before any reduction
+            int ia[4], ra[4], bidx[4];
+            QT bval[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              ia[a] = need ? __ffs(need) - 1 : -1;
+              if (need) need &= need - 1;
+              bval[a] = NegInf<QT>::v();
+              bidx[a] = 0x7fffffff;
+              ra[a] = 0;
+              if (ia[a] >= 0) {
+                ra[a] = __shfl_sync(kFull, arow, ia[a]);
+                const ThrlAgentSpec& s = G.agent[ia[a]];
+                const QT* row = tab + s.table_offset + (size_t)ra[a] * s.actions;
+                for (int kk = lane; kk < s.actions; kk += 32) {
+                  const QT v = row[kk];
+                  if (v > bval[a] || bidx[a] == 0x7fffffff) { bval[a] = v; bidx[a] = kk; }
+                }
+              }
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              if (ia[a] < 0) continue;
+              const QT wm = warp_max(bval[a]);  // numpy.argmax: first maximal index (agents.py:88)
+              const int g = (int)__reduce_min_sync(kFull, (bidx[a] != 0x7fffffff && bval[a] == wm) ? (unsigned)bidx[a] : 0xffffffffu);
+              const int gi = __shfl_sync(kFull, my_goff, ia[a]);
+              if (lane == 0) Gc[gi + ra[a]] = (uint8_t)g;
+              if (lane == ia[a]) k = g;
+            }
+          } while (need);
+          __syncwarp();
+        }
+        if (is_agent) aq = lutAQ[my_lut + k];
         double Q = 0.0;  // environments.py:27 sum(A): ((0 + A0) + A1) + ...
         for (int i = 0; i < n; ++i) Q = __dadd_rn(Q, shfl_d(aq, i));
         const double na = p.noisy ? newa[t] : G.a;
@@ -230,78 +262,124 @@ __global__ void __launch_bounds__(1024, 1) qtable_scan_generic(const __grid_cons
       }
       __syncwarp();
 
-      // ---- train_net for every agent in order (trainer.py:70, agents.py:59-78)
+      // ---- train_net for every agent (trainer.py:70, agents.py:59-78).  Agents only touch their own tables, so their
+      //      sequential passes are independent chains: they are advanced together, up to eight agents' row loads in flight at once.
+      int Lmax = 0;
       for (int i = 0; i < n; ++i) {
         const int L = __shfl_sync(kFull, my_len, i);
         const int fires = __shfl_sync(kFull, (int)(!never_fires && my_len >= my_minmem), i);
-        if (fires) {
-          const ThrlAgentSpec& s = G.agent[i];
-          const int A = s.actions;
-          QT* tb = tab + s.table_offset;
-          const double alpha = hpw[i * 5 + 0], gamma = hpw[i * 5 + 1];
-          const double one_m_alpha = __dsub_rn(1.0, alpha);
+        if (fires && L > Lmax) Lmax = L;
+        if (lane == 0) {
           int first = pos - L;
           if (first < 0) first += Hp;
-          const int goff = __shfl_sync(kFull, my_goff, i), loff = __shfl_sync(kFull, my_lut, i);
-          // encodes (:62,:66) and the stale snapshot (:67), lane-parallel
-          for (int j = lane; j <= L; j += 32) {
-            int sl = first + j;
-            if (sl >= Hp) sl -= Hp;
-            rowbuf[j] = (uint16_t)upd_row(P[sl], s.max_state, (double)s.states);
-          }
-          __syncwarp();
-          for (int j = lane; j < L; j += 32) {
-            int sl = first + j;
-            if (sl >= Hp) sl -= Hp;
-            oldv[j] = tb[(size_t)rowbuf[j] * A + act[i * Hp + sl]];
-          }
-          __syncwarp();
-          // the sequential pass (:68-76); `dirty` marks rows whose greedy action must be recomputed
-          unsigned dirty = 0;  // lane l holds rows 32*l .. 32*l+31 (+1024*w in word w; rows > 1023 fall back below)
-          bool dirty_overflow = false;
-          int sl = first;
-          for (int j = 0; j < L; ++j) {
-            const int st = rowbuf[j], ns = rowbuf[j + 1];
-            const int k = act[i * Hp + sl];
-            int sn = sl + 1;
-            if (sn == Hp) sn = 0;
-            const double reward = __dmul_rn(P[sn], lutAQ[loff + k]);
-            const double next_max = (double)row_max(tb + (size_t)ns * A, A, lane);  // live table (:71)
-            const double nv = __dadd_rn(__dmul_rn(one_m_alpha, (double)oldv[j]),
-                                        __dmul_rn(alpha, __dadd_rn(reward, __dmul_rn(gamma, next_max))));
-            if ((k & 31) == lane) {  // the lane that owns column k
-              tb[(size_t)st * A + k] = (QT)nv;
-              if (cnt) atomicAdd(cnt + s.table_offset + (size_t)st * A + k, 1u);  // :76, fire-and-forget RED
-            }
-            if (st < 1024) {
-              if ((st >> 5) == lane) dirty |= 1u << (st & 31);
-            } else {
-              dirty_overflow = true;
-            }
-            sl = sn;
-          }
-          // refresh the greedy cache of the rows that were written
-          if (dirty_overflow) {
-            for (int row = 1024; row <= s.states; ++row) {
-              const int g = row_argmax(tb + (size_t)row * A, A, lane);
-              if (lane == 0) Gc[goff + row] = (uint8_t)g;
-            }
-          }
-          unsigned any = __ballot_sync(kFull, dirty != 0);
-          while (any) {
-            const int src = __ffs(any) - 1;
-            const unsigned word = __shfl_sync(kFull, dirty, src);
-            const int bit = __ffs(word) - 1;
-            const int row = src * 32 + bit;
-            const int g = row_argmax(tb + (size_t)row * A, A, lane);
-            if (lane == 0) Gc[goff + row] = (uint8_t)g;
-            if (lane == src) dirty &= dirty - 1;
-            any = __ballot_sync(kFull, dirty != 0);
-          }
-          if (lane == i) my_len = 0;  // :77 memory.empty()
-          __syncwarp();
+          des[i * 4 + 0] = L; des[i * 4 + 1] = first; des[i * 4 + 2] = fires;
         }
       }
+      __syncwarp();
+      for (int i = 0; i < n; ++i) {  // encodes (:62,:66) and the stale snapshot (:67), lane-parallel
+        if (!des[i * 4 + 2]) continue;
+        const ThrlAgentSpec& s = G.agent[i];
+        const int L = des[i * 4 + 0], first = des[i * 4 + 1], A = s.actions;
+        uint16_t* rowbuf = rowbuf_all + i * p.row_stride;
+        QT* oldv = oldv_all + i * p.old_stride;
+        const QT* tb = tab + s.table_offset;
+        if (lane == 0) des[i * 4 + 3] = Lmax - L;
+        for (int j = lane; j <= L; j += 32) {
+          int sl = first + j;
+          if (sl >= Hp) sl -= Hp;
+          rowbuf[j] = (uint16_t)upd_row(P[sl], s.max_state, (double)s.states);
+        }
+        __syncwarp();
+        for (int j = lane; j < L; j += 32) {
+          int sl = first + j;
+          if (sl >= Hp) sl -= Hp;
+          oldv[j] = tb[(size_t)rowbuf[j] * A + act[i * Hp + sl]];
+        }
+      }
+      __syncwarp();
+      for (int j = 0; j < Lmax; ++j) {  // the sequential pass (:68-76)
+        if (!kSmemTables && lane < n && des[lane * 4 + 2]) {  // HBM tables: pull the rows of step j+4 into L2 early
+          const int jp = j + 4 - des[lane * 4 + 3];
+          if (jp >= 0 && jp < des[lane * 4 + 0]) {
+            const ThrlAgentSpec& s = G.agent[lane];
+            const QT* row = tab + s.table_offset + (size_t)rowbuf_all[lane * p.row_stride + jp + 1] * s.actions;
+            for (int b = 0; b < s.actions * (int)sizeof(QT); b += 128)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(row) + b));
+          }
+        }
+        for (int g0 = 0; g0 < n; g0 += 8) {
+          QT loc[8];
+          bool on[8];
+          bool wide = false;  // some agent has more than 128 actions: general loop below
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            const int i = g0 + a;
+            on[a] = i < n && des[i * 4 + 2] && j >= des[i * 4 + 3];
+            if (on[a] && G.agent[i].actions > 128) wide = true;
+          }
+          if (!wide) {
+            // live row max (:71): every active agent's row is loaded into registers first (up to 8 x 4 loads in flight
+            // per lane), only then reduced -- the agents' chains are independent, so their memory latencies overlap
+            QT v[8][4];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+              const int i = g0 + a;
+              const ThrlAgentSpec& s = G.agent[on[a] ? i : 0];
+              const int A = s.actions;
+              const int ns = on[a] ? (int)rowbuf_all[i * p.row_stride + (j - des[i * 4 + 3]) + 1] : 0;
+              const QT* row = tab + s.table_offset + (size_t)ns * A;
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int kk = lane + 32 * c;
+                v[a][c] = (on[a] && kk < A) ? row[kk] : NegInf<QT>::v();
+              }
+            }
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+              const QT m01 = v[a][0] > v[a][1] ? v[a][0] : v[a][1], m23 = v[a][2] > v[a][3] ? v[a][2] : v[a][3];
+              loc[a] = m01 > m23 ? m01 : m23;
+            }
+          } else {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+              const int i = g0 + a;
+              loc[a] = NegInf<QT>::v();
+              if (on[a]) {
+                const ThrlAgentSpec& s = G.agent[i];
+                const int ns = rowbuf_all[i * p.row_stride + (j - des[i * 4 + 3]) + 1];
+                const QT* row = tab + s.table_offset + (size_t)ns * s.actions;
+                for (int k = lane; k < s.actions; k += 32) { const QT v = row[k]; loc[a] = v > loc[a] ? v : loc[a]; }
+              }
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 8; ++a) {
+            if (!on[a]) continue;
+            const int i = g0 + a;
+            const ThrlAgentSpec& s = G.agent[i];
+            const int jj = j - des[i * 4 + 3];
+            int sl = des[i * 4 + 1] + jj;
+            if (sl >= Hp) sl -= Hp;
+            int sn = sl + 1;
+            if (sn == Hp) sn = 0;
+            const int st = rowbuf_all[i * p.row_stride + jj], k = act[i * Hp + sl];
+            const int loff = __shfl_sync(kFull, my_lut, i), goff = __shfl_sync(kFull, my_goff, i);
+            const double alpha = hpw[i * 5 + 0], gamma = hpw[i * 5 + 1];
+            const double reward = __dmul_rn(P[sn], lutAQ[loff + k]);
+            const double next_max = (double)warp_max(loc[a]);
+            const double nv = __dadd_rn(__dmul_rn(__dsub_rn(1.0, alpha), (double)oldv_all[i * p.old_stride + jj]),
+                                        __dmul_rn(alpha, __dadd_rn(reward, __dmul_rn(gamma, next_max))));
+            if ((k & 31) == lane) {  // the lane that owns column k: it alone ever reads or writes that column
+              tab[s.table_offset + (size_t)st * s.actions + k] = (QT)nv;
+              if (cnt) atomicAdd(cnt + s.table_offset + (size_t)st * s.actions + k, 1u);  // :76, fire-and-forget RED
+            }
+            if (lane == 0) Gc[goff + st] = 0xFF;  // the row changed: its greedy action is recomputed on the next visit
+          }
+        }
+      }
+      for (int i = 0; i < n; ++i)
+        if (des[i * 4 + 2] && lane == i) my_len = 0;  // :77 memory.empty()
+      __syncwarp();
       // epsilon decay, every epoch (:78); logs
       if (is_agent) {
         double* h = hpw + lane * 5;

@@ -101,7 +101,6 @@ __global__ void __launch_bounds__(32 * kLpcMaxWarps, 1) qtable_scan_lpc(const __
     const double* lutLogR = lutLog + ag;
     const double* lutLogX = lutLog + 2 + ag;
     QT* qg = reinterpret_cast<QT*>(p.q) + rr * G.run_stride + G.agent[ag].table_offset;
-    uint32_t* cnt = p.counter ? p.counter + rr * G.run_stride + G.agent[ag].table_offset : nullptr;
     double alpha, gamma, epsend, epsstep;
     if (p.hp) {
       const double* h = p.hp + (rr * 2 + ag) * 4;

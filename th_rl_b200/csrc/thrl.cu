@@ -99,7 +99,27 @@ void plan_generic(thrl::ScanParams* p, bool smem_tables, size_t elem) {
   const ThrlGame& G = p->game;
   const int n = G.n_agents, T = G.max_steps, Hp = p->Hp;
   int lut = 0, rows = 0;
-  for (int i = 0; i < n; ++i) { lut += G.agent[i].actions; rows += G.agent[i].states + 1; }
+  // rows the price can reach: price <= a - a * sum_i min(action_range_i) (environments.py:25-32 with new_a <= a), +2 rows
+  // of slack for rounding; the call's initial price may lie above and is handled uncached
+  double lo_sum = 0.0;
+  bool bounded = G.a >= 0.0 && G.b > 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double lo = G.agent[i].action_lo < G.agent[i].action_hi ? G.agent[i].action_lo : G.agent[i].action_hi;
+    if (!(lo >= 0.0)) bounded = false;
+    lo_sum += lo;
+  }
+  for (int i = 0; i < n; ++i) {
+    int cap = G.agent[i].states + 1;
+    if (bounded) {
+      double pmax = G.a - G.a * lo_sum;
+      if (pmax < 0.0) pmax = 0.0;
+      const double rmax = pmax / G.agent[i].max_state * (double)G.agent[i].states + 2.5;
+      if (rmax < (double)cap) cap = (int)rmax;
+    }
+    p->gcap[i] = cap;
+    lut += G.agent[i].actions;
+    rows += cap;
+  }
   p->lut_total = lut;
   p->rows_total = rows;
   p->cta_bytes = align_up(2 * lut * 8, 16);
@@ -134,12 +154,16 @@ int launch_generic(thrl::ScanParams& p, const DeviceInfo& dev, cudaStream_t stre
   int warps = (dev.smem_optin - p.cta_bytes) / p.warp_bytes;
   if (warps < 1) return fail(THRL_ERR_UNSUPPORTED, "one run needs %d B of shared memory (> %d B)", p.warp_bytes + p.cta_bytes, dev.smem_optin);
   if (warps > (smem_tables ? 32 : 16)) warps = smem_tables ? 32 : 16;
-  const long long needed_ctas = (p.n_runs + warps - 1) / warps;
+  // every warp plays whole runs one after another: spread the runs evenly over the rounds that are needed anyway
   int grid = dev.sms;
-  if (needed_ctas < grid) {  // few runs: spread them one warp-run per SM first
-    warps = (int)((p.n_runs + dev.sms - 1) / dev.sms);
+  {
+    const long long slots = (long long)dev.sms * warps;
+    const long long rounds = (p.n_runs + slots - 1) / slots;
+    const long long per_round = (p.n_runs + rounds - 1) / rounds;
+    warps = (int)((per_round + dev.sms - 1) / dev.sms);
     if (warps < 1) warps = 1;
-    grid = (int)((p.n_runs + warps - 1) / warps);
+    grid = (int)((per_round + warps - 1) / warps);
+    if (grid > dev.sms) grid = dev.sms;
   }
   const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
   auto kern = smem_tables ? thrl::qtable_scan_generic<T, true> : thrl::qtable_scan_generic<T, false>;

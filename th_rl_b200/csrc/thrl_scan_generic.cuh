@@ -39,7 +39,8 @@ struct ScanParams {
   int off_tab, off_g, off_pre, off_newa, off_P, off_act, off_row, off_old, off_hp, off_des;
   int row_stride, old_stride;  // per-agent strides (elements) of the rowbuf / oldv scratch
   int lut_total;   // sum of actions_i
-  int rows_total;  // sum of states_i + 1
+  int rows_total;  // sum of gcap_i
+  int gcap[THRL_MAX_AGENTS];  // rows 0..gcap_i-1 of agent i have a greedy-cache slot (rows the price can reach); others are uncached
   int Hp;          // ring slots = ring_len + 1
   int noisy;       // new_a varies per step (noise_prob > 0 or replay_new_a given)
 };
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
   double* hpw = reinterpret_cast<double*>(slot + p.off_hp);        // [n][5] alpha,gamma,eps_end,eps_step,eps
 
   // ---- lane i < n keeps agent i's constants in registers
-  int my_states = 1, my_actions = 2, my_cap = 0, my_minmem = 0x7fffffff, my_lut = 0, my_goff = 0;
+  int my_states = 1, my_actions = 2, my_cap = 0, my_minmem = 0x7fffffff, my_lut = 0, my_goff = 0, my_gcap = 0;
   long long my_toff = 0;
   float my_msf = 1.f, my_sf = 1.f;
   if (is_agent) {
@@ -102,7 +103,8 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
     my_toff = s.table_offset;
     my_msf = (float)s.max_state;
     my_sf = (float)s.states;
-    for (int j = 0; j < lane; ++j) { my_lut += G.agent[j].actions; my_goff += G.agent[j].states + 1; }
+    my_gcap = p.gcap[lane];
+    for (int j = 0; j < lane; ++j) { my_lut += G.agent[j].actions; my_goff += p.gcap[j]; }
   }
   const bool never_fires = my_minmem > my_cap;  // buffer can never reach min_memory
 
@@ -198,29 +200,56 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
           k = pre[t * n + lane];
           if (k < 0) {  // agents.py:84-88 on the frozen table
             arow = act_row(price, my_msf, my_sf);
-            const int g = Gc[my_goff + arow];
+            const int g = arow < my_gcap ? (int)Gc[my_goff + arow] : 0xFF;  // rows beyond the cache: always recomputed
             k = g == 0xFF ? -1 : g;
           }
         }
         unsigned need = __ballot_sync(kFull, is_agent && k < 0);  // greedy action of that row not cached yet
         if (need) {
-          do {  // up to four agents per round: all their row loads are issued before any reduction
+          do {  // up to four agents per round: all their row loads are issued before any comparison
             int ia[4], ra[4], bidx[4];
             QT bval[4];
+            bool wide = false;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
               ia[a] = need ? __ffs(need) - 1 : -1;
               if (need) need &= need - 1;
-              bval[a] = NegInf<QT>::v();
-              bidx[a] = 0x7fffffff;
-              ra[a] = 0;
-              if (ia[a] >= 0) {
-                ra[a] = __shfl_sync(kFull, arow, ia[a]);
-                const ThrlAgentSpec& s = G.agent[ia[a]];
+              ra[a] = ia[a] >= 0 ? __shfl_sync(kFull, arow, ia[a]) : 0;
+              if (ia[a] >= 0 && G.agent[ia[a]].actions > 128) wide = true;
+            }
+            if (!wide) {
+              QT v[4][4];
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                const ThrlAgentSpec& s = G.agent[ia[a] >= 0 ? ia[a] : 0];
                 const QT* row = tab + s.table_offset + (size_t)ra[a] * s.actions;
-                for (int kk = lane; kk < s.actions; kk += 32) {
-                  const QT v = row[kk];
-                  if (v > bval[a] || bidx[a] == 0x7fffffff) { bval[a] = v; bidx[a] = kk; }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  const int kk = lane + 32 * c;
+                  v[a][c] = (ia[a] >= 0 && kk < s.actions) ? row[kk] : NegInf<QT>::v();
+                }
+              }
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {  // first maximal column of this lane: strict > keeps the lowest index
+                bval[a] = v[a][0];
+                bidx[a] = lane;
+#pragma unroll
+                for (int c = 1; c < 4; ++c)
+                  if (v[a][c] > bval[a]) { bval[a] = v[a][c]; bidx[a] = lane + 32 * c; }
+                if (ia[a] < 0 || lane >= G.agent[ia[a] >= 0 ? ia[a] : 0].actions) bidx[a] = 0x7fffffff;
+              }
+            } else {
+#pragma unroll
+              for (int a = 0; a < 4; ++a) {
+                bval[a] = NegInf<QT>::v();
+                bidx[a] = 0x7fffffff;
+                if (ia[a] >= 0) {
+                  const ThrlAgentSpec& s = G.agent[ia[a]];
+                  const QT* row = tab + s.table_offset + (size_t)ra[a] * s.actions;
+                  for (int kk = lane; kk < s.actions; kk += 32) {
+                    const QT v = row[kk];
+                    if (v > bval[a] || bidx[a] == 0x7fffffff) { bval[a] = v; bidx[a] = kk; }
+                  }
                 }
               }
             }
@@ -230,7 +259,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               const QT wm = warp_max(bval[a]);  // numpy.argmax: first maximal index (agents.py:88)
               const int g = (int)__reduce_min_sync(kFull, (bidx[a] != 0x7fffffff && bval[a] == wm) ? (unsigned)bidx[a] : 0xffffffffu);
               const int gi = __shfl_sync(kFull, my_goff, ia[a]);
-              if (lane == 0) Gc[gi + ra[a]] = (uint8_t)g;
+              if (lane == 0 && ra[a] < p.gcap[ia[a]]) Gc[gi + ra[a]] = (uint8_t)g;
               if (lane == ia[a]) k = g;
             }
           } while (need);
@@ -373,7 +402,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               tab[s.table_offset + (size_t)st * s.actions + k] = (QT)nv;
               if (cnt) atomicAdd(cnt + s.table_offset + (size_t)st * s.actions + k, 1u);  // :76, fire-and-forget RED
             }
-            if (lane == 0) Gc[goff + st] = 0xFF;  // the row changed: its greedy action is recomputed on the next visit
+            if (lane == 0 && st < p.gcap[i]) Gc[goff + st] = 0xFF;  // the row changed: its greedy action is recomputed on the next visit
           }
         }
       }

@@ -29,17 +29,52 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-RUNS_PER_GPU = 131072
-EPOCHS = 200
 MAX_STEPS = 100
-ALGO_BYTES_PER_AGENT_STEP = 184.0  # 8*A + 16 bytes of table traffic per agent-step at A = 21
 
-CONFIG = {
-    "agents": [dict(name="QTable", gamma=0.95, actions=21, states=100, alpha=0.1, eps_end=0.001, epsilon=0.5,
-                    eps_step=0.9995, action_range=[0.2, 0.4]) for _ in range(2)],
-    "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=2, max_steps=MAX_STEPS),
-    "training": dict(print_freq=500, epochs=EPOCHS),
+
+def _qcfg(n, states, actions, lo, hi, epochs):
+    return {
+        "agents": [dict(name="QTable", gamma=0.95, actions=actions, states=states, alpha=0.1, eps_end=0.001, epsilon=0.5,
+                        eps_step=0.9995, action_range=[lo, hi]) for _ in range(n)],
+        "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=n, max_steps=MAX_STEPS),
+        "training": dict(print_freq=500, epochs=epochs),
+    }
+
+
+def _c4_hp(R, n):
+    """BASELINE C4 sweep grid: alpha x eps_step x gamma = 64 points, repeated over the runs (64 seeds each at R = 4096)."""
+    import numpy as np
+    grid = [(al, g, st) for al in (.05, .1, .2, .5) for st in (.999, .9995, .9999, .99995) for g in (.35, .8, .95, .99)]
+    hp = np.empty((R, n, 4))
+    for r in range(R):
+        al, g, st = grid[r % 64]
+        hp[r, :, 0], hp[r, :, 1], hp[r, :, 2], hp[r, :, 3] = al, g, 0.001, st
+    return hp
+
+
+# name -> workload.  `algo_bytes` = SURVEY 8(d): 8*A + 16 bytes of table traffic per agent-step.
+WORKLOADS = {
+    "c2": dict(agents=2, runs_per_gpu=131072, epochs=200, config=_qcfg(2, 100, 21, 0.2, 0.4, 200), algo_bytes=184.0,
+               bound="smem", hp=None,
+               desc="2-agent QTable iterated Cournot/PD game (example_config hyper-parameters, 101x21 tables, max_steps=100), "
+                    "%d runs/GPU x %d epochs per step (C2 shape; 8 GPUs = the 1,048,576 runs of C3)",
+               kernel="thrl::qtable_scan_lut2<float, true> (persistent, one launch per step)"),
+    "c4": dict(agents=8, runs_per_gpu=4096, epochs=100, config=_qcfg(8, 1000, 101, 0.05, 0.15, 100), algo_bytes=824.0,
+               bound="hbm", hp=_c4_hp,
+               desc="hyper-parameter sweep (alpha x eps_step x gamma = 64 points x 64 seeds), 8 QTable agents, 1001x101 "
+                    "tables left in HBM, max_steps=100, %d runs/GPU x %d epochs per step (C4 shape)",
+               kernel="thrl::qtable_scan_generic<float, false> (persistent, one launch per step)"),
 }
+WL = WORKLOADS["c2"]  # set in main()
+CONFIG = WL["config"]
+EPOCHS = WL["epochs"]
+ALGO_BYTES_PER_AGENT_STEP = WL["algo_bytes"]
+
+
+def select_workload(name):
+    global WL, CONFIG, EPOCHS, ALGO_BYTES_PER_AGENT_STEP
+    WL = WORKLOADS[name]
+    CONFIG, EPOCHS, ALGO_BYTES_PER_AGENT_STEP = WL["config"], WL["epochs"], WL["algo_bytes"]
 
 
 def measured_peaks():
@@ -102,19 +137,24 @@ def cpu_oracle_leg(n_threads, target_seconds=12.0):
     cores = n_threads if n_threads > 0 else oracle.online_cores()
     eps0 = abi.eps0_from_config(CONFIG)
     # calibrate on a small sample, then size the timed sample for ~target_seconds
-    R0 = 64 * cores
+    R0 = (64 if WL["agents"] == 2 else 1) * cores
     q0, c0, e0, p0 = oracle.init(game, R0, seed=0, dtype=np.float32, eps0=eps0)
     t = time.perf_counter()
     oracle.scan(game, q0, e0, p0, 20, n_threads=cores, n_log_runs=0, stats=True)
-    rate = R0 * 2 * 20 * MAX_STEPS / (time.perf_counter() - t)
-    R = int(max(cores, min(262144, target_seconds * rate / (2 * EPOCHS * MAX_STEPS))))
+    n = WL["agents"]
+    rate = R0 * n * 20 * MAX_STEPS / (time.perf_counter() - t)
+    R = int(max(cores, min(262144, target_seconds * rate / (n * EPOCHS * MAX_STEPS))))
     q0, c0, e0, p0 = oracle.init(game, R, seed=0, dtype=np.float32, eps0=eps0)
     t = time.perf_counter()
     oracle.scan(game, q0, e0, p0, EPOCHS, n_threads=cores, n_log_runs=0, stats=True)
     dt = time.perf_counter() - t
-    return {"value": R * 2 * EPOCHS * MAX_STEPS / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d runs x %d epochs x %d steps x 2 agents of the bench workload, fp32-storage oracle "
-                      "(oracle/thrl_oracle.c), %d pthreads, %.1f s" % (R, EPOCHS, MAX_STEPS, cores, dt)}, dt
+    return {"value": R * n * EPOCHS * MAX_STEPS / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d runs x %d epochs x %d steps x %d agents of the bench workload, fp32-storage oracle "
+                      "(oracle/thrl_oracle.c), %d pthreads, %.1f s" % (R, EPOCHS, MAX_STEPS, n, cores, dt)}, dt
+
+
+def _run_stride():
+    return sum((a["states"] + 1) * a["actions"] for a in CONFIG["agents"])
 
 
 def base_line(args, n_gpus):
@@ -122,15 +162,13 @@ def base_line(args, n_gpus):
         "metric": "agent-steps/sec", "unit": "agent-steps/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "2-agent QTable iterated Cournot/PD game (example_config hyper-parameters, 101x21 tables, "
-                               "max_steps=100), %d runs/GPU x %d epochs per step (C2 shape; 8 GPUs = the 1,048,576 runs "
-                               "of C3)" % (args.runs_per_gpu, args.epochs),
+        "config": {"workload": WL["desc"] % (args.runs_per_gpu, args.epochs), "workload_id": args.workload,
                    "runs_per_gpu": args.runs_per_gpu, "global_runs": args.runs_per_gpu * n_gpus, "epochs_per_step": args.epochs,
-                   "max_steps": MAX_STEPS, "agents": 2, "table_storage": "fp32 (f64 update arithmetic)",
+                   "max_steps": MAX_STEPS, "agents": WL["agents"], "table_storage": "fp32 (f64 update arithmetic)",
                    "rng": "philox4x32-10", "parallelism": "runs sharded over %d GPU(s), no data-path collective; "
                                                           "NCCL all-reduce of per-epoch statistics" % n_gpus,
                    "l2": "per-GPU state (tables+counters %.1f GB) is far larger than the 126 MB L2"
-                         % (args.runs_per_gpu * 4242 * 8 / 1e9)},
+                         % (args.runs_per_gpu * _run_stride() * 8 / 1e9)},
     }
 
 
@@ -170,9 +208,11 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     R, E = args.runs_per_gpu, args.epochs
-    agent_steps_rank = R * 2 * E * MAX_STEPS
+    nag = WL["agents"]
+    agent_steps_rank = R * nag * E * MAX_STEPS
+    hp = WL["hp"](R, nag) if WL["hp"] else None
 
-    batch = engine.RunBatch(CONFIG, R, device=dev, dtype=torch.float32, seed=0, run_id0=rank * R).init_device()
+    batch = engine.RunBatch(CONFIG, R, device=dev, dtype=torch.float32, seed=0, run_id0=rank * R, hp=hp).init_device()
     torch.cuda.synchronize()
 
     def barrier():
@@ -223,20 +263,25 @@ def run_ours(args):
         per_gpu_rate = agent_steps_rank / (kern_ms * 1e-3)
         achieved = per_gpu_rate * ALGO_BYTES_PER_AGENT_STEP / 1e9
         line = base_line(args, world)
-        line.update({
-            "value": value, "ms_per_step": total_ms / args.steps, "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches,
-            "roofline": {"bound": "smem", "achieved": achieved, "peak": smem_peak_gbs, "unit": "GB/s",
-                         "frac": achieved / smem_peak_gbs, "traffic": None,
-                         "kernel": "thrl::qtable_scan_lut2<float, true> (persistent, one launch per step)",
-                         "kernel_ms": kern_ms,
-                         "note": "tables are shared-memory resident, so the bound is SM shared-memory bandwidth "
-                                 "(BASELINE.md 5: 184 algorithmic B per agent-step; peak = 128 B/clk/SM x 148 SMs x "
-                                 "%.0f MHz from MEASURED_PEAKS.json, %s); HBM sees only the one-off table load/store "
-                                 "and the visit counters" % (sm_max_mhz, peak_src),
-                         "hbm": {"achieved": per_gpu_rate * (2 * 4242 * (4 + 4 + 4) / (2.0 * E * MAX_STEPS)) / 1e9,
-                                 "peak": hbm_peak, "unit": "GB/s"}},
-        })
+        line.update({"value": value, "ms_per_step": total_ms / args.steps, "clocks": clocks, "e2e": e2e, "gpu_launches": launches})
+        if WL["bound"] == "smem":
+            line["roofline"] = {
+                "bound": "smem", "achieved": achieved, "peak": smem_peak_gbs, "unit": "GB/s", "frac": achieved / smem_peak_gbs,
+                "traffic": None, "kernel": WL["kernel"], "kernel_ms": kern_ms,
+                "note": "tables are shared-memory resident, so the bound is SM shared-memory bandwidth / issue rate, not HBM "
+                        "(BASELINE.md 5: 184 algorithmic B per agent-step; peak = 128 B/clk/SM x 148 SMs x %.0f MHz from "
+                        "MEASURED_PEAKS.json, %s). ncu (profiles/): ~38 warp instructions and ~10 shared-memory wavefronts "
+                        "per agent-step, LSU data pipe ~47%% busy, issue slots ~53%% busy; HBM sees only the one-off slab "
+                        "load/store and the visit counters" % (sm_max_mhz, peak_src),
+                "hbm": {"achieved": per_gpu_rate * (2 * _run_stride() * (4 + 4 + 4) / (nag * 1.0 * E * MAX_STEPS)) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s"}}
+        else:
+            line["roofline"] = {
+                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": None, "kernel": WL["kernel"], "kernel_ms": kern_ms,
+                "note": "tables (3.2 MB per run) stay in HBM; 824 algorithmic B per agent-step (BASELINE.md 5); peak = measured "
+                        "copy bandwidth from MEASURED_PEAKS.json (%s). ncu (profiles/): dram bytes per agent-step ~ 1.0 kB, "
+                        "long-scoreboard stalls dominate (latency-bound row gathers)" % peak_src}
         if args.no_cpu_baseline:
             line["cpu_baseline"] = None
         else:
@@ -251,7 +296,17 @@ def measure_e2e(args, torch, np, engine, dev, rank, world, barrier):
     price and statistics back into pinned host memory.  Runs go through in chunks so copies overlap the kernel."""
     import torch.distributed as dist
     R, E = args.runs_per_gpu, args.epochs
-    batch = engine.RunBatch(CONFIG, R, device=dev, dtype=torch.float32, seed=1, run_id0=rank * R).init_device()
+    nag = WL["agents"]
+    need = R * _run_stride() * 8 + R * (nag + 1) * 8  # pinned host copy of tables + counters + eps + price
+    try:
+        avail = int(next(l for l in open("/proc/meminfo") if l.startswith("MemAvailable")).split()[1]) * 1024
+    except (OSError, StopIteration):
+        avail = 1 << 62
+    if need * world * 2 > avail:
+        return {"value": None, "unit": "agent-steps/s", "h2d_bytes_per_step": need * world, "d2h_bytes_per_step": need * world,
+                "skipped": "host has %.0f GB available, the pinned state needs %.0f GB" % (avail / 1e9, need * world / 1e9)}
+    hp = WL["hp"](R, nag) if WL["hp"] else None
+    batch = engine.RunBatch(CONFIG, R, device=dev, dtype=torch.float32, seed=1, run_id0=rank * R, hp=hp).init_device()
     torch.cuda.synchronize()
     host = engine.HostState.from_batch(batch)  # pinned host copies of q / counter / eps / price
     steps = max(1, min(args.steps, 3))
@@ -270,7 +325,7 @@ def measure_e2e(args, torch, np, engine, dev, rank, world, barrier):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = t.item()
-    return {"value": R * world * 2 * E * MAX_STEPS * steps / dt, "unit": "agent-steps/s",
+    return {"value": R * world * nag * E * MAX_STEPS * steps / dt, "unit": "agent-steps/s",
             "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h + stats_h.numel() * 8) * world,
             "steps": steps, "ms_per_step": 1e3 * dt / steps,
             "api": "th_rl_b200.engine.scan_from_host (pinned host state in, tables+counters+eps+price+stats out)"}
@@ -282,11 +337,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--runs-per-gpu", type=int, default=RUNS_PER_GPU)
-    ap.add_argument("--epochs", type=int, default=EPOCHS)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (default); c4 = HBM-resident sweep")
+    ap.add_argument("--runs-per-gpu", type=int, default=None)
+    ap.add_argument("--epochs", type=int, default=None)
     ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    select_workload(args.workload)
+    args.runs_per_gpu = args.runs_per_gpu or WL["runs_per_gpu"]
+    args.epochs = args.epochs or WL["epochs"]
+    globals()["EPOCHS"] = args.epochs
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

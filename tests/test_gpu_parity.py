@@ -226,3 +226,47 @@ def test_full_size_properties():
     for r in idx:
         ref = oracle.scan(game, q0[r:r + 1], eps0[r:r + 1], p0[r:r + 1], E, seed=2, run_id0=int(r))
         assert np.array_equal(b.q[r].cpu().numpy(), ref.q[0])
+
+
+def _c4_cfg(states, actions, n=8, T=100, lo=0.05, hi=0.15):
+    a = dict(name="QTable", gamma=0.95, actions=actions, states=states, alpha=0.1, eps_end=0.001, epsilon=0.5,
+             eps_step=0.9995, action_range=[lo, hi])
+    return {"agents": [dict(a) for _ in range(n)],
+            "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=n, max_steps=T),
+            "training": dict(print_freq=500, epochs=3)}
+
+
+def test_c4_full_shape_matches_oracle(kernel_choice):
+    """BASELINE C4 at its real shape (8 agents, 1001x101 tables left in HBM, per-run hyper-parameters): bit-exact vs oracle."""
+    if kernel_choice not in ("auto", "generic"):
+        pytest.skip("C4 always runs on the general kernel")
+    _philox_case(_c4_cfg(1000, 101), 12, 3, np.float32, seed=21, run_id0=5, hp=True)
+    _philox_case(_c4_cfg(1000, 101), 6, 2, np.float64, seed=22, hp=True)
+
+
+def test_wide_action_tables_match_oracle(kernel_choice):
+    """More than 128 actions (several columns per lane, the general load loop) and 3 agents; also a 2-agent case with
+    200 actions, which exceeds what the specialised kernels take and must fall back to the general one."""
+    if kernel_choice not in ("auto", "generic"):
+        pytest.skip("wide tables always run on the general kernel")
+    _philox_case(_c4_cfg(300, 150, n=3, T=40, lo=0.1, hi=0.3), 20, 4, np.float32, seed=23, hp=True)
+    _philox_case(_c4_cfg(120, 200, n=2, T=60, lo=0.2, hi=0.45), 20, 4, np.float32, seed=24)
+
+
+def test_initial_price_above_reachable_rows(kernel_choice):
+    """The call's initial price may encode to a row the demand curve can never reach again (beyond the greedy-cache bound):
+    start every run at p0 close to a, which is far above a - a*sum(lo)."""
+    torch, oracle, engine = _mods()
+    cfg = _c4_cfg(500, 41, n=4, T=30, lo=0.1, hi=0.2)
+    game = oracle.layout(cfg)
+    R, E = 16, 3
+    q0, c0, eps0, p0 = oracle.init(game, R, seed=31, dtype=np.float32, eps0=abi.eps0_from_config(cfg))
+    p0 = np.linspace(9.0, 9.99, R)
+    ref = oracle.scan(game, q0, eps0, p0, E, seed=31, trace=True)
+    b = engine.RunBatch(cfg, R, seed=31)
+    b.load_state(q0, eps0, p0)
+    out = b.scan(E, trace=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.trace_actions.cpu().numpy(), ref.trace_actions)
+    assert np.array_equal(b.q.cpu().numpy(), ref.q)
+    assert np.array_equal(b.counter.cpu().numpy().view(np.uint32), ref.counter)

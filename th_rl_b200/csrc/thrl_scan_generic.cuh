@@ -8,6 +8,8 @@
 //
 // Restated reference lines: see include/thrl.h; the per-step order is the one in SURVEY.md Appendix A.
 #pragma once
+#include <type_traits>
+
 #include "thrl_device.cuh"
 
 namespace thrl {
@@ -336,7 +338,8 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(row) + b));
           }
         }
-        for (int g0 = 0; g0 < n; g0 += 8) {
+        auto group = [&](auto g0c) {
+          constexpr int g0 = decltype(g0c)::value;  // compile-time base: per-agent constants become immediate operands
           QT loc[8];
           bool on[8];
           bool wide = false;  // some agent has more than 128 actions: general loop below
@@ -404,7 +407,9 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
             }
             if (lane == 0 && st < p.gcap[i]) Gc[goff + st] = 0xFF;  // the row changed: its greedy action is recomputed on the next visit
           }
-        }
+        };
+        group(std::integral_constant<int, 0>{});
+        if (n > 8) group(std::integral_constant<int, 8>{});
       }
       for (int i = 0; i < n; ++i)
         if (des[i * 4 + 2] && lane == i) my_len = 0;  // :77 memory.empty()

@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
   double2* rc = reinterpret_cast<double2*>(slot + p.off_scr + align16(2 * T * 8));  // [T][2] (reward, (1-alpha)*old)
 
   const bool in0 = lane < A0, in1 = lane < A1;
+  const bool hi_half = lane >= 16, store_lane = (lane & 15) == 0;
+  unsigned char* tab_h = reinterpret_cast<unsigned char*>(hi_half ? tab1 : tab0);
   const int L0 = p.L[0], L1 = p.L[1];
   const uint32_t dp_b = (uint32_t)A1 | (1u << 8);  // joint = dp4a(k0 | k1<<8, A1 | 1<<8)
   const double* lutLogLane = lutLog + (lane & 3);
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
       alpha1 = G.agent[1].alpha; gamma1 = G.agent[1].gamma; epsend1 = G.agent[1].eps_end; epsstep1 = G.agent[1].eps_step;
     }
     const double oma0 = __dsub_rn(1.0, alpha0), oma1 = __dsub_rn(1.0, alpha1);
+    const double alpha_h = hi_half ? alpha1 : alpha0, gamma_h = hi_half ? gamma1 : gamma0;
     double eps0 = p.eps[r * 2], eps1 = p.eps[r * 2 + 1];
     const double price_in = p.price[r];
 
@@ -328,16 +331,19 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
         if (lane == 0) *reinterpret_cast<QT*>(reinterpret_cast<unsigned char*>(tab) + cell_off) = (QT)nv;   // :75
       };
       if (L0 == L1) {
+        // Both agents in one instruction stream: the two row maxima are warp reductions, the f64 arithmetic that follows is
+        // evaluated once with lanes 0-15 carrying agent 0 and lanes 16-31 agent 1; lanes 0 and 16 store.
         const uint4* mp = reinterpret_cast<const uint4*>(meta);
-        const double2* vp = rc;
+        const double2* vp = rc + (lane >> 4);
 #pragma unroll 2
         for (int j = 0; j < L0; ++j) {
           const uint4 m = mp[j];
-          const double2 v0 = vp[2 * j], v1 = vp[2 * j + 1];
+          const double2 v = vp[2 * j];
           const double mx0 = load_max(tab0_lane, A0, in0, m.x);
           const double mx1 = load_max(tab1_lane, A1, in1, m.z);
-          store_cell(tab0, m.y, 0.0, mx0, alpha0, gamma0, v0);
-          store_cell(tab1, m.w, 0.0, mx1, alpha1, gamma1, v1);
+          const double mx = hi_half ? mx1 : mx0;
+          const double nv = __dadd_rn(v.y, __dmul_rn(alpha_h, __dadd_rn(v.x, __dmul_rn(gamma_h, mx))));  // :72-74
+          if (store_lane) *reinterpret_cast<QT*>(tab_h + (hi_half ? m.w : m.y)) = (QT)nv;                 // :75
           __syncwarp();
         }
       } else {

@@ -16,6 +16,8 @@
  *   thrl_qtable_init        <- th_rl/agents.py:29,45 (table = 12.5/(1-gamma)+randn, counter = 0)
  *                              th_rl/environments.py:15-16,50-53 (reset: price ~ U(0,a))
  *   thrl_greedy_eval        <- th_rl/utils.py:27-47 (play_game) + th_rl/agents.py:91-92 (get_action)
+ *   (agents of kind THRL_AGENT_REINFORCE inside thrl_qtable_scan)
+ *                           <- th_rl/agents.py:119-194 (Reinforce: pi / sample_action / scale / train_net + Adam)
  *
  * Conventions: plain C types only; every pointer in ThrlScanArgs is a DEVICE pointer owned by
  * the caller unless the entry point's name ends in `_host`; nothing is allocated or freed by the
@@ -33,7 +35,7 @@
 extern "C" {
 #endif
 
-#define THRL_ABI_VERSION 1
+#define THRL_ABI_VERSION 2
 #define THRL_MAX_AGENTS 16
 #define THRL_MAX_ACTIONS 255 /* greedy-action cache is one byte per table row, 0xFF = not cached */
 
@@ -51,6 +53,11 @@ typedef enum ThrlDtype {
   THRL_F64 = 1  /* the reference's own dtype: bit-exact tables (agents.py:29) */
 } ThrlDtype;
 
+typedef enum ThrlAgentKind {
+  THRL_AGENT_QTABLE = 0,   /* th_rl/agents.py:12-116 */
+  THRL_AGENT_REINFORCE = 1 /* th_rl/agents.py:119-219: MLP 1 -> hidden -> actions, policy gradient, Adam(lr) */
+} ThrlAgentKind;
+
 typedef enum ThrlRngMode {
   THRL_RNG_PHILOX = 0,        /* free running: Philox4x32-10 keyed (seed), counter (run, epoch, step, stream) */
   THRL_RNG_REPLAY_DRAWS = 1,  /* replay recorded exploration draws u / random action; greedy picked here */
@@ -67,7 +74,21 @@ typedef struct ThrlAgentSpec {
   double max_state;
   double gamma, alpha, eps_end, eps_step; /* used when ThrlScanArgs.hp == NULL */
   int64_t table_offset;                   /* element offset inside one run's slab; set by thrl_game_layout */
+  /* ABI 2: MLP agents (kind != THRL_AGENT_QTABLE).  `states` is the input width (must be 1: the price), `capacity` /
+   * `min_memory` keep their meaning, gamma is the return discount; alpha / eps_* / max_state are unused. */
+  int32_t kind;       /* ThrlAgentKind */
+  int32_t hidden;     /* width of fc1 (reference: 256) */
+  double lr;          /* Adam learning rate (reference: 2e-4); betas (0.9, 0.999), eps 1e-8 */
+  double entropy;     /* entropy coefficient (reference default 0; only 0 is supported) */
+  int64_t mlp_offset; /* float offset of this agent's block inside one run's MLP slab; set by thrl_game_layout */
 } ThrlAgentSpec;
+
+/* Layout of one MLP agent's block inside the run's MLP slab (floats / 32-bit words), P = 2*hidden + actions*hidden + actions:
+ *   [0, P)        parameters in state_dict order: fc1.weight[hidden] fc1.bias[hidden] fc_pi.weight[actions][hidden] fc_pi.bias[actions]
+ *   [P, 2P)       Adam exp_avg          [2P, 3P)  Adam exp_avg_sq
+ *   [3P, 3P+4)    int32 header: Adam step count, buffered transitions, 2 reserved
+ *   [3P+4, ...)   transition buffer, `mlp_buffer_len` entries of 3 words: state (f32), action (int32), reward (f32) */
+#define THRL_MLP_HEADER_WORDS 4
 
 /* One game = n agents + NoisyPriceState kwargs (th_rl/environments.py:5-13). */
 typedef struct ThrlGame {
@@ -78,6 +99,8 @@ typedef struct ThrlGame {
   int64_t run_stride; /* elements per run slab = sum_i (states_i+1)*actions_i; set by thrl_game_layout */
   int32_t ring_len;   /* transitions a run may hold across an epoch boundary; set by thrl_game_layout */
   int32_t regular;    /* 1 if every agent's buffer is empty at every epoch boundary (min_memory <= max_steps) */
+  int64_t mlp_stride; /* ABI 2: 32-bit words per run in the MLP slab (0 when all agents are QTables); set by thrl_game_layout */
+  int32_t mlp_buffer_len[THRL_MAX_AGENTS]; /* transitions an MLP agent can hold; set by thrl_game_layout */
 } ThrlGame;
 
 /* Fixed-point scales of the cross-run statistics (exact, order-independent integer sums). */
@@ -118,6 +141,9 @@ typedef struct ThrlScanArgs {
   int32_t* trace_actions; /* [R][E][T][n] chosen action indices */
   double* trace_rewards;  /* [R][E][T][n] */
   double* trace_prices;   /* [R][E][T] */
+  /* ABI 2 */
+  float* mlp; /* [R][game->mlp_stride] parameters, Adam state and transition buffers of the MLP agents; NULL iff mlp_stride == 0.
+                 The host initialises parameters (torch's nn.Linear init) and zeroes the rest. */
 } ThrlScanArgs;
 
 /* Host-side helpers (no device needed). */

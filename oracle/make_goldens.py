@@ -86,6 +86,23 @@ CASES = {
                                  for i in range(8)],
                          environment=_env(nplayers=8, max_steps=100),
                          training=dict(epochs=5, print_freq=1000)), 7),
+    # the shipped example_config.json pairing: QTable + Reinforce (MLP policy gradient, agents.py:119-219); 20 epochs
+    # = two Reinforce updates (min_memory 1000 = every 10 episodes)
+    "mixed_qr_seed8": (dict(agents=[_agent(), dict(name="Reinforce", gamma=0.995, actions=21, states=1,
+                                                   action_range=[0.2, 0.4])],
+                            environment=_env(), training=dict(epochs=20, print_freq=1000)), 8),
+    # configs2.json pairing, short episodes, small min_memory: Reinforce batches of 160 transitions spanning 4 episodes
+    "mixed_qr_small_seed9": (dict(agents=[_agent(gamma=0.35, alpha=0.5, epsilon=0.8),
+                                          dict(name="Reinforce", gamma=0.35, actions=21, states=1,
+                                               action_range=[0.2, 0.4], min_memory=150, capacity=400)],
+                                  environment=_env(max_steps=40), training=dict(epochs=14, print_freq=1000)), 9),
+    # two Reinforce agents and one QTable agent, 7 actions
+    "mixed_rqr_seed10": (dict(agents=[dict(name="Reinforce", gamma=0.9, actions=7, states=1, action_range=[0.1, 0.3],
+                                           min_memory=100),
+                                      _agent(actions=9, states=40, action_range=[0.1, 0.3]),
+                                      dict(name="Reinforce", gamma=0.5, actions=5, states=1, action_range=[0.05, 0.2],
+                                           min_memory=90, capacity=100)],
+                              environment=_env(nplayers=3, max_steps=30), training=dict(epochs=12, print_freq=1000)), 10),
 }
 
 
@@ -137,6 +154,20 @@ def record_case(cfg, seed):
             super().train_net()
             rec["eps_trace"].append(self.epsilon)
 
+    class Reinforce(ragents.Reinforce):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            rec.setdefault("mlp0", []).append({k: v.detach().numpy().copy() for k, v in self.state_dict().items()})
+
+        def sample_action(self, state):
+            a = super().sample_action(state)
+            rec["acts"].append((float("nan"), -1, int(a)))   # no python-random draws: the sample comes from torch's generator
+            return a
+
+        def train_net(self):
+            super().train_net()
+            rec["eps_trace"].append(float("nan"))
+
     class NoisyPriceState(renv.NoisyPriceState):
         def reset(self):
             s = super().reset()
@@ -159,10 +190,12 @@ def record_case(cfg, seed):
             return out
 
     proxy = _RandomProxy(random, draws)
-    saved = (ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState)
+    saved = (ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce)
     ragents.random = proxy
     rtrainer.QTable = QTable
+    rtrainer.Reinforce = Reinforce
     rtrainer.NoisyPriceState = NoisyPriceState
+    torch.set_num_threads(1)
     try:
         random.seed(seed)
         numpy.random.seed(seed)
@@ -175,13 +208,16 @@ def record_case(cfg, seed):
             with contextlib.redirect_stdout(io.StringIO()):
                 rtrainer.train_one(out, cpath)          # the unmodified reference loop
             n = len(cfg["agents"])
-            q_final = [numpy.load(os.path.join(out, "%d.npy" % i)) for i in range(n)]
-            c_final = [numpy.load(os.path.join(out, "%d_counter.npy" % i)) for i in range(n)]
+            kinds = [a["name"] for a in cfg["agents"]]
+            q_final = [numpy.load(os.path.join(out, "%d.npy" % i)) if kinds[i] == "QTable" else None for i in range(n)]
+            c_final = [numpy.load(os.path.join(out, "%d_counter.npy" % i)) if kinds[i] == "QTable" else None for i in range(n)]
+            mlp_final = [{k: v.numpy().copy() for k, v in torch.load(os.path.join(out, str(i))).items()}
+                         if kinds[i] != "QTable" else None for i in range(n)]
             with open(os.path.join(out, "log.csv")) as f:
                 header = [f.readline().strip(), f.readline().strip()]
                 log = numpy.loadtxt(f, delimiter=",", ndmin=2)
     finally:
-        ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState = saved
+        ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce = saved
 
     E = cfg["training"]["epochs"]
     T = cfg["environment"]["max_steps"]
@@ -203,11 +239,19 @@ def record_case(cfg, seed):
         actions_log=log[:, n:].copy(),
         log_header=numpy.array(header),
     )
-    assert len(rec["p0"]) == 1 and len(rec["q0"]) == n
+    assert len(rec["p0"]) == 1
+    qi = mi = 0
     for i in range(n):
-        g["q0_%d" % i] = rec["q0"][i]
-        g["q_final_%d" % i] = q_final[i]
-        g["counter_final_%d" % i] = c_final[i]
+        if kinds[i] == "QTable":
+            g["q0_%d" % i] = rec["q0"][qi]; qi += 1
+            g["q_final_%d" % i] = q_final[i]
+            g["counter_final_%d" % i] = c_final[i]
+        else:
+            for k, v in rec["mlp0"][mi].items():
+                g["mlp0_%d_%s" % (i, k)] = v
+            for k, v in mlp_final[i].items():
+                g["mlp_final_%d_%s" % (i, k)] = v
+            mi += 1
     return g
 
 

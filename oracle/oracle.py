@@ -60,16 +60,50 @@ def layout(config):
 
 
 def pack_tables(game, per_agent, dtype):
-    """per_agent: list over agents of arrays [R, states+1, actions] (or [states+1, actions]) -> slab [R, run_stride]."""
+    """per_agent: list over agents of arrays [R, states+1, actions] (or [states+1, actions]; None for MLP agents)
+    -> slab [R, run_stride]."""
     n = game.n_agents
-    arrs = [np.asarray(a, dtype=np.float64) for a in per_agent]
-    arrs = [a[None] if a.ndim == 2 else a for a in arrs]
-    R = arrs[0].shape[0]
+    arrs = [None if a is None else np.asarray(a, dtype=np.float64) for a in per_agent]
+    arrs = [a if a is None else (a[None] if a.ndim == 2 else a) for a in arrs]
+    R = next(a for a in arrs if a is not None).shape[0]
     out = np.zeros((R, game.run_stride), dtype=dtype)
     for i in range(n):
         s = game.agent[i]
+        if s.kind != abi.THRL_AGENT_QTABLE:
+            continue
         cells = (s.states + 1) * s.actions
         out[:, s.table_offset:s.table_offset + cells] = arrs[i].reshape(R, cells).astype(dtype)
+    return out
+
+
+def pack_mlp(game, per_agent, R=1):
+    """per_agent: list over agents of state_dict-like mappings (fc1.weight, fc1.bias, fc_pi.weight, fc_pi.bias; None for
+    QTable agents), shared by all R runs -> MLP slab [R, mlp_stride] float32 (Adam state, header and buffer zeroed)."""
+    slab = np.zeros((R, max(1, game.mlp_stride)), np.float32)
+    for i in range(game.n_agents):
+        s = game.agent[i]
+        if s.kind == abi.THRL_AGENT_QTABLE:
+            continue
+        d = per_agent[i]
+        flat = np.concatenate([np.asarray(d["fc1.weight"], np.float32).reshape(-1), np.asarray(d["fc1.bias"], np.float32).reshape(-1),
+                               np.asarray(d["fc_pi.weight"], np.float32).reshape(-1), np.asarray(d["fc_pi.bias"], np.float32).reshape(-1)])
+        assert flat.size == abi.mlp_param_count(s)
+        slab[:, s.mlp_offset:s.mlp_offset + flat.size] = flat
+    return slab
+
+
+def unpack_mlp(game, slab, run=0):
+    """-> list over agents of {name: array} in torch state_dict shapes (None for QTable agents)."""
+    out = []
+    for i in range(game.n_agents):
+        s = game.agent[i]
+        if s.kind == abi.THRL_AGENT_QTABLE:
+            out.append(None)
+            continue
+        H, A = s.hidden, s.actions
+        p = np.asarray(slab)[run, s.mlp_offset:s.mlp_offset + abi.mlp_param_count(s)]
+        out.append({"fc1.weight": p[:H].reshape(H, 1).copy(), "fc1.bias": p[H:2 * H].copy(),
+                    "fc_pi.weight": p[2 * H:2 * H + A * H].reshape(A, H).copy(), "fc_pi.bias": p[2 * H + A * H:].copy()})
     return out
 
 
@@ -77,6 +111,9 @@ def unpack_tables(game, slab):
     out = []
     for i in range(game.n_agents):
         s = game.agent[i]
+        if s.kind != abi.THRL_AGENT_QTABLE:
+            out.append(None)
+            continue
         cells = (s.states + 1) * s.actions
         out.append(slab[:, s.table_offset:s.table_offset + cells].reshape(-1, s.states + 1, s.actions))
     return out
@@ -88,14 +125,14 @@ class ScanResult:
 
 def scan(game, q, eps, price, epochs, *, epoch_begin=0, counter=None, hp=None, rng_mode=abi.THRL_RNG_PHILOX, seed=0,
          run_id0=0, replay_u=None, replay_ra=None, replay_new_a=None, n_log_runs=None, stats=False, trace=False,
-         n_threads=1):
+         n_threads=1, mlp=None):
     """Plays epochs [epoch_begin, epoch_begin+epochs) for every run.  q [R, run_stride] f32/f64, eps [R, n], price [R]
     are copied, the copies are advanced and returned in a ScanResult."""
     n, T = game.n_agents, game.max_steps
     q = np.ascontiguousarray(q).copy()
     R = q.shape[0]
     dtype = abi.THRL_F64 if q.dtype == np.float64 else abi.THRL_F32
-    assert q.dtype in (np.float32, np.float64) and q.shape == (R, game.run_stride)
+    assert q.dtype in (np.float32, np.float64) and q.shape == (R, max(1, game.run_stride)) or q.shape == (R, game.run_stride)
     eps = np.ascontiguousarray(eps, dtype=np.float64).reshape(R, n).copy()
     price = np.ascontiguousarray(price, dtype=np.float64).reshape(R).copy()
     counter = np.zeros((R, game.run_stride), np.uint32) if counter is None else np.ascontiguousarray(counter, np.uint32).copy()
@@ -103,6 +140,8 @@ def scan(game, q, eps, price, epochs, *, epoch_begin=0, counter=None, hp=None, r
     n_log = R if n_log_runs is None else int(n_log_runs)
     res = ScanResult()
     res.q, res.eps, res.price, res.counter = q, eps, price, counter
+    res.mlp = None if mlp is None else np.ascontiguousarray(mlp, np.float32).reshape(R, -1).copy()
+    assert (game.mlp_stride == 0) == (mlp is None), "games with MLP agents need the mlp slab"
     res.rewards_log = np.zeros((n_log, E, n), np.float64)
     res.actions_log = np.zeros((n_log, E, n), np.float64)
     res.stats = np.zeros((E, n, abi.THRL_STATS_K), np.int64) if stats else None
@@ -131,6 +170,7 @@ def scan(game, q, eps, price, epochs, *, epoch_begin=0, counter=None, hp=None, r
     a.rewards_log, a.actions_log, a.n_log_runs = _ptr(res.rewards_log), _ptr(res.actions_log), n_log
     a.stats = _ptr(res.stats)
     a.trace_actions, a.trace_rewards, a.trace_prices = _ptr(res.trace_actions), _ptr(res.trace_rewards), _ptr(res.trace_prices)
+    a.mlp = _ptr(res.mlp)
     rc = lib().thrl_oracle_qtable_scan(C.byref(a), n_threads)
     if rc != 0:
         raise IndexError("oracle: table row/action out of range (rc=%d)" % rc)

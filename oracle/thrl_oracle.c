@@ -20,6 +20,9 @@
  *   env step        th_rl/environments.py:22-39
  *   buffer          th_rl/buffers.py:12,18-19,28-41 (deque(maxlen=capacity), replay in order, empty)
  *   train_net()     th_rl/agents.py:59-78
+ *   mlp_*()         th_rl/agents.py:119-194 (Reinforce: pi, sample_action, scale, train_net) + torch.optim.Adam,
+ *                   torch.nn.utils.clip_grad_norm_, torch.distributions.Categorical (math restated; pinned against the
+ *                   reference's torch results to a stated tolerance, tests/test_oracle_golden.py)
  * Two modes have no reference counterpart and are specified in DESIGN.md ("fp32 storage",
  * "Philox streams"); the CUDA kernels must match this file bit-for-bit in those modes too.
  */
@@ -146,6 +149,152 @@ static double scale_action(int k, const ThrlAgentSpec* s) {
   return (double)k / ((double)s->actions - 1.0) * (s->action_hi - s->action_lo) + s->action_lo;
 }
 
+/* ---------------------------------------------------------------- Reinforce agent (th_rl/agents.py:119-194), float32
+ * Every operation is a separate IEEE f32 operation in a fixed order (no FMA), so the CUDA kernel reproduces it exactly.
+ * expf is our own (Cody-Waite reduction + Cephes polynomial, ~2 ulp): libm and libdevice expf differ in the last bit. */
+static float det_expf(float x) {
+  if (x < -87.0f) return 0.0f;
+  float kf = rintf(x * 1.44269504f);
+  float r = x - kf * 0.693359375f;
+  r = r - kf * -2.12194440e-4f;
+  float p = 1.9875691500e-4f;
+  p = p * r + 1.3981999507e-3f;
+  p = p * r + 8.3334519073e-3f;
+  p = p * r + 4.1665795894e-2f;
+  p = p * r + 1.6666665459e-1f;
+  p = p * r + 5.0000001201e-1f;
+  p = p * r;
+  p = p * r;
+  p = p + r;
+  p = p + 1.0f;
+  return ldexpf(p, (int)kf);
+}
+/* pi(x) (agents.py:148-152): h = relu(fc1(x)), logits = fc_pi(h), softmax.  par: w1[H] b1[H] W[A][H] bp[A]. */
+static void mlp_forward(const float* par, int H, int A, float s, float* h, float* prob) {
+  const float *w1 = par, *b1 = par + H, *W = par + 2 * H, *bp = par + 2 * H + (size_t)A * H;
+  for (int j = 0; j < H; ++j) {
+    float v = s * w1[j];
+    v = v + b1[j];
+    h[j] = v > 0.0f ? v : 0.0f;
+  }
+  float mx = -INFINITY;
+  for (int k = 0; k < A; ++k) {
+    float acc = 0.0f;
+    for (int j = 0; j < H; ++j) { float t = h[j] * W[(size_t)k * H + j]; acc = acc + t; }
+    acc = acc + bp[k];
+    prob[k] = acc;
+    if (acc > mx) mx = acc;
+  }
+  float sum = 0.0f;
+  for (int k = 0; k < A; ++k) { prob[k] = det_expf(prob[k] - mx); sum = sum + prob[k]; }
+  for (int k = 0; k < A; ++k) prob[k] = prob[k] / sum;
+}
+/* Categorical(prob).sample() from one 24-bit uniform: first k with cumsum > u (free-running mode only) */
+static int mlp_sample(const float* prob, int A, uint32_t x) {
+  const float u = (float)(x >> 8) * (1.0f / 16777216.0f);
+  float c = 0.0f;
+  for (int k = 0; k < A; ++k) { c = c + prob[k]; if (c > u) return k; }
+  return A - 1;
+}
+/* Reinforce.train_net (agents.py:170-194) on the N buffered transitions buf[(head+j) % cap] = (state, action, reward),
+ * then clip_grad_norm_(1.0) and one Adam step.  blk = this agent's block of the MLP slab (include/thrl.h).
+ * scratch: 2*P + H + A floats. */
+static void mlp_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, int N, float* scratch) {
+  const int H = sp->hidden, A = sp->actions;
+  const int P = 2 * H + A * H + A;
+  float *par = blk, *am = blk + P, *av = blk + 2 * (size_t)P;
+  int32_t* hdr = (int32_t*)(blk + 3 * (size_t)P);
+  const float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
+  float *g = scratch, *h = scratch + P, *prob = h + H, *disc = prob + A; /* disc: N floats, caller sizes scratch */
+  float *gw1 = g, *gb1 = g + H, *gW = g + 2 * H, *gbp = g + 2 * H + (size_t)A * H;
+  const float* W = par + 2 * H;
+  for (int i = 0; i < P; ++i) g[i] = 0.0f;
+  /* discounted returns over the whole buffer, newest to oldest (:177-180), float32 */
+  const float gam = (float)sp->gamma;
+  for (int j = N - 1; j >= 0; --j) {
+    const float r = buf[(size_t)((head + j) % cap) * 3 + 2];
+    if (j == N - 1) disc[j] = r;
+    else { float t = gam * disc[j + 1]; disc[j] = r + t; }
+  }
+  /* (discounted - mean) / std, unbiased std (:181) */
+  double sum = 0.0;
+  for (int j = 0; j < N; ++j) sum += (double)disc[j];
+  const float mean = (float)(sum / (double)N);
+  double ss = 0.0;
+  for (int j = 0; j < N; ++j) { const double d = (double)disc[j] - (double)mean; ss += d * d; }
+  const float sd = (float)sqrt(ss / (double)(N - 1));
+  const float invN = 1.0f / (float)N;
+  /* loss = -mean(log_prob(a) * G) (:185); d loss / d logits_k = (p_k - [k == a]) * G / N, back through fc_pi, relu, fc1 */
+  for (int j = 0; j < N; ++j) {
+    const float* tr = buf + (size_t)((head + j) % cap) * 3;
+    const float s = tr[0];
+    int32_t a;
+    memcpy(&a, &tr[1], 4);
+    float G = disc[j] - mean;
+    G = G / sd;
+    const float c = G * invN;
+    mlp_forward(par, H, A, s, h, prob);
+    for (int k = 0; k < A; ++k) {
+      float dl = prob[k] - (k == a ? 1.0f : 0.0f);
+      dl = dl * c;
+      prob[k] = dl; /* reuse as dlogits */
+      gbp[k] = gbp[k] + dl;
+    }
+    for (int jh = 0; jh < H; ++jh) {
+      float dh = 0.0f;
+      const float hj = h[jh];
+      for (int k = 0; k < A; ++k) {
+        const float dl = prob[k];
+        float t = dl * W[(size_t)k * H + jh];
+        dh = dh + t;
+        float u = dl * hj;
+        gW[(size_t)k * H + jh] = gW[(size_t)k * H + jh] + u;
+      }
+      if (hj > 0.0f) {
+        float t = dh * s;
+        gw1[jh] = gw1[jh] + t;
+        gb1[jh] = gb1[jh] + dh;
+      }
+    }
+  }
+  /* clip_grad_norm_(parameters, 1.0) (:191): lane-strided partial sums then lanes in order (mirrors the warp reduction) */
+  double part[32];
+  for (int l = 0; l < 32; ++l) part[l] = 0.0;
+  for (int i = 0; i < P; ++i) part[i & 31] += (double)g[i] * (double)g[i];
+  double tot = 0.0;
+  for (int l = 0; l < 32; ++l) tot += part[l];
+  const float total_norm = (float)sqrt(tot);
+  float coef = 1.0f / (total_norm + 1e-6f);
+  if (coef > 1.0f) coef = 1.0f;
+  /* Adam (torch.optim.Adam defaults; agents.py:139), single-tensor formulas */
+  const int step = hdr[0] + 1;
+  hdr[0] = step;
+  const double b1 = 0.9, b2 = 0.999;
+  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  const float neg_step_size = (float)(-(sp->lr / bc1));
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float w1m = (float)(1.0 - b1), fb2 = (float)b2, w2 = (float)(1.0 - b2), eps = 1e-8f;
+  for (int i = 0; i < P; ++i) {
+    const float gi = g[i] * coef;
+    float m = am[i], v = av[i];
+    float d = gi - m;
+    d = d * w1m;
+    m = m + d; /* exp_avg.lerp_(grad, 1 - beta1) */
+    v = v * fb2;
+    float q = w2 * gi;
+    q = q * gi;
+    v = v + q; /* exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value = 1 - beta2) */
+    am[i] = m;
+    av[i] = v;
+    float den = sqrtf(v);
+    den = den / bc2_sqrt;
+    den = den + eps;
+    float up = neg_step_size * m;
+    up = up / den;
+    par[i] = par[i] + up; /* param.addcdiv_(exp_avg, denom, value = -step_size) */
+  }
+}
+
 typedef struct Transition { /* buffers.py Experience(state, action, reward, done, new_state); `done` is never read */
   double state, reward, new_state;
   int action;
@@ -177,8 +326,22 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
   double alpha[THRL_MAX_AGENTS], gamma[THRL_MAX_AGENTS], eps_end[THRL_MAX_AGENTS], eps_step[THRL_MAX_AGENTS];
   const size_t esz = A->table_dtype == THRL_F64 ? 8 : 4;
   int rc = 0;
+  float* mlp_blk[THRL_MAX_AGENTS];
+  float* mlp_scratch = NULL;
+  size_t mlp_scratch_n = 0;
   for (int i = 0; i < n; ++i) {
     const ThrlAgentSpec* s = &G->agent[i];
+    mlp_blk[i] = NULL;
+    buf[i].item = NULL;
+    if (s->kind != THRL_AGENT_QTABLE) {
+      mlp_blk[i] = A->mlp + (size_t)r * G->mlp_stride + s->mlp_offset;
+      const size_t P = 2 * (size_t)s->hidden + (size_t)s->actions * s->hidden + s->actions;
+      const size_t need = 2 * P + s->hidden + s->actions + (size_t)G->mlp_buffer_len[i] + 8;
+      if (need > mlp_scratch_n) mlp_scratch_n = need;
+      buf[i].cap = buf[i].len = buf[i].head = 0;
+      alpha[i] = gamma[i] = eps_end[i] = eps_step[i] = 0.0;
+      continue;
+    }
     tab[i].dtype = A->table_dtype;
     tab[i].base = (char*)A->q + ((size_t)r * G->run_stride + s->table_offset) * esz;
     tab[i].rows = s->states + 1;
@@ -202,7 +365,8 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
   double* old_value = NULL;
   int64_t *st_row = NULL, *ns_row = NULL;
   int maxcap = 1;
-  for (int i = 0; i < n; ++i) if (G->agent[i].capacity > maxcap) maxcap = G->agent[i].capacity;
+  for (int i = 0; i < n; ++i) if (G->agent[i].kind == THRL_AGENT_QTABLE && G->agent[i].capacity > maxcap) maxcap = G->agent[i].capacity;
+  if (mlp_scratch_n) mlp_scratch = (float*)malloc(sizeof(float) * mlp_scratch_n);
   old_value = (double*)malloc(sizeof(double) * (size_t)maxcap);
   st_row = (int64_t*)malloc(sizeof(int64_t) * (size_t)maxcap);
   ns_row = (int64_t*)malloc(sizeof(int64_t) * (size_t)maxcap);
@@ -217,6 +381,25 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
       for (int i = 0; i < n; ++i) {
         const ThrlAgentSpec* s = &G->agent[i];
         int k;
+        if (s->kind != THRL_AGENT_QTABLE) {
+          /* Reinforce.sample_action (agents.py:160-163): in both replay modes the recorded sample is forced (it came from
+           * torch's generator); free running: inverse-CDF on one Philox word */
+          if (A->rng_mode != THRL_RNG_PHILOX) {
+            k = A->replay_ra[sidx * n + i];
+          } else {
+            float* h = mlp_scratch;
+            float* prob = h + s->hidden;
+            uint32_t x[4];
+            mlp_forward(mlp_blk[i], s->hidden, s->actions, (float)price, h, prob);
+            philox4x32_10((uint32_t)gid, (uint32_t)eabs, (uint32_t)t, (uint32_t)(i >> 1) | (STREAM_ACT << 16), k0, k1, x);
+            k = mlp_sample(prob, s->actions, x[2 * (i & 1)]);
+          }
+          if (k < 0 || k >= s->actions) { rc = -1; break; }
+          act[i] = k;
+          /* Reinforce.scale (agents.py:154-158): action / actions, not / (actions - 1) */
+          xs[i] = (double)k / (double)s->actions * (s->action_hi - s->action_lo) + s->action_lo;
+          continue;
+        }
         if (A->rng_mode == THRL_RNG_REPLAY_ACTIONS) {
           k = A->replay_ra[sidx * n + i];
         } else {
@@ -270,6 +453,26 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
       for (int i = 0; i < n; ++i) rew[i] = next_price * Aq[i];
       /* trainer.py:61-62 */
       for (int i = 0; i < n; ++i) {
+        if (G->agent[i].kind != THRL_AGENT_QTABLE) {
+          /* memory.append; replay(cast) turns state and reward into float32 (buffers.py:28-38, agents.py:142) */
+          const int cap = G->mlp_buffer_len[i];
+          if (cap > 0) {
+            const size_t P = 2 * (size_t)G->agent[i].hidden + (size_t)G->agent[i].actions * G->agent[i].hidden + G->agent[i].actions;
+            int32_t* hdr = (int32_t*)(mlp_blk[i] + 3 * P);
+            float* mb = mlp_blk[i] + 3 * P + THRL_MLP_HEADER_WORDS;
+            int len = hdr[1], head = hdr[2];
+            int slot;
+            if (len < cap) { slot = (head + len) % cap; len++; }
+            else { slot = head; head = (head + 1) % cap; }
+            const float sf = (float)price, rf = (float)rew[i];
+            const int32_t ai = act[i];
+            mb[(size_t)slot * 3] = sf;
+            memcpy(&mb[(size_t)slot * 3 + 1], &ai, 4);
+            mb[(size_t)slot * 3 + 2] = rf;
+            hdr[1] = len; hdr[2] = head;
+          }
+          continue;
+        }
         Transition tr = {price, rew[i], next_price, act[i]};
         buf_append(&buf[i], tr);
       }
@@ -288,6 +491,15 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
     for (int i = 0; i < n && rc == 0; ++i) {
       const ThrlAgentSpec* s = &G->agent[i];
       Buffer* b = &buf[i];
+      if (s->kind != THRL_AGENT_QTABLE) {
+        const size_t P = 2 * (size_t)s->hidden + (size_t)s->actions * s->hidden + s->actions;
+        int32_t* hdr = (int32_t*)(mlp_blk[i] + 3 * P);
+        if (G->mlp_buffer_len[i] > 0 && hdr[1] >= s->min_memory) { /* agents.py:171 */
+          mlp_train(mlp_blk[i], s, G->mlp_buffer_len[i], hdr[2], hdr[1], mlp_scratch);
+          hdr[1] = 0; hdr[2] = 0; /* :194 memory.empty() */
+        }
+        continue;
+      }
       if (b->len >= s->min_memory) {
         const int L = b->len;
         for (int j = 0; j < L; ++j) { /* :62,:66 encodes, :67 snapshot */
@@ -331,7 +543,7 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
   }
   A->price[r] = price;
   for (int i = 0; i < n; ++i) free(buf[i].item);
-  free(old_value); free(st_row); free(ns_row);
+  free(old_value); free(st_row); free(ns_row); free(mlp_scratch);
   return rc;
 }
 
@@ -445,24 +657,36 @@ int thrl_oracle_greedy_eval(const ThrlGame* G, int64_t n_runs, int32_t table_dty
 /* Same checks / layout as thrl_game_layout in the product, restated so the oracle stands alone. */
 int thrl_oracle_game_layout(ThrlGame* G) {
   if (G->n_agents < 1 || G->n_agents > THRL_MAX_AGENTS || G->max_steps < 1) return THRL_ERR_BAD_CONFIG;
-  int64_t off = 0;
+  int64_t off = 0, moff = 0;
   int ring = 0, regular = 1;
   for (int i = 0; i < G->n_agents; ++i) {
     ThrlAgentSpec* s = &G->agent[i];
-    if (s->states < 1 || s->actions < 2 || s->actions > THRL_MAX_ACTIONS || s->capacity < 0 || s->min_memory < 0)
-      return THRL_ERR_BAD_CONFIG;
+    G->mlp_buffer_len[i] = 0;
+    if (s->actions < 2 || s->actions > THRL_MAX_ACTIONS || s->capacity < 0 || s->min_memory < 0) return THRL_ERR_BAD_CONFIG;
+    const int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
+    int64_t need = (int64_t)T * ((mm + T - 1) / T);
+    if (need > s->capacity) need = s->capacity;
+    if (s->kind == THRL_AGENT_REINFORCE) {
+      if (s->states != 1 || s->hidden < 1 || s->entropy != 0.0) return THRL_ERR_BAD_CONFIG;
+      const int64_t P = 2 * (int64_t)s->hidden + (int64_t)s->actions * s->hidden + s->actions;
+      G->mlp_buffer_len[i] = s->min_memory <= s->capacity ? (int32_t)need : 0;
+      s->mlp_offset = moff;
+      s->table_offset = 0;
+      moff += 3 * P + THRL_MLP_HEADER_WORDS + 3 * (int64_t)G->mlp_buffer_len[i];
+      continue;
+    }
+    if (s->kind != THRL_AGENT_QTABLE || s->states < 1) return THRL_ERR_BAD_CONFIG;
     if (!(s->max_state > 0.0) || G->a > s->max_state) return THRL_ERR_BAD_CONFIG; /* row would exceed states: IndexError */
     s->table_offset = off;
+    s->mlp_offset = 0;
     off += (int64_t)(s->states + 1) * s->actions;
     if (s->min_memory <= s->capacity) { /* otherwise the update never fires and the buffer content is irrelevant */
-      int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
-      int64_t need = (int64_t)T * ((mm + T - 1) / T);
-      if (need > s->capacity) need = s->capacity;
       if (need > ring) ring = (int)need;
       if (s->min_memory > T) regular = 0;
     }
   }
   G->run_stride = off;
+  G->mlp_stride = moff;
   G->ring_len = ring;
   G->regular = regular;
   return THRL_OK;

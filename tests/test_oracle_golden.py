@@ -9,17 +9,53 @@ from oracle import oracle
 from th_rl_b200 import abi
 
 
+def is_mlp(cfg, i):
+    return cfg["agents"][i].get("name", "QTable") != "QTable"
+
+
+def golden_inputs(g, game, rng_mode, dtype):
+    """Initial state and replay streams of a golden case, shaped for one run.  MLP agents' recorded samples are forced in
+    both replay modes (they come from torch's generator, agents.py:160-163)."""
+    cfg = g["config"]
+    n = game.n_agents
+    q0 = oracle.pack_tables(game, [None if is_mlp(cfg, i) else g["q0_%d" % i] for i in range(n)], dtype)
+    mlp0 = None
+    if game.mlp_stride:
+        mlp0 = oracle.pack_mlp(game, [{k: g["mlp0_%d_%s" % (i, k)] for k in ("fc1.weight", "fc1.bias", "fc_pi.weight", "fc_pi.bias")}
+                                      if is_mlp(cfg, i) else None for i in range(n)])
+    ra = (g["ra"] if rng_mode == abi.THRL_RNG_REPLAY_DRAWS else g["actions"]).copy()
+    for i in range(n):
+        if is_mlp(cfg, i):
+            ra[..., i] = g["actions"][..., i]
+    u = np.nan_to_num(g["u"], nan=2.0)
+    noisy = cfg["environment"].get("noise_prob", 0.05) > 0
+    return q0, mlp0, u, ra, (g["new_a"] if noisy else None)
+
+
 def run_oracle(g, rng_mode, dtype=np.float64):
     cfg = g["config"]
     game = oracle.layout(cfg)
-    n = game.n_agents
-    q0 = oracle.pack_tables(game, [g["q0_%d" % i] for i in range(n)], dtype)
+    q0, mlp0, u, ra, new_a = golden_inputs(g, game, rng_mode, dtype)
     E = g["u"].shape[0]
-    ra = g["ra"] if rng_mode == abi.THRL_RNG_REPLAY_DRAWS else g["actions"]
-    noisy = cfg["environment"].get("noise_prob", 0.05) > 0
     return game, oracle.scan(game, q0, [abi.eps0_from_config(cfg)], [g["p0"]], E, rng_mode=rng_mode,
-                             replay_u=g["u"][None], replay_ra=ra[None],
-                             replay_new_a=g["new_a"][None] if noisy else None, trace=True, stats=True)
+                             replay_u=u[None], replay_ra=ra[None], replay_new_a=None if new_a is None else new_a[None],
+                             trace=True, stats=True, mlp=mlp0)
+
+
+MLP_ATOL = 2e-6  # |weight - torch's weight| after the recorded updates (two to four Adam steps of 2e-4 each)
+
+
+def check_mlp(g, game, res):
+    cfg = g["config"]
+    got = oracle.unpack_mlp(game, res.mlp)
+    for i in range(game.n_agents):
+        if not is_mlp(cfg, i):
+            continue
+        for k, v in got[i].items():
+            ref0, ref = g["mlp0_%d_%s" % (i, k)], g["mlp_final_%d_%s" % (i, k)]
+            assert np.abs(ref - ref0).max() > 1e-4, "the golden run must contain at least one update"
+            err = np.abs(v.reshape(ref.shape) - ref).max()
+            assert err < MLP_ATOL, (i, k, err)
 
 
 def check_bit_exact(g, game, res):
@@ -30,9 +66,14 @@ def check_bit_exact(g, game, res):
     tabs = oracle.unpack_tables(game, res.q)
     cnts = oracle.unpack_tables(game, res.counter)
     for i in range(n):
+        if is_mlp(g["config"], i):
+            continue
         assert np.array_equal(tabs[i][0], g["q_final_%d" % i]), "table of agent %d" % i
         assert np.array_equal(cnts[i][0].astype(np.float64), g["counter_final_%d" % i])
-    assert np.array_equal(res.eps[0], g["eps_trace"][-1])
+    qt = [i for i in range(n) if not is_mlp(g["config"], i)]
+    assert np.array_equal(res.eps[0][qt], g["eps_trace"][-1][qt])
+    if game.mlp_stride:
+        check_mlp(g, game, res)
     # log.csv round-trips through repr(float) -> exact
     assert np.array_equal(res.rewards_log[0], g["rewards_log"])
     assert np.array_equal(res.actions_log[0], g["actions_log"])
@@ -57,6 +98,8 @@ def test_replay_actions_f32_storage_tolerance(golden):
     assert np.array_equal(res.trace_prices[0], golden["prices"])
     tabs = oracle.unpack_tables(game, res.q)
     for i in range(game.n_agents):
+        if is_mlp(golden["config"], i):
+            continue
         ref = golden["q_final_%d" % i]
         rel = np.max(np.abs(tabs[i][0].astype(np.float64) - ref) / np.abs(ref))
         assert rel < 1e-6, rel

@@ -6,7 +6,7 @@ include/thrl.h, which in turn cites the reference lines each field comes from
 """
 import ctypes as C
 
-THRL_ABI_VERSION = 1
+THRL_ABI_VERSION = 2
 THRL_MAX_AGENTS = 16
 THRL_MAX_ACTIONS = 255
 THRL_STATS_K = 4
@@ -22,6 +22,10 @@ THRL_ERR_NO_DEVICE = -5
 
 THRL_F32 = 0
 THRL_F64 = 1
+
+THRL_AGENT_QTABLE = 0
+THRL_AGENT_REINFORCE = 1
+THRL_MLP_HEADER_WORDS = 4
 
 THRL_RNG_PHILOX = 0
 THRL_RNG_REPLAY_DRAWS = 1
@@ -42,6 +46,11 @@ class ThrlAgentSpec(C.Structure):
         ("eps_end", C.c_double),
         ("eps_step", C.c_double),
         ("table_offset", C.c_int64),
+        ("kind", C.c_int32),
+        ("hidden", C.c_int32),
+        ("lr", C.c_double),
+        ("entropy", C.c_double),
+        ("mlp_offset", C.c_int64),
     ]
 
 
@@ -56,6 +65,8 @@ class ThrlGame(C.Structure):
         ("run_stride", C.c_int64),
         ("ring_len", C.c_int32),
         ("regular", C.c_int32),
+        ("mlp_stride", C.c_int64),
+        ("mlp_buffer_len", C.c_int32 * THRL_MAX_AGENTS),
     ]
 
 
@@ -85,12 +96,16 @@ class ThrlScanArgs(C.Structure):
         ("trace_actions", C.c_void_p),
         ("trace_rewards", C.c_void_p),
         ("trace_prices", C.c_void_p),
+        ("mlp", C.c_void_p),
     ]
 
 
 # QTable.__init__ defaults (th_rl/agents.py:13-27)
 QTABLE_DEFAULTS = dict(states=16, actions=4, action_range=[0, 1], gamma=0.99, buffer="ReplayBuffer", capacity=500,
                        max_state=10, alpha=0.1, eps_end=2e-2, epsilon=0.5, eps_step=5e-4, min_memory=100)
+# Reinforce.__init__ defaults (th_rl/agents.py:120-131)
+REINFORCE_DEFAULTS = dict(states=4, actions=2, action_range=[0, 1], gamma=0.98, buffer="ReplayBuffer", capacity=50000,
+                          min_memory=1000, entropy=0)
 # NoisyPriceState.__init__ defaults (th_rl/environments.py:5)
 ENV_DEFAULTS = dict(action_range=[0, 1], a=10, b=1, max_steps=1, noise_prob=0.05)
 
@@ -116,13 +131,25 @@ def game_from_config(config):
     g.b = float(env["b"])
     g.noise_prob = float(env["noise_prob"])
     for i, ad in enumerate(agents):
-        if ad.get("name", "QTable") != "QTable":
+        name = ad.get("name", "QTable")
+        s = g.agent[i]
+        if name == "Reinforce":
+            d = dict(REINFORCE_DEFAULTS)
+            d.update(ad)
+            s.kind = THRL_AGENT_REINFORCE
+            s.states, s.actions = int(d["states"]), int(d["actions"])
+            s.min_memory, s.capacity = int(d["min_memory"]), int(d["capacity"])
+            s.action_lo, s.action_hi = float(d["action_range"][0]), float(d["action_range"][1])
+            s.max_state = float("nan")
+            s.gamma = float(d["gamma"])
+            s.hidden, s.lr, s.entropy = 256, 2e-4, float(d["entropy"])  # agents.py:137-139
+            continue
+        if name != "QTable":
             raise NotImplementedError(
-                "agent %d is %r: only QTable agents are on the B200 hot path (DESIGN.md, out of scope: MLP agents)"
-                % (i, ad.get("name")))
+                "agent %d is %r: the B200 hot path covers QTable and Reinforce agents (DESIGN.md: ActorCritic / CAC are next)"
+                % (i, name))
         d = dict(QTABLE_DEFAULTS)
         d.update(ad)
-        s = g.agent[i]
         s.states = int(d["states"])
         s.actions = int(d["actions"])
         s.min_memory = int(d["min_memory"])
@@ -138,4 +165,9 @@ def game_from_config(config):
 
 
 def eps0_from_config(config):
-    return [float(dict(QTABLE_DEFAULTS, **ad)["epsilon"]) for ad in config["agents"]]
+    return [float(dict(QTABLE_DEFAULTS, **ad)["epsilon"]) if ad.get("name", "QTable") == "QTable" else 0.0
+            for ad in config["agents"]]
+
+
+def mlp_param_count(spec):
+    return 2 * spec.hidden + spec.actions * spec.hidden + spec.actions

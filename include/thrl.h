@@ -162,6 +162,11 @@ int thrl_qtable_scan_host(const ThrlScanArgs* args, int device);
 int thrl_qtable_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
                      const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps, double* price,
                      void* stream);
+/* ABI 2: thrl_qtable_init for games that may contain MLP agents: additionally fills the MLP slab (parameters ~ nn.Linear's
+ * default U(-1/sqrt(fan_in), 1/sqrt(fan_in)), Adam state / header / buffer zero).  mlp may be NULL iff mlp_stride == 0. */
+int thrl_game_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
+                   const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps, double* price, float* mlp,
+                   void* stream);
 /* Greedy rollout (no exploration, no update): `iters` episodes per run, each starting from price0[r][it];
  * rewards/actions [R][iters*T][n] as utils.play_game returns them per run. */
 int thrl_greedy_eval(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, int32_t iters,

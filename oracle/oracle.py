@@ -40,6 +40,8 @@ def lib():
         _lib.thrl_oracle_qtable_init.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int64, C.c_uint64, C.c_int32,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.thrl_oracle_qtable_init.restype = C.c_int
+        _lib.thrl_oracle_game_init.argtypes = _lib.thrl_oracle_qtable_init.argtypes + [C.c_void_p]
+        _lib.thrl_oracle_game_init.restype = C.c_int
         _lib.thrl_oracle_greedy_eval.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int32, C.c_void_p, C.c_int32,
                                                  C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.thrl_oracle_greedy_eval.restype = C.c_int
@@ -185,10 +187,13 @@ def init(game, n_runs, *, seed=0, run_id0=0, dtype=np.float32, hp=None, eps0=Non
     price = np.zeros((n_runs,), np.float64)
     eps0 = np.ascontiguousarray(eps0 if eps0 is not None else [0.5] * n, np.float64)
     hp_a = None if hp is None else np.ascontiguousarray(hp, np.float64)
-    rc = lib().thrl_oracle_qtable_init(C.byref(game), n_runs, run_id0, seed,
-                                       abi.THRL_F64 if dtype == np.float64 else abi.THRL_F32,
-                                       _ptr(hp_a), _ptr(eps0), _ptr(q), _ptr(counter), _ptr(eps), _ptr(price))
+    mlp = np.zeros((n_runs, game.mlp_stride), np.float32) if game.mlp_stride else None
+    rc = lib().thrl_oracle_game_init(C.byref(game), n_runs, run_id0, seed,
+                                     abi.THRL_F64 if dtype == np.float64 else abi.THRL_F32,
+                                     _ptr(hp_a), _ptr(eps0), _ptr(q), _ptr(counter), _ptr(eps), _ptr(price), _ptr(mlp))
     assert rc == 0
+    if game.mlp_stride:
+        return q, counter, eps, price, mlp
     return q, counter, eps, price
 
 

@@ -204,7 +204,7 @@ static void mlp_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, in
   const int P = 2 * H + A * H + A;
   float *par = blk, *am = blk + P, *av = blk + 2 * (size_t)P;
   int32_t* hdr = (int32_t*)(blk + 3 * (size_t)P);
-  const float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
+  float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
   float *g = scratch, *h = scratch + P, *prob = h + H, *disc = prob + A; /* disc: N floats, caller sizes scratch */
   float *gw1 = g, *gb1 = g + H, *gW = g + 2 * H, *gbp = g + 2 * H + (size_t)A * H;
   const float* W = par + 2 * H;
@@ -215,6 +215,7 @@ static void mlp_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, in
     const float r = buf[(size_t)((head + j) % cap) * 3 + 2];
     if (j == N - 1) disc[j] = r;
     else { float t = gam * disc[j + 1]; disc[j] = r + t; }
+    buf[(size_t)((head + j) % cap) * 3 + 2] = disc[j]; /* kept in the (about to be emptied) buffer, as the device does */
   }
   /* (discounted - mean) / std, unbiased std (:181) */
   double sum = 0.0;
@@ -270,7 +271,9 @@ static void mlp_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, in
   const int step = hdr[0] + 1;
   hdr[0] = step;
   const double b1 = 0.9, b2 = 0.999;
-  const double bc1 = 1.0 - pow(b1, (double)step), bc2 = 1.0 - pow(b2, (double)step);
+  double pw1 = 1.0, pw2 = 1.0; /* beta^step by repeated multiplication: reproducible on the device, unlike pow() */
+  for (int q2 = 0; q2 < step; ++q2) { pw1 *= b1; pw2 *= b2; }
+  const double bc1 = 1.0 - pw1, bc2 = 1.0 - pw2;
   const float neg_step_size = (float)(-(sp->lr / bc1));
   const float bc2_sqrt = (float)sqrt(bc2);
   const float w1m = (float)(1.0 - b1), fb2 = (float)b2, w2 = (float)(1.0 - b2), eps = 1e-8f;
@@ -384,9 +387,9 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
         if (s->kind != THRL_AGENT_QTABLE) {
           /* Reinforce.sample_action (agents.py:160-163): in both replay modes the recorded sample is forced (it came from
            * torch's generator); free running: inverse-CDF on one Philox word */
-          if (A->rng_mode != THRL_RNG_PHILOX) {
+          if (A->rng_mode != THRL_RNG_PHILOX && A->replay_ra[sidx * n + i] >= 0) {
             k = A->replay_ra[sidx * n + i];
-          } else {
+          } else { /* free running, or a replay stream that leaves this agent's sample to the device (negative entry) */
             float* h = mlp_scratch;
             float* prob = h + s->hidden;
             uint32_t x[4];
@@ -585,15 +588,42 @@ int thrl_oracle_online_cores(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); 
 
 /* DESIGN.md "Device init": q = 12.5/(1-gamma) + N(0,1) (agents.py:29), counter = 0 (agents.py:45),
  * price ~ U(0,a) (environments.py:15-16), eps = eps0. */
+int thrl_oracle_game_init(const ThrlGame* G, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
+                          const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps, double* price,
+                          float* mlp);
 int thrl_oracle_qtable_init(const ThrlGame* G, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
                             const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps,
                             double* price) {
+  return thrl_oracle_game_init(G, n_runs, run_id0, seed, table_dtype, hp, eps0, q, counter, eps, price, NULL);
+}
+int thrl_oracle_game_init(const ThrlGame* G, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
+                          const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps, double* price,
+                          float* mlp) {
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   const int n = G->n_agents;
   for (int64_t r = 0; r < n_runs; ++r) {
     const uint64_t gid = (uint64_t)(run_id0 + r);
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec* s = &G->agent[i];
+      if (s->kind != THRL_AGENT_QTABLE) { /* nn.Linear default init, the rest of the block zero */
+        const int64_t Pn = 2 * (int64_t)s->hidden + (int64_t)s->actions * s->hidden + s->actions;
+        const int64_t words = 3 * Pn + THRL_MLP_HEADER_WORDS + 3 * (int64_t)G->mlp_buffer_len[i];
+        float* blk = mlp + (size_t)r * G->mlp_stride + s->mlp_offset;
+        const float b_fc1 = 1.0f, b_pi = (float)(1.0 / sqrt((double)s->hidden));
+        for (int64_t w = 0; w < words; ++w) {
+          float v = 0.0f;
+          if (w < Pn) {
+            uint32_t x[4];
+            philox4x32_10((uint32_t)gid, (uint32_t)(w >> 1), (uint32_t)i, (uint32_t)(STREAM_INIT_Q << 16), k0, k1, x);
+            const double u = (w & 1) ? u53(x[2], x[3]) : u53(x[0], x[1]);
+            const float bound = (w < 2 * (int64_t)s->hidden) ? b_fc1 : b_pi;
+            v = (float)(2.0 * u - 1.0) * bound;
+          }
+          blk[w] = v;
+        }
+        eps[(size_t)r * n + i] = eps0[i];
+        continue;
+      }
       const double gamma = hp ? hp[((size_t)r * n + i) * 4 + 1] : s->gamma;
       const double base = 12.5 / (1.0 - gamma);
       const int64_t cells = (int64_t)(s->states + 1) * s->actions;

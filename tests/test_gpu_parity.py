@@ -35,19 +35,21 @@ def _mods():
 
 
 def _cuda_replay(g, rng_mode, dtype):
+    from test_oracle_golden import golden_inputs
     torch, oracle, engine = _mods()
     cfg = g["config"]
     tdt = torch.float64 if dtype == np.float64 else torch.float32
     b = engine.RunBatch(cfg, 1, dtype=tdt)
-    n = b.game.n_agents
-    q0 = oracle.pack_tables(b.game, [g["q0_%d" % i] for i in range(n)], dtype)
-    b.load_state(q0, [abi.eps0_from_config(cfg)], [g["p0"]])
+    q0, mlp0, u, ra, new_a = golden_inputs(g, b.game, rng_mode, dtype)
+    b.load_state(q0, [abi.eps0_from_config(cfg)], [g["p0"]], mlp=mlp0)
     E = g["u"].shape[0]
-    ra = g["ra"] if rng_mode == abi.THRL_RNG_REPLAY_DRAWS else g["actions"]
-    noisy = cfg["environment"].get("noise_prob", 0.05) > 0
-    out = b.scan(E, rng_mode=rng_mode, replay_u=g["u"][None], replay_ra=ra[None],
-                 replay_new_a=g["new_a"][None] if noisy else None, n_log_runs=1, stats=True, trace=True)
+    out = b.scan(E, rng_mode=rng_mode, replay_u=u[None], replay_ra=ra[None],
+                 replay_new_a=None if new_a is None else new_a[None], n_log_runs=1, stats=True, trace=True)
     torch.cuda.synchronize()
+    if mlp0 is not None:  # the oracle on the same inputs: the MLP slab (weights, Adam state, buffers) must agree bit for bit
+        ref = oracle.scan(b.game, q0, [abi.eps0_from_config(cfg)], [g["p0"]], E, rng_mode=rng_mode, replay_u=u[None],
+                          replay_ra=ra[None], replay_new_a=None if new_a is None else new_a[None], mlp=mlp0)
+        assert np.array_equal(b.mlp.cpu().numpy().view(np.uint32), ref.mlp.view(np.uint32)), "MLP slab differs from the oracle"
     return b, out
 
 
@@ -56,8 +58,15 @@ def _check_vs_golden(g, b, out, exact_tables=True):
     assert np.array_equal(out.trace_actions[0].cpu().numpy(), g["actions"])
     assert np.array_equal(out.trace_rewards[0].cpu().numpy(), g["rewards"])
     assert np.array_equal(out.trace_prices[0].cpu().numpy(), g["prices"])
+    from test_oracle_golden import MLP_ATOL, is_mlp
     tabs, cnts = b.tables(), b.counters()
+    sds = b.mlp_state_dicts(0) if b.mlp is not None else None
     for i in range(n):
+        if is_mlp(g["config"], i):  # against the reference's torch weights: tolerance (float32, different summation order)
+            for k, v in sds[i].items():
+                ref = g["mlp_final_%d_%s" % (i, k)]
+                assert np.abs(v.numpy().reshape(ref.shape) - ref).max() < MLP_ATOL, (i, k)
+            continue
         got = tabs[i][0].cpu().numpy().astype(np.float64)
         ref = g["q_final_%d" % i]
         if exact_tables:
@@ -66,7 +75,8 @@ def _check_vs_golden(g, b, out, exact_tables=True):
             rel = np.max(np.abs(got - ref) / np.abs(ref))
             assert rel < 1e-6, rel  # fp32 storage tolerance stated in BASELINE.json north_star
         assert np.array_equal(cnts[i][0].cpu().numpy().astype(np.float64), g["counter_final_%d" % i])
-    assert np.array_equal(b.eps[0].cpu().numpy(), g["eps_trace"][-1])
+    qt = [i for i in range(n) if not is_mlp(g["config"], i)]
+    assert np.array_equal(b.eps[0].cpu().numpy()[qt], g["eps_trace"][-1][qt])
     assert np.array_equal(out.rewards_log[0].cpu().numpy(), g["rewards_log"])
     assert np.array_equal(out.actions_log[0].cpu().numpy(), g["actions_log"])
     assert b.price[0].item() == g["prices"][-1, -1]
@@ -103,12 +113,13 @@ def _philox_case(cfg, R, E, dtype, seed, run_id0=0, hp=False, chunks=None):
     n = game.n_agents
     rng = np.random.default_rng(seed)
     hpa = _sweep_hp(rng, R, n) if hp else None
-    q0, c0, eps0, p0 = oracle.init(game, R, seed=seed, run_id0=run_id0, dtype=dtype, hp=hpa,
-                                   eps0=abi.eps0_from_config(cfg))
-    ref = oracle.scan(game, q0, eps0, p0, E, hp=hpa, seed=seed, run_id0=run_id0, stats=True, trace=True, n_threads=0)
+    q0, c0, eps0, p0, *rest = oracle.init(game, R, seed=seed, run_id0=run_id0, dtype=dtype, hp=hpa,
+                                          eps0=abi.eps0_from_config(cfg))
+    mlp0 = rest[0] if rest else None
+    ref = oracle.scan(game, q0, eps0, p0, E, hp=hpa, seed=seed, run_id0=run_id0, stats=True, trace=True, n_threads=0, mlp=mlp0)
     tdt = torch.float64 if dtype == np.float64 else torch.float32
     b = engine.RunBatch(cfg, R, dtype=tdt, seed=seed, run_id0=run_id0, hp=hpa)
-    b.load_state(q0, eps0, p0)
+    b.load_state(q0, eps0, p0, mlp=mlp0)
     outs = [b.scan(e, n_log_runs=R, stats=True, trace=True) for e in (chunks or [E])]
     torch.cuda.synchronize()
     cat = lambda f, ax: np.concatenate([getattr(o, f).cpu().numpy() for o in outs], axis=ax)
@@ -119,6 +130,8 @@ def _philox_case(cfg, R, E, dtype, seed, run_id0=0, hp=False, chunks=None):
     assert np.array_equal(b.counter.cpu().numpy().view(np.uint32), ref.counter)
     assert np.array_equal(b.eps.cpu().numpy(), ref.eps)
     assert np.array_equal(b.price.cpu().numpy(), ref.price)
+    if mlp0 is not None:
+        assert np.array_equal(b.mlp.cpu().numpy().view(np.uint32), ref.mlp.view(np.uint32))
     assert np.array_equal(cat("rewards_log", 1), ref.rewards_log)
     assert np.array_equal(cat("actions_log", 1), ref.actions_log)
     assert np.array_equal(cat("stats", 0), ref.stats)
@@ -129,12 +142,14 @@ def _philox_case(cfg, R, E, dtype, seed, run_id0=0, hp=False, chunks=None):
 def test_philox_free_running_matches_oracle(golden, dtype):
     """Free-running Philox mode, many runs, per-run hyper-parameters: bit-exact against the oracle in both dtypes."""
     E = 6 if golden["config"]["environment"]["nplayers"] > 2 else 10
-    _philox_case(golden["config"], 96, E, dtype, seed=1234, run_id0=7, hp=True)
+    mixed = any(a["name"] != "QTable" for a in golden["config"]["agents"])
+    _philox_case(golden["config"], 24 if mixed else 96, 12 if mixed else E, dtype, seed=1234, run_id0=7, hp=True)
 
 
 def test_chunked_scan_equals_single_call(golden):
     """Splitting the epoch range over several calls (state and pending transitions carried on the device) changes nothing."""
-    _philox_case(golden["config"], 40, 9, np.float32, seed=5, chunks=[1, 3, 5])
+    mixed = any(a["name"] != "QTable" for a in golden["config"]["agents"])
+    _philox_case(golden["config"], 12 if mixed else 40, 11 if mixed else 9, np.float32, seed=5, chunks=[1, 3, 7] if mixed else [1, 3, 5])
 
 
 def test_host_buffer_entry_point(golden):
@@ -142,11 +157,15 @@ def test_host_buffer_entry_point(golden):
     torch, oracle, engine = _mods()
     cfg = golden["config"]
     game = oracle.layout(cfg)
-    q0, c0, eps0, p0 = oracle.init(game, 33, seed=9, dtype=np.float32, eps0=abi.eps0_from_config(cfg))
-    ref = oracle.scan(game, q0, eps0, p0, 5, seed=9, stats=True)
+    q0, c0, eps0, p0, *rest = oracle.init(game, 33, seed=9, dtype=np.float32, eps0=abi.eps0_from_config(cfg))
+    mlp0 = rest[0] if rest else None
+    ref = oracle.scan(game, q0, eps0, p0, 5, seed=9, stats=True, mlp=mlp0)
     q, eps, p, cnt = q0.copy(), eps0.copy(), p0.copy(), c0.copy()
-    out = engine.scan_host(cfg, q, eps, p, 5, counter=cnt, seed=9, n_log_runs=33, stats=True)
+    mlp = None if mlp0 is None else mlp0.copy()
+    out = engine.scan_host(cfg, q, eps, p, 5, counter=cnt, seed=9, n_log_runs=33, stats=True, mlp=mlp)
     assert np.array_equal(q, ref.q) and np.array_equal(cnt, ref.counter)
+    if mlp is not None:
+        assert np.array_equal(mlp.view(np.uint32), ref.mlp.view(np.uint32))
     assert np.array_equal(eps, ref.eps) and np.array_equal(p, ref.price)
     assert np.array_equal(out.rewards_log, ref.rewards_log) and np.array_equal(out.stats, ref.stats)
 
@@ -156,14 +175,19 @@ def test_device_init_matches_oracle(golden, dtype):
     torch, oracle, engine = _mods()
     cfg = golden["config"]
     game = oracle.layout(cfg)
-    q0, c0, eps0, p0 = oracle.init(game, 50, seed=77, run_id0=1000, dtype=dtype, eps0=abi.eps0_from_config(cfg))
+    q0, c0, eps0, p0, *rest = oracle.init(game, 50, seed=77, run_id0=1000, dtype=dtype, eps0=abi.eps0_from_config(cfg))
     b = engine.RunBatch(cfg, 50, dtype=torch.float64 if dtype == np.float64 else torch.float32, seed=77, run_id0=1000)
     b.init_device()
     torch.cuda.synchronize()
     assert np.array_equal(b.q.cpu().numpy(), q0)
     assert np.array_equal(b.eps.cpu().numpy(), eps0) and np.array_equal(b.price.cpu().numpy(), p0)
+    if rest:  # nn.Linear default init for the MLP agents, everything else in their blocks zero
+        assert np.array_equal(b.mlp.cpu().numpy().view(np.uint32), rest[0].view(np.uint32))
+        sd = next(d for d in b.mlp_state_dicts(3) if d is not None)
+        assert sd["fc1.weight"].abs().max() <= 1.0 and sd["fc_pi.weight"].abs().max() <= 1.0 / 16 and sd["fc_pi.weight"].std() > 0.02
     # agents.py:29: 12.5/(1-gamma) + N(0,1)
-    z = b.tables()[0].cpu().numpy().astype(np.float64) - 12.5 / (1 - game.agent[0].gamma)
+    iq = next(i for i in range(game.n_agents) if game.agent[i].kind == abi.THRL_AGENT_QTABLE)
+    z = b.tables()[iq].cpu().numpy().astype(np.float64) - 12.5 / (1 - game.agent[iq].gamma)
     assert abs(z.mean()) < 0.05 and abs(z.std() - 1.0) < 0.05
 
 
@@ -171,6 +195,8 @@ def test_greedy_eval_matches_oracle(golden):
     torch, oracle, engine = _mods()
     cfg = golden["config"]
     game = oracle.layout(cfg)
+    if game.mlp_stride:
+        pytest.skip("greedy evaluation covers QTable agents")
     q0, c0, eps0, p0 = oracle.init(game, 20, seed=3, dtype=np.float64, eps0=abi.eps0_from_config(cfg))
     price0 = np.random.default_rng(0).uniform(0, game.a, size=(20, 3))
     ref_a, ref_r = oracle.greedy_eval(game, q0, price0)

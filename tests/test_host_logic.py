@@ -71,10 +71,21 @@ def test_layout_matches_oracle_and_validates():
     bad["environment"]["nplayers"] = 3  # trainer.py:21-23
     with pytest.raises(AssertionError):
         _lib.game_layout(bad)
-    mlp = _cfg()
-    mlp["agents"][1]["name"] = "Reinforce"
+    ac = _cfg()
+    ac["agents"][1]["name"] = "ActorCritic"  # only QTable and Reinforce agents are implemented
     with pytest.raises(NotImplementedError):
-        _lib.game_layout(mlp)
+        _lib.game_layout(ac)
+    # the shipped example_config.json pairing: QTable + Reinforce (MLP 1 -> 256 -> 21)
+    mixed = _cfg()
+    mixed["agents"][1] = dict(name="Reinforce", gamma=0.995, actions=21, states=1, action_range=[0.2, 0.4])
+    g, o = _lib.game_layout(mixed), oracle.layout(mixed)
+    P = 2 * 256 + 21 * 256 + 21
+    assert g.run_stride == 101 * 21 and g.mlp_stride == 3 * P + 4 + 3 * 1000 == o.mlp_stride
+    assert g.mlp_buffer_len[1] == 1000 and g.agent[1].kind == abi.THRL_AGENT_REINFORCE and g.regular == 1
+    bad = _cfg()
+    bad["agents"][1] = dict(name="Reinforce", actions=21, states=4)  # the environment's state is one number
+    with pytest.raises(ValueError):
+        _lib.game_layout(bad)
 
 
 def test_dropin_class_surface():
@@ -111,9 +122,11 @@ def test_reference_streams_reproduce_recorded_draws(golden):
     the golden run, it regenerates the recorded u / random-action / demand-intercept streams bit for bit."""
     from th_rl_b200 import trainer
     cfg = golden["config"]
+    import torch
     seed = int(golden["seed"])
     random.seed(seed)
     np.random.seed(seed)
+    torch.manual_seed(seed)
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         p = os.path.join(d, "c.json")
@@ -121,12 +134,16 @@ def test_reference_streams_reproduce_recorded_draws(golden):
         config, ags, env = trainer.create_game(p)
     n = len(ags)
     for i in range(n):
-        assert np.array_equal(ags[i].table, golden["q0_%d" % i])
+        if cfg["agents"][i]["name"] == "QTable":
+            assert np.array_equal(ags[i].table, golden["q0_%d" % i])
+        else:  # same nn.Linear construction order => same initial weights under the same torch seed
+            for k, v in ags[i].state_dict().items():
+                assert np.array_equal(v.numpy(), golden["mlp0_%d_%s" % (i, k)]), k
     state = env.reset()
     assert state[0] == golden["p0"]
     E = golden["u"].shape[0]
     u, ra, new_a = trainer.reference_streams(ags, env, E)
-    assert np.array_equal(u, golden["u"]) and np.array_equal(ra, golden["ra"]) and np.array_equal(new_a, golden["new_a"])
+    assert np.array_equal(u, golden["u"], equal_nan=True) and np.array_equal(ra, golden["ra"]) and np.array_equal(new_a, golden["new_a"])
 
 
 def test_shard_bounds_cover_everything():

@@ -42,6 +42,8 @@ def lib():
     L.thrl_qtable_init.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int64, C.c_uint64, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.thrl_qtable_init.restype = C.c_int
+    L.thrl_game_init.argtypes = L.thrl_qtable_init.argtypes[:-1] + [C.c_void_p, C.c_void_p]
+    L.thrl_game_init.restype = C.c_int
     L.thrl_greedy_eval.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
     L.thrl_greedy_eval.restype = C.c_int

@@ -64,4 +64,59 @@ class QTable:
         self.counter = numpy.load(loc + "_counter.npy")
 
 
-AGENTS = {"QTable": QTable}
+class Reinforce:
+    """Host-side mirror of th_rl/agents.py:119-219 (MLP 1 -> 256 -> actions, policy gradient, Adam lr 2e-4).
+
+    The constructor builds the same two nn.Linear layers in the same order, so a script that seeds torch gets the same
+    initial weights as the reference; `save` / `load` use torch.save(state_dict) with the reference's key names.  Acting and
+    training are fused into the device scan (csrc/thrl_scan_mixed.cuh)."""
+
+    def __init__(self, states=4, actions=2, action_range=[0, 1], gamma=0.98, buffer="ReplayBuffer", capacity=50000,
+                 min_memory=1000, entropy=0, **kwargs):
+        import torch.nn as nn
+        self.gamma = gamma
+        self.action_range = action_range
+        self.actions = actions
+        self.states = states
+        self.fc1 = nn.Linear(states, 256)       # agents.py:137
+        self.fc_pi = nn.Linear(256, actions)    # agents.py:138
+        if buffer != "ReplayBuffer":
+            raise ValueError("unknown buffer %r (the reference only ships ReplayBuffer)" % (buffer,))
+        self.memory = ReplayBuffer(capacity, None)
+        self.capacity = capacity
+        self.min_memory = min_memory
+        self.entropy = entropy
+
+    def state_dict(self):
+        return {"fc1.weight": self.fc1.weight.detach().clone(), "fc1.bias": self.fc1.bias.detach().clone(),
+                "fc_pi.weight": self.fc_pi.weight.detach().clone(), "fc_pi.bias": self.fc_pi.bias.detach().clone()}
+
+    def load_state_dict(self, sd):
+        import torch
+        with torch.no_grad():
+            self.fc1.weight.copy_(torch.as_tensor(sd["fc1.weight"]).reshape(self.fc1.weight.shape))
+            self.fc1.bias.copy_(torch.as_tensor(sd["fc1.bias"]))
+            self.fc_pi.weight.copy_(torch.as_tensor(sd["fc_pi.weight"]))
+            self.fc_pi.bias.copy_(torch.as_tensor(sd["fc_pi.bias"]))
+
+    # agents.py:154-158 (note: / actions, not / (actions - 1))
+    def scale(self, action):
+        return action / self.actions * (self.action_range[1] - self.action_range[0]) + self.action_range[0]
+
+    def sample_action(self, state):
+        raise NotImplementedError(_FUSED % "Reinforce.sample_action")
+
+    def train_net(self):
+        raise NotImplementedError(_FUSED % "Reinforce.train_net")
+
+    # agents.py:215-219
+    def save(self, loc):
+        import torch
+        torch.save(self.state_dict(), loc)
+
+    def load(self, loc):
+        import torch
+        self.load_state_dict(torch.load(loc))
+
+
+AGENTS = {"QTable": QTable, "Reinforce": Reinforce}

@@ -19,6 +19,7 @@
 #include "thrl_scan_generic.cuh"
 #include "thrl_scan_lut2.cuh"
 #include "thrl_scan_lpc.cuh"
+#include "thrl_scan_mixed.cuh"
 #include "thrl_aux_kernels.cuh"
 
 namespace {
@@ -60,29 +61,44 @@ int validate_layout(ThrlGame* G) {
     return fail(THRL_ERR_BAD_CONFIG, "n_agents=%d outside 1..%d", G->n_agents, THRL_MAX_AGENTS);
   if (G->max_steps < 1) return fail(THRL_ERR_BAD_CONFIG, "max_steps=%d", G->max_steps);
   if (!(G->b == G->b) || G->b == 0.0) return fail(THRL_ERR_BAD_CONFIG, "b must be non-zero");
-  long long off = 0;
+  long long off = 0, moff = 0;
   int ring = 0, regular = 1;
   for (int i = 0; i < G->n_agents; ++i) {
     ThrlAgentSpec* s = &G->agent[i];
-    if (s->states < 1 || s->states > 65534) return fail(THRL_ERR_BAD_CONFIG, "agent %d: states=%d outside 1..65534", i, s->states);
+    G->mlp_buffer_len[i] = 0;
     if (s->actions < 2 || s->actions > THRL_MAX_ACTIONS)
       return fail(THRL_ERR_BAD_CONFIG, "agent %d: actions=%d outside 2..%d", i, s->actions, THRL_MAX_ACTIONS);
     if (s->capacity < 0 || s->min_memory < 0) return fail(THRL_ERR_BAD_CONFIG, "agent %d: negative capacity/min_memory", i);
+    const int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
+    long long need = (long long)T * ((mm + T - 1) / T);
+    if (need > s->capacity) need = s->capacity;
+    if (s->kind == THRL_AGENT_REINFORCE) {
+      if (s->states != 1) return fail(THRL_ERR_BAD_CONFIG, "agent %d: Reinforce.states=%d, the environment's state is one number", i, s->states);
+      if (s->hidden < 1 || s->hidden > 1024) return fail(THRL_ERR_BAD_CONFIG, "agent %d: hidden=%d outside 1..1024", i, s->hidden);
+      if (s->entropy != 0.0) return fail(THRL_ERR_UNSUPPORTED, "agent %d: entropy coefficient %g (only the reference default 0 is implemented)", i, s->entropy);
+      const long long P = 2LL * s->hidden + (long long)s->actions * s->hidden + s->actions;
+      G->mlp_buffer_len[i] = s->min_memory <= s->capacity ? (int32_t)need : 0;
+      s->mlp_offset = moff;
+      s->table_offset = 0;
+      moff += 3 * P + THRL_MLP_HEADER_WORDS + 3LL * G->mlp_buffer_len[i];
+      continue;
+    }
+    if (s->kind != THRL_AGENT_QTABLE) return fail(THRL_ERR_BAD_CONFIG, "agent %d: unknown kind %d", i, s->kind);
+    if (s->states < 1 || s->states > 65534) return fail(THRL_ERR_BAD_CONFIG, "agent %d: states=%d outside 1..65534", i, s->states);
     // the reference raises IndexError on the first encode whose row exceeds `states` (agents.py:88): price <= a
     if (!(s->max_state > 0.0) || G->a > s->max_state)
       return fail(THRL_ERR_BAD_CONFIG, "agent %d: a=%g > max_state=%g would index past the table (reference: IndexError)", i,
                   G->a, s->max_state);
     s->table_offset = off;
+    s->mlp_offset = 0;
     off += (long long)(s->states + 1) * s->actions;
     if (s->min_memory <= s->capacity) {
-      const int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
-      long long need = (long long)T * ((mm + T - 1) / T);
-      if (need > s->capacity) need = s->capacity;
       if (need > ring) ring = (int)need;
       if (s->min_memory > T) regular = 0;
     }
   }
   G->run_stride = off;
+  G->mlp_stride = moff;
   G->ring_len = ring;
   G->regular = regular;
   return THRL_OK;
@@ -346,6 +362,60 @@ int launch_lpc(thrl::Lut2Params& p, const DeviceInfo& dev, cudaStream_t stream) 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ mixed (MLP) launch
+template <typename QT>
+int launch_mixed(thrl::MixedParams& p, const DeviceInfo& dev, cudaStream_t stream) {
+  const ThrlGame& G = p.game;
+  const int n = G.n_agents, T = G.max_steps, Hp = p.Hp, esz = (int)sizeof(QT);
+  int lut = 0, par = 0, pmax = 0, hmax = 0, amax = 0;
+  for (int i = 0; i < n; ++i) {
+    const ThrlAgentSpec& s = G.agent[i];
+    lut += s.actions;
+    p.par_off[i] = 0;
+    if (s.kind == THRL_AGENT_QTABLE) continue;
+    const int P = 2 * s.hidden + s.actions * s.hidden + s.actions;
+    p.par_off[i] = par;
+    par += align_up(P, 4);
+    if (P > pmax) pmax = P;
+    if (s.hidden > hmax) hmax = s.hidden;
+    if (s.actions > amax) amax = s.actions;
+  }
+  p.lut_total = lut;
+  p.cta_bytes = align_up(2 * lut * 8, 16);
+  int o = 0;
+  p.off_P = o;    o += align_up(Hp * 8, 16);
+  p.off_newa = o; o += p.noisy ? align_up(T * 8, 16) : 0;
+  p.off_hp = o;   o += align_up(n * 5 * 8, 16);
+  p.off_old = o;  o += align_up(Hp * esz, 16);
+  p.off_pre = o;  o += align_up(T * n * 2, 16);
+  p.off_row = o;  o += align_up((Hp + 1) * 2, 16);
+  p.off_act = o;  o += align_up(n * Hp, 16);
+  p.off_par = o;  o += align_up(par * 4, 16);
+  p.off_grad = o; o += align_up(pmax * 4, 16);
+  p.off_h = o;    o += align_up((hmax + amax + 32) * 4, 16);
+  p.warp_bytes = o;
+  int warps = (dev.smem_optin - p.cta_bytes) / p.warp_bytes;
+  if (warps < 1) return fail(THRL_ERR_UNSUPPORTED, "one run with its MLP agents needs %d B of shared memory (> %d B)", p.warp_bytes + p.cta_bytes, dev.smem_optin);
+  if (warps > 16) warps = 16;
+  int grid = dev.sms;
+  {
+    const long long slots = (long long)dev.sms * warps;
+    const long long rounds = (p.n_runs + slots - 1) / slots;
+    const long long per_round = (p.n_runs + rounds - 1) / rounds;
+    warps = (int)((per_round + dev.sms - 1) / dev.sms);
+    if (warps < 1) warps = 1;
+    grid = (int)((per_round + warps - 1) / warps);
+    if (grid > dev.sms) grid = dev.sms;
+  }
+  const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
+  auto kern = thrl::qtable_scan_mixed<QT>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, warps * 32, smem, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return THRL_OK;
+}
+
 int check_args(const ThrlScanArgs* a) {
   if (!a || !a->game) return fail(THRL_ERR_BAD_ARGS, "args/game is NULL");
   if (a->n_runs < 0 || a->epoch_end < a->epoch_begin) return fail(THRL_ERR_BAD_ARGS, "negative run or epoch count");
@@ -354,6 +424,9 @@ int check_args(const ThrlScanArgs* a) {
   if (!a->q || !a->eps || !a->price) return fail(THRL_ERR_BAD_ARGS, "q / eps / price must not be NULL");
   if (a->rng_mode != THRL_RNG_PHILOX && !a->replay_ra) return fail(THRL_ERR_BAD_ARGS, "replay mode without replay_ra");
   if (a->rng_mode == THRL_RNG_REPLAY_DRAWS && !a->replay_u) return fail(THRL_ERR_BAD_ARGS, "REPLAY_DRAWS without replay_u");
+  bool has_mlp = false;
+  for (int i = 0; i < a->game->n_agents && i < THRL_MAX_AGENTS; ++i) has_mlp |= a->game->agent[i].kind != THRL_AGENT_QTABLE;
+  if (has_mlp && !a->mlp) return fail(THRL_ERR_BAD_ARGS, "the game has MLP agents but args->mlp is NULL");
   if (a->n_log_runs < 0 || a->n_log_runs > a->n_runs) return fail(THRL_ERR_BAD_ARGS, "n_log_runs=%lld outside 0..n_runs", (long long)a->n_log_runs);
   return THRL_OK;
 }
@@ -403,6 +476,19 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
   p.Hp = (p.game.ring_len > 0 ? p.game.ring_len : 1) + 1;
   p.noisy = (a->rng_mode == THRL_RNG_PHILOX) ? (p.game.noise_prob > 0.0) : (a->replay_new_a != nullptr);
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (p.game.mlp_stride > 0) {  // games with Reinforce agents: their own (correctness-first) kernel
+    thrl::MixedParams* m = new thrl::MixedParams();
+    std::unique_ptr<thrl::MixedParams> hold(m);
+    m->game = p.game;
+    m->n_runs = p.n_runs; m->run_id0 = p.run_id0; m->epoch_begin = p.epoch_begin; m->E = p.E; m->rng_mode = p.rng_mode;
+    m->k0 = p.k0; m->k1 = p.k1;
+    m->q = p.q; m->counter = p.counter; m->eps = p.eps; m->price = p.price; m->hp = p.hp;
+    m->replay_u = p.replay_u; m->replay_ra = p.replay_ra; m->replay_new_a = p.replay_new_a;
+    m->rewards_log = p.rewards_log; m->actions_log = p.actions_log; m->n_log_runs = p.n_log_runs; m->stats = p.stats;
+    m->trace_actions = p.trace_actions; m->trace_rewards = p.trace_rewards; m->trace_prices = p.trace_prices;
+    m->mlp = a->mlp; m->Hp = p.Hp; m->noisy = p.noisy; m->ring = p.ring; m->ring_bytes = p.ring_bytes;
+    return a->table_dtype == THRL_F64 ? launch_mixed<double>(*m, dev, stream) : launch_mixed<float>(*m, dev, stream);
+  }
   // Kernel choice.  THRL_KERNEL=generic forces the general kernel, lut2 / lpc pick one of the two specialised kernels
   // where they apply (tests exercise all three); default: see below.
   const char* force = getenv("THRL_KERNEL");
@@ -430,7 +516,13 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
 int thrl_qtable_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
                      const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps, double* price,
                      void* stream) {
-  if (!game || !eps0 || !q || !eps || !price) return fail(THRL_ERR_BAD_ARGS, "thrl_qtable_init: NULL argument");
+  return thrl_game_init(game, n_runs, run_id0, seed, table_dtype, hp, eps0, q, counter, eps, price, nullptr, stream);
+}
+
+int thrl_game_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
+                   const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps, double* price, float* mlp,
+                   void* stream) {
+  if (!game || !eps0 || !q || !eps || !price) return fail(THRL_ERR_BAD_ARGS, "thrl_game_init: NULL argument");
   if (table_dtype != THRL_F32 && table_dtype != THRL_F64) return fail(THRL_ERR_BAD_ARGS, "table_dtype=%d", table_dtype);
   thrl::InitParams p;
   memset(&p, 0, sizeof(p));
@@ -446,10 +538,12 @@ int thrl_qtable_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint
   p.f64 = table_dtype == THRL_F64;
   p.hp = hp;
   for (int i = 0; i < p.game.n_agents; ++i) p.eps0[i] = eps0[i];
-  p.q = q; p.counter = counter; p.eps = eps; p.price = price;
+  p.q = q; p.counter = counter; p.eps = eps; p.price = price; p.mlp = mlp;
+  if (p.game.mlp_stride > 0 && !mlp) return fail(THRL_ERR_BAD_ARGS, "the game has MLP agents but mlp is NULL");
   long long max_cells = 0;
   for (int i = 0; i < p.game.n_agents; ++i) {
-    const long long c = (long long)(p.game.agent[i].states + 1) * p.game.agent[i].actions;
+    const ThrlAgentSpec& sa = p.game.agent[i];
+    const long long c = sa.kind == THRL_AGENT_QTABLE ? (long long)(sa.states + 1) * sa.actions : 2 * (3LL * (2 * sa.hidden + sa.actions * sa.hidden + sa.actions) + 4 + 3LL * p.game.mlp_buffer_len[i]);
     if (c > max_cells) max_cells = c;
   }
   dim3 grid((unsigned)((max_cells / 2 + 255) / 256), (unsigned)(n_runs < 65535 ? n_runs : 65535));
@@ -470,6 +564,7 @@ int thrl_greedy_eval(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, 
   p.game = *game;
   int rc = validate_layout(&p.game);
   if (rc) return rc;
+  if (p.game.mlp_stride > 0) return fail(THRL_ERR_UNSUPPORTED, "thrl_greedy_eval covers QTable agents only");
   if (n_runs <= 0 || iters <= 0) return THRL_OK;
   DeviceInfo dev;
   rc = device_info(&dev);
@@ -526,7 +621,8 @@ extern "C" int thrl_qtable_scan_host(const ThrlScanArgs* a, int device) {
   const size_t qb = R * (size_t)G.run_stride * esz, cb = R * (size_t)G.run_stride * 4;
   const size_t logb = (size_t)a->n_log_runs * E * n * 8, statb = E * n * THRL_STATS_K * 8;
   const size_t rb = (size_t)ring_bytes(&G) * R;
-  DevBuf q, cnt, eps, price, hp, ring, ru, rra, rna, rl, al, st, ta, tr, tp;
+  DevBuf q, cnt, eps, price, hp, ring, ru, rra, rna, rl, al, st, ta, tr, tp, mlp;
+  const size_t mlpb = R * (size_t)G.mlp_stride * 4;
   ThrlScanArgs d = *a;
   d.game = &G;
 #define TRY(x) do { rc = (x); if (rc) { cudaStreamDestroy(s); return rc; } } while (0)
@@ -536,6 +632,7 @@ extern "C" int thrl_qtable_scan_host(const ThrlScanArgs* a, int device) {
   TRY(price.up(a->price, R * 8, s)); d.price = (double*)price.d;
   TRY(hp.up(a->hp, R * n * 32, s)); d.hp = (const double*)hp.d;
   TRY(ring.up(a->ring, rb, s)); d.ring = ring.d;
+  TRY(mlp.up(a->mlp, mlpb, s)); d.mlp = (float*)mlp.d;
   TRY(ru.up(a->replay_u, R * E * T * n * 8, s)); d.replay_u = (const double*)ru.d;
   TRY(rra.up(a->replay_ra, R * E * T * n * 4, s)); d.replay_ra = (const int32_t*)rra.d;
   TRY(rna.up(a->replay_new_a, R * E * T * 8, s)); d.replay_new_a = (const double*)rna.d;
@@ -551,6 +648,7 @@ extern "C" int thrl_qtable_scan_host(const ThrlScanArgs* a, int device) {
   TRY(eps.down(a->eps, R * n * 8, s));
   TRY(price.down(a->price, R * 8, s));
   TRY(ring.down(a->ring, rb, s));
+  TRY(mlp.down(a->mlp, mlpb, s));
   TRY(rl.down(a->rewards_log, logb, s));
   TRY(al.down(a->actions_log, logb, s));
   TRY(st.down(a->stats, statb, s));

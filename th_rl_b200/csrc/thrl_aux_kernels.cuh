@@ -51,6 +51,7 @@ struct InitParams {
   uint32_t* counter;
   double* eps;
   double* price;
+  float* mlp;
 };
 
 // grid.y = run, threads stride over the cell pairs of all agents: coalesced stores of the run slab.
@@ -61,6 +62,26 @@ __global__ void __launch_bounds__(256) qtable_init(const __grid_constant__ InitP
     const uint32_t gid = (uint32_t)(p.run_id0 + r);
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
+      if (s.kind != THRL_AGENT_QTABLE) {
+        // nn.Linear default init (kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias,
+        // agents.py:137-138); Adam state, header and transition buffer zeroed
+        const long long Pn = 2LL * s.hidden + (long long)s.actions * s.hidden + s.actions;
+        const long long words = 3 * Pn + THRL_MLP_HEADER_WORDS + 3LL * G.mlp_buffer_len[i];
+        float* blk = p.mlp + r * G.mlp_stride + s.mlp_offset;
+        const float b_fc1 = 1.0f, b_pi = (float)__ddiv_rn(1.0, sqrt((double)s.hidden));
+        for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (long long)gridDim.x * blockDim.x) {
+          float v = 0.0f;
+          if (w < Pn) {
+            uint32_t x[4];
+            philox4x32_10(gid, (uint32_t)(w >> 1), (uint32_t)i, kStreamInitQ << 16, p.k0, p.k1, x);
+            const double u = (w & 1) ? u53(x[2], x[3]) : u53(x[0], x[1]);
+            const float bound = (w < 2LL * s.hidden) ? b_fc1 : b_pi;
+            v = __fmul_rn((float)__dsub_rn(__dmul_rn(2.0, u), 1.0), bound);
+          }
+          blk[w] = v;
+        }
+        continue;
+      }
       const double gamma = p.hp ? p.hp[(r * n + i) * 4 + 1] : s.gamma;
       const double base = 12.5 / (1.0 - gamma);  // agents.py:29
       const long long cells = (long long)(s.states + 1) * s.actions;

@@ -48,6 +48,9 @@ class RunBatch:
             self.eps = torch.empty((R, n), dtype=torch.float64, device=self.device)
             self.price = torch.empty((R,), dtype=torch.float64, device=self.device)
             self.hp = None if hp is None else torch.as_tensor(np.ascontiguousarray(hp, np.float64)).reshape(R, n, 4).to(self.device)
+            self.mlp = None  # parameters, Adam state and transition buffers of the MLP agents (include/thrl.h)
+            if g.mlp_stride:
+                self.mlp = torch.zeros((R, g.mlp_stride), dtype=torch.float32, device=self.device)
             self.ring = None
             if not g.regular:
                 rb = lib().thrl_ring_bytes(C.byref(g))
@@ -58,13 +61,13 @@ class RunBatch:
         """QTable.__init__ / environment.reset() for every run, on the device, from Philox(seed, global run id)."""
         eps0 = (C.c_double * self.game.n_agents)(*abi.eps0_from_config(self.config))
         with torch.cuda.device(self.device):
-            check(lib().thrl_qtable_init(C.byref(self.game), self.n_runs, self.run_id0, self.seed, self.table_dtype,
-                                         _dp(self.hp), eps0, _dp(self.q), _dp(self.counter), _dp(self.eps),
-                                         _dp(self.price), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            check(lib().thrl_game_init(C.byref(self.game), self.n_runs, self.run_id0, self.seed, self.table_dtype,
+                                       _dp(self.hp), eps0, _dp(self.q), _dp(self.counter), _dp(self.eps),
+                                       _dp(self.price), _dp(self.mlp), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         self.epoch = 0
         return self
 
-    def load_state(self, q, eps, price, counter=None, non_blocking=False):
+    def load_state(self, q, eps, price, counter=None, non_blocking=False, mlp=None):
         """Initial state provided by the caller as host arrays / tensors (e.g. tables drawn by numpy like the reference)."""
         def put(dst, src, dt):
             src = (src if torch.is_tensor(src) else torch.as_tensor(np.asarray(src))).reshape(dst.shape)
@@ -74,6 +77,10 @@ class RunBatch:
         put(self.q, q, self.dtype)
         put(self.eps, eps, torch.float64)
         put(self.price, price, torch.float64)
+        if self.mlp is not None:
+            if mlp is None:
+                raise ValueError("games with MLP agents need the mlp slab")
+            put(self.mlp, mlp, torch.float32)
         if counter is not None:
             put(self.counter, torch.as_tensor(np.asarray(counter).astype(np.uint32).view(np.int32)) if not torch.is_tensor(counter) else counter, torch.int32)
         else:
@@ -126,6 +133,7 @@ class RunBatch:
             a.q, a.counter, a.eps, a.price = _dp(self.q[rb:re_]), _dp(self.counter[rb:re_]), _dp(self.eps[rb:re_]), _dp(self.price[rb:re_])
             a.hp = None if self.hp is None else _dp(self.hp[rb:re_])
             a.ring = None if self.ring is None else _dp(self.ring[rb:re_])
+            a.mlp = None if self.mlp is None else _dp(self.mlp[rb:re_])
             a.replay_u, a.replay_ra, a.replay_new_a = _dp(ru), _dp(rra), _dp(rna)
             a.rewards_log, a.actions_log, a.n_log_runs = _dp(out.rewards_log), _dp(out.actions_log), int(n_log_runs)
             a.stats = _dp(out.stats)
@@ -143,12 +151,27 @@ class RunBatch:
         """Per-agent tables [R, states+1, actions] (views of the packed slab)."""
         q = self.q if run is None else self.q[run:run + 1]
         return [q[:, s.table_offset:s.table_offset + (s.states + 1) * s.actions].reshape(-1, s.states + 1, s.actions)
+                if s.kind == abi.THRL_AGENT_QTABLE else None
                 for s in (self.game.agent[i] for i in range(self.game.n_agents))]
 
     def counters(self, run=None):
         c = self.counter if run is None else self.counter[run:run + 1]
         return [c[:, s.table_offset:s.table_offset + (s.states + 1) * s.actions].reshape(-1, s.states + 1, s.actions)
+                if s.kind == abi.THRL_AGENT_QTABLE else None
                 for s in (self.game.agent[i] for i in range(self.game.n_agents))]
+
+    def mlp_state_dicts(self, run=0):
+        """Per agent: parameters of `run` in torch state_dict names/shapes (None for QTable agents)."""
+        out = []
+        for s in (self.game.agent[i] for i in range(self.game.n_agents)):
+            if s.kind == abi.THRL_AGENT_QTABLE:
+                out.append(None)
+                continue
+            H, A = s.hidden, s.actions
+            p = self.mlp[run, s.mlp_offset:s.mlp_offset + abi.mlp_param_count(s)].cpu()
+            out.append({"fc1.weight": p[:H].reshape(H, 1).clone(), "fc1.bias": p[H:2 * H].clone(),
+                        "fc_pi.weight": p[2 * H:2 * H + A * H].reshape(A, H).clone(), "fc_pi.bias": p[2 * H + A * H:].clone()})
+        return out
 
     def greedy_eval(self, price0):
         """utils.play_game for every run: price0 [R, iters] -> (actions, rewards) [R, iters*T, n] f64 device tensors."""
@@ -219,13 +242,15 @@ def scan_from_host(batch, host, epochs, n_chunks=8):
 
 def scan_host(config, q, eps, price, epochs, *, counter=None, hp=None, rng_mode=abi.THRL_RNG_PHILOX, seed=0, run_id0=0,
               epoch_begin=0, replay_u=None, replay_ra=None, replay_new_a=None, n_log_runs=0, stats=False, trace=False,
-              device=0):
+              device=0, mlp=None):
     """thrl_qtable_scan_host: HOST numpy buffers in and out, all copies inside the call (the reference-facing
     boundary; bench.py's e2e leg times exactly this).  q/eps/price(/counter) are updated IN PLACE."""
     g = game_layout(config)
     n, T, E = g.n_agents, g.max_steps, int(epochs)
     R = q.shape[0]
     assert q.flags.c_contiguous and q.dtype in (np.float32, np.float64) and q.shape == (R, g.run_stride)
+    if g.mlp_stride:
+        assert mlp is not None and mlp.dtype == np.float32 and mlp.flags.c_contiguous and mlp.shape == (R, g.mlp_stride)
     assert eps.dtype == np.float64 and price.dtype == np.float64 and eps.flags.c_contiguous and price.flags.c_contiguous
     out = ScanOutput()
     keep = []
@@ -260,6 +285,7 @@ def scan_host(config, q, eps, price, epochs, *, counter=None, hp=None, rng_mode=
         assert counter.dtype == np.uint32 and counter.shape == q.shape and counter.flags.c_contiguous
         a.counter = outp(counter)
     a.hp = inp(hp, np.float64, (R, n, 4))
+    a.mlp = outp(mlp) if g.mlp_stride else None
     a.replay_u = inp(replay_u, np.float64, (R, E, T, n))
     a.replay_ra = inp(replay_ra, np.int32, (R, E, T, n))
     a.replay_new_a = inp(replay_new_a, np.float64, (R, E, T))

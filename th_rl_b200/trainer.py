@@ -37,8 +37,8 @@ def create_game(configpath):
     agents = []
     for agent in config["agents"]:
         if agent["name"] not in AGENTS:
-            raise NameError("name %r is not defined (th_rl_b200 implements the QTable hot path; MLP agents are out of "
-                            "scope, see DESIGN.md)" % agent["name"])
+            raise NameError("name %r is not defined (th_rl_b200 implements QTable and Reinforce agents; ActorCritic / CAC "
+                            "are the next row, see DESIGN.md)" % agent["name"])
         agents.append(AGENTS[agent["name"]](**agent))
     assert len(agents) == config["environment"]["nplayers"], "Bad config. Check number of agents."
     if config["environment"]["name"] not in ENVIRONMENTS:
@@ -53,17 +53,20 @@ def reference_streams(agents, environment, epochs):
     frozen within an episode, decayed after it: agents.py:78); then the environment's numpy.random.uniform(0,1) and, iff it is
     below noise_prob, numpy.random.uniform(0.7a, a) (environments.py:28-29).  Returns (u, ra, new_a) for REPLAY_DRAWS."""
     n, T = len(agents), environment.max_steps
-    u = numpy.empty((epochs, T, n), numpy.float64)
+    u = numpy.full((epochs, T, n), numpy.nan, numpy.float64)
     ra = numpy.full((epochs, T, n), -1, numpy.int32)
     new_a = numpy.empty((epochs, T), numpy.float64)
-    eps = [a.epsilon for a in agents]
-    spaces = [a.action_space for a in agents]
+    qt = [hasattr(a, "epsilon") for a in agents]  # MLP agents draw from torch's generator inside the step, not here:
+    eps = [a.epsilon if q else 0.0 for a, q in zip(agents, qt)]  # their columns stay (nan, -1) = "sample on the device"
+    spaces = [a.action_space if q else None for a, q in zip(agents, qt)]
     a_hi, noise = environment.a, environment.noise_prob
     uniform, choice, npuniform = random.uniform, random.choice, numpy.random.uniform
     for e in range(epochs):
         ue, re_, ne = u[e], ra[e], new_a[e]
         for t in range(T):
             for i in range(n):
+                if not qt[i]:
+                    continue
                 x = uniform(0, 1)
                 ue[t, i] = x
                 if x < eps[i]:
@@ -72,7 +75,7 @@ def reference_streams(agents, environment, epochs):
                 ne[t] = npuniform(a_hi * 0.7, a_hi)
             else:
                 ne[t] = a_hi
-        eps = [a.eps_end + (x - a.eps_end) * a.eps_step for a, x in zip(agents, eps)]
+        eps = [a.eps_end + (x - a.eps_end) * a.eps_step if q else 0.0 for a, x, q in zip(agents, eps, qt)]
     return u, ra, new_a
 
 
@@ -124,16 +127,27 @@ def train_one(exp_path, configpath, loadonly=False, print_eps=False, rng="refere
     t = time.time()
     state = environment.reset()  # trainer.py:45 — the second uniform draw, like the reference
     batch = engine.RunBatch(config, 1, device=device, dtype=torch.float64, seed=random.getrandbits(63) if rng != "reference" else 0)
-    q0 = numpy.concatenate([a.table.reshape(-1) for a in agents])[None]
-    batch.load_state(q0, [[a.epsilon for a in agents]], [float(state[0])])
+    is_q = [isinstance(a, AGENTS["QTable"]) for a in agents]
+    tabs0 = [a.table.reshape(-1) for a, q in zip(agents, is_q) if q]
+    q0 = numpy.concatenate(tabs0)[None] if tabs0 else numpy.zeros((1, 0))
+    mlp0 = None
+    if batch.mlp is not None:  # MLP agents: the constructor's nn.Linear initialisation (agents.py:137-138)
+        mlp0 = numpy.zeros((1, batch.game.mlp_stride), numpy.float32)
+        for i, a in enumerate(agents):
+            if not is_q[i]:
+                flat = numpy.concatenate([v.numpy().reshape(-1) for v in a.state_dict().values()])
+                mlp0[0, batch.game.agent[i].mlp_offset:batch.game.agent[i].mlp_offset + flat.size] = flat
+    batch.load_state(q0, [[a.epsilon if q else 0.0 for a, q in zip(agents, is_q)]], [float(state[0])], mlp=mlp0)
     chunk = int(chunk_epochs or max(1, min(epochs, print_freq, max(1, 2_000_000 // max(1, max_steps * n)))))
     e0 = 0
     while e0 < epochs:
         E = min(chunk, epochs - e0)
         if rng == "reference":
-            for a, x in zip(agents, batch.eps[0].tolist()):
-                a.epsilon = x
+            for a, x, q in zip(agents, batch.eps[0].tolist(), is_q):
+                if q:
+                    a.epsilon = x
             u, ra, new_a = reference_streams(agents, environment, E)
+            u = numpy.nan_to_num(u, nan=2.0)  # MLP agents: no host draw; ra = -1 leaves their sample to the device
             noisy = environment.noise_prob > 0
             out = batch.scan(E, rng_mode=abi.THRL_RNG_REPLAY_DRAWS, replay_u=u[None], replay_ra=ra[None],
                              replay_new_a=new_a[None] if noisy else None, n_log_runs=1)
@@ -144,15 +158,19 @@ def train_one(exp_path, configpath, loadonly=False, print_eps=False, rng="refere
         eps_now = batch.eps[0].tolist()
         for e in range(e0, e0 + E):
             if not (e + 1) % print_freq:
-                _print_progress(config, config["agents"], rewards_log, actions_log, eps_now, e, print_freq,
+                _print_progress(config, config["agents"], rewards_log, actions_log, [x for x, q in zip(eps_now, is_q) if q], e, print_freq,
                                 time.time() - t, print_eps)
                 t = time.time()
         e0 += E
 
-    tabs = [x[0].cpu().numpy() for x in batch.tables()]
-    cnts = [x[0].cpu().numpy().view(numpy.uint32).astype(numpy.float64) for x in batch.counters()]
+    tabs, cnts, sds = batch.tables(), batch.counters(), batch.mlp_state_dicts(0) if batch.mlp is not None else [None] * n
     for i, a in enumerate(agents):
-        a.table, a.counter, a.epsilon = tabs[i].astype(numpy.float64), cnts[i], batch.eps[0, i].item()
+        if is_q[i]:
+            a.table = tabs[i][0].cpu().numpy().astype(numpy.float64)
+            a.counter = cnts[i][0].cpu().numpy().view(numpy.uint32).astype(numpy.float64)
+            a.epsilon = batch.eps[0, i].item()
+        else:
+            a.load_state_dict(sds[i])
     environment.state = batch.price[0].item()
     save_run(exp_path, config, agents, rewards_log, actions_log)
 
@@ -224,18 +242,23 @@ def train_many(config, runs, epochs=None, *, seed=0, dtype=None, device=None, lo
 
 def export_runs_to(cfg_dir, config, res, count, first_index=0):
     """Write local runs 0..count-1 as <cfg_dir>/<global index>/{k.npy, k_counter.npy, config.json, log.csv}."""
-    from .agents import QTable
     b = res.batch
     if count <= 0:
         return
     if not os.path.exists(cfg_dir):
         os.makedirs(cfg_dir)
-    tabs = [t[:count].cpu().numpy().astype(numpy.float64) for t in b.tables()]
-    cnts = [c[:count].cpu().numpy().view(numpy.uint32).astype(numpy.float64) for c in b.counters()]
-    state = numpy.random.get_state()
+    import torch
+    tabs = [None if t is None else t[:count].cpu().numpy().astype(numpy.float64) for t in b.tables()]
+    cnts = [None if c is None else c[:count].cpu().numpy().view(numpy.uint32).astype(numpy.float64) for c in b.counters()]
+    state, tstate = numpy.random.get_state(), torch.get_rng_state()
     for r in range(count):
-        agents = [QTable(**a) for a in config["agents"]]
+        agents = [AGENTS[a["name"]](**a) for a in config["agents"]]
+        sds = b.mlp_state_dicts(r) if b.mlp is not None else [None] * len(agents)
         for i, a in enumerate(agents):
-            a.table, a.counter = tabs[i][r], cnts[i][r]
+            if tabs[i] is None:
+                a.load_state_dict(sds[i])
+            else:
+                a.table, a.counter = tabs[i][r], cnts[i][r]
         save_run(os.path.join(cfg_dir, str(first_index + r)), config, agents, res.rewards_log[r], res.actions_log[r])
-    numpy.random.set_state(state)  # building the carrier objects must not disturb the caller's numpy stream
+    numpy.random.set_state(state)  # building the carrier objects must not disturb the caller's random streams
+    torch.set_rng_state(tstate)

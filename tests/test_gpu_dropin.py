@@ -115,3 +115,39 @@ def test_train_many_matches_single_batch_and_exports(tmp_path):
     assert np.array_equal(np.load(tmp_path / "x" / "1" / "0.npy"), b.tables()[0][1].cpu().numpy().astype(np.float64))
     # learning signal: total reward per step sits between 0 and the cartel level 25 (th_rl/utils.py:91-92)
     assert 0 < mean_r.sum(1).mean() < 25.0
+
+
+def _shipped_example_config(epochs):
+    """th_rl/some_path/configs/example_config.json as shipped (QTable + Reinforce), with training.epochs shortened."""
+    return {"agents": [dict(name="QTable", gamma=0.95, actions=21, states=100, alpha=0.1, eps_end=0.001, epsilon=0.5,
+                            eps_step=0.9995, action_range=[0.2, 0.4]),
+                       dict(name="Reinforce", gamma=0.995, actions=21, states=1, action_range=[0.2, 0.4])],
+            "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=2, max_steps=100),
+            "training": dict(print_freq=500, epochs=epochs)}
+
+
+def test_cli_runs_the_shipped_example_config(tmp_path):
+    """main.py on the reference's own example config (QTable agent 0, Reinforce agent 1): both CLI modes write the
+    reference's artefacts -- `1` is a torch state_dict exactly as th_rl/agents.py:215-216 saves it."""
+    import torch
+    from click.testing import CliRunner
+    from th_rl_b200.main import main
+    cdir = tmp_path / "configs"
+    cdir.mkdir()
+    (cdir / "example_config.json").write_text(json.dumps(_shipped_example_config(30)))
+    r = CliRunner().invoke(main, ["--dir", str(cdir), "--runs", "2"])
+    assert r.exit_code == 0, r.output
+    for i in range(2):
+        d = tmp_path / "runs" / "example_config" / str(i)
+        assert sorted(os.listdir(d)) == ["0.npy", "0_counter.npy", "1", "config.json", "log.csv"]
+        sd = torch.load(d / "1")
+        assert {k: tuple(v.shape) for k, v in sd.items()} == {"fc1.weight": (256, 1), "fc1.bias": (256,),
+                                                              "fc_pi.weight": (21, 256), "fc_pi.bias": (21,)}
+        assert np.load(d / "0_counter.npy").sum() == 30 * 100
+        assert len((d / "log.csv").read_text().splitlines()) == 32
+    a, b = torch.load(tmp_path / "runs" / "example_config" / "0" / "1"), torch.load(tmp_path / "runs" / "example_config" / "1" / "1")
+    assert not torch.equal(a["fc_pi.weight"], b["fc_pi.weight"])  # independent runs
+    (cdir / "second.json").write_text(json.dumps(_shipped_example_config(12)))
+    r = CliRunner().invoke(main, ["--dir", str(cdir), "--runs", "1", "--mode", "reference"])
+    assert r.exit_code == 0, r.output
+    assert sorted(os.listdir(tmp_path / "runs" / "second" / "0")) == ["0.npy", "0_counter.npy", "1", "config.json", "log.csv"]

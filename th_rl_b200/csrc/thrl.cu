@@ -97,6 +97,7 @@ int validate_layout(ThrlGame* G) {
       if (s->min_memory > T) regular = 0;
     }
   }
+  if (off >= (1LL << 31) || moff >= (1LL << 31)) return fail(THRL_ERR_UNSUPPORTED, "one run's tables hold %lld elements (limit 2^31-1)", off);
   G->run_stride = off;
   G->mlp_stride = moff;
   G->ring_len = ring;

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
 #pragma unroll
               for (int a = 0; a < 4; ++a) {
                 const ThrlAgentSpec& s = G.agent[ia[a] >= 0 ? ia[a] : 0];
-                const QT* row = tab + s.table_offset + (size_t)ra[a] * s.actions;
+                const QT* row = tab + ((int)s.table_offset + ra[a] * s.actions);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   const int kk = lane + 32 * c;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
                 bidx[a] = 0x7fffffff;
                 if (ia[a] >= 0) {
                   const ThrlAgentSpec& s = G.agent[ia[a]];
-                  const QT* row = tab + s.table_offset + (size_t)ra[a] * s.actions;
+                  const QT* row = tab + ((int)s.table_offset + ra[a] * s.actions);
                   for (int kk = lane; kk < s.actions; kk += 32) {
                     const QT v = row[kk];
                     if (v > bval[a] || bidx[a] == 0x7fffffff) { bval[a] = v; bidx[a] = kk; }
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
         for (int j = lane; j < L; j += 32) {
           int sl = first + j;
           if (sl >= Hp) sl -= Hp;
-          oldv[j] = tb[(size_t)rowbuf[j] * A + act[i * Hp + sl]];
+          oldv[j] = tb[(int)rowbuf[j] * A + act[i * Hp + sl]];
         }
       }
       __syncwarp();
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               const ThrlAgentSpec& s = G.agent[on[a] ? i : 0];
               const int A = s.actions;
               const int ns = on[a] ? (int)rowbuf_all[i * p.row_stride + (j - des[i * 4 + 3]) + 1] : 0;
-              const QT* row = tab + s.table_offset + (size_t)ns * A;
+              const QT* row = tab + ((int)s.table_offset + ns * A);
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const int kk = lane + 32 * c;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               if (on[a]) {
                 const ThrlAgentSpec& s = G.agent[i];
                 const int ns = rowbuf_all[i * p.row_stride + (j - des[i * 4 + 3]) + 1];
-                const QT* row = tab + s.table_offset + (size_t)ns * s.actions;
+                const QT* row = tab + ((int)s.table_offset + ns * s.actions);
                 for (int k = lane; k < s.actions; k += 32) { const QT v = row[k]; loc[a] = v > loc[a] ? v : loc[a]; }
               }
             }
@@ -402,8 +402,9 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
             const double nv = __dadd_rn(__dmul_rn(__dsub_rn(1.0, alpha), (double)oldv_all[i * p.old_stride + jj]),
                                         __dmul_rn(alpha, __dadd_rn(reward, __dmul_rn(gamma, next_max))));
             if ((k & 31) == lane) {  // the lane that owns column k: it alone ever reads or writes that column
-              tab[s.table_offset + (size_t)st * s.actions + k] = (QT)nv;
-              if (cnt) atomicAdd(cnt + s.table_offset + (size_t)st * s.actions + k, 1u);  // :76, fire-and-forget RED
+              const int cell = (int)s.table_offset + st * s.actions + k;  // a run's slab has < 2^31 elements (checked at layout)
+              tab[cell] = (QT)nv;
+              if (cnt) atomicAdd(cnt + cell, 1u);  // :76, fire-and-forget RED
             }
             if (lane == 0 && st < p.gcap[i]) Gc[goff + st] = 0xFF;  // the row changed: its greedy action is recomputed on the next visit
           }

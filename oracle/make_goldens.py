@@ -103,6 +103,17 @@ CASES = {
                                       dict(name="Reinforce", gamma=0.5, actions=5, states=1, action_range=[0.05, 0.2],
                                            min_memory=90, capacity=100)],
                               environment=_env(nplayers=3, max_steps=30), training=dict(epochs=12, print_freq=1000)), 10),
+    # ActorCritic (agents.py:222-305): value head with bias 1000, [N,N] advantage broadcast; QTable + ActorCritic
+    "mixed_qa_seed11": (dict(agents=[_agent(), dict(name="ActorCritic", gamma=0.98, actions=21, states=1,
+                                                    action_range=[0.2, 0.4], min_memory=200)],
+                             environment=_env(), training=dict(epochs=8, print_freq=1000)), 11),
+    # ActorCritic + Reinforce + QTable, short episodes
+    "mixed_arq_seed12": (dict(agents=[dict(name="ActorCritic", gamma=0.9, actions=7, states=1, action_range=[0.1, 0.3],
+                                           min_memory=90, capacity=120),
+                                      dict(name="Reinforce", gamma=0.5, actions=5, states=1, action_range=[0.05, 0.2],
+                                           min_memory=60),
+                                      _agent(actions=9, states=40, action_range=[0.1, 0.3])],
+                              environment=_env(nplayers=3, max_steps=30), training=dict(epochs=12, print_freq=1000)), 12),
 }
 
 
@@ -168,6 +179,20 @@ def record_case(cfg, seed):
             super().train_net()
             rec["eps_trace"].append(float("nan"))
 
+    class ActorCritic(ragents.ActorCritic):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            rec.setdefault("mlp0", []).append({k: v.detach().numpy().copy() for k, v in self.state_dict().items()})
+
+        def sample_action(self, state):
+            a = super().sample_action(state)
+            rec["acts"].append((float("nan"), -1, int(a)))
+            return a
+
+        def train_net(self):
+            super().train_net()
+            rec["eps_trace"].append(float("nan"))
+
     class NoisyPriceState(renv.NoisyPriceState):
         def reset(self):
             s = super().reset()
@@ -190,10 +215,11 @@ def record_case(cfg, seed):
             return out
 
     proxy = _RandomProxy(random, draws)
-    saved = (ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce)
+    saved = (ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce, rtrainer.ActorCritic)
     ragents.random = proxy
     rtrainer.QTable = QTable
     rtrainer.Reinforce = Reinforce
+    rtrainer.ActorCritic = ActorCritic
     rtrainer.NoisyPriceState = NoisyPriceState
     torch.set_num_threads(1)
     try:
@@ -217,7 +243,7 @@ def record_case(cfg, seed):
                 header = [f.readline().strip(), f.readline().strip()]
                 log = numpy.loadtxt(f, delimiter=",", ndmin=2)
     finally:
-        ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce = saved
+        ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce, rtrainer.ActorCritic = saved
 
     E = cfg["training"]["epochs"]
     T = cfg["environment"]["max_steps"]

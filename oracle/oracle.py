@@ -87,8 +87,7 @@ def pack_mlp(game, per_agent, R=1):
         if s.kind == abi.THRL_AGENT_QTABLE:
             continue
         d = per_agent[i]
-        flat = np.concatenate([np.asarray(d["fc1.weight"], np.float32).reshape(-1), np.asarray(d["fc1.bias"], np.float32).reshape(-1),
-                               np.asarray(d["fc_pi.weight"], np.float32).reshape(-1), np.asarray(d["fc_pi.bias"], np.float32).reshape(-1)])
+        flat = np.concatenate([np.asarray(d[k], np.float32).reshape(-1) for k in abi.mlp_param_names(s)])
         assert flat.size == abi.mlp_param_count(s)
         slab[:, s.mlp_offset:s.mlp_offset + flat.size] = flat
     return slab
@@ -102,10 +101,13 @@ def unpack_mlp(game, slab, run=0):
         if s.kind == abi.THRL_AGENT_QTABLE:
             out.append(None)
             continue
-        H, A = s.hidden, s.actions
         p = np.asarray(slab)[run, s.mlp_offset:s.mlp_offset + abi.mlp_param_count(s)]
-        out.append({"fc1.weight": p[:H].reshape(H, 1).copy(), "fc1.bias": p[H:2 * H].copy(),
-                    "fc_pi.weight": p[2 * H:2 * H + A * H].reshape(A, H).copy(), "fc_pi.bias": p[2 * H + A * H:].copy()})
+        d, o = {}, 0
+        for k, shp in abi.mlp_param_shapes(s).items():
+            cnt = int(np.prod(shp))
+            d[k] = p[o:o + cnt].reshape(shp).copy()
+            o += cnt
+        out.append(d)
     return out
 
 

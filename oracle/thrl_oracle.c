@@ -169,6 +169,11 @@ static float det_expf(float x) {
   p = p + 1.0f;
   return ldexpf(p, (int)kf);
 }
+static int mlp_P(const ThrlAgentSpec* s) {
+  const int p = 2 * s->hidden + s->actions * s->hidden + s->actions;
+  return s->kind == THRL_AGENT_ACTORCRITIC ? p + s->hidden + 1 : p;
+}
+static int mlp_entry_words(const ThrlAgentSpec* s) { return s->kind == THRL_AGENT_ACTORCRITIC ? 4 : 3; }
 /* pi(x) (agents.py:148-152): h = relu(fc1(x)), logits = fc_pi(h), softmax.  par: w1[H] b1[H] W[A][H] bp[A]. */
 static void mlp_forward(const float* par, int H, int A, float s, float* h, float* prob) {
   const float *w1 = par, *b1 = par + H, *W = par + 2 * H, *bp = par + 2 * H + (size_t)A * H;
@@ -196,69 +201,33 @@ static int mlp_sample(const float* prob, int A, uint32_t x) {
   for (int k = 0; k < A; ++k) { c = c + prob[k]; if (c > u) return k; }
   return A - 1;
 }
-/* Reinforce.train_net (agents.py:170-194) on the N buffered transitions buf[(head+j) % cap] = (state, action, reward),
- * then clip_grad_norm_(1.0) and one Adam step.  blk = this agent's block of the MLP slab (include/thrl.h).
- * scratch: 2*P + H + A floats. */
-static void mlp_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, int N, float* scratch) {
-  const int H = sp->hidden, A = sp->actions;
-  const int P = 2 * H + A * H + A;
+/* xor-butterfly sum of 32 lane partials, the order the device's shuffle reduction uses */
+static float butterfly_sum(float* p) {
+  for (int off = 16; off >= 1; off >>= 1) {
+    float q[32];
+    for (int l = 0; l < 32; ++l) q[l] = p[l] + p[l ^ off];
+    for (int l = 0; l < 32; ++l) p[l] = q[l];
+  }
+  return p[0];
+}
+/* v(x) (agents.py:259-262) with h = relu(fc1(x)) already computed: lane-strided partial dot products, butterfly sum, + bias */
+static float ac_value(const float* wv, float bv, const float* h, int H) {
+  float part[32];
+  for (int l = 0; l < 32; ++l) part[l] = 0.0f;
+  for (int j = 0; j < H; ++j) { float t = h[j] * wv[j]; part[j & 31] = part[j & 31] + t; }
+  float v = butterfly_sum(part);
+  return v + bv;
+}
+static void mlp_hidden(const float* par, int H, float s, float* h) {
+  const float *w1 = par, *b1 = par + H;
+  for (int j = 0; j < H; ++j) { float v = s * w1[j]; v = v + b1[j]; h[j] = v > 0.0f ? v : 0.0f; }
+}
+
+/* clip_grad_norm_(parameters, 1.0) then one Adam step (torch.optim.Adam defaults, single-tensor formulas); g in state_dict order */
+static void mlp_clip_adam(float* blk, const ThrlAgentSpec* sp, const float* g) {
+  const int P = mlp_P(sp);
   float *par = blk, *am = blk + P, *av = blk + 2 * (size_t)P;
   int32_t* hdr = (int32_t*)(blk + 3 * (size_t)P);
-  float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
-  float *g = scratch, *h = scratch + P, *prob = h + H, *disc = prob + A; /* disc: N floats, caller sizes scratch */
-  float *gw1 = g, *gb1 = g + H, *gW = g + 2 * H, *gbp = g + 2 * H + (size_t)A * H;
-  const float* W = par + 2 * H;
-  for (int i = 0; i < P; ++i) g[i] = 0.0f;
-  /* discounted returns over the whole buffer, newest to oldest (:177-180), float32 */
-  const float gam = (float)sp->gamma;
-  for (int j = N - 1; j >= 0; --j) {
-    const float r = buf[(size_t)((head + j) % cap) * 3 + 2];
-    if (j == N - 1) disc[j] = r;
-    else { float t = gam * disc[j + 1]; disc[j] = r + t; }
-    buf[(size_t)((head + j) % cap) * 3 + 2] = disc[j]; /* kept in the (about to be emptied) buffer, as the device does */
-  }
-  /* (discounted - mean) / std, unbiased std (:181) */
-  double sum = 0.0;
-  for (int j = 0; j < N; ++j) sum += (double)disc[j];
-  const float mean = (float)(sum / (double)N);
-  double ss = 0.0;
-  for (int j = 0; j < N; ++j) { const double d = (double)disc[j] - (double)mean; ss += d * d; }
-  const float sd = (float)sqrt(ss / (double)(N - 1));
-  const float invN = 1.0f / (float)N;
-  /* loss = -mean(log_prob(a) * G) (:185); d loss / d logits_k = (p_k - [k == a]) * G / N, back through fc_pi, relu, fc1 */
-  for (int j = 0; j < N; ++j) {
-    const float* tr = buf + (size_t)((head + j) % cap) * 3;
-    const float s = tr[0];
-    int32_t a;
-    memcpy(&a, &tr[1], 4);
-    float G = disc[j] - mean;
-    G = G / sd;
-    const float c = G * invN;
-    mlp_forward(par, H, A, s, h, prob);
-    for (int k = 0; k < A; ++k) {
-      float dl = prob[k] - (k == a ? 1.0f : 0.0f);
-      dl = dl * c;
-      prob[k] = dl; /* reuse as dlogits */
-      gbp[k] = gbp[k] + dl;
-    }
-    for (int jh = 0; jh < H; ++jh) {
-      float dh = 0.0f;
-      const float hj = h[jh];
-      for (int k = 0; k < A; ++k) {
-        const float dl = prob[k];
-        float t = dl * W[(size_t)k * H + jh];
-        dh = dh + t;
-        float u = dl * hj;
-        gW[(size_t)k * H + jh] = gW[(size_t)k * H + jh] + u;
-      }
-      if (hj > 0.0f) {
-        float t = dh * s;
-        gw1[jh] = gw1[jh] + t;
-        gb1[jh] = gb1[jh] + dh;
-      }
-    }
-  }
-  /* clip_grad_norm_(parameters, 1.0) (:191): lane-strided partial sums then lanes in order (mirrors the warp reduction) */
   double part[32];
   for (int l = 0; l < 32; ++l) part[l] = 0.0;
   for (int i = 0; i < P; ++i) part[i & 31] += (double)g[i] * (double)g[i];
@@ -267,7 +236,6 @@ static void mlp_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, in
   const float total_norm = (float)sqrt(tot);
   float coef = 1.0f / (total_norm + 1e-6f);
   if (coef > 1.0f) coef = 1.0f;
-  /* Adam (torch.optim.Adam defaults; agents.py:139), single-tensor formulas */
   const int step = hdr[0] + 1;
   hdr[0] = step;
   const double b1 = 0.9, b2 = 0.999;
@@ -296,6 +264,142 @@ static void mlp_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, in
     up = up / den;
     par[i] = par[i] + up; /* param.addcdiv_(exp_avg, denom, value = -step_size) */
   }
+}
+
+/* accumulate the gradient of one sample through fc_pi: dl[k] = d loss / d logits_k; adds into g and into dh[H] */
+static void mlp_back_pi(const float* par, int H, int A, const float* h, const float* dl, float* g, float* dh) {
+  const float* W = par + 2 * H;
+  float *gW = g + 2 * H, *gbp = g + 2 * H + (size_t)A * H;
+  for (int k = 0; k < A; ++k) gbp[k] = gbp[k] + dl[k];
+  for (int jh = 0; jh < H; ++jh) {
+    float acc = 0.0f;
+    const float hj = h[jh];
+    for (int k = 0; k < A; ++k) {
+      float t = dl[k] * W[(size_t)k * H + jh];
+      acc = acc + t;
+      float u = dl[k] * hj;
+      gW[(size_t)k * H + jh] = gW[(size_t)k * H + jh] + u;
+    }
+    dh[jh] = acc;
+  }
+}
+static void mlp_back_fc1(int H, const float* h, const float* dh, float s, float* g) {
+  float *gw1 = g, *gb1 = g + H;
+  for (int jh = 0; jh < H; ++jh) {
+    if (h[jh] > 0.0f) {
+      float t = dh[jh] * s;
+      gw1[jh] = gw1[jh] + t;
+      gb1[jh] = gb1[jh] + dh[jh];
+    }
+  }
+}
+
+/* Reinforce.train_net (agents.py:170-194) on the N buffered transitions buf[(head+j) % cap] = (state, action, reward),
+ * then clip_grad_norm_(1.0) and one Adam step.  blk = this agent's block of the MLP slab (include/thrl.h).
+ * scratch: P + 2H + A + N floats. */
+static void mlp_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, int N, float* scratch) {
+  const int H = sp->hidden, A = sp->actions;
+  const int P = mlp_P(sp), EW = mlp_entry_words(sp);
+  float* par = blk;
+  float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
+  float *g = scratch, *h = scratch + P, *dh = h + H, *prob = dh + H, *disc = prob + A;
+  for (int i = 0; i < P; ++i) g[i] = 0.0f;
+  /* discounted returns over the whole buffer, newest to oldest (:177-180), float32 */
+  const float gam = (float)sp->gamma;
+  for (int j = N - 1; j >= 0; --j) {
+    const float r = buf[(size_t)((head + j) % cap) * EW + 2];
+    if (j == N - 1) disc[j] = r;
+    else { float t = gam * disc[j + 1]; disc[j] = r + t; }
+    buf[(size_t)((head + j) % cap) * EW + 2] = disc[j]; /* kept in the (about to be emptied) buffer, as the device does */
+  }
+  /* (discounted - mean) / std, unbiased std (:181) */
+  double sum = 0.0;
+  for (int j = 0; j < N; ++j) sum += (double)disc[j];
+  const float mean = (float)(sum / (double)N);
+  double ss = 0.0;
+  for (int j = 0; j < N; ++j) { const double d = (double)disc[j] - (double)mean; ss += d * d; }
+  const float sd = (float)sqrt(ss / (double)(N - 1));
+  const float invN = 1.0f / (float)N;
+  /* loss = -mean(log_prob(a) * G) (:185); d loss / d logits_k = (p_k - [k == a]) * G / N, back through fc_pi, relu, fc1 */
+  for (int j = 0; j < N; ++j) {
+    const float* tr = buf + (size_t)((head + j) % cap) * EW;
+    const float s = tr[0];
+    int32_t a;
+    memcpy(&a, &tr[1], 4);
+    float G = disc[j] - mean;
+    G = G / sd;
+    const float c = G * invN;
+    mlp_forward(par, H, A, s, h, prob);
+    for (int k = 0; k < A; ++k) { float dl = prob[k] - (k == a ? 1.0f : 0.0f); prob[k] = dl * c; }
+    mlp_back_pi(par, H, A, h, prob, g, dh);
+    mlp_back_fc1(H, h, dh, s, g);
+  }
+  mlp_clip_adam(blk, sp, g);
+}
+
+/* ActorCritic.train_net (agents.py:280-305).  The reference's `rewards` is reshaped to [N] while v, v' stay [N,1], so
+ * advantage = rewards + gamma*v' - v broadcasts to [N,N]: adv[i][j] = r_j + d_i with d_i = gamma*v'(s'_i) - v(s_i); critic
+ * loss adv^2, actor loss -log_prob(a_j)*adv[i][j].detach(), loss = mean over the N^2 entries (entropy coefficient 0).
+ * The N^2 sums collapse:  dL/dd_i = 2 (R + N d_i) / N^2  (R = sum r_j; v' is NOT detached, so dL/dv'_i = gamma * that,
+ * dL/dv_i = - that), and dL/dlogits_jk = (p_jk - [k == a_j]) (N r_j + D) / N^2  (D = sum d_i). */
+static void ac_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, int N, float* scratch) {
+  const int H = sp->hidden, A = sp->actions;
+  const int P = mlp_P(sp), EW = mlp_entry_words(sp);
+  float* par = blk;
+  const float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
+  const float *wv = par + 2 * H + (size_t)A * H + A, bv = par[2 * H + (size_t)A * H + A + H];
+  float *g = scratch, *h = scratch + P, *dh = h + H, *prob = dh + H, *dval = prob + A;
+  float *gwv = g + 2 * H + (size_t)A * H + A, *gbv = gwv + H;
+  for (int i = 0; i < P; ++i) g[i] = 0.0f;
+  const float gam = (float)sp->gamma;
+  double R = 0.0, D = 0.0;
+  for (int i = 0; i < N; ++i) { /* d_i = gamma * v(s'_i) - v(s_i) (:289) */
+    const float* tr = buf + (size_t)((head + i) % cap) * EW;
+    mlp_hidden(par, H, tr[0], h);
+    const float v = ac_value(wv, bv, h, H);
+    mlp_hidden(par, H, tr[3], h);
+    const float vp = ac_value(wv, bv, h, H);
+    float t = gam * vp;
+    dval[i] = t - v;
+    R += (double)tr[2];
+    D += (double)dval[i];
+  }
+  const float fN = (float)N, fR = (float)R, fD = (float)D;
+  const float invN2 = 1.0f / (fN * fN);
+  for (int j = 0; j < N; ++j) {
+    const float* tr = buf + (size_t)((head + j) % cap) * EW;
+    const float s = tr[0], s2 = tr[3];
+    int32_t a;
+    memcpy(&a, &tr[1], 4);
+    float ca = fN * tr[2];
+    ca = ca + fD;
+    ca = ca * invN2; /* actor weight (N r_j + D) / N^2 */
+    float cv = fN * dval[j];
+    cv = fR + cv;
+    cv = cv * invN2;
+    cv = -2.0f * cv; /* dL/dv_j = -2 (R + N d_j) / N^2 */
+    const float cvp = (-gam) * cv; /* dL/dv'_j */
+    mlp_forward(par, H, A, s, h, prob);
+    for (int k = 0; k < A; ++k) { float dl = prob[k] - (k == a ? 1.0f : 0.0f); prob[k] = dl * ca; }
+    mlp_back_pi(par, H, A, h, prob, g, dh);
+    for (int jh = 0; jh < H; ++jh) { /* value head at s_j shares h with the policy head */
+      float t = cv * h[jh];
+      gwv[jh] = gwv[jh] + t;
+      float u = cv * wv[jh];
+      dh[jh] = dh[jh] + u;
+    }
+    gbv[0] = gbv[0] + cv;
+    mlp_back_fc1(H, h, dh, s, g);
+    mlp_hidden(par, H, s2, h); /* value head at s'_j */
+    for (int jh = 0; jh < H; ++jh) {
+      float t = cvp * h[jh];
+      gwv[jh] = gwv[jh] + t;
+      dh[jh] = cvp * wv[jh];
+    }
+    gbv[0] = gbv[0] + cvp;
+    mlp_back_fc1(H, h, dh, s2, g);
+  }
+  mlp_clip_adam(blk, sp, g);
 }
 
 typedef struct Transition { /* buffers.py Experience(state, action, reward, done, new_state); `done` is never read */
@@ -338,8 +442,8 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
     buf[i].item = NULL;
     if (s->kind != THRL_AGENT_QTABLE) {
       mlp_blk[i] = A->mlp + (size_t)r * G->mlp_stride + s->mlp_offset;
-      const size_t P = 2 * (size_t)s->hidden + (size_t)s->actions * s->hidden + s->actions;
-      const size_t need = 2 * P + s->hidden + s->actions + (size_t)G->mlp_buffer_len[i] + 8;
+      const size_t P = (size_t)mlp_P(s);
+      const size_t need = 2 * P + 2 * (size_t)s->hidden + s->actions + (size_t)G->mlp_buffer_len[i] + 8;
       if (need > mlp_scratch_n) mlp_scratch_n = need;
       buf[i].cap = buf[i].len = buf[i].head = 0;
       alpha[i] = gamma[i] = eps_end[i] = eps_step[i] = 0.0;
@@ -460,7 +564,8 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
           /* memory.append; replay(cast) turns state and reward into float32 (buffers.py:28-38, agents.py:142) */
           const int cap = G->mlp_buffer_len[i];
           if (cap > 0) {
-            const size_t P = 2 * (size_t)G->agent[i].hidden + (size_t)G->agent[i].actions * G->agent[i].hidden + G->agent[i].actions;
+            const size_t P = (size_t)mlp_P(&G->agent[i]);
+            const int EW = mlp_entry_words(&G->agent[i]);
             int32_t* hdr = (int32_t*)(mlp_blk[i] + 3 * P);
             float* mb = mlp_blk[i] + 3 * P + THRL_MLP_HEADER_WORDS;
             int len = hdr[1], head = hdr[2];
@@ -469,9 +574,10 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
             else { slot = head; head = (head + 1) % cap; }
             const float sf = (float)price, rf = (float)rew[i];
             const int32_t ai = act[i];
-            mb[(size_t)slot * 3] = sf;
-            memcpy(&mb[(size_t)slot * 3 + 1], &ai, 4);
-            mb[(size_t)slot * 3 + 2] = rf;
+            mb[(size_t)slot * EW] = sf;
+            memcpy(&mb[(size_t)slot * EW + 1], &ai, 4);
+            mb[(size_t)slot * EW + 2] = rf;
+            if (EW == 4) mb[(size_t)slot * EW + 3] = (float)next_price;
             hdr[1] = len; hdr[2] = head;
           }
           continue;
@@ -495,10 +601,11 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
       const ThrlAgentSpec* s = &G->agent[i];
       Buffer* b = &buf[i];
       if (s->kind != THRL_AGENT_QTABLE) {
-        const size_t P = 2 * (size_t)s->hidden + (size_t)s->actions * s->hidden + s->actions;
+        const size_t P = (size_t)mlp_P(s);
         int32_t* hdr = (int32_t*)(mlp_blk[i] + 3 * P);
-        if (G->mlp_buffer_len[i] > 0 && hdr[1] >= s->min_memory) { /* agents.py:171 */
-          mlp_train(mlp_blk[i], s, G->mlp_buffer_len[i], hdr[2], hdr[1], mlp_scratch);
+        if (G->mlp_buffer_len[i] > 0 && hdr[1] >= s->min_memory) { /* agents.py:171 / :281 */
+          if (s->kind == THRL_AGENT_ACTORCRITIC) ac_train(mlp_blk[i], s, G->mlp_buffer_len[i], hdr[2], hdr[1], mlp_scratch);
+          else mlp_train(mlp_blk[i], s, G->mlp_buffer_len[i], hdr[2], hdr[1], mlp_scratch);
           hdr[1] = 0; hdr[2] = 0; /* :194 memory.empty() */
         }
         continue;
@@ -606,8 +713,8 @@ int thrl_oracle_game_init(const ThrlGame* G, int64_t n_runs, int64_t run_id0, ui
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec* s = &G->agent[i];
       if (s->kind != THRL_AGENT_QTABLE) { /* nn.Linear default init, the rest of the block zero */
-        const int64_t Pn = 2 * (int64_t)s->hidden + (int64_t)s->actions * s->hidden + s->actions;
-        const int64_t words = 3 * Pn + THRL_MLP_HEADER_WORDS + 3 * (int64_t)G->mlp_buffer_len[i];
+        const int64_t Pn = mlp_P(s);
+        const int64_t words = 3 * Pn + THRL_MLP_HEADER_WORDS + (int64_t)mlp_entry_words(s) * G->mlp_buffer_len[i];
         float* blk = mlp + (size_t)r * G->mlp_stride + s->mlp_offset;
         const float b_fc1 = 1.0f, b_pi = (float)(1.0 / sqrt((double)s->hidden));
         for (int64_t w = 0; w < words; ++w) {
@@ -618,6 +725,7 @@ int thrl_oracle_game_init(const ThrlGame* G, int64_t n_runs, int64_t run_id0, ui
             const double u = (w & 1) ? u53(x[2], x[3]) : u53(x[0], x[1]);
             const float bound = (w < 2 * (int64_t)s->hidden) ? b_fc1 : b_pi;
             v = (float)(2.0 * u - 1.0) * bound;
+            if (s->kind == THRL_AGENT_ACTORCRITIC && w == Pn - 1) v = 1000.0f; /* fc_v.bias.data.fill_(1000.0), agents.py:244 */
           }
           blk[w] = v;
         }
@@ -696,13 +804,13 @@ int thrl_oracle_game_layout(ThrlGame* G) {
     const int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
     int64_t need = (int64_t)T * ((mm + T - 1) / T);
     if (need > s->capacity) need = s->capacity;
-    if (s->kind == THRL_AGENT_REINFORCE) {
+    if (s->kind == THRL_AGENT_REINFORCE || s->kind == THRL_AGENT_ACTORCRITIC) {
       if (s->states != 1 || s->hidden < 1 || s->entropy != 0.0) return THRL_ERR_BAD_CONFIG;
-      const int64_t P = 2 * (int64_t)s->hidden + (int64_t)s->actions * s->hidden + s->actions;
+      const int64_t P = mlp_P(s);
       G->mlp_buffer_len[i] = s->min_memory <= s->capacity ? (int32_t)need : 0;
       s->mlp_offset = moff;
       s->table_offset = 0;
-      moff += 3 * P + THRL_MLP_HEADER_WORDS + 3 * (int64_t)G->mlp_buffer_len[i];
+      moff += 3 * P + THRL_MLP_HEADER_WORDS + (int64_t)mlp_entry_words(s) * G->mlp_buffer_len[i];
       continue;
     }
     if (s->kind != THRL_AGENT_QTABLE || s->states < 1) return THRL_ERR_BAD_CONFIG;

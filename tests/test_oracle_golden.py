@@ -21,7 +21,7 @@ def golden_inputs(g, game, rng_mode, dtype):
     q0 = oracle.pack_tables(game, [None if is_mlp(cfg, i) else g["q0_%d" % i] for i in range(n)], dtype)
     mlp0 = None
     if game.mlp_stride:
-        mlp0 = oracle.pack_mlp(game, [{k: g["mlp0_%d_%s" % (i, k)] for k in ("fc1.weight", "fc1.bias", "fc_pi.weight", "fc_pi.bias")}
+        mlp0 = oracle.pack_mlp(game, [{k: g["mlp0_%d_%s" % (i, k)] for k in abi.mlp_param_names(game.agent[i])}
                                       if is_mlp(cfg, i) else None for i in range(n)])
     ra = (g["ra"] if rng_mode == abi.THRL_RNG_REPLAY_DRAWS else g["actions"]).copy()
     for i in range(n):
@@ -43,6 +43,7 @@ def run_oracle(g, rng_mode, dtype=np.float64):
 
 
 MLP_ATOL = 1e-7  # |weight - torch's weight| after the recorded updates (two to four Adam steps of 2e-4 each); measured <= 1.5e-8
+MLP_RTOL = 2e-7  # relative part: ActorCritic's fc_v.bias sits at 1000 (agents.py:244), one float32 ulp there is 6e-5
 
 
 def check_mlp(g, game, res):
@@ -54,8 +55,8 @@ def check_mlp(g, game, res):
         for k, v in got[i].items():
             ref0, ref = g["mlp0_%d_%s" % (i, k)], g["mlp_final_%d_%s" % (i, k)]
             assert np.abs(ref - ref0).max() > 1e-4, "the golden run must contain at least one update"
-            err = np.abs(v.reshape(ref.shape) - ref).max()
-            assert err < MLP_ATOL, (i, k, err)
+            err = np.abs(v.reshape(ref.shape) - ref)
+            assert np.all(err <= MLP_ATOL + MLP_RTOL * np.abs(ref)), (i, k, float(err.max()))
 
 
 def check_bit_exact(g, game, res):

@@ -25,6 +25,7 @@ THRL_F64 = 1
 
 THRL_AGENT_QTABLE = 0
 THRL_AGENT_REINFORCE = 1
+THRL_AGENT_ACTORCRITIC = 2
 THRL_MLP_HEADER_WORDS = 4
 
 THRL_RNG_PHILOX = 0
@@ -106,6 +107,9 @@ QTABLE_DEFAULTS = dict(states=16, actions=4, action_range=[0, 1], gamma=0.99, bu
 # Reinforce.__init__ defaults (th_rl/agents.py:120-131)
 REINFORCE_DEFAULTS = dict(states=4, actions=2, action_range=[0, 1], gamma=0.98, buffer="ReplayBuffer", capacity=50000,
                           min_memory=1000, entropy=0)
+# ActorCritic.__init__ defaults (th_rl/agents.py:223-234)
+ACTORCRITIC_DEFAULTS = dict(states=4, actions=2, action_range=[0, 1], gamma=0.98, buffer="ReplayBuffer", capacity=50000,
+                            min_memory=1000, entropy=0)
 # NoisyPriceState.__init__ defaults (th_rl/environments.py:5)
 ENV_DEFAULTS = dict(action_range=[0, 1], a=10, b=1, max_steps=1, noise_prob=0.05)
 
@@ -133,10 +137,10 @@ def game_from_config(config):
     for i, ad in enumerate(agents):
         name = ad.get("name", "QTable")
         s = g.agent[i]
-        if name == "Reinforce":
-            d = dict(REINFORCE_DEFAULTS)
+        if name in ("Reinforce", "ActorCritic"):
+            d = dict(REINFORCE_DEFAULTS if name == "Reinforce" else ACTORCRITIC_DEFAULTS)
             d.update(ad)
-            s.kind = THRL_AGENT_REINFORCE
+            s.kind = THRL_AGENT_REINFORCE if name == "Reinforce" else THRL_AGENT_ACTORCRITIC
             s.states, s.actions = int(d["states"]), int(d["actions"])
             s.min_memory, s.capacity = int(d["min_memory"]), int(d["capacity"])
             s.action_lo, s.action_hi = float(d["action_range"][0]), float(d["action_range"][1])
@@ -146,7 +150,7 @@ def game_from_config(config):
             continue
         if name != "QTable":
             raise NotImplementedError(
-                "agent %d is %r: the B200 hot path covers QTable and Reinforce agents (DESIGN.md: ActorCritic / CAC are next)"
+                "agent %d is %r: the B200 hot path covers QTable, Reinforce and ActorCritic agents (DESIGN.md: CAC is next)"
                 % (i, name))
         d = dict(QTABLE_DEFAULTS)
         d.update(ad)
@@ -170,4 +174,22 @@ def eps0_from_config(config):
 
 
 def mlp_param_count(spec):
-    return 2 * spec.hidden + spec.actions * spec.hidden + spec.actions
+    p = 2 * spec.hidden + spec.actions * spec.hidden + spec.actions
+    return p + spec.hidden + 1 if spec.kind == THRL_AGENT_ACTORCRITIC else p
+
+
+def mlp_entry_words(spec):
+    return 4 if spec.kind == THRL_AGENT_ACTORCRITIC else 3
+
+
+def mlp_param_names(spec):
+    names = ["fc1.weight", "fc1.bias", "fc_pi.weight", "fc_pi.bias"]
+    return names + ["fc_v.weight", "fc_v.bias"] if spec.kind == THRL_AGENT_ACTORCRITIC else names
+
+
+def mlp_param_shapes(spec):
+    H, A = spec.hidden, spec.actions
+    sh = {"fc1.weight": (H, 1), "fc1.bias": (H,), "fc_pi.weight": (A, H), "fc_pi.bias": (A,)}
+    if spec.kind == THRL_AGENT_ACTORCRITIC:
+        sh.update({"fc_v.weight": (1, H), "fc_v.bias": (1,)})
+    return sh

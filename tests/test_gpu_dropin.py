@@ -38,7 +38,8 @@ def test_train_one_reproduces_reference_files(golden, tmp_path):
                 assert c.sum() == golden["counter_final_%d" % i].sum()
             else:
                 sd = torch.load(out / str(i))
-                assert list(sd) == ["fc1.weight", "fc1.bias", "fc_pi.weight", "fc_pi.bias"]
+                want = ["fc1.weight", "fc1.bias", "fc_pi.weight", "fc_pi.bias"] + (["fc_v.weight", "fc_v.bias"] if a["name"] == "ActorCritic" else [])
+                assert list(sd) == want
                 for k, v in sd.items():
                     ref0 = golden["mlp0_%d_%s" % (i, k)]
                     assert v.dtype == torch.float32 and tuple(v.shape) == ref0.shape

@@ -71,10 +71,15 @@ def test_layout_matches_oracle_and_validates():
     bad["environment"]["nplayers"] = 3  # trainer.py:21-23
     with pytest.raises(AssertionError):
         _lib.game_layout(bad)
-    ac = _cfg()
-    ac["agents"][1]["name"] = "ActorCritic"  # only QTable and Reinforce agents are implemented
+    cac = _cfg()
+    cac["agents"][1]["name"] = "CAC"  # QTable, Reinforce and ActorCritic agents are implemented; CAC is not
     with pytest.raises(NotImplementedError):
-        _lib.game_layout(ac)
+        _lib.game_layout(cac)
+    ac = _cfg()
+    ac["agents"][1] = dict(name="ActorCritic", gamma=0.98, actions=21, states=1, action_range=[0.2, 0.4], min_memory=200)
+    g, o = _lib.game_layout(ac), oracle.layout(ac)
+    Pac = 2 * 256 + 21 * 256 + 21 + 256 + 1
+    assert g.mlp_stride == 3 * Pac + 4 + 4 * 200 == o.mlp_stride and g.agent[1].kind == abi.THRL_AGENT_ACTORCRITIC
     # the shipped example_config.json pairing: QTable + Reinforce (MLP 1 -> 256 -> 21)
     mixed = _cfg()
     mixed["agents"][1] = dict(name="Reinforce", gamma=0.995, actions=21, states=1, action_range=[0.2, 0.4])

@@ -119,4 +119,36 @@ class Reinforce:
         self.load_state_dict(torch.load(loc))
 
 
-AGENTS = {"QTable": QTable, "Reinforce": Reinforce}
+class ActorCritic(Reinforce):
+    """Host-side mirror of th_rl/agents.py:222-330: Reinforce's network plus the value head fc_v (bias filled with 1000.0,
+    agents.py:244).  Constructed in the reference's order (fc1, fc_pi, fc_v) so seeded torch gives the same initial weights."""
+
+    def __init__(self, states=4, actions=2, action_range=[0, 1], gamma=0.98, buffer="ReplayBuffer", capacity=50000,
+                 min_memory=1000, entropy=0, **kwargs):
+        import torch.nn as nn
+        super().__init__(states=states, actions=actions, action_range=action_range, gamma=gamma, buffer=buffer,
+                         capacity=capacity, min_memory=min_memory, entropy=entropy)
+        self.fc_v = nn.Linear(256, 1)           # agents.py:243
+        self.fc_v.bias.data.fill_(1000.0)       # agents.py:244
+
+    def state_dict(self):
+        sd = super().state_dict()
+        sd["fc_v.weight"] = self.fc_v.weight.detach().clone()
+        sd["fc_v.bias"] = self.fc_v.bias.detach().clone()
+        return sd
+
+    def load_state_dict(self, sd):
+        import torch
+        super().load_state_dict(sd)
+        with torch.no_grad():
+            self.fc_v.weight.copy_(torch.as_tensor(sd["fc_v.weight"]).reshape(self.fc_v.weight.shape))
+            self.fc_v.bias.copy_(torch.as_tensor(sd["fc_v.bias"]).reshape(self.fc_v.bias.shape))
+
+    def sample_action(self, state):
+        raise NotImplementedError(_FUSED % "ActorCritic.sample_action")
+
+    def train_net(self):
+        raise NotImplementedError(_FUSED % "ActorCritic.train_net")
+
+
+AGENTS = {"QTable": QTable, "Reinforce": Reinforce, "ActorCritic": ActorCritic}

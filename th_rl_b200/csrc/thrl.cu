@@ -72,15 +72,16 @@ int validate_layout(ThrlGame* G) {
     const int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
     long long need = (long long)T * ((mm + T - 1) / T);
     if (need > s->capacity) need = s->capacity;
-    if (s->kind == THRL_AGENT_REINFORCE) {
-      if (s->states != 1) return fail(THRL_ERR_BAD_CONFIG, "agent %d: Reinforce.states=%d, the environment's state is one number", i, s->states);
+    if (s->kind == THRL_AGENT_REINFORCE || s->kind == THRL_AGENT_ACTORCRITIC) {
+      if (s->states != 1) return fail(THRL_ERR_BAD_CONFIG, "agent %d: states=%d for an MLP agent, the environment's state is one number", i, s->states);
       if (s->hidden < 1 || s->hidden > 1024) return fail(THRL_ERR_BAD_CONFIG, "agent %d: hidden=%d outside 1..1024", i, s->hidden);
       if (s->entropy != 0.0) return fail(THRL_ERR_UNSUPPORTED, "agent %d: entropy coefficient %g (only the reference default 0 is implemented)", i, s->entropy);
-      const long long P = 2LL * s->hidden + (long long)s->actions * s->hidden + s->actions;
+      const bool ac = s->kind == THRL_AGENT_ACTORCRITIC;
+      const long long P = 2LL * s->hidden + (long long)s->actions * s->hidden + s->actions + (ac ? s->hidden + 1 : 0);
       G->mlp_buffer_len[i] = s->min_memory <= s->capacity ? (int32_t)need : 0;
       s->mlp_offset = moff;
       s->table_offset = 0;
-      moff += 3 * P + THRL_MLP_HEADER_WORDS + 3LL * G->mlp_buffer_len[i];
+      moff += 3 * P + THRL_MLP_HEADER_WORDS + (ac ? 4LL : 3LL) * G->mlp_buffer_len[i];
       continue;
     }
     if (s->kind != THRL_AGENT_QTABLE) return fail(THRL_ERR_BAD_CONFIG, "agent %d: unknown kind %d", i, s->kind);
@@ -374,7 +375,7 @@ int launch_mixed(thrl::MixedParams& p, const DeviceInfo& dev, cudaStream_t strea
     lut += s.actions;
     p.par_off[i] = 0;
     if (s.kind == THRL_AGENT_QTABLE) continue;
-    const int P = 2 * s.hidden + s.actions * s.hidden + s.actions;
+    const int P = 2 * s.hidden + s.actions * s.hidden + s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? s.hidden + 1 : 0);
     p.par_off[i] = par;
     par += align_up(P, 4);
     if (P > pmax) pmax = P;
@@ -544,7 +545,7 @@ int thrl_game_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64
   long long max_cells = 0;
   for (int i = 0; i < p.game.n_agents; ++i) {
     const ThrlAgentSpec& sa = p.game.agent[i];
-    const long long c = sa.kind == THRL_AGENT_QTABLE ? (long long)(sa.states + 1) * sa.actions : 2 * (3LL * (2 * sa.hidden + sa.actions * sa.hidden + sa.actions) + 4 + 3LL * p.game.mlp_buffer_len[i]);
+    const long long c = sa.kind == THRL_AGENT_QTABLE ? (long long)(sa.states + 1) * sa.actions : 2 * (3LL * (3 * sa.hidden + sa.actions * sa.hidden + sa.actions + 1) + 4 + 4LL * p.game.mlp_buffer_len[i]);
     if (c > max_cells) max_cells = c;
   }
   dim3 grid((unsigned)((max_cells / 2 + 255) / 256), (unsigned)(n_runs < 65535 ? n_runs : 65535));

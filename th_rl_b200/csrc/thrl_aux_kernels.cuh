@@ -65,8 +65,9 @@ __global__ void __launch_bounds__(256) qtable_init(const __grid_constant__ InitP
       if (s.kind != THRL_AGENT_QTABLE) {
         // nn.Linear default init (kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias,
         // agents.py:137-138); Adam state, header and transition buffer zeroed
-        const long long Pn = 2LL * s.hidden + (long long)s.actions * s.hidden + s.actions;
-        const long long words = 3 * Pn + THRL_MLP_HEADER_WORDS + 3LL * G.mlp_buffer_len[i];
+        const bool ac = s.kind == THRL_AGENT_ACTORCRITIC;
+        const long long Pn = 2LL * s.hidden + (long long)s.actions * s.hidden + s.actions + (ac ? s.hidden + 1 : 0);
+        const long long words = 3 * Pn + THRL_MLP_HEADER_WORDS + (ac ? 4LL : 3LL) * G.mlp_buffer_len[i];
         float* blk = p.mlp + r * G.mlp_stride + s.mlp_offset;
         const float b_fc1 = 1.0f, b_pi = (float)__ddiv_rn(1.0, sqrt((double)s.hidden));
         for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (long long)gridDim.x * blockDim.x) {
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) qtable_init(const __grid_constant__ InitP
             const double u = (w & 1) ? u53(x[2], x[3]) : u53(x[0], x[1]);
             const float bound = (w < 2LL * s.hidden) ? b_fc1 : b_pi;
             v = __fmul_rn((float)__dsub_rn(__dmul_rn(2.0, u), 1.0), bound);
+            if (ac && w == Pn - 1) v = 1000.0f;  // fc_v.bias.data.fill_(1000.0), agents.py:244
           }
           blk[w] = v;
         }

@@ -1,5 +1,5 @@
-// thrl_scan_mixed.cuh — games that contain Reinforce (MLP policy-gradient) agents next to QTable agents
-// (th_rl/agents.py:119-194; both configs the reference ships pair a QTable with a Reinforce agent).
+// thrl_scan_mixed.cuh — games that contain MLP agents (Reinforce, th_rl/agents.py:119-194; ActorCritic, :222-305) next to
+// QTable agents (both configs the reference ships pair a QTable with a Reinforce agent).
 //
 // Correctness-first tier: one warp plays one run; QTable tables stay in HBM and are addressed directly (no greedy cache);
 // every MLP agent's parameters are staged in shared memory (fc_pi.weight transposed to [hidden][actions] so that both the
@@ -42,6 +42,12 @@ struct MixedParams {
   int par_off[THRL_MAX_AGENTS];  // float offset of MLP agent i's staged parameters inside off_par
   int lut_total, Hp, noisy;
 };
+
+__device__ __forceinline__ int mlp_P(const ThrlAgentSpec& s) {
+  const int p = 2 * s.hidden + s.actions * s.hidden + s.actions;
+  return s.kind == THRL_AGENT_ACTORCRITIC ? p + s.hidden + 1 : p;
+}
+__device__ __forceinline__ int mlp_entry_words(const ThrlAgentSpec& s) { return s.kind == THRL_AGENT_ACTORCRITIC ? 4 : 3; }
 
 // expf with the oracle's operation sequence (Cody-Waite + Cephes polynomial)
 __device__ __forceinline__ float det_expf(float x) {
@@ -93,15 +99,74 @@ __device__ __forceinline__ void mlp_forward_warp(const float* sp, int H, int A, 
   __syncwarp();
 }
 
-// Reinforce.train_net + clip_grad_norm_ + Adam (agents.py:170-194) for one agent of one run; mirrors oracle mlp_train.
+// h = relu(fc1(x)) into shared memory
+__device__ __forceinline__ void mlp_hidden_warp(const float* sp, int H, float s, float* hs, int lane) {
+  const float *w1 = sp, *b1 = sp + H;
+  __syncwarp();
+  for (int j = lane; j < H; j += 32) {
+    const float v = __fadd_rn(__fmul_rn(s, w1[j]), b1[j]);
+    hs[j] = v > 0.0f ? v : 0.0f;
+  }
+  __syncwarp();
+}
+// v(x) (agents.py:259-262) from h in shared memory: lane-strided partial dot products, xor-butterfly sum, + bias (oracle ac_value)
+__device__ __forceinline__ float ac_value_warp(const float* wv, float bv, const float* hs, int H, int lane) {
+  float part = 0.0f;
+  for (int j = lane; j < H; j += 32) part = __fadd_rn(part, __fmul_rn(hs[j], wv[j]));
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) part = __fadd_rn(part, __shfl_xor_sync(kFull, part, off));
+  return __fadd_rn(part, bv);
+}
+
+// clip_grad_norm_(1.0) + one Adam step (oracle mlp_clip_adam).  gs: gradient in the staged layout.
+__device__ inline void mlp_clip_adam_warp(float* blk, const ThrlAgentSpec& spec, float* sp, const float* gs, int lane) {
+  const int H = spec.hidden, A = spec.actions;
+  const int P = mlp_P(spec);
+  float *am = blk + P, *av = blk + 2 * (size_t)P;
+  int32_t* hdr = reinterpret_cast<int32_t*>(blk + 3 * (size_t)P);
+  // Flat index i runs over the state_dict order as in the oracle; flat2st maps it to the staged layout (fc_pi.weight transposed)
+  auto flat2st = [&](int i) {
+    if (i < 2 * H || i >= 2 * H + A * H) return i;
+    const int e = i - 2 * H, k = e / H, j = e - k * H;
+    return 2 * H + j * A + k;
+  };
+  __syncwarp();
+  double part = 0.0;
+  for (int i = lane; i < P; i += 32) { const double gd = (double)gs[flat2st(i)]; part = __dadd_rn(part, __dmul_rn(gd, gd)); }
+  double tot = 0.0;
+  for (int l = 0; l < 32; ++l) tot = __dadd_rn(tot, shfl_d(part, l));
+  const float total_norm = (float)sqrt(tot);
+  float coef = __fdiv_rn(1.0f, __fadd_rn(total_norm, 1e-6f));
+  if (coef > 1.0f) coef = 1.0f;
+  const int step = hdr[0] + 1;
+  double pw1 = 1.0, pw2 = 1.0;
+  for (int q2 = 0; q2 < step; ++q2) { pw1 = __dmul_rn(pw1, 0.9); pw2 = __dmul_rn(pw2, 0.999); }
+  const double bc1 = __dsub_rn(1.0, pw1), bc2 = __dsub_rn(1.0, pw2);
+  const float neg_step_size = (float)(-__ddiv_rn(spec.lr, bc1));
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float w1m = (float)__dsub_rn(1.0, 0.9), fb2 = (float)0.999, w2 = (float)__dsub_rn(1.0, 0.999), eps = 1e-8f;
+  for (int i = lane; i < P; i += 32) {
+    const int st = flat2st(i);
+    const float gi = __fmul_rn(gs[st], coef);
+    float m = am[i], v = av[i];
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(gi, m), w1m));
+    v = __fadd_rn(__fmul_rn(v, fb2), __fmul_rn(__fmul_rn(w2, gi), gi));
+    am[i] = m;
+    av[i] = v;
+    const float den = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps);
+    sp[st] = __fadd_rn(sp[st], __fdiv_rn(__fmul_rn(neg_step_size, m), den));
+  }
+  __syncwarp();
+  if (lane == 0) hdr[0] = step;
+}
+
+// Reinforce.train_net (agents.py:170-194) for one agent of one run; mirrors oracle mlp_train.
 // blk: the agent's block in the global MLP slab; sp: staged parameters (updated in place); gs: gradient scratch [P] in the
 // same staged layout; hs/ps: [H] / [A + 32] scratch.
 __device__ inline void mlp_train_warp(float* blk, const ThrlAgentSpec& spec, int cap, int head, int N, float* sp, float* gs,
                                       float* hs, float* ps, int lane) {
   const int H = spec.hidden, A = spec.actions;
-  const int P = 2 * H + A * H + A;
-  float *am = blk + P, *av = blk + 2 * (size_t)P;
-  int32_t* hdr = reinterpret_cast<int32_t*>(blk + 3 * (size_t)P);
+  const int P = mlp_P(spec), EW = mlp_entry_words(spec);
   float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
   float *gw1 = gs, *gb1 = gs + H, *gWT = gs + 2 * H, *gbp = gs + 2 * H + H * A;
   const float* WT = sp + 2 * H;
@@ -114,18 +179,18 @@ __device__ inline void mlp_train_warp(float* blk, const ThrlAgentSpec& spec, int
     for (int j = N - 1; j >= 0; --j) {
       int sl = head + j;
       if (sl >= cap) sl -= cap;
-      const float r = buf[(size_t)sl * 3 + 2];
+      const float r = buf[(size_t)sl * EW + 2];
       const float d = j == N - 1 ? r : __fadd_rn(r, __fmul_rn(gam, nxt));
-      buf[(size_t)sl * 3 + 2] = d;
+      buf[(size_t)sl * EW + 2] = d;
       nxt = d;
     }
     double sum = 0.0;
-    for (int j = 0; j < N; ++j) { int sl = head + j; if (sl >= cap) sl -= cap; sum = __dadd_rn(sum, (double)buf[(size_t)sl * 3 + 2]); }
+    for (int j = 0; j < N; ++j) { int sl = head + j; if (sl >= cap) sl -= cap; sum = __dadd_rn(sum, (double)buf[(size_t)sl * EW + 2]); }
     mean = (float)__ddiv_rn(sum, (double)N);
     double ss = 0.0;
     for (int j = 0; j < N; ++j) {
       int sl = head + j; if (sl >= cap) sl -= cap;
-      const double d = __dsub_rn((double)buf[(size_t)sl * 3 + 2], (double)mean);
+      const double d = __dsub_rn((double)buf[(size_t)sl * EW + 2], (double)mean);
       ss = __dadd_rn(ss, __dmul_rn(d, d));
     }
     sd = (float)sqrt(__ddiv_rn(ss, (double)(N - 1)));
@@ -137,9 +202,9 @@ __device__ inline void mlp_train_warp(float* blk, const ThrlAgentSpec& spec, int
   for (int j = 0; j < N; ++j) {
     int sl = head + j;
     if (sl >= cap) sl -= cap;
-    const float s = buf[(size_t)sl * 3];
-    const int a = __float_as_int(buf[(size_t)sl * 3 + 1]);
-    const float G = __fdiv_rn(__fsub_rn(buf[(size_t)sl * 3 + 2], mean), sd);
+    const float s = buf[(size_t)sl * EW];
+    const int a = __float_as_int(buf[(size_t)sl * EW + 1]);
+    const float G = __fdiv_rn(__fsub_rn(buf[(size_t)sl * EW + 2], mean), sd);
     const float c = __fmul_rn(G, invN);
     mlp_forward_warp(sp, H, A, s, hs, ps, lane);
     for (int k = lane; k < A; k += 32) {  // d loss / d logits (:185)
@@ -163,41 +228,83 @@ __device__ inline void mlp_train_warp(float* blk, const ThrlAgentSpec& spec, int
     }
     __syncwarp();
   }
-  // clip_grad_norm_(1.0) (:191).  Flat index i runs over the state_dict order (w1, b1, W[A][H], bp) as in the oracle;
-  // flat2st maps it to the staged (transposed) layout.
-  auto flat2st = [&](int i) {
-    if (i < 2 * H || i >= 2 * H + A * H) return i;
-    const int e = i - 2 * H, k = e / H, j = e - k * H;
-    return 2 * H + j * A + k;
-  };
-  double part = 0.0;
-  for (int i = lane; i < P; i += 32) { const double gd = (double)gs[flat2st(i)]; part = __dadd_rn(part, __dmul_rn(gd, gd)); }
-  double tot = 0.0;
-  for (int l = 0; l < 32; ++l) tot = __dadd_rn(tot, shfl_d(part, l));
-  const float total_norm = (float)sqrt(tot);
-  float coef = __fdiv_rn(1.0f, __fadd_rn(total_norm, 1e-6f));
-  if (coef > 1.0f) coef = 1.0f;
-  // Adam (torch.optim.Adam defaults, agents.py:139)
-  const int step = hdr[0] + 1;
-  double pw1 = 1.0, pw2 = 1.0;
-  for (int q2 = 0; q2 < step; ++q2) { pw1 = __dmul_rn(pw1, 0.9); pw2 = __dmul_rn(pw2, 0.999); }
-  const double bc1 = __dsub_rn(1.0, pw1), bc2 = __dsub_rn(1.0, pw2);
-  const float neg_step_size = (float)(-__ddiv_rn(spec.lr, bc1));
-  const float bc2_sqrt = (float)sqrt(bc2);
-  const float w1m = (float)__dsub_rn(1.0, 0.9), fb2 = (float)0.999, w2 = (float)__dsub_rn(1.0, 0.999), eps = 1e-8f;
-  for (int i = lane; i < P; i += 32) {
-    const int st = flat2st(i);
-    const float gi = __fmul_rn(gs[st], coef);
-    float m = am[i], v = av[i];
-    m = __fadd_rn(m, __fmul_rn(__fsub_rn(gi, m), w1m));
-    v = __fadd_rn(__fmul_rn(v, fb2), __fmul_rn(__fmul_rn(w2, gi), gi));
-    am[i] = m;
-    av[i] = v;
-    const float den = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps);
-    sp[st] = __fadd_rn(sp[st], __fdiv_rn(__fmul_rn(neg_step_size, m), den));
+  mlp_clip_adam_warp(blk, spec, sp, gs, lane);
+}
+
+// ActorCritic.train_net (agents.py:280-305); the [N,N] advantage broadcast collapsed to O(N) sums, see oracle ac_train.
+__device__ inline void ac_train_warp(float* blk, const ThrlAgentSpec& spec, int cap, int head, int N, float* sp, float* gs,
+                                     float* hs, float* ps, int lane) {
+  const int H = spec.hidden, A = spec.actions;
+  const int P = mlp_P(spec), EW = mlp_entry_words(spec);
+  const float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
+  float *gw1 = gs, *gb1 = gs + H, *gWT = gs + 2 * H, *gbp = gs + 2 * H + H * A, *gwv = gbp + A, *gbv = gwv + H;
+  const float *WT = sp + 2 * H, *wv = sp + 2 * H + H * A + A;
+  const float bv = sp[2 * H + H * A + A + H];
+  for (int i = lane; i < P; i += 32) gs[i] = 0.0f;
+  const float gam = (float)spec.gamma;
+  double R = 0.0, D = 0.0;  // every lane accumulates the same (warp-uniform) values in the same order
+  for (int i = 0; i < N; ++i) {  // d_i = gamma * v(s'_i) - v(s_i) (:289)
+    int sl = head + i;
+    if (sl >= cap) sl -= cap;
+    mlp_hidden_warp(sp, H, buf[(size_t)sl * EW], hs, lane);
+    const float v = ac_value_warp(wv, bv, hs, H, lane);
+    mlp_hidden_warp(sp, H, buf[(size_t)sl * EW + 3], hs, lane);
+    const float vp = ac_value_warp(wv, bv, hs, H, lane);
+    const float d = __fsub_rn(__fmul_rn(gam, vp), v);
+    R = __dadd_rn(R, (double)buf[(size_t)sl * EW + 2]);
+    D = __dadd_rn(D, (double)d);
   }
-  __syncwarp();
-  if (lane == 0) hdr[0] = step;
+  const float fN = (float)N, fR = (float)R, fD = (float)D;
+  const float invN2 = __fdiv_rn(1.0f, __fmul_rn(fN, fN));
+  for (int j = 0; j < N; ++j) {
+    int sl = head + j;
+    if (sl >= cap) sl -= cap;
+    const float s = buf[(size_t)sl * EW], r = buf[(size_t)sl * EW + 2], s2 = buf[(size_t)sl * EW + 3];
+    const int a = __float_as_int(buf[(size_t)sl * EW + 1]);
+    mlp_hidden_warp(sp, H, s2, hs, lane);
+    const float vp = ac_value_warp(wv, bv, hs, H, lane);
+    mlp_forward_warp(sp, H, A, s, hs, ps, lane);  // leaves h(s) in hs, pi(s) in ps
+    const float v = ac_value_warp(wv, bv, hs, H, lane);
+    const float d = __fsub_rn(__fmul_rn(gam, vp), v);
+    const float ca = __fmul_rn(__fadd_rn(__fmul_rn(fN, r), fD), invN2);                        // actor weight (N r_j + D) / N^2
+    const float cv = __fmul_rn(-2.0f, __fmul_rn(__fadd_rn(fR, __fmul_rn(fN, d)), invN2));      // dL/dv_j
+    const float cvp = __fmul_rn(-gam, cv);                                                     // dL/dv'_j
+    for (int k = lane; k < A; k += 32) {
+      const float dl = __fmul_rn(__fsub_rn(ps[k], k == a ? 1.0f : 0.0f), ca);
+      ps[k] = dl;
+      gbp[k] = __fadd_rn(gbp[k], dl);
+    }
+    __syncwarp();
+    for (int jh = lane; jh < H; jh += 32) {
+      float dh = 0.0f;
+      const float hj = hs[jh];
+      for (int k = 0; k < A; ++k) {
+        const float dl = ps[k];
+        dh = __fadd_rn(dh, __fmul_rn(dl, WT[jh * A + k]));
+        gWT[jh * A + k] = __fadd_rn(gWT[jh * A + k], __fmul_rn(dl, hj));
+      }
+      gwv[jh] = __fadd_rn(gwv[jh], __fmul_rn(cv, hj));  // value head at s_j shares h with the policy head
+      dh = __fadd_rn(dh, __fmul_rn(cv, wv[jh]));
+      if (hj > 0.0f) {
+        gw1[jh] = __fadd_rn(gw1[jh], __fmul_rn(dh, s));
+        gb1[jh] = __fadd_rn(gb1[jh], dh);
+      }
+    }
+    if (lane == 0) gbv[0] = __fadd_rn(gbv[0], cv);
+    mlp_hidden_warp(sp, H, s2, hs, lane);  // value head at s'_j
+    for (int jh = lane; jh < H; jh += 32) {
+      const float hj = hs[jh];
+      gwv[jh] = __fadd_rn(gwv[jh], __fmul_rn(cvp, hj));
+      const float dh = __fmul_rn(cvp, wv[jh]);
+      if (hj > 0.0f) {
+        gw1[jh] = __fadd_rn(gw1[jh], __fmul_rn(dh, s2));
+        gb1[jh] = __fadd_rn(gb1[jh], dh);
+      }
+    }
+    if (lane == 0) gbv[0] = __fadd_rn(gbv[0], cvp);
+    __syncwarp();
+  }
+  mlp_clip_adam_warp(blk, spec, sp, gs, lane);
 }
 
 template <typename QT>
@@ -275,7 +382,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
       if (s.kind == THRL_AGENT_QTABLE) continue;
-      const int H = s.hidden, A = s.actions, Pn = 2 * H + A * H + A;
+      const int H = s.hidden, A = s.actions, Pn = mlp_P(s);
       const float* src = slab + s.mlp_offset;
       float* dst = par + p.par_off[i];
       for (int e2 = lane; e2 < Pn; e2 += 32) {
@@ -400,16 +507,17 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
             const ThrlAgentSpec& s = G.agent[lane];
             const int cap = G.mlp_buffer_len[lane];
             if (cap > 0) {
-              const int Pn = 2 * s.hidden + s.actions * s.hidden + s.actions;
+              const int Pn = mlp_P(s), EW = mlp_entry_words(s);
               float* blk = slab + s.mlp_offset;
               int32_t* hdr = reinterpret_cast<int32_t*>(blk + 3 * (size_t)Pn);
               float* mb = blk + 3 * (size_t)Pn + THRL_MLP_HEADER_WORDS;
               int len = hdr[1], head = hdr[2], sl;
               if (len < cap) { sl = head + len; if (sl >= cap) sl -= cap; len++; }
               else { sl = head; head = head + 1 == cap ? 0 : head + 1; }
-              mb[(size_t)sl * 3] = (float)price;
-              mb[(size_t)sl * 3 + 1] = __int_as_float(k);
-              mb[(size_t)sl * 3 + 2] = (float)rew;
+              mb[(size_t)sl * EW] = (float)price;
+              mb[(size_t)sl * EW + 1] = __int_as_float(k);
+              mb[(size_t)sl * EW + 2] = (float)rew;
+              if (EW == 4) mb[(size_t)sl * EW + 3] = (float)next_price;
               hdr[1] = len; hdr[2] = head;
             }
           }
@@ -431,12 +539,13 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
         if (s.kind != THRL_AGENT_QTABLE) {  // Reinforce.train_net (agents.py:170-194)
           const int cap = G.mlp_buffer_len[i];
           if (cap == 0) continue;
-          const int Pn = 2 * s.hidden + s.actions * s.hidden + s.actions;
+          const int Pn = mlp_P(s);
           float* blk = slab + s.mlp_offset;
           int32_t* hdr = reinterpret_cast<int32_t*>(blk + 3 * (size_t)Pn);
           const int len = hdr[1], head = hdr[2];
           if (len >= s.min_memory) {
-            mlp_train_warp(blk, s, cap, head, len, par + p.par_off[i], grad, hs, ps, lane);
+            if (s.kind == THRL_AGENT_ACTORCRITIC) ac_train_warp(blk, s, cap, head, len, par + p.par_off[i], grad, hs, ps, lane);
+            else mlp_train_warp(blk, s, cap, head, len, par + p.par_off[i], grad, hs, ps, lane);
             if (lane == 0) { hdr[1] = 0; hdr[2] = 0; }  // :194 memory.empty()
             __syncwarp();
           }
@@ -506,7 +615,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
       if (s.kind == THRL_AGENT_QTABLE) continue;
-      const int H = s.hidden, A = s.actions, Pn = 2 * H + A * H + A;
+      const int H = s.hidden, A = s.actions, Pn = mlp_P(s);
       float* dstg = slab + s.mlp_offset;
       const float* srcs = par + p.par_off[i];
       for (int e2 = lane; e2 < Pn; e2 += 32) {

@@ -167,10 +167,13 @@ class RunBatch:
             if s.kind == abi.THRL_AGENT_QTABLE:
                 out.append(None)
                 continue
-            H, A = s.hidden, s.actions
             p = self.mlp[run, s.mlp_offset:s.mlp_offset + abi.mlp_param_count(s)].cpu()
-            out.append({"fc1.weight": p[:H].reshape(H, 1).clone(), "fc1.bias": p[H:2 * H].clone(),
-                        "fc_pi.weight": p[2 * H:2 * H + A * H].reshape(A, H).clone(), "fc_pi.bias": p[2 * H + A * H:].clone()})
+            d, o = {}, 0
+            for k, shp in abi.mlp_param_shapes(s).items():
+                cnt = int(np.prod(shp))
+                d[k] = p[o:o + cnt].reshape(shp).clone()
+                o += cnt
+            out.append(d)
         return out
 
     def greedy_eval(self, price0):

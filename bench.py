@@ -65,6 +65,18 @@ WORKLOADS = {
                     "tables left in HBM, max_steps=100, %d runs/GPU x %d epochs per step (C4 shape)",
                kernel="thrl::qtable_scan_generic<float, false> (persistent, one launch per step)"),
 }
+def _c5_cfg(epochs):
+    a = dict(name="ActorCritic", gamma=0.98, actions=21, states=1, action_range=[0.2, 0.4])  # 1 -> 256 -> {21, 1}, N = 1000
+    return {"agents": [dict(a), dict(a)],
+            "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=2, max_steps=MAX_STEPS),
+            "training": dict(print_freq=500, epochs=epochs)}
+
+
+# ~1.1e4 flop per act + ~3.4e4 flop per agent-step of amortised update (N = 1000 batch every 10 episodes)
+WORKLOADS["c5"] = dict(agents=2, runs_per_gpu=16384, epochs=20, config=_c5_cfg(20), algo_bytes=4.5e4, bound="tensor", hp=None,
+                       desc="2 ActorCritic agents (MLP 1->256->{21,1}, Adam, N=1000 transition batches every 10 episodes), "
+                            "%d runs/GPU x %d epochs per step (C5 shape)",
+                       kernel="thrl::qtable_scan_mixed<float> (persistent, one launch per step; CUDA-core fp32, no tensor cores yet)")
 WL = WORKLOADS["c2"]  # set in main()
 CONFIG = WL["config"]
 EPOCHS = WL["epochs"]
@@ -83,6 +95,13 @@ def measured_peaks():
         d = json.load(open(p))
         return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured"
     return 6650.0, 1965.0, "fallback"
+
+
+def measured_tflops():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("bf16_tflops_sustained", 1400.0), "measured (sustained)"
+    return 1400.0, "fallback"
 
 
 class ClockSampler:
@@ -138,15 +157,15 @@ def cpu_oracle_leg(n_threads, target_seconds=12.0):
     eps0 = abi.eps0_from_config(CONFIG)
     # calibrate on a small sample, then size the timed sample for ~target_seconds
     R0 = (64 if WL["agents"] == 2 else 1) * cores
-    q0, c0, e0, p0 = oracle.init(game, R0, seed=0, dtype=np.float32, eps0=eps0)
+    q0, c0, e0, p0, *rest = oracle.init(game, R0, seed=0, dtype=np.float32, eps0=eps0)
     t = time.perf_counter()
-    oracle.scan(game, q0, e0, p0, 20, n_threads=cores, n_log_runs=0, stats=True)
+    oracle.scan(game, q0, e0, p0, 20, n_threads=cores, n_log_runs=0, stats=True, mlp=rest[0] if rest else None)
     n = WL["agents"]
     rate = R0 * n * 20 * MAX_STEPS / (time.perf_counter() - t)
     R = int(max(cores, min(262144, target_seconds * rate / (n * EPOCHS * MAX_STEPS))))
-    q0, c0, e0, p0 = oracle.init(game, R, seed=0, dtype=np.float32, eps0=eps0)
+    q0, c0, e0, p0, *rest = oracle.init(game, R, seed=0, dtype=np.float32, eps0=eps0)
     t = time.perf_counter()
-    oracle.scan(game, q0, e0, p0, EPOCHS, n_threads=cores, n_log_runs=0, stats=True)
+    oracle.scan(game, q0, e0, p0, EPOCHS, n_threads=cores, n_log_runs=0, stats=True, mlp=rest[0] if rest else None)
     dt = time.perf_counter() - t
     return {"value": R * n * EPOCHS * MAX_STEPS / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
             "sample": "%d runs x %d epochs x %d steps x %d agents of the bench workload, fp32-storage oracle "
@@ -154,7 +173,13 @@ def cpu_oracle_leg(n_threads, target_seconds=12.0):
 
 
 def _run_stride():
-    return sum((a["states"] + 1) * a["actions"] for a in CONFIG["agents"])
+    return sum((a["states"] + 1) * a["actions"] for a in CONFIG["agents"] if a["name"] == "QTable")
+
+
+def _state_bytes(R):
+    from th_rl_b200 import _lib
+    g = _lib.game_layout(CONFIG)
+    return R * (g.run_stride * 8 + g.mlp_stride * 4)
 
 
 def base_line(args, n_gpus):
@@ -167,8 +192,7 @@ def base_line(args, n_gpus):
                    "max_steps": MAX_STEPS, "agents": WL["agents"], "table_storage": "fp32 (f64 update arithmetic)",
                    "rng": "philox4x32-10", "parallelism": "runs sharded over %d GPU(s), no data-path collective; "
                                                           "NCCL all-reduce of per-epoch statistics" % n_gpus,
-                   "l2": "per-GPU state (tables+counters %.1f GB) is far larger than the 126 MB L2"
-                         % (args.runs_per_gpu * _run_stride() * 8 / 1e9)},
+                   "l2": "per-GPU state (%.1f GB) is far larger than the 126 MB L2" % (_state_bytes(args.runs_per_gpu) / 1e9)},
     }
 
 
@@ -275,6 +299,16 @@ def run_ours(args):
                         "load/store and the visit counters" % (sm_max_mhz, peak_src),
                 "hbm": {"achieved": per_gpu_rate * (2 * _run_stride() * (4 + 4 + 4) / (nag * 1.0 * E * MAX_STEPS)) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s"}}
+        elif WL["bound"] == "tensor":
+            tf_peak, tf_src = measured_tflops()
+            tf = per_gpu_rate * ALGO_BYTES_PER_AGENT_STEP / 1e12
+            line["roofline"] = {
+                "bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
+                "kernel": WL["kernel"], "kernel_ms": kern_ms,
+                "note": "4.5e4 algorithmic flop per agent-step (BASELINE.md 5); peak = bf16 dense from MEASURED_PEAKS.json (%s). "
+                        "This tier is correctness-first: fp32 on CUDA cores in the oracle's operation order (bit-equal to it); "
+                        "tensor-pipe utilisation is 0 by construction. The per-run-weight grouped GEMMs (16,384 x 1000x256x22) "
+                        "on tcgen05 are the next round's work" % tf_src}
         else:
             line["roofline"] = {
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -337,7 +371,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (default); c4 = HBM-resident sweep")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (default); c4 = HBM-resident sweep; c5 = MLP (ActorCritic) agents")
     ap.add_argument("--runs-per-gpu", type=int, default=None)
     ap.add_argument("--epochs", type=int, default=None)
     ap.add_argument("--e2e-chunks", type=int, default=8)

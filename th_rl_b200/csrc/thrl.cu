@@ -423,7 +423,7 @@ int check_args(const ThrlScanArgs* a) {
   if (a->n_runs < 0 || a->epoch_end < a->epoch_begin) return fail(THRL_ERR_BAD_ARGS, "negative run or epoch count");
   if (a->table_dtype != THRL_F32 && a->table_dtype != THRL_F64) return fail(THRL_ERR_BAD_ARGS, "table_dtype=%d", a->table_dtype);
   if (a->rng_mode < THRL_RNG_PHILOX || a->rng_mode > THRL_RNG_REPLAY_ACTIONS) return fail(THRL_ERR_BAD_ARGS, "rng_mode=%d", a->rng_mode);
-  if (!a->q || !a->eps || !a->price) return fail(THRL_ERR_BAD_ARGS, "q / eps / price must not be NULL");
+  if (!a->eps || !a->price) return fail(THRL_ERR_BAD_ARGS, "eps / price must not be NULL");
   if (a->rng_mode != THRL_RNG_PHILOX && !a->replay_ra) return fail(THRL_ERR_BAD_ARGS, "replay mode without replay_ra");
   if (a->rng_mode == THRL_RNG_REPLAY_DRAWS && !a->replay_u) return fail(THRL_ERR_BAD_ARGS, "REPLAY_DRAWS without replay_u");
   bool has_mlp = false;
@@ -457,6 +457,7 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
   p.game = *a->game;
   rc = validate_layout(&p.game);
   if (rc) return rc;
+  if (p.game.run_stride > 0 && !a->q) return fail(THRL_ERR_BAD_ARGS, "q must not be NULL (the game has Q-tables)");
   if (a->n_runs == 0 || a->epoch_end == a->epoch_begin) return THRL_OK;
   DeviceInfo dev;
   rc = device_info(&dev);
@@ -524,7 +525,7 @@ int thrl_qtable_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint
 int thrl_game_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,
                    const double* hp, const double* eps0, void* q, uint32_t* counter, double* eps, double* price, float* mlp,
                    void* stream) {
-  if (!game || !eps0 || !q || !eps || !price) return fail(THRL_ERR_BAD_ARGS, "thrl_game_init: NULL argument");
+  if (!game || !eps0 || !eps || !price) return fail(THRL_ERR_BAD_ARGS, "thrl_game_init: NULL argument");
   if (table_dtype != THRL_F32 && table_dtype != THRL_F64) return fail(THRL_ERR_BAD_ARGS, "table_dtype=%d", table_dtype);
   thrl::InitParams p;
   memset(&p, 0, sizeof(p));
@@ -542,6 +543,7 @@ int thrl_game_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64
   for (int i = 0; i < p.game.n_agents; ++i) p.eps0[i] = eps0[i];
   p.q = q; p.counter = counter; p.eps = eps; p.price = price; p.mlp = mlp;
   if (p.game.mlp_stride > 0 && !mlp) return fail(THRL_ERR_BAD_ARGS, "the game has MLP agents but mlp is NULL");
+  if (p.game.run_stride > 0 && !q) return fail(THRL_ERR_BAD_ARGS, "q must not be NULL (the game has Q-tables)");
   long long max_cells = 0;
   for (int i = 0; i < p.game.n_agents; ++i) {
     const ThrlAgentSpec& sa = p.game.agent[i];

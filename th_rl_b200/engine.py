@@ -192,8 +192,8 @@ class RunBatch:
 class HostState:
     """Per-run state in pinned host memory (what a host-side caller owns between calls)."""
 
-    def __init__(self, q, counter, eps, price):
-        self.q, self.counter, self.eps, self.price = q, counter, eps, price
+    def __init__(self, q, counter, eps, price, mlp=None):
+        self.q, self.counter, self.eps, self.price, self.mlp = q, counter, eps, price, mlp
 
     @classmethod
     def from_batch(cls, batch):
@@ -201,10 +201,11 @@ class HostState:
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             h.copy_(t)
             return h
-        return cls(pin(batch.q), pin(batch.counter), pin(batch.eps), pin(batch.price))
+        return cls(pin(batch.q), pin(batch.counter), pin(batch.eps), pin(batch.price),
+                   None if batch.mlp is None else pin(batch.mlp))
 
     def nbytes(self):
-        return sum(t.numel() * t.element_size() for t in (self.q, self.counter, self.eps, self.price))
+        return sum(t.numel() * t.element_size() for t in (self.q, self.counter, self.eps, self.price, self.mlp) if t is not None)
 
 
 def scan_from_host(batch, host, epochs, n_chunks=8):
@@ -223,7 +224,9 @@ def scan_from_host(batch, host, epochs, n_chunks=8):
         cs = torch.cuda.current_stream()
         stats = torch.zeros((E, n, abi.THRL_STATS_K), dtype=torch.int64, device=dev)
         up.wait_stream(cs)
-        pairs = ((batch.q, host.q), (batch.counter, host.counter), (batch.eps, host.eps), (batch.price, host.price))
+        pairs = [(batch.q, host.q), (batch.counter, host.counter), (batch.eps, host.eps), (batch.price, host.price)]
+        if batch.mlp is not None:
+            pairs.append((batch.mlp, host.mlp))
         for c in range(n_chunks):
             b, e = bounds[c], bounds[c + 1]
             with torch.cuda.stream(up):

@@ -316,6 +316,14 @@ def run_ours(args):
                 "note": "tables (3.2 MB per run) stay in HBM; 824 algorithmic B per agent-step (BASELINE.md 5); peak = measured "
                         "copy bandwidth from MEASURED_PEAKS.json (%s). ncu (profiles/): dram bytes per agent-step ~ 1.0 kB, "
                         "long-scoreboard stalls dominate (latency-bound row gathers)" % peak_src}
+        try:  # DRAM traffic per launch, measured once with ncu --set full on this exact command (profiles/)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
+            if tr and args.runs_per_gpu == WL["runs_per_gpu"] and args.epochs == WL["epochs"]:
+                line["roofline"]["traffic"] = tr["traffic_bytes_per_launch"]
+                line["roofline"]["traffic_source"] = tr["source"]
+                line["roofline"]["algorithmic_bytes_per_launch"] = agent_steps_rank * ALGO_BYTES_PER_AGENT_STEP
+        except (OSError, ValueError):
+            pass
         if args.no_cpu_baseline:
             line["cpu_baseline"] = None
         else:

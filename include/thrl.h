@@ -56,7 +56,10 @@ typedef enum ThrlDtype {
 typedef enum ThrlAgentKind {
   THRL_AGENT_QTABLE = 0,   /* th_rl/agents.py:12-116 */
   THRL_AGENT_REINFORCE = 1,  /* th_rl/agents.py:119-219: MLP 1 -> hidden -> actions, policy gradient, Adam(lr) */
-  THRL_AGENT_ACTORCRITIC = 2 /* th_rl/agents.py:222-330: as Reinforce plus value head fc_v (bias 1000), [N,N] advantage loss */
+  THRL_AGENT_ACTORCRITIC = 2, /* th_rl/agents.py:222-330: as Reinforce plus value head fc_v (bias 1000), [N,N] advantage loss */
+  THRL_AGENT_CAC = 3          /* th_rl/agents.py:333-442: continuous action sigmoid(N(mu, std)), heads fc_mu / fc_std / fc_v.
+                                 Its actions are float32 values: action streams (replay_ra, trace_actions, buffers) carry their
+                                 bit patterns; `actions` is unused (set it to 2) */
 } ThrlAgentKind;
 
 typedef enum ThrlRngMode {
@@ -85,13 +88,14 @@ typedef struct ThrlAgentSpec {
 } ThrlAgentSpec;
 
 /* Layout of one MLP agent's block inside the run's MLP slab (floats / 32-bit words), P = 2*hidden + actions*hidden + actions
- * (+ hidden + 1 for ActorCritic):
+ * (+ hidden + 1 for ActorCritic; CAC: P = 5*hidden + 3):
  *   [0, P)        parameters in state_dict order: fc1.weight[hidden] fc1.bias[hidden] fc_pi.weight[actions][hidden] fc_pi.bias[actions]
- *                 (ActorCritic: then fc_v.weight[hidden] fc_v.bias[1])
+ *                 (ActorCritic: then fc_v.weight[hidden] fc_v.bias[1]; CAC: fc1.weight fc1.bias fc_mu.weight[hidden] fc_mu.bias[1]
+ *                 fc_std.weight[hidden] fc_std.bias[1] fc_v.weight[hidden] fc_v.bias[1])
  *   [P, 2P)       Adam exp_avg          [2P, 3P)  Adam exp_avg_sq
  *   [3P, 3P+4)    int32 header: Adam step count, buffered transitions, 2 reserved
  *   [3P+4, ...)   transition buffer, `mlp_buffer_len` entries of 3 words: state (f32), action (int32), reward (f32);
- *                 ActorCritic entries have a 4th word: new_state (f32) */
+ *                 ActorCritic and CAC entries have a 4th word: new_state (f32); CAC's action word is a float32 */
 #define THRL_MLP_HEADER_WORDS 4
 
 /* One game = n agents + NoisyPriceState kwargs (th_rl/environments.py:5-13). */

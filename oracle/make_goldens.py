@@ -114,6 +114,12 @@ CASES = {
                                            min_memory=60),
                                       _agent(actions=9, states=40, action_range=[0.1, 0.3])],
                               environment=_env(nplayers=3, max_steps=30), training=dict(epochs=12, print_freq=1000)), 12),
+    # CAC (agents.py:333-442): continuous action = sigmoid(Normal(mu, std).sample()), [N,N] log_prob x advantage loss
+    "mixed_qc_seed13": (dict(agents=[_agent(), dict(name="CAC", gamma=0.98, states=1, action_range=[0.2, 0.4], min_memory=200)],
+                             environment=_env(), training=dict(epochs=8, print_freq=1000)), 13),
+    "mixed_cc_seed14": (dict(agents=[dict(name="CAC", gamma=0.9, states=1, action_range=[0.1, 0.3], min_memory=90, capacity=120),
+                                     dict(name="CAC", gamma=0.5, states=1, action_range=[0.05, 0.2], min_memory=60)],
+                             environment=_env(max_steps=30), training=dict(epochs=12, print_freq=1000)), 14),
 }
 
 
@@ -193,6 +199,20 @@ def record_case(cfg, seed):
             super().train_net()
             rec["eps_trace"].append(float("nan"))
 
+    class CAC(ragents.CAC):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            rec.setdefault("mlp0", []).append({k: v.detach().numpy().copy() for k, v in self.state_dict().items()})
+
+        def sample_action(self, state):
+            a = super().sample_action(state)   # python float holding a float32 value in (0, 1)
+            rec["acts"].append((float("nan"), -1, int(numpy.float32(a).view(numpy.int32))))   # stored as its float32 bit pattern
+            return a
+
+        def train_net(self):
+            super().train_net()
+            rec["eps_trace"].append(float("nan"))
+
     class NoisyPriceState(renv.NoisyPriceState):
         def reset(self):
             s = super().reset()
@@ -215,11 +235,12 @@ def record_case(cfg, seed):
             return out
 
     proxy = _RandomProxy(random, draws)
-    saved = (ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce, rtrainer.ActorCritic)
+    saved = (ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce, rtrainer.ActorCritic, rtrainer.CAC)
     ragents.random = proxy
     rtrainer.QTable = QTable
     rtrainer.Reinforce = Reinforce
     rtrainer.ActorCritic = ActorCritic
+    rtrainer.CAC = CAC
     rtrainer.NoisyPriceState = NoisyPriceState
     torch.set_num_threads(1)
     try:
@@ -243,7 +264,7 @@ def record_case(cfg, seed):
                 header = [f.readline().strip(), f.readline().strip()]
                 log = numpy.loadtxt(f, delimiter=",", ndmin=2)
     finally:
-        ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce, rtrainer.ActorCritic = saved
+        ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce, rtrainer.ActorCritic, rtrainer.CAC = saved
 
     E = cfg["training"]["epochs"]
     T = cfg["environment"]["max_steps"]

@@ -67,7 +67,7 @@ def pack_tables(game, per_agent, dtype):
     n = game.n_agents
     arrs = [None if a is None else np.asarray(a, dtype=np.float64) for a in per_agent]
     arrs = [a if a is None else (a[None] if a.ndim == 2 else a) for a in arrs]
-    R = next(a for a in arrs if a is not None).shape[0]
+    R = next((a.shape[0] for a in arrs if a is not None), 1)  # a game may have no Q-tables at all
     out = np.zeros((R, game.run_stride), dtype=dtype)
     for i in range(n):
         s = game.agent[i]

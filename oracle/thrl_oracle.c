@@ -170,10 +170,11 @@ static float det_expf(float x) {
   return ldexpf(p, (int)kf);
 }
 static int mlp_P(const ThrlAgentSpec* s) {
+  if (s->kind == THRL_AGENT_CAC) return 5 * s->hidden + 3;
   const int p = 2 * s->hidden + s->actions * s->hidden + s->actions;
   return s->kind == THRL_AGENT_ACTORCRITIC ? p + s->hidden + 1 : p;
 }
-static int mlp_entry_words(const ThrlAgentSpec* s) { return s->kind == THRL_AGENT_ACTORCRITIC ? 4 : 3; }
+static int mlp_entry_words(const ThrlAgentSpec* s) { return s->kind == THRL_AGENT_REINFORCE ? 3 : 4; }
 /* pi(x) (agents.py:148-152): h = relu(fc1(x)), logits = fc_pi(h), softmax.  par: w1[H] b1[H] W[A][H] bp[A]. */
 static void mlp_forward(const float* par, int H, int A, float s, float* h, float* prob) {
   const float *w1 = par, *b1 = par + H, *W = par + 2 * H, *bp = par + 2 * H + (size_t)A * H;
@@ -402,6 +403,128 @@ static void ac_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, int
   mlp_clip_adam(blk, sp, g);
 }
 
+/* ---------------------------------------------------------------- CAC agent (th_rl/agents.py:333-417), float32 / f64 mix
+ * Transcendentals are our own deterministic sequences (exp: det_expf; log: det_log in f64) so host and device agree. */
+static float det_tanhf(float x) {
+  const float ax = fabsf(x);
+  float t;
+  if (ax < 0.1f) { /* odd series: x - x^3/3 + 2x^5/15 - 17x^7/315 */
+    const float x2 = ax * ax;
+    float p = -17.0f / 315.0f;
+    p = p * x2 + 2.0f / 15.0f;
+    p = p * x2 - 1.0f / 3.0f;
+    p = p * x2;
+    p = p * ax;
+    t = ax + p;
+  } else {
+    const float e = det_expf(-2.0f * ax);
+    t = (1.0f - e) / (1.0f + e);
+  }
+  return x < 0.0f ? -t : t;
+}
+static float det_sigmoidf(float x) { /* 1 / (1 + exp(-x)) */
+  if (x >= 0.0f) { const float e = det_expf(-x); return 1.0f / (1.0f + e); }
+  const float e = det_expf(x);
+  return e / (1.0f + e);
+}
+static float det_softplusf(float x) { /* F.softplus: x if x > 20 else log1p(exp(x)) */
+  if (x > 20.0f) return x;
+  const float e = det_expf(-fabsf(x));
+  const float l = (float)det_log(1.0 + (double)e);
+  return (x > 0.0f ? x : 0.0f) + l;
+}
+/* CAC.pi (agents.py:362-366) and v at one state; h must hold relu(fc1(s)).  par: w1 b1 | wmu bmu | wsd bsd | wv bv */
+static void cac_heads(const float* par, int H, const float* h, float* zmu, float* zsd, float* v) {
+  const float *wmu = par + 2 * H, *wsd = wmu + H + 1, *wv = wsd + H + 1;
+  *zmu = ac_value(wmu, wmu[H], h, H);
+  *zsd = ac_value(wsd, wsd[H], h, H);
+  *v = ac_value(wv, wv[H], h, H);
+}
+/* sample_action (agents.py:374-378): sigmoid(Normal(mu, std).sample()); z = standard normal deviate */
+static float cac_action(const float* par, int H, float s, float* h, double z) {
+  float zmu, zsd, v;
+  mlp_hidden(par, H, s, h);
+  cac_heads(par, H, h, &zmu, &zsd, &v);
+  const float mu = 4.0f * det_tanhf(zmu), sd = det_softplusf(zsd);
+  float raw = sd * (float)z;
+  raw = mu + raw;
+  return det_sigmoidf(raw);
+}
+/* CAC.train_net (agents.py:391-417).  As in ActorCritic, `rewards` is [N] while mu, std, v, v' are [N,1]: adv[i][j] = r_j + d_i,
+ * log_prob[i][j] = logN(l_j; mu_i, sd_i) with l_j = logit(5e-5 + (1 - 1e-4) a_j); loss = mean_ij(adv^2 - log_prob * adv.detach()).
+ * With the moments Sr = sum r, Sl = sum l, Sl2 = sum l^2, Srl = sum r l, Srl2 = sum r l^2 (f64):
+ *   dL/dd_i  = 2 (Sr + N d_i) / N^2
+ *   dL/dmu_i = -[Srl - mu Sr + d (Sl - N mu)] / (N^2 sd^2)
+ *   dL/dsd_i = -[(Srl2 - 2 mu Srl + mu^2 Sr + d (Sl2 - 2 mu Sl + N mu^2)) / sd^3 - (Sr + N d) / sd] / N^2 */
+static void cac_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, int N, float* scratch) {
+  const int H = sp->hidden;
+  const int P = mlp_P(sp), EW = mlp_entry_words(sp);
+  float* par = blk;
+  const float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
+  const float *wmu = par + 2 * H, *wsd = wmu + H + 1, *wv = wsd + H + 1;
+  float *g = scratch, *h = scratch + P, *dh = h + H;
+  float *gwmu = g + 2 * H, *gwsd = gwmu + H + 1, *gwv = gwsd + H + 1;
+  for (int i = 0; i < P; ++i) g[i] = 0.0f;
+  const float gam = (float)sp->gamma;
+  double Sr = 0.0, Sl = 0.0, Sl2 = 0.0, Srl = 0.0, Srl2 = 0.0;
+  for (int j = 0; j < N; ++j) {
+    const float* tr = buf + (size_t)((head + j) % cap) * EW;
+    float a_ = (1.0f - 1e-4f) * tr[1];
+    a_ = 5e-5f + a_;
+    const float ratio = a_ / (1.0f - a_);
+    const double l = (double)(float)det_log((double)ratio), r = (double)tr[2];
+    Sr += r; Sl += l; Sl2 += l * l; Srl += r * l; Srl2 += r * l * l;
+  }
+  const double dN = (double)N, invN2 = 1.0 / (dN * dN);
+  for (int i = 0; i < N; ++i) {
+    const float* tr = buf + (size_t)((head + i) % cap) * EW;
+    const float s = tr[0], s2 = tr[3];
+    float zmu, zsd, v, z2, z3, vp;
+    mlp_hidden(par, H, s2, h);
+    cac_heads(par, H, h, &z2, &z3, &vp);
+    mlp_hidden(par, H, s, h);
+    cac_heads(par, H, h, &zmu, &zsd, &v);
+    const float t = det_tanhf(zmu), mu = 4.0f * t, sd = det_softplusf(zsd);
+    float d = gam * vp;
+    d = d - v;
+    const double dd = (double)d, dmu = (double)mu, dsd = (double)sd;
+    const double A0 = Sr + dN * dd;
+    const double A1 = Srl - dmu * Sr + dd * (Sl - dN * dmu);
+    const double A2 = Srl2 - 2.0 * dmu * Srl + dmu * dmu * Sr + dd * (Sl2 - 2.0 * dmu * Sl + dN * dmu * dmu);
+    const float gmu = (float)(-(A1 / (dsd * dsd)) * invN2);
+    const float gsd = (float)(-(A2 / (dsd * dsd * dsd) - A0 / dsd) * invN2);
+    const float cv = (float)(-2.0 * A0 * invN2); /* dL/dv_i */
+    const float cvp = (-gam) * cv;               /* dL/dv'_i */
+    float dzmu = 1.0f - t * t;
+    dzmu = 4.0f * dzmu;
+    dzmu = gmu * dzmu;                            /* through mu = 4 tanh(z) */
+    const float dzsd = gsd * det_sigmoidf(zsd);   /* through softplus */
+    for (int jh = 0; jh < H; ++jh) {
+      const float hj = h[jh];
+      float u = dzmu * hj; gwmu[jh] = gwmu[jh] + u;
+      u = dzsd * hj; gwsd[jh] = gwsd[jh] + u;
+      u = cv * hj; gwv[jh] = gwv[jh] + u;
+      float acc = dzmu * wmu[jh];
+      u = dzsd * wsd[jh]; acc = acc + u;
+      u = cv * wv[jh]; acc = acc + u;
+      dh[jh] = acc;
+    }
+    gwmu[H] = gwmu[H] + dzmu;
+    gwsd[H] = gwsd[H] + dzsd;
+    gwv[H] = gwv[H] + cv;
+    mlp_back_fc1(H, h, dh, s, g);
+    mlp_hidden(par, H, s2, h); /* value head at s'_i */
+    for (int jh = 0; jh < H; ++jh) {
+      float u = cvp * h[jh];
+      gwv[jh] = gwv[jh] + u;
+      dh[jh] = cvp * wv[jh];
+    }
+    gwv[H] = gwv[H] + cvp;
+    mlp_back_fc1(H, h, dh, s2, g);
+  }
+  mlp_clip_adam(blk, sp, g);
+}
+
 typedef struct Transition { /* buffers.py Experience(state, action, reward, done, new_state); `done` is never read */
   double state, reward, new_state;
   int action;
@@ -491,6 +614,22 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
         if (s->kind != THRL_AGENT_QTABLE) {
           /* Reinforce.sample_action (agents.py:160-163): in both replay modes the recorded sample is forced (it came from
            * torch's generator); free running: inverse-CDF on one Philox word */
+          if (s->kind == THRL_AGENT_CAC) {
+            /* CAC.sample_action (agents.py:374-378): a float32 in (0,1); streams carry its bit pattern (never negative) */
+            float af;
+            if (A->rng_mode != THRL_RNG_PHILOX && A->replay_ra[sidx * n + i] >= 0) {
+              memcpy(&af, &A->replay_ra[sidx * n + i], 4);
+            } else {
+              uint32_t x[4];
+              philox4x32_10((uint32_t)gid, (uint32_t)eabs, (uint32_t)t, (uint32_t)(i >> 1) | (STREAM_ACT << 16), k0, k1, x);
+              const uint64_t m = ((uint64_t)x[2 * (i & 1)] << 21) | (x[2 * (i & 1) + 1] >> 11);
+              const double z = det_norminv(((double)m + 0.5) * (1.0 / 9007199254740992.0));
+              af = cac_action(mlp_blk[i], s->hidden, (float)price, mlp_scratch, z);
+            }
+            memcpy(&act[i], &af, 4);
+            xs[i] = (double)af * (s->action_hi - s->action_lo) + s->action_lo; /* CAC.scale (agents.py:368-372) */
+            continue;
+          }
           if (A->rng_mode != THRL_RNG_PHILOX && A->replay_ra[sidx * n + i] >= 0) {
             k = A->replay_ra[sidx * n + i];
           } else { /* free running, or a replay stream that leaves this agent's sample to the device (negative entry) */
@@ -604,7 +743,8 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
         const size_t P = (size_t)mlp_P(s);
         int32_t* hdr = (int32_t*)(mlp_blk[i] + 3 * P);
         if (G->mlp_buffer_len[i] > 0 && hdr[1] >= s->min_memory) { /* agents.py:171 / :281 */
-          if (s->kind == THRL_AGENT_ACTORCRITIC) ac_train(mlp_blk[i], s, G->mlp_buffer_len[i], hdr[2], hdr[1], mlp_scratch);
+          if (s->kind == THRL_AGENT_CAC) cac_train(mlp_blk[i], s, G->mlp_buffer_len[i], hdr[2], hdr[1], mlp_scratch);
+          else if (s->kind == THRL_AGENT_ACTORCRITIC) ac_train(mlp_blk[i], s, G->mlp_buffer_len[i], hdr[2], hdr[1], mlp_scratch);
           else mlp_train(mlp_blk[i], s, G->mlp_buffer_len[i], hdr[2], hdr[1], mlp_scratch);
           hdr[1] = 0; hdr[2] = 0; /* :194 memory.empty() */
         }
@@ -726,6 +866,7 @@ int thrl_oracle_game_init(const ThrlGame* G, int64_t n_runs, int64_t run_id0, ui
             const float bound = (w < 2 * (int64_t)s->hidden) ? b_fc1 : b_pi;
             v = (float)(2.0 * u - 1.0) * bound;
             if (s->kind == THRL_AGENT_ACTORCRITIC && w == Pn - 1) v = 1000.0f; /* fc_v.bias.data.fill_(1000.0), agents.py:244 */
+            /* (CAC does not touch fc_v.bias: agents.py:349-352) */
           }
           blk[w] = v;
         }
@@ -804,7 +945,7 @@ int thrl_oracle_game_layout(ThrlGame* G) {
     const int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
     int64_t need = (int64_t)T * ((mm + T - 1) / T);
     if (need > s->capacity) need = s->capacity;
-    if (s->kind == THRL_AGENT_REINFORCE || s->kind == THRL_AGENT_ACTORCRITIC) {
+    if (s->kind == THRL_AGENT_REINFORCE || s->kind == THRL_AGENT_ACTORCRITIC || s->kind == THRL_AGENT_CAC) {
       if (s->states != 1 || s->hidden < 1 || s->entropy != 0.0) return THRL_ERR_BAD_CONFIG;
       const int64_t P = mlp_P(s);
       G->mlp_buffer_len[i] = s->min_memory <= s->capacity ? (int32_t)need : 0;

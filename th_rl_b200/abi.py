@@ -26,6 +26,7 @@ THRL_F64 = 1
 THRL_AGENT_QTABLE = 0
 THRL_AGENT_REINFORCE = 1
 THRL_AGENT_ACTORCRITIC = 2
+THRL_AGENT_CAC = 3
 THRL_MLP_HEADER_WORDS = 4
 
 THRL_RNG_PHILOX = 0
@@ -110,6 +111,8 @@ REINFORCE_DEFAULTS = dict(states=4, actions=2, action_range=[0, 1], gamma=0.98, 
 # ActorCritic.__init__ defaults (th_rl/agents.py:223-234)
 ACTORCRITIC_DEFAULTS = dict(states=4, actions=2, action_range=[0, 1], gamma=0.98, buffer="ReplayBuffer", capacity=50000,
                             min_memory=1000, entropy=0)
+# CAC.__init__ defaults (th_rl/agents.py:334-343); it has no `actions`
+CAC_DEFAULTS = dict(states=4, action_range=[0, 1], gamma=0.98, buffer="ReplayBuffer", capacity=50000, min_memory=1000, entropy=0)
 # NoisyPriceState.__init__ defaults (th_rl/environments.py:5)
 ENV_DEFAULTS = dict(action_range=[0, 1], a=10, b=1, max_steps=1, noise_prob=0.05)
 
@@ -137,11 +140,11 @@ def game_from_config(config):
     for i, ad in enumerate(agents):
         name = ad.get("name", "QTable")
         s = g.agent[i]
-        if name in ("Reinforce", "ActorCritic"):
-            d = dict(REINFORCE_DEFAULTS if name == "Reinforce" else ACTORCRITIC_DEFAULTS)
+        if name in ("Reinforce", "ActorCritic", "CAC"):
+            d = dict({"Reinforce": REINFORCE_DEFAULTS, "ActorCritic": ACTORCRITIC_DEFAULTS, "CAC": CAC_DEFAULTS}[name])
             d.update(ad)
-            s.kind = THRL_AGENT_REINFORCE if name == "Reinforce" else THRL_AGENT_ACTORCRITIC
-            s.states, s.actions = int(d["states"]), int(d["actions"])
+            s.kind = {"Reinforce": THRL_AGENT_REINFORCE, "ActorCritic": THRL_AGENT_ACTORCRITIC, "CAC": THRL_AGENT_CAC}[name]
+            s.states, s.actions = int(d["states"]), (2 if name == "CAC" else int(d["actions"]))
             s.min_memory, s.capacity = int(d["min_memory"]), int(d["capacity"])
             s.action_lo, s.action_hi = float(d["action_range"][0]), float(d["action_range"][1])
             s.max_state = float("nan")
@@ -150,7 +153,7 @@ def game_from_config(config):
             continue
         if name != "QTable":
             raise NotImplementedError(
-                "agent %d is %r: the B200 hot path covers QTable, Reinforce and ActorCritic agents (DESIGN.md: CAC is next)"
+                "agent %d is %r: the B200 hot path covers the reference's QTable, Reinforce, ActorCritic and CAC agents"
                 % (i, name))
         d = dict(QTABLE_DEFAULTS)
         d.update(ad)
@@ -174,22 +177,27 @@ def eps0_from_config(config):
 
 
 def mlp_param_count(spec):
+    if spec.kind == THRL_AGENT_CAC:
+        return 5 * spec.hidden + 3
     p = 2 * spec.hidden + spec.actions * spec.hidden + spec.actions
     return p + spec.hidden + 1 if spec.kind == THRL_AGENT_ACTORCRITIC else p
 
 
 def mlp_entry_words(spec):
-    return 4 if spec.kind == THRL_AGENT_ACTORCRITIC else 3
-
-
-def mlp_param_names(spec):
-    names = ["fc1.weight", "fc1.bias", "fc_pi.weight", "fc_pi.bias"]
-    return names + ["fc_v.weight", "fc_v.bias"] if spec.kind == THRL_AGENT_ACTORCRITIC else names
+    return 3 if spec.kind == THRL_AGENT_REINFORCE else 4
 
 
 def mlp_param_shapes(spec):
+    """state_dict names -> shapes, in the order the parameters sit in the MLP slab."""
     H, A = spec.hidden, spec.actions
+    if spec.kind == THRL_AGENT_CAC:
+        return {"fc1.weight": (H, 1), "fc1.bias": (H,), "fc_mu.weight": (1, H), "fc_mu.bias": (1,),
+                "fc_std.weight": (1, H), "fc_std.bias": (1,), "fc_v.weight": (1, H), "fc_v.bias": (1,)}
     sh = {"fc1.weight": (H, 1), "fc1.bias": (H,), "fc_pi.weight": (A, H), "fc_pi.bias": (A,)}
     if spec.kind == THRL_AGENT_ACTORCRITIC:
         sh.update({"fc_v.weight": (1, H), "fc_v.bias": (1,)})
     return sh
+
+
+def mlp_param_names(spec):
+    return list(mlp_param_shapes(spec))

@@ -38,13 +38,16 @@ def test_train_one_reproduces_reference_files(golden, tmp_path):
                 assert c.sum() == golden["counter_final_%d" % i].sum()
             else:
                 sd = torch.load(out / str(i))
-                want = ["fc1.weight", "fc1.bias", "fc_pi.weight", "fc_pi.bias"] + (["fc_v.weight", "fc_v.bias"] if a["name"] == "ActorCritic" else [])
+                want = {"Reinforce": ["fc1.weight", "fc1.bias", "fc_pi.weight", "fc_pi.bias"],
+                        "ActorCritic": ["fc1.weight", "fc1.bias", "fc_pi.weight", "fc_pi.bias", "fc_v.weight", "fc_v.bias"],
+                        "CAC": ["fc1.weight", "fc1.bias", "fc_mu.weight", "fc_mu.bias", "fc_std.weight", "fc_std.bias",
+                                "fc_v.weight", "fc_v.bias"]}[a["name"]]
                 assert list(sd) == want
                 for k, v in sd.items():
                     ref0 = golden["mlp0_%d_%s" % (i, k)]
                     assert v.dtype == torch.float32 and tuple(v.shape) == ref0.shape
                 # same torch seed => same initial weights; the saved ones have moved by a few Adam steps of 2e-4
-                d = (sd["fc_pi.weight"].numpy() - golden["mlp0_%d_fc_pi.weight" % i])
+                d = (sd["fc1.weight"].numpy() - golden["mlp0_%d_fc1.weight" % i])
                 assert 1e-4 < np.abs(d).max() < 2e-3
         lines = (out / "log.csv").read_text().splitlines()
         assert lines[0] == str(golden["log_header"][0]) and lines[1] == str(golden["log_header"][1]) and len(lines) == 2 + E

@@ -71,10 +71,14 @@ def test_layout_matches_oracle_and_validates():
     bad["environment"]["nplayers"] = 3  # trainer.py:21-23
     with pytest.raises(AssertionError):
         _lib.game_layout(bad)
-    cac = _cfg()
-    cac["agents"][1]["name"] = "CAC"  # QTable, Reinforce and ActorCritic agents are implemented; CAC is not
+    unknown = _cfg()
+    unknown["agents"][1]["name"] = "DQN"  # not an agent of the reference
     with pytest.raises(NotImplementedError):
-        _lib.game_layout(cac)
+        _lib.game_layout(unknown)
+    cac = _cfg()
+    cac["agents"][1] = dict(name="CAC", gamma=0.98, states=1, action_range=[0.2, 0.4], min_memory=200)
+    g, o = _lib.game_layout(cac), oracle.layout(cac)
+    assert g.mlp_stride == 3 * (5 * 256 + 3) + 4 + 4 * 200 == o.mlp_stride and g.agent[1].kind == abi.THRL_AGENT_CAC
     ac = _cfg()
     ac["agents"][1] = dict(name="ActorCritic", gamma=0.98, actions=21, states=1, action_range=[0.2, 0.4], min_memory=200)
     g, o = _lib.game_layout(ac), oracle.layout(ac)

@@ -151,4 +151,62 @@ class ActorCritic(Reinforce):
         raise NotImplementedError(_FUSED % "ActorCritic.train_net")
 
 
-AGENTS = {"QTable": QTable, "Reinforce": Reinforce, "ActorCritic": ActorCritic}
+class CAC:
+    """Host-side mirror of th_rl/agents.py:333-442 (continuous actor-critic: heads fc_mu, fc_std, fc_v on a 1 -> 256 trunk;
+    action = sigmoid(Normal(4 tanh(mu), softplus(std)).sample())).  Layers are built in the reference's order."""
+
+    def __init__(self, states=4, action_range=[0, 1], gamma=0.98, buffer="ReplayBuffer", capacity=50000, min_memory=1000,
+                 entropy=0, **kwargs):
+        import torch.nn as nn
+        self.gamma = gamma
+        self.action_range = action_range
+        self.states = states
+        self.fc1 = nn.Linear(states, 256)   # agents.py:349-352
+        self.fc_mu = nn.Linear(256, 1)
+        self.fc_std = nn.Linear(256, 1)
+        self.fc_v = nn.Linear(256, 1)
+        if buffer != "ReplayBuffer":
+            raise ValueError("unknown buffer %r (the reference only ships ReplayBuffer)" % (buffer,))
+        self.memory = ReplayBuffer(capacity, None)
+        self.capacity = capacity
+        self.min_memory = min_memory
+        self.entropy = entropy
+
+    _LAYERS = ("fc1", "fc_mu", "fc_std", "fc_v")
+
+    def state_dict(self):
+        sd = {}
+        for nm in self._LAYERS:
+            layer = getattr(self, nm)
+            sd[nm + ".weight"] = layer.weight.detach().clone()
+            sd[nm + ".bias"] = layer.bias.detach().clone()
+        return sd
+
+    def load_state_dict(self, sd):
+        import torch
+        with torch.no_grad():
+            for nm in self._LAYERS:
+                layer = getattr(self, nm)
+                layer.weight.copy_(torch.as_tensor(sd[nm + ".weight"]).reshape(layer.weight.shape))
+                layer.bias.copy_(torch.as_tensor(sd[nm + ".bias"]).reshape(layer.bias.shape))
+
+    # agents.py:368-372
+    def scale(self, action):
+        return action * (self.action_range[1] - self.action_range[0]) + self.action_range[0]
+
+    def sample_action(self, state):
+        raise NotImplementedError(_FUSED % "CAC.sample_action")
+
+    def train_net(self):
+        raise NotImplementedError(_FUSED % "CAC.train_net")
+
+    def save(self, loc):
+        import torch
+        torch.save(self.state_dict(), loc)
+
+    def load(self, loc):
+        import torch
+        self.load_state_dict(torch.load(loc))
+
+
+AGENTS = {"QTable": QTable, "Reinforce": Reinforce, "ActorCritic": ActorCritic, "CAC": CAC}

@@ -72,12 +72,13 @@ int validate_layout(ThrlGame* G) {
     const int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
     long long need = (long long)T * ((mm + T - 1) / T);
     if (need > s->capacity) need = s->capacity;
-    if (s->kind == THRL_AGENT_REINFORCE || s->kind == THRL_AGENT_ACTORCRITIC) {
+    if (s->kind == THRL_AGENT_REINFORCE || s->kind == THRL_AGENT_ACTORCRITIC || s->kind == THRL_AGENT_CAC) {
       if (s->states != 1) return fail(THRL_ERR_BAD_CONFIG, "agent %d: states=%d for an MLP agent, the environment's state is one number", i, s->states);
       if (s->hidden < 1 || s->hidden > 1024) return fail(THRL_ERR_BAD_CONFIG, "agent %d: hidden=%d outside 1..1024", i, s->hidden);
       if (s->entropy != 0.0) return fail(THRL_ERR_UNSUPPORTED, "agent %d: entropy coefficient %g (only the reference default 0 is implemented)", i, s->entropy);
-      const bool ac = s->kind == THRL_AGENT_ACTORCRITIC;
-      const long long P = 2LL * s->hidden + (long long)s->actions * s->hidden + s->actions + (ac ? s->hidden + 1 : 0);
+      const bool ac = s->kind != THRL_AGENT_REINFORCE;  // 4-word transitions (new_state kept)
+      const long long P = s->kind == THRL_AGENT_CAC ? 5LL * s->hidden + 3
+                                                    : 2LL * s->hidden + (long long)s->actions * s->hidden + s->actions + (s->kind == THRL_AGENT_ACTORCRITIC ? s->hidden + 1 : 0);
       G->mlp_buffer_len[i] = s->min_memory <= s->capacity ? (int32_t)need : 0;
       s->mlp_offset = moff;
       s->table_offset = 0;
@@ -375,7 +376,7 @@ int launch_mixed(thrl::MixedParams& p, const DeviceInfo& dev, cudaStream_t strea
     lut += s.actions;
     p.par_off[i] = 0;
     if (s.kind == THRL_AGENT_QTABLE) continue;
-    const int P = 2 * s.hidden + s.actions * s.hidden + s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? s.hidden + 1 : 0);
+    const int P = s.kind == THRL_AGENT_CAC ? 5 * s.hidden + 3 : 2 * s.hidden + s.actions * s.hidden + s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? s.hidden + 1 : 0);
     p.par_off[i] = par;
     par += align_up(P, 4);
     if (P > pmax) pmax = P;
@@ -389,7 +390,7 @@ int launch_mixed(thrl::MixedParams& p, const DeviceInfo& dev, cudaStream_t strea
   p.off_newa = o; o += p.noisy ? align_up(T * 8, 16) : 0;
   p.off_hp = o;   o += align_up(n * 5 * 8, 16);
   p.off_old = o;  o += align_up(Hp * esz, 16);
-  p.off_pre = o;  o += align_up(T * n * 2, 16);
+  p.off_pre = o;  o += align_up(T * n * 4, 16);
   p.off_row = o;  o += align_up((Hp + 1) * 2, 16);
   p.off_act = o;  o += align_up(n * Hp, 16);
   p.off_par = o;  o += align_up(par * 4, 16);

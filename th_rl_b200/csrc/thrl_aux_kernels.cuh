@@ -66,8 +66,9 @@ __global__ void __launch_bounds__(256) qtable_init(const __grid_constant__ InitP
         // nn.Linear default init (kaiming_uniform(a=sqrt(5)) == U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias,
         // agents.py:137-138); Adam state, header and transition buffer zeroed
         const bool ac = s.kind == THRL_AGENT_ACTORCRITIC;
-        const long long Pn = 2LL * s.hidden + (long long)s.actions * s.hidden + s.actions + (ac ? s.hidden + 1 : 0);
-        const long long words = 3 * Pn + THRL_MLP_HEADER_WORDS + (ac ? 4LL : 3LL) * G.mlp_buffer_len[i];
+        const long long Pn = s.kind == THRL_AGENT_CAC ? 5LL * s.hidden + 3
+                                                      : 2LL * s.hidden + (long long)s.actions * s.hidden + s.actions + (ac ? s.hidden + 1 : 0);
+        const long long words = 3 * Pn + THRL_MLP_HEADER_WORDS + (s.kind == THRL_AGENT_REINFORCE ? 3LL : 4LL) * G.mlp_buffer_len[i];
         float* blk = p.mlp + r * G.mlp_stride + s.mlp_offset;
         const float b_fc1 = 1.0f, b_pi = (float)__ddiv_rn(1.0, sqrt((double)s.hidden));
         for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < words; w += (long long)gridDim.x * blockDim.x) {

@@ -10,6 +10,7 @@
 #pragma once
 #include "thrl_device.cuh"
 #include "thrl_scan_generic.cuh"  // RingHeader
+#include "thrl_aux_kernels.cuh"   // det_log, det_norminv
 
 namespace thrl {
 
@@ -44,10 +45,18 @@ struct MixedParams {
 };
 
 __device__ __forceinline__ int mlp_P(const ThrlAgentSpec& s) {
+  if (s.kind == THRL_AGENT_CAC) return 5 * s.hidden + 3;
   const int p = 2 * s.hidden + s.actions * s.hidden + s.actions;
   return s.kind == THRL_AGENT_ACTORCRITIC ? p + s.hidden + 1 : p;
 }
-__device__ __forceinline__ int mlp_entry_words(const ThrlAgentSpec& s) { return s.kind == THRL_AGENT_ACTORCRITIC ? 4 : 3; }
+__device__ __forceinline__ int mlp_entry_words(const ThrlAgentSpec& s) { return s.kind == THRL_AGENT_REINFORCE ? 3 : 4; }
+// state_dict order -> staged order: fc_pi.weight [A][H] is staged transposed [H][A]; CAC has no matrix head (identity)
+__device__ __forceinline__ int mlp_flat2st(const ThrlAgentSpec& s, int i) {
+  const int H = s.hidden, A = s.actions;
+  if (s.kind == THRL_AGENT_CAC || i < 2 * H || i >= 2 * H + A * H) return i;
+  const int e = i - 2 * H, k = e / H, j = e - k * H;
+  return 2 * H + j * A + k;
+}
 
 // expf with the oracle's operation sequence (Cody-Waite + Cephes polynomial)
 __device__ __forceinline__ float det_expf(float x) {
@@ -120,16 +129,10 @@ __device__ __forceinline__ float ac_value_warp(const float* wv, float bv, const 
 
 // clip_grad_norm_(1.0) + one Adam step (oracle mlp_clip_adam).  gs: gradient in the staged layout.
 __device__ inline void mlp_clip_adam_warp(float* blk, const ThrlAgentSpec& spec, float* sp, const float* gs, int lane) {
-  const int H = spec.hidden, A = spec.actions;
   const int P = mlp_P(spec);
   float *am = blk + P, *av = blk + 2 * (size_t)P;
   int32_t* hdr = reinterpret_cast<int32_t*>(blk + 3 * (size_t)P);
-  // Flat index i runs over the state_dict order as in the oracle; flat2st maps it to the staged layout (fc_pi.weight transposed)
-  auto flat2st = [&](int i) {
-    if (i < 2 * H || i >= 2 * H + A * H) return i;
-    const int e = i - 2 * H, k = e / H, j = e - k * H;
-    return 2 * H + j * A + k;
-  };
+  auto flat2st = [&](int i) { return mlp_flat2st(spec, i); };  // state_dict order (oracle) -> staged layout
   __syncwarp();
   double part = 0.0;
   for (int i = lane; i < P; i += 32) { const double gd = (double)gs[flat2st(i)]; part = __dadd_rn(part, __dmul_rn(gd, gd)); }
@@ -307,6 +310,125 @@ __device__ inline void ac_train_warp(float* blk, const ThrlAgentSpec& spec, int 
   mlp_clip_adam_warp(blk, spec, sp, gs, lane);
 }
 
+// ---- CAC (agents.py:333-417): deterministic transcendentals with the oracle's operation sequences
+__device__ __forceinline__ float det_tanhf(float x) {
+  const float ax = fabsf(x);
+  float t;
+  if (ax < 0.1f) {
+    const float x2 = __fmul_rn(ax, ax);
+    float p = -17.0f / 315.0f;
+    p = __fadd_rn(__fmul_rn(p, x2), 2.0f / 15.0f);
+    p = __fsub_rn(__fmul_rn(p, x2), 1.0f / 3.0f);
+    p = __fmul_rn(p, x2);
+    p = __fmul_rn(p, ax);
+    t = __fadd_rn(ax, p);
+  } else {
+    const float e = det_expf(__fmul_rn(-2.0f, ax));
+    t = __fdiv_rn(__fsub_rn(1.0f, e), __fadd_rn(1.0f, e));
+  }
+  return x < 0.0f ? -t : t;
+}
+__device__ __forceinline__ float det_sigmoidf(float x) {
+  if (x >= 0.0f) { const float e = det_expf(-x); return __fdiv_rn(1.0f, __fadd_rn(1.0f, e)); }
+  const float e = det_expf(x);
+  return __fdiv_rn(e, __fadd_rn(1.0f, e));
+}
+__device__ __forceinline__ float det_softplusf(float x) {
+  if (x > 20.0f) return x;
+  const float e = det_expf(-fabsf(x));
+  const float l = (float)det_log(__dadd_rn(1.0, (double)e));
+  return __fadd_rn(x > 0.0f ? x : 0.0f, l);
+}
+// staged CAC parameters: w1 b1 | wmu bmu | wsd bsd | wv bv
+__device__ __forceinline__ float cac_head(const float* w, const float* hs, int H, int lane) { return ac_value_warp(w, w[H], hs, H, lane); }
+
+// CAC.sample_action (agents.py:374-378) for a standard normal deviate z; warp-cooperative, every lane returns the action
+__device__ inline float cac_action_warp(const float* sp, int H, float s, float* hs, double z, int lane) {
+  mlp_hidden_warp(sp, H, s, hs, lane);
+  const float zmu = cac_head(sp + 2 * H, hs, H, lane), zsd = cac_head(sp + 3 * H + 1, hs, H, lane);
+  const float mu = __fmul_rn(4.0f, det_tanhf(zmu)), sd = det_softplusf(zsd);
+  return det_sigmoidf(__fadd_rn(mu, __fmul_rn(sd, (float)z)));
+}
+
+// CAC.train_net (agents.py:391-417); closed form of the [N,N] loss via five moments, see oracle cac_train.
+__device__ inline void cac_train_warp(float* blk, const ThrlAgentSpec& spec, int cap, int head, int N, float* sp, float* gs,
+                                      float* hs, int lane) {
+  const int H = spec.hidden;
+  const int P = mlp_P(spec), EW = mlp_entry_words(spec);
+  const float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
+  const float *wmu = sp + 2 * H, *wsd = wmu + H + 1, *wv = wsd + H + 1;
+  float *gw1 = gs, *gb1 = gs + H, *gwmu = gs + 2 * H, *gwsd = gwmu + H + 1, *gwv = gwsd + H + 1;
+  for (int i = lane; i < P; i += 32) gs[i] = 0.0f;
+  const float gam = (float)spec.gamma;
+  double Sr = 0.0, Sl = 0.0, Sl2 = 0.0, Srl = 0.0, Srl2 = 0.0;  // every lane the same values, same order
+  for (int j = 0; j < N; ++j) {
+    int sl = head + j;
+    if (sl >= cap) sl -= cap;
+    const float a_ = __fadd_rn(5e-5f, __fmul_rn(__fsub_rn(1.0f, 1e-4f), buf[(size_t)sl * EW + 1]));
+    const float ratio = __fdiv_rn(a_, __fsub_rn(1.0f, a_));
+    const double l = (double)(float)det_log((double)ratio), r = (double)buf[(size_t)sl * EW + 2];
+    Sr = __dadd_rn(Sr, r);
+    Sl = __dadd_rn(Sl, l);
+    Sl2 = __dadd_rn(Sl2, __dmul_rn(l, l));
+    Srl = __dadd_rn(Srl, __dmul_rn(r, l));
+    Srl2 = __dadd_rn(Srl2, __dmul_rn(__dmul_rn(r, l), l));
+  }
+  const double dN = (double)N, invN2 = __ddiv_rn(1.0, __dmul_rn(dN, dN));
+  for (int i = 0; i < N; ++i) {
+    int sl = head + i;
+    if (sl >= cap) sl -= cap;
+    const float s = buf[(size_t)sl * EW], s2 = buf[(size_t)sl * EW + 3];
+    mlp_hidden_warp(sp, H, s2, hs, lane);
+    const float vp = cac_head(wv, hs, H, lane);
+    mlp_hidden_warp(sp, H, s, hs, lane);
+    const float zmu = cac_head(wmu, hs, H, lane), zsd = cac_head(wsd, hs, H, lane), v = cac_head(wv, hs, H, lane);
+    const float t = det_tanhf(zmu), mu = __fmul_rn(4.0f, t), sd = det_softplusf(zsd);
+    const float d = __fsub_rn(__fmul_rn(gam, vp), v);
+    const double dd = (double)d, dmu = (double)mu, dsd = (double)sd;
+    const double A0 = __dadd_rn(Sr, __dmul_rn(dN, dd));
+    const double A1 = __dadd_rn(__dsub_rn(Srl, __dmul_rn(dmu, Sr)), __dmul_rn(dd, __dsub_rn(Sl, __dmul_rn(dN, dmu))));
+    const double A2 = __dadd_rn(__dadd_rn(__dsub_rn(Srl2, __dmul_rn(__dmul_rn(2.0, dmu), Srl)), __dmul_rn(__dmul_rn(dmu, dmu), Sr)),
+                                __dmul_rn(dd, __dadd_rn(__dsub_rn(Sl2, __dmul_rn(__dmul_rn(2.0, dmu), Sl)), __dmul_rn(__dmul_rn(dN, dmu), dmu))));
+    const float gmu = (float)__dmul_rn(-__ddiv_rn(A1, __dmul_rn(dsd, dsd)), invN2);
+    const float gsd = (float)__dmul_rn(-__dsub_rn(__ddiv_rn(A2, __dmul_rn(__dmul_rn(dsd, dsd), dsd)), __ddiv_rn(A0, dsd)), invN2);
+    const float cv = (float)__dmul_rn(__dmul_rn(-2.0, A0), invN2);
+    const float cvp = __fmul_rn(-gam, cv);
+    const float dzmu = __fmul_rn(gmu, __fmul_rn(4.0f, __fsub_rn(1.0f, __fmul_rn(t, t))));
+    const float dzsd = __fmul_rn(gsd, det_sigmoidf(zsd));
+    for (int jh = lane; jh < H; jh += 32) {
+      const float hj = hs[jh];
+      gwmu[jh] = __fadd_rn(gwmu[jh], __fmul_rn(dzmu, hj));
+      gwsd[jh] = __fadd_rn(gwsd[jh], __fmul_rn(dzsd, hj));
+      gwv[jh] = __fadd_rn(gwv[jh], __fmul_rn(cv, hj));
+      float dh = __fmul_rn(dzmu, wmu[jh]);
+      dh = __fadd_rn(dh, __fmul_rn(dzsd, wsd[jh]));
+      dh = __fadd_rn(dh, __fmul_rn(cv, wv[jh]));
+      if (hj > 0.0f) {
+        gw1[jh] = __fadd_rn(gw1[jh], __fmul_rn(dh, s));
+        gb1[jh] = __fadd_rn(gb1[jh], dh);
+      }
+    }
+    if (lane == 0) {
+      gwmu[H] = __fadd_rn(gwmu[H], dzmu);
+      gwsd[H] = __fadd_rn(gwsd[H], dzsd);
+      gwv[H] = __fadd_rn(gwv[H], cv);
+    }
+    mlp_hidden_warp(sp, H, s2, hs, lane);  // value head at s'_i
+    for (int jh = lane; jh < H; jh += 32) {
+      const float hj = hs[jh];
+      gwv[jh] = __fadd_rn(gwv[jh], __fmul_rn(cvp, hj));
+      const float dh = __fmul_rn(cvp, wv[jh]);
+      if (hj > 0.0f) {
+        gw1[jh] = __fadd_rn(gw1[jh], __fmul_rn(dh, s2));
+        gb1[jh] = __fadd_rn(gb1[jh], dh);
+      }
+    }
+    if (lane == 0) gwv[H] = __fadd_rn(gwv[H], cvp);
+    __syncwarp();
+  }
+  mlp_clip_adam_warp(blk, spec, sp, gs, lane);
+}
+
 template <typename QT>
 __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constant__ MixedParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -338,7 +460,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
   unsigned char* slot = smem + p.cta_bytes + (size_t)warp * p.warp_bytes;
   double* P = reinterpret_cast<double*>(slot + p.off_P);          // [Hp] price ring (QTable batches)
   uint8_t* act = slot + p.off_act;                                // [n][Hp]
-  int16_t* pre = reinterpret_cast<int16_t*>(slot + p.off_pre);    // [T][n] forced action, -1 greedy (QTable), -2 sample (MLP)
+  int32_t* pre = reinterpret_cast<int32_t*>(slot + p.off_pre);    // [T][n] forced action (CAC: float32 bits), -1 greedy (QTable), -2 sample (MLP)
   double* newa = reinterpret_cast<double*>(slot + p.off_newa);    // [T]
   uint16_t* rowbuf = reinterpret_cast<uint16_t*>(slot + p.off_row);
   QT* oldv = reinterpret_cast<QT*>(slot + p.off_old);
@@ -382,14 +504,10 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
       if (s.kind == THRL_AGENT_QTABLE) continue;
-      const int H = s.hidden, A = s.actions, Pn = mlp_P(s);
+      const int Pn = mlp_P(s);
       const float* src = slab + s.mlp_offset;
       float* dst = par + p.par_off[i];
-      for (int e2 = lane; e2 < Pn; e2 += 32) {
-        int st = e2;
-        if (e2 >= 2 * H && e2 < 2 * H + A * H) { const int q2 = e2 - 2 * H, k = q2 / H, j = q2 - k * H; st = 2 * H + j * A + k; }
-        dst[st] = src[e2];
-      }
+      for (int e2 = lane; e2 < Pn; e2 += 32) dst[mlp_flat2st(s, e2)] = src[e2];
     }
     double price = p.price[r];
     int pos = 0;
@@ -431,7 +549,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
           const int ra = (int)__umulhi(x[2 * (i & 1) + 1], (uint32_t)G.agent[i].actions);
           v = u < hpw[i * 5 + 4] ? ra : -1;
         }
-        pre[idx] = (int16_t)v;
+        pre[idx] = v;
       }
       if (p.noisy) {
         for (int t = lane; t < T; t += 32) {
@@ -454,7 +572,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
       // ---- the episode (trainer.py:50-67)
       double rlog = 0.0, alog = 0.0;
       for (int t = 0; t < T; ++t) {
-        int k = is_agent ? (int)pre[t * n + lane] : 0;
+        int k = is_agent ? pre[t * n + lane] : 0;
         int arow = 0;
         if (is_agent && k == -1) arow = act_row(price, my_msf, my_sf);
         // greedy QTable actions: first argmax of the live (frozen within the episode) table row (agents.py:84-88)
@@ -473,9 +591,17 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
           const int i = __ffs(samp) - 1;
           samp &= samp - 1;
           const ThrlAgentSpec& s = G.agent[i];
-          mlp_forward_warp(par + p.par_off[i], s.hidden, s.actions, (float)price, hs, ps, lane);
           uint32_t x[4];
           philox4x32_10(gid, eabs, (uint32_t)t, (uint32_t)(i >> 1) | (kStreamAct << 16), p.k0, p.k1, x);
+          if (s.kind == THRL_AGENT_CAC) {  // sigmoid(Normal(mu, std).sample()) (agents.py:374-378)
+            const unsigned long long m = ((unsigned long long)x[2 * (i & 1)] << 21) | (unsigned long long)(x[2 * (i & 1) + 1] >> 11);
+            const double z = det_norminv(((double)m + 0.5) * (1.0 / 9007199254740992.0));
+            const float af = cac_action_warp(par + p.par_off[i], s.hidden, (float)price, hs, z, lane);
+            if (lane == i) k = __float_as_int(af);
+            __syncwarp();
+            continue;
+          }
+          mlp_forward_warp(par + p.par_off[i], s.hidden, s.actions, (float)price, hs, ps, lane);
           const float u = __fmul_rn((float)(x[2 * (i & 1)] >> 8), 1.0f / 16777216.0f);
           float c = 0.0f;
           int ks = s.actions - 1;
@@ -486,8 +612,18 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
           if (lane == i) k = ks;
           __syncwarp();
         }
-        double aq = 0.0;
-        if (is_agent) aq = lutAQ[my_lut + k];
+        double aq = 0.0, xt = 0.0;
+        if (is_agent) {
+          if (my_kind == THRL_AGENT_CAC) {  // CAC.scale (agents.py:368-372): action * (hi - lo) + lo, action a float32 in (0,1)
+            const ThrlAgentSpec& s = G.agent[lane];
+            const double x = __dadd_rn(__dmul_rn((double)__int_as_float(k), __dsub_rn(s.action_hi, s.action_lo)), s.action_lo);
+            aq = __dmul_rn(__ddiv_rn(G.a, G.b), x);
+            xt = __ddiv_rn(x, (double)T);
+          } else {
+            aq = lutAQ[my_lut + k];
+            xt = lutXT[my_lut + k];
+          }
+        }
         double Q = 0.0;
         for (int i = 0; i < n; ++i) Q = __dadd_rn(Q, shfl_d(aq, i));
         const double na = p.noisy ? newa[t] : G.a;
@@ -498,7 +634,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
         if (nxt == Hp) nxt = 0;
         if (is_agent) {
           rlog = __dadd_rn(rlog, __ddiv_rn(rew, (double)T));
-          alog = __dadd_rn(alog, lutXT[my_lut + k]);
+          alog = __dadd_rn(alog, xt);
           if (my_kind == THRL_AGENT_QTABLE) {
             act[lane * Hp + pos] = (uint8_t)k;
             my_len = my_len < my_cap ? my_len + 1 : my_cap;
@@ -544,7 +680,8 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
           int32_t* hdr = reinterpret_cast<int32_t*>(blk + 3 * (size_t)Pn);
           const int len = hdr[1], head = hdr[2];
           if (len >= s.min_memory) {
-            if (s.kind == THRL_AGENT_ACTORCRITIC) ac_train_warp(blk, s, cap, head, len, par + p.par_off[i], grad, hs, ps, lane);
+            if (s.kind == THRL_AGENT_CAC) cac_train_warp(blk, s, cap, head, len, par + p.par_off[i], grad, hs, lane);
+            else if (s.kind == THRL_AGENT_ACTORCRITIC) ac_train_warp(blk, s, cap, head, len, par + p.par_off[i], grad, hs, ps, lane);
             else mlp_train_warp(blk, s, cap, head, len, par + p.par_off[i], grad, hs, ps, lane);
             if (lane == 0) { hdr[1] = 0; hdr[2] = 0; }  // :194 memory.empty()
             __syncwarp();
@@ -615,14 +752,10 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
       if (s.kind == THRL_AGENT_QTABLE) continue;
-      const int H = s.hidden, A = s.actions, Pn = mlp_P(s);
+      const int Pn = mlp_P(s);
       float* dstg = slab + s.mlp_offset;
       const float* srcs = par + p.par_off[i];
-      for (int e2 = lane; e2 < Pn; e2 += 32) {
-        int st = e2;
-        if (e2 >= 2 * H && e2 < 2 * H + A * H) { const int q2 = e2 - 2 * H, k = q2 / H, j = q2 - k * H; st = 2 * H + j * A + k; }
-        dstg[e2] = srcs[st];
-      }
+      for (int e2 = lane; e2 < Pn; e2 += 32) dstg[e2] = srcs[mlp_flat2st(s, e2)];
     }
     if (is_agent) p.eps[r * n + lane] = hpw[lane * 5 + 4];
     if (lane == 0) p.price[r] = price;

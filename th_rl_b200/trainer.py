@@ -37,8 +37,7 @@ def create_game(configpath):
     agents = []
     for agent in config["agents"]:
         if agent["name"] not in AGENTS:
-            raise NameError("name %r is not defined (th_rl_b200 implements QTable, Reinforce and ActorCritic agents; CAC is "
-                            "the next row, see DESIGN.md)" % agent["name"])
+            raise NameError("name %r is not defined (the reference's agents are QTable, Reinforce, ActorCritic and CAC)" % agent["name"])
         agents.append(AGENTS[agent["name"]](**agent))
     assert len(agents) == config["environment"]["nplayers"], "Bad config. Check number of agents."
     if config["environment"]["name"] not in ENVIRONMENTS:

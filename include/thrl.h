@@ -179,6 +179,10 @@ int thrl_game_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64
  * rewards/actions [R][iters*T][n] as utils.play_game returns them per run. */
 int thrl_greedy_eval(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, int32_t iters,
                      const double* price0, double* rewards, double* actions, void* stream);
+/* ABI 2: the same for games with MLP agents (get_action of Reinforce / ActorCritic = argmax of pi, of CAC = sigmoid(mu)); mlp is
+ * the run slab of ThrlScanArgs.mlp (read only); q / mlp may be NULL when the game has no Q-tables / no MLP agents. */
+int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
+                         int32_t iters, const double* price0, double* rewards, double* actions, void* stream);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 int64_t thrl_launch_count(void);
 

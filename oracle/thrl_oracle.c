@@ -899,12 +899,15 @@ int thrl_oracle_game_init(const ThrlGame* G, int64_t n_runs, int64_t run_id0, ui
   return THRL_OK;
 }
 
-/* utils.py:27-47 play_game with agents.py:91-92 get_action (float64 encode of the state, no exploration,
- * no update).  price0[r][it] replaces environment.reset()'s draw.  rewards/actions: [R][iters*T][n]. */
-int thrl_oracle_greedy_eval(const ThrlGame* G, int64_t n_runs, int32_t table_dtype, const void* q, int32_t iters,
-                            const double* price0, double* rewards, double* actions) {
+/* utils.py:27-47 play_game with each agent's get_action: QTable agents.py:91-92 (float64 encode of the state, first argmax);
+ * Reinforce / ActorCritic agents.py:165-168 / :275-278 (argmax of pi(float32 state)); CAC agents.py:380-384
+ * (Normal(mu, 0).sample() == mu, so the action is sigmoid(4 tanh(fc_mu(h)))).  No exploration, no update.
+ * price0[r][it] replaces environment.reset()'s draw.  rewards/actions: [R][iters*T][n]. */
+int thrl_oracle_greedy_eval_mlp(const ThrlGame* G, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
+                                int32_t iters, const double* price0, double* rewards, double* actions) {
   const int n = G->n_agents, T = G->max_steps;
   const size_t esz = table_dtype == THRL_F64 ? 8 : 4;
+  float hbuf[1024 + 512];
   for (int64_t r = 0; r < n_runs; ++r) {
     for (int it = 0; it < iters; ++it) {
       double price = price0[(size_t)r * iters + it];
@@ -914,11 +917,30 @@ int thrl_oracle_greedy_eval(const ThrlGame* G, int64_t n_runs, int32_t table_dty
         double Q = 0.0;
         for (int i = 0; i < n; ++i) {
           const ThrlAgentSpec* s = &G->agent[i];
-          Table tb = {table_dtype, (char*)q + ((size_t)r * G->run_stride + s->table_offset) * esz, s->states + 1,
-                      s->actions};
-          int64_t row = upd_row(price, s);
-          if (row < 0 || row > s->states) return THRL_ERR_BAD_CONFIG;
-          xs[i] = scale_action(row_argmax(&tb, row), s);
+          if (s->kind == THRL_AGENT_QTABLE) {
+            Table tb = {table_dtype, (char*)q + ((size_t)r * G->run_stride + s->table_offset) * esz, s->states + 1,
+                        s->actions};
+            int64_t row = upd_row(price, s);
+            if (row < 0 || row > s->states) return THRL_ERR_BAD_CONFIG;
+            xs[i] = scale_action(row_argmax(&tb, row), s);
+          } else {
+            if (s->hidden > 1024 || s->actions > 256) return THRL_ERR_BAD_CONFIG;
+            const float* par = mlp + (size_t)r * G->mlp_stride + s->mlp_offset;
+            float* h = hbuf;
+            float* prob = hbuf + 1024;
+            if (s->kind == THRL_AGENT_CAC) {
+              float zmu, zsd, v;
+              mlp_hidden(par, s->hidden, (float)price, h);
+              cac_heads(par, s->hidden, h, &zmu, &zsd, &v);
+              const float af = det_sigmoidf(4.0f * det_tanhf(zmu));
+              xs[i] = (double)af * (s->action_hi - s->action_lo) + s->action_lo;
+            } else {
+              mlp_forward(par, s->hidden, s->actions, (float)price, h, prob);
+              int best = 0;
+              for (int k = 1; k < s->actions; ++k) if (prob[k] > prob[best]) best = k; /* torch.argmax: first maximal index */
+              xs[i] = (double)best / (double)s->actions * (s->action_hi - s->action_lo) + s->action_lo;
+            }
+          }
           Aq[i] = ab * xs[i];
           Q = Q + Aq[i];
         }
@@ -931,6 +953,10 @@ int thrl_oracle_greedy_eval(const ThrlGame* G, int64_t n_runs, int32_t table_dty
     }
   }
   return THRL_OK;
+}
+int thrl_oracle_greedy_eval(const ThrlGame* G, int64_t n_runs, int32_t table_dtype, const void* q, int32_t iters,
+                            const double* price0, double* rewards, double* actions) {
+  return thrl_oracle_greedy_eval_mlp(G, n_runs, table_dtype, q, NULL, iters, price0, rewards, actions);
 }
 
 /* Same checks / layout as thrl_game_layout in the product, restated so the oracle stands alone. */

@@ -197,13 +197,12 @@ def test_greedy_eval_matches_oracle(golden):
     torch, oracle, engine = _mods()
     cfg = golden["config"]
     game = oracle.layout(cfg)
-    if game.mlp_stride:
-        pytest.skip("greedy evaluation covers QTable agents")
-    q0, c0, eps0, p0 = oracle.init(game, 20, seed=3, dtype=np.float64, eps0=abi.eps0_from_config(cfg))
+    q0, c0, eps0, p0, *rest = oracle.init(game, 20, seed=3, dtype=np.float64, eps0=abi.eps0_from_config(cfg))
+    mlp0 = rest[0] if rest else None
     price0 = np.random.default_rng(0).uniform(0, game.a, size=(20, 3))
-    ref_a, ref_r = oracle.greedy_eval(game, q0, price0)
+    ref_a, ref_r = oracle.greedy_eval(game, q0, price0, mlp=mlp0)
     b = engine.RunBatch(cfg, 20, dtype=torch.float64)
-    b.load_state(q0, eps0, p0)
+    b.load_state(q0, eps0, p0, mlp=mlp0)
     a, r = b.greedy_eval(price0)
     torch.cuda.synchronize()
     assert np.array_equal(a.cpu().numpy(), ref_a) and np.array_equal(r.cpu().numpy(), ref_r)

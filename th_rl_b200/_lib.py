@@ -47,6 +47,9 @@ def lib():
     L.thrl_greedy_eval.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p]
     L.thrl_greedy_eval.restype = C.c_int
+    L.thrl_greedy_eval_mlp.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.thrl_greedy_eval_mlp.restype = C.c_int
     L.thrl_launch_count.restype = C.c_int64
     _lib = L
     return L

@@ -562,23 +562,60 @@ int thrl_game_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64
 
 int thrl_greedy_eval(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, int32_t iters,
                      const double* price0, double* rewards, double* actions, void* stream) {
-  if (!game || !q || !price0 || !rewards || !actions) return fail(THRL_ERR_BAD_ARGS, "thrl_greedy_eval: NULL argument");
+  return thrl_greedy_eval_mlp(game, n_runs, table_dtype, q, nullptr, iters, price0, rewards, actions, stream);
+}
+
+int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
+                         int32_t iters, const double* price0, double* rewards, double* actions, void* stream) {
+  if (!game || !price0 || !rewards || !actions) return fail(THRL_ERR_BAD_ARGS, "thrl_greedy_eval: NULL argument");
   if (table_dtype != THRL_F32 && table_dtype != THRL_F64) return fail(THRL_ERR_BAD_ARGS, "table_dtype=%d", table_dtype);
-  thrl::EvalParams p;
-  memset(&p, 0, sizeof(p));
-  p.game = *game;
-  int rc = validate_layout(&p.game);
+  ThrlGame G = *game;
+  int rc = validate_layout(&G);
   if (rc) return rc;
-  if (p.game.mlp_stride > 0) return fail(THRL_ERR_UNSUPPORTED, "thrl_greedy_eval covers QTable agents only");
+  if (G.run_stride > 0 && !q) return fail(THRL_ERR_BAD_ARGS, "q must not be NULL (the game has Q-tables)");
+  if (G.mlp_stride > 0 && !mlp) return fail(THRL_ERR_BAD_ARGS, "the game has MLP agents but mlp is NULL");
   if (n_runs <= 0 || iters <= 0) return THRL_OK;
   DeviceInfo dev;
   rc = device_info(&dev);
   if (rc) return rc;
-  p.n_runs = n_runs; p.iters = iters; p.q = q; p.price0 = price0; p.rewards = rewards; p.actions = actions;
   long long blocks = (n_runs + 7) / 8;
   if (blocks > dev.sms * 8) blocks = dev.sms * 8;
-  if (table_dtype == THRL_F64) thrl::greedy_eval<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
-  else thrl::greedy_eval<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  if (G.mlp_stride == 0) {
+    thrl::EvalParams p;
+    memset(&p, 0, sizeof(p));
+    p.game = G;
+    p.n_runs = n_runs; p.iters = iters; p.q = q; p.price0 = price0; p.rewards = rewards; p.actions = actions;
+    if (table_dtype == THRL_F64) thrl::greedy_eval<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    else thrl::greedy_eval<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  } else {
+    thrl::EvalMixedParams* p = new thrl::EvalMixedParams();
+    std::unique_ptr<thrl::EvalMixedParams> hold(p);
+    memset(p, 0, sizeof(*p));
+    p->game = G;
+    p->n_runs = n_runs; p->iters = iters; p->q = q; p->mlp = mlp; p->price0 = price0; p->rewards = rewards; p->actions = actions;
+    int par = 0, hmax = 0, amax = 0;
+    for (int i = 0; i < G.n_agents; ++i) {
+      const ThrlAgentSpec& s = G.agent[i];
+      if (s.kind == THRL_AGENT_QTABLE) continue;
+      const int P = s.kind == THRL_AGENT_CAC ? 5 * s.hidden + 3 : 2 * s.hidden + s.actions * s.hidden + s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? s.hidden + 1 : 0);
+      p->par_off[i] = par;
+      par += align_up(P, 4);
+      if (s.hidden > hmax) hmax = s.hidden;
+      if (s.actions > amax) amax = s.actions;
+    }
+    p->off_par = 0;
+    p->off_h = align_up(par * 4, 16);
+    p->warp_bytes = p->off_h + align_up((hmax + amax + 32) * 4, 16);
+    int warps = dev.smem_optin / p->warp_bytes;
+    if (warps < 1) return fail(THRL_ERR_UNSUPPORTED, "one run's MLP agents need %d B of shared memory", p->warp_bytes);
+    if (warps > 8) warps = 8;
+    const size_t smem = (size_t)warps * p->warp_bytes;
+    blocks = (n_runs + warps - 1) / warps;
+    if (blocks > dev.sms) blocks = dev.sms;
+    auto kern = table_dtype == THRL_F64 ? thrl::greedy_eval_mixed<double> : thrl::greedy_eval_mixed<float>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, warps * 32, smem, (cudaStream_t)stream>>>(*p);
+  }
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
   return THRL_OK;

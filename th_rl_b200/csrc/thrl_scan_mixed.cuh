@@ -773,4 +773,86 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------- greedy evaluation with MLP agents (utils.py:27-47)
+struct EvalMixedParams {
+  ThrlGame game;
+  long long n_runs;
+  int iters;
+  const void* q;
+  const float* mlp;
+  const double* price0;
+  double* rewards;
+  double* actions;
+  int warp_bytes, off_par, off_h;
+  int par_off[THRL_MAX_AGENTS];
+};
+
+// play_game with every agent's get_action: QTable first argmax on the f64 encode (agents.py:91-92); Reinforce / ActorCritic
+// argmax of pi(float32 state) (agents.py:165-168, 275-278); CAC sigmoid(4 tanh(fc_mu(h))) (agents.py:380-384).  Warp per run.
+template <typename QT>
+__global__ void __launch_bounds__(256) greedy_eval_mixed(const __grid_constant__ EvalMixedParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ThrlGame& G = p.game;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = G.n_agents, T = G.max_steps;
+  unsigned char* slot = smem + (size_t)warp * p.warp_bytes;
+  float* par = reinterpret_cast<float*>(slot + p.off_par);
+  float* hs = reinterpret_cast<float*>(slot + p.off_h);
+  int Hmax = 0;
+  for (int i = 0; i < n; ++i) if (G.agent[i].kind != THRL_AGENT_QTABLE && G.agent[i].hidden > Hmax) Hmax = G.agent[i].hidden;
+  float* ps = hs + Hmax;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long total = ((long long)gridDim.x * blockDim.x) >> 5;
+  const double ab = __ddiv_rn(G.a, G.b);
+  for (long long r = gw; r < p.n_runs; r += total) {
+    const QT* tab = reinterpret_cast<const QT*>(p.q) + r * G.run_stride;
+    const float* slab = p.mlp + r * G.mlp_stride;
+    __syncwarp();
+    for (int i = 0; i < n; ++i) {
+      const ThrlAgentSpec& s = G.agent[i];
+      if (s.kind == THRL_AGENT_QTABLE) continue;
+      const int Pn = mlp_P(s);
+      for (int e2 = lane; e2 < Pn; e2 += 32) par[p.par_off[i] + mlp_flat2st(s, e2)] = slab[s.mlp_offset + e2];
+    }
+    __syncwarp();
+    for (int it = 0; it < p.iters; ++it) {
+      double price = p.price0[r * p.iters + it];
+      for (int t = 0; t < T; ++t) {
+        double Q = 0.0, my_x = 0.0, my_aq = 0.0;
+        for (int i = 0; i < n; ++i) {
+          const ThrlAgentSpec& s = G.agent[i];
+          double x;
+          if (s.kind == THRL_AGENT_QTABLE) {
+            const int row = upd_row(price, s.max_state, (double)s.states);
+            const int k = row_argmax(tab + s.table_offset + (size_t)row * s.actions, s.actions, lane);
+            x = scale_action(k, s.actions, s.action_lo, s.action_hi);
+          } else if (s.kind == THRL_AGENT_CAC) {
+            const float* sp = par + p.par_off[i];
+            mlp_hidden_warp(sp, s.hidden, (float)price, hs, lane);
+            const float zmu = cac_head(sp + 2 * s.hidden, hs, s.hidden, lane);
+            const float af = det_sigmoidf(__fmul_rn(4.0f, det_tanhf(zmu)));
+            x = __dadd_rn(__dmul_rn((double)af, __dsub_rn(s.action_hi, s.action_lo)), s.action_lo);
+          } else {
+            mlp_forward_warp(par + p.par_off[i], s.hidden, s.actions, (float)price, hs, ps, lane);
+            const int k = row_argmax(ps, s.actions, lane);  // torch.argmax: first maximal index
+            x = __dadd_rn(__dmul_rn(__ddiv_rn((double)k, (double)s.actions), __dsub_rn(s.action_hi, s.action_lo)), s.action_lo);
+            __syncwarp();
+          }
+          const double aq = __dmul_rn(ab, x);
+          Q = __dadd_rn(Q, aq);
+          if (lane == i) { my_x = x; my_aq = aq; }
+        }
+        const double pn = __dsub_rn(G.a, __dmul_rn(G.b, Q));
+        const double next_price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
+        if (lane < n) {
+          const long long o = ((r * p.iters + it) * T + t) * n + lane;
+          p.rewards[o] = __dmul_rn(next_price, my_aq);
+          p.actions[o] = my_x;
+        }
+        price = next_price;
+      }
+    }
+  }
+}
+
 }  // namespace thrl

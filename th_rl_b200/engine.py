@@ -184,8 +184,8 @@ class RunBatch:
         rewards = torch.empty((R, iters * T, n), dtype=torch.float64, device=self.device)
         actions = torch.empty((R, iters * T, n), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            check(lib().thrl_greedy_eval(C.byref(g), R, self.table_dtype, _dp(self.q), iters, _dp(p0), _dp(rewards),
-                                         _dp(actions), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            check(lib().thrl_greedy_eval_mlp(C.byref(g), R, self.table_dtype, _dp(self.q), _dp(self.mlp), iters, _dp(p0),
+                                             _dp(rewards), _dp(actions), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return actions, rewards
 
 

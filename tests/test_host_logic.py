@@ -202,3 +202,59 @@ def test_sharded_stats_allreduce_gloo_world2():
     whole = oracle.scan(game, q0, e0, p0, 3, seed=5, stats=True)
     assert np.array_equal(stats, whole.stats)
     assert np.array_equal(qhead, whole.q[:2])
+
+
+def test_c_abi_error_paths_need_no_device():
+    """Argument and configuration errors are reported (negative ThrlStatus + message) before any device access, so they can
+    be checked on a CPU-only box; a valid call on a box without a GPU fails loudly with THRL_ERR_NO_DEVICE (no fallback)."""
+    import ctypes as C
+    from th_rl_b200 import _lib
+    L = _lib.lib()
+    cfg = _cfg()
+    g = _lib.game_layout(cfg)
+    R, n = 2, 2
+    q = np.zeros((R, g.run_stride), np.float32)
+    eps = np.full((R, n), 0.5)
+    price = np.full((R,), 3.0)
+
+    def args(**kw):
+        a = abi.ThrlScanArgs()
+        a.game = C.pointer(g)
+        a.n_runs, a.epoch_begin, a.epoch_end = R, 0, 1
+        a.table_dtype, a.rng_mode = abi.THRL_F32, abi.THRL_RNG_PHILOX
+        a.q, a.eps, a.price = q.ctypes.data, eps.ctypes.data, price.ctypes.data
+        for k, v in kw.items():
+            setattr(a, k, v)
+        return a
+
+    def err():
+        return L.thrl_last_error().decode()
+
+    assert L.thrl_qtable_scan(None, None) == abi.THRL_ERR_BAD_ARGS
+    assert L.thrl_qtable_scan(C.byref(args(table_dtype=7)), None) == abi.THRL_ERR_BAD_ARGS and "table_dtype" in err()
+    assert L.thrl_qtable_scan(C.byref(args(rng_mode=9)), None) == abi.THRL_ERR_BAD_ARGS
+    assert L.thrl_qtable_scan(C.byref(args(eps=None)), None) == abi.THRL_ERR_BAD_ARGS
+    assert L.thrl_qtable_scan(C.byref(args(q=None)), None) == abi.THRL_ERR_BAD_ARGS and "q must not be NULL" in err()
+    assert L.thrl_qtable_scan(C.byref(args(rng_mode=abi.THRL_RNG_REPLAY_DRAWS)), None) == abi.THRL_ERR_BAD_ARGS  # no streams
+    assert L.thrl_qtable_scan(C.byref(args(n_log_runs=5)), None) == abi.THRL_ERR_BAD_ARGS
+    assert L.thrl_qtable_scan(C.byref(args(epoch_end=-1)), None) == abi.THRL_ERR_BAD_ARGS
+    bad = abi.game_from_config(_cfg(a=20))  # reference: IndexError on the first encode
+    a = args()
+    a.game = C.pointer(bad)
+    assert L.thrl_qtable_scan(C.byref(a), None) == abi.THRL_ERR_BAD_CONFIG and "IndexError" in err()
+    mixed = _cfg()
+    mixed["agents"][1] = dict(name="Reinforce", gamma=0.9, actions=5, states=1, action_range=[0.1, 0.2])
+    gm = _lib.game_layout(mixed)
+    a = args()
+    a.game = C.pointer(gm)
+    assert L.thrl_qtable_scan(C.byref(a), None) == abi.THRL_ERR_BAD_ARGS and "mlp" in err()
+    ent = abi.game_from_config(mixed)
+    ent.agent[1].entropy = 0.01
+    assert L.thrl_game_layout(C.byref(ent)) == abi.THRL_ERR_UNSUPPORTED and "entropy" in err()
+    assert L.thrl_qtable_scan(C.byref(args(n_runs=0)), None) == abi.THRL_OK  # nothing to do
+    import torch
+    if not torch.cuda.is_available():
+        assert L.thrl_qtable_scan(C.byref(args()), None) == abi.THRL_ERR_NO_DEVICE and "no CPU fallback" in err()
+        from th_rl_b200 import engine
+        with pytest.raises(RuntimeError):
+            engine.RunBatch(cfg, 4)

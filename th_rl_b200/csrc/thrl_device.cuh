@@ -114,6 +114,13 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
   return __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
 }
 
+__device__ __forceinline__ float shfl_xor_t(float v, int off) { return __shfl_xor_sync(kFull, v, off); }
+__device__ __forceinline__ double shfl_xor_t(double v, int off) {
+  const long long b = __double_as_longlong(v);
+  const int lo = __shfl_xor_sync(kFull, (int)b, off), hi = __shfl_xor_sync(kFull, (int)(b >> 32), off);
+  return __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
+}
+
 // fixed-point statistics (include/thrl.h THRL_STATS_*): exact integer sums, independent of run order and sharding
 __device__ __forceinline__ long long fx_round(double x) { return __double2ll_rn(x); }
 

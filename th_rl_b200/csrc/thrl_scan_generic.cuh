@@ -45,6 +45,8 @@ struct ScanParams {
   int gcap[THRL_MAX_AGENTS];  // rows 0..gcap_i-1 of agent i have a greedy-cache slot (rows the price can reach); others are uncached
   int Hp;          // ring slots = ring_len + 1
   int noisy;       // new_a varies per step (noise_prob > 0 or replay_new_a given)
+  int quarter;     // use the quarter-warp update path (n <= 8 and every agent has <= 128 actions)
+  int qchunks;     // ceil(max actions / 8), rounded up to a multiple of 4
 };
 
 // Per-run ring blob carried between calls when the game is not regular (include/thrl.h ThrlScanArgs.ring).
@@ -133,6 +135,27 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
       h[4] = p.eps[r * n + lane];
     }
     __syncwarp();
+    // Quarter-warp mapping for the update (n <= 8, every agent <= 128 actions): lanes 8q..8q+7 serve agents q and 4+q; the
+    // scalar work of four agents' update steps then runs SIMD across the quarters instead of once per agent on all 32 lanes.
+    const int ql = lane & 7, qq = lane >> 3;
+    int qa_A[2], qa_toff[2], qa_loff[2], qa_goff[2], qa_gcap[2];
+    double qa_alpha[2], qa_gamma[2], qa_oma[2];
+    bool qa_ok[2];
+#pragma unroll
+    for (int g2 = 0; g2 < 2; ++g2) {
+      const int i = 4 * g2 + qq;
+      qa_ok[g2] = i < n;
+      const int ii = qa_ok[g2] ? i : 0;
+      const ThrlAgentSpec& s = G.agent[ii];
+      qa_A[g2] = s.actions;
+      qa_toff[g2] = (int)s.table_offset;
+      qa_loff[g2] = 0; qa_goff[g2] = 0;
+      for (int j2 = 0; j2 < ii; ++j2) { qa_loff[g2] += G.agent[j2].actions; qa_goff[g2] += p.gcap[j2]; }
+      qa_gcap[g2] = p.gcap[ii];
+      qa_alpha[g2] = hpw[ii * 5 + 0];
+      qa_gamma[g2] = hpw[ii * 5 + 1];
+      qa_oma[g2] = __dsub_rn(1.0, qa_alpha[g2]);
+    }
     // greedy-action cache: 0xFF = not computed; filled on first visit, invalidated when the row is written
     for (int c = lane; c < p.rows_total; c += 32) Gc[c] = 0xFF;
     double price = p.price[r];
@@ -409,8 +432,61 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
             if (lane == 0 && st < p.gcap[i]) Gc[goff + st] = 0xFF;  // the row changed: its greedy action is recomputed on the next visit
           }
         };
-        group(std::integral_constant<int, 0>{});
-        if (n > 8) group(std::integral_constant<int, 8>{});
+        if (p.quarter) {
+          // ---- quarter-warp path: phase 1 loads + row max for up to 8 agents (two passes of four), phase 2 finishes + stores
+          QT qm[2];
+          bool qon[2];
+          int qjj[2];
+#pragma unroll
+          for (int g2 = 0; g2 < 2; ++g2) {
+            const int i = qa_ok[g2] ? 4 * g2 + qq : 0;
+            qon[g2] = qa_ok[g2] && des[i * 4 + 2] && j >= des[i * 4 + 3];
+            qjj[g2] = qon[g2] ? j - des[i * 4 + 3] : 0;
+            const int ns = rowbuf_all[i * p.row_stride + qjj[g2] + 1];
+            const QT* row = tab + (qa_toff[g2] + ns * qa_A[g2]);
+            QT m = NegInf<QT>::v();
+            for (int c0 = 0; c0 < p.qchunks; c0 += 4) {  // live table (:71): this lane's columns ql, ql+8, ...
+              QT v[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int kk = ql + 8 * (c0 + c);
+                v[c] = (qon[g2] && kk < qa_A[g2]) ? row[kk] : NegInf<QT>::v();
+              }
+              const QT m01 = v[0] > v[1] ? v[0] : v[1], m23 = v[2] > v[3] ? v[2] : v[3];
+              const QT m4 = m01 > m23 ? m01 : m23;
+              m = m4 > m ? m4 : m;
+            }
+            qm[g2] = m;
+          }
+#pragma unroll
+          for (int g2 = 0; g2 < 2; ++g2) {
+            QT m = qm[g2];
+#pragma unroll
+            for (int off = 4; off >= 1; off >>= 1) {  // max over the quarter's 8 lanes
+              const QT o = shfl_xor_t(m, off);
+              m = o > m ? o : m;
+            }
+            const int i = qa_ok[g2] ? 4 * g2 + qq : 0;
+            const int jj = qjj[g2];
+            int sl = des[i * 4 + 1] + jj;
+            if (sl >= Hp) sl -= Hp;
+            int sn = sl + 1;
+            if (sn == Hp) sn = 0;
+            const int st = rowbuf_all[i * p.row_stride + jj], k = act[i * Hp + sl];
+            const double reward = __dmul_rn(P[sn], lutAQ[qa_loff[g2] + k]);
+            const double nv = __dadd_rn(__dmul_rn(qa_oma[g2], (double)oldv_all[i * p.old_stride + jj]),
+                                        __dmul_rn(qa_alpha[g2], __dadd_rn(reward, __dmul_rn(qa_gamma[g2], (double)m))));
+            if (qon[g2] && (k & 7) == ql) {  // the lane of this quarter that owns column k: it alone reads or writes it
+              const int cell = qa_toff[g2] + st * qa_A[g2] + k;
+              tab[cell] = (QT)nv;
+              if (cnt) atomicAdd(cnt + cell, 1u);  // :76, fire-and-forget RED
+            }
+            if (qon[g2] && ql == 0 && st < qa_gcap[g2]) Gc[qa_goff[g2] + st] = 0xFF;  // greedy action recomputed on next visit
+          }
+        } else {
+          group(std::integral_constant<int, 0>{});
+          if (n > 8) group(std::integral_constant<int, 8>{});
+        }
       }
       for (int i = 0; i < n; ++i)
         if (des[i * 4 + 2] && lane == i) my_len = 0;  // :77 memory.empty()

@@ -144,7 +144,7 @@ void plan_generic(thrl::ScanParams* p, bool smem_tables, size_t elem) {
   int amax = 0;
   for (int i = 0; i < n; ++i) if (G.agent[i].actions > amax) amax = G.agent[i].actions;
   p->quarter = (n <= 8 && amax <= 128 && !getenv("THRL_NO_QUARTER")) ? 1 : 0;
-  p->qchunks = ((amax + 7) / 8 + 3) / 4 * 4;
+  p->qchunks = (amax + 7) / 8;
   p->cta_bytes = align_up(2 * lut * 8, 16);
   int o = 0;
   p->off_tab = o;

@@ -230,6 +230,62 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
           }
         }
         unsigned need = __ballot_sync(kFull, is_agent && k < 0);  // greedy action of that row not cached yet
+        if (need && p.quarter) {
+          // quarter-warp fill: quarter q computes the first argmax of agent 4*g2+q's row (8 lanes x qchunks columns); the loads
+          // of both passes are issued before any reduction
+          QT bv[2];
+          int bi[2], rr[2];
+          auto fill_rows = [&](auto ncc) {
+            constexpr int NC = decltype(ncc)::value;
+            QT v[2][NC];
+            bool mine[2];
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+              const int i = 4 * g2 + qq;
+              mine[g2] = qa_ok[g2] && ((need >> i) & 1u);
+              rr[g2] = __shfl_sync(kFull, arow, qa_ok[g2] ? i : 0);
+              const QT* row = tab + (qa_toff[g2] + (mine[g2] ? rr[g2] : 0) * qa_A[g2]);
+#pragma unroll
+              for (int c = 0; c < NC; ++c) {
+                const int kk = ql + 8 * c;
+                v[g2][c] = (mine[g2] && kk < qa_A[g2]) ? row[kk] : NegInf<QT>::v();
+              }
+            }
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+              bv[g2] = NegInf<QT>::v();
+              bi[g2] = 0x7fffffff;
+#pragma unroll
+              for (int c = 0; c < NC; ++c) {  // ascending columns, strict >: lowest index of this lane's maximum
+                const int kk = ql + 8 * c;
+                if (mine[g2] && kk < qa_A[g2] && (v[g2][c] > bv[g2] || bi[g2] == 0x7fffffff)) { bv[g2] = v[g2][c]; bi[g2] = kk; }
+              }
+            }
+          };
+          if (p.qchunks <= 4) fill_rows(std::integral_constant<int, 4>{});
+          else if (p.qchunks <= 8) fill_rows(std::integral_constant<int, 8>{});
+          else if (p.qchunks <= 12) fill_rows(std::integral_constant<int, 12>{});
+          else fill_rows(std::integral_constant<int, 16>{});
+#pragma unroll
+          for (int g2 = 0; g2 < 2; ++g2) {
+            if (!((need >> (4 * g2)) & 0xFu)) continue;
+            QT v = bv[g2];
+            int idx = bi[g2];
+#pragma unroll
+            for (int off = 4; off >= 1; off >>= 1) {  // numpy.argmax: first maximal index (agents.py:88)
+              const QT ov = shfl_xor_t(v, off);
+              const int oi = __shfl_xor_sync(kFull, idx, off);
+              if (oi != 0x7fffffff && (idx == 0x7fffffff || ov > v || (ov == v && oi < idx))) { v = ov; idx = oi; }
+            }
+            const int i = 4 * g2 + qq;
+            const bool mine = qa_ok[g2] && ((need >> i) & 1u);
+            if (mine && ql == 0 && rr[g2] < qa_gcap[g2]) Gc[qa_goff[g2] + rr[g2]] = (uint8_t)idx;
+            const int got = __shfl_sync(kFull, idx, 8 * (lane & 3));  // agent lane l is served by quarter l & 3 in pass l >> 2
+            if (is_agent && (lane >> 2) == g2 && k < 0) k = got;
+          }
+          __syncwarp();
+          need = 0;
+        }
         if (need) {
           do {  // up to four agents per round: all their row loads are issued before any comparison
             int ia[4], ra[4], bidx[4];
@@ -437,27 +493,34 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
           QT qm[2];
           bool qon[2];
           int qjj[2];
+          auto load_rows = [&](auto ncc) {
+            constexpr int NC = decltype(ncc)::value;  // columns per lane, compile time: every load is issued before any compare
+            QT v[2][NC];
 #pragma unroll
-          for (int g2 = 0; g2 < 2; ++g2) {
-            const int i = qa_ok[g2] ? 4 * g2 + qq : 0;
-            qon[g2] = qa_ok[g2] && des[i * 4 + 2] && j >= des[i * 4 + 3];
-            qjj[g2] = qon[g2] ? j - des[i * 4 + 3] : 0;
-            const int ns = rowbuf_all[i * p.row_stride + qjj[g2] + 1];
-            const QT* row = tab + (qa_toff[g2] + ns * qa_A[g2]);
-            QT m = NegInf<QT>::v();
-            for (int c0 = 0; c0 < p.qchunks; c0 += 4) {  // live table (:71): this lane's columns ql, ql+8, ...
-              QT v[4];
+            for (int g2 = 0; g2 < 2; ++g2) {
+              const int i = qa_ok[g2] ? 4 * g2 + qq : 0;
+              qon[g2] = qa_ok[g2] && des[i * 4 + 2] && j >= des[i * 4 + 3];
+              qjj[g2] = qon[g2] ? j - des[i * 4 + 3] : 0;
+              const int ns = rowbuf_all[i * p.row_stride + qjj[g2] + 1];
+              const QT* row = tab + (qa_toff[g2] + ns * qa_A[g2]);
 #pragma unroll
-              for (int c = 0; c < 4; ++c) {
-                const int kk = ql + 8 * (c0 + c);
-                v[c] = (qon[g2] && kk < qa_A[g2]) ? row[kk] : NegInf<QT>::v();
+              for (int c = 0; c < NC; ++c) {  // live table (:71): this lane's columns ql, ql+8, ...
+                const int kk = ql + 8 * c;
+                v[g2][c] = (qon[g2] && kk < qa_A[g2]) ? row[kk] : NegInf<QT>::v();
               }
-              const QT m01 = v[0] > v[1] ? v[0] : v[1], m23 = v[2] > v[3] ? v[2] : v[3];
-              const QT m4 = m01 > m23 ? m01 : m23;
-              m = m4 > m ? m4 : m;
             }
-            qm[g2] = m;
-          }
+#pragma unroll
+            for (int g2 = 0; g2 < 2; ++g2) {
+              QT m = v[g2][0];
+#pragma unroll
+              for (int c = 1; c < NC; ++c) m = v[g2][c] > m ? v[g2][c] : m;
+              qm[g2] = m;
+            }
+          };
+          if (p.qchunks <= 4) load_rows(std::integral_constant<int, 4>{});
+          else if (p.qchunks <= 8) load_rows(std::integral_constant<int, 8>{});
+          else if (p.qchunks <= 12) load_rows(std::integral_constant<int, 12>{});
+          else load_rows(std::integral_constant<int, 16>{});
 #pragma unroll
           for (int g2 = 0; g2 < 2; ++g2) {
             QT m = qm[g2];

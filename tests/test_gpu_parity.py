@@ -297,3 +297,61 @@ def test_initial_price_above_reachable_rows(kernel_choice):
     assert np.array_equal(out.trace_actions.cpu().numpy(), ref.trace_actions)
     assert np.array_equal(b.q.cpu().numpy(), ref.q)
     assert np.array_equal(b.counter.cpu().numpy().view(np.uint32), ref.counter)
+
+
+class _GuardedArena:
+    """One device allocation filled with a canary byte; every buffer handed to the library is carved out of it with a
+    4 KiB gap on both sides, so a store outside any buffer's bounds shows up as a damaged canary."""
+
+    CANARY, GAP = 0xA5, 4096
+
+    def __init__(self, torch, nbytes, device):
+        self.torch = torch
+        self.mem = torch.full((nbytes,), self.CANARY, dtype=torch.uint8, device=device)
+        self.used = torch.zeros((nbytes,), dtype=torch.bool, device=device)
+        self.off = self.GAP
+
+    def zeros(self, shape, dtype, device=None):
+        n = int(np.prod(shape)) * self.torch.empty((), dtype=dtype).element_size()
+        off = (self.off + 255) // 256 * 256
+        assert off + n + self.GAP <= self.mem.numel(), "arena too small"
+        self.off = off + n + self.GAP
+        self.used[off:off + n] = True
+        view = self.mem[off:off + n]
+        view.zero_()
+        return view.view(dtype).reshape(shape)
+
+    def adopt(self, t):
+        if t is None:
+            return None
+        v = self.zeros(tuple(t.shape), t.dtype)
+        v.copy_(t)
+        return v
+
+    def damaged(self):
+        return int(((self.mem != self.CANARY) & ~self.used).sum().item())
+
+
+GUARD_CASES = ["c1_example_2q_seed0", "noise_2q_seed3", "hetero_3q_seed4", "overflow_2q_seed5", "c4_8q_seed7",
+               "mixed_qr_small_seed9", "mixed_arq_seed12", "mixed_cc_seed14"]
+
+
+@pytest.mark.parametrize("case", GUARD_CASES)
+def test_no_store_outside_buffers(case, kernel_choice):
+    """Bounds check without a sanitizer: state and output buffers sit between canary bands; scans (a ragged run count,
+    chunked, sub-range) and the greedy evaluation must leave every canary byte intact."""
+    from conftest import load_golden
+    torch, oracle, engine = _mods()
+    cfg = load_golden(case)["config"]
+    R, E = 37, 2
+    b = engine.RunBatch(cfg, R, seed=41).init_device()
+    arena = _GuardedArena(torch, 96 << 20, b.device)
+    for name in ("q", "counter", "eps", "price", "hp", "mlp", "ring"):
+        setattr(b, name, arena.adopt(getattr(b, name)))
+    b._zeros = arena.zeros
+    b.scan(E, stats=True, trace=True, n_log_runs=3)
+    b.scan(1, run_range=(5, 30), stats=True, n_log_runs=2, advance=False)
+    b.scan(1, stats=True)
+    b.greedy_eval(np.full((R, 2), 3.0))
+    torch.cuda.synchronize()
+    assert arena.damaged() == 0

@@ -41,6 +41,7 @@ class RunBatch:
         self.run_id0 = int(run_id0)
         self.seed = int(seed)
         self.epoch = 0
+        self._zeros = torch.zeros  # allocator of the per-call output buffers (tests substitute a guard-banded arena)
         g, R, n = self.game, self.n_runs, self.game.n_agents
         with torch.cuda.device(self.device):
             self.q = torch.empty((R, g.run_stride), dtype=dtype, device=self.device)
@@ -115,16 +116,16 @@ class RunBatch:
             rra = dev_in(replay_ra, torch.int32, (R, E, T, n))
             rna = dev_in(replay_new_a, torch.float64, (R, E, T))
             if n_log_runs:
-                out.rewards_log = torch.zeros((n_log_runs, E, n), dtype=torch.float64, device=dev)
-                out.actions_log = torch.zeros((n_log_runs, E, n), dtype=torch.float64, device=dev)
+                out.rewards_log = self._zeros((n_log_runs, E, n), dtype=torch.float64, device=dev)
+                out.actions_log = self._zeros((n_log_runs, E, n), dtype=torch.float64, device=dev)
             if torch.is_tensor(stats):
                 out.stats = stats
             elif stats:
-                out.stats = torch.zeros((E, n, abi.THRL_STATS_K), dtype=torch.int64, device=dev)
+                out.stats = self._zeros((E, n, abi.THRL_STATS_K), dtype=torch.int64, device=dev)
             if trace:
-                out.trace_actions = torch.zeros((R, E, T, n), dtype=torch.int32, device=dev)
-                out.trace_rewards = torch.zeros((R, E, T, n), dtype=torch.float64, device=dev)
-                out.trace_prices = torch.zeros((R, E, T), dtype=torch.float64, device=dev)
+                out.trace_actions = self._zeros((R, E, T, n), dtype=torch.int32, device=dev)
+                out.trace_rewards = self._zeros((R, E, T, n), dtype=torch.float64, device=dev)
+                out.trace_prices = self._zeros((R, E, T), dtype=torch.float64, device=dev)
             a = abi.ThrlScanArgs()
             a.game = C.pointer(g)
             a.n_runs, a.run_id0 = R, self.run_id0 + rb
@@ -181,8 +182,8 @@ class RunBatch:
         g, R, n, T = self.game, self.n_runs, self.game.n_agents, self.game.max_steps
         p0 = torch.as_tensor(price0, dtype=torch.float64).reshape(R, -1).contiguous().to(self.device)
         iters = p0.shape[1]
-        rewards = torch.empty((R, iters * T, n), dtype=torch.float64, device=self.device)
-        actions = torch.empty((R, iters * T, n), dtype=torch.float64, device=self.device)
+        rewards = self._zeros((R, iters * T, n), dtype=torch.float64, device=self.device)
+        actions = self._zeros((R, iters * T, n), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             check(lib().thrl_greedy_eval_mlp(C.byref(g), R, self.table_dtype, _dp(self.q), _dp(self.mlp), iters, _dp(p0),
                                              _dp(rewards), _dp(actions), C.c_void_p(torch.cuda.current_stream().cuda_stream)))

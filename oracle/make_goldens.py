@@ -120,6 +120,26 @@ CASES = {
     "mixed_cc_seed14": (dict(agents=[dict(name="CAC", gamma=0.9, states=1, action_range=[0.1, 0.3], min_memory=90, capacity=120),
                                      dict(name="CAC", gamma=0.5, states=1, action_range=[0.05, 0.2], min_memory=60)],
                              environment=_env(max_steps=30), training=dict(epochs=12, print_freq=1000)), 14),
+    # games made of discrete-action MLP agents only (the BASELINE C5 family): two ActorCritic agents, four updates each
+    "mlp_aa_seed15": (dict(agents=[dict(name="ActorCritic", gamma=0.98, actions=21, states=1, action_range=[0.2, 0.4],
+                                        min_memory=200),
+                                   dict(name="ActorCritic", gamma=0.9, actions=21, states=1, action_range=[0.2, 0.4],
+                                        min_memory=150, capacity=300)],
+                           environment=_env(), training=dict(epochs=8, print_freq=1000)), 15),
+    # two Reinforce agents, short episodes, unequal action grids, ring overflow (capacity 100 < 4 episodes)
+    "mlp_rr_seed16": (dict(agents=[dict(name="Reinforce", gamma=0.9, actions=7, states=1, action_range=[0.1, 0.3],
+                                        min_memory=100),
+                                   dict(name="Reinforce", gamma=0.5, actions=5, states=1, action_range=[0.05, 0.2],
+                                        min_memory=90, capacity=100)],
+                           environment=_env(max_steps=30), training=dict(epochs=12, print_freq=1000)), 16),
+    # Reinforce + two ActorCritic agents
+    "mlp_raa_seed17": (dict(agents=[dict(name="Reinforce", gamma=0.8, actions=6, states=1, action_range=[0.1, 0.2],
+                                         min_memory=60),
+                                    dict(name="ActorCritic", gamma=0.9, actions=7, states=1, action_range=[0.1, 0.3],
+                                         min_memory=90, capacity=120),
+                                    dict(name="ActorCritic", gamma=0.95, actions=5, states=1, action_range=[0.05, 0.2],
+                                         min_memory=45)],
+                            environment=_env(nplayers=3, max_steps=30), training=dict(epochs=12, print_freq=1000)), 17),
 }
 
 

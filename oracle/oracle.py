@@ -49,6 +49,8 @@ def lib():
                                                      C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.thrl_oracle_greedy_eval_mlp.restype = C.c_int
         _lib.thrl_oracle_online_cores.restype = C.c_int
+        _lib.thrl_oracle_py_sum.restype = C.c_double
+        _lib.thrl_oracle_py_sum.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
     return _lib
 
 
@@ -216,6 +218,12 @@ def greedy_eval(game, q, price0, mlp=None):
     if rc != 0:
         raise IndexError("oracle greedy_eval rc=%d" % rc)
     return actions, rewards
+
+
+def py_sum(items, lead):
+    """The restated CPython >= 3.12 builtin sum() over scaled quantities whose first `lead` items are exact floats."""
+    arr = (C.c_double * len(items))(*[float(v) for v in items])
+    return lib().thrl_oracle_py_sum(arr, len(items), int(lead))
 
 
 def online_cores():

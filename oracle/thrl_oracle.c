@@ -149,6 +149,37 @@ static double scale_action(int k, const ThrlAgentSpec* s) {
   return (double)k / ((double)s->actions - 1.0) * (s->action_hi - s->action_lo) + s->action_lo;
 }
 
+/* environments.py:27 `Q = sum(A)` as CPython >= 3.12 evaluates it (Python/bltinmodule.c builtin_sum): while the running
+ * result and the items are exact Python floats the sum is Neumaier-compensated, the compensation is folded in when the
+ * first other item (or the end) is reached, and everything after that is plain left-to-right addition.  Scaled actions
+ * of Reinforce / ActorCritic / CAC are Python floats (`.item()`, agents.py:160-163,270-273,374-378); a QTable's are
+ * numpy.float64 (numpy.int64 index, agents.py:80-89), which is not an exact float.  So: `lead` = number of leading MLP
+ * agents; for lead <= 2 this equals the naive sum.  (Interpreters before 3.12 sum naively; the goldens are recorded with
+ * the 3.12 of this image.)  Checked against builtin sum() on 3e5 random mixed lists by tests/test_oracle_golden.py. */
+static int lead_exact_floats(const ThrlGame* G) {
+  int m = 0;
+  while (m < G->n_agents && G->agent[m].kind != THRL_AGENT_QTABLE) ++m;
+  return m;
+}
+static double py_sum_quantities(const double* aq, int n, int lead) {
+  if (lead == 0) {
+    double q = 0.0;
+    for (int i = 0; i < n; ++i) q = q + aq[i];
+    return q;
+  }
+  double f = 0.0 + aq[0], c = 0.0;
+  int i = 1;
+  for (; i < lead; ++i) {
+    const double x = aq[i], t = f + x;
+    if (fabs(f) >= fabs(x)) { double d = f - t; d = d + x; c = c + d; }
+    else { double d = x - t; d = d + f; c = c + d; }
+    f = t;
+  }
+  if (c != 0.0 && isfinite(c)) f = f + c;
+  for (; i < n; ++i) f = f + aq[i];
+  return f;
+}
+
 /* ---------------------------------------------------------------- Reinforce agent (th_rl/agents.py:119-194), float32
  * Every operation is a separate IEEE f32 operation in a fixed order (no FMA), so the CUDA kernel reproduces it exactly.
  * expf is our own (Cody-Waite reduction + Cephes polynomial, ~2 ulp): libm and libdevice expf differ in the last bit. */
@@ -676,8 +707,8 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
       if (rc) break;
       /* environments.py:25-39 */
       const double ab = G->a / G->b;
-      double Q = 0.0;
-      for (int i = 0; i < n; ++i) { Aq[i] = ab * xs[i]; Q = Q + Aq[i]; }
+      for (int i = 0; i < n; ++i) Aq[i] = ab * xs[i];
+      const double Q = py_sum_quantities(Aq, n, lead_exact_floats(G));
       double new_a;
       if (A->rng_mode == THRL_RNG_PHILOX) {
         new_a = G->a;
@@ -831,6 +862,9 @@ int thrl_oracle_qtable_scan(const ThrlScanArgs* args, int n_threads) {
   for (int i = 1; i < n_threads; ++i) { pthread_join(th[i], NULL); bad |= w[i].bad; }
   return bad ? THRL_ERR_BAD_CONFIG : THRL_OK;
 }
+/* test hook: the restated builtin sum() (tests compare it with the interpreter's own sum) */
+double thrl_oracle_py_sum(const double* items, int n, int lead) { return py_sum_quantities(items, n, lead); }
+
 int thrl_oracle_online_cores(void) { return (int)sysconf(_SC_NPROCESSORS_ONLN); }
 
 /* DESIGN.md "Device init": q = 12.5/(1-gamma) + N(0,1) (agents.py:29), counter = 0 (agents.py:45),
@@ -914,7 +948,6 @@ int thrl_oracle_greedy_eval_mlp(const ThrlGame* G, int64_t n_runs, int32_t table
       for (int t = 0; t < T; ++t) {
         double xs[THRL_MAX_AGENTS], Aq[THRL_MAX_AGENTS];
         const double ab = G->a / G->b;
-        double Q = 0.0;
         for (int i = 0; i < n; ++i) {
           const ThrlAgentSpec* s = &G->agent[i];
           if (s->kind == THRL_AGENT_QTABLE) {
@@ -942,8 +975,8 @@ int thrl_oracle_greedy_eval_mlp(const ThrlGame* G, int64_t n_runs, int32_t table
             }
           }
           Aq[i] = ab * xs[i];
-          Q = Q + Aq[i];
         }
+        const double Q = py_sum_quantities(Aq, n, lead_exact_floats(G));
         double pn = G->a - G->b * Q; /* deterministic demand: evaluation is defined for noise_prob == 0 */
         double next_price = pn > 0.0 ? pn : 0.0;
         size_t o = (((size_t)r * iters + it) * T + t) * n;

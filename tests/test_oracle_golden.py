@@ -4,6 +4,7 @@ Every quantity the hot path produces must be BIT-EXACT in the reference's own dt
 chosen actions, rewards, prices, final tables, visit counters, epsilon and both per-epoch logs.
 """
 import numpy as np
+import pytest
 
 from oracle import oracle
 from th_rl_b200 import abi
@@ -113,3 +114,26 @@ def test_stats_are_fixed_point_sums(golden):
     assert np.array_equal(res.stats[:, :, 0], want)
     want = np.rint(res.actions_log[0] ** 2 * abi.THRL_STATS_SCALE_SQ).astype(np.int64)
     assert np.array_equal(res.stats[:, :, 3], want)
+
+
+def test_quantity_sum_follows_the_interpreters_sum():
+    """environments.py:27 uses builtin sum(): compensated while the items are exact floats (MLP agents' actions), plain
+    once a numpy.float64 (QTable action) is met.  The oracle's restatement must equal the running interpreter's sum()."""
+    import random
+    import sys
+    if sys.version_info < (3, 12):
+        pytest.skip("builtin sum() is only compensated from CPython 3.12 on; the goldens were recorded with 3.12")
+    rng = random.Random(7)
+    differs = 0
+    for _ in range(20000):
+        n = rng.randint(1, 8)
+        vals = [rng.uniform(0.0, 5.0) for _ in range(n)]
+        lead = rng.randint(0, n)
+        items = [v if i < lead else np.float64(v) for i, v in enumerate(vals)]
+        want = float(sum(items))
+        assert oracle.py_sum(vals, lead) == want
+        naive = 0.0
+        for v in vals:
+            naive += v
+        differs += naive != want
+    assert differs > 0  # the compensation is observable, so the test is not vacuous

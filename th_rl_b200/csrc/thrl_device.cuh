@@ -121,6 +121,33 @@ __device__ __forceinline__ double shfl_xor_t(double v, int off) {
   return __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
 }
 
+// environments.py:27 `Q = sum(A)` as CPython >= 3.12 evaluates it (oracle/thrl_oracle.c py_sum_quantities): Neumaier-
+// compensated over the leading exact-float items (the MLP agents' scaled actions), plain left-to-right addition from the
+// first numpy.float64 item (a QTable agent) on.  lead <= 2 is the naive sum.  aq(i) returns agent i's scaled quantity.
+__device__ __forceinline__ int lead_exact_floats(const ThrlGame& G) {
+  int m = 0;
+  while (m < G.n_agents && G.agent[m].kind != THRL_AGENT_QTABLE) ++m;
+  return m;
+}
+template <typename F>
+__device__ __forceinline__ double py_sum_quantities(int n, int lead, F aq) {
+  if (lead <= 2) {
+    double q = 0.0;
+    for (int i = 0; i < n; ++i) q = __dadd_rn(q, aq(i));
+    return q;
+  }
+  double f = __dadd_rn(0.0, aq(0)), c = 0.0;
+  int i = 1;
+  for (; i < lead; ++i) {
+    const double x = aq(i), t = __dadd_rn(f, x);
+    c = __dadd_rn(c, fabs(f) >= fabs(x) ? __dadd_rn(__dsub_rn(f, t), x) : __dadd_rn(__dsub_rn(x, t), f));
+    f = t;
+  }
+  if (c != 0.0 && isfinite(c)) f = __dadd_rn(f, c);
+  for (; i < n; ++i) f = __dadd_rn(f, aq(i));
+  return f;
+}
+
 // fixed-point statistics (include/thrl.h THRL_STATS_*): exact integer sums, independent of run order and sharding
 __device__ __forceinline__ long long fx_round(double x) { return __double2ll_rn(x); }
 

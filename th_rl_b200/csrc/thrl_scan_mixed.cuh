@@ -481,6 +481,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
     for (int j = 0; j < lane; ++j) my_lut += G.agent[j].actions;
   }
   const bool never_fires = my_minmem > my_cap;
+  const int lead = lead_exact_floats(G);
 
   const long long total_warps = (long long)gridDim.x * warps_per_cta;
   for (long long r = (long long)blockIdx.x * warps_per_cta + warp; r < p.n_runs; r += total_warps) {
@@ -624,8 +625,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
             xt = lutXT[my_lut + k];
           }
         }
-        double Q = 0.0;
-        for (int i = 0; i < n; ++i) Q = __dadd_rn(Q, shfl_d(aq, i));
+        const double Q = py_sum_quantities(n, lead, [&](int i) { return shfl_d(aq, i); });  // environments.py:27 sum(A)
         const double na = p.noisy ? newa[t] : G.a;
         const double pn = __dsub_rn(na, __dmul_rn(G.b, Q));
         const double next_price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(256) greedy_eval_mixed(const __grid_constant__
     for (int it = 0; it < p.iters; ++it) {
       double price = p.price0[r * p.iters + it];
       for (int t = 0; t < T; ++t) {
-        double Q = 0.0, my_x = 0.0, my_aq = 0.0;
+        double my_x = 0.0, my_aq = 0.0;
         for (int i = 0; i < n; ++i) {
           const ThrlAgentSpec& s = G.agent[i];
           double x;
@@ -839,9 +839,9 @@ __global__ void __launch_bounds__(256) greedy_eval_mixed(const __grid_constant__
             __syncwarp();
           }
           const double aq = __dmul_rn(ab, x);
-          Q = __dadd_rn(Q, aq);
           if (lane == i) { my_x = x; my_aq = aq; }
         }
+        const double Q = py_sum_quantities(n, lead_exact_floats(G), [&](int i) { return shfl_d(my_aq, i); });
         const double pn = __dsub_rn(G.a, __dmul_rn(G.b, Q));
         const double next_price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
         if (lane < n) {

@@ -76,7 +76,8 @@ def _c5_cfg(epochs):
 WORKLOADS["c5"] = dict(agents=2, runs_per_gpu=16384, epochs=20, config=_c5_cfg(20), algo_bytes=4.5e4, bound="tensor", hp=None,
                        desc="2 ActorCritic agents (MLP 1->256->{21,1}, Adam, N=1000 transition batches every 10 episodes), "
                             "%d runs/GPU x %d epochs per step (C5 shape)",
-                       kernel="thrl::qtable_scan_mixed<float> (persistent, one launch per step; CUDA-core fp32, no tensor cores yet)")
+                       kernel="thrl::mlp_scan_pwl (persistent, one launch per step; policy LUT per lattice state + sorted-breakpoint "
+                              "gradient sweep, f64 accumulation; no dense contraction is left)")
 WL = WORKLOADS["c2"]  # set in main()
 CONFIG = WL["config"]
 EPOCHS = WL["epochs"]
@@ -305,10 +306,12 @@ def run_ours(args):
             line["roofline"] = {
                 "bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
                 "kernel": WL["kernel"], "kernel_ms": kern_ms,
-                "note": "4.5e4 algorithmic flop per agent-step (BASELINE.md 5); peak = bf16 dense from MEASURED_PEAKS.json (%s). "
-                        "This tier is correctness-first: fp32 on CUDA cores in the oracle's operation order (bit-equal to it); "
-                        "tensor-pipe utilisation is 0 by construction. The per-run-weight grouped GEMMs (16,384 x 1000x256x22) "
-                        "on tcgen05 are the next round's work" % tf_src}
+                "note": "4.5e4 algorithmic flop per agent-step (BASELINE.md 5: per-step forward + N = 1000 batched update as dense "
+                        "GEMMs); peak = bf16 dense from MEASURED_PEAKS.json (%s).  The kernel does NOT execute those flops: the "
+                        "network input is a scalar from a finite price lattice, so pi(.|s) is tabulated per state and the exact "
+                        "gradient comes from one sorted-breakpoint sweep, O(states*A + H*A) per update instead of O(N*H*A) "
+                        "(DESIGN.md 4.5).  `achieved` is therefore the rate the dense formulation would have needed; tensor-pipe "
+                        "utilisation is 0 by construction and the real limiter is SM issue rate (profiles/)" % tf_src}
         else:
             line["roofline"] = {
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

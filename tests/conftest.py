@@ -32,3 +32,17 @@ def golden(request):
     g = load_golden(request.param)
     g["name"] = request.param
     return g
+
+
+def uses_lattice_kernel(cfg):
+    """Games the library plays with the lattice kernel (th_rl_b200/csrc/thrl_scan_pwl.cuh): only Reinforce / ActorCritic
+    agents, noise-free demand, at most 1024 joint actions.  Its MLP results match the order-exact kernel / the oracle to
+    float32 rounding instead of bit for bit; THRL_KERNEL=mixed selects the order-exact kernel."""
+    if cfg["environment"].get("noise_prob", 0.05) > 0:
+        return False
+    joint = 1
+    for a in cfg["agents"]:
+        if a["name"] not in ("Reinforce", "ActorCritic") or a.get("actions", 4) > 31:
+            return False
+        joint *= a.get("actions", 4)
+    return joint <= 1024

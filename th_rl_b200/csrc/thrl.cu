@@ -8,7 +8,9 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <array>
+#include <cmath>
 #include <atomic>
 #include <map>
 #include <memory>
@@ -20,6 +22,7 @@
 #include "thrl_scan_lut2.cuh"
 #include "thrl_scan_lpc.cuh"
 #include "thrl_scan_mixed.cuh"
+#include "thrl_scan_pwl.cuh"
 #include "thrl_aux_kernels.cuh"
 
 namespace {
@@ -423,6 +426,143 @@ int launch_mixed(thrl::MixedParams& p, const DeviceInfo& dev, cudaStream_t strea
   return THRL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ lattice (pwl) launch
+double h_scale_mlp(int k, int actions, double lo, double hi) {  // Reinforce.scale: k / actions * (hi - lo) + lo
+  double d = (double)k / (double)actions;
+  d = d * (hi - lo);
+  return d + lo;
+}
+// builtin sum() of CPython >= 3.12 over scaled quantities whose first `lead` items are exact floats (thrl_device.cuh)
+double h_py_sum(const double* aq, int n, int lead) {
+  if (lead <= 2) {
+    double q = 0.0;
+    for (int i = 0; i < n; ++i) q = q + aq[i];
+    return q;
+  }
+  double f = 0.0 + aq[0], c = 0.0;
+  int i = 1;
+  for (; i < lead; ++i) {
+    const double x = aq[i], t = f + x;
+    if (std::fabs(f) >= std::fabs(x)) { double d = f - t; d = d + x; c = c + d; }
+    else { double d = x - t; d = d + f; c = c + d; }
+    f = t;
+  }
+  if (c != 0.0 && std::isfinite(c)) f = f + c;
+  for (; i < n; ++i) f = f + aq[i];
+  return f;
+}
+
+static_assert(sizeof(thrl::PwlParams) < 32000, "kernel parameters are limited to 32,764 bytes");
+
+// Fills p (lattice tables + layouts) when the game consists of Reinforce / ActorCritic agents on the noise-free demand
+// curve with few enough joint actions; otherwise the order-exact kernel takes the game.
+bool plan_pwl(thrl::PwlParams* p, bool noisy, int smem_optin, int* warps) {
+  const ThrlGame& G = p->game;
+  const int n = G.n_agents, T = G.max_steps;
+  if (noisy || n < 1) return false;
+  long long J = 1;
+  int lut = 0, Hmax = 0, Amax = 0, Pmax = 0, capmax = 0;
+  for (int i = 0; i < n; ++i) {
+    const ThrlAgentSpec& s = G.agent[i];
+    if (s.kind != THRL_AGENT_REINFORCE && s.kind != THRL_AGENT_ACTORCRITIC) return false;
+    if (s.actions < 1 || s.actions > 31 || s.hidden < 1 || s.hidden > 8192) return false;
+    J *= s.actions;
+    if (J > thrl::kPwlMaxJoint) return false;
+    p->a_off[i] = lut;
+    lut += s.actions;
+    const int P = 2 * s.hidden + s.actions * s.hidden + s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? s.hidden + 1 : 0);
+    if (P > Pmax) Pmax = P;
+    if (s.hidden > Hmax) Hmax = s.hidden;
+    if (s.actions > Amax) Amax = s.actions;
+    if (G.mlp_buffer_len[i] > capmax) capmax = G.mlp_buffer_len[i];
+  }
+  p->J = (int)J;
+  p->lut_total = lut;
+  p->jmul[n - 1] = 1;
+  for (int i = n - 2; i >= 0; --i) p->jmul[i] = p->jmul[i + 1] * G.agent[i + 1].actions;
+  const double ab = G.a / G.b;
+  std::vector<float> fl((size_t)J);
+  for (int j = 0; j < (int)J; ++j) {
+    double aq[THRL_MAX_AGENTS];
+    for (int i = 0; i < n; ++i) {
+      const ThrlAgentSpec& s = G.agent[i];
+      aq[i] = ab * h_scale_mlp((j / p->jmul[i]) % s.actions, s.actions, s.action_lo, s.action_hi);
+    }
+    const double Q = h_py_sum(aq, n, n);
+    const double pn = G.a - G.b * Q;
+    const double price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
+    if (price != price) return false;
+    p->priceJ[j] = price;
+    fl[j] = (float)price;
+  }
+  std::vector<float> uniq(fl);
+  std::sort(uniq.begin(), uniq.end());
+  uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+  const int NS = (int)uniq.size();
+  if (NS > thrl::kPwlMaxLattice) return false;
+  p->NS = NS;
+  for (int x = 0; x < NS; ++x) p->slot_val[x] = uniq[x];
+  for (int j = 0; j < (int)J; ++j)
+    p->slot_of[j] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), fl[j]) - uniq.begin());
+  const int NSX = NS + thrl::kPwlExtras;
+  // shared memory
+  int o = align_up(2 * lut * 8, 16);
+  p->off_priceJ = o; o += align_up((int)J * 8, 16);
+  p->off_rT = o;     o += align_up((int)J * n * 8, 16);
+  p->off_slotof = o; o += align_up((int)J, 16);
+  p->cta_bytes = o;
+  o = 0;
+  p->off_sv = o;  o += align_up(NSX * 4, 16);
+  p->off_cdf = o;
+  int cdf = 0;
+  for (int i = 0; i < n; ++i) { p->cdf_off[i] = cdf; cdf += NSX * G.agent[i].actions; p->val_off[i] = i * NSX; }
+  o += align_up(cdf * 4, 16);
+  p->off_val = o; o += align_up(n * NSX * 4, 16);
+  p->off_pre = o; o += align_up(T * n * 4, 16);
+  p->off_ev = o;  o += align_up(Hmax * 2, 16);
+  p->off_ord = o; o += align_up(Hmax * 2, 16);
+  p->off_bkt = o; o += align_up((NS + 2) * 2, 16);
+  p->warp_bytes = o;
+  // per-warp workspace in global memory
+  long long w = 0;
+  p->ws_acc = w;  w += align_up(NSX * (Amax + 2) * 8, 16);
+  p->ws_p = w;    w += align_up(cdf * 4, 16);
+  p->ws_grad = w; w += align_up(Pmax * 4, 16);
+  p->ws_xs = w;   w += (long long)(capmax > 0 ? capmax : 1) * 16;
+  p->ws_warp_bytes = (w + 255) / 256 * 256;
+  const int fit = (smem_optin - p->cta_bytes) / p->warp_bytes;
+  if (fit < 1) return false;
+  *warps = fit > 16 ? 16 : fit;
+  return true;
+}
+
+int launch_pwl(thrl::PwlParams& p, int warps, const DeviceInfo& dev, cudaStream_t stream) {
+  int grid = dev.sms;
+  {
+    const long long slots = (long long)dev.sms * warps;
+    const long long rounds = (p.n_runs + slots - 1) / slots;
+    const long long per_round = (p.n_runs + rounds - 1) / rounds;
+    warps = (int)((per_round + dev.sms - 1) / dev.sms);
+    if (warps < 1) warps = 1;
+    grid = (int)((per_round + warps - 1) / warps);
+    if (grid > dev.sms) grid = dev.sms;
+  }
+  const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
+  void* ws = nullptr;
+  CUDA_TRY(cudaMallocAsync(&ws, (size_t)grid * warps * (size_t)p.ws_warp_bytes, stream));  // stream-ordered scratch
+  p.ws = (unsigned char*)ws;
+  auto kern = thrl::mlp_scan_pwl;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    kern<<<grid, warps * 32, smem, stream>>>(p);
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(ws, stream);
+  CUDA_TRY(e);
+  g_launches.fetch_add(1);
+  return THRL_OK;
+}
+
 int check_args(const ThrlScanArgs* a) {
   if (!a || !a->game) return fail(THRL_ERR_BAD_ARGS, "args/game is NULL");
   if (a->n_runs < 0 || a->epoch_end < a->epoch_begin) return fail(THRL_ERR_BAD_ARGS, "negative run or epoch count");
@@ -484,7 +624,24 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
   p.Hp = (p.game.ring_len > 0 ? p.game.ring_len : 1) + 1;
   p.noisy = (a->rng_mode == THRL_RNG_PHILOX) ? (p.game.noise_prob > 0.0) : (a->replay_new_a != nullptr);
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (p.game.mlp_stride > 0) {  // games with Reinforce agents: their own (correctness-first) kernel
+  if (p.game.mlp_stride > 0) {  // games with MLP agents
+    const char* forced = getenv("THRL_KERNEL");
+    if (!(forced && strcmp(forced, "mixed") == 0)) {  // lattice kernel where it applies (thrl_scan_pwl.cuh)
+      thrl::PwlParams* w = new thrl::PwlParams();
+      std::unique_ptr<thrl::PwlParams> hold_w(w);
+      memset(w, 0, sizeof(*w));
+      w->game = p.game;
+      int warps = 0;
+      if (plan_pwl(w, p.noisy != 0, dev.smem_optin, &warps)) {
+        w->n_runs = p.n_runs; w->run_id0 = p.run_id0; w->epoch_begin = p.epoch_begin; w->E = p.E; w->rng_mode = p.rng_mode;
+        w->k0 = p.k0; w->k1 = p.k1;
+        w->price = p.price; w->replay_ra = p.replay_ra;
+        w->rewards_log = p.rewards_log; w->actions_log = p.actions_log; w->n_log_runs = p.n_log_runs; w->stats = p.stats;
+        w->trace_actions = p.trace_actions; w->trace_rewards = p.trace_rewards; w->trace_prices = p.trace_prices;
+        w->mlp = a->mlp;
+        return launch_pwl(*w, warps, dev, stream);
+      }
+    }
     thrl::MixedParams* m = new thrl::MixedParams();
     std::unique_ptr<thrl::MixedParams> hold(m);
     m->game = p.game;

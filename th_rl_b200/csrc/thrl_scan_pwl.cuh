@@ -1,0 +1,663 @@
+// thrl_scan_pwl.cuh — games made only of discrete-action MLP agents (Reinforce, th_rl/agents.py:119-194; ActorCritic,
+// :222-305) on the noise-free demand curve: the BASELINE C5 family.
+//
+// Two facts make the per-run "1000 x 256 x 22 GEMMs" of such a game collapse:
+//  (1) the network input is the price, and with discrete actions and no demand noise the price only takes the finitely
+//      many values a - b*sum(A) of the joint actions (the LATTICE, <= 240 distinct float32 states; plus the run's
+//      arbitrary initial price, an "extra" state).  pi(.|s) and v(s) are therefore tabulated once per parameter update
+//      (policy LUT, stored as a CDF so that acting is one shared-memory row read + ballot), and a batch of N
+//      transitions is equivalent to at most NS weighted states: the per-sample loss coefficients are summed per state
+//      (and per state x action) with fixed-point integer atomics, which makes the sums independent of the order.
+//  (2) a 1 -> H -> A ReLU network of a scalar is piecewise linear with one breakpoint per hidden unit: unit j is active
+//      on a prefix or a suffix of the sorted lattice (the float32 predicate fl(fl(s*w1)+b1) > 0 is monotone in s).
+//      Sorting the units by breakpoint, one sweep over the lattice evaluates every logit as S1*s + S0 with running f64
+//      sums (forward), and one sweep of f64 prefix sums of the per-state gradient coefficients yields every
+//      d loss / d fc_pi.weight[k][j] = w1_j*M1[k][j] + b1_j*M0[k][j] and the fc1 gradients (backward).
+// Work per update: O(NS*A + H*A) instead of O(N*H*A); no dense contraction is left, so there is nothing to put on the
+// tensor cores.  The arithmetic is the same real-number computation as the reference's autograd graph, summed in a
+// different order (f64 accumulation): results agree with oracle/thrl_oracle.c (which follows the reference's order and
+// is pinned against torch) to float32 rounding, not bit for bit; tests/test_gpu_pwl.py states the tolerance.
+// THRL_KERNEL=mixed selects the order-exact kernel (thrl_scan_mixed.cuh) instead.
+#pragma once
+#include "thrl_device.cuh"
+#include "thrl_scan_mixed.cuh"  // mlp_P, mlp_entry_words, det_expf
+
+namespace thrl {
+
+constexpr int kPwlMaxJoint = 1024;   // joint actions (price table in the kernel parameters)
+constexpr int kPwlMaxLattice = 240;  // distinct float32 lattice prices
+constexpr int kPwlExtras = 4;        // off-lattice states one run may hold at a time (its initial price)
+
+struct PwlParams {
+  ThrlGame game;
+  long long n_runs, run_id0;
+  int epoch_begin, E, rng_mode;
+  uint32_t k0, k1;
+  double* price;
+  const int32_t* replay_ra;
+  double* rewards_log;
+  double* actions_log;
+  long long n_log_runs;
+  long long* stats;
+  int32_t* trace_actions;
+  double* trace_rewards;
+  double* trace_prices;
+  float* mlp;
+  unsigned char* ws;  // per resident warp: accumulators, probability LUT, gradient, per-sample scratch
+  long long ws_warp_bytes, ws_acc, ws_p, ws_grad, ws_xs;
+  int J, NS, lut_total;
+  int a_off[THRL_MAX_AGENTS];    // agent's offset in the per-action tables
+  int jmul[THRL_MAX_AGENTS];     // joint index = sum_i action_i * jmul[i]
+  int cdf_off[THRL_MAX_AGENTS];  // float offset of the agent's CDF LUT [NS + extras][A] (shared memory and ws_p alike)
+  int val_off[THRL_MAX_AGENTS];  // float offset of the agent's v(s) LUT [NS + extras]
+  int cta_bytes, off_priceJ, off_rT, off_slotof;
+  int warp_bytes, off_sv, off_cdf, off_val, off_pre, off_ev, off_ord, off_bkt;
+  float slot_val[kPwlMaxLattice];   // lattice states, ascending
+  uint8_t slot_of[kPwlMaxJoint];    // joint action -> lattice state
+  double priceJ[kPwlMaxJoint];      // joint action -> next price (environments.py:25-33)
+};
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+__device__ __forceinline__ double warp_sum(double v) {  // xor butterfly: every lane ends with the same bits
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v = __dadd_rn(v, shfl_xor_t(v, off));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, off));
+  return v;
+}
+
+// index of state s among the lattice states sv[0..NS) (ascending) or the extras sv[NS..NS+nx); -1 when absent
+__device__ __forceinline__ int pwl_find(const float* sv, int NS, int nx, float s) {
+  int lo = 0, hi = NS;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (sv[mid] < s) lo = mid + 1; else hi = mid;
+  }
+  if (lo < NS && sv[lo] == s) return lo;
+  for (int e = 0; e < nx; ++e)
+    if (__float_as_int(sv[NS + e]) == __float_as_int(s)) return NS + e;
+  return -1;
+}
+
+__device__ __forceinline__ bool pwl_active(float s, float w, float b) { return __fadd_rn(__fmul_rn(s, w), b) > 0.0f; }
+
+// Breakpoint of every hidden unit on the sorted lattice and the units in breakpoint order.
+// ev[j] = key | leave << 15:  leave = 0: unit j is active on ranks [key, NS);  leave = 1: active on ranks [0, key).
+// ord[0..H): unit indices sorted by key (stable in j, so the result does not depend on the schedule).
+__device__ inline void pwl_unit_events(const float* w1, const float* b1, int H, const float* sv, int NS, uint16_t* ev,
+                                       uint16_t* ord, uint16_t* bkt, int lane) {
+  const int NB = NS + 2;
+  __syncwarp();
+  for (int b = lane; b < NB; b += 32) bkt[b] = 0;
+  __syncwarp();
+  for (int j0 = 0; j0 < H; j0 += 32) {
+    const int j = j0 + lane;
+    unsigned kk = 0x10000u + (unsigned)lane;  // lanes past H: unique, no bucket
+    if (j < H) {
+      const float w = w1[j], b = b1[j];
+      int key;
+      unsigned leave;
+      if (w > 0.0f) {  // the predicate is non-decreasing in the rank: first active rank
+        int lo = 0, hi = NS;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (pwl_active(sv[mid], w, b)) hi = mid; else lo = mid + 1;
+        }
+        key = lo; leave = 0;
+      } else if (w < 0.0f) {  // non-increasing: first inactive rank
+        int lo = 0, hi = NS;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (pwl_active(sv[mid], w, b)) lo = mid + 1; else hi = mid;
+        }
+        key = lo; leave = 1;
+      } else {  // w == 0 (or NaN: never active): the same for every state
+        key = (w == 0.0f && b > 0.0f) ? NS : 0; leave = 1;
+      }
+      ev[j] = (uint16_t)(key | (leave << 15));
+      kk = (unsigned)key;
+    }
+    const unsigned peers = __match_any_sync(kFull, kk);
+    if (j < H && (peers & lanemask_lt()) == 0) bkt[kk + 1] += (uint16_t)__popc(peers);
+    __syncwarp();
+  }
+  {  // inclusive scan: afterwards bkt[k] = first position of bucket k
+    const int per = (NB + 31) / 32;
+    const int beg = lane * per, end = beg + per < NB ? beg + per : NB;
+    int s = 0;
+    for (int b = beg; b < end; ++b) s += bkt[b];
+    int incl = s;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, off);
+      if (lane >= off) incl += t;
+    }
+    int run = incl - s;
+    for (int b = beg; b < end; ++b) { run += bkt[b]; bkt[b] = (uint16_t)run; }
+  }
+  __syncwarp();
+  for (int j0 = 0; j0 < H; j0 += 32) {
+    const int j = j0 + lane;
+    const unsigned kk = j < H ? (unsigned)(ev[j] & 0x7fff) : 0x10000u + (unsigned)lane;
+    const unsigned peers = __match_any_sync(kFull, kk);
+    int base = 0;
+    if (j < H) {
+      base = bkt[kk];
+      ord[base + __popc(peers & lanemask_lt())] = (uint16_t)j;
+    }
+    __syncwarp();
+    if (j < H && (peers & lanemask_lt()) == 0) bkt[kk] = (uint16_t)(base + __popc(peers));
+    __syncwarp();
+  }
+}
+
+// softmax over the lanes < A of one state's logits -> probabilities (ws) and their running sum (shared CDF row);
+// the lane A of an ActorCritic agent carries v(s).
+__device__ __forceinline__ void pwl_emit(float z, bool col, bool vcol, int A, int x, float* cdf, float* val, float* pws, int lane) {
+  const float mx = warp_max(col ? z : NegInf<float>::v());
+  const float ex = col ? det_expf(__fsub_rn(z, mx)) : 0.0f;
+  const float sum = warp_sum(ex);
+  const float pk = __fdiv_rn(ex, sum);
+  float c = pk;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const float t = __shfl_up_sync(kFull, c, off);
+    if (lane >= off) c = __fadd_rn(c, t);
+  }
+  if (col) { cdf[x * A + lane] = c; pws[x * A + lane] = pk; }
+  if (vcol) val[x] = z;
+}
+
+// pi(.|s) and v(s) for every lattice state (one sweep, see the header) and for the extras (direct evaluation).
+// Needs ev / ord of the CURRENT parameters (pwl_unit_events).  blk: the agent's parameters in state_dict order.
+__device__ inline void pwl_build_lut(const float* blk, const ThrlAgentSpec& spec, const float* sv, int NS, int nx,
+                                     const uint16_t* ev, const uint16_t* ord, float* cdf, float* val, float* pws, int lane) {
+  const int H = spec.hidden, A = spec.actions;
+  const bool ac = spec.kind == THRL_AGENT_ACTORCRITIC;
+  const float *w1 = blk, *b1 = blk + H, *W = blk + 2 * H, *bp = W + (size_t)A * H, *wv = bp + A;
+  const bool col = lane < A, vcol = ac && lane == A, use = col || vcol;
+  const float* crow = col ? W + (size_t)lane * H : wv;  // this lane's row of fc_pi.weight, or fc_v.weight
+  const double bias = col ? (double)bp[lane] : (vcol ? (double)wv[H] : 0.0);
+  double S1 = 0.0, S0 = 0.0;
+  __syncwarp();
+#pragma unroll 4
+  for (int e = 0; e < H; ++e) {  // units active from rank 0 on
+    const int j = ord[e];
+    const double c = use ? (double)crow[j] : 0.0;
+    const double t1 = __dmul_rn(c, (double)w1[j]), t0 = __dmul_rn(c, (double)b1[j]);
+    if (ev[j] & 0x8000) { S1 = __dadd_rn(S1, t1); S0 = __dadd_rn(S0, t0); }
+  }
+  int e = 0;
+  for (int r = 0; r < NS; ++r) {
+    while (e < H) {
+      const int j = ord[e];
+      const unsigned v = ev[j];
+      if ((int)(v & 0x7fff) > r) break;
+      const double c = use ? (double)crow[j] : 0.0;
+      const double t1 = __dmul_rn(c, (double)w1[j]), t0 = __dmul_rn(c, (double)b1[j]);
+      if (v & 0x8000) { S1 = __dsub_rn(S1, t1); S0 = __dsub_rn(S0, t0); }
+      else { S1 = __dadd_rn(S1, t1); S0 = __dadd_rn(S0, t0); }
+      ++e;
+    }
+    const float z = (float)__dadd_rn(__dadd_rn(__dmul_rn(S1, (double)sv[r]), S0), bias);
+    pwl_emit(z, col, vcol, A, r, cdf, val, pws, lane);
+  }
+  for (int x = NS; x < NS + nx; ++x) {  // off-lattice states: the plain sum over the hidden units
+    const float s = sv[x];
+    double acc = 0.0;
+    for (int j = 0; j < H; ++j) {
+      const float hv = __fadd_rn(__fmul_rn(s, w1[j]), b1[j]);
+      if (hv > 0.0f) acc = __dadd_rn(acc, __dmul_rn((double)hv, use ? (double)crow[j] : 0.0));
+    }
+    pwl_emit((float)__dadd_rn(acc, bias), col, vcol, A, x, cdf, val, pws, lane);
+  }
+  __syncwarp();
+}
+
+// 2^k with N * cmax * 2^k < 2^62: the fixed-point scale of one update's coefficient sums
+__device__ __forceinline__ double pwl_scale(float cmax, int N) {
+  if (!(cmax > 0.0f)) return 1.0;
+  int e;
+  frexpf(cmax, &e);  // cmax < 2^e
+  int k = 62 - e - (32 - __clz(N));
+  k = k > 1000 ? 1000 : (k < -1000 ? -1000 : k);
+  return ldexp(1.0, k);
+}
+
+// clip_grad_norm_(1.0) + one Adam step (oracle mlp_clip_adam) on parameters that stay in the global slab; g: state_dict order
+__device__ inline void pwl_clip_adam(float* blk, const ThrlAgentSpec& spec, const float* g, int lane) {
+  const int P = mlp_P(spec);
+  float *am = blk + P, *av = blk + 2 * (size_t)P;
+  int32_t* hdr = reinterpret_cast<int32_t*>(blk + 3 * (size_t)P);
+  __syncwarp();
+  double part = 0.0;
+  for (int i = lane; i < P; i += 32) { const double gd = (double)g[i]; part = __dadd_rn(part, __dmul_rn(gd, gd)); }
+  double tot = 0.0;
+  for (int l = 0; l < 32; ++l) tot = __dadd_rn(tot, shfl_d(part, l));
+  const float total_norm = (float)sqrt(tot);
+  float coef = __fdiv_rn(1.0f, __fadd_rn(total_norm, 1e-6f));
+  if (coef > 1.0f) coef = 1.0f;
+  const int step = hdr[0] + 1;
+  double pw1 = 1.0, pw2 = 1.0;
+  for (int q2 = 0; q2 < step; ++q2) { pw1 = __dmul_rn(pw1, 0.9); pw2 = __dmul_rn(pw2, 0.999); }
+  const double bc1 = __dsub_rn(1.0, pw1), bc2 = __dsub_rn(1.0, pw2);
+  const float neg_step_size = (float)(-__ddiv_rn(spec.lr, bc1));
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float w1m = (float)__dsub_rn(1.0, 0.9), fb2 = (float)0.999, w2 = (float)__dsub_rn(1.0, 0.999), eps = 1e-8f;
+  for (int i = lane; i < P; i += 32) {
+    const float gi = __fmul_rn(g[i], coef);
+    float m = am[i], v = av[i];
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(gi, m), w1m));
+    v = __fadd_rn(__fmul_rn(v, fb2), __fmul_rn(__fmul_rn(w2, gi), gi));
+    am[i] = m;
+    av[i] = v;
+    const float den = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps);
+    blk[i] = __fadd_rn(blk[i], __fdiv_rn(__fmul_rn(neg_step_size, m), den));
+  }
+  __syncwarp();
+  if (lane == 0) hdr[0] = step;
+  __syncwarp();
+}
+
+// Reinforce.train_net (agents.py:170-194) / ActorCritic.train_net (:280-305) on the N buffered transitions, by states.
+// The per-sample coefficients are the oracle's (mlp_train / ac_train, float32, same operation order); only the sums over
+// samples and hidden units are re-associated.  val: v(s) LUT of the current parameters; pws: their pi(.|s) LUT.
+__device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap, int head, int N, const float* sv, int NS,
+                                 int nx, uint16_t* ev, uint16_t* ord, uint16_t* bkt, const float* val, const float* pws,
+                                 long long* acc, float* g, float4* xs, int lane) {
+  const int H = spec.hidden, A = spec.actions, P = mlp_P(spec), EW = mlp_entry_words(spec);
+  const bool ac = spec.kind == THRL_AGENT_ACTORCRITIC;
+  float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
+  const float *w1 = blk, *b1 = blk + H, *W = blk + 2 * H, *wv = W + (size_t)A * H + A;
+  const int C = A + 2;  // accumulator columns per state: [0, A) state x action, A: value head, A + 1: state total
+  const int NX = NS + nx;
+  const float gam = (float)spec.gamma;
+  auto entry = [&](int nn) {
+    int sl = head + nn;
+    if (sl >= cap) sl -= cap;
+    return buf + (size_t)sl * EW;
+  };
+  __syncwarp();
+  for (int i = lane; i < NX * C; i += 32) acc[i] = 0;
+  bool bad = false;
+  float camax = 0.0f, cvmax = 0.0f;
+  if (!ac) {
+    // discounted returns, newest to oldest (:177-180): the float32 recurrence itself, 32 transitions per round
+    float carry = 0.0f;
+    bool first = true;
+    double part = 0.0;
+    for (int hi = N; hi > 0; hi -= 32) {
+      const int nn = hi - 32 + lane;
+      float rv = 0.0f;
+      if (nn >= 0) rv = entry(nn)[2];
+      float dv = 0.0f;
+      const int lmin = hi >= 32 ? 0 : 32 - hi;
+      for (int l = 31; l >= lmin; --l) {
+        const float rl = __shfl_sync(kFull, rv, l);
+        const float d = first ? rl : __fadd_rn(rl, __fmul_rn(gam, carry));
+        first = false;
+        carry = d;
+        if (lane == l) dv = d;
+      }
+      if (nn >= 0) { entry(nn)[2] = dv; part = __dadd_rn(part, (double)dv); }  // kept in the buffer like the order-exact kernel
+    }
+    __syncwarp();
+    const float mean = (float)__ddiv_rn(warp_sum(part), (double)N);
+    double ss = 0.0;
+    for (int nn = lane; nn < N; nn += 32) {
+      const double d = __dsub_rn((double)entry(nn)[2], (double)mean);
+      ss = __dadd_rn(ss, __dmul_rn(d, d));
+    }
+    const float sd = (float)sqrt(__ddiv_rn(warp_sum(ss), (double)(N - 1)));  // unbiased std (:181)
+    const float invN = __fdiv_rn(1.0f, (float)N);
+    for (int nn = lane; nn < N; nn += 32) {
+      const float* en = entry(nn);
+      const float ca = __fmul_rn(__fdiv_rn(__fsub_rn(en[2], mean), sd), invN);  // d loss / d logits = (p - onehot) * G / N (:185)
+      const int x = pwl_find(sv, NS, nx, en[0]);
+      bad |= !isfinite(ca) || x < 0;
+      camax = fmaxf(camax, fabsf(ca));
+      xs[nn] = make_float4(__int_as_float(x & 0xff), ca, 0.0f, 0.0f);
+    }
+  } else {
+    double Rp = 0.0, Dp = 0.0;
+    for (int nn = lane; nn < N; nn += 32) {  // d_i = gamma * v(s'_i) - v(s_i) (:289)
+      const float* en = entry(nn);
+      const int x = pwl_find(sv, NS, nx, en[0]), x2 = pwl_find(sv, NS, nx, en[3]);
+      bad |= x < 0 || x2 < 0;
+      const float v = val[x < 0 ? 0 : x], vp = val[x2 < 0 ? 0 : x2];
+      const float d = __fsub_rn(__fmul_rn(gam, vp), v);
+      Rp = __dadd_rn(Rp, (double)en[2]);
+      Dp = __dadd_rn(Dp, (double)d);
+      xs[nn] = make_float4(__int_as_float((x & 0xff) | ((x2 & 0xff) << 8)), 0.0f, 0.0f, d);
+    }
+    const float fN = (float)N, fR = (float)warp_sum(Rp), fD = (float)warp_sum(Dp);
+    const float invN2 = __fdiv_rn(1.0f, __fmul_rn(fN, fN));
+    for (int nn = lane; nn < N; nn += 32) {  // the [N,N] advantage broadcast collapsed as in oracle ac_train
+      float4 q = xs[nn];
+      const float r = entry(nn)[2];
+      q.y = __fmul_rn(__fadd_rn(__fmul_rn(fN, r), fD), invN2);                       // actor weight (N r_j + D) / N^2
+      q.z = __fmul_rn(-2.0f, __fmul_rn(__fadd_rn(fR, __fmul_rn(fN, q.w)), invN2));   // dL/dv_j; dL/dv'_j = -gamma * that
+      bad |= !isfinite(q.y) || !isfinite(q.z);
+      camax = fmaxf(camax, fabsf(q.y));
+      cvmax = fmaxf(cvmax, fmaxf(fabsf(q.z), fabsf(__fmul_rn(-gam, q.z))));
+      xs[nn] = q;
+    }
+  }
+  bad = __any_sync(kFull, bad);
+  camax = warp_max(camax);
+  cvmax = warp_max(cvmax);
+  if (bad) {  // non-finite coefficients (e.g. zero return variance): the reference's gradient is NaN everywhere
+    for (int i = lane; i < P; i += 32) g[i] = __int_as_float(0x7fc00000);
+    pwl_clip_adam(blk, spec, g, lane);
+    return;
+  }
+  const double sa = pwl_scale(camax, N), sc = pwl_scale(cvmax, 2 * N);
+  __syncwarp();
+  {
+    unsigned long long* uacc = reinterpret_cast<unsigned long long*>(acc);
+    for (int nn = lane; nn < N; nn += 32) {
+      const float4 q = xs[nn];
+      const int xb = __float_as_int(q.x), x = xb & 0xff, x2 = (xb >> 8) & 0xff;
+      const int a = __float_as_int(entry(nn)[1]);
+      const unsigned long long fa = (unsigned long long)__double2ll_rn(__dmul_rn((double)q.y, sa));
+      atomicAdd(uacc + x * C + a, fa);
+      atomicAdd(uacc + x * C + A + 1, fa);
+      if (ac) {
+        atomicAdd(uacc + x * C + A, (unsigned long long)__double2ll_rn(__dmul_rn((double)q.z, sc)));
+        atomicAdd(uacc + x2 * C + A, (unsigned long long)__double2ll_rn(__dmul_rn((double)__fmul_rn(-gam, q.z), sc)));
+      }
+    }
+  }
+  __syncwarp();
+  pwl_unit_events(w1, b1, H, sv, NS, ev, ord, bkt, lane);
+  // per-state gradient coefficients of this lane's column: DL[x][k] = pi(k|x) * CA[x] - CAa[x][k]; value lane: CV[x]
+  const bool col = lane < A, vcol = ac && lane == A, use = col || vcol;
+  const float* crow = col ? W + (size_t)lane * H : wv;
+  const double isa = __ddiv_rn(1.0, sa), isc = __ddiv_rn(1.0, sc);
+  double T0 = 0.0, T1 = 0.0, DLx[kPwlExtras];
+#pragma unroll
+  for (int e = 0; e < kPwlExtras; ++e) DLx[e] = 0.0;
+  for (int x = 0; x < NX; ++x) {
+    double dl = 0.0;
+    if (use) {
+      const double raw = (double)__ldcg(acc + x * C + lane);
+      if (col) {
+        const double cax = __dmul_rn((double)__ldcg(acc + x * C + A + 1), isa);
+        dl = __dsub_rn(__dmul_rn((double)pws[x * A + lane], cax), __dmul_rn(raw, isa));
+      } else {
+        dl = __dmul_rn(raw, isc);
+      }
+    }
+    if (x < NS) {
+      if (use) acc[x * C + lane] = __double_as_longlong(dl);  // own column: read back by this lane in the sweep
+      T0 = __dadd_rn(T0, dl);
+      T1 = __dadd_rn(T1, __dmul_rn(dl, (double)sv[x]));
+    } else {
+#pragma unroll
+      for (int e = 0; e < kPwlExtras; ++e) if (x - NS == e) DLx[e] = dl;
+    }
+  }
+  // sweep: P0/P1 = sums over the ranks below r; a unit entering at r sees total - prefix, a unit leaving at r the prefix
+  double P0 = 0.0, P1 = 0.0;
+  int e = 0;
+  for (int r = 0; r <= NS; ++r) {
+    while (e < H) {
+      const int j = ord[e];
+      const unsigned v = ev[j];
+      if ((int)(v & 0x7fff) != r) break;
+      double M0 = (v & 0x8000) ? P0 : __dsub_rn(T0, P0), M1 = (v & 0x8000) ? P1 : __dsub_rn(T1, P1);
+      const float w = w1[j], b = b1[j];
+#pragma unroll
+      for (int x2 = 0; x2 < kPwlExtras; ++x2) {
+        if (x2 < nx) {
+          const float s = sv[NS + x2];
+          if (pwl_active(s, w, b)) { M0 = __dadd_rn(M0, DLx[x2]); M1 = __dadd_rn(M1, __dmul_rn(DLx[x2], (double)s)); }
+        }
+      }
+      const float gc = (float)__dadd_rn(__dmul_rn((double)w, M1), __dmul_rn((double)b, M0));  // sum_x DL[x] * h_x[j]
+      if (col) g[2 * H + lane * H + j] = gc;
+      else if (vcol) g[2 * H + A * H + A + j] = gc;
+      const double c = use ? (double)crow[j] : 0.0;
+      const double t0 = warp_sum(__dmul_rn(c, M0)), t1 = warp_sum(__dmul_rn(c, M1));  // back through fc_pi / fc_v into fc1
+      if (lane == 0) { g[j] = (float)t1; g[H + j] = (float)t0; }
+      ++e;
+    }
+    if (r < NS) {
+      const double d = use ? __longlong_as_double(acc[r * C + lane]) : 0.0;
+      P0 = __dadd_rn(P0, d);
+      P1 = __dadd_rn(P1, __dmul_rn(d, (double)sv[r]));
+    }
+  }
+  double tot = T0;
+#pragma unroll
+  for (int x2 = 0; x2 < kPwlExtras; ++x2) if (x2 < nx) tot = __dadd_rn(tot, DLx[x2]);
+  if (col) g[2 * H + A * H + lane] = (float)tot;
+  if (vcol) g[2 * H + A * H + A + H] = (float)tot;
+  pwl_clip_adam(blk, spec, g, lane);
+}
+
+__global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ PwlParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const ThrlGame& G = p.game;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
+  const int n = G.n_agents, T = G.max_steps, E = p.E, NS = p.NS, J = p.J;
+  const bool is_agent = lane < n;
+
+  // ---- CTA-shared tables: per-action quantities, joint action -> price / lattice state / reward share
+  double* lutAQ = reinterpret_cast<double*>(smem);
+  double* lutXT = lutAQ + p.lut_total;
+  double* priceJ = reinterpret_cast<double*>(smem + p.off_priceJ);
+  double* rT = reinterpret_cast<double*>(smem + p.off_rT);  // [J][n] reward / max_steps (trainer.py:63)
+  uint8_t* slot_of = smem + p.off_slotof;
+  {
+    const double ab = __ddiv_rn(G.a, G.b);
+    for (int i = 0; i < n; ++i) {
+      const ThrlAgentSpec& s = G.agent[i];
+      for (int k = threadIdx.x; k < s.actions; k += blockDim.x) {  // Reinforce.scale: k / A (agents.py:154-158)
+        const double x = __dadd_rn(__dmul_rn(__ddiv_rn((double)k, (double)s.actions), __dsub_rn(s.action_hi, s.action_lo)), s.action_lo);
+        lutAQ[p.a_off[i] + k] = __dmul_rn(ab, x);
+        lutXT[p.a_off[i] + k] = __ddiv_rn(x, (double)T);
+      }
+    }
+    for (int j = threadIdx.x; j < J; j += blockDim.x) { priceJ[j] = p.priceJ[j]; slot_of[j] = p.slot_of[j]; }
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < J * n; idx += blockDim.x) {
+    const int j = idx / n, i = idx - j * n;
+    const int k = (j / p.jmul[i]) % G.agent[i].actions;
+    rT[idx] = __ddiv_rn(__dmul_rn(priceJ[j], lutAQ[p.a_off[i] + k]), (double)T);
+  }
+  __syncthreads();
+
+  unsigned char* slot = smem + p.cta_bytes + (size_t)warp * p.warp_bytes;
+  float* sv = reinterpret_cast<float*>(slot + p.off_sv);      // [NS + extras] state values
+  float* cdfb = reinterpret_cast<float*>(slot + p.off_cdf);   // per agent [NS + extras][A] running sums of pi(.|s)
+  float* valb = reinterpret_cast<float*>(slot + p.off_val);   // per agent [NS + extras] v(s)
+  int32_t* pre = reinterpret_cast<int32_t*>(slot + p.off_pre);  // [T][n] forced action, or 0x80000000 | 24-bit uniform
+  uint16_t* ev = reinterpret_cast<uint16_t*>(slot + p.off_ev);
+  uint16_t* ord = reinterpret_cast<uint16_t*>(slot + p.off_ord);
+  uint16_t* bkt = reinterpret_cast<uint16_t*>(slot + p.off_bkt);
+  unsigned char* wsw = p.ws + ((size_t)blockIdx.x * wpc + warp) * p.ws_warp_bytes;
+  long long* acc = reinterpret_cast<long long*>(wsw + p.ws_acc);
+  float* pws = reinterpret_cast<float*>(wsw + p.ws_p);
+  float* gws = reinterpret_cast<float*>(wsw + p.ws_grad);
+  float4* xs = reinterpret_cast<float4*>(wsw + p.ws_xs);
+  for (int x = lane; x < NS; x += 32) sv[x] = p.slot_val[x];
+
+  int my_cap = 0, my_aoff = 0, my_EW = 3, my_P = 0;
+  long long my_off = 0;
+  if (is_agent) {
+    const ThrlAgentSpec& s = G.agent[lane];
+    my_cap = G.mlp_buffer_len[lane];
+    my_aoff = p.a_off[lane];
+    my_EW = mlp_entry_words(s);
+    my_P = mlp_P(s);
+    my_off = s.mlp_offset;
+  }
+
+  const long long total_warps = (long long)gridDim.x * wpc;
+  for (long long r = (long long)blockIdx.x * wpc + warp; r < p.n_runs; r += total_warps) {
+    float* slab = p.mlp + r * G.mlp_stride;
+    const uint32_t gid = (uint32_t)(p.run_id0 + r);
+    double price = p.price[r];
+    int nx = 0;
+    bool overflow = false;
+    auto find_or_insert = [&](float s) {  // warp-uniform s
+      int x = pwl_find(sv, NS, nx, s);
+      if (x < 0) {
+        if (nx < kPwlExtras) {
+          __syncwarp();
+          if (lane == 0) sv[NS + nx] = s;
+          __syncwarp();
+          x = NS + nx;
+          ++nx;
+        } else {
+          overflow = true;
+          x = NS + kPwlExtras - 1;
+        }
+      }
+      return x;
+    };
+    __syncwarp();
+    int x = find_or_insert((float)price);
+    // transitions pending from the previous call may hold off-lattice states too
+    int my_len = 0, my_head = 0;
+    float* my_buf = nullptr;
+    int32_t* my_hdr = nullptr;
+    if (is_agent) {
+      float* blk = slab + my_off;
+      my_hdr = reinterpret_cast<int32_t*>(blk + 3 * (size_t)my_P);
+      my_buf = blk + 3 * (size_t)my_P + THRL_MLP_HEADER_WORDS;
+      if (my_cap > 0) { my_len = my_hdr[1]; my_head = my_hdr[2]; }
+    }
+    for (int i = 0; i < n; ++i) {
+      const ThrlAgentSpec& s = G.agent[i];
+      const int L = __shfl_sync(kFull, my_len, i), hd = __shfl_sync(kFull, my_head, i), cap = G.mlp_buffer_len[i];
+      const int EW = mlp_entry_words(s);
+      const float* buf = slab + s.mlp_offset + 3 * (size_t)mlp_P(s) + THRL_MLP_HEADER_WORDS;
+      for (int b0 = 0; b0 < L; b0 += 32) {
+        const int nn = b0 + lane;
+        float s0 = 0.0f, s1 = 0.0f;
+        bool m0 = false, m1 = false;
+        if (nn < L) {
+          int sl = hd + nn;
+          if (sl >= cap) sl -= cap;
+          s0 = buf[(size_t)sl * EW];
+          m0 = pwl_find(sv, NS, nx, s0) < 0;
+          if (EW == 4) { s1 = buf[(size_t)sl * EW + 3]; m1 = pwl_find(sv, NS, nx, s1) < 0; }
+        }
+        unsigned mm = __ballot_sync(kFull, m0);
+        while (mm) { const int l = __ffs(mm) - 1; mm &= mm - 1; (void)find_or_insert(__shfl_sync(kFull, s0, l)); }
+        mm = __ballot_sync(kFull, m1);
+        while (mm) { const int l = __ffs(mm) - 1; mm &= mm - 1; (void)find_or_insert(__shfl_sync(kFull, s1, l)); }
+      }
+    }
+    for (int i = 0; i < n; ++i) {
+      const ThrlAgentSpec& s = G.agent[i];
+      const float* blk = slab + s.mlp_offset;
+      pwl_unit_events(blk, blk + s.hidden, s.hidden, sv, NS, ev, ord, bkt, lane);
+      pwl_build_lut(blk, s, sv, NS, nx, ev, ord, cdfb + p.cdf_off[i], valb + p.val_off[i], pws + p.cdf_off[i], lane);
+    }
+
+    for (int e = 0; e < E; ++e) {
+      const uint32_t eabs = (uint32_t)(p.epoch_begin + e);
+      const long long step0 = (r * E + e) * (long long)T;
+      // ---- per-episode draws: a forced action in the replay modes, else the 24-bit uniform of Categorical.sample()
+      for (int idx = lane; idx < T * n; idx += 32) {
+        const int t = idx / n, i = idx - t * n;
+        int v = p.rng_mode == THRL_RNG_PHILOX ? -1 : p.replay_ra[step0 * n + idx];
+        if (v < 0) {
+          uint32_t xr[4];
+          philox4x32_10(gid, eabs, (uint32_t)t, (uint32_t)(i >> 1) | (kStreamAct << 16), p.k0, p.k1, xr);
+          v = (int)(0x80000000u | (xr[2 * (i & 1)] >> 8));
+        }
+        pre[idx] = v;
+      }
+      __syncwarp();
+
+      // ---- the episode (trainer.py:50-67): pi(.|s) is a row of the CDF LUT, the environment a table of the joint action
+      double rlog = 0.0, alog = 0.0;
+      for (int t = 0; t < T; ++t) {
+        int joint = 0, kmine = 0;
+        for (int i = 0; i < n; ++i) {
+          const int v = pre[t * n + i];
+          const int Ai = G.agent[i].actions;
+          int k = v;
+          if (v < 0) {  // first k with cumsum(pi)[k] > u (agents.py:160-163), last action if none
+            const float u = __fmul_rn((float)(v & 0xffffff), 1.0f / 16777216.0f);
+            const float c = lane < Ai ? cdfb[p.cdf_off[i] + x * Ai + lane] : 0.0f;
+            const unsigned m = __ballot_sync(kFull, lane < Ai && c > u);
+            k = m ? __ffs(m) - 1 : Ai - 1;
+          }
+          joint += k * p.jmul[i];
+          if (lane == i) kmine = k;
+        }
+        const double next_price = priceJ[joint];
+        const int xn = slot_of[joint];
+        if (is_agent) {
+          const double rew = __dmul_rn(next_price, lutAQ[my_aoff + kmine]);
+          rlog = __dadd_rn(rlog, rT[joint * n + lane]);
+          alog = __dadd_rn(alog, lutXT[my_aoff + kmine]);
+          if (my_cap > 0) {  // memory.append; replay(cast) makes state and reward float32 (buffers.py:28-38, agents.py:142)
+            int sl;
+            if (my_len < my_cap) { sl = my_head + my_len; if (sl >= my_cap) sl -= my_cap; my_len++; }
+            else { sl = my_head; my_head = my_head + 1 == my_cap ? 0 : my_head + 1; }
+            float* en = my_buf + (size_t)sl * my_EW;
+            en[0] = sv[x];
+            en[1] = __int_as_float(kmine);
+            en[2] = (float)rew;
+            if (my_EW == 4) en[3] = (float)next_price;
+          }
+          if (p.trace_actions) p.trace_actions[(step0 + t) * n + lane] = kmine;
+          if (p.trace_rewards) p.trace_rewards[(step0 + t) * n + lane] = rew;
+        }
+        if (lane == 0 && p.trace_prices) p.trace_prices[step0 + t] = next_price;
+        x = xn;
+        price = next_price;
+      }
+      __syncwarp();
+
+      // ---- train_net for every agent in order (trainer.py:70), then the agent's LUTs of the new parameters
+      for (int i = 0; i < n; ++i) {
+        const ThrlAgentSpec& s = G.agent[i];
+        const int cap = G.mlp_buffer_len[i];
+        if (cap == 0) continue;
+        const int L = __shfl_sync(kFull, my_len, i), hd = __shfl_sync(kFull, my_head, i);
+        if (L < s.min_memory) continue;
+        float* blk = slab + s.mlp_offset;
+        pwl_train(blk, s, cap, hd, L, sv, NS, nx, ev, ord, bkt, valb + p.val_off[i], pws + p.cdf_off[i], acc, gws, xs, lane);
+        if (lane == i) { my_len = 0; my_head = 0; }  // :194 memory.empty()
+        pwl_unit_events(blk, blk + s.hidden, s.hidden, sv, NS, ev, ord, bkt, lane);
+        pwl_build_lut(blk, s, sv, NS, nx, ev, ord, cdfb + p.cdf_off[i], valb + p.val_off[i], pws + p.cdf_off[i], lane);
+      }
+      if (is_agent) {
+        if (r < p.n_log_runs) {
+          if (p.rewards_log) p.rewards_log[(r * E + e) * n + lane] = rlog;
+          if (p.actions_log) p.actions_log[(r * E + e) * n + lane] = alog;
+        }
+        if (p.stats) {
+          unsigned long long* s4 = reinterpret_cast<unsigned long long*>(p.stats) + ((size_t)e * n + lane) * THRL_STATS_K;
+          atomicAdd(s4 + 0, (unsigned long long)fx_round(__dmul_rn(rlog, THRL_STATS_SCALE_SUM)));
+          atomicAdd(s4 + 1, (unsigned long long)fx_round(__dmul_rn(__dmul_rn(rlog, rlog), THRL_STATS_SCALE_SQ)));
+          atomicAdd(s4 + 2, (unsigned long long)fx_round(__dmul_rn(alog, THRL_STATS_SCALE_SUM)));
+          atomicAdd(s4 + 3, (unsigned long long)fx_round(__dmul_rn(__dmul_rn(alog, alog), THRL_STATS_SCALE_SQ)));
+        }
+      }
+      __syncwarp();
+    }
+
+    if (is_agent && my_cap > 0) { my_hdr[1] = my_len; my_hdr[2] = my_head; }
+    if (overflow && lane == 0) slab[G.agent[0].mlp_offset] = __int_as_float(0x7fc00000);  // more off-lattice states than kPwlExtras: fail loudly
+    if (lane == 0) p.price[r] = price;
+    __syncwarp();
+  }
+}
+
+}  // namespace thrl

@@ -73,7 +73,7 @@ def _c5_cfg(epochs):
 
 
 # ~1.1e4 flop per act + ~3.4e4 flop per agent-step of amortised update (N = 1000 batch every 10 episodes)
-WORKLOADS["c5"] = dict(agents=2, runs_per_gpu=16384, epochs=20, config=_c5_cfg(20), algo_bytes=4.5e4, bound="tensor", hp=None,
+WORKLOADS["c5"] = dict(agents=2, runs_per_gpu=16384, epochs=200, config=_c5_cfg(200), algo_bytes=4.5e4, bound="tensor", hp=None,
                        desc="2 ActorCritic agents (MLP 1->256->{21,1}, Adam, N=1000 transition batches every 10 episodes), "
                             "%d runs/GPU x %d epochs per step (C5 shape)",
                        kernel="thrl::mlp_scan_pwl (persistent, one launch per step; policy LUT per lattice state + sorted-breakpoint "

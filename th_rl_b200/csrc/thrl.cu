@@ -14,6 +14,7 @@
 #include <atomic>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <vector>
 
@@ -509,6 +510,7 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, int smem_optin, int* warps) {
   int o = align_up(2 * lut * 8, 16);
   p->off_priceJ = o; o += align_up((int)J * 8, 16);
   p->off_rT = o;     o += align_up((int)J * n * 8, 16);
+  p->off_rF = o;     o += align_up((int)J * n * 4, 16);
   p->off_slotof = o; o += align_up((int)J, 16);
   p->cta_bytes = o;
   o = 0;
@@ -526,6 +528,7 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, int smem_optin, int* warps) {
   // per-warp workspace in global memory
   long long w = 0;
   p->ws_acc = w;  w += align_up(NSX * (Amax + 2) * 8, 16);
+  p->ws_pf = w;   w += align_up((NSX + 1) * (Amax + 1) * 16, 16);
   p->ws_p = w;    w += align_up(cdf * 4, 16);
   p->ws_grad = w; w += align_up(Pmax * 4, 16);
   p->ws_xs = w;   w += (long long)(capmax > 0 ? capmax : 1) * 16;
@@ -548,10 +551,31 @@ int launch_pwl(thrl::PwlParams& p, int warps, const DeviceInfo& dev, cudaStream_
     if (grid > dev.sms) grid = dev.sms;
   }
   const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
+  // Stream-ordered scratch from the library's own pool (one per device).  The pool keeps what it has been given instead
+  // of returning it to the driver at every synchronisation (release threshold), so steady-state calls allocate nothing.
+  static cudaMemPool_t pools[64] = {};
+  static std::mutex pool_mu;
+  int device = 0;
+  CUDA_TRY(cudaGetDevice(&device));
+  cudaMemPool_t pool = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(pool_mu);
+    if (device < 0 || device >= 64) return fail(THRL_ERR_BAD_ARGS, "device index %d", device);
+    if (!pools[device]) {
+      cudaMemPoolProps props = {};
+      props.allocType = cudaMemAllocationTypePinned;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = device;
+      CUDA_TRY(cudaMemPoolCreate(&pools[device], &props));
+      unsigned long long keep = ~0ull;
+      CUDA_TRY(cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    pool = pools[device];
+  }
   void* ws = nullptr;
-  CUDA_TRY(cudaMallocAsync(&ws, (size_t)grid * warps * (size_t)p.ws_warp_bytes, stream));  // stream-ordered scratch
+  CUDA_TRY(cudaMallocFromPoolAsync(&ws, (size_t)grid * warps * (size_t)p.ws_warp_bytes, pool, stream));
   p.ws = (unsigned char*)ws;
-  auto kern = thrl::mlp_scan_pwl;
+  auto kern = p.game.n_agents == 2 ? thrl::mlp_scan_pwl<2> : thrl::mlp_scan_pwl<0>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
     kern<<<grid, warps * 32, smem, stream>>>(p);

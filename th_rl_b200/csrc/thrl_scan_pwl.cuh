@@ -44,13 +44,13 @@ struct PwlParams {
   double* trace_prices;
   float* mlp;
   unsigned char* ws;  // per resident warp: accumulators, probability LUT, gradient, per-sample scratch
-  long long ws_warp_bytes, ws_acc, ws_p, ws_grad, ws_xs;
+  long long ws_warp_bytes, ws_acc, ws_pf, ws_p, ws_grad, ws_xs;
   int J, NS, lut_total;
   int a_off[THRL_MAX_AGENTS];    // agent's offset in the per-action tables
   int jmul[THRL_MAX_AGENTS];     // joint index = sum_i action_i * jmul[i]
   int cdf_off[THRL_MAX_AGENTS];  // float offset of the agent's CDF LUT [NS + extras][A] (shared memory and ws_p alike)
   int val_off[THRL_MAX_AGENTS];  // float offset of the agent's v(s) LUT [NS + extras]
-  int cta_bytes, off_priceJ, off_rT, off_slotof;
+  int cta_bytes, off_priceJ, off_rT, off_rF, off_slotof;
   int warp_bytes, off_sv, off_cdf, off_val, off_pre, off_ev, off_ord, off_bkt;
   float slot_val[kPwlMaxLattice];   // lattice states, ascending
   uint8_t slot_of[kPwlMaxJoint];    // joint action -> lattice state
@@ -92,7 +92,7 @@ __device__ __forceinline__ bool pwl_active(float s, float w, float b) { return _
 // ev[j] = key | leave << 15:  leave = 0: unit j is active on ranks [key, NS);  leave = 1: active on ranks [0, key).
 // ord[0..H): unit indices sorted by key (stable in j, so the result does not depend on the schedule).
 __device__ inline void pwl_unit_events(const float* w1, const float* b1, int H, const float* sv, int NS, uint16_t* ev,
-                                       uint16_t* ord, uint16_t* bkt, int lane) {
+                                       uint16_t* ord, uint16_t* bkt, int lane, bool sort = true) {
   const int NB = NS + 2;
   __syncwarp();
   for (int b = lane; b < NB; b += 32) bkt[b] = 0;
@@ -124,10 +124,13 @@ __device__ inline void pwl_unit_events(const float* w1, const float* b1, int H, 
       ev[j] = (uint16_t)(key | (leave << 15));
       kk = (unsigned)key;
     }
-    const unsigned peers = __match_any_sync(kFull, kk);
-    if (j < H && (peers & lanemask_lt()) == 0) bkt[kk + 1] += (uint16_t)__popc(peers);
+    if (sort) {
+      const unsigned peers = __match_any_sync(kFull, kk);
+      if (j < H && (peers & lanemask_lt()) == 0) bkt[kk + 1] += (uint16_t)__popc(peers);
+    }
     __syncwarp();
   }
+  if (!sort) return;
   {  // inclusive scan: afterwards bkt[k] = first position of bucket k
     const int per = (NB + 31) / 32;
     const int beg = lane * per, end = beg + per < NB ? beg + per : NB;
@@ -239,9 +242,7 @@ __device__ inline void pwl_clip_adam(float* blk, const ThrlAgentSpec& spec, cons
   __syncwarp();
   double part = 0.0;
   for (int i = lane; i < P; i += 32) { const double gd = (double)g[i]; part = __dadd_rn(part, __dmul_rn(gd, gd)); }
-  double tot = 0.0;
-  for (int l = 0; l < 32; ++l) tot = __dadd_rn(tot, shfl_d(part, l));
-  const float total_norm = (float)sqrt(tot);
+  const float total_norm = (float)sqrt(warp_sum(part));
   float coef = __fdiv_rn(1.0f, __fadd_rn(total_norm, 1e-6f));
   if (coef > 1.0f) coef = 1.0f;
   const int step = hdr[0] + 1;
@@ -251,6 +252,7 @@ __device__ inline void pwl_clip_adam(float* blk, const ThrlAgentSpec& spec, cons
   const float neg_step_size = (float)(-__ddiv_rn(spec.lr, bc1));
   const float bc2_sqrt = (float)sqrt(bc2);
   const float w1m = (float)__dsub_rn(1.0, 0.9), fb2 = (float)0.999, w2 = (float)__dsub_rn(1.0, 0.999), eps = 1e-8f;
+#pragma unroll 4
   for (int i = lane; i < P; i += 32) {
     const float gi = __fmul_rn(g[i], coef);
     float m = am[i], v = av[i];
@@ -271,11 +273,11 @@ __device__ inline void pwl_clip_adam(float* blk, const ThrlAgentSpec& spec, cons
 // samples and hidden units are re-associated.  val: v(s) LUT of the current parameters; pws: their pi(.|s) LUT.
 __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap, int head, int N, const float* sv, int NS,
                                  int nx, uint16_t* ev, uint16_t* ord, uint16_t* bkt, const float* val, const float* pws,
-                                 long long* acc, float* g, float4* xs, int lane) {
+                                 long long* acc, double2* pf, float* g, float4* xs, int lane) {
   const int H = spec.hidden, A = spec.actions, P = mlp_P(spec), EW = mlp_entry_words(spec);
   const bool ac = spec.kind == THRL_AGENT_ACTORCRITIC;
   float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
-  const float *w1 = blk, *b1 = blk + H, *W = blk + 2 * H, *wv = W + (size_t)A * H + A;
+  const float *w1 = blk, *b1 = blk + H;
   const int C = A + 2;  // accumulator columns per state: [0, A) state x action, A: value head, A + 1: state total
   const int NX = NS + nx;
   const float gam = (float)spec.gamma;
@@ -376,73 +378,83 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
     }
   }
   __syncwarp();
-  pwl_unit_events(w1, b1, H, sv, NS, ev, ord, bkt, lane);
-  // per-state gradient coefficients of this lane's column: DL[x][k] = pi(k|x) * CA[x] - CAa[x][k]; value lane: CV[x]
+  pwl_unit_events(w1, b1, H, sv, NS, ev, ord, bkt, lane, /*sort=*/false);
+  // ---- lane = column (action k, or the value head): per-state gradient coefficients
+  //   DL[x][k] = pi(k|x) * CA[x] - CAa[x][k],  DL[x][A] = CV[x]
+  // and their running sums over the sorted lattice, pf[r][c] = (sum_{x<r} DL[x][c], sum_{x<r} DL[x][c] * s_x), r = 0..NS
+  // (row NS = totals); rows NS+1.. hold (DL, DL * s) of the extra states.
   const bool col = lane < A, vcol = ac && lane == A, use = col || vcol;
-  const float* crow = col ? W + (size_t)lane * H : wv;
+  const int CW = A + 1;
   const double isa = __ddiv_rn(1.0, sa), isc = __ddiv_rn(1.0, sc);
-  double T0 = 0.0, T1 = 0.0, DLx[kPwlExtras];
-#pragma unroll
-  for (int e = 0; e < kPwlExtras; ++e) DLx[e] = 0.0;
-  for (int x = 0; x < NX; ++x) {
-    double dl = 0.0;
-    if (use) {
-      const double raw = (double)__ldcg(acc + x * C + lane);
-      if (col) {
-        const double cax = __dmul_rn((double)__ldcg(acc + x * C + A + 1), isa);
-        dl = __dsub_rn(__dmul_rn((double)pws[x * A + lane], cax), __dmul_rn(raw, isa));
-      } else {
-        dl = __dmul_rn(raw, isc);
-      }
-    }
-    if (x < NS) {
-      if (use) acc[x * C + lane] = __double_as_longlong(dl);  // own column: read back by this lane in the sweep
-      T0 = __dadd_rn(T0, dl);
-      T1 = __dadd_rn(T1, __dmul_rn(dl, (double)sv[x]));
-    } else {
-#pragma unroll
-      for (int e = 0; e < kPwlExtras; ++e) if (x - NS == e) DLx[e] = dl;
-    }
-  }
-  // sweep: P0/P1 = sums over the ranks below r; a unit entering at r sees total - prefix, a unit leaving at r the prefix
-  double P0 = 0.0, P1 = 0.0;
-  int e = 0;
-  for (int r = 0; r <= NS; ++r) {
-    while (e < H) {
-      const int j = ord[e];
-      const unsigned v = ev[j];
-      if ((int)(v & 0x7fff) != r) break;
-      double M0 = (v & 0x8000) ? P0 : __dsub_rn(T0, P0), M1 = (v & 0x8000) ? P1 : __dsub_rn(T1, P1);
-      const float w = w1[j], b = b1[j];
-#pragma unroll
-      for (int x2 = 0; x2 < kPwlExtras; ++x2) {
-        if (x2 < nx) {
-          const float s = sv[NS + x2];
-          if (pwl_active(s, w, b)) { M0 = __dadd_rn(M0, DLx[x2]); M1 = __dadd_rn(M1, __dmul_rn(DLx[x2], (double)s)); }
+  {
+    double P0 = 0.0, P1 = 0.0, tot = 0.0;
+    for (int x = 0; x < NX; ++x) {
+      double dl = 0.0;
+      if (use) {
+        const double raw = (double)__ldcg(acc + x * C + lane);
+        if (col) {
+          const double cax = __dmul_rn((double)__ldcg(acc + x * C + A + 1), isa);
+          dl = __dsub_rn(__dmul_rn((double)pws[x * A + lane], cax), __dmul_rn(raw, isa));
+        } else {
+          dl = __dmul_rn(raw, isc);
         }
+        const double ds = __dmul_rn(dl, (double)sv[x]);
+        if (x < NS) {
+          pf[x * CW + lane] = make_double2(P0, P1);
+          P0 = __dadd_rn(P0, dl);
+          P1 = __dadd_rn(P1, ds);
+        } else {
+          pf[(x + 1) * CW + lane] = make_double2(dl, ds);
+        }
+        tot = __dadd_rn(tot, dl);
       }
-      const float gc = (float)__dadd_rn(__dmul_rn((double)w, M1), __dmul_rn((double)b, M0));  // sum_x DL[x] * h_x[j]
-      if (col) g[2 * H + lane * H + j] = gc;
-      else if (vcol) g[2 * H + A * H + A + j] = gc;
-      const double c = use ? (double)crow[j] : 0.0;
-      const double t0 = warp_sum(__dmul_rn(c, M0)), t1 = warp_sum(__dmul_rn(c, M1));  // back through fc_pi / fc_v into fc1
-      if (lane == 0) { g[j] = (float)t1; g[H + j] = (float)t0; }
-      ++e;
     }
-    if (r < NS) {
-      const double d = use ? __longlong_as_double(acc[r * C + lane]) : 0.0;
-      P0 = __dadd_rn(P0, d);
-      P1 = __dadd_rn(P1, __dmul_rn(d, (double)sv[r]));
+    if (use) pf[NS * CW + lane] = make_double2(P0, P1);
+    if (col) g[2 * H + A * H + lane] = (float)tot;      // fc_pi.bias
+    if (vcol) g[2 * H + A * H + A + H] = (float)tot;    // fc_v.bias
+  }
+  __syncwarp();
+  // ---- lane = hidden unit: unit j is active on the ranks [key, NS) or [0, key), so with M0/M1 = the sums of DL, DL * s
+  // over its active states:  d/dW[k][j] = w1_j * M1 + b1_j * M0 (= sum_x DL[x][k] * h_x[j]),
+  // d/db1[j] = sum_c W[c][j] * M0[c], d/dw1[j] = sum_c W[c][j] * M1[c]   (c runs over the actions and the value head)
+  const int NC = ac ? A + 1 : A;
+  for (int j0 = 0; j0 < H; j0 += 32) {
+    const int j = j0 + lane;
+    if (j < H) {
+      const float w = w1[j], b = b1[j];
+      const unsigned evj = ev[j];
+      const int key = (int)(evj & 0x7fff);
+      const bool leave = (evj & 0x8000) != 0;
+      unsigned xm = 0;
+      for (int e2 = 0; e2 < nx; ++e2) xm |= pwl_active(sv[NS + e2], w, b) ? 1u << e2 : 0u;
+      double gw = 0.0, gb = 0.0;
+#pragma unroll 2
+      for (int c = 0; c < NC; ++c) {
+        const double2 pre = pf[key * CW + c], tt = pf[NS * CW + c];
+        double M0 = leave ? pre.x : __dsub_rn(tt.x, pre.x), M1 = leave ? pre.y : __dsub_rn(tt.y, pre.y);
+        for (int e2 = 0; e2 < nx; ++e2) {
+          if (xm >> e2 & 1) {
+            const double2 dx = pf[(NS + 1 + e2) * CW + c];
+            M0 = __dadd_rn(M0, dx.x);
+            M1 = __dadd_rn(M1, dx.y);
+          }
+        }
+        const float gc = (float)__dadd_rn(__dmul_rn((double)w, M1), __dmul_rn((double)b, M0));
+        const int wi = c < A ? 2 * H + c * H + j : 2 * H + A * H + A + j;  // fc_pi.weight[c][j] / fc_v.weight[j]
+        g[wi] = gc;
+        const double cw = (double)blk[wi];
+        gb = __dadd_rn(gb, __dmul_rn(cw, M0));
+        gw = __dadd_rn(gw, __dmul_rn(cw, M1));
+      }
+      g[j] = (float)gw;
+      g[H + j] = (float)gb;
     }
   }
-  double tot = T0;
-#pragma unroll
-  for (int x2 = 0; x2 < kPwlExtras; ++x2) if (x2 < nx) tot = __dadd_rn(tot, DLx[x2]);
-  if (col) g[2 * H + A * H + lane] = (float)tot;
-  if (vcol) g[2 * H + A * H + A + H] = (float)tot;
   pwl_clip_adam(blk, spec, g, lane);
 }
 
+// kN: number of agents when it is 2 (the agent loop of the episode is unrolled with its constants in registers), else 0
+template <int kN>
 __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ PwlParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ThrlGame& G = p.game;
@@ -455,6 +467,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
   double* lutXT = lutAQ + p.lut_total;
   double* priceJ = reinterpret_cast<double*>(smem + p.off_priceJ);
   double* rT = reinterpret_cast<double*>(smem + p.off_rT);  // [J][n] reward / max_steps (trainer.py:63)
+  float* rF = reinterpret_cast<float*>(smem + p.off_rF);    // [J][n] reward as the float32 the buffers hold (agents.py:142)
   uint8_t* slot_of = smem + p.off_slotof;
   {
     const double ab = __ddiv_rn(G.a, G.b);
@@ -472,7 +485,9 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
   for (int idx = threadIdx.x; idx < J * n; idx += blockDim.x) {
     const int j = idx / n, i = idx - j * n;
     const int k = (j / p.jmul[i]) % G.agent[i].actions;
-    rT[idx] = __ddiv_rn(__dmul_rn(priceJ[j], lutAQ[p.a_off[i] + k]), (double)T);
+    const double rew = __dmul_rn(priceJ[j], lutAQ[p.a_off[i] + k]);
+    rT[idx] = __ddiv_rn(rew, (double)T);
+    rF[idx] = (float)rew;
   }
   __syncthreads();
 
@@ -487,6 +502,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
   unsigned char* wsw = p.ws + ((size_t)blockIdx.x * wpc + warp) * p.ws_warp_bytes;
   long long* acc = reinterpret_cast<long long*>(wsw + p.ws_acc);
   float* pws = reinterpret_cast<float*>(wsw + p.ws_p);
+  double2* pfw = reinterpret_cast<double2*>(wsw + p.ws_pf);
   float* gws = reinterpret_cast<float*>(wsw + p.ws_grad);
   float4* xs = reinterpret_cast<float4*>(wsw + p.ws_xs);
   for (int x = lane; x < NS; x += 32) sv[x] = p.slot_val[x];
@@ -502,11 +518,16 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
     my_off = s.mlp_offset;
   }
 
+  const bool tracing = p.trace_actions || p.trace_rewards || p.trace_prices;
+  const int A0 = G.agent[0].actions, A1 = G.agent[kN == 2 ? 1 : 0].actions;
+  const float *cdf0 = cdfb + p.cdf_off[0], *cdf1 = cdfb + p.cdf_off[kN == 2 ? 1 : 0];
+
   const long long total_warps = (long long)gridDim.x * wpc;
   for (long long r = (long long)blockIdx.x * wpc + warp; r < p.n_runs; r += total_warps) {
     float* slab = p.mlp + r * G.mlp_stride;
     const uint32_t gid = (uint32_t)(p.run_id0 + r);
-    double price = p.price[r];
+    const double price = p.price[r];
+    int jlast = -1;  // joint action of the latest step: the run's price is priceJ[jlast]
     int nx = 0;
     bool overflow = false;
     auto find_or_insert = [&](float s) {  // warp-uniform s
@@ -528,14 +549,18 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
     __syncwarp();
     int x = find_or_insert((float)price);
     // transitions pending from the previous call may hold off-lattice states too
-    int my_len = 0, my_head = 0;
+    int my_len = 0, my_head = 0, my_wr = 0;  // deque(maxlen = capacity): length, oldest slot (at entry), next slot to write
     float* my_buf = nullptr;
     int32_t* my_hdr = nullptr;
     if (is_agent) {
       float* blk = slab + my_off;
       my_hdr = reinterpret_cast<int32_t*>(blk + 3 * (size_t)my_P);
       my_buf = blk + 3 * (size_t)my_P + THRL_MLP_HEADER_WORDS;
-      if (my_cap > 0) { my_len = my_hdr[1]; my_head = my_hdr[2]; }
+      if (my_cap > 0) {
+        my_len = my_hdr[1]; my_head = my_hdr[2];
+        my_wr = my_head + my_len;
+        if (my_wr >= my_cap) my_wr -= my_cap;
+      }
     }
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
@@ -569,14 +594,17 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
     for (int e = 0; e < E; ++e) {
       const uint32_t eabs = (uint32_t)(p.epoch_begin + e);
       const long long step0 = (r * E + e) * (long long)T;
-      // ---- per-episode draws: a forced action in the replay modes, else the 24-bit uniform of Categorical.sample()
+      // ---- per-episode draws: -1 - action when the action is forced (replay modes), else the bits of the uniform
+      // u = 24 random bits * 2^-24 in [0, 1) that Categorical.sample() is emulated with
       for (int idx = lane; idx < T * n; idx += 32) {
         const int t = idx / n, i = idx - t * n;
         int v = p.rng_mode == THRL_RNG_PHILOX ? -1 : p.replay_ra[step0 * n + idx];
         if (v < 0) {
           uint32_t xr[4];
           philox4x32_10(gid, eabs, (uint32_t)t, (uint32_t)(i >> 1) | (kStreamAct << 16), p.k0, p.k1, xr);
-          v = (int)(0x80000000u | (xr[2 * (i & 1)] >> 8));
+          v = __float_as_int(__fmul_rn((float)(xr[2 * (i & 1)] >> 8), 1.0f / 16777216.0f));
+        } else {
+          v = -1 - v;
         }
         pre[idx] = v;
       }
@@ -584,43 +612,51 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
 
       // ---- the episode (trainer.py:50-67): pi(.|s) is a row of the CDF LUT, the environment a table of the joint action
       double rlog = 0.0, alog = 0.0;
+      // first k with cumsum(pi)[k] > u (agents.py:160-163), the last action if there is none
+      auto pick = [&](int v, const float* cdf, int Ai) {
+        if (v < 0) return -1 - v;
+        const float c = lane < Ai ? cdf[x * Ai + lane] : 0.0f;
+        const unsigned m = __ballot_sync(kFull, lane < Ai && c > __int_as_float(v));
+        return m ? __ffs(m) - 1 : Ai - 1;
+      };
       for (int t = 0; t < T; ++t) {
         int joint = 0, kmine = 0;
-        for (int i = 0; i < n; ++i) {
-          const int v = pre[t * n + i];
-          const int Ai = G.agent[i].actions;
-          int k = v;
-          if (v < 0) {  // first k with cumsum(pi)[k] > u (agents.py:160-163), last action if none
-            const float u = __fmul_rn((float)(v & 0xffffff), 1.0f / 16777216.0f);
-            const float c = lane < Ai ? cdfb[p.cdf_off[i] + x * Ai + lane] : 0.0f;
-            const unsigned m = __ballot_sync(kFull, lane < Ai && c > u);
-            k = m ? __ffs(m) - 1 : Ai - 1;
+        if (kN == 2) {
+          const int2 v = *reinterpret_cast<const int2*>(pre + 2 * t);
+          const int k0 = pick(v.x, cdf0, A0), k1 = pick(v.y, cdf1, A1);
+          joint = k0 * A1 + k1;
+          kmine = lane == 0 ? k0 : k1;
+        } else {
+          for (int i = 0; i < n; ++i) {
+            const int k = pick(pre[t * n + i], cdfb + p.cdf_off[i], G.agent[i].actions);
+            joint += k * p.jmul[i];
+            if (lane == i) kmine = k;
           }
-          joint += k * p.jmul[i];
-          if (lane == i) kmine = k;
         }
-        const double next_price = priceJ[joint];
         const int xn = slot_of[joint];
         if (is_agent) {
-          const double rew = __dmul_rn(next_price, lutAQ[my_aoff + kmine]);
           rlog = __dadd_rn(rlog, rT[joint * n + lane]);
           alog = __dadd_rn(alog, lutXT[my_aoff + kmine]);
           if (my_cap > 0) {  // memory.append; replay(cast) makes state and reward float32 (buffers.py:28-38, agents.py:142)
-            int sl;
-            if (my_len < my_cap) { sl = my_head + my_len; if (sl >= my_cap) sl -= my_cap; my_len++; }
-            else { sl = my_head; my_head = my_head + 1 == my_cap ? 0 : my_head + 1; }
-            float* en = my_buf + (size_t)sl * my_EW;
+            float* en = my_buf + (size_t)my_wr * my_EW;
             en[0] = sv[x];
             en[1] = __int_as_float(kmine);
-            en[2] = (float)rew;
-            if (my_EW == 4) en[3] = (float)next_price;
+            en[2] = rF[joint * n + lane];
+            if (my_EW == 4) en[3] = sv[xn];
+            my_wr = my_wr + 1 == my_cap ? 0 : my_wr + 1;
+            my_len = my_len < my_cap ? my_len + 1 : my_cap;
           }
-          if (p.trace_actions) p.trace_actions[(step0 + t) * n + lane] = kmine;
-          if (p.trace_rewards) p.trace_rewards[(step0 + t) * n + lane] = rew;
         }
-        if (lane == 0 && p.trace_prices) p.trace_prices[step0 + t] = next_price;
+        if (tracing) {
+          const double next_price = priceJ[joint];
+          if (is_agent) {
+            if (p.trace_actions) p.trace_actions[(step0 + t) * n + lane] = kmine;
+            if (p.trace_rewards) p.trace_rewards[(step0 + t) * n + lane] = __dmul_rn(next_price, lutAQ[my_aoff + kmine]);
+          }
+          if (lane == 0 && p.trace_prices) p.trace_prices[step0 + t] = next_price;
+        }
         x = xn;
-        price = next_price;
+        jlast = joint;
       }
       __syncwarp();
 
@@ -629,11 +665,13 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
         const ThrlAgentSpec& s = G.agent[i];
         const int cap = G.mlp_buffer_len[i];
         if (cap == 0) continue;
-        const int L = __shfl_sync(kFull, my_len, i), hd = __shfl_sync(kFull, my_head, i);
+        const int L = __shfl_sync(kFull, my_len, i);
         if (L < s.min_memory) continue;
+        int hd = __shfl_sync(kFull, my_wr, i) - L;  // oldest buffered transition
+        if (hd < 0) hd += cap;
         float* blk = slab + s.mlp_offset;
-        pwl_train(blk, s, cap, hd, L, sv, NS, nx, ev, ord, bkt, valb + p.val_off[i], pws + p.cdf_off[i], acc, gws, xs, lane);
-        if (lane == i) { my_len = 0; my_head = 0; }  // :194 memory.empty()
+        pwl_train(blk, s, cap, hd, L, sv, NS, nx, ev, ord, bkt, valb + p.val_off[i], pws + p.cdf_off[i], acc, pfw, gws, xs, lane);
+        if (lane == i) { my_len = 0; my_wr = 0; }  // :194 memory.empty()
         pwl_unit_events(blk, blk + s.hidden, s.hidden, sv, NS, ev, ord, bkt, lane);
         pwl_build_lut(blk, s, sv, NS, nx, ev, ord, cdfb + p.cdf_off[i], valb + p.val_off[i], pws + p.cdf_off[i], lane);
       }
@@ -653,9 +691,14 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
       __syncwarp();
     }
 
-    if (is_agent && my_cap > 0) { my_hdr[1] = my_len; my_hdr[2] = my_head; }
+    if (is_agent && my_cap > 0) {
+      int hd = my_wr - my_len;
+      if (hd < 0) hd += my_cap;
+      my_hdr[1] = my_len;
+      my_hdr[2] = my_len ? hd : 0;
+    }
     if (overflow && lane == 0) slab[G.agent[0].mlp_offset] = __int_as_float(0x7fc00000);  // more off-lattice states than kPwlExtras: fail loudly
-    if (lane == 0) p.price[r] = price;
+    if (lane == 0 && jlast >= 0) p.price[r] = priceJ[jlast];
     __syncwarp();
   }
 }

@@ -167,7 +167,7 @@ __device__ __forceinline__ void pwl_emit(float z, bool col, bool vcol, int A, in
   const float mx = warp_max(col ? z : NegInf<float>::v());
   const float ex = col ? det_expf(__fsub_rn(z, mx)) : 0.0f;
   const float sum = warp_sum(ex);
-  const float pk = __fdiv_rn(ex, sum);
+  const float pk = col ? __fdiv_rn(ex, sum) : 0.0f;
   float c = pk;
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
@@ -260,8 +260,11 @@ __device__ inline void pwl_clip_adam(float* blk, const ThrlAgentSpec& spec, cons
     v = __fadd_rn(__fmul_rn(v, fb2), __fmul_rn(__fmul_rn(w2, gi), gi));
     am[i] = m;
     av[i] = v;
-    const float den = __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps);
-    blk[i] = __fadd_rn(blk[i], __fdiv_rn(__fmul_rn(neg_step_size, m), den));
+    // entries whose gradient has been exactly zero so far (units that are inactive on the whole lattice) keep m = v = 0:
+    // same result as the general formula, without sending the warp through the slow paths of sqrt and division
+    const float den = v != 0.0f ? __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps) : eps;
+    const float num = __fmul_rn(neg_step_size, m);
+    blk[i] = __fadd_rn(blk[i], m != 0.0f ? __fdiv_rn(num, den) : num);
   }
   __syncwarp();
   if (lane == 0) hdr[0] = step;

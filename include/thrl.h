@@ -185,6 +185,10 @@ int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dty
                          int32_t iters, const double* price0, double* rewards, double* actions, void* stream);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 int64_t thrl_launch_count(void);
+/* Name of the scan kernel the calling thread's latest thrl_qtable_scan / thrl_qtable_scan_host launched: "lut2", "lpc",
+ * "generic" (Q-table games), "pwl" (lattice kernel for games with Reinforce / ActorCritic agents), "mixed" (order-exact MLP
+ * kernel).  The dispatch is a function of the game, the inputs and THRL_KERNEL; tests use this to check it. */
+const char* thrl_last_kernel(void);
 
 #ifdef __cplusplus
 }

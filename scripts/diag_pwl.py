@@ -23,7 +23,10 @@ def replay(name):
     game = b.game
     print(name, "rewards equal golden:", np.array_equal(res["pwl"][1][0], g["rewards"]), "prices:", np.array_equal(res["pwl"][2][0], g["prices"]))
     for i in range(game.n_agents):
-        s = game.agent[i]; P, o = abi.mlp_param_count(s), s.mlp_offset
+        s = game.agent[i]
+        if s.kind == abi.THRL_AGENT_QTABLE:
+            continue
+        P, o = abi.mlp_param_count(s), s.mlp_offset
         a, m = res["pwl"][0][0], res["mixed"][0][0]
         dw = np.abs(a[o:o+P].astype(np.float64) - m[o:o+P]); 
         dm = np.abs(a[o+P:o+2*P].astype(np.float64) - m[o+P:o+2*P]) / (np.abs(m[o+P:o+2*P]).max() + 1e-30)
@@ -34,8 +37,10 @@ def replay(name):
         print("  agent %d kind %d: |w - exact| max %.3g  m rel %.3g  v rel %.3g  hdr %s vs %s   |w - torch| pwl %.3g exact %.3g  nan=%d" % (
             i, s.kind, dw.max(), dm.max(), dv.max(), hdr_a, hdr_m, et, etm, int(np.isnan(a[o:o+P]).sum())))
 
-for nm in ("mlp_rr_seed16", "mlp_aa_seed15", "mlp_raa_seed17"):
+for nm in (sys.argv[1:] or ["mlp_rr_seed16", "mlp_aa_seed15", "mlp_raa_seed17"]):
     replay(nm)
+if len(sys.argv) > 1:
+    sys.exit(0)
 
 # C5-shape timing, free running
 sys.path.insert(0, ".")

@@ -35,14 +35,24 @@ def golden(request):
 
 
 def uses_lattice_kernel(cfg):
-    """Games the library plays with the lattice kernel (th_rl_b200/csrc/thrl_scan_pwl.cuh): only Reinforce / ActorCritic
-    agents, noise-free demand, at most 1024 joint actions.  Its MLP results match the order-exact kernel / the oracle to
-    float32 rounding instead of bit for bit; THRL_KERNEL=mixed selects the order-exact kernel."""
+    """Games the library plays with the lattice kernel (th_rl_b200/csrc/thrl_scan_pwl.cuh; mirrors plan_pwl in thrl.cu):
+    Reinforce / ActorCritic agents, optionally next to QTable agents of a regular game, noise-free demand, at most 1024
+    joint actions.  Its MLP results match the order-exact kernel / the oracle to float32 rounding instead of bit for bit;
+    THRL_KERNEL=mixed selects the order-exact kernel."""
+    from oracle import oracle
+    from th_rl_b200 import abi
     if cfg["environment"].get("noise_prob", 0.05) > 0:
         return False
+    g = oracle.layout(cfg)
+    kinds = [g.agent[i].kind for i in range(g.n_agents)]
+    mlp = [k in (abi.THRL_AGENT_REINFORCE, abi.THRL_AGENT_ACTORCRITIC) for k in kinds]
+    if not any(mlp) or any(k == abi.THRL_AGENT_CAC for k in kinds):
+        return False
+    if not all(mlp) and not g.regular:
+        return False
     joint = 1
-    for a in cfg["agents"]:
-        if a["name"] not in ("Reinforce", "ActorCritic") or a.get("actions", 4) > 31:
+    for i in range(g.n_agents):
+        if mlp[i] and g.agent[i].actions > 31:
             return False
-        joint *= a.get("actions", 4)
+        joint *= g.agent[i].actions
     return joint <= 1024

@@ -38,17 +38,19 @@ def kernel_choice(request, monkeypatch):
 
 # Lattice kernel vs the order-exact computation (oracle): the same real-number gradient summed in another order (f64
 # prefix sums instead of sequential float32).  What is compared:
-#  * the gradient itself, through Adam's exp_avg / exp_avg_sq: within 2e-5 of the moment's max-norm.  Measured: <= 7e-7
-#    for Reinforce (the float32 summation noise of the ORDER-EXACT side over N = 100..1000 terms) and <= 3e-6 for
-#    ActorCritic, whose value head sits at 1000 (agents.py:244): one float32 ulp of v(s) is 6e-5, i.e. 3e-6 of the TD
-#    term gamma * v(s') - v(s) that every coefficient of the update contains;
+#  * the gradient itself, through Adam's exp_avg / exp_avg_sq, relative to the moment's max-norm: within 2e-5 for
+#    Reinforce (measured <= 9e-7: the float32 summation noise of the ORDER-EXACT side over N = 100..1000 terms) and within
+#    3e-4 for ActorCritic (measured <= 8e-5 over 24 runs x 6 updates).  ActorCritic's value head sits at 1000
+#    (agents.py:244): one float32 ulp of v(s) is 6e-5, the TD terms d_i = gamma * v(s') - v(s) ~ -20 carry that noise, and
+#    the actor weight (N r_j + D) / N^2 with D = sum d_i ~ -N * 20 nearly cancels for the high-reward samples -- the
+#    reference's own float32 evaluation has the same sensitivity (any other summation order of v moves it as much);
 #  * the weights: within 1e-6 absolute + 1e-6 relative (north_star's "1e-6") -- except that Adam moves a weight by
 #    lr * g / (|g| + 1e-8) per step, which turns that noise into a visible difference on the few entries whose gradient is
 #    itself of the size of the noise.  Those entries (at most 0.1 % of an agent's weights) may differ by up to a quarter
 #    of the distance Adam can have moved them, 0.25 * lr * steps; measured: 1 weight in 1.5e5 at 1e-5 (lr = 2e-4).
 PWL_ATOL = 1e-6
 PWL_RTOL = 1e-6
-PWL_MOMENT_TOL = 2e-5
+PWL_MOMENT_TOL = {1: 2e-5, 2: 3e-4}  # by agent kind: Reinforce, ActorCritic
 
 
 def _lattice(cfg, kernel_choice):
@@ -70,7 +72,7 @@ def _mlp_close(game, got, ref):
         for k in (1, 2):  # exp_avg, exp_avg_sq
             m, mr = got[:, o + k * P:o + (k + 1) * P].astype(np.float64), ref[:, o + k * P:o + (k + 1) * P].astype(np.float64)
             scale = np.abs(mr).max(axis=1, keepdims=True) + 1e-30
-            assert np.all(np.abs(m - mr) <= PWL_MOMENT_TOL * scale), (i, k, float((np.abs(m - mr) / scale).max()))
+            assert np.all(np.abs(m - mr) <= PWL_MOMENT_TOL[s.kind] * scale), (i, k, float((np.abs(m - mr) / scale).max()))
         w, wr = got[:, o:o + P].astype(np.float64), ref[:, o:o + P].astype(np.float64)
         err = np.abs(w - wr)
         loose = err > PWL_ATOL + PWL_RTOL * np.abs(wr)
@@ -81,6 +83,20 @@ def _mlp_close(game, got, ref):
 def torch_int32():
     import torch
     return torch.int32
+
+
+def _check_dispatch(cfg):
+    """The kernel that just ran is the one the game and THRL_KERNEL call for."""
+    import os
+    from conftest import uses_lattice_kernel
+    from th_rl_b200 import _lib
+    forced, got = os.environ.get("THRL_KERNEL"), _lib.last_kernel()
+    if any(a["name"] != "QTable" for a in cfg["agents"]):
+        assert got == ("pwl" if uses_lattice_kernel(cfg) and forced != "mixed" else "mixed"), got
+    elif forced == "generic":
+        assert got == "generic", got
+    else:
+        assert got in ("lut2", "lpc", "generic"), got
 
 
 def _mods():
@@ -103,6 +119,7 @@ def _cuda_replay(g, rng_mode, dtype, exact=True):
     out = b.scan(E, rng_mode=rng_mode, replay_u=u[None], replay_ra=ra[None],
                  replay_new_a=None if new_a is None else new_a[None], n_log_runs=1, stats=True, trace=True)
     torch.cuda.synchronize()
+    _check_dispatch(cfg)
     if mlp0 is not None:  # the oracle on the same inputs: the MLP slab (weights, Adam state, buffers) must agree bit for bit
         ref = oracle.scan(b.game, q0, [abi.eps0_from_config(cfg)], [g["p0"]], E, rng_mode=rng_mode, replay_u=u[None],
                           replay_ra=ra[None], replay_new_a=None if new_a is None else new_a[None], mlp=mlp0)
@@ -214,18 +231,22 @@ def _lattice_philox_case(cfg, R, E, seed, run_id0=0, chunks=None):
     for bit, the MLP state within the stated tolerance.  Splitting the call must not change a single bit."""
     torch, oracle, engine = _mods()
     game = oracle.layout(cfg)
-    q0, c0, eps0, p0, mlp0 = oracle.init(game, R, seed=seed, run_id0=run_id0, dtype=np.float32, eps0=abi.eps0_from_config(cfg))
-    ref = oracle.scan(game, q0, eps0, p0, E, seed=seed, run_id0=run_id0, stats=True, trace=True, n_threads=0, mlp=mlp0)
+    rng = np.random.default_rng(seed)
+    hpa = _sweep_hp(rng, R, game.n_agents) if game.run_stride else None
+    q0, c0, eps0, p0, mlp0 = oracle.init(game, R, seed=seed, run_id0=run_id0, dtype=np.float32, hp=hpa, eps0=abi.eps0_from_config(cfg))
+    ref = oracle.scan(game, q0, eps0, p0, E, hp=hpa, seed=seed, run_id0=run_id0, stats=True, trace=True, n_threads=0, mlp=mlp0)
 
     def run(chs):
-        b = engine.RunBatch(cfg, R, seed=seed, run_id0=run_id0)
+        b = engine.RunBatch(cfg, R, seed=seed, run_id0=run_id0, hp=hpa)
         b.load_state(q0, eps0, p0, mlp=mlp0)
         outs = [b.scan(e, n_log_runs=R, stats=True, trace=True) for e in chs]
         torch.cuda.synchronize()
+        _check_dispatch(cfg)
         cat = lambda f, ax: np.concatenate([getattr(o, f).cpu().numpy() for o in outs], axis=ax)
         res = {f: cat(f, 1) for f in ("trace_actions", "trace_prices", "trace_rewards", "rewards_log", "actions_log")}
         res["stats"] = cat("stats", 0)
         res["mlp"], res["price"] = b.mlp.cpu().numpy(), b.price.cpu().numpy()
+        res["q"], res["counter"], res["eps"] = b.q.cpu().numpy(), b.counter.cpu().numpy().view(np.uint32), b.eps.cpu().numpy()
         return res
 
     o = run([E])
@@ -234,6 +255,8 @@ def _lattice_philox_case(cfg, R, E, seed, run_id0=0, chunks=None):
     for f in ("trace_prices", "trace_rewards", "rewards_log", "actions_log"):
         assert np.array_equal(o[f][same], getattr(ref, f)[same]), f
     assert np.array_equal(o["price"][same], ref.price[same])
+    for f in ("q", "counter", "eps"):  # QTable agents of the same game: bit for bit
+        assert np.array_equal(o[f][same], getattr(ref, f)[same]), f
     _mlp_close(game, o["mlp"][same], ref.mlp[same])
     if same.all():
         assert np.array_equal(o["stats"], ref.stats)
@@ -275,10 +298,11 @@ def test_host_buffer_entry_point(golden, kernel_choice):
         b.load_state(q0, eps0, p0, mlp=mlp0)
         dev = b.scan(5, n_log_runs=33, stats=True)
         torch.cuda.synchronize()
-        eps, p, mlp = eps0.copy(), p0.copy(), mlp0.copy()
-        out = engine.scan_host(cfg, q0.copy(), eps, p, 5, counter=c0.copy(), seed=9, n_log_runs=33, stats=True, mlp=mlp)
+        q, cnt, eps, p, mlp = q0.copy(), c0.copy(), eps0.copy(), p0.copy(), mlp0.copy()
+        out = engine.scan_host(cfg, q, eps, p, 5, counter=cnt, seed=9, n_log_runs=33, stats=True, mlp=mlp)
         assert np.array_equal(mlp.view(np.uint32), b.mlp.cpu().numpy().view(np.uint32))
-        assert np.array_equal(p, b.price.cpu().numpy())
+        assert np.array_equal(q, b.q.cpu().numpy()) and np.array_equal(cnt, b.counter.cpu().numpy().view(np.uint32))
+        assert np.array_equal(eps, b.eps.cpu().numpy()) and np.array_equal(p, b.price.cpu().numpy())
         assert np.array_equal(out.rewards_log, dev.rewards_log.cpu().numpy()) and np.array_equal(out.stats, dev.stats.cpu().numpy())
         return
     ref = oracle.scan(game, q0, eps0, p0, 5, seed=9, stats=True, mlp=mlp0)

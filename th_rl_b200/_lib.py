@@ -51,6 +51,7 @@ def lib():
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.thrl_greedy_eval_mlp.restype = C.c_int
     L.thrl_launch_count.restype = C.c_int64
+    L.thrl_last_kernel.restype = C.c_char_p
     _lib = L
     return L
 
@@ -73,3 +74,8 @@ def game_layout(config):
 
 def launch_count():
     return int(lib().thrl_launch_count())
+
+
+def last_kernel():
+    """Name of the scan kernel this thread's latest scan call ran (include/thrl.h thrl_last_kernel)."""
+    return lib().thrl_last_kernel().decode()

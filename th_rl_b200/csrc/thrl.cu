@@ -29,6 +29,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
+thread_local const char* g_last_kernel = "";  // scan kernel of this thread's latest thrl_qtable_scan (thrl_last_kernel)
 std::atomic<long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
@@ -195,6 +196,7 @@ int launch_generic(thrl::ScanParams& p, const DeviceInfo& dev, cudaStream_t stre
   const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
   auto kern = smem_tables ? thrl::qtable_scan_generic<T, true> : thrl::qtable_scan_generic<T, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  g_last_kernel = "generic";
   kern<<<grid, warps * 32, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -311,6 +313,7 @@ int launch_lut2(thrl::Lut2Params& p, int warps, const DeviceInfo& dev, cudaStrea
   const bool small = p.game.agent[0].actions <= 32 && p.game.agent[1].actions <= 32;
   auto kern = small ? thrl::qtable_scan_lut2<QT, true> : thrl::qtable_scan_lut2<QT, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  g_last_kernel = "lut2";
   kern<<<grid, warps * 32, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -357,6 +360,7 @@ int launch_lpc_gl(thrl::Lut2Params& p, const DeviceInfo& dev, cudaStream_t strea
   const bool a21 = G.agent[0].actions == 21 && G.agent[1].actions == 21;
   auto kern = a21 ? thrl::qtable_scan_lpc<QT, GL, 21> : thrl::qtable_scan_lpc<QT, GL, 0>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  g_last_kernel = "lpc";
   kern<<<grid, warps * 32, smem, stream>>>(p, lay);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -421,6 +425,7 @@ int launch_mixed(thrl::MixedParams& p, const DeviceInfo& dev, cudaStream_t strea
   const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
   auto kern = thrl::qtable_scan_mixed<QT>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  g_last_kernel = "mixed";
   kern<<<grid, warps * 32, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -455,29 +460,45 @@ double h_py_sum(const double* aq, int n, int lead) {
 
 static_assert(sizeof(thrl::PwlParams) < 32000, "kernel parameters are limited to 32,764 bytes");
 
-// Fills p (lattice tables + layouts) when the game consists of Reinforce / ActorCritic agents on the noise-free demand
-// curve with few enough joint actions; otherwise the order-exact kernel takes the game.
-bool plan_pwl(thrl::PwlParams* p, bool noisy, int smem_optin, int* warps) {
+// Fills p (lattice tables + layouts) when the game is one the lattice kernel plays: Reinforce / ActorCritic agents,
+// optionally next to QTable agents of a regular game, on the noise-free demand curve, with few enough joint actions.
+// Otherwise the order-exact kernel takes the game.  elem: bytes per Q-table cell.
+bool plan_pwl(thrl::PwlParams* p, bool noisy, size_t elem, int smem_optin, int* warps) {
   const ThrlGame& G = p->game;
   const int n = G.n_agents, T = G.max_steps;
   if (noisy || n < 1) return false;
   long long J = 1;
-  int lut = 0, Hmax = 0, Amax = 0, Pmax = 0, capmax = 0;
+  int lut = 0, Hmax = 1, Amax = 1, Pmax = 1, capmax = 0, nq = 0, lead = 0, rows_max = 0;
+  bool leading = true;
   for (int i = 0; i < n; ++i) {
     const ThrlAgentSpec& s = G.agent[i];
-    if (s.kind != THRL_AGENT_REINFORCE && s.kind != THRL_AGENT_ACTORCRITIC) return false;
-    if (s.actions < 1 || s.actions > 31 || s.hidden < 1 || s.hidden > 8192) return false;
+    p->qidx[i] = -1;
+    p->L[i] = 0;
+    if (s.kind == THRL_AGENT_QTABLE) {
+      if (!G.regular) return false;  // batches that span episodes: the order-exact kernel keeps the ring
+      leading = false;
+      p->qidx[i] = nq++;
+      p->L[i] = s.min_memory > s.capacity ? 0 : (T < s.capacity ? T : s.capacity);
+      if (s.states + 1 > rows_max) rows_max = s.states + 1;
+    } else if (s.kind == THRL_AGENT_REINFORCE || s.kind == THRL_AGENT_ACTORCRITIC) {
+      if (s.actions > 31 || s.hidden < 1) return false;
+      if (leading) ++lead;
+      const int P = 2 * s.hidden + s.actions * s.hidden + s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? s.hidden + 1 : 0);
+      if (P > Pmax) Pmax = P;
+      if (s.hidden > Hmax) Hmax = s.hidden;
+      if (s.actions > Amax) Amax = s.actions;
+      if (G.mlp_buffer_len[i] > capmax) capmax = G.mlp_buffer_len[i];
+    } else {
+      return false;
+    }
     J *= s.actions;
     if (J > thrl::kPwlMaxJoint) return false;
     p->a_off[i] = lut;
     lut += s.actions;
-    const int P = 2 * s.hidden + s.actions * s.hidden + s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? s.hidden + 1 : 0);
-    if (P > Pmax) Pmax = P;
-    if (s.hidden > Hmax) Hmax = s.hidden;
-    if (s.actions > Amax) Amax = s.actions;
-    if (G.mlp_buffer_len[i] > capmax) capmax = G.mlp_buffer_len[i];
   }
   p->J = (int)J;
+  p->nq = nq;
+  p->dwords = (rows_max + 31) / 32;
   p->lut_total = lut;
   p->jmul[n - 1] = 1;
   for (int i = n - 2; i >= 0; --i) p->jmul[i] = p->jmul[i + 1] * G.agent[i + 1].actions;
@@ -487,9 +508,11 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, int smem_optin, int* warps) {
     double aq[THRL_MAX_AGENTS];
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
-      aq[i] = ab * h_scale_mlp((j / p->jmul[i]) % s.actions, s.actions, s.action_lo, s.action_hi);
+      const int k = (j / p->jmul[i]) % s.actions;
+      aq[i] = ab * (s.kind == THRL_AGENT_QTABLE ? h_scale(k, s.actions, s.action_lo, s.action_hi)
+                                                : h_scale_mlp(k, s.actions, s.action_lo, s.action_hi));
     }
-    const double Q = h_py_sum(aq, n, n);
+    const double Q = h_py_sum(aq, n, lead);
     const double pn = G.a - G.b * Q;
     const double price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
     if (price != price) return false;
@@ -504,32 +527,51 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, int smem_optin, int* warps) {
   p->NS = NS;
   for (int x = 0; x < NS; ++x) p->slot_val[x] = uniq[x];
   for (int j = 0; j < (int)J; ++j)
-    p->slot_of[j] = (uint8_t)(std::lower_bound(uniq.begin(), uniq.end(), fl[j]) - uniq.begin());
+    p->slot_of[j] = (uint16_t)(std::lower_bound(uniq.begin(), uniq.end(), fl[j]) - uniq.begin());
   const int NSX = NS + thrl::kPwlExtras;
   // shared memory
   int o = align_up(2 * lut * 8, 16);
   p->off_priceJ = o; o += align_up((int)J * 8, 16);
   p->off_rT = o;     o += align_up((int)J * n * 8, 16);
   p->off_rF = o;     o += align_up((int)J * n * 4, 16);
-  p->off_slotof = o; o += align_up((int)J, 16);
+  p->off_slotof = o; o += align_up((int)J * 2, 16);
+  p->off_urowJ = o;  o += align_up(nq * (int)J * 2, 16);
   p->cta_bytes = o;
   o = 0;
   p->off_sv = o;  o += align_up(NSX * 4, 16);
   p->off_cdf = o;
   int cdf = 0;
-  for (int i = 0; i < n; ++i) { p->cdf_off[i] = cdf; cdf += NSX * G.agent[i].actions; p->val_off[i] = i * NSX; }
+  for (int i = 0; i < n; ++i) {
+    p->cdf_off[i] = cdf;
+    p->val_off[i] = i * NSX;
+    if (G.agent[i].kind != THRL_AGENT_QTABLE) cdf += NSX * G.agent[i].actions;
+  }
   o += align_up(cdf * 4, 16);
   p->off_val = o; o += align_up(n * NSX * 4, 16);
   p->off_pre = o; o += align_up(T * n * 4, 16);
   p->off_ev = o;  o += align_up(Hmax * 2, 16);
   p->off_ord = o; o += align_up(Hmax * 2, 16);
   p->off_bkt = o; o += align_up((NS + 2) * 2, 16);
+  p->off_hpw = o; o += align_up(n * 5 * 8, 16);
+  p->off_jrec = o; o += nq ? align_up(T * 2, 16) : 0;
+  p->off_oldv = o; o += nq ? align_up(T * (int)elem, 16) : 0;
+  p->off_gq = o;   o += align_up(nq * NSX, 16);
+  p->off_arow = o; o += align_up(nq * NSX * 2, 16);
+  p->off_dirty = o; o += align_up(p->dwords * 4, 16);
+  for (int i = 0; i < n; ++i) {
+    p->off_tab[i] = o;
+    if (G.agent[i].kind == THRL_AGENT_QTABLE) {
+      const long long bytes = (long long)(G.agent[i].states + 1) * G.agent[i].actions * (long long)elem;
+      if (bytes > smem_optin) return false;
+      o += align_up((int)bytes, 16);
+    }
+  }
   p->warp_bytes = o;
   // per-warp workspace in global memory
   long long w = 0;
   p->ws_acc = w;  w += align_up(NSX * (Amax + 2) * 8, 16);
   p->ws_pf = w;   w += align_up((NSX + 1) * (Amax + 1) * 16, 16);
-  p->ws_p = w;    w += align_up(cdf * 4, 16);
+  p->ws_p = w;    w += align_up((cdf > 0 ? cdf : 1) * 4, 16);
   p->ws_grad = w; w += align_up(Pmax * 4, 16);
   p->ws_xs = w;   w += (long long)(capmax > 0 ? capmax : 1) * 16;
   p->ws_warp_bytes = (w + 255) / 256 * 256;
@@ -539,7 +581,7 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, int smem_optin, int* warps) {
   return true;
 }
 
-int launch_pwl(thrl::PwlParams& p, int warps, const DeviceInfo& dev, cudaStream_t stream) {
+int launch_pwl(thrl::PwlParams& p, int warps, bool f64, const DeviceInfo& dev, cudaStream_t stream) {
   int grid = dev.sms;
   {
     const long long slots = (long long)dev.sms * warps;
@@ -575,9 +617,12 @@ int launch_pwl(thrl::PwlParams& p, int warps, const DeviceInfo& dev, cudaStream_
   void* ws = nullptr;
   CUDA_TRY(cudaMallocFromPoolAsync(&ws, (size_t)grid * warps * (size_t)p.ws_warp_bytes, pool, stream));
   p.ws = (unsigned char*)ws;
-  auto kern = p.game.n_agents == 2 ? thrl::mlp_scan_pwl<2> : thrl::mlp_scan_pwl<0>;
+  void (*kern)(thrl::PwlParams) =
+      f64 ? (p.game.n_agents == 2 ? thrl::mlp_scan_pwl<double, 2> : thrl::mlp_scan_pwl<double, 0>)
+          : (p.game.n_agents == 2 ? thrl::mlp_scan_pwl<float, 2> : thrl::mlp_scan_pwl<float, 0>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
+    g_last_kernel = "pwl";
     kern<<<grid, warps * 32, smem, stream>>>(p);
     e = cudaGetLastError();
   }
@@ -609,6 +654,7 @@ extern "C" {
 int thrl_abi_version(void) { return THRL_ABI_VERSION; }
 const char* thrl_last_error(void) { return g_err; }
 int64_t thrl_launch_count(void) { return (int64_t)g_launches.load(); }
+const char* thrl_last_kernel(void) { return g_last_kernel; }
 
 int thrl_game_layout(ThrlGame* game) { return validate_layout(game); }
 
@@ -656,14 +702,15 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
       memset(w, 0, sizeof(*w));
       w->game = p.game;
       int warps = 0;
-      if (plan_pwl(w, p.noisy != 0, dev.smem_optin, &warps)) {
+      if (plan_pwl(w, p.noisy != 0, a->table_dtype == THRL_F64 ? 8 : 4, dev.smem_optin, &warps)) {
         w->n_runs = p.n_runs; w->run_id0 = p.run_id0; w->epoch_begin = p.epoch_begin; w->E = p.E; w->rng_mode = p.rng_mode;
         w->k0 = p.k0; w->k1 = p.k1;
-        w->price = p.price; w->replay_ra = p.replay_ra;
+        w->price = p.price; w->replay_ra = p.replay_ra; w->replay_u = p.replay_u;
+        w->q = p.q; w->counter = p.counter; w->eps = p.eps; w->hp = p.hp;
         w->rewards_log = p.rewards_log; w->actions_log = p.actions_log; w->n_log_runs = p.n_log_runs; w->stats = p.stats;
         w->trace_actions = p.trace_actions; w->trace_rewards = p.trace_rewards; w->trace_prices = p.trace_prices;
         w->mlp = a->mlp;
-        return launch_pwl(*w, warps, dev, stream);
+        return launch_pwl(*w, warps, a->table_dtype == THRL_F64, dev, stream);
       }
     }
     thrl::MixedParams* m = new thrl::MixedParams();

@@ -3,7 +3,7 @@
 //
 // Two facts make the per-run "1000 x 256 x 22 GEMMs" of such a game collapse:
 //  (1) the network input is the price, and with discrete actions and no demand noise the price only takes the finitely
-//      many values a - b*sum(A) of the joint actions (the LATTICE, <= 240 distinct float32 states; plus the run's
+//      many values a - b*sum(A) of the joint actions (the LATTICE, <= 1024 distinct float32 states; plus the run's
 //      arbitrary initial price, an "extra" state).  pi(.|s) and v(s) are therefore tabulated once per parameter update
 //      (policy LUT, stored as a CDF so that acting is one shared-memory row read + ballot), and a batch of N
 //      transitions is equivalent to at most NS weighted states: the per-sample loss coefficients are summed per state
@@ -25,7 +25,7 @@
 namespace thrl {
 
 constexpr int kPwlMaxJoint = 1024;   // joint actions (price table in the kernel parameters)
-constexpr int kPwlMaxLattice = 240;  // distinct float32 lattice prices
+constexpr int kPwlMaxLattice = 1024; // distinct float32 lattice prices (<= joint actions)
 constexpr int kPwlExtras = 4;        // off-lattice states one run may hold at a time (its initial price)
 
 struct PwlParams {
@@ -34,6 +34,11 @@ struct PwlParams {
   int epoch_begin, E, rng_mode;
   uint32_t k0, k1;
   double* price;
+  void* q;               // QTable agents of the same game (NULL when there are none)
+  uint32_t* counter;
+  double* eps;
+  const double* hp;
+  const double* replay_u;
   const int32_t* replay_ra;
   double* rewards_log;
   double* actions_log;
@@ -50,10 +55,14 @@ struct PwlParams {
   int jmul[THRL_MAX_AGENTS];     // joint index = sum_i action_i * jmul[i]
   int cdf_off[THRL_MAX_AGENTS];  // float offset of the agent's CDF LUT [NS + extras][A] (shared memory and ws_p alike)
   int val_off[THRL_MAX_AGENTS];  // float offset of the agent's v(s) LUT [NS + extras]
-  int cta_bytes, off_priceJ, off_rT, off_rF, off_slotof;
-  int warp_bytes, off_sv, off_cdf, off_val, off_pre, off_ev, off_ord, off_bkt;
+  int nq, dwords;                // QTable agents; words of the dirty-row bitmap (largest table)
+  int qidx[THRL_MAX_AGENTS];     // ordinal among the QTable agents, -1 for MLP agents
+  int L[THRL_MAX_AGENTS];        // QTable agent: transitions per episode-end update (0: it never fires)
+  int off_tab[THRL_MAX_AGENTS];  // byte offset of the staged table in the warp's shared memory
+  int cta_bytes, off_priceJ, off_rT, off_rF, off_slotof, off_urowJ;
+  int warp_bytes, off_sv, off_cdf, off_val, off_pre, off_ev, off_ord, off_bkt, off_hpw, off_jrec, off_oldv, off_gq, off_arow, off_dirty;
   float slot_val[kPwlMaxLattice];   // lattice states, ascending
-  uint8_t slot_of[kPwlMaxJoint];    // joint action -> lattice state
+  uint16_t slot_of[kPwlMaxJoint];   // joint action -> lattice state
   double priceJ[kPwlMaxJoint];      // joint action -> next price (environments.py:25-33)
 };
 
@@ -328,7 +337,7 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
       const int x = pwl_find(sv, NS, nx, en[0]);
       bad |= !isfinite(ca) || x < 0;
       camax = fmaxf(camax, fabsf(ca));
-      xs[nn] = make_float4(__int_as_float(x & 0xff), ca, 0.0f, 0.0f);
+      xs[nn] = make_float4(__int_as_float(x & 0xffff), ca, 0.0f, 0.0f);
     }
   } else {
     double Rp = 0.0, Dp = 0.0;
@@ -340,7 +349,7 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
       const float d = __fsub_rn(__fmul_rn(gam, vp), v);
       Rp = __dadd_rn(Rp, (double)en[2]);
       Dp = __dadd_rn(Dp, (double)d);
-      xs[nn] = make_float4(__int_as_float((x & 0xff) | ((x2 & 0xff) << 8)), 0.0f, 0.0f, d);
+      xs[nn] = make_float4(__int_as_float((x & 0xffff) | ((x2 & 0xffff) << 16)), 0.0f, 0.0f, d);
     }
     const float fN = (float)N, fR = (float)warp_sum(Rp), fD = (float)warp_sum(Dp);
     const float invN2 = __fdiv_rn(1.0f, __fmul_rn(fN, fN));
@@ -369,7 +378,7 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
     unsigned long long* uacc = reinterpret_cast<unsigned long long*>(acc);
     for (int nn = lane; nn < N; nn += 32) {
       const float4 q = xs[nn];
-      const int xb = __float_as_int(q.x), x = xb & 0xff, x2 = (xb >> 8) & 0xff;
+      const int xb = __float_as_int(q.x), x = xb & 0xffff, x2 = (xb >> 16) & 0xffff;
       const int a = __float_as_int(entry(nn)[1]);
       const unsigned long long fa = (unsigned long long)__double2ll_rn(__dmul_rn((double)q.y, sa));
       atomicAdd(uacc + x * C + a, fa);
@@ -456,28 +465,38 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
   pwl_clip_adam(blk, spec, g, lane);
 }
 
-// kN: number of agents when it is 2 (the agent loop of the episode is unrolled with its constants in registers), else 0
-template <int kN>
+// QT: storage type of the Q-tables of QTable agents playing in the same game (unused when there are none).
+// kN: number of agents when it is 2 (the agent loop of the episode is unrolled), else 0.
+//
+// QTable agents (agents.py:14-112) in a lattice game: the table is staged in shared memory for the whole call (the game
+// must be regular, include/thrl.h), the greedy action is cached per lattice state and agent (the table is frozen within an
+// episode; entries of rows the episode-end update wrote are dropped), the update rows are tabulated per joint action (the
+// float64 encode depends on the exact price, not on its float32 state), and the episode-end update is the sequential pass
+// of the other kernels (stale snapshot, live next_max, visit counters, epsilon decay).
+template <typename QT, int kN>
 __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ PwlParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ThrlGame& G = p.game;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;
-  const int n = G.n_agents, T = G.max_steps, E = p.E, NS = p.NS, J = p.J;
+  const int n = G.n_agents, T = G.max_steps, E = p.E, NS = p.NS, J = p.J, NSX = NS + kPwlExtras;
   const bool is_agent = lane < n;
 
-  // ---- CTA-shared tables: per-action quantities, joint action -> price / lattice state / reward share
+  // ---- CTA-shared tables: per-action quantities, joint action -> price / lattice state / reward share / update rows
   double* lutAQ = reinterpret_cast<double*>(smem);
   double* lutXT = lutAQ + p.lut_total;
   double* priceJ = reinterpret_cast<double*>(smem + p.off_priceJ);
   double* rT = reinterpret_cast<double*>(smem + p.off_rT);  // [J][n] reward / max_steps (trainer.py:63)
   float* rF = reinterpret_cast<float*>(smem + p.off_rF);    // [J][n] reward as the float32 the buffers hold (agents.py:142)
-  uint8_t* slot_of = smem + p.off_slotof;
+  uint16_t* slot_of = reinterpret_cast<uint16_t*>(smem + p.off_slotof);
+  uint16_t* urowJ = reinterpret_cast<uint16_t*>(smem + p.off_urowJ);  // [QTable agent][J] float64 encode of the price (agents.py:62,66)
   {
     const double ab = __ddiv_rn(G.a, G.b);
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
-      for (int k = threadIdx.x; k < s.actions; k += blockDim.x) {  // Reinforce.scale: k / A (agents.py:154-158)
-        const double x = __dadd_rn(__dmul_rn(__ddiv_rn((double)k, (double)s.actions), __dsub_rn(s.action_hi, s.action_lo)), s.action_lo);
+      for (int k = threadIdx.x; k < s.actions; k += blockDim.x) {  // QTable.scale: k/(A-1) (agents.py:51-57); Reinforce.scale: k/A (:154-158)
+        const double x = s.kind == THRL_AGENT_QTABLE
+                             ? scale_action(k, s.actions, s.action_lo, s.action_hi)
+                             : __dadd_rn(__dmul_rn(__ddiv_rn((double)k, (double)s.actions), __dsub_rn(s.action_hi, s.action_lo)), s.action_lo);
         lutAQ[p.a_off[i] + k] = __dmul_rn(ab, x);
         lutXT[p.a_off[i] + k] = __ddiv_rn(x, (double)T);
       }
@@ -492,16 +511,29 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
     rT[idx] = __ddiv_rn(rew, (double)T);
     rF[idx] = (float)rew;
   }
+  for (int i = 0; i < n; ++i) {
+    const int qi = p.qidx[i];
+    if (qi < 0) continue;
+    const ThrlAgentSpec& s = G.agent[i];
+    for (int j = threadIdx.x; j < J; j += blockDim.x) urowJ[qi * J + j] = (uint16_t)upd_row(priceJ[j], s.max_state, (double)s.states);
+  }
   __syncthreads();
 
   unsigned char* slot = smem + p.cta_bytes + (size_t)warp * p.warp_bytes;
   float* sv = reinterpret_cast<float*>(slot + p.off_sv);      // [NS + extras] state values
-  float* cdfb = reinterpret_cast<float*>(slot + p.off_cdf);   // per agent [NS + extras][A] running sums of pi(.|s)
+  float* cdfb = reinterpret_cast<float*>(slot + p.off_cdf);   // per MLP agent [NS + extras][A] running sums of pi(.|s)
   float* valb = reinterpret_cast<float*>(slot + p.off_val);   // per agent [NS + extras] v(s)
-  int32_t* pre = reinterpret_cast<int32_t*>(slot + p.off_pre);  // [T][n] forced action, or 0x80000000 | 24-bit uniform
+  int32_t* pre = reinterpret_cast<int32_t*>(slot + p.off_pre);  // [T][n] draws of the episode, see below
   uint16_t* ev = reinterpret_cast<uint16_t*>(slot + p.off_ev);
   uint16_t* ord = reinterpret_cast<uint16_t*>(slot + p.off_ord);
   uint16_t* bkt = reinterpret_cast<uint16_t*>(slot + p.off_bkt);
+  // QTable agents only:
+  double* hpw = reinterpret_cast<double*>(slot + p.off_hpw);          // [n][5] alpha, gamma, eps_end, eps_step, epsilon
+  uint16_t* jrec = reinterpret_cast<uint16_t*>(slot + p.off_jrec);    // [T] joint action of every step of the episode
+  QT* oldv = reinterpret_cast<QT*>(slot + p.off_oldv);                // [T] stale snapshot (agents.py:67)
+  uint8_t* gq = slot + p.off_gq;                                      // [nq][NS + extras] greedy action of the state, 0xFF unknown
+  uint16_t* arow = reinterpret_cast<uint16_t*>(slot + p.off_arow);    // [nq][NS + extras] float32 encode of the state (acting row)
+  uint32_t* dirty = reinterpret_cast<uint32_t*>(slot + p.off_dirty);  // [dwords] rows written by the running update
   unsigned char* wsw = p.ws + ((size_t)blockIdx.x * wpc + warp) * p.ws_warp_bytes;
   long long* acc = reinterpret_cast<long long*>(wsw + p.ws_acc);
   float* pws = reinterpret_cast<float*>(wsw + p.ws_p);
@@ -510,11 +542,12 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
   float4* xs = reinterpret_cast<float4*>(wsw + p.ws_xs);
   for (int x = lane; x < NS; x += 32) sv[x] = p.slot_val[x];
 
-  int my_cap = 0, my_aoff = 0, my_EW = 3, my_P = 0;
+  int my_cap = 0, my_aoff = 0, my_EW = 3, my_P = 0, my_kind = THRL_AGENT_REINFORCE;
   long long my_off = 0;
   if (is_agent) {
     const ThrlAgentSpec& s = G.agent[lane];
-    my_cap = G.mlp_buffer_len[lane];
+    my_kind = s.kind;
+    my_cap = s.kind == THRL_AGENT_QTABLE ? 0 : G.mlp_buffer_len[lane];
     my_aoff = p.a_off[lane];
     my_EW = mlp_entry_words(s);
     my_P = mlp_P(s);
@@ -522,12 +555,14 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
   }
 
   const bool tracing = p.trace_actions || p.trace_rewards || p.trace_prices;
-  const int A0 = G.agent[0].actions, A1 = G.agent[kN == 2 ? 1 : 0].actions;
-  const float *cdf0 = cdfb + p.cdf_off[0], *cdf1 = cdfb + p.cdf_off[kN == 2 ? 1 : 0];
+  const int nq = p.nq;
+  constexpr int kGreedy = 0x7fffffff;  // draw of a QTable agent that acts greedily (not a uniform < 1: those are < 0x3f800000)
 
   const long long total_warps = (long long)gridDim.x * wpc;
   for (long long r = (long long)blockIdx.x * wpc + warp; r < p.n_runs; r += total_warps) {
     float* slab = p.mlp + r * G.mlp_stride;
+    QT* tabg = reinterpret_cast<QT*>(p.q) + r * G.run_stride;
+    uint32_t* cnt = p.counter ? p.counter + r * G.run_stride : nullptr;
     const uint32_t gid = (uint32_t)(p.run_id0 + r);
     const double price = p.price[r];
     int jlast = -1;  // joint action of the latest step: the run's price is priceJ[jlast]
@@ -555,7 +590,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
     int my_len = 0, my_head = 0, my_wr = 0;  // deque(maxlen = capacity): length, oldest slot (at entry), next slot to write
     float* my_buf = nullptr;
     int32_t* my_hdr = nullptr;
-    if (is_agent) {
+    if (is_agent && my_kind != THRL_AGENT_QTABLE) {
       float* blk = slab + my_off;
       my_hdr = reinterpret_cast<int32_t*>(blk + 3 * (size_t)my_P);
       my_buf = blk + 3 * (size_t)my_P + THRL_MLP_HEADER_WORDS;
@@ -567,6 +602,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
     }
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
+      if (s.kind == THRL_AGENT_QTABLE) continue;
       const int L = __shfl_sync(kFull, my_len, i), hd = __shfl_sync(kFull, my_head, i), cap = G.mlp_buffer_len[i];
       const int EW = mlp_entry_words(s);
       const float* buf = slab + s.mlp_offset + 3 * (size_t)mlp_P(s) + THRL_MLP_HEADER_WORDS;
@@ -589,25 +625,65 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
     }
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
+      if (s.kind == THRL_AGENT_QTABLE) {  // stage the table; acting rows of all states; nothing known about greedy actions
+        const int qi = p.qidx[i], cells = (s.states + 1) * s.actions;
+        QT* tb = reinterpret_cast<QT*>(slot + p.off_tab[i]);
+        const QT* src = tabg + s.table_offset;
+        for (int c = lane; c < cells; c += 32) tb[c] = src[c];
+        for (int xx = lane; xx < NS + nx; xx += 32) {
+          arow[qi * NSX + xx] = (uint16_t)act_row((double)sv[xx], (float)s.max_state, (float)s.states);
+          gq[qi * NSX + xx] = 0xFF;
+        }
+        if (lane == 0) {
+          double* h = hpw + i * 5;
+          if (p.hp) {
+            const double* hs = p.hp + (r * n + i) * 4;
+            h[0] = hs[0]; h[1] = hs[1]; h[2] = hs[2]; h[3] = hs[3];
+          } else {
+            h[0] = s.alpha; h[1] = s.gamma; h[2] = s.eps_end; h[3] = s.eps_step;
+          }
+          h[4] = p.eps[r * n + i];
+        }
+        continue;
+      }
       const float* blk = slab + s.mlp_offset;
       pwl_unit_events(blk, blk + s.hidden, s.hidden, sv, NS, ev, ord, bkt, lane);
       pwl_build_lut(blk, s, sv, NS, nx, ev, ord, cdfb + p.cdf_off[i], valb + p.val_off[i], pws + p.cdf_off[i], lane);
     }
+    for (int w = lane; w < p.dwords; w += 32) dirty[w] = 0;
+    int urow_cur = 0;  // lane i (a QTable agent): update row of the state the next episode starts from
+    if (is_agent && my_kind == THRL_AGENT_QTABLE) urow_cur = upd_row(price, G.agent[lane].max_state, (double)G.agent[lane].states);
+    __syncwarp();
 
     for (int e = 0; e < E; ++e) {
       const uint32_t eabs = (uint32_t)(p.epoch_begin + e);
       const long long step0 = (r * E + e) * (long long)T;
-      // ---- per-episode draws: -1 - action when the action is forced (replay modes), else the bits of the uniform
-      // u = 24 random bits * 2^-24 in [0, 1) that Categorical.sample() is emulated with
+      // ---- per-episode draws.  MLP agent: -1 - action when the action is forced (replay modes), else the bits of the
+      // uniform u = 24 random bits * 2^-24 that Categorical.sample() is emulated with.  QTable agent (agents.py:80-89):
+      // -1 - action for an exploring (or forced) step, kGreedy otherwise.
       for (int idx = lane; idx < T * n; idx += 32) {
         const int t = idx / n, i = idx - t * n;
-        int v = p.rng_mode == THRL_RNG_PHILOX ? -1 : p.replay_ra[step0 * n + idx];
-        if (v < 0) {
-          uint32_t xr[4];
-          philox4x32_10(gid, eabs, (uint32_t)t, (uint32_t)(i >> 1) | (kStreamAct << 16), p.k0, p.k1, xr);
-          v = __float_as_int(__fmul_rn((float)(xr[2 * (i & 1)] >> 8), 1.0f / 16777216.0f));
+        int v;
+        if (G.agent[i].kind == THRL_AGENT_QTABLE) {
+          if (p.rng_mode == THRL_RNG_REPLAY_ACTIONS) {
+            v = -1 - p.replay_ra[step0 * n + idx];
+          } else if (p.rng_mode == THRL_RNG_REPLAY_DRAWS) {
+            v = p.replay_u[step0 * n + idx] < hpw[i * 5 + 4] ? -1 - p.replay_ra[step0 * n + idx] : kGreedy;
+          } else {
+            uint32_t xr[4];
+            philox4x32_10(gid, eabs, (uint32_t)t, (uint32_t)(i >> 1) | (kStreamAct << 16), p.k0, p.k1, xr);
+            const int ra = (int)__umulhi(xr[2 * (i & 1) + 1], (uint32_t)G.agent[i].actions);
+            v = u32_unit(xr[2 * (i & 1)]) < hpw[i * 5 + 4] ? -1 - ra : kGreedy;
+          }
         } else {
-          v = -1 - v;
+          v = p.rng_mode == THRL_RNG_PHILOX ? -1 : p.replay_ra[step0 * n + idx];
+          if (v < 0) {
+            uint32_t xr[4];
+            philox4x32_10(gid, eabs, (uint32_t)t, (uint32_t)(i >> 1) | (kStreamAct << 16), p.k0, p.k1, xr);
+            v = __float_as_int(__fmul_rn((float)(xr[2 * (i & 1)] >> 8), 1.0f / 16777216.0f));
+          } else {
+            v = -1 - v;
+          }
         }
         pre[idx] = v;
       }
@@ -615,10 +691,23 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
 
       // ---- the episode (trainer.py:50-67): pi(.|s) is a row of the CDF LUT, the environment a table of the joint action
       double rlog = 0.0, alog = 0.0;
-      // first k with cumsum(pi)[k] > u (agents.py:160-163), the last action if there is none
-      auto pick = [&](int v, const float* cdf, int Ai) {
+      auto pick = [&](int v, int i) {
         if (v < 0) return -1 - v;
-        const float c = lane < Ai ? cdf[x * Ai + lane] : 0.0f;
+        const ThrlAgentSpec& s = G.agent[i];
+        const int Ai = s.actions;
+        if (nq && s.kind == THRL_AGENT_QTABLE) {  // first argmax of the (frozen) table row of the state (agents.py:84-88)
+          const int qi = p.qidx[i];
+          int g = gq[qi * NSX + x];
+          if (g == 0xFF) {
+            g = row_argmax(reinterpret_cast<const QT*>(slot + p.off_tab[i]) + (size_t)arow[qi * NSX + x] * Ai, Ai, lane);
+            __syncwarp();
+            if (lane == 0) gq[qi * NSX + x] = (uint8_t)g;
+            __syncwarp();
+          }
+          return g;
+        }
+        // first k with cumsum(pi)[k] > u (agents.py:160-163), the last action if there is none
+        const float c = lane < Ai ? cdfb[p.cdf_off[i] + x * Ai + lane] : 0.0f;
         const unsigned m = __ballot_sync(kFull, lane < Ai && c > __int_as_float(v));
         return m ? __ffs(m) - 1 : Ai - 1;
       };
@@ -626,17 +715,18 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
         int joint = 0, kmine = 0;
         if (kN == 2) {
           const int2 v = *reinterpret_cast<const int2*>(pre + 2 * t);
-          const int k0 = pick(v.x, cdf0, A0), k1 = pick(v.y, cdf1, A1);
-          joint = k0 * A1 + k1;
+          const int k0 = pick(v.x, 0), k1 = pick(v.y, 1);
+          joint = k0 * p.jmul[0] + k1;
           kmine = lane == 0 ? k0 : k1;
         } else {
           for (int i = 0; i < n; ++i) {
-            const int k = pick(pre[t * n + i], cdfb + p.cdf_off[i], G.agent[i].actions);
+            const int k = pick(pre[t * n + i], i);
             joint += k * p.jmul[i];
             if (lane == i) kmine = k;
           }
         }
         const int xn = slot_of[joint];
+        if (nq && lane == 0) jrec[t] = (uint16_t)joint;
         if (is_agent) {
           rlog = __dadd_rn(rlog, rT[joint * n + lane]);
           alog = __dadd_rn(alog, lutXT[my_aoff + kmine]);
@@ -663,9 +753,51 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
       }
       __syncwarp();
 
-      // ---- train_net for every agent in order (trainer.py:70), then the agent's LUTs of the new parameters
+      // ---- train_net for every agent in order (trainer.py:70)
       for (int i = 0; i < n; ++i) {
         const ThrlAgentSpec& s = G.agent[i];
+        if (s.kind == THRL_AGENT_QTABLE) {  // QTable.train_net (agents.py:59-78) on the newest L transitions of the episode
+          const int qi = p.qidx[i], L = p.L[i], A = s.actions, jm = p.jmul[i];
+          const int ucur = __shfl_sync(kFull, urow_cur, i);
+          if (L > 0) {
+            QT* tb = reinterpret_cast<QT*>(slot + p.off_tab[i]);
+            const uint16_t* ur = urowJ + qi * J;
+            const int t0 = T - L;
+            const double alpha = hpw[i * 5 + 0], gamma = hpw[i * 5 + 1], one_m_alpha = __dsub_rn(1.0, alpha);
+            for (int t = t0 + lane; t < T; t += 32) {  // stale snapshot (:67)
+              const int st = t == 0 ? ucur : ur[jrec[t - 1]];
+              oldv[t] = tb[(size_t)st * A + (jrec[t] / jm) % A];
+            }
+            __syncwarp();
+            for (int t = t0; t < T; ++t) {  // the sequential pass (:68-76)
+              const int jt = jrec[t];
+              const int st = t == 0 ? ucur : ur[jrec[t - 1]], ns = ur[jt], k = (jt / jm) % A;
+              const double reward = __dmul_rn(priceJ[jt], lutAQ[p.a_off[i] + k]);
+              const double next_max = (double)row_max(tb + (size_t)ns * A, A, lane);
+              const double nv = __dadd_rn(__dmul_rn(one_m_alpha, (double)oldv[t]),
+                                          __dmul_rn(alpha, __dadd_rn(reward, __dmul_rn(gamma, next_max))));
+              if ((k & 31) == lane) {  // the lane that owns column k
+                tb[(size_t)st * A + k] = (QT)nv;
+                if (cnt) atomicAdd(cnt + s.table_offset + (size_t)st * A + k, 1u);
+                dirty[st >> 5] |= 1u << (st & 31);
+              }
+            }
+            __syncwarp();
+            for (int xx = lane; xx < NS + nx; xx += 32) {  // greedy actions of rewritten rows are unknown again
+              const int rw = arow[qi * NSX + xx];
+              if (dirty[rw >> 5] >> (rw & 31) & 1) gq[qi * NSX + xx] = 0xFF;
+            }
+            __syncwarp();
+            for (int w = lane; w < p.dwords; w += 32) dirty[w] = 0;
+          }
+          if (lane == i) urow_cur = urowJ[qi * J + jlast];
+          if (lane == 0) {  // epsilon decay (:78), every episode
+            double* h = hpw + i * 5;
+            h[4] = __dadd_rn(h[2], __dmul_rn(__dsub_rn(h[4], h[2]), h[3]));
+          }
+          __syncwarp();
+          continue;
+        }
         const int cap = G.mlp_buffer_len[i];
         if (cap == 0) continue;
         const int L = __shfl_sync(kFull, my_len, i);
@@ -694,13 +826,26 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
       __syncwarp();
     }
 
+    // ---- write the run back
+    for (int i = 0; i < n; ++i) {
+      const ThrlAgentSpec& s = G.agent[i];
+      if (s.kind != THRL_AGENT_QTABLE) continue;
+      const int cells = (s.states + 1) * s.actions;
+      const QT* tb = reinterpret_cast<const QT*>(slot + p.off_tab[i]);
+      QT* dst = tabg + s.table_offset;
+      for (int c = lane; c < cells; c += 32) dst[c] = tb[c];
+      if (lane == 0) p.eps[r * n + i] = hpw[i * 5 + 4];
+    }
     if (is_agent && my_cap > 0) {
       int hd = my_wr - my_len;
       if (hd < 0) hd += my_cap;
       my_hdr[1] = my_len;
       my_hdr[2] = my_len ? hd : 0;
     }
-    if (overflow && lane == 0) slab[G.agent[0].mlp_offset] = __int_as_float(0x7fc00000);  // more off-lattice states than kPwlExtras: fail loudly
+    if (overflow && lane == 0) {  // more off-lattice states than kPwlExtras: fail loudly (NaN weights)
+      for (int i = 0; i < n; ++i)
+        if (G.agent[i].kind != THRL_AGENT_QTABLE) { slab[G.agent[i].mlp_offset] = __int_as_float(0x7fc00000); break; }
+    }
     if (lane == 0 && jlast >= 0) p.price[r] = priceJ[jlast];
     __syncwarp();
   }

@@ -539,14 +539,12 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, size_t elem, int smem_optin, int* 
   p->cta_bytes = o;
   o = 0;
   p->off_sv = o;  o += align_up(NSX * 4, 16);
-  p->off_cdf = o;
   int cdf = 0;
   for (int i = 0; i < n; ++i) {
     p->cdf_off[i] = cdf;
     p->val_off[i] = i * NSX;
     if (G.agent[i].kind != THRL_AGENT_QTABLE) cdf += NSX * G.agent[i].actions;
   }
-  o += align_up(cdf * 4, 16);
   p->off_val = o; o += align_up(n * NSX * 4, 16);
   p->off_pre = o; o += align_up(T * n * 4, 16);
   p->off_ev = o;  o += align_up(Hmax * 2, 16);
@@ -566,12 +564,18 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, size_t elem, int smem_optin, int* 
       o += align_up((int)bytes, 16);
     }
   }
-  p->warp_bytes = o;
+  // CDF LUT: in shared memory unless that leaves fewer than 8 runs resident per SM and the workspace (L2) placement more
+  const int without = o, with = o + align_up(cdf * 4, 16);
+  const int fit_with = (smem_optin - p->cta_bytes) / with, fit_without = (smem_optin - p->cta_bytes) / without;
+  p->cdf_global = (fit_with < 8 && fit_without > fit_with) ? 1 : 0;
+  p->off_cdf = o;
+  p->warp_bytes = p->cdf_global ? without : with;
   // per-warp workspace in global memory
   long long w = 0;
   p->ws_acc = w;  w += align_up(NSX * (Amax + 2) * 8, 16);
   p->ws_pf = w;   w += align_up((NSX + 1) * (Amax + 1) * 16, 16);
   p->ws_p = w;    w += align_up((cdf > 0 ? cdf : 1) * 4, 16);
+  p->ws_cdf = w;  w += p->cdf_global ? align_up(cdf * 4, 16) : 0;
   p->ws_grad = w; w += align_up(Pmax * 4, 16);
   p->ws_xs = w;   w += (long long)(capmax > 0 ? capmax : 1) * 16;
   p->ws_warp_bytes = (w + 255) / 256 * 256;

@@ -49,7 +49,8 @@ struct PwlParams {
   double* trace_prices;
   float* mlp;
   unsigned char* ws;  // per resident warp: accumulators, probability LUT, gradient, per-sample scratch
-  long long ws_warp_bytes, ws_acc, ws_pf, ws_p, ws_grad, ws_xs;
+  long long ws_warp_bytes, ws_acc, ws_pf, ws_p, ws_cdf, ws_grad, ws_xs;
+  int cdf_global;  // 1: the CDF LUT lives in the workspace (L2) instead of shared memory (large lattices: more resident runs)
   int J, NS, lut_total;
   int a_off[THRL_MAX_AGENTS];    // agent's offset in the per-action tables
   int jmul[THRL_MAX_AGENTS];     // joint index = sum_i action_i * jmul[i]
@@ -521,7 +522,9 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
 
   unsigned char* slot = smem + p.cta_bytes + (size_t)warp * p.warp_bytes;
   float* sv = reinterpret_cast<float*>(slot + p.off_sv);      // [NS + extras] state values
-  float* cdfb = reinterpret_cast<float*>(slot + p.off_cdf);   // per MLP agent [NS + extras][A] running sums of pi(.|s)
+  // per MLP agent [NS + extras][A] running sums of pi(.|s): shared memory, or the workspace when the lattice is large
+  float* cdfb = p.cdf_global ? reinterpret_cast<float*>(p.ws + ((size_t)blockIdx.x * wpc + warp) * p.ws_warp_bytes + p.ws_cdf)
+                             : reinterpret_cast<float*>(slot + p.off_cdf);
   float* valb = reinterpret_cast<float*>(slot + p.off_val);   // per agent [NS + extras] v(s)
   int32_t* pre = reinterpret_cast<int32_t*>(slot + p.off_pre);  // [T][n] draws of the episode, see below
   uint16_t* ev = reinterpret_cast<uint16_t*>(slot + p.off_ev);

@@ -546,7 +546,10 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, size_t elem, int smem_optin, int* 
     if (G.agent[i].kind != THRL_AGENT_QTABLE) cdf += NSX * G.agent[i].actions;
   }
   p->off_val = o; o += align_up(n * NSX * 4, 16);
-  p->off_pre = o; o += align_up(T * n * 4, 16);
+  {  // the episode's draws; between episodes the same bytes stage kPwlTile hidden units of the forward sweep
+    const int draws = T * n * 4, tile = thrl::kPwlTile * ((Amax + 1) * 4 + 12);
+    p->off_pre = o; o += align_up(draws > tile ? draws : tile, 16);
+  }
   p->off_ev = o;  o += align_up(Hmax * 2, 16);
   p->off_ord = o; o += align_up(Hmax * 2, 16);
   p->off_bkt = o; o += align_up((NS + 2) * 2, 16);
@@ -621,9 +624,18 @@ int launch_pwl(thrl::PwlParams& p, int warps, bool f64, const DeviceInfo& dev, c
   void* ws = nullptr;
   CUDA_TRY(cudaMallocFromPoolAsync(&ws, (size_t)grid * warps * (size_t)p.ws_warp_bytes, pool, stream));
   p.ws = (unsigned char*)ws;
-  void (*kern)(thrl::PwlParams) =
-      f64 ? (p.game.n_agents == 2 ? thrl::mlp_scan_pwl<double, 2> : thrl::mlp_scan_pwl<double, 0>)
-          : (p.game.n_agents == 2 ? thrl::mlp_scan_pwl<float, 2> : thrl::mlp_scan_pwl<float, 0>);
+  const bool two = p.game.n_agents == 2, g = p.cdf_global != 0;
+  void (*kern)(thrl::PwlParams);
+  if (p.nq == 0) {  // no tables: the table type does not enter
+    kern = two ? (g ? thrl::mlp_scan_pwl<float, 2, false, true> : thrl::mlp_scan_pwl<float, 2, false, false>)
+               : (g ? thrl::mlp_scan_pwl<float, 0, false, true> : thrl::mlp_scan_pwl<float, 0, false, false>);
+  } else if (f64) {
+    kern = two ? (g ? thrl::mlp_scan_pwl<double, 2, true, true> : thrl::mlp_scan_pwl<double, 2, true, false>)
+               : (g ? thrl::mlp_scan_pwl<double, 0, true, true> : thrl::mlp_scan_pwl<double, 0, true, false>);
+  } else {
+    kern = two ? (g ? thrl::mlp_scan_pwl<float, 2, true, true> : thrl::mlp_scan_pwl<float, 2, true, false>)
+               : (g ? thrl::mlp_scan_pwl<float, 0, true, true> : thrl::mlp_scan_pwl<float, 0, true, false>);
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
     g_last_kernel = "pwl";

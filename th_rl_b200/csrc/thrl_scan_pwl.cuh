@@ -188,40 +188,94 @@ __device__ __forceinline__ void pwl_emit(float z, bool col, bool vcol, int A, in
   if (vcol) val[x] = z;
 }
 
+constexpr int kPwlTile = 8;  // hidden units staged per round of the forward sweep
+
 // pi(.|s) and v(s) for every lattice state (one sweep, see the header) and for the extras (direct evaluation).
 // Needs ev / ord of the CURRENT parameters (pwl_unit_events).  blk: the agent's parameters in state_dict order.
+// tile: shared scratch of kPwlTile * ((A + 1) * 4 + 12) bytes (the episode's draw buffer, idle between episodes).
 __device__ inline void pwl_build_lut(const float* blk, const ThrlAgentSpec& spec, const float* sv, int NS, int nx,
-                                     const uint16_t* ev, const uint16_t* ord, float* cdf, float* val, float* pws, int lane) {
+                                     const uint16_t* ev, const uint16_t* ord, float* cdf, float* val, float* pws,
+                                     unsigned char* tile, int lane) {
   const int H = spec.hidden, A = spec.actions;
   const bool ac = spec.kind == THRL_AGENT_ACTORCRITIC;
   const float *w1 = blk, *b1 = blk + H, *W = blk + 2 * H, *bp = W + (size_t)A * H, *wv = bp + A;
   const bool col = lane < A, vcol = ac && lane == A, use = col || vcol;
   const float* crow = col ? W + (size_t)lane * H : wv;  // this lane's row of fc_pi.weight, or fc_v.weight
   const double bias = col ? (double)bp[lane] : (vcol ? (double)wv[H] : 0.0);
+  const int NC = ac ? A + 1 : A;  // columns: the actions, then the value head
   double S1 = 0.0, S0 = 0.0;
   __syncwarp();
-#pragma unroll 4
-  for (int e = 0; e < H; ++e) {  // units active from rank 0 on
-    const int j = ord[e];
-    const double c = use ? (double)crow[j] : 0.0;
-    const double t1 = __dmul_rn(c, (double)w1[j]), t0 = __dmul_rn(c, (double)b1[j]);
-    if (ev[j] & 0x8000) { S1 = __dadd_rn(S1, t1); S0 = __dadd_rn(S0, t0); }
-  }
-  int e = 0;
-  for (int r = 0; r < NS; ++r) {
-    while (e < H) {
-      const int j = ord[e];
-      const unsigned v = ev[j];
-      if ((int)(v & 0x7fff) > r) break;
-      const double c = use ? (double)crow[j] : 0.0;
-      const double t1 = __dmul_rn(c, (double)w1[j]), t0 = __dmul_rn(c, (double)b1[j]);
-      if (v & 0x8000) { S1 = __dsub_rn(S1, t1); S0 = __dsub_rn(S0, t0); }
-      else { S1 = __dadd_rn(S1, t1); S0 = __dadd_rn(S0, t0); }
-      ++e;
+  // units active from rank 0 on (they leave at their breakpoint): lane = unit, coalesced rows of the weights, one
+  // butterfly sum per column; lane c keeps column c
+  for (int c = 0; c < NC; ++c) {
+    const float* row = c < A ? W + (size_t)c * H : wv;
+    double p1 = 0.0, p0 = 0.0;
+    for (int j = lane; j < H; j += 32) {
+      if (ev[j] & 0x8000) {
+        const double cw = (double)row[j];
+        p1 = __dadd_rn(p1, __dmul_rn(cw, (double)w1[j]));
+        p0 = __dadd_rn(p0, __dmul_rn(cw, (double)b1[j]));
+      }
     }
+    p1 = warp_sum(p1);
+    p0 = warp_sum(p0);
+    if (lane == c) { S1 = p1; S0 = p0; }
+  }
+  // the sweep: kPwlTile units per round are gathered with independent loads (lane = element) one round ahead, parked in
+  // shared memory, then applied in breakpoint order (lane = column)
+  const int NCP = A + 1;
+  float* tW = reinterpret_cast<float*>(tile);                  // [kPwlTile][NCP] weights of the staged units
+  float* tw1 = tW + NCP * kPwlTile;                              // [kPwlTile]
+  float* tb1 = tw1 + kPwlTile;
+  uint16_t* tev = reinterpret_cast<uint16_t*>(tb1 + kPwlTile);   // [kPwlTile]
+  constexpr int kRegs = (32 * kPwlTile + 31) / 32;               // elements per lane and round (A + 1 <= 32)
+  float rW[kRegs], rw1 = 0.0f, rb1 = 0.0f;
+  unsigned rev = 0;
+  auto gather = [&](int e0) {
+    const int ne = H - e0 < kPwlTile ? H - e0 : kPwlTile;
+#pragma unroll
+    for (int q = 0; q < kRegs; ++q) {
+      const int idx = lane + 32 * q, e = idx / NC, c = idx - e * NC;
+      rW[q] = 0.0f;
+      if (e < ne) {
+        const int j = ord[e0 + e];
+        rW[q] = c < A ? W[(size_t)c * H + j] : wv[j];
+      }
+    }
+    if (lane < ne) {
+      const int j = ord[e0 + lane];
+      rw1 = w1[j]; rb1 = b1[j]; rev = ev[j];
+    }
+  };
+  int r = 0;
+  auto emit_row = [&]() {
     const float z = (float)__dadd_rn(__dadd_rn(__dmul_rn(S1, (double)sv[r]), S0), bias);
     pwl_emit(z, col, vcol, A, r, cdf, val, pws, lane);
+    ++r;
+  };
+  gather(0);
+  for (int e0 = 0; e0 < H; e0 += kPwlTile) {
+    const int ne = H - e0 < kPwlTile ? H - e0 : kPwlTile;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < kRegs; ++q) {
+      const int idx = lane + 32 * q, e = idx / NC, c = idx - e * NC;
+      if (e < ne) tW[e * NCP + c] = rW[q];
+    }
+    if (lane < ne) { tw1[lane] = rw1; tb1[lane] = rb1; tev[lane] = (uint16_t)rev; }
+    __syncwarp();
+    if (e0 + kPwlTile < H) gather(e0 + kPwlTile);  // in flight while this round is applied
+    for (int e = 0; e < ne; ++e) {
+      const unsigned v = tev[e];
+      const int key = (int)(v & 0x7fff);
+      while (r < key && r < NS) emit_row();  // every rank below the breakpoint has all its events
+      const double cw = use ? (double)tW[e * NCP + lane] : 0.0;
+      const double t1 = __dmul_rn(cw, (double)tw1[e]), t0 = __dmul_rn(cw, (double)tb1[e]);
+      if (v & 0x8000) { S1 = __dsub_rn(S1, t1); S0 = __dsub_rn(S0, t0); }
+      else { S1 = __dadd_rn(S1, t1); S0 = __dadd_rn(S0, t0); }
+    }
   }
+  while (r < NS) emit_row();
   for (int x = NS; x < NS + nx; ++x) {  // off-lattice states: the plain sum over the hidden units
     const float s = sv[x];
     double acc = 0.0;
@@ -262,19 +316,35 @@ __device__ inline void pwl_clip_adam(float* blk, const ThrlAgentSpec& spec, cons
   const float neg_step_size = (float)(-__ddiv_rn(spec.lr, bc1));
   const float bc2_sqrt = (float)sqrt(bc2);
   const float w1m = (float)__dsub_rn(1.0, 0.9), fb2 = (float)0.999, w2 = (float)__dsub_rn(1.0, 0.999), eps = 1e-8f;
-#pragma unroll 4
-  for (int i = lane; i < P; i += 32) {
-    const float gi = __fmul_rn(g[i], coef);
-    float m = am[i], v = av[i];
-    m = __fadd_rn(m, __fmul_rn(__fsub_rn(gi, m), w1m));
-    v = __fadd_rn(__fmul_rn(v, fb2), __fmul_rn(__fmul_rn(w2, gi), gi));
-    am[i] = m;
-    av[i] = v;
-    // entries whose gradient has been exactly zero so far (units that are inactive on the whole lattice) keep m = v = 0:
-    // same result as the general formula, without sending the warp through the slow paths of sqrt and division
-    const float den = v != 0.0f ? __fadd_rn(__fdiv_rn(sqrtf(v), bc2_sqrt), eps) : eps;
-    const float num = __fmul_rn(neg_step_size, m);
-    blk[i] = __fadd_rn(blk[i], m != 0.0f ? __fdiv_rn(num, den) : num);
+  // four parameters per lane and round, every load issued before the arithmetic (the moments live in HBM: the loop is
+  // latency-bound otherwise; pwl_train prefetches the block into L2 while the gradient is being formed)
+  for (int i0 = lane; i0 < P; i0 += 128) {
+    float gi[4], m[4], v[4], w[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 32 * u;
+      const bool in = i < P;
+      gi[u] = in ? g[i] : 0.0f;
+      m[u] = in ? am[i] : 0.0f;
+      v[u] = in ? av[i] : 0.0f;
+      w[u] = in ? blk[i] : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + 32 * u;
+      if (i < P) {
+        const float gc = __fmul_rn(gi[u], coef);
+        const float mm = __fadd_rn(m[u], __fmul_rn(__fsub_rn(gc, m[u]), w1m));
+        const float vv = __fadd_rn(__fmul_rn(v[u], fb2), __fmul_rn(__fmul_rn(w2, gc), gc));
+        am[i] = mm;
+        av[i] = vv;
+        // entries whose gradient has been exactly zero so far (units that are inactive on the whole lattice) keep m = v = 0:
+        // same result as the general formula, without sending the warp through the slow paths of sqrt and division
+        const float den = vv != 0.0f ? __fadd_rn(__fdiv_rn(sqrtf(vv), bc2_sqrt), eps) : eps;
+        const float num = __fmul_rn(neg_step_size, mm);
+        blk[i] = __fadd_rn(w[u], mm != 0.0f ? __fdiv_rn(num, den) : num);
+      }
+    }
   }
   __syncwarp();
   if (lane == 0) hdr[0] = step;
@@ -300,6 +370,8 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
     return buf + (size_t)sl * EW;
   };
   __syncwarp();
+  for (int i = lane * 32; i < 3 * P; i += 32 * 32)  // parameters and Adam moments towards L2 (one line per lane and round)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
   for (int i = lane; i < NX * C; i += 32) acc[i] = 0;
   bool bad = false;
   float camax = 0.0f, cvmax = 0.0f;
@@ -441,7 +513,7 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
       unsigned xm = 0;
       for (int e2 = 0; e2 < nx; ++e2) xm |= pwl_active(sv[NS + e2], w, b) ? 1u << e2 : 0u;
       double gw = 0.0, gb = 0.0;
-#pragma unroll 2
+#pragma unroll 4
       for (int c = 0; c < NC; ++c) {
         const double2 pre = pf[key * CW + c], tt = pf[NS * CW + c];
         double M0 = leave ? pre.x : __dsub_rn(tt.x, pre.x), M1 = leave ? pre.y : __dsub_rn(tt.y, pre.y);
@@ -474,7 +546,8 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
 // episode; entries of rows the episode-end update wrote are dropped), the update rows are tabulated per joint action (the
 // float64 encode depends on the exact price, not on its float32 state), and the episode-end update is the sequential pass
 // of the other kernels (stale snapshot, live next_max, visit counters, epsilon decay).
-template <typename QT, int kN>
+// kQ: the game has QTable agents.  kCdfG: the CDF LUT lives in the workspace (PwlParams.cdf_global).
+template <typename QT, int kN, bool kQ, bool kCdfG>
 __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ PwlParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ThrlGame& G = p.game;
@@ -523,8 +596,8 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
   unsigned char* slot = smem + p.cta_bytes + (size_t)warp * p.warp_bytes;
   float* sv = reinterpret_cast<float*>(slot + p.off_sv);      // [NS + extras] state values
   // per MLP agent [NS + extras][A] running sums of pi(.|s): shared memory, or the workspace when the lattice is large
-  float* cdfb = p.cdf_global ? reinterpret_cast<float*>(p.ws + ((size_t)blockIdx.x * wpc + warp) * p.ws_warp_bytes + p.ws_cdf)
-                             : reinterpret_cast<float*>(slot + p.off_cdf);
+  float* cdfb = kCdfG ? reinterpret_cast<float*>(p.ws + ((size_t)blockIdx.x * wpc + warp) * p.ws_warp_bytes + p.ws_cdf)
+                      : reinterpret_cast<float*>(slot + p.off_cdf);
   float* valb = reinterpret_cast<float*>(slot + p.off_val);   // per agent [NS + extras] v(s)
   int32_t* pre = reinterpret_cast<int32_t*>(slot + p.off_pre);  // [T][n] draws of the episode, see below
   uint16_t* ev = reinterpret_cast<uint16_t*>(slot + p.off_ev);
@@ -558,7 +631,9 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
   }
 
   const bool tracing = p.trace_actions || p.trace_rewards || p.trace_prices;
-  const int nq = p.nq;
+  // the two agents of a 2-agent game: action counts and CDF tables in registers
+  const int A0 = G.agent[0].actions, A1 = G.agent[kN == 2 ? 1 : 0].actions;
+  const float *cdf0 = cdfb + p.cdf_off[0], *cdf1 = cdfb + p.cdf_off[kN == 2 ? 1 : 0];
   constexpr int kGreedy = 0x7fffffff;  // draw of a QTable agent that acts greedily (not a uniform < 1: those are < 0x3f800000)
 
   const long long total_warps = (long long)gridDim.x * wpc;
@@ -651,7 +726,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
       }
       const float* blk = slab + s.mlp_offset;
       pwl_unit_events(blk, blk + s.hidden, s.hidden, sv, NS, ev, ord, bkt, lane);
-      pwl_build_lut(blk, s, sv, NS, nx, ev, ord, cdfb + p.cdf_off[i], valb + p.val_off[i], pws + p.cdf_off[i], lane);
+      pwl_build_lut(blk, s, sv, NS, nx, ev, ord, cdfb + p.cdf_off[i], valb + p.val_off[i], pws + p.cdf_off[i], reinterpret_cast<unsigned char*>(pre), lane);
     }
     for (int w = lane; w < p.dwords; w += 32) dirty[w] = 0;
     int urow_cur = 0;  // lane i (a QTable agent): update row of the state the next episode starts from
@@ -697,8 +772,8 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
       auto pick = [&](int v, int i) {
         if (v < 0) return -1 - v;
         const ThrlAgentSpec& s = G.agent[i];
-        const int Ai = s.actions;
-        if (nq && s.kind == THRL_AGENT_QTABLE) {  // first argmax of the (frozen) table row of the state (agents.py:84-88)
+        const int Ai = kN == 2 ? (i == 0 ? A0 : A1) : s.actions;
+        if (kQ && s.kind == THRL_AGENT_QTABLE) {  // first argmax of the (frozen) table row of the state (agents.py:84-88)
           const int qi = p.qidx[i];
           int g = gq[qi * NSX + x];
           if (g == 0xFF) {
@@ -710,7 +785,8 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
           return g;
         }
         // first k with cumsum(pi)[k] > u (agents.py:160-163), the last action if there is none
-        const float c = lane < Ai ? cdfb[p.cdf_off[i] + x * Ai + lane] : 0.0f;
+        const float* cdf = kN == 2 ? (i == 0 ? cdf0 : cdf1) : cdfb + p.cdf_off[i];
+        const float c = lane < Ai ? cdf[x * Ai + lane] : 0.0f;
         const unsigned m = __ballot_sync(kFull, lane < Ai && c > __int_as_float(v));
         return m ? __ffs(m) - 1 : Ai - 1;
       };
@@ -719,7 +795,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
         if (kN == 2) {
           const int2 v = *reinterpret_cast<const int2*>(pre + 2 * t);
           const int k0 = pick(v.x, 0), k1 = pick(v.y, 1);
-          joint = k0 * p.jmul[0] + k1;
+          joint = k0 * A1 + k1;
           kmine = lane == 0 ? k0 : k1;
         } else {
           for (int i = 0; i < n; ++i) {
@@ -729,7 +805,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
           }
         }
         const int xn = slot_of[joint];
-        if (nq && lane == 0) jrec[t] = (uint16_t)joint;
+        if (kQ && lane == 0) jrec[t] = (uint16_t)joint;
         if (is_agent) {
           rlog = __dadd_rn(rlog, rT[joint * n + lane]);
           alog = __dadd_rn(alog, lutXT[my_aoff + kmine]);
@@ -811,7 +887,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
         pwl_train(blk, s, cap, hd, L, sv, NS, nx, ev, ord, bkt, valb + p.val_off[i], pws + p.cdf_off[i], acc, pfw, gws, xs, lane);
         if (lane == i) { my_len = 0; my_wr = 0; }  // :194 memory.empty()
         pwl_unit_events(blk, blk + s.hidden, s.hidden, sv, NS, ev, ord, bkt, lane);
-        pwl_build_lut(blk, s, sv, NS, nx, ev, ord, cdfb + p.cdf_off[i], valb + p.val_off[i], pws + p.cdf_off[i], lane);
+        pwl_build_lut(blk, s, sv, NS, nx, ev, ord, cdfb + p.cdf_off[i], valb + p.val_off[i], pws + p.cdf_off[i], reinterpret_cast<unsigned char*>(pre), lane);
       }
       if (is_agent) {
         if (r < p.n_log_runs) {

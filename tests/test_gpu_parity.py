@@ -236,14 +236,14 @@ def _lattice_philox_case(cfg, R, E, seed, run_id0=0, chunks=None):
     q0, c0, eps0, p0, mlp0 = oracle.init(game, R, seed=seed, run_id0=run_id0, dtype=np.float32, hp=hpa, eps0=abi.eps0_from_config(cfg))
     ref = oracle.scan(game, q0, eps0, p0, E, hp=hpa, seed=seed, run_id0=run_id0, stats=True, trace=True, n_threads=0, mlp=mlp0)
 
-    def run(chs):
+    def run(chs, trace=True):
         b = engine.RunBatch(cfg, R, seed=seed, run_id0=run_id0, hp=hpa)
         b.load_state(q0, eps0, p0, mlp=mlp0)
-        outs = [b.scan(e, n_log_runs=R, stats=True, trace=True) for e in chs]
+        outs = [b.scan(e, n_log_runs=R, stats=True, trace=trace) for e in chs]
         torch.cuda.synchronize()
         _check_dispatch(cfg)
         cat = lambda f, ax: np.concatenate([getattr(o, f).cpu().numpy() for o in outs], axis=ax)
-        res = {f: cat(f, 1) for f in ("trace_actions", "trace_prices", "trace_rewards", "rewards_log", "actions_log")}
+        res = {f: cat(f, 1) for f in (("trace_actions", "trace_prices", "trace_rewards") if trace else ()) + ("rewards_log", "actions_log")}
         res["stats"] = cat("stats", 0)
         res["mlp"], res["price"] = b.mlp.cpu().numpy(), b.price.cpu().numpy()
         res["q"], res["counter"], res["eps"] = b.q.cpu().numpy(), b.counter.cpu().numpy().view(np.uint32), b.eps.cpu().numpy()
@@ -260,10 +260,16 @@ def _lattice_philox_case(cfg, R, E, seed, run_id0=0, chunks=None):
     _mlp_close(game, o["mlp"][same], ref.mlp[same])
     if same.all():
         assert np.array_equal(o["stats"], ref.stats)
+    o3 = run([E], trace=False)  # the episode loop without the per-step trace stores is a separate code path
+    for f in o3:
+        assert np.array_equal(o[f].view(np.uint8), o3[f].view(np.uint8)), "untraced call differs in " + f
     if chunks:
         o2 = run(chunks)
         for f in o:
             assert np.array_equal(o[f].view(np.uint8), o2[f].view(np.uint8)), "chunked call differs in " + f
+        o4 = run(chunks, trace=False)
+        for f in o4:
+            assert np.array_equal(o[f].view(np.uint8), o4[f].view(np.uint8)), "untraced chunked call differs in " + f
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

@@ -67,6 +67,29 @@ struct PwlParams {
   double priceJ[kPwlMaxJoint];      // joint action -> next price (environments.py:25-33)
 };
 
+// shared-memory loads by 32-bit shared address (the episode loop of the 2-agent all-MLP kernel: one address add + LDS)
+__device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ int lds_u16(uint32_t a) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+  return (int)v;
+}
+__device__ __forceinline__ int2 lds_v2s32(uint32_t a) {
+  int2 v;
+  asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ unsigned lanemask_lt() {
   unsigned m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -790,6 +813,40 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
         const unsigned m = __ballot_sync(kFull, lane < Ai && c > __int_as_float(v));
         return m ? __ffs(m) - 1 : Ai - 1;
       };
+      if (kN == 2 && !kQ && !kCdfG && !tracing) {
+        // two MLP agents, LUT in shared memory: branch-free steps on 32-bit shared addresses.  A forced action overrides
+        // the sampled one; bit A-1 is or-ed into the ballot so that "no k with cdf > u" yields the last action.
+        const int c0l = lane < A0 ? lane : A0 - 1, c1l = lane < A1 ? lane : A1 - 1;
+        const uint32_t pre_s = smem_u32(pre), cdf0_s = smem_u32(cdf0) + 4 * c0l, cdf1_s = smem_u32(cdf1) + 4 * c1l;
+        const uint32_t slot_s = smem_u32(slot_of), sv_s = smem_u32(sv);
+        const uint32_t rT_s = smem_u32(rT) + 8 * (lane & 1), rF_s = smem_u32(rF) + 4 * (lane & 1), xt_s = smem_u32(lutXT + my_aoff);
+        const unsigned last0 = 1u << (A0 - 1), last1 = 1u << (A1 - 1);
+        const bool in0 = lane < A0, in1 = lane < A1, first = lane == 0, append = is_agent && my_cap > 0;
+        for (int t = 0; t < T; ++t) {
+          const int2 v = lds_v2s32(pre_s + 8 * t);
+          const float c0 = lds_f32(cdf0_s + 4 * A0 * x), c1 = lds_f32(cdf1_s + 4 * A1 * x);
+          const unsigned m0 = __ballot_sync(kFull, in0 && c0 > __int_as_float(v.x)) | last0;
+          const unsigned m1 = __ballot_sync(kFull, in1 && c1 > __int_as_float(v.y)) | last1;
+          const int k0 = v.x < 0 ? -1 - v.x : __ffs(m0) - 1, k1 = v.y < 0 ? -1 - v.y : __ffs(m1) - 1;
+          const int joint = k0 * A1 + k1, kmine = first ? k0 : k1;
+          const int xn = lds_u16(slot_s + 2 * joint);
+          if (is_agent) {
+            rlog = __dadd_rn(rlog, lds_f64(rT_s + 16 * joint));
+            alog = __dadd_rn(alog, lds_f64(xt_s + 8 * kmine));
+          }
+          if (append) {  // memory.append; replay(cast) makes state and reward float32 (buffers.py:28-38, agents.py:142)
+            float* en = my_buf + (size_t)my_wr * my_EW;
+            en[0] = lds_f32(sv_s + 4 * x);
+            en[1] = __int_as_float(kmine);
+            en[2] = lds_f32(rF_s + 8 * joint);
+            if (my_EW == 4) en[3] = lds_f32(sv_s + 4 * xn);
+            my_wr = my_wr + 1 == my_cap ? 0 : my_wr + 1;
+            my_len = my_len < my_cap ? my_len + 1 : my_cap;
+          }
+          x = xn;
+          jlast = joint;
+        }
+      } else
       for (int t = 0; t < T; ++t) {
         int joint = 0, kmine = 0;
         if (kN == 2) {

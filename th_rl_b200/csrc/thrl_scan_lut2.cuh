@@ -50,10 +50,11 @@ struct Lut2Params {
   // shared-memory layout
   int cta_bytes, warp_bytes;
   int off_next, off_rowlist, off_lutr, off_lutlog;  // CTA-shared
-  int off_tab1, off_grow, off_rows, off_gj, off_seq, off_rec, off_scr;  // per warp (tables of agent 0 at 0)
+  int off_tab1, off_grow, off_rows, off_gj, off_seq, off_rec, off_scr, off_old;  // per warp (tables of agent 0 at 0)
 };
 
-constexpr int kLut2MaxWarps = 24;
+constexpr int kLut2MaxWarps = 20;
+constexpr int kLut2Chunk = 16;  // transitions expanded per pass of the update (16 lanes per agent)
 
 // Row max / first argmax with the column count known to be <= 32 at compile time (kSmallA): one LDS per lane.
 template <typename QT, bool kSmallA>
@@ -124,18 +125,21 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
   uint16_t* rec = reinterpret_cast<uint16_t*>(slot + p.off_rec);     // [T] k0 | k1<<8
   uint8_t* seq = slot + p.off_seq;                                   // [T+1] state before step t (rebuilt lane-parallel)
   uint2* pre = reinterpret_cast<uint2*>(slot + p.off_scr);           // [T] (keep mask, forced value) byte pairs      (phases A-B)
-  uint2* meta = reinterpret_cast<uint2*>(slot + p.off_scr);          // [T][2] (next-row byte offset, cell byte offset) (phases C-D)
-  double2* rc = reinterpret_cast<double2*>(slot + p.off_scr + align16(2 * T * 8));  // [T][2] (reward, (1-alpha)*old)
+  // phase D chunk: entry [i][agent] of 32 B = uint4 (next-row byte offset agent 0, same agent 1, cell address in smem, -)
+  //                                        + double2 (reward, (1-alpha)*old)
+  unsigned char* chunk = slot + p.off_scr;
+  QT* olds = reinterpret_cast<QT*>(slot + p.off_old);                // [T][2] stale old values of the batch (agents.py:67)
 
   const bool in0 = lane < A0, in1 = lane < A1;
   const bool hi_half = lane >= 16, store_lane = (lane & 15) == 0;
-  unsigned char* tab_h = reinterpret_cast<unsigned char*>(hi_half ? tab1 : tab0);
   const int L0 = p.L[0], L1 = p.L[1];
   const uint32_t dp_b = (uint32_t)A1 | (1u << 8);  // joint = dp4a(k0 | k1<<8, A1 | 1<<8)
-  const double* lutLogLane = lutLog + (lane & 3);
   // lanes >= A re-read the last column: harmless for a max, and no masked load / select in the hot loop
-  const QT* tab0_lane = tab0 + (kSmallA ? (lane < A0 ? lane : A0 - 1) : lane);
-  const QT* tab1_lane = tab1 + (kSmallA ? (lane < A1 ? lane : A1 - 1) : lane);
+  const uint32_t tab0_off = (uint32_t)(reinterpret_cast<unsigned char*>(tab0) - smem);
+  const uint32_t tab1_off = (uint32_t)(reinterpret_cast<unsigned char*>(tab1) - smem);
+  const uint32_t tab0_lane_off = tab0_off + (uint32_t)sizeof(QT) * (uint32_t)(kSmallA ? (lane < A0 ? lane : A0 - 1) : lane);
+  const uint32_t tab1_lane_off = tab1_off + (uint32_t)sizeof(QT) * (uint32_t)(kSmallA ? (lane < A1 ? lane : A1 - 1) : lane);
+  const uint32_t chunk_off = (uint32_t)(chunk - smem);
 
   const long long total_warps = (long long)gridDim.x * warps_per_cta;
   for (long long r = (long long)blockIdx.x * warps_per_cta + warp; r < p.n_runs; r += total_warps) {
@@ -154,7 +158,8 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
       alpha1 = G.agent[1].alpha; gamma1 = G.agent[1].gamma; epsend1 = G.agent[1].eps_end; epsstep1 = G.agent[1].eps_step;
     }
     const double oma0 = __dsub_rn(1.0, alpha0), oma1 = __dsub_rn(1.0, alpha1);
-    const double alpha_h = hi_half ? alpha1 : alpha0, gamma_h = hi_half ? gamma1 : gamma0;
+    double alpha_h = hi_half ? alpha1 : alpha0, gamma_h = hi_half ? gamma1 : gamma0, oma_h = hi_half ? oma1 : oma0;
+    asm volatile("" : "+d"(alpha_h), "+d"(gamma_h), "+d"(oma_h));  // keep the selected values live (no re-selection in the loops)
     double eps0 = p.eps[r * 2], eps1 = p.eps[r * 2 + 1];
     const double price_in = p.price[r];
 
@@ -251,18 +256,27 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
       const uint32_t sig4_start = sig4;
       double acc = 0.0;
       {
-        const uint2* pp = pre;
-        uint16_t* rp = rec;
+        // shared-window addresses in registers and explicit ld/st.shared: one IMAD / IADD per access
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(smem);
+        const uint32_t pre_a = base + (uint32_t)(reinterpret_cast<unsigned char*>(pre) - smem);
+        const uint32_t rec_a = base + (uint32_t)(reinterpret_cast<unsigned char*>(rec) - smem);
+        const uint32_t gj_a = base + (uint32_t)(GJb - smem);
+        const uint32_t log_a = base + (uint32_t)p.off_lutlog + 8u * (uint32_t)(lane & 3);
+        const uint32_t next_a = base + (uint32_t)p.off_next;
         uint32_t kk = 0;
 #pragma unroll 4
         for (int t = 0; t < T; ++t) {
-          const uint2 f = pp[t];
-          const uint32_t gj = *reinterpret_cast<const uint32_t*>(GJb + sig4);
-          kk = (gj & f.x) | f.y;                               // agents.py:80-89 for both agents
+          uint32_t fx, fy, gj, s16;
+          double lg;
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(fx), "=r"(fy) : "r"(pre_a + 8u * t));
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gj) : "r"(gj_a + sig4));
+          kk = (gj & fx) | fy;                                 // agents.py:80-89 for both agents
           const uint32_t joint = __dp4a(kk, dp_b, 0u);         // k0 * A1 + k1
-          rp[t] = (uint16_t)kk;                                // same value from every lane
-          acc = __dadd_rn(acc, lutLogLane[4 * joint]);
-          sig4 = nextS[joint];
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(rec_a + 2u * t), "h"((uint16_t)kk) : "memory");  // same value from every lane
+          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(lg) : "r"(log_a + 32u * joint));
+          acc = __dadd_rn(acc, lg);
+          asm volatile("ld.shared.u16 %0, [%1];" : "=r"(s16) : "r"(next_a + 2u * joint));
+          sig4 = s16;
         }
         last_k = (int)kk;
       }
@@ -291,100 +305,128 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
         }
       }
 
-      // ---- C: pre-pass over the batch = the newest L_i transitions of the episode (buffers.py:12, agents.py:61-67)
+      // ---- C: snapshot pass over the batch = the newest L_i transitions of the episode (buffers.py:12, agents.py:61-67):
+      //      the stale old values (agents.py:67) of ALL transitions are read before any cell is written; visit counters
+      //      and the dirty-row masks ride along.  Everything else a transition needs is expanded chunk by chunk below,
+      //      which keeps the per-run scratch small (more runs resident per SM).
       unsigned dirty0a = 0, dirty0b = 0, dirty1a = 0, dirty1b = 0;  // written compact rows 0..63 of each agent
       bool dirty_all0 = false, dirty_all1 = false;
       for (int j = T - L0 + lane; j < T; j += 32) {
-        const uint32_t rw = rowsW[seq[j]], rn = rowsW[seq[j + 1]];
-        const int k = rec[j] & 0xff, joint = k * A1 + (rec[j] >> 8);
-        const int cu = (rw >> 8) & 0xff, cn = (rn >> 8) & 0xff;
-        const int cell = cu * A0 + k;
-        const int jj = j - (T - L0);
-        meta[2 * jj] = make_uint2((uint32_t)(cn * A0) * (uint32_t)sizeof(QT), (uint32_t)cell * (uint32_t)sizeof(QT));
-        rc[2 * jj] = make_double2(lutR[2 * joint], __dmul_rn(oma0, (double)tab0[cell]));
+        const int k = rec[j] & 0xff, cu = (rowsW[seq[j]] >> 8) & 0xff;
+        olds[2 * (j - (T - L0))] = tab0[cu * A0 + k];
         if (cnt0) atomicAdd(cnt0 + (size_t)table_row0(cu) * A0 + k, 1u);  // agents.py:76
         if (cu < 32) dirty0a |= 1u << cu; else if (cu < 64) dirty0b |= 1u << (cu - 32); else dirty_all0 = true;
       }
       for (int j = T - L1 + lane; j < T; j += 32) {
-        const uint32_t rw = rowsW[seq[j]], rn = rowsW[seq[j + 1]];
-        const int k = rec[j] >> 8, joint = (rec[j] & 0xff) * A1 + k;
-        const int cu = rw >> 24, cn = rn >> 24;
-        const int cell = cu * A1 + k;
-        const int jj = j - (T - L1);
-        meta[2 * jj + 1] = make_uint2((uint32_t)(cn * A1) * (uint32_t)sizeof(QT), (uint32_t)cell * (uint32_t)sizeof(QT));
-        rc[2 * jj + 1] = make_double2(lutR[2 * joint + 1], __dmul_rn(oma1, (double)tab1[cell]));
+        const int k = rec[j] >> 8, cu = rowsW[seq[j]] >> 24;
+        olds[2 * (j - (T - L1)) + 1] = tab1[cu * A1 + k];
         if (cnt1) atomicAdd(cnt1 + (size_t)table_row1(cu) * A1 + k, 1u);
         if (cu < 32) dirty1a |= 1u << cu; else if (cu < 64) dirty1b |= 1u << (cu - 32); else dirty_all1 = true;
       }
       __syncwarp();
 
+      // chunk expansion, lane-parallel: transition jj of agent ag -> (next-row byte offset, cell address, reward, (1-alpha)*old)
+      auto expand = [&](int jj, int ag, int La, double oma, uint32_t& row_off, uint32_t& cell_addr, double2& v) {
+        const int j = T - La + jj;
+        const uint32_t rw = rowsW[seq[j]], rn = rowsW[seq[j + 1]];
+        const uint32_t kk = rec[j];
+        const int joint = (int)__dp4a(kk, dp_b, 0u);
+        const int Aa = ag ? A1 : A0, k = ag ? (int)(kk >> 8) : (int)(kk & 0xff);
+        const int cu = ag ? (int)(rw >> 24) : (int)((rw >> 8) & 0xff), cn = ag ? (int)(rn >> 24) : (int)((rn >> 8) & 0xff);
+        row_off = (uint32_t)(cn * Aa) * (uint32_t)sizeof(QT);
+        cell_addr = (ag ? tab1_off : tab0_off) + (uint32_t)(cu * Aa + k) * (uint32_t)sizeof(QT);
+        v = make_double2(lutR[2 * joint + ag], __dmul_rn(oma, (double)olds[2 * jj + ag]));
+      };
+
       // ---- D: the sequential pass (agents.py:68-76).  The two agents' chains are independent: both rows are loaded
       //      before either cell is stored so the two dependency chains overlap.
-      auto load_max = [&](const QT* tab_lane, int A, bool in, uint32_t row_off) -> double {
-        const QT* row_lane = reinterpret_cast<const QT*>(reinterpret_cast<const unsigned char*>(tab_lane) + row_off);
-        if (kSmallA) return (double)warp_max(row_lane[0]);                        // live table (:71)
-        return (double)lut2_row_max<QT, false>(row_lane, A, lane, in);
-      };
-      auto store_cell = [&](QT* tab, uint32_t cell_off, double v, double next_max, double alpha, double gamma, double2 rcv) {
-        (void)v;
-        const double nv = __dadd_rn(rcv.y, __dmul_rn(alpha, __dadd_rn(rcv.x, __dmul_rn(gamma, next_max))));  // :72-74
-        if (lane == 0) *reinterpret_cast<QT*>(reinterpret_cast<unsigned char*>(tab) + cell_off) = (QT)nv;   // :75
+      auto load_max = [&](uint32_t tab_lane_off, int A, bool in, uint32_t row_off) -> QT {
+        const QT* row_lane = reinterpret_cast<const QT*>(smem + (tab_lane_off + row_off));
+        if (kSmallA) return warp_max(row_lane[0]);                        // live table (:71)
+        return lut2_row_max<QT, false>(row_lane, A, lane, in);
       };
       if (L0 == L1) {
         // Both agents in one instruction stream: the two row maxima are warp reductions, the f64 arithmetic that follows is
         // evaluated once with lanes 0-15 carrying agent 0 and lanes 16-31 agent 1; lanes 0 and 16 store.
-        const uint4* mp = reinterpret_cast<const uint4*>(meta);
-        const double2* vp = rc + (lane >> 4);
-#pragma unroll 2
-        for (int j = 0; j < L0; ++j) {
-          const uint4 m = mp[j];
-          const double2 v = vp[2 * j];
-          const double mx0 = load_max(tab0_lane, A0, in0, m.x);
-          const double mx1 = load_max(tab1_lane, A1, in1, m.z);
-          const double mx = hi_half ? mx1 : mx0;
-          const double nv = __dadd_rn(v.y, __dmul_rn(alpha_h, __dadd_rn(v.x, __dmul_rn(gamma_h, mx))));  // :72-74
-          if (store_lane) *reinterpret_cast<QT*>(tab_h + (hi_half ? m.w : m.y)) = (QT)nv;                 // :75
+        const uint32_t ent = chunk_off + (uint32_t)(lane >> 4) * 32u;
+        const int li = lane & (kLut2Chunk - 1);
+        for (int c0 = 0; c0 < L0; c0 += kLut2Chunk) {
+          const int n = L0 - c0 < kLut2Chunk ? L0 - c0 : kLut2Chunk;
+          {
+            uint32_t row_off = 0, cell_addr = 0;
+            double2 v = make_double2(0.0, 0.0);
+            if (li < n) expand(c0 + li, lane >> 4, L0, oma_h, row_off, cell_addr, v);
+            const uint32_t other = __shfl_xor_sync(kFull, row_off, 16);
+            if (li < n) {
+              *reinterpret_cast<uint4*>(smem + ent + li * 64) = make_uint4(hi_half ? other : row_off, hi_half ? row_off : other, cell_addr, 0u);
+              *reinterpret_cast<double2*>(smem + ent + li * 64 + 16) = v;
+            }
+          }
           __syncwarp();
+#pragma unroll 2
+          for (int j = 0; j < n; ++j) {
+            const uint4 m = *reinterpret_cast<const uint4*>(smem + ent + j * 64);
+            const double2 v = *reinterpret_cast<const double2*>(smem + ent + j * 64 + 16);
+            const QT mx0 = load_max(tab0_lane_off, A0, in0, m.x);
+            const QT mx1 = load_max(tab1_lane_off, A1, in1, m.y);
+            const double mx = (double)(hi_half ? mx1 : mx0);
+            const double nv = __dadd_rn(v.y, __dmul_rn(alpha_h, __dadd_rn(v.x, __dmul_rn(gamma_h, mx))));  // :72-74
+            if (store_lane) *reinterpret_cast<QT*>(smem + m.z) = (QT)nv;                                    // :75
+            __syncwarp();
+          }
         }
       } else {
-        for (int j = 0; j < L0; ++j) {
-          const uint2 m = meta[2 * j];
-          store_cell(tab0, m.y, 0.0, load_max(tab0_lane, A0, in0, m.x), alpha0, gamma0, rc[2 * j]);
-          __syncwarp();
-        }
-        for (int j = 0; j < L1; ++j) {
-          const uint2 m = meta[2 * j + 1];
-          store_cell(tab1, m.y, 0.0, load_max(tab1_lane, A1, in1, m.x), alpha1, gamma1, rc[2 * j + 1]);
-          __syncwarp();
+        for (int ag = 0; ag < 2; ++ag) {
+          const int La = ag ? L1 : L0;
+          const uint32_t ent = chunk_off + (uint32_t)ag * 32u;
+          const double alpha = ag ? alpha1 : alpha0, gamma = ag ? gamma1 : gamma0;
+          for (int c0 = 0; c0 < La; c0 += kLut2Chunk) {
+            const int n = La - c0 < kLut2Chunk ? La - c0 : kLut2Chunk;
+            if (lane < n) {
+              uint32_t row_off, cell_addr;
+              double2 v;
+              expand(c0 + lane, ag, La, ag ? oma1 : oma0, row_off, cell_addr, v);
+              *reinterpret_cast<uint4*>(smem + ent + lane * 64) = make_uint4(row_off, row_off, cell_addr, 0u);
+              *reinterpret_cast<double2*>(smem + ent + lane * 64 + 16) = v;
+            }
+            __syncwarp();
+            for (int j = 0; j < n; ++j) {
+              const uint4 m = *reinterpret_cast<const uint4*>(smem + ent + j * 64);
+              const double2 v = *reinterpret_cast<const double2*>(smem + ent + j * 64 + 16);
+              const double mx = (double)(ag ? load_max(tab1_lane_off, A1, in1, m.x) : load_max(tab0_lane_off, A0, in0, m.x));
+              const double nv = __dadd_rn(v.y, __dmul_rn(alpha, __dadd_rn(v.x, __dmul_rn(gamma, mx))));  // :72-74
+              if (lane == 0) *reinterpret_cast<QT*>(smem + m.z) = (QT)nv;                                // :75
+              __syncwarp();
+            }
+          }
         }
       }
 
       // ---- E: refresh the greedy cache of written rows, then the per-state greedy pairs
       {
-        auto refresh = [&](QT* tab, int A, bool in, int NRa, uint8_t* gr, unsigned wa, unsigned wb, bool all) {
+        // lane = compact row: every lane scans one written row left to right (first maximum, agents.py:88); rows of
+        // distinct lanes start A elements apart, so for odd A the scan is bank-conflict-free
+        auto refresh = [&](const QT* tab, int A, int NRa, uint8_t* gr, unsigned wa, unsigned wb, bool all) {
           wa = __reduce_or_sync(kFull, wa);
           wb = __reduce_or_sync(kFull, wb);
-          if (__any_sync(kFull, all)) {
-            for (int c = 64; c < NRa + 2; ++c) {
-              const int g = lut2_row_argmax<QT, kSmallA>(tab + c * A, A, lane, in);
-              if (lane == 0) gr[c] = (uint8_t)g;
+          const bool every = __any_sync(kFull, all);
+          for (int c = lane; c < NRa + 2; c += 32) {
+            const bool d = c < 32 ? (wa >> c) & 1u : (c < 64 ? (wb >> (c - 32)) & 1u : every);
+            if (d) {
+              const QT* row = tab + c * A;
+              QT m = row[0];
+              int g = 0;
+#pragma unroll 4
+              for (int k = 1; k < A; ++k) {
+                const QT v = row[k];
+                if (v > m) { m = v; g = k; }
+              }
+              gr[c] = (uint8_t)g;
             }
           }
-          while (wa) {
-            const int c = __ffs(wa) - 1;
-            wa &= wa - 1;
-            const int g = lut2_row_argmax<QT, kSmallA>(tab + c * A, A, lane, in);
-            if (lane == 0) gr[c] = (uint8_t)g;
-          }
-          while (wb) {
-            const int c = 32 + __ffs(wb) - 1;
-            wb &= wb - 1;
-            const int g = lut2_row_argmax<QT, kSmallA>(tab + c * A, A, lane, in);
-            if (lane == 0) gr[c] = (uint8_t)g;
-          }
         };
-        refresh(tab0, A0, in0, NR0, grow, dirty0a, dirty0b, dirty_all0);
-        refresh(tab1, A1, in1, NR1, grow + NR0 + 2, dirty1a, dirty1b, dirty_all1);
+        refresh(tab0, A0, NR0, grow, dirty0a, dirty0b, dirty_all0);
+        refresh(tab1, A1, NR1, grow + NR0 + 2, dirty1a, dirty1b, dirty_all1);
         __syncwarp();
         for (int s = lane; s <= NS; s += 32) {
           const uint32_t rw = rowsW[s];

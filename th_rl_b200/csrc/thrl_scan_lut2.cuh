@@ -124,14 +124,13 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
   uint32_t* GJ = reinterpret_cast<uint32_t*>(GJb);
   uint16_t* rec = reinterpret_cast<uint16_t*>(slot + p.off_rec);     // [T] k0 | k1<<8
   uint8_t* seq = slot + p.off_seq;                                   // [T+1] state before step t (rebuilt lane-parallel)
-  uint2* pre = reinterpret_cast<uint2*>(slot + p.off_scr);           // [T] (keep mask, forced value) byte pairs      (phases A-B)
-  // phase D chunk: entry [i][agent] of 32 B = uint4 (next-row byte offset agent 0, same agent 1, cell address in smem, -)
-  //                                        + double2 (reward, (1-alpha)*old)
+  uint2* pre = reinterpret_cast<uint2*>(slot + p.off_old);           // [T] (keep mask, forced value) byte pairs (phases A-B; olds in C-D)
+  // phase D chunk: [kLut2Chunk] uint2 = next-row byte offsets of (agent 0, agent 1) for the transitions being applied
   unsigned char* chunk = slot + p.off_scr;
   QT* olds = reinterpret_cast<QT*>(slot + p.off_old);                // [T][2] stale old values of the batch (agents.py:67)
 
   const bool in0 = lane < A0, in1 = lane < A1;
-  const bool hi_half = lane >= 16, store_lane = (lane & 15) == 0;
+  const bool hi_half = lane >= 16;
   const int L0 = p.L[0], L1 = p.L[1];
   const uint32_t dp_b = (uint32_t)A1 | (1u << 8);  // joint = dp4a(k0 | k1<<8, A1 | 1<<8)
   // lanes >= A re-read the last column: harmless for a max, and no masked load / select in the hot loop
@@ -140,6 +139,7 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
   const uint32_t tab0_lane_off = tab0_off + (uint32_t)sizeof(QT) * (uint32_t)(kSmallA ? (lane < A0 ? lane : A0 - 1) : lane);
   const uint32_t tab1_lane_off = tab1_off + (uint32_t)sizeof(QT) * (uint32_t)(kSmallA ? (lane < A1 ? lane : A1 - 1) : lane);
   const uint32_t chunk_off = (uint32_t)(chunk - smem);
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem);
 
   const long long total_warps = (long long)gridDim.x * warps_per_cta;
   for (long long r = (long long)blockIdx.x * warps_per_cta + warp; r < p.n_runs; r += total_warps) {
@@ -262,21 +262,38 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
         const uint32_t rec_a = base + (uint32_t)(reinterpret_cast<unsigned char*>(rec) - smem);
         const uint32_t gj_a = base + (uint32_t)(GJb - smem);
         const uint32_t log_a = base + (uint32_t)p.off_lutlog + 8u * (uint32_t)(lane & 3);
-        const uint32_t next_a = base + (uint32_t)p.off_next;
+        uint32_t next_a = base + (uint32_t)p.off_next;
+        asm volatile("" : "+r"(next_a));  // keep it in a register
+        const uint32_t log_lane = lane < 4 ? 1u : 0u;
+        double lg = 0.0;
         uint32_t kk = 0;
-#pragma unroll 4
-        for (int t = 0; t < T; ++t) {
-          uint32_t fx, fy, gj, s16;
-          double lg;
-          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(fx), "=r"(fy) : "r"(pre_a + 8u * t));
+        // one step: greedy pair of the state, forced override, joint action, log accumulate (lanes 0-3 only), next state
+        auto step = [&](uint32_t fx, uint32_t fy) {
+          uint32_t gj, s16;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gj) : "r"(gj_a + sig4));
           kk = (gj & fx) | fy;                                 // agents.py:80-89 for both agents
           const uint32_t joint = __dp4a(kk, dp_b, 0u);         // k0 * A1 + k1
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(rec_a + 2u * t), "h"((uint16_t)kk) : "memory");  // same value from every lane
-          asm volatile("ld.shared.f64 %0, [%1];" : "=d"(lg) : "r"(log_a + 32u * joint));
-          acc = __dadd_rn(acc, lg);
+          asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q ld.shared.f64 %0, [%1]; }"
+                       : "+d"(lg) : "r"(log_a + 32u * joint), "r"(log_lane));  // lanes 0-3 only (other lanes keep lg = 0)
+          acc = __dadd_rn(acc, lg);                            // trainer.py:65-66
           asm volatile("ld.shared.u16 %0, [%1];" : "=r"(s16) : "r"(next_a + 2u * joint));
           sig4 = s16;
+        };
+        uint32_t pa = pre_a, ra = rec_a;
+#pragma unroll 2
+        for (int n2 = T >> 1; n2 > 0; --n2, pa += 16u, ra += 4u) {  // two steps per 16-byte load of pre and per 4-byte store of rec
+          uint32_t f0x, f0y, f1x, f1y;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f0x), "=r"(f0y), "=r"(f1x), "=r"(f1y) : "r"(pa));
+          step(f0x, f0y);
+          const uint32_t ka = kk;
+          step(f1x, f1y);
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(ra), "r"(__byte_perm(ka, kk, 0x5410)) : "memory");  // same value from every lane
+        }
+        if (T & 1) {
+          uint32_t fx, fy;
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(fx), "=r"(fy) : "r"(pa));
+          step(fx, fy);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(ra), "h"((uint16_t)kk) : "memory");
         }
         last_k = (int)kk;
       }
@@ -346,56 +363,51 @@ __global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const 
         return lut2_row_max<QT, false>(row_lane, A, lane, in);
       };
       if (L0 == L1) {
-        // Both agents in one instruction stream: the two row maxima are warp reductions, the f64 arithmetic that follows is
-        // evaluated once with lanes 0-15 carrying agent 0 and lanes 16-31 agent 1; lanes 0 and 16 store.
-        const uint32_t ent = chunk_off + (uint32_t)(lane >> 4) * 32u;
+        // Both agents in one instruction stream, lanes 0-15 carrying agent 0 and lanes 16-31 agent 1.  Lane i of each half
+        // expands transition c0+i of its agent and keeps the cell address, reward and (1-alpha)*old in registers; only the
+        // two next-row offsets of every transition go through shared memory (one uniform 8-byte load per iteration).  The
+        // row maxima are warp reductions, so every lane evaluates :72-74 and the lane that owns transition j stores.
         const int li = lane & (kLut2Chunk - 1);
         for (int c0 = 0; c0 < L0; c0 += kLut2Chunk) {
           const int n = L0 - c0 < kLut2Chunk ? L0 - c0 : kLut2Chunk;
-          {
-            uint32_t row_off = 0, cell_addr = 0;
-            double2 v = make_double2(0.0, 0.0);
-            if (li < n) expand(c0 + li, lane >> 4, L0, oma_h, row_off, cell_addr, v);
-            const uint32_t other = __shfl_xor_sync(kFull, row_off, 16);
-            if (li < n) {
-              *reinterpret_cast<uint4*>(smem + ent + li * 64) = make_uint4(hi_half ? other : row_off, hi_half ? row_off : other, cell_addr, 0u);
-              *reinterpret_cast<double2*>(smem + ent + li * 64 + 16) = v;
-            }
-          }
+          uint32_t row_off = 0, cell_addr = 0;
+          double2 v = make_double2(0.0, 0.0);
+          if (li < n) expand(c0 + li, lane >> 4, L0, oma_h, row_off, cell_addr, v);
+          const uint32_t other = __shfl_xor_sync(kFull, row_off, 16);
+          if (lane < n) *reinterpret_cast<uint2*>(smem + chunk_off + lane * 8) = make_uint2(row_off, other);
           __syncwarp();
+          uint32_t ca = smem_base + chunk_off;
+          int cd = li;  // iterations until this lane's transition is applied
 #pragma unroll 2
-          for (int j = 0; j < n; ++j) {
-            const uint4 m = *reinterpret_cast<const uint4*>(smem + ent + j * 64);
-            const double2 v = *reinterpret_cast<const double2*>(smem + ent + j * 64 + 16);
-            const QT mx0 = load_max(tab0_lane_off, A0, in0, m.x);
-            const QT mx1 = load_max(tab1_lane_off, A1, in1, m.y);
+          for (int j = n; j > 0; --j, ca += 8u, --cd) {
+            uint32_t mx_, my_;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mx_), "=r"(my_) : "r"(ca));
+            const QT mx0 = load_max(tab0_lane_off, A0, in0, mx_);
+            const QT mx1 = load_max(tab1_lane_off, A1, in1, my_);
             const double mx = (double)(hi_half ? mx1 : mx0);
             const double nv = __dadd_rn(v.y, __dmul_rn(alpha_h, __dadd_rn(v.x, __dmul_rn(gamma_h, mx))));  // :72-74
-            if (store_lane) *reinterpret_cast<QT*>(smem + m.z) = (QT)nv;                                    // :75
+            if (cd == 0) *reinterpret_cast<QT*>(smem + cell_addr) = (QT)nv;                                 // :75
             __syncwarp();
           }
         }
       } else {
         for (int ag = 0; ag < 2; ++ag) {
           const int La = ag ? L1 : L0;
-          const uint32_t ent = chunk_off + (uint32_t)ag * 32u;
           const double alpha = ag ? alpha1 : alpha0, gamma = ag ? gamma1 : gamma0;
           for (int c0 = 0; c0 < La; c0 += kLut2Chunk) {
             const int n = La - c0 < kLut2Chunk ? La - c0 : kLut2Chunk;
+            uint32_t row_off = 0, cell_addr = 0;
+            double2 v = make_double2(0.0, 0.0);
             if (lane < n) {
-              uint32_t row_off, cell_addr;
-              double2 v;
               expand(c0 + lane, ag, La, ag ? oma1 : oma0, row_off, cell_addr, v);
-              *reinterpret_cast<uint4*>(smem + ent + lane * 64) = make_uint4(row_off, row_off, cell_addr, 0u);
-              *reinterpret_cast<double2*>(smem + ent + lane * 64 + 16) = v;
+              *reinterpret_cast<uint32_t*>(smem + chunk_off + lane * 8) = row_off;
             }
             __syncwarp();
             for (int j = 0; j < n; ++j) {
-              const uint4 m = *reinterpret_cast<const uint4*>(smem + ent + j * 64);
-              const double2 v = *reinterpret_cast<const double2*>(smem + ent + j * 64 + 16);
-              const double mx = (double)(ag ? load_max(tab1_lane_off, A1, in1, m.x) : load_max(tab0_lane_off, A0, in0, m.x));
+              const uint32_t ro = *reinterpret_cast<const uint32_t*>(smem + chunk_off + j * 8);
+              const double mx = (double)(ag ? load_max(tab1_lane_off, A1, in1, ro) : load_max(tab0_lane_off, A0, in0, ro));
               const double nv = __dadd_rn(v.y, __dmul_rn(alpha, __dadd_rn(v.x, __dmul_rn(gamma, mx))));  // :72-74
-              if (lane == 0) *reinterpret_cast<QT*>(smem + m.z) = (QT)nv;                                // :75
+              if (lane == j) *reinterpret_cast<QT*>(smem + cell_addr) = (QT)nv;                          // :75
               __syncwarp();
             }
           }

@@ -300,7 +300,8 @@ bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int
   p->warp_bytes = o;
   const int w = (smem_optin - p->cta_bytes) / p->warp_bytes;
   if (w < 2) return false;
-  *warps = w > thrl::kLut2MaxWarps ? thrl::kLut2MaxWarps : w;
+  const int wmax = elem == 8 ? thrl::Lut2Warps<double>::kMax : thrl::Lut2Warps<float>::kMax;
+  *warps = w > wmax ? wmax : w;
   return true;
 }
 

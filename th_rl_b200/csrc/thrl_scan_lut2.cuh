@@ -53,7 +53,9 @@ struct Lut2Params {
   int off_tab1, off_grow, off_rows, off_gj, off_seq, off_rec, off_scr, off_old;  // per warp (tables of agent 0 at 0)
 };
 
-constexpr int kLut2MaxWarps = 20;
+constexpr int kLut2MaxWarps = 24;  // float tables: 6 warps per scheduler at 80 registers
+template <typename QT> struct Lut2Warps { static constexpr int kMax = kLut2MaxWarps; };
+template <> struct Lut2Warps<double> { static constexpr int kMax = 16; };  // shared memory caps f64 tables at ~12 runs per SM: leave ptxas 128 registers
 constexpr int kLut2Chunk = 16;  // transitions expanded per pass of the update (16 lanes per agent)
 
 // Row max / first argmax with the column count known to be <= 32 at compile time (kSmallA): one LDS per lane.
@@ -74,7 +76,7 @@ __device__ __forceinline__ int lut2_row_argmax(const QT* row, int A, int lane, b
 }
 
 template <typename QT, bool kSmallA>
-__global__ void __launch_bounds__(32 * kLut2MaxWarps, 1) qtable_scan_lut2(const __grid_constant__ Lut2Params p) {
+__global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(const __grid_constant__ Lut2Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ThrlGame& G = p.game;
   const int lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;

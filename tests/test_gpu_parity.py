@@ -432,6 +432,36 @@ def test_wide_action_tables_match_oracle(kernel_choice):
     _philox_case(_c4_cfg(120, 200, n=2, T=60, lo=0.2, hi=0.45), 20, 4, np.float32, seed=24)
 
 
+def _two_agent_cfg(T, a0, a1, env=None):
+    base = dict(name="QTable", gamma=0.95, alpha=0.1, eps_end=0.001, epsilon=0.5, eps_step=0.9995, states=100, actions=21,
+                action_range=[0.2, 0.4])
+    return {"agents": [dict(base, **a0), dict(base, **a1)],
+            "environment": dict(dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=2, max_steps=T), **(env or {})),
+            "training": dict(print_freq=500, epochs=3)}
+
+
+@pytest.mark.parametrize("case", ["odd_T", "short_T", "partial_chunks", "unequal_batches", "one_never_fires", "unequal_actions",
+                                  "wide_actions"])
+def test_two_agent_edge_shapes_match_oracle(case, kernel_choice):
+    """Shapes that exercise the corners of the specialised 2-agent kernel: odd / tiny episode lengths (rollout tail, a single
+    partial update chunk), batches that are not a multiple of the 16-transition chunk, agents whose batches differ in
+    length (separate update loops), an agent whose buffer never reaches min_memory, unequal and > 32-column action grids."""
+    from th_rl_b200 import _lib
+    cfg = {
+        "odd_T": _two_agent_cfg(33, dict(min_memory=33, capacity=500), dict(min_memory=20, capacity=500)),
+        "short_T": _two_agent_cfg(7, dict(min_memory=5, capacity=50), dict(min_memory=7, capacity=50)),
+        "partial_chunks": _two_agent_cfg(100, dict(min_memory=50, capacity=53), dict(min_memory=10, capacity=53)),
+        "unequal_batches": _two_agent_cfg(60, dict(min_memory=10, capacity=17), dict(min_memory=40, capacity=45)),
+        "one_never_fires": _two_agent_cfg(40, dict(min_memory=30, capacity=40), dict(min_memory=100, capacity=50)),
+        "unequal_actions": _two_agent_cfg(50, dict(actions=5, min_memory=50, capacity=500), dict(actions=9, states=37, min_memory=50, capacity=500)),
+        "wide_actions": _two_agent_cfg(30, dict(actions=40, states=60, min_memory=30), dict(actions=21, min_memory=30)),
+    }[case]
+    for dtype, seed in ((np.float32, 41), (np.float64, 42)):
+        _philox_case(cfg, 40, 4, dtype, seed=seed, run_id0=3, hp=(case == "partial_chunks"), chunks=[1, 3] if case == "odd_T" else None)
+    if kernel_choice == "auto":
+        assert _lib.last_kernel() == "lut2", _lib.last_kernel()
+
+
 def test_initial_price_above_reachable_rows(kernel_choice):
     """The call's initial price may encode to a row the demand curve can never reach again (beyond the greedy-cache bound):
     start every run at p0 close to a, which is far above a - a*sum(lo)."""

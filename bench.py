@@ -295,8 +295,8 @@ def run_ours(args):
                 "traffic": None, "kernel": WL["kernel"], "kernel_ms": kern_ms,
                 "note": "tables are shared-memory resident, so the bound is SM shared-memory bandwidth / issue rate, not HBM "
                         "(BASELINE.md 5: 184 algorithmic B per agent-step; peak = 128 B/clk/SM x 148 SMs x %.0f MHz from "
-                        "MEASURED_PEAKS.json, %s). ncu (profiles/): ~38 warp instructions and ~10 shared-memory wavefronts "
-                        "per agent-step, LSU data pipe ~47%% busy, issue slots ~53%% busy; HBM sees only the one-off slab "
+                        "MEASURED_PEAKS.json, %s). ncu (profiles/): ~31 warp instructions and ~6 shared-memory wavefronts "
+                        "per agent-step, LSU data pipe ~52%% busy, issue slots ~70%% busy; HBM sees only the one-off slab "
                         "load/store and the visit counters" % (sm_max_mhz, peak_src),
                 "hbm": {"achieved": per_gpu_rate * (2 * _run_stride() * (4 + 4 + 4) / (nag * 1.0 * E * MAX_STEPS)) / 1e9,
                         "peak": hbm_peak, "unit": "GB/s"}}

@@ -385,7 +385,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (default); c4 = HBM-resident sweep; c5 = MLP (ActorCritic) agents")
     ap.add_argument("--runs-per-gpu", type=int, default=None)
     ap.add_argument("--epochs", type=int, default=None)
-    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--e2e-chunks", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     select_workload(args.workload)

@@ -189,6 +189,10 @@ int64_t thrl_launch_count(void);
  * "generic" (Q-table games), "pwl" (lattice kernel for games with Reinforce / ActorCritic agents), "mixed" (order-exact MLP
  * kernel).  The dispatch is a function of the game, the inputs and THRL_KERNEL; tests use this to check it. */
 const char* thrl_last_kernel(void);
+/* Runs the calling thread's latest scan launch kept resident at once (persistent grid x runs per CTA).  A caller that cuts a
+ * batch into several launches (engine.scan_from_host overlaps them with host copies) sizes the pieces in multiples of this,
+ * so no launch ends on a partly filled round. */
+int64_t thrl_last_wave_runs(void);
 
 #ifdef __cplusplus
 }

@@ -22,7 +22,8 @@ def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "thrl.h")).read()
     names = set(re.findall(r"\b(thrl_[a-z0-9_]+)\s*\(", hdr))
     assert {"thrl_qtable_scan", "thrl_qtable_scan_host", "thrl_qtable_init", "thrl_greedy_eval", "thrl_game_layout",
-            "thrl_ring_bytes", "thrl_last_error", "thrl_abi_version", "thrl_launch_count"} <= names
+            "thrl_ring_bytes", "thrl_last_error", "thrl_abi_version", "thrl_launch_count", "thrl_last_kernel",
+            "thrl_last_wave_runs"} <= names
     for nm in names:
         assert hasattr(L, nm), nm
     assert L.thrl_abi_version() == abi.THRL_ABI_VERSION

@@ -52,6 +52,7 @@ def lib():
     L.thrl_greedy_eval_mlp.restype = C.c_int
     L.thrl_launch_count.restype = C.c_int64
     L.thrl_last_kernel.restype = C.c_char_p
+    L.thrl_last_wave_runs.restype = C.c_int64
     _lib = L
     return L
 
@@ -79,3 +80,8 @@ def launch_count():
 def last_kernel():
     """Name of the scan kernel this thread's latest scan call ran (include/thrl.h thrl_last_kernel)."""
     return lib().thrl_last_kernel().decode()
+
+
+def last_wave_runs():
+    """Runs the latest scan launch of this thread kept resident at once (include/thrl.h thrl_last_wave_runs)."""
+    return int(lib().thrl_last_wave_runs())

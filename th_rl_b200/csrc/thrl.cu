@@ -29,6 +29,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
+thread_local long long g_last_wave = 0;  // runs resident at once in this thread's latest scan launch (thrl_last_wave_runs)
 thread_local const char* g_last_kernel = "";  // scan kernel of this thread's latest thrl_qtable_scan (thrl_last_kernel)
 std::atomic<long long> g_launches{0};
 
@@ -197,6 +198,7 @@ int launch_generic(thrl::ScanParams& p, const DeviceInfo& dev, cudaStream_t stre
   auto kern = smem_tables ? thrl::qtable_scan_generic<T, true> : thrl::qtable_scan_generic<T, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_last_kernel = "generic";
+  g_last_wave = (long long)grid * warps;
   kern<<<grid, warps * 32, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -308,6 +310,7 @@ bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int
 template <typename QT>
 int launch_lut2(thrl::Lut2Params& p, int warps, const DeviceInfo& dev, cudaStream_t stream) {
   int grid = dev.sms;
+  g_last_wave = (long long)dev.sms * warps;
   const long long needed_ctas = (p.n_runs + warps - 1) / warps;
   if (needed_ctas < grid) {
     warps = (int)((p.n_runs + dev.sms - 1) / dev.sms);
@@ -366,6 +369,7 @@ int launch_lpc_gl(thrl::Lut2Params& p, const DeviceInfo& dev, cudaStream_t strea
   auto kern = a21 ? thrl::qtable_scan_lpc<QT, GL, 21> : thrl::qtable_scan_lpc<QT, GL, 0>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_last_kernel = "lpc";
+  g_last_wave = (long long)grid * warps * (GL / 2);
   kern<<<grid, warps * 32, smem, stream>>>(p, lay);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -431,6 +435,7 @@ int launch_mixed(thrl::MixedParams& p, const DeviceInfo& dev, cudaStream_t strea
   auto kern = thrl::qtable_scan_mixed<QT>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_last_kernel = "mixed";
+  g_last_wave = (long long)grid * warps;
   kern<<<grid, warps * 32, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);
@@ -644,6 +649,7 @@ int launch_pwl(thrl::PwlParams& p, int warps, bool f64, const DeviceInfo& dev, c
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
     g_last_kernel = "pwl";
+    g_last_wave = (long long)grid * warps;
     kern<<<grid, warps * 32, smem, stream>>>(p);
     e = cudaGetLastError();
   }
@@ -676,6 +682,7 @@ int thrl_abi_version(void) { return THRL_ABI_VERSION; }
 const char* thrl_last_error(void) { return g_err; }
 int64_t thrl_launch_count(void) { return (int64_t)g_launches.load(); }
 const char* thrl_last_kernel(void) { return g_last_kernel; }
+int64_t thrl_last_wave_runs(void) { return g_last_wave; }
 
 int thrl_game_layout(ThrlGame* game) { return validate_layout(game); }
 

@@ -41,6 +41,7 @@ class RunBatch:
         self.run_id0 = int(run_id0)
         self.seed = int(seed)
         self.epoch = 0
+        self.wave = 0  # runs one scan launch keeps resident (learned from the first scan)
         self._zeros = torch.zeros  # allocator of the per-call output buffers (tests substitute a guard-banded arena)
         g, R, n = self.game, self.n_runs, self.game.n_agents
         with torch.cuda.device(self.device):
@@ -141,6 +142,7 @@ class RunBatch:
             a.trace_actions, a.trace_rewards, a.trace_prices = _dp(out.trace_actions), _dp(out.trace_rewards), _dp(out.trace_prices)
             s = stream if stream is not None else torch.cuda.current_stream()
             check(lib().thrl_qtable_scan(C.byref(a), C.c_void_p(s.cuda_stream)))
+            self.wave = max(self.wave, int(lib().thrl_last_wave_runs()))  # resident runs per launch (see scan_from_host)
             for t in keep:  # inputs must outlive the asynchronous kernel
                 t.record_stream(s)
         if advance:
@@ -209,7 +211,7 @@ class HostState:
         return sum(t.numel() * t.element_size() for t in (self.q, self.counter, self.eps, self.price, self.mlp) if t is not None)
 
 
-def scan_from_host(batch, host, epochs, n_chunks=8):
+def scan_from_host(batch, host, epochs, n_chunks=12):
     """Host-resident state -> `epochs` more epochs -> host-resident state, plus the cross-run statistics.
 
     The run range is cut into n_chunks; chunk c+1's host->device copy and chunk c-1's device->host copy run on their
@@ -217,14 +219,19 @@ def scan_from_host(batch, host, epochs, n_chunks=8):
     """
     dev, R, E, n = batch.device, batch.n_runs, int(epochs), batch.game.n_agents
     n_chunks = max(1, min(int(n_chunks), R))
-    # the first upload and the last download are the only copies no kernel hides: make those two chunks half-size
+    # The first upload and the last download are the only copies no kernel hides: those two chunks get half the weight.  Once a
+    # scan has told us how many runs one launch keeps resident (thrl_last_wave_runs), chunks are whole multiples of that, so
+    # no launch ends on a partly filled round of the persistent grid.
     w = [2] * n_chunks
     if n_chunks >= 3:
         w[0] = w[-1] = 1
+    unit = batch.wave if batch.wave and R >= 2 * n_chunks * batch.wave else 1
+    units = -(-R // unit)
     acc, tot, bounds = 0, sum(w), [0]
     for x in w:
         acc += x
-        bounds.append(R * acc // tot)
+        bounds.append(min(R, (units * acc // tot) * unit))
+    bounds[-1] = R
     with torch.cuda.device(dev):
         if not hasattr(batch, "_streams"):
             batch._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))

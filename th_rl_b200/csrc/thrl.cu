@@ -294,7 +294,7 @@ bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int
   p->off_gj = o;      o += align_up((NS + 1) * 4, 16);
   p->off_seq = o;     o += align_up(T + 1, 16);
   p->off_rec = o;     o += align_up(2 * T, 16);
-  p->off_scr = o;     o += thrl::kLut2Chunk * 8;                 // phase D: next-row offsets of one chunk of transitions
+  p->off_scr = o;     o += thrl::kLut2Chunk * 8 + 16;            // phase D: next-row offsets of one chunk of transitions (+ read-ahead pad)
   {  // phases A-B: pre[T] uint2; phases C-D: olds[T][2] -- disjoint lifetimes, one region
     const int pre = align_up(T * 8, 16), olds = align_up(2 * T * (int)elem, 16);
     p->off_old = o;   o += pre > olds ? pre : olds;

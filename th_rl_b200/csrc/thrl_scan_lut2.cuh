@@ -380,12 +380,16 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
           __syncwarp();
           uint32_t ca = smem_base + chunk_off;
           int cd = li;  // iterations until this lane's transition is applied
+          uint32_t mx_, my_;  // next-row offsets, loaded one iteration ahead (off the store -> load chain; the slot after the
+                              // last transition of a full chunk is the 8-byte pad behind it)
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mx_), "=r"(my_) : "r"(ca));
 #pragma unroll 2
-          for (int j = n; j > 0; --j, ca += 8u, --cd) {
-            uint32_t mx_, my_;
+          for (int j = n; j > 0; --j, --cd) {
+            const uint32_t ox = mx_, oy = my_;
+            ca += 8u;
             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(mx_), "=r"(my_) : "r"(ca));
-            const QT mx0 = load_max(tab0_lane_off, A0, in0, mx_);
-            const QT mx1 = load_max(tab1_lane_off, A1, in1, my_);
+            const QT mx0 = load_max(tab0_lane_off, A0, in0, ox);
+            const QT mx1 = load_max(tab1_lane_off, A1, in1, oy);
             const double mx = (double)(hi_half ? mx1 : mx0);
             const double nv = __dadd_rn(v.y, __dmul_rn(alpha_h, __dadd_rn(v.x, __dmul_rn(gamma_h, mx))));  // :72-74
             if (cd == 0) *reinterpret_cast<QT*>(smem + cell_addr) = (QT)nv;                                 // :75

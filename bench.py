@@ -54,7 +54,7 @@ def _c4_hp(R, n):
 
 # name -> workload.  `algo_bytes` = SURVEY 8(d): 8*A + 16 bytes of table traffic per agent-step.
 WORKLOADS = {
-    "c2": dict(agents=2, runs_per_gpu=131072, epochs=200, config=_qcfg(2, 100, 21, 0.2, 0.4, 200), algo_bytes=184.0,
+    "c2": dict(agents=2, runs_per_gpu=131072, epochs=1000, config=_qcfg(2, 100, 21, 0.2, 0.4, 1000), algo_bytes=184.0,
                bound="smem", hp=None,
                desc="2-agent QTable iterated Cournot/PD game (example_config hyper-parameters, 101x21 tables, max_steps=100), "
                     "%d runs/GPU x %d epochs per step (C2 shape; 8 GPUs = the 1,048,576 runs of C3)",

@@ -462,6 +462,29 @@ def test_two_agent_edge_shapes_match_oracle(case, kernel_choice):
         assert _lib.last_kernel() == "lut2", _lib.last_kernel()
 
 
+def test_host_pipeline_equals_resident_scan(kernel_choice):
+    """engine.scan_from_host (bench.py's e2e leg: pinned host state in, chunked launches overlapped with the copies, state
+    out) leaves exactly the state and statistics of one resident scan -- with plain chunks and with chunks sized in whole
+    multiples of the kernel's resident-run count (thrl_last_wave_runs)."""
+    if kernel_choice != "auto":
+        pytest.skip("host pipeline is independent of the kernel choice")
+    torch, oracle, engine = _mods()
+    cfg = _two_agent_cfg(20, dict(min_memory=20), dict(min_memory=20))
+    for R, chunks in ((1000, 7), (30000, 3)):
+        a = engine.RunBatch(cfg, R, seed=5).init_device()
+        b = engine.RunBatch(cfg, R, seed=5).init_device()
+        ref = a.scan(2, stats=True)
+        host = engine.HostState.from_batch(b)
+        if R > 20000:
+            b.wave = 148 * 23  # what a full-size launch reports on a B200
+        stats, h2d, d2h = engine.scan_from_host(b, host, 2, n_chunks=chunks)
+        torch.cuda.synchronize()
+        assert h2d == d2h == host.nbytes()
+        assert torch.equal(host.q, a.q.cpu()) and torch.equal(host.counter, a.counter.cpu())
+        assert torch.equal(host.eps, a.eps.cpu()) and torch.equal(host.price, a.price.cpu())
+        assert torch.equal(stats, ref.stats)
+
+
 def test_initial_price_above_reachable_rows(kernel_choice):
     """The call's initial price may encode to a row the demand curve can never reach again (beyond the greedy-cache bound):
     start every run at p0 close to a, which is far above a - a*sum(lo)."""

@@ -299,7 +299,12 @@ def run_ours(args):
                         "per agent-step, LSU data pipe ~52%% busy, issue slots ~70%% busy; HBM sees only the one-off slab "
                         "load/store and the visit counters" % (sm_max_mhz, peak_src),
                 "hbm": {"achieved": per_gpu_rate * (2 * _run_stride() * (4 + 4 + 4) / (nag * 1.0 * E * MAX_STEPS)) / 1e9,
-                        "peak": hbm_peak, "unit": "GB/s"}}
+                        "peak": hbm_peak, "unit": "GB/s"},
+                # the limiter ncu names: warp-instruction issue.  Instructions per agent-step come from the committed ncu
+                # capture of this command (profiles/r1_bench_c2_lut2_ncu_summary.md), the rate is the live one.
+                "issue_slots": {"warp_inst_per_agent_step": 30.4, "achieved": per_gpu_rate * 30.4,
+                                "peak": 4 * 148 * sm_max_mhz * 1e6, "unit": "warp-inst/s",
+                                "frac": per_gpu_rate * 30.4 / (4 * 148 * sm_max_mhz * 1e6)}}
         elif WL["bound"] == "tensor":
             tf_peak, tf_src = measured_tflops()
             tf = per_gpu_rate * ALGO_BYTES_PER_AGENT_STEP / 1e12

@@ -151,6 +151,12 @@ void plan_generic(thrl::ScanParams* p, bool smem_tables, size_t elem) {
   for (int i = 0; i < n; ++i) if (G.agent[i].actions > amax) amax = G.agent[i].actions;
   p->quarter = (n <= 8 && amax <= 128 && !getenv("THRL_NO_QUARTER")) ? 1 : 0;
   p->qchunks = (amax + 7) / 8;
+  {  // columns per lane the kernel dispatches to (thrl_scan_generic.cuh); qfull: only the last of them can lie beyond a row's end
+    const int nc = p->qchunks <= 4 ? 4 : (p->qchunks <= 8 ? 8 : (p->qchunks <= 13 ? 13 : 16));
+    int amin = amax;
+    for (int i = 0; i < n; ++i) if (G.agent[i].actions < amin) amin = G.agent[i].actions;
+    p->qfull = (amin >= 8 * (nc - 1) && !getenv("THRL_NO_QFULL")) ? 1 : 0;
+  }
   p->cta_bytes = align_up(2 * lut * 8, 16);
   int o = 0;
   p->off_tab = o;

@@ -46,7 +46,8 @@ struct ScanParams {
   int Hp;          // ring slots = ring_len + 1
   int noisy;       // new_a varies per step (noise_prob > 0 or replay_new_a given)
   int quarter;     // use the quarter-warp update path (n <= 8 and every agent has <= 128 actions)
-  int qchunks;     // ceil(max actions / 8), rounded up to a multiple of 4
+  int qfull;       // every agent has >= 8*(NC-1) actions, NC = the dispatched column count: only the last column needs a bounds test
+  int qchunks;     // ceil(max actions / 8): columns per lane of a quarter warp (dispatched to 4 / 8 / 13 / 16 at compile time)
 };
 
 // Per-run ring blob carried between calls when the game is not regular (include/thrl.h ThrlScanArgs.ring).
@@ -235,37 +236,45 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
           // of both passes are issued before any reduction
           QT bv[2];
           int bi[2], rr[2];
-          auto fill_rows = [&](auto ncc) {
+          auto fill_rows = [&](auto ncc, auto fullc) {
             constexpr int NC = decltype(ncc)::value;
+            constexpr bool kFullRows = decltype(fullc)::value;  // every agent has >= 8*(NC-1) actions: only the last column can be missing
             QT v[2][NC];
-            bool mine[2];
+            int left[2];  // columns of the row at or beyond this lane's first one (<= 0: the lane has none)
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
               const int i = 4 * g2 + qq;
-              mine[g2] = qa_ok[g2] && ((need >> i) & 1u);
+              const bool mine = qa_ok[g2] && ((need >> i) & 1u);
               rr[g2] = __shfl_sync(kFull, arow, qa_ok[g2] ? i : 0);
-              const QT* row = tab + (qa_toff[g2] + (mine[g2] ? rr[g2] : 0) * qa_A[g2]);
+              left[g2] = (mine ? qa_A[g2] : 0) - ql;
+              const QT* row = tab + (qa_toff[g2] + (mine ? rr[g2] : 0) * qa_A[g2]);
 #pragma unroll
-              for (int c = 0; c < NC; ++c) {
-                const int kk = ql + 8 * c;
-                v[g2][c] = (mine[g2] && kk < qa_A[g2]) ? row[kk] : NegInf<QT>::v();
-              }
+              for (int c = 0; c < NC; ++c)  // (rows of quarters that are not served are read too -- row 0, valid memory -- and ignored)
+                v[g2][c] = ((kFullRows && c < NC - 1) || 8 * c < left[g2]) ? row[ql + 8 * c] : NegInf<QT>::v();
             }
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
-              bv[g2] = NegInf<QT>::v();
-              bi[g2] = 0x7fffffff;
+              // ascending columns, strict >: lowest index of this lane's maximum.  A lane without a first column has no
+              // column at all, and a missing column reads as -inf, which is never > anything: no validity tests needed.
+              bv[g2] = v[g2][0];
+              int bc = 0;  // chunk of the maximum (compile-time values: the select takes an immediate)
 #pragma unroll
-              for (int c = 0; c < NC; ++c) {  // ascending columns, strict >: lowest index of this lane's maximum
-                const int kk = ql + 8 * c;
-                if (mine[g2] && kk < qa_A[g2] && (v[g2][c] > bv[g2] || bi[g2] == 0x7fffffff)) { bv[g2] = v[g2][c]; bi[g2] = kk; }
-              }
+              for (int c = 1; c < NC; ++c)
+                if (v[g2][c] > bv[g2]) { bv[g2] = v[g2][c]; bc = c; }
+              bi[g2] = left[g2] > 0 ? ql + 8 * bc : 0x7fffffff;
             }
           };
-          if (p.qchunks <= 4) fill_rows(std::integral_constant<int, 4>{});
-          else if (p.qchunks <= 8) fill_rows(std::integral_constant<int, 8>{});
-          else if (p.qchunks <= 12) fill_rows(std::integral_constant<int, 12>{});
-          else fill_rows(std::integral_constant<int, 16>{});
+          if (p.qfull) {
+            if (p.qchunks <= 4) fill_rows(std::integral_constant<int, 4>{}, std::true_type{});
+            else if (p.qchunks <= 8) fill_rows(std::integral_constant<int, 8>{}, std::true_type{});
+            else if (p.qchunks <= 13) fill_rows(std::integral_constant<int, 13>{}, std::true_type{});  // C4: 101 actions = 13 columns per lane
+            else fill_rows(std::integral_constant<int, 16>{}, std::true_type{});
+          } else {
+            if (p.qchunks <= 4) fill_rows(std::integral_constant<int, 4>{}, std::false_type{});
+            else if (p.qchunks <= 8) fill_rows(std::integral_constant<int, 8>{}, std::false_type{});
+            else if (p.qchunks <= 13) fill_rows(std::integral_constant<int, 13>{}, std::false_type{});
+            else fill_rows(std::integral_constant<int, 16>{}, std::false_type{});
+          }
 #pragma unroll
           for (int g2 = 0; g2 < 2; ++g2) {
             if (!((need >> (4 * g2)) & 0xFu)) continue;
@@ -493,21 +502,21 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
           QT qm[2];
           bool qon[2];
           int qjj[2];
-          auto load_rows = [&](auto ncc) {
+          auto load_rows = [&](auto ncc, auto fullc) {
             constexpr int NC = decltype(ncc)::value;  // columns per lane, compile time: every load is issued before any compare
+            constexpr bool kFullRows = decltype(fullc)::value;
             QT v[2][NC];
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
               const int i = qa_ok[g2] ? 4 * g2 + qq : 0;
               qon[g2] = qa_ok[g2] && des[i * 4 + 2] && j >= des[i * 4 + 3];
               qjj[g2] = qon[g2] ? j - des[i * 4 + 3] : 0;
-              const int ns = rowbuf_all[i * p.row_stride + qjj[g2] + 1];
+              const int ns = qon[g2] ? (int)rowbuf_all[i * p.row_stride + qjj[g2] + 1] : 0;  // idle quarters read row 0 and are ignored
               const QT* row = tab + (qa_toff[g2] + ns * qa_A[g2]);
+              const int left = (qon[g2] ? qa_A[g2] : 0) - ql;  // columns at or beyond this lane's first one
 #pragma unroll
-              for (int c = 0; c < NC; ++c) {  // live table (:71): this lane's columns ql, ql+8, ...
-                const int kk = ql + 8 * c;
-                v[g2][c] = (qon[g2] && kk < qa_A[g2]) ? row[kk] : NegInf<QT>::v();
-              }
+              for (int c = 0; c < NC; ++c)  // live table (:71): this lane's columns ql, ql+8, ...
+                v[g2][c] = ((kFullRows && c < NC - 1) || 8 * c < left) ? row[ql + 8 * c] : NegInf<QT>::v();
             }
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
@@ -517,10 +526,17 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               qm[g2] = m;
             }
           };
-          if (p.qchunks <= 4) load_rows(std::integral_constant<int, 4>{});
-          else if (p.qchunks <= 8) load_rows(std::integral_constant<int, 8>{});
-          else if (p.qchunks <= 12) load_rows(std::integral_constant<int, 12>{});
-          else load_rows(std::integral_constant<int, 16>{});
+          if (p.qfull) {
+            if (p.qchunks <= 4) load_rows(std::integral_constant<int, 4>{}, std::true_type{});
+            else if (p.qchunks <= 8) load_rows(std::integral_constant<int, 8>{}, std::true_type{});
+            else if (p.qchunks <= 13) load_rows(std::integral_constant<int, 13>{}, std::true_type{});
+            else load_rows(std::integral_constant<int, 16>{}, std::true_type{});
+          } else {
+            if (p.qchunks <= 4) load_rows(std::integral_constant<int, 4>{}, std::false_type{});
+            else if (p.qchunks <= 8) load_rows(std::integral_constant<int, 8>{}, std::false_type{});
+            else if (p.qchunks <= 13) load_rows(std::integral_constant<int, 13>{}, std::false_type{});
+            else load_rows(std::integral_constant<int, 16>{}, std::false_type{});
+          }
 #pragma unroll
           for (int g2 = 0; g2 < 2; ++g2) {
             QT m = qm[g2];

@@ -52,14 +52,16 @@ def _c4_hp(R, n):
     return hp
 
 
-# name -> workload.  `algo_bytes` = SURVEY 8(d): 8*A + 16 bytes of table traffic per agent-step.
+# name -> workload.  `algo_bytes` = SURVEY 8(d): 8*A + 16 bytes of table traffic per agent-step.  `e2e_chunks`: launches the host
+# pipeline cuts a step into (c4 is copy-bound: many small launches keep both DMA directions busy; c5 has only 7 resident waves
+# per step: fewer, fuller launches).
 WORKLOADS = {
-    "c2": dict(agents=2, runs_per_gpu=131072, epochs=1000, config=_qcfg(2, 100, 21, 0.2, 0.4, 1000), algo_bytes=184.0,
+    "c2": dict(agents=2, runs_per_gpu=131072, epochs=1000, e2e_chunks=12, config=_qcfg(2, 100, 21, 0.2, 0.4, 1000), algo_bytes=184.0,
                bound="smem", hp=None,
                desc="2-agent QTable iterated Cournot/PD game (example_config hyper-parameters, 101x21 tables, max_steps=100), "
                     "%d runs/GPU x %d epochs per step (C2 shape; 8 GPUs = the 1,048,576 runs of C3)",
                kernel="thrl::qtable_scan_lut2<float, true> (persistent, one launch per step)"),
-    "c4": dict(agents=8, runs_per_gpu=4096, epochs=100, config=_qcfg(8, 1000, 101, 0.05, 0.15, 100), algo_bytes=824.0,
+    "c4": dict(agents=8, runs_per_gpu=4096, epochs=100, e2e_chunks=12, config=_qcfg(8, 1000, 101, 0.05, 0.15, 100), algo_bytes=824.0,
                bound="hbm", hp=_c4_hp,
                desc="hyper-parameter sweep (alpha x eps_step x gamma = 64 points x 64 seeds), 8 QTable agents, 1001x101 "
                     "tables left in HBM, max_steps=100, %d runs/GPU x %d epochs per step (C4 shape)",
@@ -73,7 +75,7 @@ def _c5_cfg(epochs):
 
 
 # ~1.1e4 flop per act + ~3.4e4 flop per agent-step of amortised update (N = 1000 batch every 10 episodes)
-WORKLOADS["c5"] = dict(agents=2, runs_per_gpu=16384, epochs=200, config=_c5_cfg(200), algo_bytes=4.5e4, bound="tensor", hp=None,
+WORKLOADS["c5"] = dict(agents=2, runs_per_gpu=16384, epochs=200, e2e_chunks=4, config=_c5_cfg(200), algo_bytes=4.5e4, bound="tensor", hp=None,
                        desc="2 ActorCritic agents (MLP 1->256->{21,1}, Adam, N=1000 transition batches every 10 episodes), "
                             "%d runs/GPU x %d epochs per step (C5 shape)",
                        kernel="thrl::mlp_scan_pwl (persistent, one launch per step; policy LUT per lattice state + sorted-breakpoint "
@@ -390,12 +392,13 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (default); c4 = HBM-resident sweep; c5 = MLP (ActorCritic) agents")
     ap.add_argument("--runs-per-gpu", type=int, default=None)
     ap.add_argument("--epochs", type=int, default=None)
-    ap.add_argument("--e2e-chunks", type=int, default=12)
+    ap.add_argument("--e2e-chunks", type=int, default=None, help="launches the host pipeline cuts a step into (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     select_workload(args.workload)
     args.runs_per_gpu = args.runs_per_gpu or WL["runs_per_gpu"]
     args.epochs = args.epochs or WL["epochs"]
+    args.e2e_chunks = args.e2e_chunks or WL["e2e_chunks"]
     globals()["EPOCHS"] = args.epochs
     if args.impl == "reference":
         return run_reference(args)

@@ -54,7 +54,7 @@ def _c4_hp(R, n):
 
 # name -> workload.  `algo_bytes` = SURVEY 8(d): 8*A + 16 bytes of table traffic per agent-step.  `e2e_chunks`: launches the host
 # pipeline cuts a step into (c4 is copy-bound: many small launches keep both DMA directions busy; c5 has only 7 resident waves
-# per step: fewer, fuller launches).
+# per step: about one launch per wave).
 WORKLOADS = {
     "c2": dict(agents=2, runs_per_gpu=131072, epochs=1000, e2e_chunks=12, config=_qcfg(2, 100, 21, 0.2, 0.4, 1000), algo_bytes=184.0,
                bound="smem", hp=None,
@@ -75,7 +75,7 @@ def _c5_cfg(epochs):
 
 
 # ~1.1e4 flop per act + ~3.4e4 flop per agent-step of amortised update (N = 1000 batch every 10 episodes)
-WORKLOADS["c5"] = dict(agents=2, runs_per_gpu=16384, epochs=200, e2e_chunks=4, config=_c5_cfg(200), algo_bytes=4.5e4, bound="tensor", hp=None,
+WORKLOADS["c5"] = dict(agents=2, runs_per_gpu=16384, epochs=200, e2e_chunks=8, config=_c5_cfg(200), algo_bytes=4.5e4, bound="tensor", hp=None,
                        desc="2 ActorCritic agents (MLP 1->256->{21,1}, Adam, N=1000 transition batches every 10 episodes), "
                             "%d runs/GPU x %d epochs per step (C5 shape)",
                        kernel="thrl::mlp_scan_pwl (persistent, one launch per step; policy LUT per lattice state + sorted-breakpoint "

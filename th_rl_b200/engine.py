@@ -225,7 +225,7 @@ def scan_from_host(batch, host, epochs, n_chunks=12):
     w = [2] * n_chunks
     if n_chunks >= 3:
         w[0] = w[-1] = 1
-    unit = batch.wave if batch.wave and -(-R // batch.wave) >= n_chunks else 1  # every chunk at least one full round
+    unit = batch.wave if batch.wave and -(-R // batch.wave) >= 2 * n_chunks else 1  # only when chunks span several rounds
     units = -(-R // unit)
     acc, tot, bounds = 0, sum(w), [0]
     for x in w:

@@ -10,10 +10,15 @@
 //
 // One warp = one run; per epoch:
 //   A  draws      lane-parallel Philox (or replay streams) -> per-step forced actions (epsilon is frozen in an episode)
-//   B  rollout    sequential: state -> greedy pair (cached per state) -> forced override -> joint action -> next state
-//   C  pre-pass   lane-parallel: stale snapshot (agents.py:67), rewards, cell/row addresses, visit counters (RED)
-//   D  update     sequential (agents.py:68-76), both agents' chains interleaved; row max = 1 LDS + 1 CREDUX.MAX
-//   E  refresh    greedy cache of the rows that were written; epsilon decay; logs / statistics
+//   B  rollout    sequential, two steps per iteration: state -> greedy pair (cached per state) -> forced override ->
+//                 joint action -> next state; log sums on lanes 0-3
+//   C  snapshot   lane-parallel: stale old value of every transition of the batch (agents.py:67), visit counters (RED),
+//                 dirty-row masks
+//   D  update     sequential (agents.py:68-76) in chunks of 16 transitions; lane i of a half-warp expands transition i of
+//                 its agent and keeps cell address / reward / (1-alpha)*old in registers; both agents' chains interleaved;
+//                 row max = 1 LDS + 1 CREDUX.MAX; the owning lane stores
+//   E  refresh    greedy cache of the rows that were written (lane = row); epsilon decay; logs / statistics
+// Shared memory per run: compact tables + ~1.7 KB of scratch: 23 runs per SM at the C2 shape.
 #pragma once
 #include "thrl_device.cuh"
 

@@ -328,8 +328,8 @@ def run_ours(args):
                         "long-scoreboard stalls dominate (latency-bound row gathers)" % peak_src}
         try:  # DRAM traffic per launch, measured once with ncu --set full on this exact command (profiles/)
             tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
-            if tr and args.runs_per_gpu == WL["runs_per_gpu"] and args.epochs == WL["epochs"]:
-                line["roofline"]["traffic"] = tr["traffic_bytes_per_launch"]
+            if tr and args.runs_per_gpu == WL["runs_per_gpu"]:  # per agent-step as captured x the agent-steps of this launch
+                line["roofline"]["traffic"] = tr["traffic_bytes_per_agent_step"] * agent_steps_rank
                 line["roofline"]["traffic_source"] = tr["source"]
                 line["roofline"]["algorithmic_bytes_per_launch"] = agent_steps_rank * ALGO_BYTES_PER_AGENT_STEP
         except (OSError, ValueError):

@@ -59,6 +59,8 @@ struct RingHeader {
 };
 static_assert(sizeof(RingHeader) == 80, "ring header");
 
+constexpr int kPrefetchAhead = 4;  // update pass, HBM-resident tables: rows of transition j + kPrefetchAhead are pulled into L2
+
 template <typename QT, bool kSmemTables>
 __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_generic(const __grid_constant__ ScanParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -409,7 +411,25 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
           rowbuf[j] = (uint16_t)upd_row(P[sl], s.max_state, (double)s.states);
         }
         __syncwarp();
-        for (int j = lane; j < L; j += 32) {
+        if (!kSmemTables && lane < kPrefetchAhead && lane < L) {  // rows the first transitions of the pass will read: into L2 now
+          const QT* row = tb + (size_t)rowbuf[lane + 1] * A;
+          for (int b = 0; b < A * (int)sizeof(QT); b += 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(row) + b));
+        }
+        {  // snapshot: up to four scattered cells per lane are in flight before the first one is stored
+          QT v4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = lane + 32 * u;
+            int sl = first + j;
+            if (sl >= Hp) sl -= Hp;
+            v4[u] = j < L ? tb[(int)rowbuf[j] * A + act[i * Hp + sl]] : (QT)0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (lane + 32 * u < L) oldv[lane + 32 * u] = v4[u];
+        }
+        for (int j = lane + 128; j < L; j += 32) {
           int sl = first + j;
           if (sl >= Hp) sl -= Hp;
           oldv[j] = tb[(int)rowbuf[j] * A + act[i * Hp + sl]];
@@ -417,8 +437,8 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
       }
       __syncwarp();
       for (int j = 0; j < Lmax; ++j) {  // the sequential pass (:68-76)
-        if (!kSmemTables && lane < n && des[lane * 4 + 2]) {  // HBM tables: pull the rows of step j+4 into L2 early
-          const int jp = j + 4 - des[lane * 4 + 3];
+        if (!kSmemTables && lane < n && des[lane * 4 + 2]) {  // HBM tables: pull the rows of step j + kPrefetchAhead into L2 early
+          const int jp = j + kPrefetchAhead - des[lane * 4 + 3];
           if (jp >= 0 && jp < des[lane * 4 + 0]) {
             const ThrlAgentSpec& s = G.agent[lane];
             const QT* row = tab + s.table_offset + (size_t)rowbuf_all[lane * p.row_stride + jp + 1] * s.actions;

@@ -258,12 +258,19 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
             for (int g2 = 0; g2 < 2; ++g2) {
               // ascending columns, strict >: lowest index of this lane's maximum.  A lane without a first column has no
               // column at all, and a missing column reads as -inf, which is never > anything: no validity tests needed.
-              bv[g2] = v[g2][0];
-              int bc = 0;  // chunk of the maximum (compile-time values: the select takes an immediate)
+              // pairwise tree (depth log2 NC instead of a chain of NC dependent selects); the left operand has the lower
+              // columns and wins ties, so the result is the one of the left-to-right scan
+              int ci[NC];
 #pragma unroll
-              for (int c = 1; c < NC; ++c)
-                if (v[g2][c] > bv[g2]) { bv[g2] = v[g2][c]; bc = c; }
-              bi[g2] = left[g2] > 0 ? ql + 8 * bc : 0x7fffffff;
+              for (int c = 0; c < NC; ++c) ci[c] = c;
+#pragma unroll
+              for (int st = 1; st < NC; st *= 2) {
+#pragma unroll
+                for (int c = 0; c + st < NC; c += 2 * st)
+                  if (v[g2][c + st] > v[g2][c]) { v[g2][c] = v[g2][c + st]; ci[c] = ci[c + st]; }
+              }
+              bv[g2] = v[g2][0];
+              bi[g2] = left[g2] > 0 ? ql + 8 * ci[0] : 0x7fffffff;
             }
           };
           if (p.qfull) {
@@ -540,10 +547,12 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
             }
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
-              QT m = v[g2][0];
 #pragma unroll
-              for (int c = 1; c < NC; ++c) m = v[g2][c] > m ? v[g2][c] : m;
-              qm[g2] = m;
+              for (int st = 1; st < NC; st *= 2) {  // pairwise tree: depth log2 NC
+#pragma unroll
+                for (int c = 0; c + st < NC; c += 2 * st) v[g2][c] = v[g2][c + st] > v[g2][c] ? v[g2][c + st] : v[g2][c];
+              }
+              qm[g2] = v[g2][0];
             }
           };
           if (p.qfull) {

@@ -443,6 +443,13 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
         }
       }
       __syncwarp();
+      // Quarter path: (max, first argmax) of the row an agent's NEXT transition will write -- it is the row this transition
+      // reads for its bootstrap (s'_j = s_{j+1}) -- carried to the next iteration, where one more comparison against the
+      // value just written gives the row's new greedy action.  The greedy cache then survives the update instead of being
+      // invalidated, and the next episodes act from the cache without touching HBM.  cok = the carried pair is valid.
+      QT cm[2] = {NegInf<QT>::v(), NegInf<QT>::v()};
+      int ca[2] = {0, 0};
+      bool cok[2] = {false, false};
       for (int j = 0; j < Lmax; ++j) {  // the sequential pass (:68-76)
         if (!kSmemTables && lane < n && des[lane * 4 + 2]) {  // HBM tables: pull the rows of step j + kPrefetchAhead into L2 early
           const int jp = j + kPrefetchAhead - des[lane * 4 + 3];
@@ -528,7 +535,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
           // ---- quarter-warp path: phase 1 loads + row max for up to 8 agents (two passes of four), phase 2 finishes + stores
           QT qm[2];
           bool qon[2];
-          int qjj[2];
+          int qjj[2], qidx[2], qns[2], qleft[2];
           auto load_rows = [&](auto ncc, auto fullc) {
             constexpr int NC = decltype(ncc)::value;  // columns per lane, compile time: every load is issued before any compare
             constexpr bool kFullRows = decltype(fullc)::value;
@@ -541,18 +548,25 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               const int ns = qon[g2] ? (int)rowbuf_all[i * p.row_stride + qjj[g2] + 1] : 0;  // idle quarters read row 0 and are ignored
               const QT* row = tab + (qa_toff[g2] + ns * qa_A[g2]);
               const int left = (qon[g2] ? qa_A[g2] : 0) - ql;  // columns at or beyond this lane's first one
+              qns[g2] = ns;
+              qleft[g2] = left;
 #pragma unroll
               for (int c = 0; c < NC; ++c)  // live table (:71): this lane's columns ql, ql+8, ...
                 v[g2][c] = ((kFullRows && c < NC - 1) || 8 * c < left) ? row[ql + 8 * c] : NegInf<QT>::v();
             }
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
+              int ci[NC];
 #pragma unroll
-              for (int st = 1; st < NC; st *= 2) {  // pairwise tree: depth log2 NC
+              for (int c = 0; c < NC; ++c) ci[c] = c;
 #pragma unroll
-                for (int c = 0; c + st < NC; c += 2 * st) v[g2][c] = v[g2][c + st] > v[g2][c] ? v[g2][c + st] : v[g2][c];
+              for (int st = 1; st < NC; st *= 2) {  // pairwise tree: depth log2 NC; the left operand (lower columns) wins ties
+#pragma unroll
+                for (int c = 0; c + st < NC; c += 2 * st)
+                  if (v[g2][c + st] > v[g2][c]) { v[g2][c] = v[g2][c + st]; ci[c] = ci[c + st]; }
               }
               qm[g2] = v[g2][0];
+              qidx[g2] = qleft[g2] > 0 ? ql + 8 * ci[0] : 0x7fffffff;
             }
           };
           if (p.qfull) {
@@ -569,10 +583,12 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
 #pragma unroll
           for (int g2 = 0; g2 < 2; ++g2) {
             QT m = qm[g2];
+            int am = qidx[g2];
 #pragma unroll
-            for (int off = 4; off >= 1; off >>= 1) {  // max over the quarter's 8 lanes
+            for (int off = 4; off >= 1; off >>= 1) {  // (max, first maximal column) over the quarter's 8 lanes
               const QT o = shfl_xor_t(m, off);
-              m = o > m ? o : m;
+              const int oi = __shfl_xor_sync(kFull, am, off);
+              if (oi != 0x7fffffff && (am == 0x7fffffff || o > m || (o == m && oi < am))) { m = o; am = oi; }
             }
             const int i = qa_ok[g2] ? 4 * g2 + qq : 0;
             const int jj = qjj[g2];
@@ -589,7 +605,25 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               tab[cell] = (QT)nv;
               if (cnt) atomicAdd(cnt + cell, 1u);  // :76, fire-and-forget RED
             }
-            if (qon[g2] && ql == 0 && st < qa_gcap[g2]) Gc[qa_goff[g2] + st] = 0xFF;  // greedy action recomputed on next visit
+            // (max, argmax) of a row after its cell k became x.  Unknown when the holder of the maximum went down.
+            auto patch = [](QT& rm, int& ra, bool& ok, int kk, QT x) {
+              if (kk != ra) {
+                if (x > rm || (x == rm && kk < ra)) { rm = x; ra = kk; }
+              } else if (x >= rm) {
+                rm = x;
+              } else {
+                ok = false;
+              }
+            };
+            const QT nvq = (QT)nv;
+            // row st as this write leaves it: from the pair carried over from the previous transition's bootstrap row
+            patch(cm[g2], ca[g2], cok[g2], k, nvq);
+            if (qon[g2] && ql == 0 && st < qa_gcap[g2]) Gc[qa_goff[g2] + st] = cok[g2] ? (uint8_t)ca[g2] : (uint8_t)0xFF;
+            // the row just read is the one the next transition writes; if it is also the row just written, apply that write
+            cm[g2] = m;
+            ca[g2] = am;
+            cok[g2] = qon[g2] && am != 0x7fffffff;
+            if (qns[g2] == st) patch(cm[g2], ca[g2], cok[g2], k, nvq);
           }
         } else {
           group(std::integral_constant<int, 0>{});

@@ -114,6 +114,8 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
   return __longlong_as_double(((long long)hi << 32) | (unsigned)lo);
 }
 
+__device__ __forceinline__ float shfl_t(float v, int src) { return __shfl_sync(kFull, v, src); }
+__device__ __forceinline__ double shfl_t(double v, int src) { return shfl_d(v, src); }
 __device__ __forceinline__ float shfl_xor_t(float v, int off) { return __shfl_xor_sync(kFull, v, off); }
 __device__ __forceinline__ double shfl_xor_t(double v, int off) {
   const long long b = __double_as_longlong(v);

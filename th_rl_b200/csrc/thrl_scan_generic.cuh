@@ -443,10 +443,12 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
         }
       }
       __syncwarp();
-      // Quarter path: (max, first argmax) of the row an agent's NEXT transition will write -- it is the row this transition
-      // reads for its bootstrap (s'_j = s_{j+1}) -- carried to the next iteration, where one more comparison against the
-      // value just written gives the row's new greedy action.  The greedy cache then survives the update instead of being
-      // invalidated, and the next episodes act from the cache without touching HBM.  cok = the carried pair is valid.
+      // Quarter path: the row a transition reads for its bootstrap is the row the agent's NEXT transition writes (s'_j =
+      // s_{j+1}), and the column that write will hit is known (the action ring).  The row scan therefore yields the
+      // (max, first argmax) over all OTHER columns plus the value of that column; the pair is carried to the next
+      // iteration, where one comparison against the value just written gives the row's greedy action after the write.
+      // The greedy cache survives the update instead of being invalidated by it, and later episodes act from the cache
+      // without touching HBM.  cok = the carried pair is valid.
       QT cm[2] = {NegInf<QT>::v(), NegInf<QT>::v()};
       int ca[2] = {0, 0};
       bool cok[2] = {false, false};
@@ -535,7 +537,8 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
           // ---- quarter-warp path: phase 1 loads + row max for up to 8 agents (two passes of four), phase 2 finishes + stores
           QT qm[2];
           bool qon[2];
-          int qjj[2], qidx[2], qns[2], qleft[2];
+          int qjj[2], qidx[2], qns[2], qleft[2], qknx[2];
+          QT qvk[2];
           auto load_rows = [&](auto ncc, auto fullc) {
             constexpr int NC = decltype(ncc)::value;  // columns per lane, compile time: every load is issued before any compare
             constexpr bool kFullRows = decltype(fullc)::value;
@@ -550,6 +553,11 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               const int left = (qon[g2] ? qa_A[g2] : 0) - ql;  // columns at or beyond this lane's first one
               qns[g2] = ns;
               qleft[g2] = left;
+              {  // column the agent's next transition writes in this row (-1: there is none)
+                int sn2 = des[i * 4 + 1] + qjj[g2] + 1;
+                if (sn2 >= Hp) sn2 -= Hp;
+                qknx[g2] = (qon[g2] && qjj[g2] + 1 < des[i * 4 + 0]) ? (int)act[i * Hp + sn2] : -1;
+              }
 #pragma unroll
               for (int c = 0; c < NC; ++c)  // live table (:71): this lane's columns ql, ql+8, ...
                 v[g2][c] = ((kFullRows && c < NC - 1) || 8 * c < left) ? row[ql + 8 * c] : NegInf<QT>::v();
@@ -557,8 +565,13 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
 #pragma unroll
             for (int g2 = 0; g2 < 2; ++g2) {
               int ci[NC];
+              const int cst = (qknx[g2] >= 0 && (qknx[g2] & 7) == ql) ? (qknx[g2] >> 3) : -1;  // this lane holds the excluded column
+              qvk[g2] = NegInf<QT>::v();
 #pragma unroll
-              for (int c = 0; c < NC; ++c) ci[c] = c;
+              for (int c = 0; c < NC; ++c) {
+                ci[c] = c;
+                if (c == cst) { qvk[g2] = v[g2][c]; v[g2][c] = NegInf<QT>::v(); }
+              }
 #pragma unroll
               for (int st = 1; st < NC; st *= 2) {  // pairwise tree: depth log2 NC; the left operand (lower columns) wins ties
 #pragma unroll
@@ -582,14 +595,16 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
           }
 #pragma unroll
           for (int g2 = 0; g2 < 2; ++g2) {
-            QT m = qm[g2];
+            QT mex = qm[g2];  // (max, first maximal column) over the quarter's 8 lanes, the next write's column excluded
             int am = qidx[g2];
 #pragma unroll
-            for (int off = 4; off >= 1; off >>= 1) {  // (max, first maximal column) over the quarter's 8 lanes
-              const QT o = shfl_xor_t(m, off);
+            for (int off = 4; off >= 1; off >>= 1) {
+              const QT o = shfl_xor_t(mex, off);
               const int oi = __shfl_xor_sync(kFull, am, off);
-              if (oi != 0x7fffffff && (am == 0x7fffffff || o > m || (o == m && oi < am))) { m = o; am = oi; }
+              if (oi != 0x7fffffff && (am == 0x7fffffff || o > mex || (o == mex && oi < am))) { mex = o; am = oi; }
             }
+            const QT vkq = shfl_t(qvk[g2], (lane & 24) | (qknx[g2] & 7));  // value of the excluded column (-inf: none)
+            const QT m = vkq > mex ? vkq : mex;                              // live row max (:71)
             const int i = qa_ok[g2] ? 4 * g2 + qq : 0;
             const int jj = qjj[g2];
             int sl = des[i * 4 + 1] + jj;
@@ -616,14 +631,17 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               }
             };
             const QT nvq = (QT)nv;
-            // row st as this write leaves it: from the pair carried over from the previous transition's bootstrap row
-            patch(cm[g2], ca[g2], cok[g2], k, nvq);
-            if (qon[g2] && ql == 0 && st < qa_gcap[g2]) Gc[qa_goff[g2] + st] = cok[g2] ? (uint8_t)ca[g2] : (uint8_t)0xFF;
-            // the row just read is the one the next transition writes; if it is also the row just written, apply that write
-            cm[g2] = m;
+            // row st as this write leaves it: the carried pair covers every column but k, the one written now
+            if (qon[g2] && ql == 0 && st < qa_gcap[g2]) {
+              const bool mine = nvq > cm[g2] || (nvq == cm[g2] && k < ca[g2]);
+              Gc[qa_goff[g2] + st] = cok[g2] ? (uint8_t)(mine ? k : ca[g2]) : (uint8_t)0xFF;
+            }
+            // the row just read is the one the next transition writes (its column excluded); if it is also the row written
+            // just now, apply that write to the pair -- unless it hit the excluded column itself
+            cm[g2] = mex;
             ca[g2] = am;
-            cok[g2] = qon[g2] && am != 0x7fffffff;
-            if (qns[g2] == st) patch(cm[g2], ca[g2], cok[g2], k, nvq);
+            cok[g2] = qon[g2] && qknx[g2] >= 0 && am != 0x7fffffff;
+            if (qns[g2] == st && k != qknx[g2]) patch(cm[g2], ca[g2], cok[g2], k, nvq);
           }
         } else {
           group(std::integral_constant<int, 0>{});

@@ -324,8 +324,9 @@ def run_ours(args):
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "traffic": None, "kernel": WL["kernel"], "kernel_ms": kern_ms,
                 "note": "tables (3.2 MB per run) stay in HBM; 824 algorithmic B per agent-step (BASELINE.md 5); peak = measured "
-                        "copy bandwidth from MEASURED_PEAKS.json (%s). ncu (profiles/): dram bytes per agent-step ~ 1.0 kB, "
-                        "long-scoreboard stalls dominate (latency-bound row gathers)" % peak_src}
+                        "copy bandwidth from MEASURED_PEAKS.json (%s). ncu (profiles/): ~0.87 kB of DRAM traffic and ~123 warp "
+                        "instructions per agent-step; the greedy-action cache is carried through the update, so rollouts stop waiting on "
+                        "HBM once it is warm; the update pass is a chain of L2 hits at 14 resident warps per SM" % peak_src}
         try:  # DRAM traffic per launch, measured once with ncu --set full on this exact command (profiles/)
             tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
             if tr and args.runs_per_gpu == WL["runs_per_gpu"]:  # per agent-step as captured x the agent-steps of this launch

@@ -259,3 +259,21 @@ def test_c_abi_error_paths_need_no_device():
         from th_rl_b200 import engine
         with pytest.raises(RuntimeError):
             engine.RunBatch(cfg, 4)
+
+
+def test_host_pipeline_chunk_bounds():
+    """engine.chunk_bounds (the launches scan_from_host cuts a batch into): every run exactly once, half-weight first and last
+    chunk, and whole multiples of the kernel's resident-run count once the chunks span several rounds of the persistent grid."""
+    from th_rl_b200.engine import chunk_bounds
+    for R, n, wave in ((131072, 12, 148 * 23), (16384, 8, 147 * 16), (4096, 2, 147 * 14), (1000, 7, 0), (5, 12, 3404), (1, 1, 0),
+                       (30000, 3, 3404), (100000, 12, 1)):
+        b = chunk_bounds(R, n, wave)
+        assert b[0] == 0 and b[-1] == R and all(x <= y for x, y in zip(b, b[1:])), (R, n, wave, b)
+        assert len(b) == min(n, R) + 1
+    b = chunk_bounds(131072, 12, 3404)  # 38.5 rounds: every inner boundary on a round boundary
+    assert all(x % 3404 == 0 for x in b[1:-1])
+    sizes = [y - x for x, y in zip(b, b[1:])]
+    assert sizes[0] <= max(sizes[1:-1]) // 2 + 3404 and max(sizes) <= 4 * 3404
+    b = chunk_bounds(16384, 8, 2352)    # 7 rounds for 8 chunks: plain weighted split, no alignment
+    assert [y - x for x, y in zip(b, b[1:])][1:-1] == [2340, 2341, 2340, 2341, 2340, 2341] or any(x % 2352 for x in b[1:-1])
+    assert chunk_bounds(4096, 2, 2058) == [0, 2048, 4096]

@@ -211,6 +211,26 @@ class HostState:
         return sum(t.numel() * t.element_size() for t in (self.q, self.counter, self.eps, self.price, self.mlp) if t is not None)
 
 
+def chunk_bounds(R, n_chunks, wave=0):
+    """Run-range boundaries of the launches scan_from_host cuts a batch of R runs into.
+
+    The first upload and the last download are the only copies no kernel hides: those two chunks get half the weight.  Once a
+    scan has told us how many runs one launch keeps resident (`wave`, thrl_last_wave_runs) and the chunks span several rounds
+    of the persistent grid, chunks are whole multiples of that, so no launch ends on a partly filled round."""
+    n_chunks = max(1, min(int(n_chunks), R))
+    w = [2] * n_chunks
+    if n_chunks >= 3:
+        w[0] = w[-1] = 1
+    unit = wave if wave and -(-R // wave) >= 2 * n_chunks else 1
+    units = -(-R // unit)
+    acc, tot, bounds = 0, sum(w), [0]
+    for x in w:
+        acc += x
+        bounds.append(min(R, (units * acc // tot) * unit))
+    bounds[-1] = R
+    return bounds
+
+
 def scan_from_host(batch, host, epochs, n_chunks=12):
     """Host-resident state -> `epochs` more epochs -> host-resident state, plus the cross-run statistics.
 
@@ -219,19 +239,7 @@ def scan_from_host(batch, host, epochs, n_chunks=12):
     """
     dev, R, E, n = batch.device, batch.n_runs, int(epochs), batch.game.n_agents
     n_chunks = max(1, min(int(n_chunks), R))
-    # The first upload and the last download are the only copies no kernel hides: those two chunks get half the weight.  Once a
-    # scan has told us how many runs one launch keeps resident (thrl_last_wave_runs), chunks are whole multiples of that, so
-    # no launch ends on a partly filled round of the persistent grid.
-    w = [2] * n_chunks
-    if n_chunks >= 3:
-        w[0] = w[-1] = 1
-    unit = batch.wave if batch.wave and -(-R // batch.wave) >= 2 * n_chunks else 1  # only when chunks span several rounds
-    units = -(-R // unit)
-    acc, tot, bounds = 0, sum(w), [0]
-    for x in w:
-        acc += x
-        bounds.append(min(R, (units * acc // tot) * unit))
-    bounds[-1] = R
+    bounds = chunk_bounds(R, n_chunks, batch.wave)
     with torch.cuda.device(dev):
         if not hasattr(batch, "_streams"):
             batch._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))

@@ -277,3 +277,42 @@ def test_host_pipeline_chunk_bounds():
     b = chunk_bounds(16384, 8, 2352)    # 7 rounds for 8 chunks: plain weighted split, no alignment
     assert [y - x for x, y in zip(b, b[1:])][1:-1] == [2340, 2341, 2340, 2341, 2340, 2341] or any(x % 2352 for x in b[1:-1])
     assert chunk_bounds(4096, 2, 2058) == [0, 2048, 4096]
+
+
+def test_greedy_cache_carry_rules_are_exact():
+    """The rule the general kernel uses to keep its greedy-action cache through the update pass (thrl_scan_generic.cuh,
+    DESIGN.md 4.2), restated on one row: from (max, first argmax) over all columns but k -- taken before the write, and
+    corrected by `patch` for an intervening write to another column -- the first argmax after `row[k] = x` is k when
+    x > max or (x == max and k < argmax), else the carried argmax.  Checked against numpy.argmax on random rows with ties."""
+    rng = np.random.default_rng(3)
+
+    def patch(rm, ra, ok, kk, x):  # (max, argmax, valid) of the tracked columns after column kk := x
+        if kk != ra:
+            if x > rm or (x == rm and kk < ra):
+                rm, ra = x, kk
+        elif x >= rm:
+            rm = x
+        else:
+            ok = False
+        return rm, ra, ok
+
+    unknown = 0
+    for _ in range(4000):
+        A = int(rng.integers(2, 12))
+        row = rng.integers(0, 4, A).astype(np.float32)  # few distinct values: many ties
+        k = int(rng.integers(A))                         # the column the next transition writes
+        others = [c for c in range(A) if c != k]
+        rm, ra, ok = float(max(row[others])), int(others[int(np.argmax(row[others]))]), True
+        if rng.random() < 0.5:                           # the transition in between writes the same row (state repeats)
+            k2, x2 = int(rng.integers(A)), np.float32(rng.integers(0, 4))
+            row[k2] = x2
+            if k2 != k:
+                rm, ra, ok = patch(rm, ra, ok, k2, float(x2))
+        x = np.float32(rng.integers(0, 4))
+        row[k] = x
+        if not ok:
+            unknown += 1
+            continue
+        got = k if (x > rm or (x == rm and k < ra)) else ra
+        assert got == int(np.argmax(row)), (row, k, x, rm, ra)
+    assert unknown < 1200  # only a lowered maximum under a repeated state loses the entry

@@ -140,7 +140,55 @@ CASES = {
                                     dict(name="ActorCritic", gamma=0.95, actions=5, states=1, action_range=[0.05, 0.2],
                                          min_memory=45)],
                             environment=_env(nplayers=3, max_steps=30), training=dict(epochs=12, print_freq=1000)), 17),
+    # BASELINE C5 at the bench's own shape (bench.py _c5_cfg): two ActorCritic agents with the constructor's min_memory = 1000
+    # (agents.py:223-234), i.e. N = 1000-transition batches every 10 episodes; 20 epochs = two updates per agent
+    "c5_aa_bench_seed18": (dict(agents=[dict(name="ActorCritic", gamma=0.98, actions=21, states=1, action_range=[0.2, 0.4]),
+                                        dict(name="ActorCritic", gamma=0.98, actions=21, states=1, action_range=[0.2, 0.4])],
+                                environment=_env(), training=dict(epochs=20, print_freq=1000)), 18),
 }
+
+EVAL_ITERS = 3  # episodes of utils.play_game recorded per case (noise-free cases only)
+
+
+def _stub_plotly():
+    """th_rl/utils.py imports plotly at module level (utils.py:7-9); plotly is not installed here and play_game /
+    load_experiment never touch it, so empty stand-in modules are enough to import the file unmodified."""
+    import types
+    for name in ("plotly", "plotly.graph_objects", "plotly.subplots", "plotly.express"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["plotly.subplots"].make_subplots = None
+    sys.modules["plotly"].graph_objects = sys.modules["plotly.graph_objects"]
+    sys.modules["plotly"].subplots = sys.modules["plotly.subplots"]
+    sys.modules["plotly"].express = sys.modules["plotly.express"]
+
+
+def record_play_game(out, cfg, seed):
+    """th_rl/utils.py:27-47 `play_game` (unmodified) on the agents train_one just saved, loaded back by
+    utils.load_experiment (utils.py:12-24; two-agent runs) or create_game + agent.load.  The initial price of every
+    episode (environment.reset, environments.py:50-53) is recorded so the rollout can be replayed."""
+    import torch
+    _stub_plotly()
+    import th_rl.utils as rutils
+    numpy.random.seed(seed + 7919)
+    torch.manual_seed(seed + 7919)
+    if len(cfg["agents"]) == 2:
+        _, agents, environment, _, _ = rutils.load_experiment(out)
+    else:
+        _, agents, environment = rutils.create_game(os.path.join(out, "config.json"))
+        for i, agent in enumerate(agents):
+            agent.load(os.path.join(out, str(i)))
+    p0s, orig = [], environment.reset
+
+    def reset():
+        s = orig()
+        p0s.append(float(s[0]))
+        return s
+
+    environment.reset = reset
+    acts, rwds = rutils.play_game(agents, environment, iters=EVAL_ITERS)
+    return numpy.array(p0s), numpy.asarray(acts, numpy.float64), numpy.asarray(rwds, numpy.float64)
+
 
 
 class _RandomProxy:
@@ -283,6 +331,12 @@ def record_case(cfg, seed):
             with open(os.path.join(out, "log.csv")) as f:
                 header = [f.readline().strip(), f.readline().strip()]
                 log = numpy.loadtxt(f, delimiter=",", ndmin=2)
+            ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce, rtrainer.ActorCritic, rtrainer.CAC = saved
+            # play_game: noise-free games without CAC agents.  (CAC.get_action builds Normal(mu, 0), agents.py:385-389, which
+            # torch's argument validation rejects -- the reference itself raises ValueError there, with the pinned torch 1.10 too.)
+            evalrec = None
+            if cfg["environment"].get("noise_prob", 0.05) == 0 and all(a["name"] != "CAC" for a in cfg["agents"]):
+                evalrec = record_play_game(out, cfg, seed)
     finally:
         ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce, rtrainer.ActorCritic, rtrainer.CAC = saved
 
@@ -307,6 +361,8 @@ def record_case(cfg, seed):
         log_header=numpy.array(header),
     )
     assert len(rec["p0"]) == 1
+    if evalrec is not None:  # utils.play_game on the trained agents: [iters] initial prices, [iters*T, n] scaled actions / rewards
+        g["eval_p0"], g["eval_actions"], g["eval_rewards"] = evalrec
     qi = mi = 0
     for i in range(n):
         if kinds[i] == "QTable":

@@ -15,6 +15,7 @@ GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "lattice_game: the test's game runs on the lattice kernel by default (kernel_choice fixture)")
 
 
 def golden_names():

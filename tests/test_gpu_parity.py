@@ -20,7 +20,7 @@ def kernel_choice(request, monkeypatch):
     monkeypatch.delenv("THRL_KERNEL", raising=False)
     monkeypatch.delenv("THRL_LPC_GL", raising=False)
     name = getattr(request.node, "callspec", None) and request.node.callspec.params.get("golden")
-    lattice = bool(name) and uses_lattice_kernel(load_golden(name)["config"])
+    lattice = (bool(name) and uses_lattice_kernel(load_golden(name)["config"])) or request.node.get_closest_marker("lattice_game") is not None
     if request.param == "mixed" and not lattice:
         pytest.skip("the order-exact MLP kernel is already the default here")
     if lattice and request.param in ("generic", "lpc", "lpc16"):
@@ -251,7 +251,9 @@ def _lattice_philox_case(cfg, R, E, seed, run_id0=0, chunks=None):
 
     o = run([E])
     same = (o["trace_actions"] == ref.trace_actions).reshape(R, -1).all(axis=1)
-    assert same.mean() >= 0.75, "too many runs left the oracle's trajectory: %d of %d agree" % (same.sum(), R)
+    # a run leaves the oracle's trajectory only when a `cdf > u` comparison falls within float32 rounding of a tie (~1e-7 per
+    # draw): over R runs x E epochs x T steps x n agents draws that is at most one run in a few dozen
+    assert same.sum() >= R - max(1, R // 24), "too many runs left the oracle's trajectory: %d of %d agree" % (same.sum(), R)
     for f in ("trace_prices", "trace_rewards", "rewards_log", "actions_log"):
         assert np.array_equal(o[f][same], getattr(ref, f)[same]), f
     assert np.array_equal(o["price"][same], ref.price[same])
@@ -358,6 +360,38 @@ def test_greedy_eval_matches_oracle(golden):
     a, r = b.greedy_eval(price0)
     torch.cuda.synchronize()
     assert np.array_equal(a.cpu().numpy(), ref_a) and np.array_equal(r.cpu().numpy(), ref_r)
+
+
+def test_greedy_eval_matches_play_game(golden):
+    """thrl_greedy_eval(_mlp) against th_rl/utils.py:27-47 `play_game` recorded from the unmodified reference on the agents
+    the golden run saved: scaled actions and rewards of every step, bit for bit (f64 tables, the reference's dtype)."""
+    from test_oracle_golden import final_state
+    torch, oracle, engine = _mods()
+    if "eval_p0" not in golden:
+        pytest.skip("no play_game record for this case (demand noise, or CAC whose get_action raises in the reference)")
+    cfg = golden["config"]
+    b = engine.RunBatch(cfg, 1, dtype=torch.float64)
+    q, mlp = final_state(golden, b.game)
+    b.load_state(q, [abi.eps0_from_config(cfg)], [golden["p0"]], mlp=mlp)
+    a, r = b.greedy_eval(golden["eval_p0"][None])
+    torch.cuda.synchronize()
+    assert np.array_equal(a[0].cpu().numpy(), golden["eval_actions"])
+    assert np.array_equal(r[0].cpu().numpy(), golden["eval_rewards"])
+
+
+@pytest.mark.lattice_game
+def test_c5_bench_shape_matches_oracle(kernel_choice):
+    """BASELINE C5 exactly as bench.py runs it (bench._c5_cfg: two ActorCritic agents, constructor min_memory = 1000, i.e.
+    N = 1000-transition batches every 10 episodes of T = 100): 21 epochs = two updates per agent.  Lattice kernel within the
+    stated float32 tolerance of the oracle, chunked == single call; THRL_KERNEL=mixed bit-equal to the oracle."""
+    import bench
+    cfg = bench._c5_cfg(21)
+    if kernel_choice == "auto":
+        _lattice_philox_case(cfg, 24, 21, seed=77, run_id0=3, chunks=[4, 9, 8])
+    elif kernel_choice == "mixed":
+        _philox_case(cfg, 12, 21, np.float32, seed=77, run_id0=3)
+    else:
+        pytest.skip("same dispatch as the default for this game")
 
 
 def test_sharding_is_invisible():

@@ -137,3 +137,27 @@ def test_quantity_sum_follows_the_interpreters_sum():
             naive += v
         differs += naive != want
     assert differs > 0  # the compensation is observable, so the test is not vacuous
+
+
+def final_state(g, game, dtype=np.float64):
+    """The agents train_one saved at the end of the golden run, packed for the oracle / the device."""
+    cfg, n = g["config"], game.n_agents
+    q = oracle.pack_tables(game, [None if is_mlp(cfg, i) else g["q_final_%d" % i] for i in range(n)], dtype)
+    mlp = None
+    if game.mlp_stride:
+        mlp = oracle.pack_mlp(game, [{k: g["mlp_final_%d_%s" % (i, k)] for k in abi.mlp_param_names(game.agent[i])}
+                                     if is_mlp(cfg, i) else None for i in range(n)])
+    return q, mlp
+
+
+def test_greedy_eval_matches_play_game(golden):
+    """oracle.greedy_eval against th_rl/utils.py:27-47 `play_game`, recorded from the unmodified reference on the agents the
+    golden run saved (oracle/make_goldens.py record_play_game): scaled actions and rewards of every step, bit for bit."""
+    if "eval_p0" not in golden:
+        pytest.skip("no play_game record: demand noise (the rollout would need the noise draws) or a CAC agent "
+                    "(the reference's CAC.get_action raises ValueError: Normal(mu, 0), agents.py:385-389)")
+    game = oracle.layout(golden["config"])
+    q, mlp = final_state(golden, game)
+    acts, rews = oracle.greedy_eval(game, q, golden["eval_p0"][None], mlp=mlp)
+    assert np.array_equal(acts[0], golden["eval_actions"])
+    assert np.array_equal(rews[0], golden["eval_rewards"])

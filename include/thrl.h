@@ -20,9 +20,14 @@
  *                           <- th_rl/agents.py:119-194 (Reinforce: pi / sample_action / scale / train_net + Adam)
  *
  * Conventions: plain C types only; every pointer in ThrlScanArgs is a DEVICE pointer owned by
- * the caller unless the entry point's name ends in `_host`; nothing is allocated or freed by the
- * library on the device-pointer path; calls are asynchronous on the caller's cudaStream_t (passed
- * as void*); the return value is 0 or a negative ThrlStatus, with a message in thrl_last_error().
+ * the caller unless the entry point's name ends in `_host`; calls are asynchronous on the caller's
+ * cudaStream_t (passed as void*); the return value is 0 or a negative ThrlStatus, with a message in
+ * thrl_last_error().  Device memory: the Q-table kernels allocate nothing.  Two paths use
+ * library-owned scratch, both stream-ordered and cached (steady-state calls allocate nothing): the
+ * lattice kernel for MLP agents takes its per-warp workspace from a per-device memory pool
+ * (cudaMallocFromPoolAsync on the caller's stream, release threshold = keep), and the `_host` entry
+ * point keeps a per-device staging arena (three chunk slots) between calls; thrl_release_device_memory()
+ * returns both to the driver.
  * The reference raises AssertionError/IndexError for bad configs (trainer.py:21-23, agents.py:88);
  * here those become THRL_ERR_BAD_CONFIG before anything is launched.
  */
@@ -35,7 +40,7 @@
 extern "C" {
 #endif
 
-#define THRL_ABI_VERSION 2
+#define THRL_ABI_VERSION 3
 #define THRL_MAX_AGENTS 16
 #define THRL_MAX_ACTIONS 255 /* greedy-action cache is one byte per table row, 0xFF = not cached */
 
@@ -85,6 +90,13 @@ typedef struct ThrlAgentSpec {
   double lr;          /* Adam learning rate (reference: 2e-4); betas (0.9, 0.999), eps 1e-8 */
   double entropy;     /* entropy coefficient (reference default 0; only 0 is supported) */
   int64_t mlp_offset; /* float offset of this agent's block inside one run's MLP slab; set by thrl_game_layout */
+  /* ABI 3: elements between the starts of consecutive table rows; set by thrl_game_layout.  Equal to `actions` while one run's
+   * tables are small enough to be staged in shared memory; games whose tables stay in HBM (sum_i (states_i+1)*actions_i*4 B >=
+   * THRL_PAD_THRESHOLD_BYTES) get rows padded to a multiple of 4 elements, table offsets and run_stride likewise, so that every
+   * row starts 16-byte aligned (fp32) and can be moved with one bulk copy / 16-byte vector loads.  Padding cells are never read
+   * as values and never written by the scan; thrl_game_init zeroes them. */
+  int32_t row_stride;
+  int32_t reserved_;
 } ThrlAgentSpec;
 
 /* Layout of one MLP agent's block inside the run's MLP slab (floats / 32-bit words), P = 2*hidden + actions*hidden + actions
@@ -97,6 +109,9 @@ typedef struct ThrlAgentSpec {
  *   [3P+4, ...)   transition buffer, `mlp_buffer_len` entries of 3 words: state (f32), action (int32), reward (f32);
  *                 ActorCritic and CAC entries have a 4th word: new_state (f32); CAC's action word is a float32 */
 #define THRL_MLP_HEADER_WORDS 4
+/* one run's fp32 tables at or above this size are left in HBM by every kernel (a quarter of the 227 KB of shared memory an
+ * sm_100 CTA can have: fewer than four runs would fit per SM); from here on the slab layout is padded (ThrlAgentSpec.row_stride) */
+#define THRL_PAD_THRESHOLD_BYTES 58112
 
 /* One game = n agents + NoisyPriceState kwargs (th_rl/environments.py:5-13). */
 typedef struct ThrlGame {
@@ -104,7 +119,7 @@ typedef struct ThrlGame {
   int32_t max_steps;
   double a, b, noise_prob;
   ThrlAgentSpec agent[THRL_MAX_AGENTS];
-  int64_t run_stride; /* elements per run slab = sum_i (states_i+1)*actions_i; set by thrl_game_layout */
+  int64_t run_stride; /* elements per run slab = sum_i (states_i+1)*row_stride_i (rounded up to 4 when padded); set by thrl_game_layout */
   int32_t ring_len;   /* transitions a run may hold across an epoch boundary; set by thrl_game_layout */
   int32_t regular;    /* 1 if every agent's buffer is empty at every epoch boundary (min_memory <= max_steps) */
   int64_t mlp_stride; /* ABI 2: 32-bit words per run in the MLP slab (0 when all agents are QTables); set by thrl_game_layout */
@@ -119,7 +134,8 @@ typedef struct ThrlGame {
 typedef struct ThrlScanArgs {
   const ThrlGame* game; /* HOST pointer */
   int64_t n_runs;       /* runs held by this call (this GPU's shard) */
-  int64_t run_id0;      /* global id of local run 0: Philox counters use global ids => results do not depend on the sharding */
+  int64_t run_id0;      /* global id of local run 0: Philox counters use global ids => results do not depend on the sharding.
+                           The id occupies one 32-bit counter word: run_id0 + n_runs <= 2^32 (THRL_ERR_BAD_ARGS beyond) */
   int32_t epoch_begin;  /* epochs [epoch_begin, epoch_end) are played; arrays below are indexed by e - epoch_begin */
   int32_t epoch_end;
   int32_t table_dtype; /* ThrlDtype */
@@ -127,13 +143,14 @@ typedef struct ThrlScanArgs {
   uint64_t seed;
 
   /* per-run state, read and written in place */
-  void* q;           /* [R][run_stride] f32 or f64; agent i's table at table_offset_i, row-major [states_i+1][actions_i] */
+  void* q;           /* [R][run_stride] f32 or f64; agent i's table at table_offset_i, row-major [states_i+1][row_stride_i],
+                        columns 0..actions_i-1 of every row used; 16-byte aligned */
   uint32_t* counter; /* [R][run_stride] visit counts (agents.py:45,76); may be NULL */
   double* eps;       /* [R][n] current epsilon */
   double* price;     /* [R] current state = last price (environments.py:36) */
   const double* hp;  /* NULL or [R][n][4] = alpha, gamma, eps_end, eps_step per run (hyper-parameter sweeps) */
-  void* ring;        /* NULL or [R][thrl_ring_bytes(game)] opaque transition buffer carried between calls;
-                        required when game->regular == 0 */
+  void* ring;        /* [R][thrl_ring_bytes(game)] opaque transition buffer carried between calls (zero-filled = empty buffers);
+                        REQUIRED when game->regular == 0 (THRL_ERR_BAD_ARGS otherwise), ignored (may be NULL) for regular games */
 
   /* replay streams (rng_mode != PHILOX); [R][E][T][n] / [R][E][T] */
   const double* replay_u;     /* recorded random.uniform(0,1) (agents.py:81); REPLAY_DRAWS only */
@@ -163,8 +180,14 @@ int64_t thrl_ring_bytes(const ThrlGame* game);
 
 /* Device entry points. `stream` is a cudaStream_t. */
 int thrl_qtable_scan(const ThrlScanArgs* args, void* stream);
-/* Same arguments but every pointer in *args is a HOST pointer; copies in, scans, copies back, synchronises. */
+/* Same arguments but every pointer in *args is a HOST pointer.  The run range is cut into chunks (whole multiples of the
+ * kernel's resident-run count); chunk c+1's host->device copies and chunk c-1's device->host copies run on their own streams
+ * while chunk c is in the kernel; three chunk slots of device memory are kept in a per-device arena between calls.  Copies
+ * overlap the kernel when the host buffers are page-locked (cudaHostRegister / pinned allocations); pageable buffers work,
+ * serialised by the driver.  Returns after everything has been copied back. */
 int thrl_qtable_scan_host(const ThrlScanArgs* args, int device);
+/* Frees the library-owned device scratch of the current device (lattice-kernel pool, `_host` staging arena). */
+int thrl_release_device_memory(void);
 /* Fills q (12.5/(1-gamma_i) + N(0,1)), counter (0), eps (eps0[i]), price (U(0,a)) for runs of this shard from
  * Philox(seed, global run id); eps0 is a HOST array of n doubles. */
 int thrl_qtable_init(const ThrlGame* game, int64_t n_runs, int64_t run_id0, uint64_t seed, int32_t table_dtype,

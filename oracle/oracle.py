@@ -68,19 +68,8 @@ def layout(config):
 
 def pack_tables(game, per_agent, dtype):
     """per_agent: list over agents of arrays [R, states+1, actions] (or [states+1, actions]; None for MLP agents)
-    -> slab [R, run_stride]."""
-    n = game.n_agents
-    arrs = [None if a is None else np.asarray(a, dtype=np.float64) for a in per_agent]
-    arrs = [a if a is None else (a[None] if a.ndim == 2 else a) for a in arrs]
-    R = next((a.shape[0] for a in arrs if a is not None), 1)  # a game may have no Q-tables at all
-    out = np.zeros((R, game.run_stride), dtype=dtype)
-    for i in range(n):
-        s = game.agent[i]
-        if s.kind != abi.THRL_AGENT_QTABLE:
-            continue
-        cells = (s.states + 1) * s.actions
-        out[:, s.table_offset:s.table_offset + cells] = arrs[i].reshape(R, cells).astype(dtype)
-    return out
+    -> slab [R, run_stride] (include/thrl.h layout; padding cells zero)."""
+    return abi.pack_tables(game, [None if a is None else np.asarray(a, dtype=np.float64) for a in per_agent], dtype)
 
 
 def pack_mlp(game, per_agent, R=1):
@@ -117,15 +106,8 @@ def unpack_mlp(game, slab, run=0):
 
 
 def unpack_tables(game, slab):
-    out = []
-    for i in range(game.n_agents):
-        s = game.agent[i]
-        if s.kind != abi.THRL_AGENT_QTABLE:
-            out.append(None)
-            continue
-        cells = (s.states + 1) * s.actions
-        out.append(slab[:, s.table_offset:s.table_offset + cells].reshape(-1, s.states + 1, s.actions))
-    return out
+    return [abi.table_view(slab, game.agent[i]) if game.agent[i].kind == abi.THRL_AGENT_QTABLE else None
+            for i in range(game.n_agents)]
 
 
 class ScanResult:

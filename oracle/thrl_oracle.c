@@ -101,13 +101,14 @@ typedef struct Table {
   int dtype;
   void* base; /* this agent's table of this run */
   int rows, cols;
+  int stride; /* elements between rows (ThrlAgentSpec.row_stride) */
 } Table;
 static double tget(const Table* t, int64_t row, int64_t col) {
-  int64_t i = row * t->cols + col;
+  int64_t i = row * t->stride + col;
   return t->dtype == THRL_F64 ? ((const double*)t->base)[i] : (double)((const float*)t->base)[i];
 }
 static void tset(Table* t, int64_t row, int64_t col, double v) {
-  int64_t i = row * t->cols + col;
+  int64_t i = row * t->stride + col;
   if (t->dtype == THRL_F64) ((double*)t->base)[i] = v;
   else ((float*)t->base)[i] = (float)v; /* fp32 storage: one rounding, to nearest even */
 }
@@ -607,6 +608,7 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
     tab[i].base = (char*)A->q + ((size_t)r * G->run_stride + s->table_offset) * esz;
     tab[i].rows = s->states + 1;
     tab[i].cols = s->actions;
+    tab[i].stride = s->row_stride;
     buf[i].cap = s->capacity;
     buf[i].len = buf[i].head = 0;
     buf[i].item = (Transition*)malloc(sizeof(Transition) * (size_t)(s->capacity > 0 ? s->capacity : 1));
@@ -797,7 +799,7 @@ static int scan_run(const ThrlScanArgs* A, int64_t r) {
           double next_max = row_max(&tab[i], ns_row[j]);
           double new_value = (1.0 - alpha[i]) * old_value[j] + alpha[i] * (tr->reward + gamma[i] * next_max);
           tset(&tab[i], st_row[j], tr->action, new_value);
-          if (cnt) cnt[st_row[j] * s->actions + tr->action] += 1;
+          if (cnt) cnt[st_row[j] * s->row_stride + tr->action] += 1;
         }
         b->len = 0; b->head = 0; /* :77 */
       }
@@ -918,7 +920,8 @@ int thrl_oracle_game_init(const ThrlGame* G, int64_t n_runs, int64_t run_id0, ui
           uint64_t m = ((uint64_t)x[2 * h] << 21) | (x[2 * h + 1] >> 11);
           double p = ((double)m + 0.5) * (1.0 / 9007199254740992.0);
           double v = base + det_norminv(p);
-          size_t idx = (size_t)r * G->run_stride + s->table_offset + (size_t)(c + h);
+          /* the draw of a cell depends on its logical index row * actions + col only, not on the row padding */
+          size_t idx = (size_t)r * G->run_stride + s->table_offset + (size_t)((c + h) / s->actions) * s->row_stride + (size_t)((c + h) % s->actions);
           if (table_dtype == THRL_F64) ((double*)q)[idx] = v;
           else ((float*)q)[idx] = (float)v;
           if (counter) counter[idx] = 0;
@@ -952,7 +955,7 @@ int thrl_oracle_greedy_eval_mlp(const ThrlGame* G, int64_t n_runs, int32_t table
           const ThrlAgentSpec* s = &G->agent[i];
           if (s->kind == THRL_AGENT_QTABLE) {
             Table tb = {table_dtype, (char*)q + ((size_t)r * G->run_stride + s->table_offset) * esz, s->states + 1,
-                        s->actions};
+                        s->actions, s->row_stride};
             int64_t row = upd_row(price, s);
             if (row < 0 || row > s->states) return THRL_ERR_BAD_CONFIG;
             xs[i] = scale_action(row_argmax(&tb, row), s);
@@ -995,11 +998,17 @@ int thrl_oracle_greedy_eval(const ThrlGame* G, int64_t n_runs, int32_t table_dty
 /* Same checks / layout as thrl_game_layout in the product, restated so the oracle stands alone. */
 int thrl_oracle_game_layout(ThrlGame* G) {
   if (G->n_agents < 1 || G->n_agents > THRL_MAX_AGENTS || G->max_steps < 1) return THRL_ERR_BAD_CONFIG;
-  int64_t off = 0, moff = 0;
+  int64_t off = 0, moff = 0, cells = 0;
   int ring = 0, regular = 1;
+  for (int i = 0; i < G->n_agents; ++i)
+    if (G->agent[i].kind == THRL_AGENT_QTABLE && G->agent[i].states >= 1 && G->agent[i].actions >= 1)
+      cells += (int64_t)(G->agent[i].states + 1) * G->agent[i].actions;
+  const int padded = cells * 4 >= THRL_PAD_THRESHOLD_BYTES; /* include/thrl.h: HBM-resident tables have rows of 4k elements */
   for (int i = 0; i < G->n_agents; ++i) {
     ThrlAgentSpec* s = &G->agent[i];
     G->mlp_buffer_len[i] = 0;
+    s->row_stride = 0;
+    s->reserved_ = 0;
     if (s->actions < 2 || s->actions > THRL_MAX_ACTIONS || s->capacity < 0 || s->min_memory < 0) return THRL_ERR_BAD_CONFIG;
     const int T = G->max_steps, mm = s->min_memory > 0 ? s->min_memory : 1;
     int64_t need = (int64_t)T * ((mm + T - 1) / T);
@@ -1014,10 +1023,13 @@ int thrl_oracle_game_layout(ThrlGame* G) {
       continue;
     }
     if (s->kind != THRL_AGENT_QTABLE || s->states < 1) return THRL_ERR_BAD_CONFIG;
-    if (!(s->max_state > 0.0) || G->a > s->max_state) return THRL_ERR_BAD_CONFIG; /* row would exceed states: IndexError */
+    /* a row beyond `states` is an IndexError in the reference (agents.py:88); prices never exceed a (environments.py:28-32) */
+    if (!(s->max_state > 0.0) || !(G->a == G->a)) return THRL_ERR_BAD_CONFIG;
+    if (act_row(G->a, s) > s->states || upd_row(G->a, s) > s->states) return THRL_ERR_BAD_CONFIG;
     s->table_offset = off;
     s->mlp_offset = 0;
-    off += (int64_t)(s->states + 1) * s->actions;
+    s->row_stride = padded ? (s->actions + 3) / 4 * 4 : s->actions;
+    off += (int64_t)(s->states + 1) * s->row_stride;
     if (s->min_memory <= s->capacity) { /* otherwise the update never fires and the buffer content is irrelevant */
       if (need > ring) ring = (int)need;
       if (s->min_memory > T) regular = 0;

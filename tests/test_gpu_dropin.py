@@ -155,3 +155,31 @@ def test_cli_runs_the_shipped_example_config(tmp_path):
     r = CliRunner().invoke(main, ["--dir", str(cdir), "--runs", "1", "--mode", "reference"])
     assert r.exit_code == 0, r.output
     assert sorted(os.listdir(tmp_path / "runs" / "second" / "0")) == ["0.npy", "0_counter.npy", "1", "config.json", "log.csv"]
+
+
+def test_reference_mode_runs_have_independent_policy_samples(tmp_path, monkeypatch):
+    """train_one in reference mode takes the Philox key of the MLP agents' action samples from torch's generator: successive
+    runs get different keys (so their sampling noise is independent, like the reference's own runs), and reseeding torch
+    reproduces a run bit for bit."""
+    import torch
+    from th_rl_b200 import engine, trainer
+    cpath = tmp_path / "cfg.json"
+    cpath.write_text(json.dumps(_shipped_example_config(12)))
+    seeds, real = [], engine.RunBatch
+
+    def recording(*a, **kw):
+        seeds.append(kw.get("seed"))
+        return real(*a, **kw)
+
+    monkeypatch.setattr(engine, "RunBatch", recording)
+    logs = []
+    for k, seed in enumerate((5, None, 5)):
+        random.seed(5), np.random.seed(5)
+        if seed is not None:
+            torch.manual_seed(seed)  # (run 1: torch's generator simply continues)
+        out = tmp_path / ("run%d" % k)
+        trainer.train_one(str(out), str(cpath))
+        logs.append(np.loadtxt((out / "log.csv").read_text().splitlines()[2:], delimiter=",", ndmin=2))
+    assert seeds[0] != seeds[1] and seeds[0] == seeds[2] and seeds[0] not in (0, None)
+    assert not np.array_equal(logs[0][:, 3], logs[1][:, 3])  # the Reinforce agent's mean actions per epoch
+    assert np.array_equal(logs[0], logs[2])

@@ -50,6 +50,7 @@ def lib():
     L.thrl_greedy_eval_mlp.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.thrl_greedy_eval_mlp.restype = C.c_int
+    L.thrl_release_device_memory.restype = C.c_int
     L.thrl_launch_count.restype = C.c_int64
     L.thrl_last_kernel.restype = C.c_char_p
     L.thrl_last_wave_runs.restype = C.c_int64

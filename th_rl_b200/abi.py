@@ -6,7 +6,7 @@ include/thrl.h, which in turn cites the reference lines each field comes from
 """
 import ctypes as C
 
-THRL_ABI_VERSION = 2
+THRL_ABI_VERSION = 3
 THRL_MAX_AGENTS = 16
 THRL_MAX_ACTIONS = 255
 THRL_STATS_K = 4
@@ -28,6 +28,7 @@ THRL_AGENT_REINFORCE = 1
 THRL_AGENT_ACTORCRITIC = 2
 THRL_AGENT_CAC = 3
 THRL_MLP_HEADER_WORDS = 4
+THRL_PAD_THRESHOLD_BYTES = 58112
 
 THRL_RNG_PHILOX = 0
 THRL_RNG_REPLAY_DRAWS = 1
@@ -53,6 +54,8 @@ class ThrlAgentSpec(C.Structure):
         ("lr", C.c_double),
         ("entropy", C.c_double),
         ("mlp_offset", C.c_int64),
+        ("row_stride", C.c_int32),
+        ("reserved_", C.c_int32),
     ]
 
 
@@ -201,3 +204,25 @@ def mlp_param_shapes(spec):
 
 def mlp_param_names(spec):
     return list(mlp_param_shapes(spec))
+
+
+# ---- slab layout helpers (include/thrl.h: agent i's table at table_offset_i, rows row_stride_i apart, `actions` columns used)
+def table_view(slab, spec):
+    """[R, run_stride] slab (numpy array or torch tensor) -> view [R, states+1, actions] of one QTable agent's table."""
+    rows = spec.states + 1
+    return slab[:, spec.table_offset:spec.table_offset + rows * spec.row_stride].reshape(-1, rows, spec.row_stride)[:, :, :spec.actions]
+
+
+def pack_tables(game, per_agent, dtype):
+    """per_agent: list over agents of arrays [R, states+1, actions] or [states+1, actions] (None for MLP agents) -> numpy slab
+    [R, run_stride] in the layout of include/thrl.h (padding cells zero)."""
+    import numpy as np
+    arrs = [None if a is None else np.asarray(a) for a in per_agent]
+    arrs = [a if a is None else (a[None] if a.ndim == 2 else a) for a in arrs]
+    R = next((a.shape[0] for a in arrs if a is not None), 1)  # a game may have no Q-tables at all
+    out = np.zeros((R, game.run_stride), dtype=dtype)
+    for i in range(game.n_agents):
+        s = game.agent[i]
+        if s.kind == THRL_AGENT_QTABLE:
+            table_view(out, s)[...] = arrs[i].astype(dtype)
+    return out

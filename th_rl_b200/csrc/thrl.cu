@@ -20,6 +20,7 @@
 
 #include "thrl_device.cuh"
 #include "thrl_scan_generic.cuh"
+#include "thrl_scan_hbm.cuh"
 #include "thrl_scan_lut2.cuh"
 #include "thrl_scan_lpc.cuh"
 #include "thrl_scan_mixed.cuh"
@@ -61,6 +62,10 @@ int device_info(DeviceInfo* d) {
   return THRL_OK;
 }
 
+double h_scale(int k, int actions, double lo, double hi);
+int h_act_row(double price, double max_state, int states);
+int h_upd_row(double price, double max_state, int states);
+
 int validate_layout(ThrlGame* G) {
   if (!G) return fail(THRL_ERR_BAD_ARGS, "game is NULL");
   if (G->n_agents < 1 || G->n_agents > THRL_MAX_AGENTS)
@@ -69,9 +74,17 @@ int validate_layout(ThrlGame* G) {
   if (!(G->b == G->b) || G->b == 0.0) return fail(THRL_ERR_BAD_CONFIG, "b must be non-zero");
   long long off = 0, moff = 0;
   int ring = 0, regular = 1;
+  // tables that stay in HBM are padded: rows, table offsets and the run stride are multiples of 4 elements (include/thrl.h)
+  long long cells = 0;
+  for (int i = 0; i < G->n_agents; ++i)
+    if (G->agent[i].kind == THRL_AGENT_QTABLE && G->agent[i].states >= 1 && G->agent[i].actions >= 1)
+      cells += (long long)(G->agent[i].states + 1) * G->agent[i].actions;
+  const bool padded = cells * 4 >= THRL_PAD_THRESHOLD_BYTES;
   for (int i = 0; i < G->n_agents; ++i) {
     ThrlAgentSpec* s = &G->agent[i];
     G->mlp_buffer_len[i] = 0;
+    s->row_stride = 0;
+    s->reserved_ = 0;
     if (s->actions < 2 || s->actions > THRL_MAX_ACTIONS)
       return fail(THRL_ERR_BAD_CONFIG, "agent %d: actions=%d outside 2..%d", i, s->actions, THRL_MAX_ACTIONS);
     if (s->capacity < 0 || s->min_memory < 0) return fail(THRL_ERR_BAD_CONFIG, "agent %d: negative capacity/min_memory", i);
@@ -93,13 +106,18 @@ int validate_layout(ThrlGame* G) {
     }
     if (s->kind != THRL_AGENT_QTABLE) return fail(THRL_ERR_BAD_CONFIG, "agent %d: unknown kind %d", i, s->kind);
     if (s->states < 1 || s->states > 65534) return fail(THRL_ERR_BAD_CONFIG, "agent %d: states=%d outside 1..65534", i, s->states);
-    // the reference raises IndexError on the first encode whose row exceeds `states` (agents.py:88): price <= a
-    if (!(s->max_state > 0.0) || G->a > s->max_state)
-      return fail(THRL_ERR_BAD_CONFIG, "agent %d: a=%g > max_state=%g would index past the table (reference: IndexError)", i,
-                  G->a, s->max_state);
+    // the reference raises IndexError on the first encode whose row exceeds `states` (agents.py:88).  Prices never exceed a
+    // (environments.py:28-32: new_a <= a), so the largest reachable row is the encode of a itself -- by either encode, the
+    // float32 one of sample_action or the float64 one of train_net; a slightly above max_state may still round into the table
+    if (!(s->max_state > 0.0) || !(G->a == G->a))
+      return fail(THRL_ERR_BAD_CONFIG, "agent %d: max_state=%g", i, s->max_state);
+    if (h_act_row(G->a, s->max_state, s->states) > s->states || h_upd_row(G->a, s->max_state, s->states) > s->states)
+      return fail(THRL_ERR_BAD_CONFIG, "agent %d: a=%g with max_state=%g encodes to a row past the table's %d (reference: IndexError)", i,
+                  G->a, s->max_state, s->states);
     s->table_offset = off;
     s->mlp_offset = 0;
-    off += (long long)(s->states + 1) * s->actions;
+    s->row_stride = padded ? align_up(s->actions, 4) : s->actions;
+    off += (long long)(s->states + 1) * s->row_stride;
     if (s->min_memory <= s->capacity) {
       if (need > ring) ring = (int)need;
       if (s->min_memory > T) regular = 0;
@@ -204,6 +222,128 @@ int launch_generic(thrl::ScanParams& p, const DeviceInfo& dev, cudaStream_t stre
   auto kern = smem_tables ? thrl::qtable_scan_generic<T, true> : thrl::qtable_scan_generic<T, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_last_kernel = "generic";
+  g_last_wave = (long long)grid * warps;
+  kern<<<grid, warps * 32, smem, stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return THRL_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ HBM-resident tables
+// Fills p (per-agent constants + shared-memory layout) when thrl_scan_hbm.cuh plays the game; *warps = runs resident per CTA.
+bool plan_hbm(thrl::HbmParams* p, size_t elem, const DeviceInfo& dev, int* warps) {
+  const ThrlGame& G = p->game;
+  const int n = G.n_agents, T = G.max_steps, esz = (int)elem;
+  if (G.mlp_stride > 0 || !G.regular || T > thrl::kHbmMaxT || G.run_stride % 4) return false;
+  if (G.run_stride * (long long)elem < THRL_PAD_THRESHOLD_BYTES) return false;  // small tables are staged in shared memory
+  int lut = 0, rows = 0, slot = 0;
+  double lo_sum = 0.0;
+  bool bounded = G.a >= 0.0 && G.b > 0.0;
+  for (int i = 0; i < n; ++i) {
+    const ThrlAgentSpec& s = G.agent[i];
+    if (s.kind != THRL_AGENT_QTABLE || s.row_stride % 4 || s.table_offset % 4 || s.actions > 128) return false;
+    const double lo = s.action_lo < s.action_hi ? s.action_lo : s.action_hi;
+    if (!(lo >= 0.0)) bounded = false;
+    lo_sum += lo;
+  }
+  for (int i = 0; i < n; ++i) {
+    const ThrlAgentSpec& s = G.agent[i];
+    // rows the price can reach: price <= a - a * sum_i min(action_range_i) (environments.py:25-32 with new_a <= a), +2 rows
+    // of slack for rounding; the call's initial price may lie above and is handled uncached
+    int cap = s.states + 1;
+    if (bounded) {
+      double pmax = G.a - G.a * lo_sum;
+      if (pmax < 0.0) pmax = 0.0;
+      const double rmax = pmax / s.max_state * (double)s.states + 2.5;
+      if (rmax < (double)cap) cap = (int)rmax;
+    }
+    p->gcap[i] = cap;
+    p->goff[i] = rows;
+    p->loff[i] = lut;
+    p->L[i] = s.min_memory > s.capacity ? 0 : (T < s.capacity ? T : s.capacity);
+    rows += cap;
+    lut += s.actions;
+    if (s.row_stride * esz > slot) slot = s.row_stride * esz;
+  }
+  p->lut_total = lut;
+  p->rows_total = rows;
+  p->slot_bytes = slot;
+  p->Tp = align_up(T, 4);
+  p->Sp = align_up(T + 1, 4);
+  p->cta_bytes = align_up(2 * lut * 8 + n * 8 * 4, 128);
+  const int Tp = p->Tp, Sp = p->Sp;
+  auto layout = [&](int nb) {
+    int o = 0;
+    p->off_bar = o;   o += thrl::kHbmMaxNb * 8;
+    p->off_g = o;     o += align_up(rows, 16);
+    p->off_P = o;     o += align_up((T + 1) * 8, 16);
+    p->off_act = o;   o += align_up(n * Tp, 16);
+    p->off_hp = o;    o += align_up(n * 5 * 8, 16);
+    p->off_srow = o;  o += align_up(n * Sp * 2, 16);
+    p->off_cur = o;   o += align_up(n * Tp * esz, 16);
+    p->off_canon = o; o += align_up(n * Tp, 16);
+    p->off_bm = o;    o += align_up(n * Sp * esz, 16);
+    p->off_ba = o;    o += align_up(n * Sp, 16);
+    o = align_up(o, 128);
+    p->off_stage = o;
+    p->off_pre = o;
+    p->off_newa = o + align_up(T * n * 2, 16);
+    const int draws = align_up(T * n * 2, 16) + (p->noisy ? T * 8 : 0);
+    p->off_rs = o;
+    p->off_vkey = o + align_up(n * Sp, 16);
+    p->off_cmin = p->off_vkey + align_up(n * Sp * esz, 16);
+    const int merge = align_up(n * Sp, 16) + align_up(n * Sp * esz, 16) + n * Sp * 4;
+    const int ring = nb * n * slot;
+    o += std::max(ring, std::max(draws, merge));
+    p->nb = nb;
+    p->warp_bytes = align_up(o, 128);
+    return p->warp_bytes;
+  };
+  const int avail = dev.smem_optin - p->cta_bytes;
+  int nb = 3;
+  if (avail / layout(nb) < 1) nb = 2;
+  int w = avail / layout(nb);
+  if (w < 1) return false;
+  if (w > 16) w = 16;
+  {  // the rounds of the persistent grid are fixed by what fits; a deeper ring that still fits them costs nothing
+    const long long slots = (long long)dev.sms * w;
+    const long long rounds = (p->n_runs + slots - 1) / slots;
+    const long long per_round = (p->n_runs + rounds - 1) / rounds;
+    int wneed = (int)((per_round + dev.sms - 1) / dev.sms);
+    if (wneed < 1) wneed = 1;
+    const char* force = getenv("THRL_HBM_NB");
+    if (force && atoi(force) >= 1 && atoi(force) <= thrl::kHbmMaxNb) {
+      nb = atoi(force);
+      if (avail / layout(nb) < 1) return false;
+    } else {
+      while (nb < thrl::kHbmMaxNb && nb < T + 1 && (long long)layout(nb + 1) * wneed <= avail) ++nb;
+      layout(nb);
+    }
+    w = avail / p->warp_bytes;
+    if (w > 16) w = 16;
+  }
+  const char* g = getenv("THRL_HBM_GATHER");
+  p->bulk = (g && strcmp(g, "ldg") == 0) ? 0 : 1;
+  *warps = w;
+  return true;
+}
+
+template <typename QT>
+int launch_hbm(thrl::HbmParams& p, int warps, const DeviceInfo& dev, cudaStream_t stream) {
+  int grid = dev.sms;
+  {  // every warp plays whole runs one after another: spread the runs evenly over the rounds that are needed anyway
+    const long long slots = (long long)dev.sms * warps;
+    const long long rounds = (p.n_runs + slots - 1) / slots;
+    const long long per_round = (p.n_runs + rounds - 1) / rounds;
+    warps = (int)((per_round + dev.sms - 1) / dev.sms);
+    if (warps < 1) warps = 1;
+    grid = (int)((per_round + warps - 1) / warps);
+    if (grid > dev.sms) grid = dev.sms;
+  }
+  const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
+  auto kern = thrl::qtable_scan_hbm<QT>;
+  CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  g_last_kernel = "hbm";
   g_last_wave = (long long)grid * warps;
   kern<<<grid, warps * 32, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
@@ -578,7 +718,7 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, size_t elem, int smem_optin, int* 
   for (int i = 0; i < n; ++i) {
     p->off_tab[i] = o;
     if (G.agent[i].kind == THRL_AGENT_QTABLE) {
-      const long long bytes = (long long)(G.agent[i].states + 1) * G.agent[i].actions * (long long)elem;
+      const long long bytes = (long long)(G.agent[i].states + 1) * G.agent[i].row_stride * (long long)elem;
       if (bytes > smem_optin) return false;
       o += align_up((int)bytes, 16);
     }
@@ -604,6 +744,24 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, size_t elem, int smem_optin, int* 
   return true;
 }
 
+// The library's own stream-ordered pool for the lattice kernel's workspace (one per device).  It keeps what it has been given
+// instead of returning it to the driver at every synchronisation (release threshold), so steady-state calls allocate nothing.
+cudaMemPool_t pwl_pool(int device, bool create) {
+  static cudaMemPool_t pools[64] = {};
+  static std::mutex pool_mu;
+  std::lock_guard<std::mutex> lock(pool_mu);
+  if (!pools[device] && create) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    if (cudaMemPoolCreate(&pools[device], &props) != cudaSuccess) { pools[device] = nullptr; return nullptr; }
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  return pools[device];
+}
+
 int launch_pwl(thrl::PwlParams& p, int warps, bool f64, const DeviceInfo& dev, cudaStream_t stream) {
   int grid = dev.sms;
   {
@@ -616,27 +774,12 @@ int launch_pwl(thrl::PwlParams& p, int warps, bool f64, const DeviceInfo& dev, c
     if (grid > dev.sms) grid = dev.sms;
   }
   const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
-  // Stream-ordered scratch from the library's own pool (one per device).  The pool keeps what it has been given instead
-  // of returning it to the driver at every synchronisation (release threshold), so steady-state calls allocate nothing.
-  static cudaMemPool_t pools[64] = {};
-  static std::mutex pool_mu;
+  // stream-ordered scratch from the library's own pool
   int device = 0;
   CUDA_TRY(cudaGetDevice(&device));
-  cudaMemPool_t pool = nullptr;
-  {
-    std::lock_guard<std::mutex> lock(pool_mu);
-    if (device < 0 || device >= 64) return fail(THRL_ERR_BAD_ARGS, "device index %d", device);
-    if (!pools[device]) {
-      cudaMemPoolProps props = {};
-      props.allocType = cudaMemAllocationTypePinned;
-      props.location.type = cudaMemLocationTypeDevice;
-      props.location.id = device;
-      CUDA_TRY(cudaMemPoolCreate(&pools[device], &props));
-      unsigned long long keep = ~0ull;
-      CUDA_TRY(cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep));
-    }
-    pool = pools[device];
-  }
+  if (device < 0 || device >= 64) return fail(THRL_ERR_BAD_ARGS, "device index %d", device);
+  cudaMemPool_t pool = pwl_pool(device, true);
+  if (!pool) return fail(THRL_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
   void* ws = nullptr;
   CUDA_TRY(cudaMallocFromPoolAsync(&ws, (size_t)grid * warps * (size_t)p.ws_warp_bytes, pool, stream));
   p.ws = (unsigned char*)ws;
@@ -665,6 +808,36 @@ int launch_pwl(thrl::PwlParams& p, int warps, bool f64, const DeviceInfo& dev, c
   return THRL_OK;
 }
 
+// Plans (structure tables + shared-memory layouts) are functions of the laid-out game, the cell size and the noise flag only:
+// they are built once and copied per call (train_one's small chunks and the host pipeline launch the same game many times).
+template <typename P>
+struct PlanCache {
+  struct Entry { ThrlGame g; int elem, noisy, smem; bool ok; int warps; std::unique_ptr<P> plan; };
+  std::vector<Entry> entries;
+  std::mutex mu;
+  // Returns whether the kernel applies; on true *out holds the plan (pointers and run counts zero) and *warps its residency.
+  template <typename F>
+  bool get(const ThrlGame& G, int elem, int noisy, int smem, P* out, int* warps, F build) {
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& e : entries)
+      if (e.elem == elem && e.noisy == noisy && e.smem == smem && memcmp(&e.g, &G, sizeof(G)) == 0) {
+        if (e.ok) { *out = *e.plan; *warps = e.warps; }
+        return e.ok;
+      }
+    Entry e{G, elem, noisy, smem, false, 0, std::unique_ptr<P>(new P())};
+    memset(e.plan.get(), 0, sizeof(P));
+    e.plan->game = G;
+    e.ok = build(e.plan.get(), &e.warps);
+    if (e.ok) { *out = *e.plan; *warps = e.warps; }
+    const bool ok = e.ok;
+    if (entries.size() >= 16) entries.erase(entries.begin());
+    entries.push_back(std::move(e));
+    return ok;
+  }
+};
+PlanCache<thrl::Lut2Params> g_lut2_plans;
+PlanCache<thrl::PwlParams> g_pwl_plans;
+
 int check_args(const ThrlScanArgs* a) {
   if (!a || !a->game) return fail(THRL_ERR_BAD_ARGS, "args/game is NULL");
   if (a->n_runs < 0 || a->epoch_end < a->epoch_begin) return fail(THRL_ERR_BAD_ARGS, "negative run or epoch count");
@@ -677,6 +850,32 @@ int check_args(const ThrlScanArgs* a) {
   for (int i = 0; i < a->game->n_agents && i < THRL_MAX_AGENTS; ++i) has_mlp |= a->game->agent[i].kind != THRL_AGENT_QTABLE;
   if (has_mlp && !a->mlp) return fail(THRL_ERR_BAD_ARGS, "the game has MLP agents but args->mlp is NULL");
   if (a->n_log_runs < 0 || a->n_log_runs > a->n_runs) return fail(THRL_ERR_BAD_ARGS, "n_log_runs=%lld outside 0..n_runs", (long long)a->n_log_runs);
+  // Philox counters carry the global run id in one 32-bit word (thrl_device.cuh): ids beyond 2^32 would alias streams
+  if (a->run_id0 < 0 || a->run_id0 + a->n_runs > (1LL << 32))
+    return fail(THRL_ERR_BAD_ARGS, "global run ids [%lld, %lld) leave the 32-bit range of the Philox counter word", (long long)a->run_id0,
+                (long long)(a->run_id0 + a->n_runs));
+  return THRL_OK;
+}
+
+// Checks that need the laid-out game: the carried ring of non-regular games, and the range of the fixed-point statistics.
+int check_args_game(const ThrlScanArgs* a, const ThrlGame& G) {
+  if (!G.regular && !a->ring)
+    return fail(THRL_ERR_BAD_ARGS, "the game is not regular (an agent's min_memory exceeds max_steps, so transitions are pending at "
+                                   "epoch boundaries): args->ring is required (thrl_ring_bytes per run, zero-filled = empty buffers)");
+  if (a->stats) {
+    // sums over the call's runs of r * 2^32 and r^2 * 2^24 in int64 (accumulated across calls by the caller: leave 2 bits).
+    // |per-epoch mean reward| <= price * quantity <= a * (a/b) * max|action|, |mean action| <= max|action|.
+    double xmax = 0.0;
+    for (int i = 0; i < G.n_agents; ++i) {
+      const double m = std::fmax(std::fabs(G.agent[i].action_lo), std::fabs(G.agent[i].action_hi));
+      if (m > xmax) xmax = m;
+    }
+    const double rmax = std::fabs(G.a) * std::fabs(G.a / G.b) * xmax, big = std::fmax(rmax, xmax);
+    const double lim = 2305843009213693952.0;  // 2^61
+    if (!(big * THRL_STATS_SCALE_SUM * (double)a->n_runs < lim) || !(big * big * THRL_STATS_SCALE_SQ * (double)a->n_runs < lim))
+      return fail(THRL_ERR_UNSUPPORTED, "stats: %lld runs of rewards up to %g would overflow the fixed-point sums (THRL_STATS_SCALE_*); "
+                                        "split the call or pass stats = NULL", (long long)a->n_runs, rmax);
+  }
   return THRL_OK;
 }
 
@@ -707,6 +906,8 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
   rc = validate_layout(&p.game);
   if (rc) return rc;
   if (p.game.run_stride > 0 && !a->q) return fail(THRL_ERR_BAD_ARGS, "q must not be NULL (the game has Q-tables)");
+  rc = check_args_game(a, p.game);
+  if (rc) return rc;
   if (a->n_runs == 0 || a->epoch_end == a->epoch_begin) return THRL_OK;
   DeviceInfo dev;
   rc = device_info(&dev);
@@ -733,10 +934,11 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
     if (!(forced && strcmp(forced, "mixed") == 0)) {  // lattice kernel where it applies (thrl_scan_pwl.cuh)
       thrl::PwlParams* w = new thrl::PwlParams();
       std::unique_ptr<thrl::PwlParams> hold_w(w);
-      memset(w, 0, sizeof(*w));
-      w->game = p.game;
       int warps = 0;
-      if (plan_pwl(w, p.noisy != 0, a->table_dtype == THRL_F64 ? 8 : 4, dev.smem_optin, &warps)) {
+      const int elem = a->table_dtype == THRL_F64 ? 8 : 4;
+      if (g_pwl_plans.get(p.game, elem, p.noisy, dev.smem_optin, w, &warps, [&](thrl::PwlParams* q, int* wq) {
+            return plan_pwl(q, p.noisy != 0, (size_t)elem, dev.smem_optin, wq);
+          })) {
         w->n_runs = p.n_runs; w->run_id0 = p.run_id0; w->epoch_begin = p.epoch_begin; w->E = p.E; w->rng_mode = p.rng_mode;
         w->k0 = p.k0; w->k1 = p.k1;
         w->price = p.price; w->replay_ra = p.replay_ra; w->replay_u = p.replay_u;
@@ -766,9 +968,11 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
   if (!want_generic) {
     thrl::Lut2Params* l = new thrl::Lut2Params();
     std::unique_ptr<thrl::Lut2Params> hold(l);
-    l->game = p.game;
     int warps = 0;
-    if (plan_lut2(l, p.noisy != 0, a->table_dtype == THRL_F64 ? 8 : 4, dev.smem_optin, &warps)) {
+    const int elem = a->table_dtype == THRL_F64 ? 8 : 4;
+    if (g_lut2_plans.get(p.game, elem, p.noisy, dev.smem_optin, l, &warps, [&](thrl::Lut2Params* q, int* wq) {
+          return plan_lut2(q, p.noisy != 0, (size_t)elem, dev.smem_optin, wq);
+        })) {
       l->n_runs = p.n_runs; l->run_id0 = p.run_id0; l->epoch_begin = p.epoch_begin; l->E = p.E; l->rng_mode = p.rng_mode;
       l->k0 = p.k0; l->k1 = p.k1;
       l->q = p.q; l->counter = p.counter; l->eps = p.eps; l->price = p.price; l->hp = p.hp;
@@ -778,6 +982,24 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
       if (force && strcmp(force, "lpc") == 0)
         return a->table_dtype == THRL_F64 ? launch_lpc<double>(*l, dev, stream) : launch_lpc<float>(*l, dev, stream);
       return a->table_dtype == THRL_F64 ? launch_lut2<double>(*l, warps, dev, stream) : launch_lut2<float>(*l, warps, dev, stream);
+    }
+  }
+  if (!want_generic) {  // tables that stay in HBM: gather / on-chip walk kernel (thrl_scan_hbm.cuh)
+    thrl::HbmParams h;
+    memset(&h, 0, sizeof(h));
+    h.game = p.game;
+    h.n_runs = p.n_runs;
+    h.noisy = p.noisy;
+    int warps = 0;
+    if (plan_hbm(&h, a->table_dtype == THRL_F64 ? 8 : 4, dev, &warps)) {
+      h.run_id0 = p.run_id0; h.epoch_begin = p.epoch_begin; h.E = p.E; h.rng_mode = p.rng_mode;
+      h.k0 = p.k0; h.k1 = p.k1;
+      h.q = p.q; h.counter = p.counter; h.eps = p.eps; h.price = p.price; h.hp = p.hp;
+      h.replay_u = p.replay_u; h.replay_ra = p.replay_ra; h.replay_new_a = p.replay_new_a;
+      h.rewards_log = p.rewards_log; h.actions_log = p.actions_log; h.n_log_runs = p.n_log_runs; h.stats = p.stats;
+      h.trace_actions = p.trace_actions; h.trace_rewards = p.trace_rewards; h.trace_prices = p.trace_prices;
+      if (((uintptr_t)h.q & 15u) != 0) return fail(THRL_ERR_BAD_ARGS, "q must be 16-byte aligned (padded slab layout, include/thrl.h)");
+      return a->table_dtype == THRL_F64 ? launch_hbm<double>(h, warps, dev, stream) : launch_hbm<float>(h, warps, dev, stream);
     }
   }
   return a->table_dtype == THRL_F64 ? launch_generic<double>(p, dev, stream) : launch_generic<float>(p, dev, stream);
@@ -840,6 +1062,11 @@ int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dty
   if (rc) return rc;
   if (G.run_stride > 0 && !q) return fail(THRL_ERR_BAD_ARGS, "q must not be NULL (the game has Q-tables)");
   if (G.mlp_stride > 0 && !mlp) return fail(THRL_ERR_BAD_ARGS, "the game has MLP agents but mlp is NULL");
+  // utils.play_game steps the environment, which perturbs the demand intercept when noise_prob > 0 (environments.py:28-31);
+  // the rollout kernels evaluate the noise-free curve only, so a noisy game is refused instead of being played without noise
+  if (G.noise_prob > 0.0)
+    return fail(THRL_ERR_UNSUPPORTED, "thrl_greedy_eval: noise_prob=%g > 0 (only the noise-free demand curve is implemented; "
+                                      "evaluate with noise_prob = 0)", G.noise_prob);
   if (n_runs <= 0 || iters <= 0) return THRL_OK;
   DeviceInfo dev;
   rc = device_info(&dev);
@@ -890,28 +1117,91 @@ int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dty
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------ host-buffer call
+// thrl_qtable_scan_host: the run range goes through in chunks; chunk c+1's upload and chunk c-1's download run on their own
+// streams while chunk c is in the kernel.  Three chunk slots of device memory, the three streams and their events live in
+// a per-device arena that is kept between calls (grown when a call needs more), so steady-state calls allocate nothing.
 namespace {
-struct DevBuf {
-  void* d = nullptr;
-  ~DevBuf() { if (d) cudaFree(d); }
-  int up(const void* h, size_t bytes, cudaStream_t s) {
-    if (!h || bytes == 0) return THRL_OK;
-    CUDA_TRY(cudaMalloc(&d, bytes));
-    CUDA_TRY(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
-    return THRL_OK;
-  }
-  int zero(size_t bytes, cudaStream_t s) {
-    if (bytes == 0) return THRL_OK;
-    CUDA_TRY(cudaMalloc(&d, bytes));
-    CUDA_TRY(cudaMemsetAsync(d, 0, bytes, s));
-    return THRL_OK;
-  }
-  int down(void* h, size_t bytes, cudaStream_t s) {
-    if (!h || !d || bytes == 0) return THRL_OK;
-    CUDA_TRY(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
-    return THRL_OK;
-  }
+
+struct HostArena {
+  void* base = nullptr;
+  size_t bytes = 0;
+  cudaStream_t up = nullptr, run = nullptr, down = nullptr;
+  cudaEvent_t ev_up[3] = {}, ev_run[3] = {}, ev_down[3] = {};
+  bool ready = false;
+  std::mutex mu;  // one host call per device at a time
 };
+HostArena g_arena[64];
+
+// resident runs of the latest launch per game (memcmp of the laid-out ThrlGame + dtype): lets the next host call size its
+// chunks in whole rounds of the persistent grid from the first chunk on
+struct WaveEntry { ThrlGame g; int dtype; long long wave; };
+std::vector<WaveEntry> g_waves;
+std::mutex g_waves_mu;
+long long wave_lookup(const ThrlGame& G, int dtype) {
+  std::lock_guard<std::mutex> lock(g_waves_mu);
+  for (auto& e : g_waves) if (e.dtype == dtype && memcmp(&e.g, &G, sizeof(G)) == 0) return e.wave;
+  return 0;
+}
+void wave_store(const ThrlGame& G, int dtype, long long wave) {
+  std::lock_guard<std::mutex> lock(g_waves_mu);
+  for (auto& e : g_waves) if (e.dtype == dtype && memcmp(&e.g, &G, sizeof(G)) == 0) { e.wave = wave; return; }
+  if (g_waves.size() >= 32) g_waves.erase(g_waves.begin());
+  g_waves.push_back(WaveEntry{G, dtype, wave});
+}
+
+int arena_prepare(HostArena& A, size_t need) {
+  if (!A.ready) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&A.up, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&A.run, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&A.down, cudaStreamNonBlocking));
+    for (int k = 0; k < 3; ++k) {
+      CUDA_TRY(cudaEventCreateWithFlags(&A.ev_up[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&A.ev_run[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&A.ev_down[k], cudaEventDisableTiming));
+    }
+    A.ready = true;
+  }
+  if (need > A.bytes) {
+    if (A.base) CUDA_TRY(cudaFree(A.base));
+    A.base = nullptr;
+    A.bytes = 0;
+    const size_t want = need + need / 8;  // a little headroom: chunk sizes move by a wave between calls
+    if (cudaMalloc(&A.base, want) != cudaSuccess) {
+      (void)cudaGetLastError();
+      CUDA_TRY(cudaMalloc(&A.base, need));
+      A.bytes = need;
+    } else {
+      A.bytes = want;
+    }
+  }
+  return THRL_OK;
+}
+
+// Run-range boundaries of the chunks (same rule as th_rl_b200.engine.chunk_bounds): first and last chunk carry half the
+// weight (their upload / download is the only copy no kernel hides); whole multiples of `wave` once the batch spans at
+// least two rounds per chunk.
+std::vector<long long> chunk_bounds(long long R, int n_chunks, long long wave) {
+  if (n_chunks > R) n_chunks = (int)R;
+  if (n_chunks < 1) n_chunks = 1;
+  std::vector<int> w((size_t)n_chunks, 2);
+  if (n_chunks >= 3) w.front() = w.back() = 1;
+  long long tot = 0;
+  for (int x : w) tot += x;
+  const long long unit = (wave > 0 && (R + wave - 1) / wave >= 2LL * n_chunks) ? wave : 1;
+  const long long units = (R + unit - 1) / unit;
+  std::vector<long long> b{0};
+  long long acc = 0;
+  for (int x : w) {
+    acc += x;
+    long long v = units * acc / tot * unit;
+    if (v > R) v = R;
+    if (v < b.back()) v = b.back();
+    b.push_back(v);
+  }
+  b.back() = R;
+  return b;
+}
+
 }  // namespace
 
 extern "C" int thrl_qtable_scan_host(const ThrlScanArgs* a, int device) {
@@ -920,52 +1210,133 @@ extern "C" int thrl_qtable_scan_host(const ThrlScanArgs* a, int device) {
   ThrlGame G = *a->game;
   rc = validate_layout(&G);
   if (rc) return rc;
+  if (G.run_stride > 0 && !a->q) return fail(THRL_ERR_BAD_ARGS, "q must not be NULL (the game has Q-tables)");
+  rc = check_args_game(a, G);
+  if (rc) return rc;
+  if (device < 0 || device >= 64) return fail(THRL_ERR_BAD_ARGS, "device index %d", device);
   if (cudaSetDevice(device) != cudaSuccess) return fail(THRL_ERR_NO_DEVICE, "cudaSetDevice(%d) failed (there is no CPU fallback)", device);
-  cudaStream_t s;
-  CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  const size_t R = (size_t)a->n_runs, n = (size_t)G.n_agents, T = (size_t)G.max_steps;
-  const size_t E = (size_t)(a->epoch_end - a->epoch_begin);
+  const long long R = a->n_runs;
+  const size_t n = (size_t)G.n_agents, T = (size_t)G.max_steps, E = (size_t)(a->epoch_end - a->epoch_begin);
+  if (R == 0 || E == 0) return THRL_OK;
   const size_t esz = a->table_dtype == THRL_F64 ? 8 : 4;
-  const size_t qb = R * (size_t)G.run_stride * esz, cb = R * (size_t)G.run_stride * 4;
-  const size_t logb = (size_t)a->n_log_runs * E * n * 8, statb = E * n * THRL_STATS_K * 8;
-  const size_t rb = (size_t)ring_bytes(&G) * R;
-  DevBuf q, cnt, eps, price, hp, ring, ru, rra, rna, rl, al, st, ta, tr, tp, mlp;
-  const size_t mlpb = R * (size_t)G.mlp_stride * 4;
-  ThrlScanArgs d = *a;
-  d.game = &G;
-#define TRY(x) do { rc = (x); if (rc) { cudaStreamDestroy(s); return rc; } } while (0)
-  TRY(q.up(a->q, qb, s)); d.q = q.d;
-  TRY(cnt.up(a->counter, cb, s)); d.counter = (uint32_t*)cnt.d;
-  TRY(eps.up(a->eps, R * n * 8, s)); d.eps = (double*)eps.d;
-  TRY(price.up(a->price, R * 8, s)); d.price = (double*)price.d;
-  TRY(hp.up(a->hp, R * n * 32, s)); d.hp = (const double*)hp.d;
-  TRY(ring.up(a->ring, rb, s)); d.ring = ring.d;
-  TRY(mlp.up(a->mlp, mlpb, s)); d.mlp = (float*)mlp.d;
-  TRY(ru.up(a->replay_u, R * E * T * n * 8, s)); d.replay_u = (const double*)ru.d;
-  TRY(rra.up(a->replay_ra, R * E * T * n * 4, s)); d.replay_ra = (const int32_t*)rra.d;
-  TRY(rna.up(a->replay_new_a, R * E * T * 8, s)); d.replay_new_a = (const double*)rna.d;
-  if (a->rewards_log) { TRY(rl.zero(logb, s)); } d.rewards_log = (double*)rl.d;
-  if (a->actions_log) { TRY(al.zero(logb, s)); } d.actions_log = (double*)al.d;
-  if (a->stats) { TRY(st.up(a->stats, statb, s)); } d.stats = (int64_t*)st.d;
-  if (a->trace_actions) { TRY(ta.zero(R * E * T * n * 4, s)); } d.trace_actions = (int32_t*)ta.d;
-  if (a->trace_rewards) { TRY(tr.zero(R * E * T * n * 8, s)); } d.trace_rewards = (double*)tr.d;
-  if (a->trace_prices) { TRY(tp.zero(R * E * T * 8, s)); } d.trace_prices = (double*)tp.d;
-  TRY(thrl_qtable_scan(&d, s));
-  TRY(q.down(a->q, qb, s));
-  TRY(cnt.down(a->counter, cb, s));
-  TRY(eps.down(a->eps, R * n * 8, s));
-  TRY(price.down(a->price, R * 8, s));
-  TRY(ring.down(a->ring, rb, s));
-  TRY(mlp.down(a->mlp, mlpb, s));
-  TRY(rl.down(a->rewards_log, logb, s));
-  TRY(al.down(a->actions_log, logb, s));
-  TRY(st.down(a->stats, statb, s));
-  TRY(ta.down(a->trace_actions, R * E * T * n * 4, s));
-  TRY(tr.down(a->trace_rewards, R * E * T * n * 8, s));
-  TRY(tp.down(a->trace_prices, R * E * T * 8, s));
-#undef TRY
-  cudaError_t e = cudaStreamSynchronize(s);
-  cudaStreamDestroy(s);
-  if (e != cudaSuccess) return fail(THRL_ERR_CUDA, "scan failed: %s", cudaGetErrorString(e));
+
+  // per-run bytes of every buffer that travels with a chunk: {host pointer, bytes per run, upload, download}
+  struct Buf { const void* h; size_t per_run; bool in, out; size_t off; };
+  enum { Q, CNT, EPS, PRICE, HP, RING, MLP, RU, RRA, RNA, TA, TR, TP, NBUF };
+  Buf buf[NBUF] = {
+      {a->q, (size_t)G.run_stride * esz, true, true, 0},
+      {a->counter, (size_t)G.run_stride * 4, true, true, 0},
+      {a->eps, n * 8, true, true, 0},
+      {a->price, 8, true, true, 0},
+      {a->hp, n * 32, true, false, 0},
+      {G.regular ? nullptr : a->ring, (size_t)ring_bytes(&G), true, true, 0},
+      {a->mlp, (size_t)G.mlp_stride * 4, true, true, 0},
+      {a->replay_u, E * T * n * 8, true, false, 0},
+      {a->replay_ra, E * T * n * 4, true, false, 0},
+      {a->replay_new_a, E * T * 8, true, false, 0},
+      {a->trace_actions, E * T * n * 4, false, true, 0},
+      {a->trace_rewards, E * T * n * 8, false, true, 0},
+      {a->trace_prices, E * T * 8, false, true, 0},
+  };
+  size_t per_run = 0;
+  for (auto& b : buf) if (b.h) per_run += b.per_run;
+  const size_t log_per_run = E * n * 8;  // rewards_log / actions_log: only the first n_log_runs runs of the call have a row
+  const size_t statb = a->stats ? E * n * THRL_STATS_K * 8 : 0;
+
+  // chunking: small batches go through in one piece; otherwise 12 chunks (THRL_HOST_CHUNKS overrides)
+  int n_chunks = ((size_t)R * per_run < (size_t)(16u << 20)) ? 1 : 12;
+  if (const char* e = getenv("THRL_HOST_CHUNKS")) if (atoi(e) >= 1) n_chunks = atoi(e);
+  const std::vector<long long> bounds = chunk_bounds(R, n_chunks, wave_lookup(G, a->table_dtype));
+  n_chunks = (int)bounds.size() - 1;
+  long long cap = 0;
+  for (int c = 0; c < n_chunks; ++c) cap = std::max(cap, bounds[c + 1] - bounds[c]);
+
+  // slot layout for `cap` runs
+  size_t slot_bytes = 0;
+  for (auto& b : buf) {
+    if (!b.h) continue;
+    b.off = slot_bytes;
+    slot_bytes += ((size_t)cap * b.per_run + 255) / 256 * 256;
+  }
+  size_t off_rl = 0, off_al = 0;
+  if (a->rewards_log) { off_rl = slot_bytes; slot_bytes += ((size_t)std::min<long long>(cap, a->n_log_runs) * log_per_run + 255) / 256 * 256; }
+  if (a->actions_log) { off_al = slot_bytes; slot_bytes += ((size_t)std::min<long long>(cap, a->n_log_runs) * log_per_run + 255) / 256 * 256; }
+  const int n_slots = n_chunks < 3 ? n_chunks : 3;
+  const size_t stats_off = (size_t)n_slots * slot_bytes;
+
+  HostArena& A = g_arena[device];
+  std::lock_guard<std::mutex> lock(A.mu);
+  rc = arena_prepare(A, stats_off + statb + 256);
+  if (rc) return rc;
+  unsigned char* base = (unsigned char*)A.base;
+  long long* d_stats = a->stats ? (long long*)(base + stats_off) : nullptr;
+#define TRYQ(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cudaDeviceSynchronize(); return fail(THRL_ERR_CUDA, "%s: %s", #x, cudaGetErrorString(e_)); } } while (0)
+  if (a->stats) TRYQ(cudaMemcpyAsync(d_stats, a->stats, statb, cudaMemcpyHostToDevice, A.run));  // accumulated (+=) by every chunk
+  long long wave = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const long long b0 = bounds[c], b1 = bounds[c + 1], Rc = b1 - b0;
+    if (Rc <= 0) continue;
+    const int sl = c % 3;
+    unsigned char* S = base + (size_t)sl * slot_bytes;
+    if (c >= 3) TRYQ(cudaStreamWaitEvent(A.up, A.ev_down[sl], 0));  // the slot's previous chunk has left the device
+    for (auto& b : buf)
+      if (b.h && b.in)
+        TRYQ(cudaMemcpyAsync(S + b.off, (const unsigned char*)b.h + (size_t)b0 * b.per_run, (size_t)Rc * b.per_run, cudaMemcpyHostToDevice, A.up));
+    TRYQ(cudaEventRecord(A.ev_up[sl], A.up));
+    TRYQ(cudaStreamWaitEvent(A.run, A.ev_up[sl], 0));
+    if (c >= 3) TRYQ(cudaStreamWaitEvent(A.run, A.ev_down[sl], 0));  // outputs that are only written (traces, logs) share the slot too
+    ThrlScanArgs d = *a;
+    d.game = &G;
+    d.n_runs = Rc;
+    d.run_id0 = a->run_id0 + b0;
+    auto dp = [&](int k) -> void* { return buf[k].h ? (void*)(S + buf[k].off) : nullptr; };
+    d.q = dp(Q); d.counter = (uint32_t*)dp(CNT); d.eps = (double*)dp(EPS); d.price = (double*)dp(PRICE);
+    d.hp = (const double*)dp(HP); d.ring = dp(RING); d.mlp = (float*)dp(MLP);
+    d.replay_u = (const double*)dp(RU); d.replay_ra = (const int32_t*)dp(RRA); d.replay_new_a = (const double*)dp(RNA);
+    d.trace_actions = (int32_t*)dp(TA); d.trace_rewards = (double*)dp(TR); d.trace_prices = (double*)dp(TP);
+    const long long nlog = std::max<long long>(0, std::min<long long>(a->n_log_runs - b0, Rc));
+    d.n_log_runs = nlog;
+    d.rewards_log = (a->rewards_log && nlog) ? (double*)(S + off_rl) : nullptr;
+    d.actions_log = (a->actions_log && nlog) ? (double*)(S + off_al) : nullptr;
+    d.stats = (int64_t*)d_stats;
+    rc = thrl_qtable_scan(&d, A.run);
+    if (rc) { cudaDeviceSynchronize(); return rc; }
+    if (g_last_wave > wave) wave = g_last_wave;
+    TRYQ(cudaEventRecord(A.ev_run[sl], A.run));
+    TRYQ(cudaStreamWaitEvent(A.down, A.ev_run[sl], 0));
+    for (auto& b : buf)
+      if (b.h && b.out)
+        TRYQ(cudaMemcpyAsync((unsigned char*)b.h + (size_t)b0 * b.per_run, S + b.off, (size_t)Rc * b.per_run, cudaMemcpyDeviceToHost, A.down));
+    if (d.rewards_log) TRYQ(cudaMemcpyAsync((unsigned char*)a->rewards_log + (size_t)b0 * log_per_run, S + off_rl, (size_t)nlog * log_per_run, cudaMemcpyDeviceToHost, A.down));
+    if (d.actions_log) TRYQ(cudaMemcpyAsync((unsigned char*)a->actions_log + (size_t)b0 * log_per_run, S + off_al, (size_t)nlog * log_per_run, cudaMemcpyDeviceToHost, A.down));
+    TRYQ(cudaEventRecord(A.ev_down[sl], A.down));
+  }
+  if (a->stats) TRYQ(cudaMemcpyAsync(a->stats, d_stats, statb, cudaMemcpyDeviceToHost, A.run));
+  cudaError_t e1 = cudaStreamSynchronize(A.run), e2 = cudaStreamSynchronize(A.down), e3 = cudaStreamSynchronize(A.up);
+#undef TRYQ
+  if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+    return fail(THRL_ERR_CUDA, "scan failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+  if (wave > 0) wave_store(G, a->table_dtype, wave);
+  g_last_wave = wave;
+  return THRL_OK;
+}
+
+extern "C" int thrl_release_device_memory(void) {
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) return fail(THRL_ERR_NO_DEVICE, "no CUDA device");
+  HostArena& A = g_arena[device];
+  {
+    std::lock_guard<std::mutex> lock(A.mu);
+    if (A.base) {
+      CUDA_TRY(cudaDeviceSynchronize());
+      CUDA_TRY(cudaFree(A.base));
+      A.base = nullptr;
+      A.bytes = 0;
+    }
+  }
+  if (cudaMemPool_t pool = pwl_pool(device, false)) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemPoolTrimTo(pool, 0));
+  }
   return THRL_OK;
 }

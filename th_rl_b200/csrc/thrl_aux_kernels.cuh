@@ -99,11 +99,20 @@ __global__ void __launch_bounds__(256) qtable_init(const __grid_constant__ InitP
           const unsigned long long m = ((unsigned long long)x[2 * h] << 21) | (unsigned long long)(x[2 * h + 1] >> 11);
           const double u = ((double)m + 0.5) * (1.0 / 9007199254740992.0);
           const double v = base + det_norminv(u);
-          const long long idx = r * G.run_stride + s.table_offset + c;
+          // the draw of a cell depends on its logical index row * actions + col only, not on the row padding
+          const long long idx = r * G.run_stride + s.table_offset + (c / s.actions) * s.row_stride + (c % s.actions);
           if (p.f64) reinterpret_cast<double*>(p.q)[idx] = v;
           else reinterpret_cast<float*>(p.q)[idx] = (float)v;
           if (p.counter) p.counter[idx] = 0u;  // agents.py:45
         }
+      }
+      const int pad = s.row_stride - s.actions;  // padded layout (include/thrl.h): padding cells are zeroed once, here
+      for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < (long long)(s.states + 1) * pad;
+           c += (long long)gridDim.x * blockDim.x) {
+        const long long idx = r * G.run_stride + s.table_offset + (c / pad) * s.row_stride + s.actions + (c % pad);
+        if (p.f64) reinterpret_cast<double*>(p.q)[idx] = 0.0;
+        else reinterpret_cast<float*>(p.q)[idx] = 0.0f;
+        if (p.counter) p.counter[idx] = 0u;
       }
     }
     if (blockIdx.x == 0 && threadIdx.x < n) p.eps[r * n + threadIdx.x] = p.eps0[threadIdx.x];
@@ -143,7 +152,7 @@ __global__ void __launch_bounds__(256) greedy_eval(const __grid_constant__ EvalP
         for (int i = 0; i < n; ++i) {
           const ThrlAgentSpec& s = G.agent[i];
           const int row = upd_row(price, s.max_state, (double)s.states);
-          const int k = row_argmax(tab + s.table_offset + (size_t)row * s.actions, s.actions, lane);
+          const int k = row_argmax(tab + s.table_offset + (size_t)row * s.row_stride, s.actions, lane);
           const double x = scale_action(k, s.actions, s.action_lo, s.action_hi);
           const double aq = __dmul_rn(ab, x);
           Q = __dadd_rn(Q, aq);

@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
     // Quarter-warp mapping for the update (n <= 8, every agent <= 128 actions): lanes 8q..8q+7 serve agents q and 4+q; the
     // scalar work of four agents' update steps then runs SIMD across the quarters instead of once per agent on all 32 lanes.
     const int ql = lane & 7, qq = lane >> 3;
-    int qa_A[2], qa_toff[2], qa_loff[2], qa_goff[2], qa_gcap[2];
+    int qa_A[2], qa_RS[2], qa_toff[2], qa_loff[2], qa_goff[2], qa_gcap[2];
     double qa_alpha[2], qa_gamma[2], qa_oma[2];
     bool qa_ok[2];
 #pragma unroll
@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
       const int ii = qa_ok[g2] ? i : 0;
       const ThrlAgentSpec& s = G.agent[ii];
       qa_A[g2] = s.actions;
+      qa_RS[g2] = s.row_stride;
       qa_toff[g2] = (int)s.table_offset;
       qa_loff[g2] = 0; qa_goff[g2] = 0;
       for (int j2 = 0; j2 < ii; ++j2) { qa_loff[g2] += G.agent[j2].actions; qa_goff[g2] += p.gcap[j2]; }
@@ -249,7 +250,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               const bool mine = qa_ok[g2] && ((need >> i) & 1u);
               rr[g2] = __shfl_sync(kFull, arow, qa_ok[g2] ? i : 0);
               left[g2] = (mine ? qa_A[g2] : 0) - ql;
-              const QT* row = tab + (qa_toff[g2] + (mine ? rr[g2] : 0) * qa_A[g2]);
+              const QT* row = tab + (qa_toff[g2] + (mine ? rr[g2] : 0) * qa_RS[g2]);
 #pragma unroll
               for (int c = 0; c < NC; ++c)  // (rows of quarters that are not served are read too -- row 0, valid memory -- and ignored)
                 v[g2][c] = ((kFullRows && c < NC - 1) || 8 * c < left[g2]) ? row[ql + 8 * c] : NegInf<QT>::v();
@@ -321,7 +322,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
 #pragma unroll
               for (int a = 0; a < 4; ++a) {
                 const ThrlAgentSpec& s = G.agent[ia[a] >= 0 ? ia[a] : 0];
-                const QT* row = tab + ((int)s.table_offset + ra[a] * s.actions);
+                const QT* row = tab + ((int)s.table_offset + ra[a] * s.row_stride);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                   const int kk = lane + 32 * c;
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
                 bidx[a] = 0x7fffffff;
                 if (ia[a] >= 0) {
                   const ThrlAgentSpec& s = G.agent[ia[a]];
-                  const QT* row = tab + ((int)s.table_offset + ra[a] * s.actions);
+                  const QT* row = tab + ((int)s.table_offset + ra[a] * s.row_stride);
                   for (int kk = lane; kk < s.actions; kk += 32) {
                     const QT v = row[kk];
                     if (v > bval[a] || bidx[a] == 0x7fffffff) { bval[a] = v; bidx[a] = kk; }
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
       for (int i = 0; i < n; ++i) {  // encodes (:62,:66) and the stale snapshot (:67), lane-parallel
         if (!des[i * 4 + 2]) continue;
         const ThrlAgentSpec& s = G.agent[i];
-        const int L = des[i * 4 + 0], first = des[i * 4 + 1], A = s.actions;
+        const int L = des[i * 4 + 0], first = des[i * 4 + 1], A = s.actions, RS = s.row_stride;
         uint16_t* rowbuf = rowbuf_all + i * p.row_stride;
         QT* oldv = oldv_all + i * p.old_stride;
         const QT* tb = tab + s.table_offset;
@@ -419,7 +420,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
         }
         __syncwarp();
         if (!kSmemTables && lane < kPrefetchAhead && lane < L) {  // rows the first transitions of the pass will read: into L2 now
-          const QT* row = tb + (size_t)rowbuf[lane + 1] * A;
+          const QT* row = tb + (size_t)rowbuf[lane + 1] * RS;
           for (int b = 0; b < A * (int)sizeof(QT); b += 128)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(row) + b));
         }
@@ -430,7 +431,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
             const int j = lane + 32 * u;
             int sl = first + j;
             if (sl >= Hp) sl -= Hp;
-            v4[u] = j < L ? tb[(int)rowbuf[j] * A + act[i * Hp + sl]] : (QT)0;
+            v4[u] = j < L ? tb[(int)rowbuf[j] * RS + act[i * Hp + sl]] : (QT)0;
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
         for (int j = lane + 128; j < L; j += 32) {
           int sl = first + j;
           if (sl >= Hp) sl -= Hp;
-          oldv[j] = tb[(int)rowbuf[j] * A + act[i * Hp + sl]];
+          oldv[j] = tb[(int)rowbuf[j] * RS + act[i * Hp + sl]];
         }
       }
       __syncwarp();
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
           const int jp = j + kPrefetchAhead - des[lane * 4 + 3];
           if (jp >= 0 && jp < des[lane * 4 + 0]) {
             const ThrlAgentSpec& s = G.agent[lane];
-            const QT* row = tab + s.table_offset + (size_t)rowbuf_all[lane * p.row_stride + jp + 1] * s.actions;
+            const QT* row = tab + s.table_offset + (size_t)rowbuf_all[lane * p.row_stride + jp + 1] * s.row_stride;
             for (int b = 0; b < s.actions * (int)sizeof(QT); b += 128)
               asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(row) + b));
           }
@@ -483,7 +484,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               const ThrlAgentSpec& s = G.agent[on[a] ? i : 0];
               const int A = s.actions;
               const int ns = on[a] ? (int)rowbuf_all[i * p.row_stride + (j - des[i * 4 + 3]) + 1] : 0;
-              const QT* row = tab + ((int)s.table_offset + ns * A);
+              const QT* row = tab + ((int)s.table_offset + ns * s.row_stride);
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const int kk = lane + 32 * c;
@@ -503,7 +504,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               if (on[a]) {
                 const ThrlAgentSpec& s = G.agent[i];
                 const int ns = rowbuf_all[i * p.row_stride + (j - des[i * 4 + 3]) + 1];
-                const QT* row = tab + ((int)s.table_offset + ns * s.actions);
+                const QT* row = tab + ((int)s.table_offset + ns * s.row_stride);
                 for (int k = lane; k < s.actions; k += 32) { const QT v = row[k]; loc[a] = v > loc[a] ? v : loc[a]; }
               }
             }
@@ -526,7 +527,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
             const double nv = __dadd_rn(__dmul_rn(__dsub_rn(1.0, alpha), (double)oldv_all[i * p.old_stride + jj]),
                                         __dmul_rn(alpha, __dadd_rn(reward, __dmul_rn(gamma, next_max))));
             if ((k & 31) == lane) {  // the lane that owns column k: it alone ever reads or writes that column
-              const int cell = (int)s.table_offset + st * s.actions + k;  // a run's slab has < 2^31 elements (checked at layout)
+              const int cell = (int)s.table_offset + st * s.row_stride + k;  // a run's slab has < 2^31 elements (checked at layout)
               tab[cell] = (QT)nv;
               if (cnt) atomicAdd(cnt + cell, 1u);  // :76, fire-and-forget RED
             }
@@ -549,7 +550,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
               qon[g2] = qa_ok[g2] && des[i * 4 + 2] && j >= des[i * 4 + 3];
               qjj[g2] = qon[g2] ? j - des[i * 4 + 3] : 0;
               const int ns = qon[g2] ? (int)rowbuf_all[i * p.row_stride + qjj[g2] + 1] : 0;  // idle quarters read row 0 and are ignored
-              const QT* row = tab + (qa_toff[g2] + ns * qa_A[g2]);
+              const QT* row = tab + (qa_toff[g2] + ns * qa_RS[g2]);
               const int left = (qon[g2] ? qa_A[g2] : 0) - ql;  // columns at or beyond this lane's first one
               qns[g2] = ns;
               qleft[g2] = left;
@@ -616,7 +617,7 @@ __global__ void __launch_bounds__(kSmemTables ? 1024 : 512, 1) qtable_scan_gener
             const double nv = __dadd_rn(__dmul_rn(qa_oma[g2], (double)oldv_all[i * p.old_stride + jj]),
                                         __dmul_rn(qa_alpha[g2], __dadd_rn(reward, __dmul_rn(qa_gamma[g2], (double)m))));
             if (qon[g2] && (k & 7) == ql) {  // the lane of this quarter that owns column k: it alone reads or writes it
-              const int cell = qa_toff[g2] + st * qa_A[g2] + k;
+              const int cell = qa_toff[g2] + st * qa_RS[g2] + k;
               tab[cell] = (QT)nv;
               if (cnt) atomicAdd(cnt + cell, 1u);  // :76, fire-and-forget RED
             }

@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(32 * kLpcMaxWarps, 1) qtable_scan_lpc(const __
       for (int c = 0; c < NR + 2; ++c) {
         const int row = table_row(c);
         if (row < 0) continue;
-        const QT* src = qg + (size_t)row * A;
+        const QT* src = qg + (size_t)row * G.agent[ag].row_stride;
         QT best = src[0];
         int g = 0;
         tab[(c * A) * GL] = best;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(32 * kLpcMaxWarps, 1) qtable_scan_lpc(const __
             const int k = w & 0xff, cu = w >> 24;
             const int Ac = kA > 0 ? kA : (agc ? A1 : A0), NRc = agc ? NR1 : NR0;
             const int row = cu < NRc ? (int)rowlist[(agc ? NR0 : 0) + cu] : (int)xrow_sh[(cu - NRc) * GL + lc];
-            atomicAdd(p.counter + rc_run * G.run_stride + G.agent[agc].table_offset + (size_t)row * Ac + k, 1u);
+            atomicAdd(p.counter + rc_run * G.run_stride + G.agent[agc].table_offset + (size_t)row * G.agent[agc].row_stride + k, 1u);
           }
         }
       }
@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(32 * kLpcMaxWarps, 1) qtable_scan_lpc(const __
       for (int c = 0; c < NR + 2; ++c) {
         const int row = table_row(c);
         if (row < 0) continue;
-        QT* dst = qg + (size_t)row * A;
+        QT* dst = qg + (size_t)row * G.agent[ag].row_stride;
         for (int k = 0; k < A; ++k) dst[k] = tab[(c * A + k) * GL];
       }
       p.eps[r * 2 + ag] = eps;

@@ -201,11 +201,11 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
     // ---- stage compact rows (plus extra rows) into shared memory, build the caches
     for (int c = 0; c < NR0 + 2; ++c) {
       const int row = table_row0(c);
-      if (row >= 0) for (int k = lane; k < A0; k += 32) tab0[c * A0 + k] = qg0[(size_t)row * A0 + k];
+      if (row >= 0) for (int k = lane; k < A0; k += 32) tab0[c * A0 + k] = qg0[(size_t)row * G.agent[0].row_stride + k];
     }
     for (int c = 0; c < NR1 + 2; ++c) {
       const int row = table_row1(c);
-      if (row >= 0) for (int k = lane; k < A1; k += 32) tab1[c * A1 + k] = qg1[(size_t)row * A1 + k];
+      if (row >= 0) for (int k = lane; k < A1; k += 32) tab1[c * A1 + k] = qg1[(size_t)row * G.agent[1].row_stride + k];
     }
     for (int s = lane; s < NS; s += 32) rowsW[s] = p.state_rows[s];
     if (lane == 0) rowsW[NS] = (uint32_t)init_c0 | ((uint32_t)init_c1 << 8) | ((uint32_t)init_c2 << 16) | ((uint32_t)init_c3 << 24);
@@ -338,13 +338,13 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
       for (int j = T - L0 + lane; j < T; j += 32) {
         const int k = rec[j] & 0xff, cu = (rowsW[seq[j]] >> 8) & 0xff;
         olds[2 * (j - (T - L0))] = tab0[cu * A0 + k];
-        if (cnt0) atomicAdd(cnt0 + (size_t)table_row0(cu) * A0 + k, 1u);  // agents.py:76
+        if (cnt0) atomicAdd(cnt0 + (size_t)table_row0(cu) * G.agent[0].row_stride + k, 1u);  // agents.py:76
         if (cu < 32) dirty0a |= 1u << cu; else if (cu < 64) dirty0b |= 1u << (cu - 32); else dirty_all0 = true;
       }
       for (int j = T - L1 + lane; j < T; j += 32) {
         const int k = rec[j] >> 8, cu = rowsW[seq[j]] >> 24;
         olds[2 * (j - (T - L1)) + 1] = tab1[cu * A1 + k];
-        if (cnt1) atomicAdd(cnt1 + (size_t)table_row1(cu) * A1 + k, 1u);
+        if (cnt1) atomicAdd(cnt1 + (size_t)table_row1(cu) * G.agent[1].row_stride + k, 1u);
         if (cu < 32) dirty1a |= 1u << cu; else if (cu < 64) dirty1b |= 1u << (cu - 32); else dirty_all1 = true;
       }
       __syncwarp();
@@ -478,11 +478,11 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
     // ---- write the run back: only the staged rows can have changed
     for (int c = 0; c < NR0 + 2; ++c) {
       const int row = table_row0(c);
-      if (row >= 0) for (int k = lane; k < A0; k += 32) qg0[(size_t)row * A0 + k] = tab0[c * A0 + k];
+      if (row >= 0) for (int k = lane; k < A0; k += 32) qg0[(size_t)row * G.agent[0].row_stride + k] = tab0[c * A0 + k];
     }
     for (int c = 0; c < NR1 + 2; ++c) {
       const int row = table_row1(c);
-      if (row >= 0) for (int k = lane; k < A1; k += 32) qg1[(size_t)row * A1 + k] = tab1[c * A1 + k];
+      if (row >= 0) for (int k = lane; k < A1; k += 32) qg1[(size_t)row * G.agent[1].row_stride + k] = tab1[c * A1 + k];
     }
     if (lane == 0) {
       p.eps[r * 2] = eps0;

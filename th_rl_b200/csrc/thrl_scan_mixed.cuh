@@ -583,7 +583,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
           need &= need - 1;
           const int ri = __shfl_sync(kFull, arow, i);
           const ThrlAgentSpec& s = G.agent[i];
-          const int g = row_argmax(tab + s.table_offset + (size_t)ri * s.actions, s.actions, lane);
+          const int g = row_argmax(tab + s.table_offset + (size_t)ri * s.row_stride, s.actions, lane);
           if (lane == i) k = g;
         }
         // free-running MLP agents: forward pass + inverse-CDF sample (agents.py:160-163)
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
         for (int j = lane; j < L; j += 32) {  // stale snapshot (:67)
           int sl = first + j;
           if (sl >= Hp) sl -= Hp;
-          oldv[j] = tb[(size_t)rowbuf[j] * A + act[i * Hp + sl]];
+          oldv[j] = tb[(size_t)rowbuf[j] * s.row_stride + act[i * Hp + sl]];
         }
         __syncwarp();
         int sl = first;
@@ -717,12 +717,12 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_mixed(const __grid_constan
           int sn = sl + 1;
           if (sn == Hp) sn = 0;
           const double reward = __dmul_rn(P[sn], lutAQ[loff + k]);
-          const double next_max = (double)row_max(tb + (size_t)ns * A, A, lane);
+          const double next_max = (double)row_max(tb + (size_t)ns * s.row_stride, A, lane);
           const double nv = __dadd_rn(__dmul_rn(one_m_alpha, (double)oldv[j]),
                                       __dmul_rn(alpha, __dadd_rn(reward, __dmul_rn(gamma, next_max))));
           if ((k & 31) == lane) {  // the lane that owns column k
-            tb[(size_t)st * A + k] = (QT)nv;
-            if (cnt) atomicAdd(cnt + s.table_offset + (size_t)st * A + k, 1u);
+            tb[(size_t)st * s.row_stride + k] = (QT)nv;
+            if (cnt) atomicAdd(cnt + s.table_offset + (size_t)st * s.row_stride + k, 1u);
           }
           sl = sn;
         }
@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(256) greedy_eval_mixed(const __grid_constant__
           double x;
           if (s.kind == THRL_AGENT_QTABLE) {
             const int row = upd_row(price, s.max_state, (double)s.states);
-            const int k = row_argmax(tab + s.table_offset + (size_t)row * s.actions, s.actions, lane);
+            const int k = row_argmax(tab + s.table_offset + (size_t)row * s.row_stride, s.actions, lane);
             x = scale_action(k, s.actions, s.action_lo, s.action_hi);
           } else if (s.kind == THRL_AGENT_CAC) {
             const float* sp = par + p.par_off[i];

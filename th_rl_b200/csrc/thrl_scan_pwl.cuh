@@ -727,7 +727,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
       if (s.kind == THRL_AGENT_QTABLE) {  // stage the table; acting rows of all states; nothing known about greedy actions
-        const int qi = p.qidx[i], cells = (s.states + 1) * s.actions;
+        const int qi = p.qidx[i], cells = (s.states + 1) * s.row_stride;  // staged with its row padding, if any
         QT* tb = reinterpret_cast<QT*>(slot + p.off_tab[i]);
         const QT* src = tabg + s.table_offset;
         for (int c = lane; c < cells; c += 32) tb[c] = src[c];
@@ -800,7 +800,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
           const int qi = p.qidx[i];
           int g = gq[qi * NSX + x];
           if (g == 0xFF) {
-            g = row_argmax(reinterpret_cast<const QT*>(slot + p.off_tab[i]) + (size_t)arow[qi * NSX + x] * Ai, Ai, lane);
+            g = row_argmax(reinterpret_cast<const QT*>(slot + p.off_tab[i]) + (size_t)arow[qi * NSX + x] * G.agent[i].row_stride, Ai, lane);
             __syncwarp();
             if (lane == 0) gq[qi * NSX + x] = (uint8_t)g;
             __syncwarp();
@@ -902,19 +902,19 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
             const double alpha = hpw[i * 5 + 0], gamma = hpw[i * 5 + 1], one_m_alpha = __dsub_rn(1.0, alpha);
             for (int t = t0 + lane; t < T; t += 32) {  // stale snapshot (:67)
               const int st = t == 0 ? ucur : ur[jrec[t - 1]];
-              oldv[t] = tb[(size_t)st * A + (jrec[t] / jm) % A];
+              oldv[t] = tb[(size_t)st * s.row_stride + (jrec[t] / jm) % A];
             }
             __syncwarp();
             for (int t = t0; t < T; ++t) {  // the sequential pass (:68-76)
               const int jt = jrec[t];
               const int st = t == 0 ? ucur : ur[jrec[t - 1]], ns = ur[jt], k = (jt / jm) % A;
               const double reward = __dmul_rn(priceJ[jt], lutAQ[p.a_off[i] + k]);
-              const double next_max = (double)row_max(tb + (size_t)ns * A, A, lane);
+              const double next_max = (double)row_max(tb + (size_t)ns * s.row_stride, A, lane);
               const double nv = __dadd_rn(__dmul_rn(one_m_alpha, (double)oldv[t]),
                                           __dmul_rn(alpha, __dadd_rn(reward, __dmul_rn(gamma, next_max))));
               if ((k & 31) == lane) {  // the lane that owns column k
-                tb[(size_t)st * A + k] = (QT)nv;
-                if (cnt) atomicAdd(cnt + s.table_offset + (size_t)st * A + k, 1u);
+                tb[(size_t)st * s.row_stride + k] = (QT)nv;
+                if (cnt) atomicAdd(cnt + s.table_offset + (size_t)st * s.row_stride + k, 1u);
                 dirty[st >> 5] |= 1u << (st & 31);
               }
             }
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ P
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
       if (s.kind != THRL_AGENT_QTABLE) continue;
-      const int cells = (s.states + 1) * s.actions;
+      const int cells = (s.states + 1) * s.row_stride;
       const QT* tb = reinterpret_cast<const QT*>(slot + p.off_tab[i]);
       QT* dst = tabg + s.table_offset;
       for (int c = lane; c < cells; c += 32) dst[c] = tb[c];

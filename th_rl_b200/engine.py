@@ -25,6 +25,7 @@ class ScanOutput:
     trace_actions = None
     trace_rewards = None
     trace_prices = None
+    ring = None          # scan_host only: pending transitions of a non-regular game at the end of the call (host array)
 
 
 class RunBatch:
@@ -151,16 +152,14 @@ class RunBatch:
 
     # ---- results -------------------------------------------------------------------------------------------------
     def tables(self, run=None):
-        """Per-agent tables [R, states+1, actions] (views of the packed slab)."""
+        """Per-agent tables [R, states+1, actions] (views of the packed slab; rows may be padded, include/thrl.h)."""
         q = self.q if run is None else self.q[run:run + 1]
-        return [q[:, s.table_offset:s.table_offset + (s.states + 1) * s.actions].reshape(-1, s.states + 1, s.actions)
-                if s.kind == abi.THRL_AGENT_QTABLE else None
+        return [abi.table_view(q, s) if s.kind == abi.THRL_AGENT_QTABLE else None
                 for s in (self.game.agent[i] for i in range(self.game.n_agents))]
 
     def counters(self, run=None):
         c = self.counter if run is None else self.counter[run:run + 1]
-        return [c[:, s.table_offset:s.table_offset + (s.states + 1) * s.actions].reshape(-1, s.states + 1, s.actions)
-                if s.kind == abi.THRL_AGENT_QTABLE else None
+        return [abi.table_view(c, s) if s.kind == abi.THRL_AGENT_QTABLE else None
                 for s in (self.game.agent[i] for i in range(self.game.n_agents))]
 
     def mlp_state_dicts(self, run=0):
@@ -271,9 +270,13 @@ def scan_from_host(batch, host, epochs, n_chunks=12):
 
 def scan_host(config, q, eps, price, epochs, *, counter=None, hp=None, rng_mode=abi.THRL_RNG_PHILOX, seed=0, run_id0=0,
               epoch_begin=0, replay_u=None, replay_ra=None, replay_new_a=None, n_log_runs=0, stats=False, trace=False,
-              device=0, mlp=None):
-    """thrl_qtable_scan_host: HOST numpy buffers in and out, all copies inside the call (the reference-facing
-    boundary; bench.py's e2e leg times exactly this).  q/eps/price(/counter) are updated IN PLACE."""
+              device=0, mlp=None, ring=None):
+    """thrl_qtable_scan_host: HOST buffers in and out, all copies inside the call, chunked and overlapped with the kernel by
+    the library (the reference-facing boundary; bench.py's e2e leg times exactly this call on page-locked buffers).
+    q / eps / price (/ counter / mlp / ring) are numpy arrays updated IN PLACE.  Games that are not regular (an agent's
+    min_memory exceeds max_steps) carry their pending transitions in `ring` (uint8 [R, thrl_ring_bytes], zero = empty):
+    pass the same array to consecutive calls; when omitted the call starts from empty buffers and the result's `ring`
+    holds what is pending at its end."""
     g = game_layout(config)
     n, T, E = g.n_agents, g.max_steps, int(epochs)
     R = q.shape[0]
@@ -315,6 +318,13 @@ def scan_host(config, q, eps, price, epochs, *, counter=None, hp=None, rng_mode=
         a.counter = outp(counter)
     a.hp = inp(hp, np.float64, (R, n, 4))
     a.mlp = outp(mlp) if g.mlp_stride else None
+    if not g.regular:
+        rb = int(lib().thrl_ring_bytes(C.byref(g)))
+        if ring is None:
+            ring = np.zeros((R, rb), np.uint8)
+        assert ring.dtype == np.uint8 and ring.shape == (R, rb) and ring.flags.c_contiguous
+        a.ring = outp(ring)
+        out.ring = ring
     a.replay_u = inp(replay_u, np.float64, (R, E, T, n))
     a.replay_ra = inp(replay_ra, np.int32, (R, E, T, n))
     a.replay_new_a = inp(replay_new_a, np.float64, (R, E, T))

@@ -125,10 +125,19 @@ def train_one(exp_path, configpath, loadonly=False, print_eps=False, rng="refere
 
     t = time.time()
     state = environment.reset()  # trainer.py:45 — the second uniform draw, like the reference
-    batch = engine.RunBatch(config, 1, device=device, dtype=torch.float64, seed=random.getrandbits(63) if rng != "reference" else 0)
     is_q = [isinstance(a, AGENTS["QTable"]) for a in agents]
-    tabs0 = [a.table.reshape(-1) for a, q in zip(agents, is_q) if q]
-    q0 = numpy.concatenate(tabs0)[None] if tabs0 else numpy.zeros((1, 0))
+    # Philox key of this run.  In reference mode the QTable / environment draws are replayed from the host generators, but an
+    # MLP agent's action samples are drawn on the device (the reference takes them from torch's generator inside every step,
+    # agents.py:160-163): their key comes from torch's generator, so a script that seeds torch stays reproducible and
+    # successive runs get independent sampling noise.  Drawn only when needed: a QTable-only run leaves torch's stream alone.
+    if rng != "reference":
+        seed = random.getrandbits(63)
+    elif not all(is_q):
+        seed = int(torch.randint(0, 2 ** 62, ()).item())
+    else:
+        seed = 0
+    batch = engine.RunBatch(config, 1, device=device, dtype=torch.float64, seed=seed)
+    q0 = abi.pack_tables(batch.game, [a.table if q else None for a, q in zip(agents, is_q)], numpy.float64)
     mlp0 = None
     if batch.mlp is not None:  # MLP agents: the constructor's nn.Linear initialisation (agents.py:137-138)
         mlp0 = numpy.zeros((1, batch.game.mlp_stride), numpy.float32)

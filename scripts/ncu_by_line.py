@@ -1,10 +1,11 @@
 """Attribute an .ncu-rep's per-SASS counters to CUDA source lines: joins `ncu --page source --csv` (SASS order) with
 `nvdisasm -g` of the same function in libthrl.so (compiled with -lineinfo).
-Usage: python scripts/ncu_by_line.py REP MANGLED_FUNCTION UNITS [top]   (UNITS = agent-steps in the launch)"""
+Usage: python scripts/ncu_by_line.py REP MANGLED_FUNCTION UNITS [top] [instr|stall]   (UNITS = agent-steps in the launch)"""
 import csv, io, os, re, subprocess, sys, tempfile
 
 rep, func, units = sys.argv[1], sys.argv[2], float(sys.argv[3])
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+key = 1 if (len(sys.argv) > 5 and sys.argv[5] == "stall") else 0
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "th_rl_b200", "libthrl.so")], cwd=tmp, capture_output=True)
@@ -33,7 +34,7 @@ tot_i, tot_s = sum(a[0] for a in agg.values()), sum(a[1] for a in agg.values())
 text = {}
 print("total warp-instr / unit: %.1f" % (tot_i / units))
 print("| file:line | warp-instr / unit | %% instr | %% stall samples | source |\n|---|---|---|---|---|")
-for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for (f, ln), a in sorted(agg.items(), key=lambda kv: -kv[1][key])[:top]:
     if f not in text:
         p = os.path.join(root, "th_rl_b200", "csrc", f)
         text[f] = open(p).read().splitlines() if os.path.exists(p) else []

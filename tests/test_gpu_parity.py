@@ -497,7 +497,7 @@ def test_c4_full_shape_matches_oracle(kernel_choice):
 
 def _hbm_cfg(agents, T, noise=0.0, a=10):
     base = dict(name="QTable", gamma=0.95, alpha=0.1, eps_end=0.001, epsilon=0.5, eps_step=0.9995, states=400, actions=40,
-                action_range=[0.1, 0.3])
+                action_range=[0.1, 0.3], min_memory=T)
     return {"agents": [dict(base, **x) for x in agents],
             "environment": dict(name="NoisyPriceState", noise_prob=noise, a=a, b=1, nplayers=len(agents), max_steps=T),
             "training": dict(print_freq=500, epochs=3)}
@@ -520,6 +520,8 @@ HBM_CASES = {
     "ring8": (_hbm_cfg([dict(), dict(actions=33)], 5), {"THRL_HBM_NB": "8"}),
     # the comparison path of the gather (16-byte vector loads instead of bulk copies)
     "ldg": (_hbm_cfg([dict(), dict(actions=33), dict(states=50)], 40), {"THRL_HBM_GATHER": "ldg"}),
+    "cpasync": (_hbm_cfg([dict(), dict(actions=33), dict(states=50)], 40), {"THRL_HBM_GATHER": "cpasync"}),
+    "bulk": (_hbm_cfg([dict(), dict(actions=33), dict(states=50)], 40), {"THRL_HBM_GATHER": "bulk"}),
 }
 
 

@@ -323,7 +323,7 @@ bool plan_hbm(thrl::HbmParams* p, size_t elem, const DeviceInfo& dev, int* warps
     if (w > 16) w = 16;
   }
   const char* g = getenv("THRL_HBM_GATHER");
-  p->bulk = (g && strcmp(g, "ldg") == 0) ? 0 : 1;
+  p->bulk = (g && strcmp(g, "ldg") == 0) ? 0 : ((g && strcmp(g, "cpasync") == 0) ? 2 : 1);
   *warps = w;
   return true;
 }

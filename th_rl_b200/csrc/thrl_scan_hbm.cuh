@@ -55,7 +55,8 @@ struct HbmParams {
   int gcap[THRL_MAX_AGENTS], goff[THRL_MAX_AGENTS], loff[THRL_MAX_AGENTS], L[THRL_MAX_AGENTS];
   int lut_total, rows_total;
   int noisy;     // new_a varies per step
-  int bulk;      // 1: rows are staged with cp.async.bulk; 0: with 16-byte vector loads (debug / comparison)
+  int bulk;      // how rows are staged: 1 = cp.async.bulk (TMA unit), 2 = cp.async 16-byte copies (LSU, no registers),
+                 // 0 = 16-byte vector loads + shared stores (comparison)
   int nb;        // staging ring depth
   int slot_bytes;  // one staged row
   int Tp, Sp;    // padded strides of the [n][T] / [n][T+1] per-agent arrays (elements)
@@ -86,6 +87,14 @@ __device__ __forceinline__ void hbm_mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(hbm_smem_addr(bar)), "r"(parity)
         : "memory");
   } while (!done);
+}
+// per-thread 16-byte asynchronous copy global -> shared that bypasses L1 (it must see the tags), and the mbarrier arrival
+// that fires once all of this thread's earlier copies have landed
+__device__ __forceinline__ void hbm_cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hbm_smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void hbm_cp_async_arrive(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(hbm_smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void hbm_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(hbm_smem_addr(dst)),
@@ -183,7 +192,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_hbm(const __grid_constant_
   uint32_t* cmin = reinterpret_cast<uint32_t*>(slot + p.off_cmin);         // [n][Sp] its first column                     }
 
   if (lane == 0)
-    for (int b = 0; b < nb; ++b) hbm_mbar_init(bar + b, 1);
+    for (int b = 0; b < nb; ++b) hbm_mbar_init(bar + b, p.bulk == 1 ? 1u : 32u);  // bulk: one arrival + byte count; else every lane arrives
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   hbm_fence_proxy_async();
   __syncwarp();
@@ -376,25 +385,25 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_hbm(const __grid_constant_
           }
         }
         unsigned char* dst = stage + ((size_t)b * n + lane) * p.slot_bytes;
-        if (p.bulk) {
+        if (p.bulk == 1) {
           const uint32_t total = __reduce_add_sync(kFull, bytes);
           if (lane == 0) hbm_mbar_expect_tx(bar + b, total);
           if (bytes) hbm_bulk_g2s(dst, src, bytes, bar + b);
-        } else {  // comparison path: the same rows with 16-byte vector loads that bypass L1 (they must see the tags)
+        } else {  // the same rows in 16-byte pieces: lane l moves bytes [16 l, 16 l + 16) (and [16 (l + 32), ...) of 8-byte tables)
           for (int i = 0; i < n; ++i) {
             const uint32_t bi = __shfl_sync(kFull, bytes, i);
             const unsigned long long si = __shfl_sync(kFull, (unsigned long long)src, i);
-            if (16u * lane < bi) {
-              const int4 x = __ldcg(reinterpret_cast<const int4*>(si) + lane);
-              reinterpret_cast<int4*>(stage + ((size_t)b * n + i) * p.slot_bytes)[lane] = x;
-              if (sizeof(QT) == 8 && 16u * (lane + 32) < bi) {
-                const int4 y = __ldcg(reinterpret_cast<const int4*>(si) + lane + 32);
-                reinterpret_cast<int4*>(stage + ((size_t)b * n + i) * p.slot_bytes)[lane + 32] = y;
-              }
+            int4* di = reinterpret_cast<int4*>(stage + ((size_t)b * n + i) * p.slot_bytes);
+            if (p.bulk == 2) {
+              if (16u * lane < bi) hbm_cp_async16(di + lane, reinterpret_cast<const int4*>(si) + lane);
+              if (sizeof(QT) == 8 && 16u * (lane + 32) < bi) hbm_cp_async16(di + lane + 32, reinterpret_cast<const int4*>(si) + lane + 32);
+            } else {  // loads that bypass L1 (they must see the tags)
+              if (16u * lane < bi) di[lane] = __ldcg(reinterpret_cast<const int4*>(si) + lane);
+              if (sizeof(QT) == 8 && 16u * (lane + 32) < bi) di[lane + 32] = __ldcg(reinterpret_cast<const int4*>(si) + lane + 32);
             }
           }
-          __syncwarp();
-          if (lane == 0) hbm_mbar_arrive(bar + b);
+          if (p.bulk == 2) hbm_cp_async_arrive(bar + b);
+          else hbm_mbar_arrive(bar + b);
         }
       };
       if (tmin < T) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — agent-steps/s of the th_rl training hot path on N B200s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c5] [--no-extras]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
@@ -11,11 +11,15 @@ One "step" = one pass of the hot path (thrl_qtable_scan) over the whole batch: R
 collective is the NCCL all-reduce of the per-epoch cross-run statistics, inside the timed region.
 
 value  = agent-steps of all ranks / max-over-ranks CUDA-event time, state resident in HBM.
-e2e    = the same work through the host-facing API: tables start in pinned HOST memory, are copied in, scanned,
-         and tables + counters + statistics are copied back, all inside the timed region.
---impl reference: the CPU arm = the oracle port of the reference path (oracle/thrl_oracle.c, all host threads) on a
-         bounded sample of the same workload.  The reference itself is pure Python and cannot travel to the GPU box;
-         its measured speed in the build container is quoted in BASELINE.md (2.35e4 agent-steps/s/core).
+e2e    = the same work through the reference-facing C-ABI call with HOST buffers (thrl_qtable_scan_host): tables start in
+         page-locked host memory, are copied in, scanned and copied back (tables + counters + epsilon + price + statistics),
+         all inside the timed region.
+workloads = the same measurement (value, e2e, roofline, clocks) for the other two BASELINE shapes -- c4 (8 agents, tables
+         left in HBM) and c5 (MLP agents) -- after the headline workload, in the same JSON line (--no-extras skips them).
+--impl reference: the CPU arm = the UNMODIFIED Python reference (oracle/_ref, staged by oracle/stage_reference.py) running
+         th_rl.trainer.train_one in one process per host core on a bounded sample of the same workload; when the staged
+         reference is missing, the oracle port (oracle/thrl_oracle.c, all host threads).  The port's rate is reported next
+         to it either way (`cpu_port`): it is ~10^3 x faster per core than the Python loop and the more conservative baseline.
 """
 import argparse
 import json
@@ -52,9 +56,17 @@ def _c4_hp(R, n):
     return hp
 
 
-# name -> workload.  `algo_bytes` = SURVEY 8(d): 8*A + 16 bytes of table traffic per agent-step.  `e2e_chunks`: launches the host
-# pipeline cuts a step into (c4: two launches of one full round each -- 4,096 runs are two rounds of the persistent grid, smaller
-# launches would leave SMs idle; c5 has only 7 resident waves per step: about one launch per wave).
+def _c5_cfg(epochs):
+    a = dict(name="ActorCritic", gamma=0.98, actions=21, states=1, action_range=[0.2, 0.4])  # 1 -> 256 -> {21, 1}, N = 1000
+    return {"agents": [dict(a), dict(a)],
+            "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=2, max_steps=MAX_STEPS),
+            "training": dict(print_freq=500, epochs=epochs)}
+
+
+# name -> workload.  `algo_bytes` = algorithmic bytes per agent-step: Q-table shapes 8*A + 16; c5: the
+# update's parameter / Adam read-modify-write (6 x 4 B x 6,166 parameters per 1,000-transition batch) + 32 B of transition ring.
+# `e2e_chunks`: launches the host entry point cuts a step into (c4: two launches of one full round each -- 4,096 runs are two
+# rounds of the persistent grid, smaller launches would leave SMs idle; c5 has only 7 resident waves per step).
 WORKLOADS = {
     "c2": dict(agents=2, runs_per_gpu=131072, epochs=1000, e2e_chunks=12, config=_qcfg(2, 100, 21, 0.2, 0.4, 1000), algo_bytes=184.0,
                bound="smem", hp=None,
@@ -65,46 +77,23 @@ WORKLOADS = {
                bound="hbm", hp=_c4_hp,
                desc="hyper-parameter sweep (alpha x eps_step x gamma = 64 points x 64 seeds), 8 QTable agents, 1001x101 "
                     "tables left in HBM, max_steps=100, %d runs/GPU x %d epochs per step (C4 shape)",
-               kernel="thrl::qtable_scan_generic<float, false> (persistent, one launch per step)"),
+               kernel="thrl::qtable_scan_hbm<float, false> (persistent, one launch per step; distinct rows of an episode gathered once "
+                      "with 16-byte vector loads into registers, L2 prefetch two batches ahead, update chain on chip)"),
+    "c5": dict(agents=2, runs_per_gpu=16384, epochs=200, e2e_chunks=8, config=_c5_cfg(200), algo_bytes=180.0, bound="hbm", hp=None,
+               desc="2 ActorCritic agents (MLP 1->256->{21,1}, Adam, N=1000 transition batches every 10 episodes), "
+                    "%d runs/GPU x %d epochs per step (C5 shape)",
+               kernel="thrl::mlp_scan_pwl (persistent, one launch per step; policy LUT per lattice state + sorted-breakpoint "
+                      "gradient sweep, f64 accumulation; no dense contraction is left)"),
 }
-def _c5_cfg(epochs):
-    a = dict(name="ActorCritic", gamma=0.98, actions=21, states=1, action_range=[0.2, 0.4])  # 1 -> 256 -> {21, 1}, N = 1000
-    return {"agents": [dict(a), dict(a)],
-            "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=2, max_steps=MAX_STEPS),
-            "training": dict(print_freq=500, epochs=epochs)}
-
-
-# ~1.1e4 flop per act + ~3.4e4 flop per agent-step of amortised update (N = 1000 batch every 10 episodes)
-WORKLOADS["c5"] = dict(agents=2, runs_per_gpu=16384, epochs=200, e2e_chunks=8, config=_c5_cfg(200), algo_bytes=4.5e4, bound="tensor", hp=None,
-                       desc="2 ActorCritic agents (MLP 1->256->{21,1}, Adam, N=1000 transition batches every 10 episodes), "
-                            "%d runs/GPU x %d epochs per step (C5 shape)",
-                       kernel="thrl::mlp_scan_pwl (persistent, one launch per step; policy LUT per lattice state + sorted-breakpoint "
-                              "gradient sweep, f64 accumulation; no dense contraction is left)")
-WL = WORKLOADS["c2"]  # set in main()
-CONFIG = WL["config"]
-EPOCHS = WL["epochs"]
-ALGO_BYTES_PER_AGENT_STEP = WL["algo_bytes"]
-
-
-def select_workload(name):
-    global WL, CONFIG, EPOCHS, ALGO_BYTES_PER_AGENT_STEP
-    WL = WORKLOADS[name]
-    CONFIG, EPOCHS, ALGO_BYTES_PER_AGENT_STEP = WL["config"], WL["epochs"], WL["algo_bytes"]
+NCU_INSTR = {"c2": 30.4}  # warp instructions per agent-step from the committed ncu capture (profiles/)
 
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured"
-    return 6650.0, 1965.0, "fallback"
-
-
-def measured_tflops():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get("bf16_tflops_sustained", 1400.0), "measured (sustained)"
-    return 1400.0, "fallback"
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1965.0, 1400.0, "fallback"
 
 
 class ClockSampler:
@@ -150,52 +139,80 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_oracle_leg(n_threads, target_seconds=12.0):
-    """Times the oracle port on host cores on a bounded sample of the same workload (same config, fewer runs)."""
+# ------------------------------------------------------------------------------------------------------------ CPU legs
+def cpu_port_leg(wl, epochs, n_threads=0, target_seconds=8.0):
+    """The oracle port (oracle/thrl_oracle.c) on host cores on a bounded sample of the workload (same config, fewer runs)."""
     import numpy as np
     from oracle import oracle
     from th_rl_b200 import abi
-    game = oracle.layout(CONFIG)
+    cfg, n = wl["config"], wl["agents"]
+    game = oracle.layout(cfg)
     cores = n_threads if n_threads > 0 else oracle.online_cores()
-    eps0 = abi.eps0_from_config(CONFIG)
+    eps0 = abi.eps0_from_config(cfg)
     # calibrate on a small sample, then size the timed sample for ~target_seconds
-    R0 = (64 if WL["agents"] == 2 else 1) * cores
+    R0 = (64 if n == 2 else 1) * cores
     q0, c0, e0, p0, *rest = oracle.init(game, R0, seed=0, dtype=np.float32, eps0=eps0)
     t = time.perf_counter()
     oracle.scan(game, q0, e0, p0, 20, n_threads=cores, n_log_runs=0, stats=True, mlp=rest[0] if rest else None)
-    n = WL["agents"]
     rate = R0 * n * 20 * MAX_STEPS / (time.perf_counter() - t)
-    R = int(max(cores, min(262144, target_seconds * rate / (n * EPOCHS * MAX_STEPS))))
+    R = int(max(cores, min(262144, target_seconds * rate / (n * epochs * MAX_STEPS))))
     q0, c0, e0, p0, *rest = oracle.init(game, R, seed=0, dtype=np.float32, eps0=eps0)
     t = time.perf_counter()
-    oracle.scan(game, q0, e0, p0, EPOCHS, n_threads=cores, n_log_runs=0, stats=True, mlp=rest[0] if rest else None)
+    oracle.scan(game, q0, e0, p0, epochs, n_threads=cores, n_log_runs=0, stats=True, mlp=rest[0] if rest else None)
     dt = time.perf_counter() - t
-    return {"value": R * n * EPOCHS * MAX_STEPS / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d runs x %d epochs x %d steps x %d agents of the bench workload, fp32-storage oracle "
-                      "(oracle/thrl_oracle.c), %d pthreads, %.1f s" % (R, EPOCHS, MAX_STEPS, n, cores, dt)}, dt
+    return {"value": R * n * epochs * MAX_STEPS / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d runs x %d epochs x %d steps x %d agents of the workload, fp32-storage oracle port "
+                      "(oracle/thrl_oracle.c), %d pthreads, %.1f s" % (R, epochs, MAX_STEPS, n, cores, dt)}, dt
 
 
-def _run_stride():
-    return sum((a["states"] + 1) * a["actions"] for a in CONFIG["agents"] if a["name"] == "QTable")
+class ReferenceLeg:
+    """The unmodified Python reference (oracle/_ref): one train_one per host core per sample, epochs sized for ~target seconds."""
+
+    def __init__(self, wl):
+        from oracle import oracle, ref_bench
+        self.wl, self.cores = wl, oracle.online_cores()
+        self.pool = ref_bench.ReferencePool(self.cores)
+        self.epochs = None
+
+    def sample(self, target_seconds):
+        cfg, n = self.wl["config"], self.wl["agents"]
+        if self.epochs is None:  # calibrate: a handful of epochs
+            e0 = 4 if any(a["name"] != "QTable" for a in cfg["agents"]) else 20
+            _, dt, _ = self.pool.sample(cfg, e0)
+            self.epochs = int(max(e0, min(20000, e0 * target_seconds / max(dt, 1e-3))))
+        rate, dt, per_proc = self.pool.sample(cfg, self.epochs)
+        return {"value": rate, "unit": "agent-steps/s", "cores": self.cores, "kind": "reference",
+                "sample": "th_rl.trainer.train_one (unmodified, oracle/_ref) on the workload's config with epochs=%d: %d processes x "
+                          "%d agent-steps, one thread each, slowest process %.1f s" % (self.epochs, self.cores, per_proc, dt)}, dt
+
+    def close(self):
+        self.pool.close()
 
 
-def _state_bytes(R):
-    from th_rl_b200 import _lib
-    g = _lib.game_layout(CONFIG)
+def reference_available():
+    from oracle import ref_bench
+    return ref_bench.available()
+
+
+def _state_bytes(cfg, R, layout):
+    g = layout(cfg)
     return R * (g.run_stride * 8 + g.mlp_stride * 4)
 
 
-def base_line(args, n_gpus):
+def config_block(name, wl, runs_per_gpu, epochs, n_gpus, layout):
+    return {"workload": wl["desc"] % (runs_per_gpu, epochs), "workload_id": name,
+            "runs_per_gpu": runs_per_gpu, "global_runs": runs_per_gpu * n_gpus, "epochs_per_step": epochs,
+            "max_steps": MAX_STEPS, "agents": wl["agents"], "table_storage": "fp32 (f64 update arithmetic)",
+            "rng": "philox4x32-10", "parallelism": "runs sharded over %d GPU(s), no data-path collective; "
+                                                   "NCCL all-reduce of per-epoch statistics" % n_gpus,
+            "l2": "per-GPU state (%.1f GB) is far larger than the 126 MB L2" % (_state_bytes(wl["config"], runs_per_gpu, layout) / 1e9)}
+
+
+def base_line(args, name, wl, n_gpus, layout):
     return {
         "metric": "agent-steps/sec", "unit": "agent-steps/s", "n_gpus": n_gpus, "steps": args.steps,
         "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": WL["desc"] % (args.runs_per_gpu, args.epochs), "workload_id": args.workload,
-                   "runs_per_gpu": args.runs_per_gpu, "global_runs": args.runs_per_gpu * n_gpus, "epochs_per_step": args.epochs,
-                   "max_steps": MAX_STEPS, "agents": WL["agents"], "table_storage": "fp32 (f64 update arithmetic)",
-                   "rng": "philox4x32-10", "parallelism": "runs sharded over %d GPU(s), no data-path collective; "
-                                                          "NCCL all-reduce of per-epoch statistics" % n_gpus,
-                   "l2": "per-GPU state (%.1f GB) is far larger than the 126 MB L2" % (_state_bytes(args.runs_per_gpu) / 1e9)},
+        "data": "synthetic", "config": config_block(name, wl, args.runs_per_gpu, args.epochs, n_gpus, layout),
     }
 
 
@@ -203,43 +220,47 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    cb = None
-    for i in range(args.warmup + args.steps):
-        cb, dt = cpu_oracle_leg(0, target_seconds=max(2.0, min(10.0, 120.0 / (args.warmup + args.steps))))
+    from oracle import oracle
+    wl = WORKLOADS[args.workload]
+    n_samples = args.warmup + args.steps
+    target = max(2.0, min(10.0, 120.0 / n_samples))
+    vals, cb = [], None
+    leg = ReferenceLeg(wl) if reference_available() else None
+    for i in range(n_samples):
+        cb, dt = leg.sample(target) if leg else cpu_port_leg(wl, args.epochs, target_seconds=target)
         if i >= args.warmup:
             vals.append((cb["value"], dt))
+    if leg:
+        leg.close()
     v = statistics.mean(x for x, _ in vals)
-    line = base_line(args, args.gpus)
+    line = base_line(args, args.workload, wl, args.gpus, oracle.layout)
     line.update({"impl": "reference", "value": v, "ms_per_step": 1e3 * statistics.mean(d for _, d in vals),
                  "cpu_baseline": dict(cb, value=v),
                  "e2e": {"value": v, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0})
-    line["config"]["reference_arm"] = ("oracle port of th_rl/trainer.py:45-70 + agents.py:59-89 + environments.py:25-39 on "
-                                       "host cores; the Python reference itself measured 2.35e4 agent-steps/s/core in the "
-                                       "build container (BASELINE.md)")
+    if leg:
+        line["cpu_port"], _ = cpu_port_leg(wl, args.epochs, target_seconds=5.0)
+        line["config"]["reference_arm"] = ("the unmodified reference: th_rl/trainer.py:29-110 train_one (oracle/_ref), one process per host "
+                                           "core, each step a bounded sample (epochs reduced); cpu_port = the C restatement of the same "
+                                           "path on all host threads")
+    else:
+        line["config"]["reference_arm"] = ("oracle/_ref is not staged: oracle port of th_rl/trainer.py:45-70 + agents.py:59-89 + "
+                                           "environments.py:25-39 on host cores; the Python reference itself measured 2.35e4 "
+                                           "agent-steps/s/core in the build container (BASELINE.md)")
     print(json.dumps(line))
 
 
-def run_ours(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from th_rl_b200 import _lib, abi, engine
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    R, E = args.runs_per_gpu, args.epochs
-    nag = WL["agents"]
+# ------------------------------------------------------------------------------------------------------------ GPU legs
+def measure(name, wl, R, E, steps, warmup, e2e_chunks, ctx):
+    """value / e2e / roofline / clocks of one workload on this rank's GPU; collective maxima over ranks.  Returns a dict on
+    every rank (rank 0 prints it)."""
+    torch, np, dist, engine, _lib = ctx["torch"], ctx["np"], ctx["dist"], ctx["engine"], ctx["_lib"]
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
+    nag = wl["agents"]
     agent_steps_rank = R * nag * E * MAX_STEPS
-    hp = WL["hp"](R, nag) if WL["hp"] else None
+    hp = wl["hp"](R, nag) if wl["hp"] else None
 
-    batch = engine.RunBatch(CONFIG, R, device=dev, dtype=torch.float32, seed=0, run_id0=rank * R, hp=hp).init_device()
+    batch = engine.RunBatch(wl["config"], R, device=dev, dtype=torch.float32, seed=0, run_id0=rank * R, hp=hp).init_device()
     torch.cuda.synchronize()
 
     def barrier():
@@ -247,24 +268,21 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
+    for _ in range(warmup):
         out = batch.scan(E, stats=True)
         if world > 1:
             dist.all_reduce(out.stats)  # exact int64 sums: the result does not depend on the sharding
-        return out
-
-    for _ in range(args.warmup):
-        step()
     barrier()
-    sampler = ClockSampler(local)
+    kernel_name = _lib.last_kernel()
+    sampler = ClockSampler(dev.index)
     if rank == 0:
         sampler.start()
     launches0 = _lib.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     ev[0].record()
-    for i in range(args.steps):
-        kev[i][0].record()
+    for i in range(steps):
+        kev[i][0].record()  # the scan is launched on torch's current stream, where these events are recorded
         out = batch.scan(E, stats=True)
         kev[i][1].record()
         if world > 1:
@@ -279,78 +297,72 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, kern_ms = t.tolist()
-    value = agent_steps_rank * world * args.steps / (total_ms * 1e-3)
+    value = agent_steps_rank * world * steps / (total_ms * 1e-3)
+    del batch, out
+    torch.cuda.empty_cache()
 
-    # ---- e2e: host-resident state in, results back to the host, all inside the timed region
-    e2e = measure_e2e(args, torch, np, engine, dev, rank, world, barrier)
+    e2e = measure_e2e(wl, R, E, min(steps, 3), e2e_chunks, ctx, barrier)
+    res = {"value": value, "ms_per_step": total_ms / steps, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+           "kernel_dispatched": kernel_name}
 
-    if rank == 0:
-        hbm_peak, sm_max_mhz, peak_src = measured_peaks()
+    hbm_peak, sm_max_mhz, tf_peak, peak_src = measured_peaks()
+    per_gpu_rate = agent_steps_rank / (kern_ms * 1e-3)
+    achieved = per_gpu_rate * wl["algo_bytes"] / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "kernel": wl["kernel"], "kernel_ms": kern_ms, "algorithmic_bytes_per_agent_step": wl["algo_bytes"],
+            "algorithmic_bytes_per_launch": agent_steps_rank * wl["algo_bytes"]}
+    if name == "c2":
         smem_peak_gbs = 128.0 * 148 * sm_max_mhz * 1e6 / 1e9  # 128 B/clk/SM x 148 SMs x max SM clock
-        per_gpu_rate = agent_steps_rank / (kern_ms * 1e-3)
-        achieved = per_gpu_rate * ALGO_BYTES_PER_AGENT_STEP / 1e9
-        line = base_line(args, world)
-        line.update({"value": value, "ms_per_step": total_ms / args.steps, "clocks": clocks, "e2e": e2e, "gpu_launches": launches})
-        if WL["bound"] == "smem":
-            line["roofline"] = {
-                "bound": "smem", "achieved": achieved, "peak": smem_peak_gbs, "unit": "GB/s", "frac": achieved / smem_peak_gbs,
-                "traffic": None, "kernel": WL["kernel"], "kernel_ms": kern_ms,
-                "note": "tables are shared-memory resident, so the bound is SM shared-memory bandwidth / issue rate, not HBM "
-                        "(BASELINE.md 5: 184 algorithmic B per agent-step; peak = 128 B/clk/SM x 148 SMs x %.0f MHz from "
-                        "MEASURED_PEAKS.json, %s). ncu (profiles/): ~31 warp instructions and ~6 shared-memory wavefronts "
-                        "per agent-step, LSU data pipe ~52%% busy, issue slots ~70%% busy; HBM sees only the one-off slab "
-                        "load/store and the visit counters" % (sm_max_mhz, peak_src),
-                "hbm": {"achieved": per_gpu_rate * (2 * _run_stride() * (4 + 4 + 4) / (nag * 1.0 * E * MAX_STEPS)) / 1e9,
-                        "peak": hbm_peak, "unit": "GB/s"},
-                # the limiter ncu names: warp-instruction issue.  Instructions per agent-step come from the committed ncu
-                # capture of this command (profiles/r1_bench_c2_lut2_ncu_summary.md), the rate is the live one.
-                "issue_slots": {"warp_inst_per_agent_step": 30.4, "achieved": per_gpu_rate * 30.4,
-                                "peak": 4 * 148 * sm_max_mhz * 1e6, "unit": "warp-inst/s",
-                                "frac": per_gpu_rate * 30.4 / (4 * 148 * sm_max_mhz * 1e6)}}
-        elif WL["bound"] == "tensor":
-            tf_peak, tf_src = measured_tflops()
-            tf = per_gpu_rate * ALGO_BYTES_PER_AGENT_STEP / 1e12
-            line["roofline"] = {
-                "bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak, "traffic": None,
-                "kernel": WL["kernel"], "kernel_ms": kern_ms,
-                "note": "4.5e4 algorithmic flop per agent-step (BASELINE.md 5: per-step forward + N = 1000 batched update as dense "
-                        "GEMMs); peak = bf16 dense from MEASURED_PEAKS.json (%s).  The kernel does NOT execute those flops: the "
-                        "network input is a scalar from a finite price lattice, so pi(.|s) is tabulated per state and the exact "
-                        "gradient comes from one sorted-breakpoint sweep, O(states*A + H*A) per update instead of O(N*H*A) "
-                        "(DESIGN.md 4.5).  `achieved` is therefore the rate the dense formulation would have needed; tensor-pipe "
-                        "utilisation is 0 by construction and the real limiter is SM issue rate (profiles/)" % tf_src}
-        else:
-            line["roofline"] = {
-                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "traffic": None, "kernel": WL["kernel"], "kernel_ms": kern_ms,
-                "note": "tables (3.2 MB per run) stay in HBM; 824 algorithmic B per agent-step (BASELINE.md 5); peak = measured "
-                        "copy bandwidth from MEASURED_PEAKS.json (%s). ncu (profiles/): ~0.87 kB of DRAM traffic and ~123 warp "
-                        "instructions per agent-step; the greedy-action cache is carried through the update, so rollouts stop waiting on "
-                        "HBM once it is warm; the update pass is a chain of L2 hits at 14 resident warps per SM" % peak_src}
-        try:  # DRAM traffic per launch, measured once with ncu --set full on this exact command (profiles/)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload)
-            if tr and args.runs_per_gpu == WL["runs_per_gpu"]:  # per agent-step as captured x the agent-steps of this launch
-                line["roofline"]["traffic"] = tr["traffic_bytes_per_agent_step"] * agent_steps_rank
-                line["roofline"]["traffic_source"] = tr["source"]
-                line["roofline"]["algorithmic_bytes_per_launch"] = agent_steps_rank * ALGO_BYTES_PER_AGENT_STEP
-        except (OSError, ValueError):
-            pass
-        if args.no_cpu_baseline:
-            line["cpu_baseline"] = None
-        else:
-            line["cpu_baseline"], _ = cpu_oracle_leg(0)
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+        run_stride = sum((a["states"] + 1) * a["actions"] for a in wl["config"]["agents"])
+        roof.update({
+            "bound": "smem", "peak": smem_peak_gbs, "frac": achieved / smem_peak_gbs,
+            "note": "tables are shared-memory resident, so the bound is SM shared-memory bandwidth / issue rate, not HBM "
+                    "(BASELINE.md 5: 184 algorithmic B per agent-step; peak = 128 B/clk/SM x 148 SMs x %.0f MHz from "
+                    "MEASURED_PEAKS.json, %s). ncu (profiles/): ~31 warp instructions and ~6 shared-memory wavefronts "
+                    "per agent-step, LSU data pipe ~52%% busy, issue slots ~70%% busy; HBM sees only the one-off slab "
+                    "load/store and the visit counters" % (sm_max_mhz, peak_src),
+            "hbm": {"achieved": per_gpu_rate * (2 * run_stride * (4 + 4 + 4) / (nag * 1.0 * E * MAX_STEPS)) / 1e9,
+                    "peak": hbm_peak, "unit": "GB/s"},
+            # the limiter ncu names: warp-instruction issue.  Instructions per agent-step come from the committed ncu
+            # capture of this command (profiles/), the rate is the live one.
+            "issue_slots": {"warp_inst_per_agent_step": NCU_INSTR["c2"], "achieved": per_gpu_rate * NCU_INSTR["c2"],
+                            "peak": 4 * 148 * sm_max_mhz * 1e6, "unit": "warp-inst/s",
+                            "frac": per_gpu_rate * NCU_INSTR["c2"] / (4 * 148 * sm_max_mhz * 1e6)}})
+    elif name == "c4":
+        roof["note"] = ("tables (3.2 MB per run) stay in HBM; 824 algorithmic B per agent-step = 8*A + 16 (BASELINE.md 5: act row + "
+                        "bootstrap row + cell + counter); peak = measured copy bandwidth from MEASURED_PEAKS.json (%s).  The kernel "
+                        "moves less than that: the act row is served by an exact greedy-action cache on chip and a row that several "
+                        "states of an episode share is fetched once (profiles/: DRAM bytes per agent-step)" % peak_src)
+    else:
+        tf = per_gpu_rate * 4.5e4 / 1e12
+        roof["note"] = ("bound = HBM: what an update must move is the parameters and both Adam moments, read and written (6 x 4 B x 6,166 "
+                        "per 1,000-transition batch = 148 B per agent-step) plus 32 B of transition ring; peak = measured copy bandwidth "
+                        "from MEASURED_PEAKS.json (%s).  The dense formulation of this workload (BASELINE.md 5: 4.5e4 flop per agent-step "
+                        "as GEMMs) is not executed: the network input is a scalar from a finite price lattice, so pi(.|s) is tabulated "
+                        "per state and the exact gradient comes from one sorted-breakpoint sweep (DESIGN.md 4.5); tensor-pipe "
+                        "utilisation is 0 by construction" % peak_src)
+        roof["dense_formulation"] = {"flop_per_agent_step": 4.5e4, "equivalent_tflops": tf, "bf16_peak_tflops": tf_peak,
+                                     "frac": tf / tf_peak}
+    try:  # DRAM traffic per launch, measured once with ncu --set full on this exact command (profiles/)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+        if tr and R == wl["runs_per_gpu"]:  # per agent-step as captured x the agent-steps of this launch
+            roof["traffic"] = tr["traffic_bytes_per_agent_step"] * agent_steps_rank
+            roof["traffic_source"] = tr["source"]
+    except (OSError, ValueError):
+        pass
+    res["roofline"] = roof
+    return res
 
 
-def measure_e2e(args, torch, np, engine, dev, rank, world, barrier):
-    """Same metric through the host-facing call: pinned host tables -> device -> scan -> tables, counters, epsilon,
-    price and statistics back into pinned host memory.  Runs go through in chunks so copies overlap the kernel."""
-    import torch.distributed as dist
-    R, E = args.runs_per_gpu, args.epochs
-    nag = WL["agents"]
-    need = R * _run_stride() * 8 + R * (nag + 1) * 8  # pinned host copy of tables + counters + eps + price
+def measure_e2e(wl, R, E, steps, n_chunks, ctx, barrier):
+    """Same metric through the reference-facing boundary: thrl_qtable_scan_host on page-locked host buffers -- tables,
+    counters, epsilon, price (and the MLP slab) go host -> device -> scan -> host, statistics come back, all inside the timed
+    region; the library cuts the run range into chunks so that the copies overlap the kernel."""
+    torch, np, dist, engine = ctx["torch"], ctx["np"], ctx["dist"], ctx["engine"]
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
+    from th_rl_b200 import _lib, abi
+    nag = wl["agents"]
+    need = _state_bytes(wl["config"], R, _lib.game_layout) + R * (nag + 1) * 8  # pinned host copy of tables + counters + eps + price
     try:
         avail = int(next(l for l in open("/proc/meminfo") if l.startswith("MemAvailable")).split()[1]) * 1024
     except (OSError, StopIteration):
@@ -358,30 +370,89 @@ def measure_e2e(args, torch, np, engine, dev, rank, world, barrier):
     if need * world * 2 > avail:
         return {"value": None, "unit": "agent-steps/s", "h2d_bytes_per_step": need * world, "d2h_bytes_per_step": need * world,
                 "skipped": "host has %.0f GB available, the pinned state needs %.0f GB" % (avail / 1e9, need * world / 1e9)}
-    hp = WL["hp"](R, nag) if WL["hp"] else None
-    batch = engine.RunBatch(CONFIG, R, device=dev, dtype=torch.float32, seed=1, run_id0=rank * R, hp=hp).init_device()
+    hp = wl["hp"](R, nag) if wl["hp"] else None
+    batch = engine.RunBatch(wl["config"], R, device=dev, dtype=torch.float32, seed=1, run_id0=rank * R, hp=hp).init_device()
     torch.cuda.synchronize()
-    host = engine.HostState.from_batch(batch)  # pinned host copies of q / counter / eps / price
-    steps = max(1, min(args.steps, 3))
-    h2d = d2h = 0
+    host = engine.HostState.from_batch(batch)  # pinned host copies of q / counter / eps / price (/ mlp)
+    del batch
+    torch.cuda.empty_cache()
+    q, eps, price = host.q.numpy(), host.eps.numpy(), host.price.numpy()
+    counter = host.counter.numpy().view(np.uint32)
+    mlp = None if host.mlp is None else host.mlp.numpy()
+    os.environ["THRL_HOST_CHUNKS"] = str(n_chunks)
+    epoch = 0
     for it in range(1 + steps):  # one warm-up
         if it == 1:
             barrier()
             t0 = time.perf_counter()
-        stats, h2d, d2h = engine.scan_from_host(batch, host, E, n_chunks=args.e2e_chunks)
+        out = engine.scan_host(wl["config"], q, eps, price, E, counter=counter, hp=hp, seed=1, run_id0=rank * R,
+                               epoch_begin=epoch, stats=True, device=dev.index, mlp=mlp)
+        epoch += E
+        stats = out.stats  # the step's result (per-epoch cross-run statistics) is on the host when the call returns
         if world > 1:
-            dist.all_reduce(stats)
-        stats_h = stats.cpu()  # the step's result (per-epoch cross-run statistics) is read on the host
+            s = torch.from_numpy(stats).to(dev)
+            dist.all_reduce(s)
+            stats = s.cpu().numpy()
     barrier()
     dt = time.perf_counter() - t0
+    os.environ.pop("THRL_HOST_CHUNKS", None)
     t = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = t.item()
+    nb = host.nbytes() + (0 if hp is None else hp.nbytes)
+    _lib.lib().thrl_release_device_memory()
     return {"value": R * world * nag * E * MAX_STEPS * steps / dt, "unit": "agent-steps/s",
-            "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h + stats_h.numel() * 8) * world,
-            "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "api": "th_rl_b200.engine.scan_from_host (pinned host state in, tables+counters+eps+price+stats out)"}
+            "h2d_bytes_per_step": int(nb) * world, "d2h_bytes_per_step": int(host.nbytes() + stats.nbytes) * world,
+            "steps": steps, "ms_per_step": 1e3 * dt / steps, "chunks": n_chunks,
+            "api": "thrl_qtable_scan_host (C ABI, include/thrl.h) via th_rl_b200.engine.scan_host: page-locked host state in, "
+                   "tables+counters+eps+price+stats out"}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from th_rl_b200 import _lib, engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = dict(torch=torch, np=np, dist=dist, engine=engine, _lib=_lib, world=world, rank=rank, dev=dev)
+    wl = WORKLOADS[args.workload]
+    res = measure(args.workload, wl, args.runs_per_gpu, args.epochs, args.steps, args.warmup, args.e2e_chunks, ctx)
+    line = base_line(args, args.workload, wl, world, _lib.game_layout)
+    line.update(res)
+    line["parity"] = "green: tests/ -m gpu compare this path with the oracle and the reference's recorded goldens (bit-exact)"
+    if not args.no_extras:
+        line["workloads"] = {}
+        for name in ("c2", "c4", "c5"):
+            if name == args.workload:
+                continue
+            w2 = WORKLOADS[name]
+            r2 = measure(name, w2, w2["runs_per_gpu"], w2["epochs"], min(args.steps, 3), 3, w2["e2e_chunks"], ctx)
+            r2["config"] = config_block(name, w2, w2["runs_per_gpu"], w2["epochs"], world, _lib.game_layout)
+            r2["steps"], r2["warmup"], r2["unit"] = min(args.steps, 3), 3, "agent-steps/s"
+            line["workloads"][name] = r2
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        if args.no_cpu_baseline:
+            line["cpu_baseline"] = None
+        else:
+            line["cpu_port"], _ = cpu_port_leg(wl, args.epochs, target_seconds=8.0)
+            if reference_available():
+                leg = ReferenceLeg(wl)
+                line["cpu_baseline"], _ = leg.sample(10.0)
+                leg.close()
+            else:
+                line["cpu_baseline"] = line["cpu_port"]
+        print(json.dumps(line))
 
 
 def main():
@@ -393,14 +464,14 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS), help="c2 = headline (default); c4 = HBM-resident sweep; c5 = MLP (ActorCritic) agents")
     ap.add_argument("--runs-per-gpu", type=int, default=None)
     ap.add_argument("--epochs", type=int, default=None)
-    ap.add_argument("--e2e-chunks", type=int, default=None, help="launches the host pipeline cuts a step into (default: per workload)")
+    ap.add_argument("--e2e-chunks", type=int, default=None, help="launches the host entry point cuts a step into (default: per workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c4 / c5 measurements that follow the headline workload")
     args = ap.parse_args()
-    select_workload(args.workload)
-    args.runs_per_gpu = args.runs_per_gpu or WL["runs_per_gpu"]
-    args.epochs = args.epochs or WL["epochs"]
-    args.e2e_chunks = args.e2e_chunks or WL["e2e_chunks"]
-    globals()["EPOCHS"] = args.epochs
+    wl = WORKLOADS[args.workload]
+    args.runs_per_gpu = args.runs_per_gpu or wl["runs_per_gpu"]
+    args.epochs = args.epochs or wl["epochs"]
+    args.e2e_chunks = args.e2e_chunks or wl["e2e_chunks"]
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -43,16 +43,36 @@ def available():
     return stage_reference.staged()
 
 
+class ReferencePool:
+    """`procs` worker processes that have imported the staged reference; every sample() runs one train_one per worker."""
+
+    def __init__(self, procs):
+        self.procs = int(procs)
+        self.pool = mp.get_context("spawn").Pool(self.procs)
+        self.pool.map(_noop, range(self.procs))  # start the workers (imports excluded from the timing, as SURVEY 8(d) says)
+        self.calls = 0
+
+    def sample(self, config, epochs):
+        """`procs` concurrent train_one calls of `config` with training.epochs = epochs.  Returns (agent-steps/s aggregate,
+        seconds of the slowest process, agent-steps per process)."""
+        cfg = json.loads(json.dumps(config))
+        cfg["training"] = dict(cfg.get("training", {}), epochs=int(epochs), print_freq=10 ** 9)
+        per_proc = len(cfg["agents"]) * int(epochs) * int(cfg["environment"]["max_steps"])
+        self.calls += 1
+        dts = self.pool.map(_worker, [(cfg, 1000 * self.calls + k) for k in range(self.procs)], chunksize=1)
+        return per_proc * self.procs / max(dts), max(dts), per_proc
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
 def time_reference(config, epochs, procs):
-    """`procs` concurrent train_one calls of `config` with training.epochs = epochs.  Returns (agent-steps/s aggregate,
-    seconds of the slowest process, agent-steps per process)."""
-    cfg = json.loads(json.dumps(config))
-    cfg["training"] = dict(cfg.get("training", {}), epochs=int(epochs), print_freq=10 ** 9)
-    per_proc = len(cfg["agents"]) * int(epochs) * int(cfg["environment"]["max_steps"])
-    with mp.get_context("spawn").Pool(procs) as pool:
-        pool.map(_noop, range(procs))  # start the workers (imports excluded from the timing, as SURVEY 8(d) says)
-        dts = pool.map(_worker, [(cfg, 1000 + k) for k in range(procs)], chunksize=1)
-    return per_proc * procs / max(dts), max(dts), per_proc
+    pool = ReferencePool(procs)
+    try:
+        return pool.sample(config, epochs)
+    finally:
+        pool.close()
 
 
 def _noop(_):

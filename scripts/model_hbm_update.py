@@ -1,22 +1,22 @@
 #!/usr/bin/env python
-"""Model of the HBM kernel's per-episode update (th_rl_b200/csrc/thrl_scan_hbm.cuh) checked against the plain sequential
-form of QTable.train_net (th_rl/agents.py:59-78: stale snapshot, live row max, writes in batch order).
+"""Model of the HBM kernel's per-episode update (th_rl_b200/csrc/thrl_scan_hbm.cuh, steps U2-U5) checked against the plain
+sequential form of QTable.train_net (th_rl/agents.py:59-78: stale snapshot, live row max, writes in batch order).
 
-The kernel never walks the batch with a load -> max -> store chain through HBM.  It
-  1. snapshots old[j] = Q[s_j, k_j] for every transition j (before anything is written),
-  2. TAGS every cell the batch will write: the cell temporarily holds a marker carrying the smallest transition index that
-     writes it (atomic max of 1023 - j over a NaN-boxed payload) -- the table itself says which cells are being rewritten,
-  3. gathers the rows of all states of the episode with bulk copies (all loads independent),
-  4. walks the states in order entirely on chip: the gathered row with its tagged cells replaced by their current values
-     cur[canonical index] IS the live row (agents.py:71), so next_max is one reduction; the new value goes to cur[],
-  5. writes cur[] of the canonical transitions back over the tags, and refreshes the greedy-action cache of every touched
-     row exactly: (max, first argmax) over the row's untagged cells (immune to this batch) merged with the final values of
-     its tagged cells.
+The kernel never walks the batch with a load -> max -> store chain through HBM.  Per episode and agent it
+  U2  groups the episode's states by table row (ascending chain per row, the first state is the row's representative),
+  U3  gathers every DISTINCT row once (bulk copies, all independent); per gathered row the transitions of that row are
+      walked in order: the first writer of a cell takes the staged value as the stale snapshot of every writer of the cell
+      and TAGS the staged cell; then (max, first argmax) over the row's untagged cells is taken -- no write of this batch
+      can change it,
+  U4  walks the batch in order on chip: live row max = untagged max of the next state's row merged with the current values
+      of that row's rewritten cells; the new value goes to the slot of the cell's first writer,
+  U5  stores the final value of every rewritten cell and refreshes the greedy action of every touched row from the untagged
+      (max, argmax) and the final values of the rewritten cells.
 This script replays that on random batches with many repeated cells / rows and compares tables and greedy actions.
 """
 import numpy as np
 
-TAG = 1 << 40  # any value no table holds; the payload is added to it
+NONE = 0xFF
 
 
 def reference_update(Q, s, k, r, alpha, gamma):
@@ -31,38 +31,58 @@ def reference_update(Q, s, k, r, alpha, gamma):
 def kernel_update(Q, s, k, r, alpha, gamma):
     Q = Q.copy()
     L = len(k)
-    cur = Q[s[:-1], k].copy()                      # 1. snapshot, one slot per transition
-    for j in range(L):                             # 2. tag: smallest j wins
-        c = Q[s[j], k[j]]
-        Q[s[j], k[j]] = TAG + max(c - TAG if c >= TAG else -1, 1023 - j)
-    rows = [Q[s[t]].copy() for t in range(L + 1)]  # 3. gather (tags included)
-    canon = np.zeros(L, int)
-    base = []
-    for t in range(L + 1):                         # 4. on-chip walk
-        row = rows[t]
-        tagged = row >= TAG
-        idx = (1023 - (row[tagged] - TAG)).astype(int)
-        un = np.where(tagged, -np.inf, row)
-        bm = un.max()
-        ba = int(np.argmax(un)) if np.isfinite(bm) else None
-        base.append((bm, ba))
-        live = max([bm] + [cur[c] for c in idx])
-        if t >= 1:
-            j = t - 1
-            nv = (1 - alpha) * cur[j] + alpha * (r[j] + gamma * live)   # cur[j] is still the snapshot (canonical = first writer)
-            cur[canon[j]] = nv
-        if t < L:
-            canon[t] = int(1023 - (row[k[t]] - TAG))
-    for j in range(L):                             # 5a. write back over the tags
-        if canon[j] == j:
-            Q[s[j], k[j]] = cur[j]
+    # U2: chains through the states of one row, built in descending order (the head ends up being the first state)
+    head, nexts = {}, [NONE] * (L + 1)
+    for t in range(L, -1, -1):
+        nexts[t] = head.get(s[t], NONE)
+        head[s[t]] = t
+    rs = [head[s[t]] for t in range(L + 1)]
+    reps = [t for t in range(L + 1) if rs[t] == t]
+    cur = np.zeros(L)
+    canon = [0] * L
+    nextc = [NONE] * L
+    headc, bm, ba = {}, {}, {}
+    for rep in reps:                               # U3: one gathered copy per distinct row
+        staged = Q[s[rep]].copy()
+        tag = {}
+        h = NONE
+        t = rep
+        while t != NONE and t < L:
+            if k[t] in tag:
+                f = tag[k[t]]
+                cur[t], canon[t] = cur[f], f
+            else:
+                cur[t], canon[t] = staged[k[t]], t
+                tag[k[t]] = t
+                nextc[t], h = h, t
+            t = nexts[t]
+        headc[rep] = h
+        un = np.array([-np.inf if c in tag else staged[c] for c in range(len(staged))])
+        free = [c for c in range(len(staged)) if c not in tag]
+        bm[rep] = un.max()
+        ba[rep] = (int(np.argmax(un)) if np.isfinite(bm[rep]) or free else None) if free else None
+
+    def cells(rep):
+        c = headc[rep]
+        while c != NONE:
+            yield c
+            c = nextc[c]
+
+    for j in range(L):                             # U4
+        rep = rs[j + 1]
+        m = max([bm[rep]] + [cur[c] for c in cells(rep)])
+        nv = (1 - alpha) * cur[j] + alpha * (r[j] + gamma * m)
+        cur[canon[j]] = nv
     greedy = {}
-    for t in range(L + 1):                         # 5b. exact greedy refresh of every row of the episode
-        bm, ba = base[t]
-        cand = [(bm, ba)] if ba is not None else []
-        cand += [(cur[j], k[j]) for j in range(L) if canon[j] == j and s[j] == s[t]]
-        best = max(v for v, _ in cand)
-        greedy[s[t]] = min(c for v, c in cand if v == best)
+    for t in range(L + 1):                         # U5
+        if t < L and canon[t] == t:
+            Q[s[t], k[t]] = cur[t]
+        if rs[t] == t:
+            best, bidx = bm[t], (ba[t] if ba[t] is not None else 1 << 30)
+            for c in cells(t):
+                if cur[c] > best or (cur[c] == best and k[c] < bidx):
+                    best, bidx = cur[c], k[c]
+            greedy[s[t]] = bidx
     return Q, greedy
 
 

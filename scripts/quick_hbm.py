@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""C4 shape (4,096 runs x 8 agents, 1001x101 fp32 tables in HBM): agent-steps/s of the HBM kernel per gather mode / ring depth,
-and of the general kernel, on one GPU.  `python scripts/quick_hbm.py [epochs]`"""
+"""C4 shape (4,096 runs x 8 agents, 1001x101 fp32 tables in HBM): agent-steps/s of the HBM kernel per gather mode / resident warps,
+and of the general kernel, on one GPU.  `python scripts/quick_hbm.py [epochs] [runs] [case ...]`  (case = K=V,K=V)"""
 import os
 import sys
 import time
@@ -15,13 +15,17 @@ E = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 cfg = bench.WORKLOADS["c4"]["config"]
 hp = bench._c4_hp(R, 8)
-cases = [dict(), dict(THRL_HBM_GATHER="cpasync"), dict(THRL_HBM_GATHER="ldg"), dict(THRL_HBM_GATHER="cpasync", THRL_HBM_NB="2"),
-         dict(THRL_HBM_GATHER="cpasync", THRL_HBM_NB="8"), dict(THRL_HBM_NB="8"), dict(THRL_KERNEL="generic")]
+cases = [dict(), dict(THRL_HBM_GATHER="bulk"), dict(THRL_HBM_GATHER="bulk", THRL_HBM_LPR="4"), dict(THRL_KERNEL="generic")]
+if len(sys.argv) > 3:
+    cases = [dict(kv.split("=") for kv in a.split(",") if kv) for a in sys.argv[3:]]
+KEYS = ("THRL_HBM_GATHER", "THRL_HBM_NB", "THRL_HBM_LPR", "THRL_HBM_PF", "THRL_HBM_WARPS", "THRL_KERNEL", "THRL_HBM_NOCNT")
 for env in cases:
-    for k in ("THRL_HBM_GATHER", "THRL_HBM_NB", "THRL_KERNEL"):
+    for k in KEYS:
         os.environ.pop(k, None)
     os.environ.update(env)
     b = engine.RunBatch(cfg, R, seed=0, hp=hp).init_device()
+    if env.get("THRL_HBM_NOCNT"):
+        b.counter = None
     b.scan(30)  # warm the greedy cache / move down the epsilon schedule a little
     torch.cuda.synchronize()
     t = time.perf_counter()

@@ -515,28 +515,40 @@ HBM_CASES = {
     "noisy": (_hbm_cfg([dict(states=999, actions=61)], 33, noise=0.3), {}),
     # longest episode the kernel takes; 16 agents
     "long_wide": (_hbm_cfg([dict(states=100, actions=12, action_range=[0.02, 0.05]) for _ in range(16)], 254), {}),
-    # ring depths: a single staging batch, and more batches than states
-    "ring1": (_hbm_cfg([dict(), dict(actions=33)], 20), {"THRL_HBM_NB": "1"}),
-    "ring8": (_hbm_cfg([dict(), dict(actions=33)], 5), {"THRL_HBM_NB": "8"}),
-    # the comparison path of the gather (16-byte vector loads instead of bulk copies)
-    "ldg": (_hbm_cfg([dict(), dict(actions=33), dict(states=50)], 40), {"THRL_HBM_GATHER": "ldg"}),
-    "cpasync": (_hbm_cfg([dict(), dict(actions=33), dict(states=50)], 40), {"THRL_HBM_GATHER": "cpasync"}),
+    # the staged gather (bulk copies into a shared-memory ring): ring depths -- a single staging batch, more batches than states
+    "ring1": (_hbm_cfg([dict(), dict(actions=33)], 20), {"THRL_HBM_GATHER": "bulk", "THRL_HBM_NB": "1"}),
+    "ring8": (_hbm_cfg([dict(), dict(actions=33)], 5), {"THRL_HBM_GATHER": "bulk", "THRL_HBM_NB": "8"}),
     "bulk": (_hbm_cfg([dict(), dict(actions=33), dict(states=50)], 40), {"THRL_HBM_GATHER": "bulk"}),
+    "bulk_converged": (_hbm_cfg([dict(epsilon=0.0, eps_end=0.0), dict(epsilon=0.0, eps_end=0.0), dict(epsilon=0.02)], 50), {"THRL_HBM_GATHER": "bulk"}),
+    "bulk_ragged": (_hbm_cfg([dict(capacity=37, min_memory=20), dict(min_memory=500, capacity=100), dict(capacity=80, min_memory=80),
+                              dict(states=77, actions=5)], 90), {"THRL_HBM_GATHER": "bulk"}),
+    "bulk_long_wide": (_hbm_cfg([dict(states=100, actions=12, action_range=[0.02, 0.05]) for _ in range(16)], 254), {"THRL_HBM_GATHER": "bulk"}),
+    # ... its comparison path (16-byte vector loads + shared stores instead of bulk copies)
+    "ldg": (_hbm_cfg([dict(), dict(actions=33), dict(states=50)], 40), {"THRL_HBM_GATHER": "ldg"}),
+    # ... lanes per staged row: a whole row per lane (32 rows per batch) ... a quarter-warp per row (4 rows per batch)
+    "lpr1": (_hbm_cfg([dict(), dict(actions=33), dict(states=50, actions=7)], 40), {"THRL_HBM_GATHER": "bulk", "THRL_HBM_LPR": "1"}),
+    "lpr4": (_hbm_cfg([dict(), dict(actions=33), dict(states=50, actions=7)], 40), {"THRL_HBM_GATHER": "bulk", "THRL_HBM_LPR": "4"}),
+    "lpr8": (_hbm_cfg([dict(actions=128), dict(actions=33), dict(states=50, actions=3)], 40),
+             {"THRL_HBM_GATHER": "bulk", "THRL_HBM_LPR": "8", "THRL_HBM_NB": "3"}),
+    # register landing (default): no L2 prefetch, deep prefetch; widest and narrowest rows
+    "reg_pf0": (_hbm_cfg([dict(actions=128), dict(actions=33), dict(states=50, actions=3)], 40), {"THRL_HBM_PF": "0"}),
+    "reg_pf9": (_hbm_cfg([dict(actions=128), dict(actions=33), dict(states=50, actions=3)], 40), {"THRL_HBM_PF": "9"}),
 }
 
 
 @pytest.mark.parametrize("case", sorted(HBM_CASES))
 def test_hbm_kernel_edge_shapes_match_oracle(case, kernel_choice, monkeypatch):
     """Corners of the HBM-resident kernel (thrl_scan_hbm.cuh): batches made of repeated cells / rows, truncated and missing
-    batches, demand noise, the longest episode, staging-ring depths, both gather paths; fp32 and f64 tables, chunked calls."""
+    batches, demand noise, the longest episode, staging-ring depths, both gather paths, every lanes-per-row split; fp32 and
+    f64 tables, chunked calls."""
     from th_rl_b200 import _lib
     if kernel_choice != "auto":
         pytest.skip("the general kernel is held to the same oracle by the other tests")
     cfg, env = HBM_CASES[case]
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    R = 6 if case == "long_wide" else 20
-    _philox_case(cfg, R, 5, np.float32, seed=61, run_id0=9, hp=(case in ("ragged", "live_max")), chunks=[2, 3] if case in ("converged", "ragged") else None)
+    R = 6 if case.endswith("long_wide") else 20
+    _philox_case(cfg, R, 5, np.float32, seed=61, run_id0=9, hp=(case in ("ragged", "bulk_ragged", "live_max")), chunks=[2, 3] if case in ("converged", "ragged", "bulk_ragged") else None)
     assert _lib.last_kernel() == "hbm", _lib.last_kernel()
     _philox_case(cfg, R, 3, np.float64, seed=62)
     assert _lib.last_kernel() == "hbm", _lib.last_kernel()

@@ -316,3 +316,11 @@ def test_greedy_cache_carry_rules_are_exact():
         got = k if (x > rm or (x == rm and k < ra)) else ra
         assert got == int(np.argmax(row)), (row, k, x, rm, ra)
     assert unknown < 1200  # only a lowered maximum under a repeated state loses the entry
+
+
+def test_hbm_update_model_equals_sequential_train_net():
+    """scripts/model_hbm_update.py: the HBM kernel's update (row groups, first-writer tags on the gathered copy, untagged
+    max + rewritten-cell lists, exact greedy refresh) == the sequential form of agents.py:59-78 on random batches."""
+    import runpy
+    runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "model_hbm_update.py"),
+                   run_name="__main__")

@@ -236,7 +236,7 @@ bool plan_hbm(thrl::HbmParams* p, size_t elem, const DeviceInfo& dev, int* warps
   const int n = G.n_agents, T = G.max_steps, esz = (int)elem;
   if (G.mlp_stride > 0 || !G.regular || T > thrl::kHbmMaxT || G.run_stride % 4) return false;
   if (G.run_stride * (long long)elem < THRL_PAD_THRESHOLD_BYTES) return false;  // small tables are staged in shared memory
-  int lut = 0, rows = 0, slot = 0;
+  int lut = 0, rows = 0, rowbytes = 0;
   double lo_sum = 0.0;
   bool bounded = G.a >= 0.0 && G.b > 0.0;
   for (int i = 0; i < n; ++i) {
@@ -246,6 +246,7 @@ bool plan_hbm(thrl::HbmParams* p, size_t elem, const DeviceInfo& dev, int* warps
     if (!(lo >= 0.0)) bounded = false;
     lo_sum += lo;
   }
+  p->ncls = 0;
   for (int i = 0; i < n; ++i) {
     const ThrlAgentSpec& s = G.agent[i];
     // rows the price can reach: price <= a - a * sum_i min(action_range_i) (environments.py:25-32 with new_a <= a), +2 rows
@@ -259,71 +260,127 @@ bool plan_hbm(thrl::HbmParams* p, size_t elem, const DeviceInfo& dev, int* warps
     }
     p->gcap[i] = cap;
     p->goff[i] = rows;
-    p->loff[i] = lut;
     p->L[i] = s.min_memory > s.capacity ? 0 : (T < s.capacity ? T : s.capacity);
     rows += cap;
-    lut += s.actions;
-    if (s.row_stride * esz > slot) slot = s.row_stride * esz;
+    // agents with the same action grid share one action LUT (AQ / XT)
+    p->lut_owner[i] = i;
+    for (int j = 0; j < i; ++j)
+      if (G.agent[j].actions == s.actions && G.agent[j].action_lo == s.action_lo && G.agent[j].action_hi == s.action_hi) {
+        p->lut_owner[i] = p->lut_owner[j];
+        break;
+      }
+    if (p->lut_owner[i] == i) {
+      p->loff[i] = lut;
+      lut += s.actions;
+    } else {
+      p->loff[i] = p->loff[p->lut_owner[i]];
+    }
+    if (s.row_stride * esz > rowbytes) rowbytes = s.row_stride * esz;
+    // state class: agents whose float64 encode (max_state, states) and batch (its length) coincide see the same rows
+    p->cls_of[i] = -1;
+    if (p->L[i] > 0) {
+      for (int j = 0; j < i && p->cls_of[i] < 0; ++j)
+        if (p->L[j] == p->L[i] && G.agent[j].states == s.states && G.agent[j].max_state == s.max_state) p->cls_of[i] = p->cls_of[j];
+      if (p->cls_of[i] < 0) p->cls_of[i] = p->ncls++;
+    }
+  }
+  for (int c = 0, k = 0; c < p->ncls; ++c) {
+    p->cls_beg[c] = k;
+    for (int i = 0; i < n; ++i)
+      if (p->cls_of[i] == c) p->cls_agent[k++] = i;
+    p->cls_na[c] = k - p->cls_beg[c];
   }
   p->lut_total = lut;
   p->rows_total = rows;
-  p->slot_bytes = slot;
+  p->nch_max = rowbytes / 16;
   p->Tp = align_up(T, 4);
   p->Sp = align_up(T + 1, 4);
-  p->cta_bytes = align_up(2 * lut * 8 + n * 8 * 4, 128);
-  const int Tp = p->Tp, Sp = p->Sp;
-  auto layout = [&](int nb) {
+  p->cta_bytes = align_up(2 * lut * 8 + n * thrl::kHbmAgc * 4, 128);
+  const char* gmode = getenv("THRL_HBM_GATHER");  // reg (default) | bulk | ldg
+  p->staged = (gmode && (strcmp(gmode, "bulk") == 0 || strcmp(gmode, "ldg") == 0)) ? 1 : 0;
+  p->bulk = (gmode && strcmp(gmode, "ldg") == 0) ? 0 : 1;
+  p->pf_dist = 2;
+  if (const char* f = getenv("THRL_HBM_PF")) p->pf_dist = atoi(f) < 0 ? 0 : (atoi(f) > 16 ? 16 : atoi(f));
+  const int Tp = p->Tp, Sp = p->Sp, nc = p->ncls > 0 ? p->ncls : 1;
+  auto layout = [&](int nb, int lpr_shift) {
+    const int lpr = 1 << lpr_shift, rb = 32 >> lpr_shift;
+    // a quarter-warp reads 8 / lpr rows x lpr consecutive 16-byte chunks (8 rows x 1 chunk each for lpr = 1): distinct
+    // banks when the slot stride is = lpr (mod 8) chunks
+    int chunks = rowbytes / 16;
+    while (chunks % 8 != lpr % 8) ++chunks;
+    p->slot_bytes = chunks * 16;
+    p->lpr_shift = lpr_shift;
     int o = 0;
-    p->off_bar = o;   o += thrl::kHbmMaxNb * 8;
+    p->off_bar = o;   o += p->staged ? thrl::kHbmMaxNb * 8 : 0;
     p->off_g = o;     o += align_up(rows, 16);
     p->off_P = o;     o += align_up((T + 1) * 8, 16);
-    p->off_act = o;   o += align_up(n * Tp, 16);
     p->off_hp = o;    o += align_up(n * 5 * 8, 16);
-    p->off_srow = o;  o += align_up(n * Sp * 2, 16);
+    p->off_miss = o;  o += 2 * THRL_MAX_AGENTS;
+    p->off_srow = o;  o += align_up(nc * Sp * 2, 16);
+    p->off_rs = o;    o += align_up(nc * Sp, 16);
+    p->off_next = o;  o += align_up(nc * Sp, 16);
+    p->off_dl = o;    o += align_up(nc * Sp, 16);
+    p->off_act = o;   o += align_up(n * Tp, 16);
     p->off_cur = o;   o += align_up(n * Tp * esz, 16);
     p->off_canon = o; o += align_up(n * Tp, 16);
+    p->off_nextc = o; o += align_up(n * Tp, 16);
     p->off_bm = o;    o += align_up(n * Sp * esz, 16);
-    p->off_ba = o;    o += align_up(n * Sp, 16);
-    o = align_up(o, 128);
     p->off_stage = o;
     p->off_pre = o;
-    p->off_newa = o + align_up(T * n * 2, 16);
-    const int draws = align_up(T * n * 2, 16) + (p->noisy ? T * 8 : 0);
-    p->off_rs = o;
-    p->off_vkey = o + align_up(n * Sp, 16);
-    p->off_cmin = p->off_vkey + align_up(n * Sp * esz, 16);
-    const int merge = align_up(n * Sp, 16) + align_up(n * Sp * esz, 16) + n * Sp * 4;
-    const int ring = nb * n * slot;
-    o += std::max(ring, std::max(draws, merge));
+    p->off_newa = o + align_up(T * n, 16);
+    p->off_rq = o;
+    p->off_mask = o;
+    const int draws = align_up(T * n, 16) + (p->noisy ? T * 8 : 0);
+    const int ring = p->staged ? nb * rb * p->slot_bytes : 32 * 16;  // register landing: the column masks of one batch
+    int region = std::max(ring, std::max(draws, n * 8));
+    region = align_up(region, 16);
+    p->seg = region / (n * 8) < T ? region / (n * 8) : T;  // steps whose reward / max_steps fit the region at a time
+    o += region;
     p->nb = nb;
-    p->warp_bytes = align_up(o, 128);
+    p->warp_bytes = align_up(o, 16);
     return p->warp_bytes;
   };
   const int avail = dev.smem_optin - p->cta_bytes;
-  int nb = 3;
-  if (avail / layout(nb) < 1) nb = 2;
-  int w = avail / layout(nb);
-  if (w < 1) return false;
-  if (w > 16) w = 16;
-  {  // the rounds of the persistent grid are fixed by what fits; a deeper ring that still fits them costs nothing
-    const long long slots = (long long)dev.sms * w;
-    const long long rounds = (p->n_runs + slots - 1) / slots;
-    const long long per_round = (p->n_runs + rounds - 1) / rounds;
-    int wneed = (int)((per_round + dev.sms - 1) / dev.sms);
-    if (wneed < 1) wneed = 1;
-    const char* force = getenv("THRL_HBM_NB");
-    if (force && atoi(force) >= 1 && atoi(force) <= thrl::kHbmMaxNb) {
-      nb = atoi(force);
-      if (avail / layout(nb) < 1) return false;
-    } else {
-      while (nb < thrl::kHbmMaxNb && nb < T + 1 && (long long)layout(nb + 1) * wneed <= avail) ++nb;
-      layout(nb);
+  int w;
+  if (!p->staged) {
+    // Rows pass through L1 lines on their way to the registers: keep the CTA within the 196 KB shared-memory carve-out so that
+    // 60 KB of L1 are left for the loads in flight (measured on the C4 shape: 12 resident runs per SM reach 5.8e9 agent-steps/s,
+    // 13 -- which need the 228 KB carve-out -- 4.1e9).
+    const int carve = 196 * 1024 - 1024;  // the driver reserves 1 KB per CTA
+    const int budget = (avail < carve - p->cta_bytes ? avail : carve - p->cta_bytes);
+    w = budget / layout(1, 1);
+  } else {
+    int lpr_shift = 1;  // two lanes per staged row, 16 rows per batch
+    if (const char* f = getenv("THRL_HBM_LPR")) {
+      const int v = atoi(f);
+      if (v == 1) lpr_shift = 0; else if (v == 2) lpr_shift = 1; else if (v == 4) lpr_shift = 2; else if (v == 8) lpr_shift = 3;
     }
-    w = avail / p->warp_bytes;
-    if (w > 16) w = 16;
+    while (lpr_shift < 3 && avail / layout(2, lpr_shift) < 1) ++lpr_shift;  // smaller batches when even two do not fit
+    int nb = 2;
+    if (avail / layout(nb, lpr_shift) < 1) nb = 1;
+    w = avail / layout(nb, lpr_shift);
+    if (w >= 1) {  // the rounds of the persistent grid are fixed by what fits; a deeper ring that still fits them costs nothing
+      if (w > thrl::kHbmMaxWarps) w = thrl::kHbmMaxWarps;
+      const long long slots = (long long)dev.sms * w;
+      const long long rounds = (p->n_runs + slots - 1) / slots;
+      const long long per_round = (p->n_runs + rounds - 1) / rounds;
+      int wneed = (int)((per_round + dev.sms - 1) / dev.sms);
+      if (wneed < 1) wneed = 1;
+      const char* force = getenv("THRL_HBM_NB");
+      if (force && atoi(force) >= 1 && atoi(force) <= thrl::kHbmMaxNb) {
+        nb = atoi(force);
+        if (avail / layout(nb, lpr_shift) < 1) return false;
+      } else {
+        while (nb < thrl::kHbmMaxNb && nb < 4 && (long long)layout(nb + 1, lpr_shift) * wneed <= avail) ++nb;
+        layout(nb, lpr_shift);
+      }
+      w = avail / p->warp_bytes;
+    }
   }
-  const char* g = getenv("THRL_HBM_GATHER");
-  p->bulk = (g && strcmp(g, "ldg") == 0) ? 0 : ((g && strcmp(g, "cpasync") == 0) ? 2 : 1);
+  if (w < 1) return false;
+  if (w > thrl::kHbmMaxWarps) w = thrl::kHbmMaxWarps;
+  if (const char* f = getenv("THRL_HBM_WARPS"))
+    if (atoi(f) >= 1 && atoi(f) < w) w = atoi(f);
   *warps = w;
   return true;
 }
@@ -331,20 +388,21 @@ bool plan_hbm(thrl::HbmParams* p, size_t elem, const DeviceInfo& dev, int* warps
 template <typename QT>
 int launch_hbm(thrl::HbmParams& p, int warps, const DeviceInfo& dev, cudaStream_t stream) {
   int grid = dev.sms;
+  const long long capacity = (long long)dev.sms * warps;  // runs resident at once when the launch is large enough
   {  // every warp plays whole runs one after another: spread the runs evenly over the rounds that are needed anyway
     const long long slots = (long long)dev.sms * warps;
     const long long rounds = (p.n_runs + slots - 1) / slots;
     const long long per_round = (p.n_runs + rounds - 1) / rounds;
     warps = (int)((per_round + dev.sms - 1) / dev.sms);
     if (warps < 1) warps = 1;
-    grid = (int)((per_round + warps - 1) / warps);
-    if (grid > dev.sms) grid = dev.sms;
+    grid = per_round < dev.sms ? (int)per_round : dev.sms;  // partial warps of a round are spread over all SMs (slot = warp * grid + cta)
+    p.per_round = per_round;
   }
   const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
-  auto kern = thrl::qtable_scan_hbm<QT>;
+  auto kern = p.staged ? thrl::qtable_scan_hbm<QT, true> : thrl::qtable_scan_hbm<QT, false>;
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_last_kernel = "hbm";
-  g_last_wave = (long long)grid * warps;
+  g_last_wave = capacity;
   kern<<<grid, warps * 32, smem, stream>>>(p);
   CUDA_TRY(cudaGetLastError());
   g_launches.fetch_add(1);

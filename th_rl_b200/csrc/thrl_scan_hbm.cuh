@@ -2,23 +2,29 @@
 //
 // One warp plays one run, persistent grid.  The rollout (trainer.py:50-67) acts from an exact greedy-action cache in
 // shared memory, so it touches HBM only on the first visit of a table row.  QTable.train_net (agents.py:59-78: stale
-// snapshot, live row max, writes in batch order) is NOT executed as a load -> max -> store chain through memory.  Per
-// episode and agent the kernel
-//   1. snapshots old[j] = Q[s_j, k_j] of every transition (scattered 4-byte loads, all independent) and counts the visit,
-//   2. TAGS every cell the batch will write: an atomic max leaves a NaN-boxed marker in the cell that carries the smallest
-//      transition index writing it -- the table itself now says which cells are being rewritten and by whom,
-//   3. gathers the rows of all states of the episode with 1-D bulk copies (cp.async.bulk, one 16-byte-aligned padded row
-//      = one copy, completion on an mbarrier) into a ring of staging slots: every load is independent of every other, a
-//      warp keeps `nb` x n_agents rows in flight,
-//   4. walks the states in order entirely on chip: the staged row with its tagged cells replaced by their current values
-//      cur[canonical transition] IS the live row of agents.py:71, so next_max is one warp reduction; the new value goes
-//      to cur[] (shared memory),
-//   5. stores cur[] of the canonical transitions over the tags, and refreshes the greedy-action cache of every touched
-//      row exactly: (max, first argmax) over the row's untagged cells -- which no write of this batch can change -- merged
-//      with the final values of its tagged cells.
-// scripts/model_hbm_update.py replays steps 1-5 on random batches against the plain sequential form.
-// HBM traffic per agent-step: the bootstrap row (row_stride * 4 B, once), one sector for the cell and one for the
-// counter; the greedy row read of SURVEY 8(d)'s algorithmic count is served by the cache.
+// snapshot, live row max, writes in batch order) is NOT executed as a load -> max -> store chain through memory:
+//
+//   U1  float64 encodes of the episode's states (agents.py:62,66), once per *state class* (agents that share max_state,
+//       states and batch length see the same rows), lane = state.
+//   U2  the states are grouped by table row: a chain through the states of one row in ascending order, its first state
+//       is the row's representative.  Only DISTINCT rows are gathered.
+//   U3  the distinct rows of every agent are fetched from HBM with 1-D bulk copies (cp.async.bulk: one 16-byte aligned
+//       padded row = one copy issued by one lane, completion counted in bytes on an mbarrier) into a ring of staging
+//       batches in shared memory; every copy is independent of every other, `nb` batches are in flight per warp.
+//       When a batch lands, one lane per row walks the row's transitions in order: the staged cell is the stale
+//       snapshot (agents.py:67) of the first transition that writes it, which then TAGS the staged cell (a NaN-boxed
+//       transition index) -- later writers of the cell find the tag and share the first writer's slot.  Then `lpr`
+//       lanes per row scan the staged row for (max, first argmax) over its UNTAGGED cells: a hardware float compare
+//       never selects a NaN, so the tags drop out for free.  That pair cannot be changed by any write of this batch.
+//   U4  lane = agent walks its transitions in order entirely on chip: the live row max of agents.py:71 is the untagged
+//       maximum of the next state's row merged with the current values of that row's rewritten cells (a short list);
+//       the new value goes to the cell's slot in shared memory.
+//   U5  the final value of every rewritten cell is stored to HBM (one 4-byte store per distinct cell), visit counters
+//       get fire-and-forget REDs, and the greedy-action cache of every touched row is refreshed exactly from the
+//       untagged (max, argmax) and the final values of the row's rewritten cells.
+// scripts/model_hbm_update.py replays U2-U5 on random batches against the plain sequential form.
+// HBM traffic per agent-step: at most one padded row (row_stride * 4 B; less when states repeat), one sector for the
+// cell store and one for the counter; the greedy row read of SURVEY 8(d)'s algorithmic count is served by the cache.
 //
 // Applies to: Q-table agents only, regular games (every agent's batch is the newest min(T, capacity) transitions of the
 // episode), max_steps <= 254, <= 128 actions, padded slab layout (include/thrl.h ThrlAgentSpec.row_stride).  Everything
@@ -29,11 +35,13 @@
 namespace thrl {
 
 constexpr int kHbmMaxT = 254;   // transition / state indices fit one byte next to 0xFF = none
-constexpr int kHbmMaxNb = 8;    // staging ring depth (batches of n rows)
+constexpr int kHbmMaxNb = 8;    // staging ring depth (batches)
+constexpr int kHbmAgc = 17;     // ints per agent in the CTA-shared constant block (odd: lanes that read different agents' entries hit different banks)
+constexpr int kHbmMaxWarps = 14;  // resident runs per CTA: 448 threads leave 146 registers per thread
 
 struct HbmParams {
   ThrlGame game;
-  long long n_runs, run_id0;
+  long long n_runs, run_id0, per_round;  // per_round: runs played at a time (balanced over the rounds that are needed anyway)
   int epoch_begin, E, rng_mode;
   uint32_t k0, k1;
   void* q;
@@ -53,18 +61,30 @@ struct HbmParams {
   double* trace_prices;
   // per agent: rows with a greedy-cache slot, offsets into the cache / the action LUT, batch length (0 = never updates)
   int gcap[THRL_MAX_AGENTS], goff[THRL_MAX_AGENTS], loff[THRL_MAX_AGENTS], L[THRL_MAX_AGENTS];
+  // state classes: agents with equal (max_state, states, batch length) share encodes, row groups and gather order
+  int ncls;
+  int cls_of[THRL_MAX_AGENTS];     // class of agent i (-1: the agent never updates)
+  int cls_beg[THRL_MAX_AGENTS];    // class c's agents are cls_agent[cls_beg[c] .. cls_beg[c] + cls_na[c])
+  int cls_na[THRL_MAX_AGENTS];
+  int cls_agent[THRL_MAX_AGENTS];
+  int lut_owner[THRL_MAX_AGENTS];  // first agent with the same action grid: they share one action LUT
   int lut_total, rows_total;
-  int noisy;     // new_a varies per step
-  int bulk;      // how rows are staged: 1 = cp.async.bulk (TMA unit), 2 = cp.async 16-byte copies (LSU, no registers),
-                 // 0 = 16-byte vector loads + shared stores (comparison)
-  int nb;        // staging ring depth
-  int slot_bytes;  // one staged row
-  int Tp, Sp;    // padded strides of the [n][T] / [n][T+1] per-agent arrays (elements)
+  int noisy;       // new_a varies per step
+  int staged;      // 1: rows are staged in shared memory (bulk copies); 0: rows land in registers (16-byte vector loads, L2 prefetch)
+  int bulk;        // staged rows arrive by: 1 = cp.async.bulk (TMA unit); 0 = 16-byte vector loads + shared stores (comparison)
+  int pf_dist;     // register landing: batches prefetched into L2 ahead of the one being loaded
+  int nch_max;     // register landing: 16-byte chunks of the longest row
+  int seg;         // steps whose reward / max_steps are divided at a time (U4)
+  int nb;          // staging ring depth (batches)
+  int lpr_shift;   // lanes per row = 1 << lpr_shift; a batch holds 32 >> lpr_shift rows
+  int slot_bytes;  // one staged row (padded so that the lanes of a quarter-warp hit distinct banks)
+  int Tp, Sp;      // padded strides of the [.][T] / [.][T+1] arrays (elements)
   // shared memory (bytes): [cta_bytes][warp 0][warp 1]...
   int cta_bytes, warp_bytes;
-  int off_bar, off_g, off_P, off_act, off_hp, off_srow, off_cur, off_canon, off_bm, off_ba, off_stage;
-  // regions that alias the staging ring: the rollout's draws (before the update), the greedy merge (after the walk)
-  int off_pre, off_newa, off_rs, off_vkey, off_cmin;
+  int off_bar, off_g, off_P, off_hp, off_miss, off_mask, off_srow, off_rs, off_next, off_dl, off_act, off_cur, off_canon, off_nextc,
+      off_bm, off_stage;
+  // regions that alias the staging ring: the rollout's draws (before the update), reward / max_steps (after the gather)
+  int off_pre, off_newa, off_rq;
 };
 
 // ---------------------------------------------------------------- PTX: mbarrier + 1-D bulk copy (TMA unit, no descriptor)
@@ -88,85 +108,145 @@ __device__ __forceinline__ void hbm_mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   } while (!done);
 }
-// per-thread 16-byte asynchronous copy global -> shared that bypasses L1 (it must see the tags), and the mbarrier arrival
-// that fires once all of this thread's earlier copies have landed
-__device__ __forceinline__ void hbm_cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(hbm_smem_addr(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void hbm_cp_async_arrive(uint64_t* bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(hbm_smem_addr(bar)) : "memory");
-}
 __device__ __forceinline__ void hbm_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(hbm_smem_addr(dst)),
                "l"(src), "r"(bytes), "r"(hbm_smem_addr(bar))
                : "memory");
 }
-// generic-proxy accesses (the tags in global memory, this warp's use of the staging ring in shared memory) are ordered
-// before the async-proxy accesses of the bulk copies issued after the fence
+// generic-proxy accesses (this warp's table stores in global memory, its use of the staging ring in shared memory) are
+// ordered before the async-proxy accesses of the bulk copies issued after the fence
 __device__ __forceinline__ void hbm_fence_proxy_async() {
   asm volatile("fence.proxy.async.global;\n\tfence.proxy.async.shared::cta;" ::: "memory");
 }
+__device__ __forceinline__ void hbm_fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---------------------------------------------------------------- tags: NaN-boxed transition indices
-// A tagged cell holds kBase | (1023 - j): a negative quiet NaN, above every number (and -inf) as an unsigned integer, so
-// one unsigned atomic max both installs the tag over the value and keeps the SMALLEST j among the transitions that write
-// the cell.  The update arithmetic never produces such a bit pattern (its NaNs, should inputs be NaN, are positive).
+// A tagged staged cell holds kBase | t: a negative quiet NaN.  `v > best` is false for it, so the row scan skips tagged
+// cells without testing for them; as an unsigned integer it lies above every number (and -inf).  The update arithmetic
+// never produces such a bit pattern (its NaNs, should inputs be NaN, are positive).
 template <typename QT> struct HbmBits;
 template <> struct HbmBits<float> {
   using U = uint32_t;
   static constexpr U kBase = 0xFFC00000u;
   __device__ static U of(float v) { return __float_as_uint(v); }
-  __device__ static U key(float v) {  // order-preserving, -0 folded onto +0 (numpy compares them equal)
-    const U b = __float_as_uint(v == 0.0f ? 0.0f : v);
-    return (b >> 31) ? ~b : (b | 0x80000000u);
-  }
+  __device__ static float val(U b) { return __uint_as_float(b); }
 };
 template <> struct HbmBits<double> {
   using U = unsigned long long;
   static constexpr U kBase = 0xFFF8000000000000ull;
   __device__ static U of(double v) { return (U)__double_as_longlong(v); }
-  __device__ static U key(double v) { return dkey(v == 0.0 ? 0.0 : v); }
+  __device__ static double val(U b) { return __longlong_as_double((long long)b); }
 };
 
-// this lane's four columns 4*lane .. 4*lane+3 of a 16-byte aligned row (shared or global memory)
-__device__ __forceinline__ void hbm_load4(const float* row, int lane, float (&v)[4]) {
-  const float4 x = *reinterpret_cast<const float4*>(row + 4 * lane);
+// one 16-byte chunk of a row: 4 floats / 2 doubles
+template <bool kGlobal> __device__ __forceinline__ void hbm_chunk(const float* row, int c, float (&v)[4]) {
+  const float4* p = reinterpret_cast<const float4*>(row) + c;
+  const float4 x = kGlobal ? __ldcg(p) : *p;
   v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
 }
-__device__ __forceinline__ void hbm_load4(const double* row, int lane, double (&v)[4]) {
-  const double2 x = *reinterpret_cast<const double2*>(row + 4 * lane), y = *reinterpret_cast<const double2*>(row + 4 * lane + 2);
-  v[0] = x.x; v[1] = x.y; v[2] = y.x; v[3] = y.y;
+template <bool kGlobal> __device__ __forceinline__ void hbm_chunk(const double* row, int c, double (&v)[2]) {
+  const double2* p = reinterpret_cast<const double2*>(row) + c;
+  const double2 x = kGlobal ? __ldcg(p) : *p;
+  v[0] = x.x; v[1] = x.y;
 }
 
-template <typename QT>
-__global__ void __launch_bounds__(512, 1) qtable_scan_hbm(const __grid_constant__ HbmParams p) {
+// (max, first argmax) over columns [0, A) of a 16-byte aligned row, NaNs (= tags) skipped.  The lanes q = 0 .. lpr-1 of a
+// group take the 16-byte chunks q, q + lpr, ... (a quarter-warp reads consecutive chunks: conflict-free on the padded
+// staging slots); two independent compare chains per lane, merged by (value, then smaller column); then a butterfly over
+// the group, after which every lane of the group holds the result.  bidx = 0xffffffff: no column holds a value > -inf.
+template <typename QT, bool kGlobal>
+__device__ __forceinline__ void hbm_scan_row(const QT* row, int A, int q, int lpr, bool active, QT& best, unsigned& bidx) {
+  constexpr int EPC = 16 / (int)sizeof(QT);
+  constexpr unsigned kNone = 0xffffffffu;
+  QT b0 = NegInf<QT>::v(), b1 = NegInf<QT>::v();
+  unsigned i0 = kNone, i1 = kNone;
+  if (active) {
+    const int nfull = A / EPC;
+    int c = q;
+    for (; c + lpr < nfull; c += 2 * lpr) {
+      QT v[EPC], w[EPC];
+      hbm_chunk<kGlobal>(row, c, v);
+      hbm_chunk<kGlobal>(row, c + lpr, w);
+#pragma unroll
+      for (int e = 0; e < EPC; ++e) {  // ascending columns, strict >: first maximal index (agents.py:88)
+        if (v[e] > b0) { b0 = v[e]; i0 = (unsigned)(c * EPC + e); }
+        if (w[e] > b1) { b1 = w[e]; i1 = (unsigned)((c + lpr) * EPC + e); }
+      }
+    }
+    if (c < nfull) {
+      QT v[EPC];
+      hbm_chunk<kGlobal>(row, c, v);
+#pragma unroll
+      for (int e = 0; e < EPC; ++e)
+        if (v[e] > b0) { b0 = v[e]; i0 = (unsigned)(c * EPC + e); }
+    }
+    if (b1 > b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+    if (nfull * EPC < A && (nfull & (lpr - 1)) == q) {  // the partial last chunk: padding cells are not values
+      QT v[EPC];
+      hbm_chunk<kGlobal>(row, nfull, v);
+#pragma unroll
+      for (int e = 0; e < EPC; ++e)
+        if (nfull * EPC + e < A && v[e] > b0) { b0 = v[e]; i0 = (unsigned)(nfull * EPC + e); }  // highest columns: after the merge
+    }
+  }
+  for (int off = 1; off < lpr; off <<= 1) {
+    const QT ob = shfl_xor_t(b0, off);
+    const unsigned oi = __shfl_xor_sync(kFull, i0, off);
+    if (ob > b0 || (ob == b0 && oi < i0)) { b0 = ob; i0 = oi; }
+  }
+  best = b0;
+  bidx = i0;
+}
+
+// ---------------------------------------------------------------- register landing (kStaged = false)
+// lanes per row and 16-byte chunk slots per lane are compile-time so that a row lives in registers: fp32 rows (<= 128 columns =
+// 32 chunks) take 2 lanes x 16 slots, f64 rows (64 chunks) 4 lanes x 16 slots; lanes-per-row x elements-per-chunk = 8 either way
+template <typename QT> struct HbmReg {
+  static constexpr int kLprShift = sizeof(QT) == 4 ? 1 : 2;
+  static constexpr int kLpr = 1 << kLprShift;
+  static constexpr int kRows = 32 >> kLprShift;  // rows per batch
+  static constexpr int kEpc = 16 / (int)sizeof(QT);
+  static constexpr int kSlots = 16;
+};
+__device__ __forceinline__ void hbm_prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
+
+template <typename QT, bool kStaged>
+__global__ void __launch_bounds__(32 * kHbmMaxWarps, 1) qtable_scan_hbm(const __grid_constant__ HbmParams p) {
   using B = HbmBits<QT>;
   using U = typename B::U;
+  using R = HbmReg<QT>;
   extern __shared__ __align__(128) unsigned char smem_hbm[];
   unsigned char* const smem = smem_hbm;
   const ThrlGame& G = p.game;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
   const int n = G.n_agents, T = G.max_steps, E = p.E, Tp = p.Tp, Sp = p.Sp, nb = p.nb;
+  const int lpr_shift = kStaged ? p.lpr_shift : R::kLprShift;
+  const int lpr = 1 << lpr_shift, rb = 32 >> lpr_shift;     // lanes per gathered row, rows per batch
+  const int grp = lane >> lpr_shift, qq = lane & (lpr - 1);  // this lane's row of the batch and its part of the row
   const bool is_agent = lane < n;
   constexpr unsigned kNone = 0xffffffffu;
 
   // ---- CTA-shared: AQ[k] = (a/b)*scale(k), XT[k] = scale(k)/max_steps per agent, and the per-agent constants of the update
   double* lutAQ = reinterpret_cast<double*>(smem);
   double* lutXT = lutAQ + p.lut_total;
-  int* agc = reinterpret_cast<int*>(lutXT + p.lut_total);  // [n][8]: table offset, row stride, actions, lut offset, cache offset, cache rows, t0, L
+  int* agc = reinterpret_cast<int*>(lutXT + p.lut_total);  // [n][kHbmAgc]: table offset, row stride, actions, lut offset, cache offset,
+                                                           // cache rows, t0, L, class, -, -, -, 4 words: columns >= actions
   {
     const double ab = __ddiv_rn(G.a, G.b);  // environments.py:23 self.a/self.b
     for (int i = 0; i < n; ++i) {
       const ThrlAgentSpec& s = G.agent[i];
-      for (int k = threadIdx.x; k < s.actions; k += blockDim.x) {
-        const double x = scale_action(k, s.actions, s.action_lo, s.action_hi);
-        lutAQ[p.loff[i] + k] = __dmul_rn(ab, x);
-        lutXT[p.loff[i] + k] = __ddiv_rn(x, (double)T);  // trainer.py:66 scaled_acts / max_steps
-      }
+      if (p.lut_owner[i] == i)
+        for (int k = threadIdx.x; k < s.actions; k += blockDim.x) {
+          const double x = scale_action(k, s.actions, s.action_lo, s.action_hi);
+          lutAQ[p.loff[i] + k] = __dmul_rn(ab, x);
+          lutXT[p.loff[i] + k] = __ddiv_rn(x, (double)T);  // trainer.py:66 scaled_acts / max_steps
+        }
       if (threadIdx.x == 0) {
-        int* a = agc + i * 8;
+        int* a = agc + i * kHbmAgc;
         a[0] = (int)s.table_offset; a[1] = s.row_stride; a[2] = s.actions; a[3] = p.loff[i];
-        a[4] = p.goff[i]; a[5] = p.gcap[i]; a[6] = T - p.L[i]; a[7] = p.L[i];
+        a[4] = p.goff[i]; a[5] = p.gcap[i]; a[6] = T - p.L[i]; a[7] = p.L[i]; a[8] = p.cls_of[i];
+        for (int w = 0; w < 4; ++w)
+          a[12 + w] = (int)(s.actions >= 32 * w + 32 ? 0u : (s.actions <= 32 * w ? 0xffffffffu : (0xffffffffu << (s.actions - 32 * w))));
       }
     }
   }
@@ -174,46 +254,56 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_hbm(const __grid_constant_
 
   // ---- this warp's slot
   unsigned char* slot = smem + p.cta_bytes + (size_t)warp * p.warp_bytes;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(slot + p.off_bar);          // [nb] one mbarrier per staging batch
-  uint8_t* Gc = slot + p.off_g;                                            // greedy action per (agent,row); 0xFF = unknown
-  double* P = reinterpret_cast<double*>(slot + p.off_P);                   // [T+1] prices of the episode, P[0] = state it starts from
-  uint8_t* act = slot + p.off_act;                                         // [n][Tp] chosen actions
-  double* hpw = reinterpret_cast<double*>(slot + p.off_hp);                // [n][5] alpha,gamma,eps_end,eps_step,eps
-  uint16_t* srow = reinterpret_cast<uint16_t*>(slot + p.off_srow);         // [n][Sp] float64 encode of every state (agents.py:62,66)
-  QT* cur = reinterpret_cast<QT*>(slot + p.off_cur);                       // [n][Tp] snapshot, then live values of the canonical cells
-  uint8_t* canon = slot + p.off_canon;                                     // [n][Tp] first transition of the batch that writes the same cell
-  QT* bm = reinterpret_cast<QT*>(slot + p.off_bm);                         // [n][Sp] max over the untagged cells of the state's row
-  uint8_t* ba = slot + p.off_ba;                                           // [n][Sp] its first column (0xFF: every column is tagged)
-  unsigned char* stage = slot + p.off_stage;                               // [nb][n][slot_bytes] staged rows
-  int16_t* pre = reinterpret_cast<int16_t*>(slot + p.off_pre);             // [T][n] forced action or -1 (= greedy)       } alias
-  double* newa = reinterpret_cast<double*>(slot + p.off_newa);             // [T] demand intercept (noisy only)            } the
-  uint8_t* rs = slot + p.off_rs;                                           // [n][Sp] state that represents the row        } staging
-  U* vkey = reinterpret_cast<U*>(slot + p.off_vkey);                       // [n][Sp] ordered key of the row's final max   } ring
-  uint32_t* cmin = reinterpret_cast<uint32_t*>(slot + p.off_cmin);         // [n][Sp] its first column                     }
+  uint64_t* bar = reinterpret_cast<uint64_t*>(slot + p.off_bar);     // [nb] one mbarrier per staging batch
+  uint8_t* Gc = slot + p.off_g;                                       // greedy action per (agent,row); 0xFF = unknown
+  double* P = reinterpret_cast<double*>(slot + p.off_P);              // [T+1] prices of the episode, P[0] = state it starts from
+  double* hpw = reinterpret_cast<double*>(slot + p.off_hp);           // [n][5] alpha,gamma,eps_end,eps_step,eps
+  uint8_t* missk = slot + p.off_miss;                                 // [16] greedy action found by a cache miss
+  uint8_t* ndc = missk + THRL_MAX_AGENTS;                             // [16] distinct rows of the episode per state class
+  uint16_t* srow = reinterpret_cast<uint16_t*>(slot + p.off_srow);    // [ncls][Sp] float64 encode of every state (agents.py:62,66)
+  uint8_t* rs = slot + p.off_rs;                                      // [ncls][Sp] first state of the episode with the same row
+  uint8_t* nexts = slot + p.off_next;                                 // [ncls][Sp] next state with the same row (ascending), 0xFF = last
+  uint8_t* dl = slot + p.off_dl;                                      // [ncls][Sp] the representatives = distinct rows, ascending
+  uint8_t* act = slot + p.off_act;                                    // [n][Tp] chosen actions
+  QT* cur = reinterpret_cast<QT*>(slot + p.off_cur);                  // [n][Tp] snapshot; for a cell's first writer: the cell's live value
+  uint8_t* canon = slot + p.off_canon;                                // [n][Tp] first transition of the batch that writes the same cell
+  uint8_t* nextc = slot + p.off_nextc;                                // [n][Tp] a row's first writers (= its rewritten cells), ascending from the
+                                                                      //         representative transition itself; 0xFF = last
+  QT* bm = reinterpret_cast<QT*>(slot + p.off_bm);                    // [n][Sp] max over the untagged cells of the representative's row; its
+                                                                      //         first column waits in the row's greedy-cache byte (0xFF: none)
+  unsigned char* stage = slot + p.off_stage;                          // [nb][rb][slot_bytes] staged rows (kStaged)
+  int8_t* pre = reinterpret_cast<int8_t*>(slot + p.off_pre);          // [T][n] forced action or -1 (= greedy)          } alias the
+  uint32_t* maskS = reinterpret_cast<uint32_t*>(slot + p.off_mask);   // [rows per batch][4] rewritten / padding columns } (register landing)
+  double* newa = reinterpret_cast<double*>(slot + p.off_newa);        // [T] demand intercept (noisy only)               } staging
+  double* rq = reinterpret_cast<double*>(slot + p.off_rq);            // [n][seg] reward / max_steps (trainer.py:65)     } ring
+  const int seg = p.seg;
 
-  if (lane == 0)
-    for (int b = 0; b < nb; ++b) hbm_mbar_init(bar + b, p.bulk == 1 ? 1u : 32u);  // bulk: one arrival + byte count; else every lane arrives
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  hbm_fence_proxy_async();
-  __syncwarp();
   uint32_t parity = 0;  // bit b: phase the next wait on bar[b] completes
+  if (kStaged) {
+    if (lane == 0)
+      for (int b = 0; b < nb; ++b) hbm_mbar_init(bar + b, p.bulk ? 1u : 32u);  // bulk: one arrival + byte count; else every lane arrives
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    hbm_fence_proxy_async();
+    __syncwarp();
+  }
 
   // ---- lane i < n keeps agent i's constants in registers
-  int my_A = 2, my_lut = 0, my_goff = 0, my_gcap = 0;
+  int my_lut = 0, my_goff = 0, my_gcap = 0, my_t0 = T, my_cls = -1;
   float my_msf = 1.f, my_sf = 1.f;
   if (is_agent) {
     const ThrlAgentSpec& s = G.agent[lane];
-    my_A = s.actions;
     my_msf = (float)s.max_state;
     my_sf = (float)s.states;
     my_lut = p.loff[lane]; my_goff = p.goff[lane]; my_gcap = p.gcap[lane];
+    my_cls = p.cls_of[lane];
+    if (p.L[lane] > 0) my_t0 = T - p.L[lane];
   }
-  int tmin = T;  // first state any agent's batch needs
-  for (int i = 0; i < n; ++i)
-    if (p.L[i] > 0 && T - p.L[i] < tmin) tmin = T - p.L[i];
+  const double Td = (double)T;
+  const bool tracing = p.trace_actions || p.trace_rewards || p.trace_prices;
 
-  const long long total_warps = (long long)gridDim.x * warps_per_cta;
-  for (long long r = (long long)blockIdx.x * warps_per_cta + warp; r < p.n_runs; r += total_warps) {
+  // slot w * grid + b: a round that does not fill every warp leaves the idle warps spread over all SMs
+  const long long slot_id = (long long)warp * gridDim.x + blockIdx.x;
+  for (long long r = slot_id; slot_id < p.per_round && r < p.n_runs; r += p.per_round) {
     QT* qg = reinterpret_cast<QT*>(p.q) + r * G.run_stride;
     uint32_t* cnt = p.counter ? p.counter + r * G.run_stride : nullptr;
     const uint32_t gid = (uint32_t)(p.run_id0 + r);
@@ -250,8 +340,8 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_hbm(const __grid_constant_
             const int i = 2 * pr + h;
             if (i < n) {
               const double u = u32_unit(x[2 * h]);
-              const int ra = (int)__umulhi(x[2 * h + 1], (uint32_t)agc[i * 8 + 2]);
-              pre[t * n + i] = (int16_t)(u < hpw[i * 5 + 4] ? ra : -1);  // agents.py:81-82
+              const int ra = (int)__umulhi(x[2 * h + 1], (uint32_t)agc[i * kHbmAgc + 2]);
+              pre[t * n + i] = (int8_t)(u < hpw[i * 5 + 4] ? ra : -1);  // agents.py:81-82
             }
           }
         }
@@ -265,7 +355,7 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_hbm(const __grid_constant_
             const double u = p.replay_u[step0 * n + idx];
             v = u < hpw[i * 5 + 4] ? p.replay_ra[step0 * n + idx] : -1;  // agents.py:81
           }
-          pre[idx] = (int16_t)v;
+          pre[idx] = (int8_t)v;
         }
       }
       if (p.noisy) {
@@ -288,245 +378,407 @@ __global__ void __launch_bounds__(512, 1) qtable_scan_hbm(const __grid_constant_
       __syncwarp();
 
       // ---- the episode (trainer.py:50-67); lane i < n acts for agent i
-      double rlog = 0.0, alog = 0.0;  // trainer.py:40-41
+      int kpre = is_agent ? (int)pre[lane] : 0;
       for (int t = 0; t < T; ++t) {
-        int k = 0, arow = 0;
-        if (is_agent) {
-          k = pre[t * n + lane];
-          if (k < 0) {  // agents.py:84-88 on the frozen table
-            arow = act_row(price, my_msf, my_sf);
-            const int g = arow < my_gcap ? (int)Gc[my_goff + arow] : 0xFF;  // rows beyond the cache: always recomputed
-            k = g == 0xFF ? -1 : g;
-          }
+        int k = kpre, arow = 0;
+        if (is_agent && t + 1 < T) kpre = pre[(t + 1) * n + lane];  // next step's draw does not depend on this step
+        if (is_agent && k < 0) {  // agents.py:84-88 on the frozen table
+          arow = act_row(price, my_msf, my_sf);
+          const int g = arow < my_gcap ? (int)Gc[my_goff + arow] : 0xFF;  // rows beyond the cache: always recomputed
+          k = g == 0xFF ? -1 : g;
         }
-        unsigned need = __ballot_sync(kFull, is_agent && k < 0);  // first visit of a row: its greedy action is not known yet
-        while (need) {
-          const int i = __ffs(need) - 1;
-          need &= need - 1;
-          const int ri = __shfl_sync(kFull, arow, i);
-          const int* a = agc + i * 8;
-          const QT* row = qg + a[0] + (size_t)ri * a[1];
-          QT v[4];
-          if (4 * lane < a[1]) hbm_load4(row, lane, v);
-          QT best = NegInf<QT>::v();
-          unsigned bidx = kNone;
-#pragma unroll
-          for (int c = 0; c < 4; ++c)  // ascending columns, strict >: first maximal index (agents.py:88)
-            if (4 * lane + c < a[2] && (bidx == kNone || v[c] > best)) { best = v[c]; bidx = 4 * lane + c; }
-          const QT wm = warp_max(best);
-          const int g = (int)__reduce_min_sync(kFull, (bidx != kNone && best == wm) ? bidx : kNone);
-          if (lane == 0 && ri < a[5]) Gc[a[4] + ri] = (uint8_t)g;
-          if (lane == i) k = g;
+        const unsigned need = __ballot_sync(kFull, is_agent && k < 0);  // first visit of a row: its greedy action is not known yet
+        if (need) {  // lane group g reads the row of the g-th agent that missed, straight from HBM
+          unsigned left = need;
+          while (left) {
+            const unsigned tgt = __fns(left, 0, grp + 1);  // lane of this group's agent, 0xffffffff: none left for it
+            const bool has = tgt < 32u;
+            const int ri = __shfl_sync(kFull, arow, has ? (int)tgt : 0);
+            const int* a = agc + (has ? (int)tgt : 0) * kHbmAgc;
+            QT best;
+            unsigned bidx;
+            hbm_scan_row<QT, true>(qg + a[0] + (size_t)ri * a[1], a[2], qq, lpr, has, best, bidx);
+            if (has && qq == 0) {
+              const uint8_t g = bidx == kNone ? (uint8_t)0 : (uint8_t)bidx;  // numpy.argmax of a row without a value > -inf: column 0
+              if (ri < a[5]) Gc[a[4] + ri] = g;
+              missk[tgt] = g;
+            }
+            for (int z = 0; z < rb && left; ++z) left &= left - 1;
+          }
+          __syncwarp();
+          if (is_agent && k < 0) k = missk[lane];
         }
         double aq = 0.0;
         if (is_agent) aq = lutAQ[my_lut + k];
         double Q = 0.0;  // environments.py:27 sum(A): ((0 + A0) + A1) + ...
-        for (int i = 0; i < n; ++i) Q = __dadd_rn(Q, shfl_d(aq, i));
+        if (n <= 8) {    // all shuffles first, then the dependent additions; lanes >= n hold +0.0, which leaves the sum unchanged
+          double v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = shfl_d(aq, i);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) Q = __dadd_rn(Q, v[i]);
+        } else {
+          for (int i = 0; i < n; ++i) Q = __dadd_rn(Q, shfl_d(aq, i));
+        }
         const double na = p.noisy ? newa[t] : G.a;
         const double pn = __dsub_rn(na, __dmul_rn(G.b, Q));
         const double next_price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);  // numpy.max([0, x])
-        const double rew = __dmul_rn(next_price, aq);                       // environments.py:34
-        if (is_agent) {
-          rlog = __dadd_rn(rlog, __ddiv_rn(rew, (double)T));  // trainer.py:65
-          alog = __dadd_rn(alog, lutXT[my_lut + k]);          // trainer.py:66
-          act[lane * Tp + t] = (uint8_t)k;                    // trainer.py:61-62 memory.append
-          if (p.trace_actions) p.trace_actions[(step0 + t) * n + lane] = k;
-          if (p.trace_rewards) p.trace_rewards[(step0 + t) * n + lane] = rew;
-        }
-        if (lane == 0) {
-          P[t + 1] = next_price;
-          if (p.trace_prices) p.trace_prices[step0 + t] = next_price;
+        if (is_agent) act[lane * Tp + t] = (uint8_t)k;  // trainer.py:61-62 memory.append
+        if (lane == 0) P[t + 1] = next_price;
+        if (tracing) {
+          if (is_agent) {
+            if (p.trace_actions) p.trace_actions[(step0 + t) * n + lane] = k;
+            if (p.trace_rewards) p.trace_rewards[(step0 + t) * n + lane] = __dmul_rn(next_price, aq);  // environments.py:34
+          }
+          if (lane == 0 && p.trace_prices) p.trace_prices[step0 + t] = next_price;
         }
         price = next_price;  // trainer.py:67
       }
       __syncwarp();
 
       // ================================================================ train_net for every agent (trainer.py:70)
-      // ---- 1. encodes (agents.py:62,66), stale snapshot (:67) and visit counters (:76), lane-parallel
-      for (int i = 0; i < n; ++i) {
-        const int* a = agc + i * 8;
-        if (a[7] == 0) continue;
-        const double ms = G.agent[i].max_state, st = (double)G.agent[i].states;
-        for (int t = a[6] + lane; t <= T; t += 32) srow[i * Sp + t] = (uint16_t)upd_row(P[t], ms, st);
+      // ---- U1. float64 encodes (agents.py:62,66), once per state class, lane = state
+      for (int c = 0; c < p.ncls; ++c) {
+        const int i0 = p.cls_agent[p.cls_beg[c]];
+        const int t0 = agc[i0 * kHbmAgc + 6];
+        const double ms = G.agent[i0].max_state, st = (double)G.agent[i0].states;
+        for (int t = t0 + lane; t <= T; t += 32) srow[c * Sp + t] = (uint16_t)upd_row(P[t], ms, st);
       }
       __syncwarp();
-      for (int i = 0; i < n; ++i) {
-        const int* a = agc + i * 8;
-        if (a[7] == 0) continue;
-        for (int t = a[6] + lane; t < T; t += 32) {
-          const int cell = a[0] + (int)srow[i * Sp + t] * a[1] + act[i * Tp + t];  // a run's slab has < 2^31 elements (checked at layout)
-          cur[i * Tp + t] = qg[cell];
-          if (cnt) atomicAdd(cnt + cell, 1u);  // fire-and-forget RED
+      // ---- U2. group the states by row: a chain through the states of one row in ascending order.  The greedy-cache byte of a
+      //      touched row serves as the chain head while the groups are formed (it is refreshed in U5 anyway); rows beyond the
+      //      cache (only a call's initial price can lie there) are searched linearly.
+      for (int c = 0; c < p.ncls; ++c) {
+        const int* a = agc + p.cls_agent[p.cls_beg[c]] * kHbmAgc;
+        const uint16_t* sr = srow + c * Sp;
+        const int t0 = a[6], gcap = a[5];
+        uint8_t* Gh = Gc + a[4];
+        for (int t = t0 + lane; t <= T; t += 32) {
+          const int row = sr[t];
+          if (row < gcap) Gh[row] = 0xFF;
+        }
+        __syncwarp();
+        for (int tb = t0 + ((T - t0) & ~31); tb >= t0; tb -= 32) {  // 32 states at a time, last chunk first
+          const int t = tb + lane;
+          const bool valid = t <= T;
+          const int row = valid ? (int)sr[t] : 0x10000 + lane;  // idle lanes match nobody
+          const unsigned same = __match_any_sync(kFull, row);
+          const unsigned above = same & ~((2u << lane) - 1u);
+          uint8_t nx = 0xFF;
+          if (above) {
+            nx = (uint8_t)(tb + __ffs(above) - 1);
+          } else if (valid) {
+            if (row < gcap) {
+              nx = Gh[row];  // first state of the later chunks with this row
+            } else {
+              for (int u = tb + 32; u <= T; ++u)
+                if (sr[u] == row) { nx = (uint8_t)u; break; }
+            }
+          }
+          if (valid) nexts[c * Sp + t] = nx;
+          __syncwarp();
+          if (valid && row < gcap && (same & ((1u << lane) - 1u)) == 0u) Gh[row] = (uint8_t)t;
+          __syncwarp();
+        }
+        int nd = 0;  // representatives = distinct rows, compacted in ascending order
+        for (int tb = t0; tb <= T; tb += 32) {
+          const int t = tb + lane;
+          bool isrep = false;
+          if (t <= T) {
+            const int row = sr[t];
+            int rep = t;
+            if (row < gcap) {
+              rep = Gh[row];
+            } else {
+              for (int u = t0; u < t; ++u)
+                if (sr[u] == row) { rep = u; break; }
+            }
+            rs[c * Sp + t] = (uint8_t)rep;
+            isrep = rep == t;
+          }
+          const unsigned m = __ballot_sync(kFull, isrep);
+          if (isrep) dl[c * Sp + nd + __popc(m & ((1u << lane) - 1u))] = (uint8_t)t;
+          nd += __popc(m);
+        }
+        if (lane == 0) ndc[c] = (uint8_t)nd;  // <= T + 1 <= 255
+      }
+      // visit counters (agents.py:76): fire-and-forget REDs, lane = transition
+      if (cnt) {
+        for (int i = 0; i < n; ++i) {
+          const int* a = agc + i * kHbmAgc;
+          if (a[7] == 0) continue;
+          const uint16_t* sr = srow + a[8] * Sp;
+          for (int t = a[6] + lane; t < T; t += 32) atomicAdd(cnt + a[0] + (int)sr[t] * a[1] + act[i * Tp + t], 1u);
         }
       }
-      __syncwarp();  // every snapshot value has arrived (it was stored to cur[]) before any cell is tagged
-      // ---- 2. tag the cells of the batch
-      for (int i = 0; i < n; ++i) {
-        const int* a = agc + i * 8;
-        if (a[7] == 0) continue;
-        for (int t = a[6] + lane; t < T; t += 32) {
-          const int cell = a[0] + (int)srow[i * Sp + t] * a[1] + act[i * Tp + t];
-          atomicMax(reinterpret_cast<U*>(qg + cell), (U)(B::kBase | (U)(1023 - t)));
-        }
-      }
-      __threadfence();          // the tags are performed at L2 ...
-      hbm_fence_proxy_async();  // ... and ordered before the bulk copies (async proxy) that read them; also orders this
-      __syncwarp();             // warp's generic accesses to the staging ring (pre / newa / merge) before its reuse
+      if (kStaged) hbm_fence_proxy_async();  // this warp's generic accesses to the staging ring (pre / newa / rq) and to the tables
+      __syncwarp();                          // (last episode's stores) are ordered before the bulk copies that follow
 
-      // ---- 3 + 4. gather the rows of states tmin..T through the staging ring and walk them in order
-      auto issue = [&](int b, int t) {
-        uint32_t bytes = 0;
-        const QT* src = nullptr;
-        if (is_agent) {
-          const int* a = agc + lane * 8;
-          if (a[7] > 0 && t >= a[6]) {
-            bytes = (uint32_t)a[1] * (uint32_t)sizeof(QT);
-            src = qg + a[0] + (size_t)srow[lane * Sp + t] * a[1];
-          }
-        }
-        unsigned char* dst = stage + ((size_t)b * n + lane) * p.slot_bytes;
-        if (p.bulk == 1) {
-          const uint32_t total = __reduce_add_sync(kFull, bytes);
-          if (lane == 0) hbm_mbar_expect_tx(bar + b, total);
-          if (bytes) hbm_bulk_g2s(dst, src, bytes, bar + b);
-        } else {  // the same rows in 16-byte pieces: lane l moves bytes [16 l, 16 l + 16) (and [16 (l + 32), ...) of 8-byte tables)
-          for (int i = 0; i < n; ++i) {
-            const uint32_t bi = __shfl_sync(kFull, bytes, i);
-            const unsigned long long si = __shfl_sync(kFull, (unsigned long long)src, i);
-            int4* di = reinterpret_cast<int4*>(stage + ((size_t)b * n + i) * p.slot_bytes);
-            if (p.bulk == 2) {
-              if (16u * lane < bi) hbm_cp_async16(di + lane, reinterpret_cast<const int4*>(si) + lane);
-              if (sizeof(QT) == 8 && 16u * (lane + 32) < bi) hbm_cp_async16(di + lane + 32, reinterpret_cast<const int4*>(si) + lane + 32);
-            } else {  // loads that bypass L1 (they must see the tags)
-              if (16u * lane < bi) di[lane] = __ldcg(reinterpret_cast<const int4*>(si) + lane);
-              if (sizeof(QT) == 8 && 16u * (lane + 32) < bi) di[lane + 32] = __ldcg(reinterpret_cast<const int4*>(si) + lane + 32);
+      // ---- U3. gather the distinct rows; per row: stale snapshots + first writers of its rewritten cells, then (max, first
+      //      argmax) over the cells no transition of this batch writes
+      for (int c = 0; c < p.ncls; ++c) {
+        const int na = p.cls_na[c], abeg = p.cls_beg[c];
+        const int nd = ndc[c];
+        const int items = nd * na;  // item g = (distinct row g / na, agent g % na): the agents of one state land together
+        const int nbatch = (items + rb - 1) / rb;
+        const int dstep = rb / na, astep = rb - dstep * na;  // item index advances by rb per batch, without a division
+        if (kStaged) {
+          int di = grp / na, ai = grp - di * na;    // item of the batch being issued
+          int dp = di, ap = ai;                     // item of the batch being processed
+          auto issue = [&](int b) {
+            uint32_t bytes = 0;
+            const QT* src = nullptr;
+            if (di < nd) {
+              const int* a = agc + p.cls_agent[abeg + ai] * kHbmAgc;
+              bytes = (uint32_t)a[1] * (uint32_t)sizeof(QT);
+              src = qg + a[0] + (size_t)srow[c * Sp + dl[c * Sp + di]] * a[1];
             }
-          }
-          if (p.bulk == 2) hbm_cp_async_arrive(bar + b);
-          else hbm_mbar_arrive(bar + b);
-        }
-      };
-      if (tmin < T) {
-        for (int b = 0; b < nb && tmin + b <= T; ++b) issue(b, tmin + b);
-        for (int t = tmin; t <= T; ++t) {
-          const int b = (t - tmin) % nb;
-          hbm_mbar_wait(bar + b, (parity >> b) & 1u);
-          parity ^= 1u << b;
-          for (int i = 0; i < n; ++i) {
-            const int* a = agc + i * 8;
-            if (a[7] == 0 || t < a[6]) continue;
-            const int RS = a[1], A = a[2];
-            const QT* srow_s = reinterpret_cast<const QT*>(stage + ((size_t)b * n + i) * p.slot_bytes);
-            QT v[4];
-            if (4 * lane < RS) hbm_load4(srow_s, lane, v);
-            U bits[4];
-            bool tg[4];
-            QT bmv = NegInf<QT>::v();
-            unsigned bidx = kNone;
-            bool anytag = false;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {  // (max, first argmax) over this lane's untagged columns
-              const bool valid = 4 * lane + c < A;
-              bits[c] = valid ? B::of(v[c]) : (U)0;
-              tg[c] = bits[c] >= B::kBase;
-              anytag |= tg[c];
-              if (valid && !tg[c] && (bidx == kNone || v[c] > bmv)) { bmv = v[c]; bidx = 4 * lane + c; }
+            unsigned char* dst = stage + ((size_t)b * rb + grp) * p.slot_bytes;
+            if (p.bulk) {
+              const uint32_t total = __reduce_add_sync(kFull, qq == 0 ? bytes : 0u);
+              if (lane == 0) hbm_mbar_expect_tx(bar + b, total);
+              if (qq == 0 && bytes) hbm_bulk_g2s(dst, src, bytes, bar + b);
+            } else {  // comparison path: the same rows with 16-byte vector loads that bypass L1
+              for (uint32_t o = 16u * qq; o < bytes; o += 16u * lpr)
+                *reinterpret_cast<int4*>(dst + o) = __ldcg(reinterpret_cast<const int4*>(reinterpret_cast<const unsigned char*>(src) + o));
+              hbm_mbar_arrive(bar + b);
             }
-            const QT wbm = warp_max(bmv);
-            const unsigned wba = __reduce_min_sync(kFull, (bidx != kNone && bmv == wbm) ? bidx : kNone);
-            QT wlm = wbm;  // live row max (agents.py:71): tagged cells read through to their current values
-            if (__any_sync(kFull, anytag)) {
-              QT lm = bmv;
-#pragma unroll
-              for (int c = 0; c < 4; ++c)
-                if (tg[c]) {
-                  int ci = 1023 - (int)(bits[c] & (U)1023);
-                  ci = ci < T ? ci : T - 1;
-                  const QT pv = cur[i * Tp + ci];
-                  lm = pv > lm ? pv : lm;
+            di += dstep; ai += astep;
+            if (ai >= na) { ai -= na; ++di; }
+          };
+          for (int k = 0; k < nb && k < nbatch; ++k) issue(k);
+          for (int k = 0; k < nbatch; ++k) {
+            const int b = k % nb;
+            hbm_mbar_wait(bar + b, (parity >> b) & 1u);
+            parity ^= 1u << b;
+            const bool has = dp < nd;
+            const int i = p.cls_agent[abeg + ap];
+            const int rep = has ? (int)dl[c * Sp + dp] : 0;
+            const int* a = agc + i * kHbmAgc;
+            QT* srow_s = reinterpret_cast<QT*>(stage + ((size_t)b * rb + grp) * p.slot_bytes);
+            if (has && qq == 0) {
+              // the row's transitions in ascending order: the first writer of a cell takes the staged value as everybody's
+              // stale snapshot (agents.py:67) and leaves its index; later writers of the cell share its slot
+              U* cells = reinterpret_cast<U*>(srow_s);
+              int tail = rep;
+              for (int t = rep; t != 0xFF && t < T; t = nexts[c * Sp + t]) {
+                const int kt = act[i * Tp + t];
+                const U bits = cells[kt];
+                if (bits >= B::kBase) {
+                  const int f = (int)(bits & (U)0xFF);
+                  cur[i * Tp + t] = cur[i * Tp + f];
+                  canon[i * Tp + t] = (uint8_t)f;
+                } else {
+                  cur[i * Tp + t] = B::val(bits);
+                  canon[i * Tp + t] = (uint8_t)t;
+                  cells[kt] = B::kBase | (U)t;
+                  nextc[i * Tp + t] = 0xFF;
+                  if (t != rep) nextc[i * Tp + tail] = (uint8_t)t;  // the representative transition is always a first writer
+                  tail = t;
                 }
-              wlm = warp_max(lm);
+              }
             }
-            if (t < T) {  // canonical transition of the cell transition t writes: read from the tag it left in this row
-              const int kt = act[i * Tp + t];
-              const int kc = kt & 3;
-              const U bsel = kc == 0 ? bits[0] : (kc == 1 ? bits[1] : (kc == 2 ? bits[2] : bits[3]));
-              const uint32_t mine = (uint32_t)(bsel & (U)1023);
-              const int ct = 1023 - (int)__shfl_sync(kFull, mine, kt >> 2);
-              if (lane == 0) canon[i * Tp + t] = (uint8_t)ct;
+            __syncwarp();
+            QT best;
+            unsigned bidx;
+            hbm_scan_row<QT, false>(srow_s, a[2], qq, lpr, has, best, bidx);
+            if (has && qq == 0) {
+              if (bidx == kNone) {  // no untagged value above -inf: the first untagged column, if any, holds the maximum (-inf)
+                const U* cells = reinterpret_cast<const U*>(srow_s);
+                for (int col = 0; col < a[2]; ++col)
+                  if (cells[col] < B::kBase) { bidx = (unsigned)col; break; }
+              }
+              bm[i * Sp + rep] = best;
+              const int row = srow[c * Sp + rep];
+              if (row < a[5]) Gc[a[4] + row] = bidx == kNone ? (uint8_t)0xFF : (uint8_t)bidx;
             }
-            if (t > a[6]) {  // transition j = t - 1 bootstraps from this row (:71-75)
-              const int j = t - 1, kj = act[i * Tp + j];
-              const double alpha = hpw[i * 5 + 0], gamma = hpw[i * 5 + 1];
-              const double reward = __dmul_rn(P[t], lutAQ[a[3] + kj]);
-              const double nv = __dadd_rn(__dmul_rn(__dsub_rn(1.0, alpha), (double)cur[i * Tp + j]),
-                                          __dmul_rn(alpha, __dadd_rn(reward, __dmul_rn(gamma, (double)wlm))));
-              if (lane == 0) cur[i * Tp + canon[i * Tp + j]] = (QT)nv;  // cur[j] itself is still the snapshot: the canonical slot is the first writer's
+            dp += dstep; ap += astep;
+            if (ap >= na) { ap -= na; ++dp; }
+            hbm_fence_proxy_async_shared();  // the tags (generic stores) before the next bulk copy into this slot
+            __syncwarp();
+            if (k + nb < nbatch) issue(b);
+          }
+        } else {
+          // rows land in registers: 16-byte vector loads (L1 bypassed), all of a lane's chunks in flight at once, rows of the
+          // batches ahead prefetched into L2.  The columns a transition of this batch writes are a 128-bit mask per row (plus
+          // the padding columns), tested per element in the compare's predicate.
+          constexpr int EPC = R::kEpc, LPR = R::kLpr, NS = R::kSlots;
+          int dp = grp / na, ap = grp - dp * na;  // item of the batch being processed
+          int df = dp, af = ap;                   // item of the batch being prefetched
+          auto prefetch = [&]() {
+            if (df < nd) {
+              const int* a = agc + p.cls_agent[abeg + af] * kHbmAgc;
+              const unsigned char* src = reinterpret_cast<const unsigned char*>(qg + a[0] + (size_t)srow[c * Sp + dl[c * Sp + df]] * a[1]);
+              const int bytes = a[1] * (int)sizeof(QT);
+              for (int o = 32 * qq; o < bytes; o += 32 * LPR) hbm_prefetch_l2(src + o);  // one 32-byte sector per prefetch
             }
-            if (lane == 0) {
-              bm[i * Sp + t] = wbm;
-              ba[i * Sp + t] = wba == kNone ? (uint8_t)0xFF : (uint8_t)wba;
+            df += dstep; af += astep;
+            if (af >= na) { af -= na; ++df; }
+          };
+          for (int k = 0; k < p.pf_dist && k < nbatch; ++k) prefetch();
+          for (int k = 0; k < nbatch; ++k) {
+            const bool has = dp < nd;
+            const int i = p.cls_agent[abeg + ap];
+            const int rep = has ? (int)dl[c * Sp + dp] : 0;
+            const int* a = agc + i * kHbmAgc;
+            const QT* row = qg + a[0] + (size_t)(has ? (int)srow[c * Sp + rep] : 0) * a[1];
+            const int nch = has ? a[1] / EPC : 0;  // row_stride is a multiple of a chunk
+            QT v[NS][EPC];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+              if (s * LPR < p.nch_max) {  // uniform: no agent's row reaches this slot otherwise
+                const int c4 = qq + s * LPR;
+                if (c4 < nch) {
+                  hbm_chunk<true>(row, c4, v[s]);
+                } else {
+#pragma unroll
+                  for (int e2 = 0; e2 < EPC; ++e2) v[s][e2] = NegInf<QT>::v();
+                }
+              }
+            }
+            if (k + p.pf_dist < nbatch) prefetch();
+            uint32_t* M = maskS + grp * 4;
+            if (qq == 0) {
+              if (has) {
+                M[0] = (uint32_t)a[12]; M[1] = (uint32_t)a[13]; M[2] = (uint32_t)a[14]; M[3] = (uint32_t)a[15];
+                // the row's transitions in ascending order: the first writer of a cell loads everybody's stale snapshot
+                // (agents.py:67; an L2 hit behind the row loads above) and joins the row's list of rewritten cells
+                int tail = rep;
+                for (int t = rep; t != 0xFF && t < T; t = nexts[c * Sp + t]) {
+                  const int kt = act[i * Tp + t];
+                  const uint32_t bit = 1u << (kt & 31);
+                  if (M[kt >> 5] & bit) {
+                    int f = rep;
+                    while (act[i * Tp + f] != kt) f = nextc[i * Tp + f];
+                    cur[i * Tp + t] = cur[i * Tp + f];
+                    canon[i * Tp + t] = (uint8_t)f;
+                  } else {
+                    M[kt >> 5] |= bit;
+                    cur[i * Tp + t] = __ldcg(row + kt);
+                    canon[i * Tp + t] = (uint8_t)t;
+                    nextc[i * Tp + t] = 0xFF;
+                    if (t != rep) nextc[i * Tp + tail] = (uint8_t)t;  // the representative transition is always a first writer
+                    tail = t;
+                  }
+                }
+              } else {
+                M[0] = M[1] = M[2] = M[3] = 0xffffffffu;
+              }
+            }
+            __syncwarp();
+            uint32_t mq[4];
+            {
+              const uint4 m4 = *reinterpret_cast<const uint4*>(M);
+              const int sh = qq * EPC;  // element (slot s, e) of this lane is column 8 s + sh + e: bit 8 (s % 4) + e of word s / 4 after the shift
+              mq[0] = m4.x >> sh; mq[1] = m4.y >> sh; mq[2] = m4.z >> sh; mq[3] = m4.w >> sh;
+            }
+            QT b0 = NegInf<QT>::v(), b1 = NegInf<QT>::v();
+            unsigned i0 = kNone, i1 = kNone;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+              if (s * LPR < p.nch_max) {
+#pragma unroll
+                for (int e2 = 0; e2 < EPC; ++e2) {  // ascending columns, strict >: first maximal index (agents.py:88)
+                  const bool free_cell = (mq[s >> 2] & (1u << (8 * (s & 3) + e2))) == 0u;
+                  const unsigned col = (unsigned)((qq + s * LPR) * EPC + e2);
+                  if (s & 1) {
+                    if (free_cell && v[s][e2] > b1) { b1 = v[s][e2]; i1 = col; }
+                  } else {
+                    if (free_cell && v[s][e2] > b0) { b0 = v[s][e2]; i0 = col; }
+                  }
+                }
+              }
+            }
+            if (b1 > b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+#pragma unroll
+            for (int off = 1; off < LPR; off <<= 1) {
+              const QT ob = shfl_xor_t(b0, off);
+              const unsigned oi = __shfl_xor_sync(kFull, i0, off);
+              if (ob > b0 || (ob == b0 && oi < i0)) { b0 = ob; i0 = oi; }
+            }
+            if (has && qq == 0) {
+              if (i0 == kNone) {  // no free cell above -inf: the first free column, if any, holds the maximum (-inf)
+#pragma unroll
+                for (int w = 3; w >= 0; --w)
+                  if (~M[w]) i0 = (unsigned)(32 * w + __ffs((int)~M[w]) - 1);
+              }
+              bm[i * Sp + rep] = b0;
+              const int rowi = srow[c * Sp + rep];
+              if (rowi < a[5]) Gc[a[4] + rowi] = i0 == kNone ? (uint8_t)0xFF : (uint8_t)i0;
+            }
+            dp += dstep; ap += astep;
+            if (ap >= na) { ap -= na; ++dp; }
+            __syncwarp();  // the masks are rewritten by the next batch
+          }
+        }
+      }
+      __syncwarp();
+
+      // ---- U4. lane = agent: logs in step order (trainer.py:65-66) and the batch in order (agents.py:68-76), all on chip.
+      //      reward / max_steps (trainer.py:65) is divided lane-parallel, `seg` steps at a time.
+      double rlog = 0.0, alog = 0.0;  // trainer.py:40-41
+      {
+        const uint8_t* rsc = rs + (my_cls < 0 ? 0 : my_cls) * Sp;
+        const double alpha = is_agent ? hpw[lane * 5 + 0] : 0.0, gamma = is_agent ? hpw[lane * 5 + 1] : 0.0;
+        const double oma = __dsub_rn(1.0, alpha);
+        const uint8_t* actl = act + lane * Tp;
+        for (int s0 = 0; s0 < T; s0 += seg) {
+          const int sl = T - s0 < seg ? T - s0 : seg;
+          for (int idx = lane; idx < n * sl; idx += 32) {
+            const int i = idx / sl, tt = idx - i * sl;
+            const double rew = __dmul_rn(P[s0 + tt + 1], lutAQ[agc[i * kHbmAgc + 3] + act[i * Tp + s0 + tt]]);  // environments.py:34
+            rq[i * seg + tt] = __ddiv_rn(rew, Td);
+          }
+          __syncwarp();
+          if (is_agent) {
+            for (int t = s0; t < s0 + sl; ++t) {
+              const int kt = actl[t];
+              const double pn = P[t + 1], aqk = lutAQ[my_lut + kt];
+              rlog = __dadd_rn(rlog, rq[lane * seg + t - s0]);
+              alog = __dadd_rn(alog, lutXT[my_lut + kt]);
+              if (t >= my_t0) {
+                const int rep = rsc[t + 1];
+                const int cn = canon[lane * Tp + t];
+                const double oldv = (double)cur[lane * Tp + t];  // still the snapshot: only t itself or later writers change cur[t]
+                QT m = bm[lane * Sp + rep];  // live row max (agents.py:71): untagged cells + current values of the rewritten ones
+                for (int cc = rep < T ? rep : 0xFF; cc != 0xFF; cc = nextc[lane * Tp + cc]) {
+                  const QT v = cur[lane * Tp + cc];
+                  m = v > m ? v : m;
+                }
+                const double reward = __dmul_rn(pn, aqk);
+                const double nv = __dadd_rn(__dmul_rn(oma, oldv), __dmul_rn(alpha, __dadd_rn(reward, __dmul_rn(gamma, (double)m))));  // agents.py:72-75
+                cur[lane * Tp + cn] = (QT)nv;  // cur[t] itself stays the snapshot unless t is the cell's first writer
+              }
             }
           }
-          __syncwarp();  // cur[] / canon[] of this state are visible; every lane is done with staging batch b
-          if (t + nb <= T) issue(b, t + nb);
+          __syncwarp();
         }
       }
 
-      // ---- 5. write back over the tags (:75; the last write of the batch per cell), exact greedy refresh of every row touched
+      // ---- U5. final values to HBM (the last write of the batch per cell, agents.py:75); exact greedy refresh of every
+      //      touched row: untagged (max, argmax) merged with the final values of the row's rewritten cells
       for (int i = 0; i < n; ++i) {
-        const int* a = agc + i * 8;
+        const int* a = agc + i * kHbmAgc;
         if (a[7] == 0) continue;
-        for (int t = a[6] + lane; t < T; t += 32)
-          if (canon[i * Tp + t] == t) qg[a[0] + (int)srow[i * Sp + t] * a[1] + act[i * Tp + t]] = cur[i * Tp + t];
-        for (int t = a[6] + lane; t <= T; t += 32) {  // A: one representative state per distinct row (any winner)
-          const int row = srow[i * Sp + t];
-          if (row < a[5]) Gc[a[4] + row] = (uint8_t)t;
-        }
-      }
-      __syncwarp();
-      for (int i = 0; i < n; ++i) {
-        const int* a = agc + i * 8;
-        if (a[7] == 0) continue;
-        for (int t = a[6] + lane; t <= T; t += 32) {  // B: the representative starts from the untagged part of its row
-          const int row = srow[i * Sp + t];
-          uint8_t rep = 0xFF;
-          if (row < a[5]) {
-            rep = Gc[a[4] + row];
-            if (rep == t) { vkey[i * Sp + t] = B::key(bm[i * Sp + t]); cmin[i * Sp + t] = kNone; }
+        const int c = a[8];
+        const uint16_t* sr = srow + c * Sp;
+        for (int t = a[6] + lane; t <= T; t += 32) {
+          if (t < T && canon[i * Tp + t] == t) qg[a[0] + (int)sr[t] * a[1] + act[i * Tp + t]] = cur[i * Tp + t];
+          const int row = sr[t];
+          if (rs[c * Sp + t] == t && row < a[5]) {
+            QT best = bm[i * Sp + t];
+            const uint8_t ba = Gc[a[4] + row];  // first column of the untagged maximum, left there by U3
+            unsigned bidx = ba == 0xFF ? kNone : (unsigned)ba;
+            for (int cc = t < T ? t : 0xFF; cc != 0xFF; cc = nextc[i * Tp + cc]) {
+              const QT v = cur[i * Tp + cc];
+              const unsigned col = act[i * Tp + cc];
+              if (v > best || (v == best && col < bidx)) { best = v; bidx = col; }
+            }
+            Gc[a[4] + row] = bidx == kNone ? (uint8_t)0 : (uint8_t)bidx;
           }
-          rs[i * Sp + t] = rep;
         }
       }
-      __syncwarp();
-      for (int i = 0; i < n; ++i) {
-        const int* a = agc + i * 8;
-        if (a[7] == 0) continue;
-        for (int t = a[6] + lane; t < T; t += 32) {  // C1: final values of the rewritten cells
-          const int rep = rs[i * Sp + t];
-          if (rep != 0xFF && canon[i * Tp + t] == t) atomicMax(&vkey[i * Sp + rep], B::key(cur[i * Tp + t]));
-        }
-      }
-      __syncwarp();
-      for (int i = 0; i < n; ++i) {
-        const int* a = agc + i * 8;
-        if (a[7] == 0) continue;
-        for (int t = a[6] + lane; t <= T; t += 32) {  // C2: first column that holds the maximum
-          const int rep = rs[i * Sp + t];
-          if (rep == 0xFF) continue;
-          if (rep == t && ba[i * Sp + t] != 0xFF && B::key(bm[i * Sp + t]) == vkey[i * Sp + t]) atomicMin(&cmin[i * Sp + t], (uint32_t)ba[i * Sp + t]);
-          if (t < T && canon[i * Tp + t] == t && B::key(cur[i * Tp + t]) == vkey[i * Sp + rep])
-            atomicMin(&cmin[i * Sp + rep], (uint32_t)act[i * Tp + t]);
-        }
-      }
-      __syncwarp();
-      for (int i = 0; i < n; ++i) {
-        const int* a = agc + i * 8;
-        if (a[7] == 0) continue;
-        for (int t = a[6] + lane; t <= T; t += 32)  // D
-          if (rs[i * Sp + t] == t) Gc[a[4] + srow[i * Sp + t]] = (uint8_t)cmin[i * Sp + t];  // (kNone -> 0xFF: cannot happen, every row has a column)
-      }
-      __syncwarp();
+      if (kStaged) __threadfence();  // the table stores are performed before next episode's bulk copies read the rows (fence.proxy.async there)
 
       // epsilon decay, every epoch (:78); logs
       if (is_agent) {

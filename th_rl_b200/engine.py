@@ -133,7 +133,8 @@ class RunBatch:
             a.n_runs, a.run_id0 = R, self.run_id0 + rb
             a.epoch_begin, a.epoch_end = self.epoch, self.epoch + E
             a.table_dtype, a.rng_mode, a.seed = self.table_dtype, rng_mode, self.seed
-            a.q, a.counter, a.eps, a.price = _dp(self.q[rb:re_]), _dp(self.counter[rb:re_]), _dp(self.eps[rb:re_]), _dp(self.price[rb:re_])
+            a.q, a.eps, a.price = _dp(self.q[rb:re_]), _dp(self.eps[rb:re_]), _dp(self.price[rb:re_])
+            a.counter = None if self.counter is None else _dp(self.counter[rb:re_])  # NULL: visit counts are not kept
             a.hp = None if self.hp is None else _dp(self.hp[rb:re_])
             a.ring = None if self.ring is None else _dp(self.ring[rb:re_])
             a.mlp = None if self.mlp is None else _dp(self.mlp[rb:re_])

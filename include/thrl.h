@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define THRL_ABI_VERSION 3
+#define THRL_ABI_VERSION 4
 #define THRL_MAX_AGENTS 16
 #define THRL_MAX_ACTIONS 255 /* greedy-action cache is one byte per table row, 0xFF = not cached */
 
@@ -206,6 +206,16 @@ int thrl_greedy_eval(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, 
  * the run slab of ThrlScanArgs.mlp (read only); q / mlp may be NULL when the game has no Q-tables / no MLP agents. */
 int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
                          int32_t iters, const double* price0, double* rewards, double* actions, void* stream);
+/* ABI 4: cross-run quantile statistics of the learning curve, th_rl/utils.py:132-145 (plot_learning_curve_conf: per run
+ * pandas' ewm(halflife).mean() of the per-epoch mean rewards summed over the agents, then the median / quartiles over the runs).
+ * rewards_log [n_runs][epochs][n_agents] is what thrl_qtable_scan wrote (device); ewm_num [n_runs] carries every run's EWM
+ * numerator num_t = num_{t-1} * decay + x_t between calls (zero before the first epoch), decay = 1 - alpha = 0.5^(1/halflife);
+ * den [epochs] (device) holds the EWM denominators den_t = den_{t-1} * decay + 1 of the epochs of this call (den_{-1} = 0) -- the
+ * same for every run, so the host computes them.  The value
+ * num_t / den_t of every run is counted into hist [epochs][n_bins] (+=; bin = floor((v - lo) / (hi - lo) * n_bins), clamped):
+ * exact integer counts, so per-shard histograms add up (NCCL all-reduce). */
+int thrl_curve_hist(const double* rewards_log, int64_t n_runs, int32_t epochs, int32_t n_agents, double decay,
+                    const double* den, double* ewm_num, double lo, double hi, int32_t n_bins, int64_t* hist, void* stream);
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 int64_t thrl_launch_count(void);
 /* Name of the scan kernel the calling thread's latest thrl_qtable_scan / thrl_qtable_scan_host launched: "lut2", "lpc",

@@ -210,3 +210,24 @@ def py_sum(items, lead):
 
 def online_cores():
     return lib().thrl_oracle_online_cores()
+
+
+def curve_hist(rewards_log, decay, den, num, lo, hi, n_bins):
+    """CPU restatement of thrl_curve_hist (include/thrl.h; th_rl/utils.py:136-145): rewards_log [R, E, n] -> (hist [E, n_bins]
+    int64, num [R]) with exactly the device's operations: x = ((0 + r_0) + r_1) + ..., num = num * decay + x, v = num / den_t,
+    bin = floor((v - lo) * (n_bins / (hi - lo))) clamped."""
+    rewards_log = np.asarray(rewards_log, np.float64)
+    R, E, n = rewards_log.shape
+    num = np.array(num, np.float64).copy()
+    hist = np.zeros((E, n_bins), np.int64)
+    inv_width = float(n_bins) / (hi - lo)
+    for e in range(E):
+        x = np.zeros(R)
+        for i in range(n):
+            x = x + rewards_log[:, e, i]
+        num = num * decay + x
+        v = num / den[e]
+        b = np.floor((v - lo) * inv_width)
+        b = np.where(np.isnan(b), n_bins - 1, np.clip(b, 0, n_bins - 1)).astype(np.int64)
+        np.add.at(hist[e], b, 1)
+    return hist, num

@@ -51,6 +51,9 @@ def lib():
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.thrl_greedy_eval_mlp.restype = C.c_int
     L.thrl_release_device_memory.restype = C.c_int
+    L.thrl_curve_hist.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_double,
+                                  C.c_double, C.c_int32, C.c_void_p, C.c_void_p]
+    L.thrl_curve_hist.restype = C.c_int
     L.thrl_launch_count.restype = C.c_int64
     L.thrl_last_kernel.restype = C.c_char_p
     L.thrl_last_wave_runs.restype = C.c_int64

@@ -1398,3 +1398,26 @@ extern "C" int thrl_release_device_memory(void) {
   }
   return THRL_OK;
 }
+
+extern "C" int thrl_curve_hist(const double* rewards_log, int64_t n_runs, int32_t epochs, int32_t n_agents, double decay,
+                               const double* den, double* ewm_num, double lo, double hi, int32_t n_bins, int64_t* hist,
+                               void* stream) {
+  if (!rewards_log || !den || !ewm_num || !hist) return fail(THRL_ERR_BAD_ARGS, "thrl_curve_hist: NULL argument");
+  if (n_runs < 0 || epochs < 0 || n_agents < 1 || n_agents > THRL_MAX_AGENTS || n_bins < 1 || !(hi > lo) || !(decay > 0.0 && decay < 1.0))
+    return fail(THRL_ERR_BAD_ARGS, "thrl_curve_hist: n_runs=%lld epochs=%d n_agents=%d n_bins=%d lo=%g hi=%g decay=%g",
+                (long long)n_runs, epochs, n_agents, n_bins, lo, hi, decay);
+  if (n_runs == 0 || epochs == 0) return THRL_OK;
+  DeviceInfo dev;
+  int rc = device_info(&dev);
+  if (rc) return rc;
+  thrl::CurveHistParams p;
+  p.rewards_log = rewards_log; p.n_runs = n_runs; p.E = epochs; p.n = n_agents;
+  p.decay = decay;
+  p.den = den; p.ewm_num = ewm_num; p.lo = lo; p.inv_width = (double)n_bins / (hi - lo); p.n_bins = n_bins;
+  p.hist = (unsigned long long*)hist;
+  const long long blocks = (n_runs + 255) / 256;
+  thrl::curve_hist<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  g_launches.fetch_add(1);
+  return THRL_OK;
+}

@@ -171,4 +171,45 @@ __global__ void __launch_bounds__(256) greedy_eval(const __grid_constant__ EvalP
   }
 }
 
+// ---------------------------------------------------------------- learning-curve quantile statistics (utils.py:132-145)
+// plot_learning_curve_conf: per run, pandas' ewm(halflife).mean() (adjust=True) of the per-epoch mean reward, summed over the
+// agents; per epoch the median / quartiles of that over the runs.  Here: thread = run carries the run's EWM numerator
+// num_t = num_{t-1} * (1 - alpha) + x_t across epochs (and calls), x_t = ((0 + r_0) + r_1) + ... the agents' log entries;
+// the value num_t / den_t (den_t = sum_{i<=t} (1-alpha)^i is the same for every run: a host-computed array) goes into a
+// fixed-bin histogram per epoch.  Counts are exact integers, so sharded histograms add up (NCCL all-reduce).
+struct CurveHistParams {
+  const double* rewards_log;  // [n_runs][E][n]
+  long long n_runs;
+  int E, n;
+  double decay;               // 1 - alpha = 0.5^(1/halflife)
+  const double* den;          // [E]
+  double* ewm_num;            // [n_runs] in/out
+  double lo, inv_width;       // bin = floor((v - lo) * inv_width), clamped to [0, n_bins)
+  int n_bins;
+  unsigned long long* hist;   // [E][n_bins] +=
+};
+
+__global__ void __launch_bounds__(256) curve_hist(const CurveHistParams p) {
+  const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < p.n_runs;
+  const int lane = threadIdx.x & 31;
+  double num = live ? p.ewm_num[r] : 0.0;
+  const double* row = p.rewards_log + (live ? r : 0) * (long long)p.E * p.n;
+  for (int e = 0; e < p.E; ++e) {
+    int bin = -1 - lane;  // idle lanes match nobody
+    if (live) {
+      double x = 0.0;
+      for (int i = 0; i < p.n; ++i) x = __dadd_rn(x, row[(long long)e * p.n + i]);
+      num = __dadd_rn(__dmul_rn(num, p.decay), x);
+      const double v = __ddiv_rn(num, p.den[e]);
+      const double b = floor(__dmul_rn(__dsub_rn(v, p.lo), p.inv_width));
+      bin = b < 0.0 ? 0 : (b >= (double)p.n_bins ? p.n_bins - 1 : (int)b);
+      if (!(b == b)) bin = p.n_bins - 1;  // NaN rewards land in the last bin
+    }
+    const unsigned same = __match_any_sync(kFull, bin);  // one atomic per distinct bin of the warp
+    if (live && (same & ((1u << lane) - 1u)) == 0u) atomicAdd(p.hist + (long long)e * p.n_bins + bin, (unsigned long long)__popc(same));
+  }
+  if (live) p.ewm_num[r] = num;
+}
+
 }  // namespace thrl

@@ -192,6 +192,50 @@ class RunBatch:
         return actions, rewards
 
 
+def save_checkpoint(batch, path, extra=None, extra_arrays=None):
+    """Writes the batch's whole state (tables, counters, epsilon, price, hyper-parameters, MLP slab, transition rings) and
+    its position (epoch, seed, global run ids) as one packed file (th_rl_b200/checkpoint.py)."""
+    from . import checkpoint
+    arrays = {"q": batch.q.cpu().numpy(), "counter": batch.counter.cpu().numpy().view(np.uint32),
+              "eps": batch.eps.cpu().numpy(), "price": batch.price.cpu().numpy()}
+    for name in ("hp", "mlp", "ring"):
+        t = getattr(batch, name)
+        if t is not None:
+            arrays[name] = t.cpu().numpy()
+    for name, a in (extra_arrays or {}).items():  # caller's arrays (e.g. stats.CurveHistogram.num) travel as "x_<name>"
+        arrays["x_" + name] = np.ascontiguousarray(a)
+    header = dict(abi_version=abi.THRL_ABI_VERSION, config=batch.config, n_runs=batch.n_runs, run_id0=batch.run_id0,
+                  seed=batch.seed, epoch=batch.epoch, table_dtype="f64" if batch.dtype == torch.float64 else "f32",
+                  run_stride=int(batch.game.run_stride), mlp_stride=int(batch.game.mlp_stride), extra=extra or {})
+    return checkpoint.write_pack(path, header, arrays)
+
+
+def load_checkpoint(path, device="cuda:0"):
+    """-> (RunBatch positioned where the checkpoint was taken, the header's `extra` dict, the caller's extra arrays).  Scanning on from it gives
+    bit-identical results to a run that was never interrupted (Philox streams are keyed by global run id and epoch)."""
+    from . import checkpoint
+    hdr, arr = checkpoint.read_pack(path)
+    dtype = torch.float64 if hdr["table_dtype"] == "f64" else torch.float32
+    b = RunBatch(hdr["config"], hdr["n_runs"], device=device, dtype=dtype, run_id0=hdr["run_id0"], seed=hdr["seed"],
+                 hp=arr.get("hp"))
+    if int(b.game.run_stride) != hdr["run_stride"] or int(b.game.mlp_stride) != hdr["mlp_stride"]:
+        raise ValueError("%s was written with another slab layout (run_stride %d / mlp_stride %d, this library: %d / %d)"
+                         % (path, hdr["run_stride"], hdr["mlp_stride"], b.game.run_stride, b.game.mlp_stride))
+
+    def put(dst, src):
+        dst.copy_(torch.from_numpy(np.ascontiguousarray(src)).reshape(dst.shape))
+    put(b.q, arr["q"])
+    put(b.counter, np.asarray(arr["counter"]).view(np.int32))
+    put(b.eps, arr["eps"])
+    put(b.price, arr["price"])
+    if b.mlp is not None:
+        put(b.mlp, arr["mlp"])
+    if b.ring is not None:
+        put(b.ring, arr["ring"])
+    b.epoch = int(hdr["epoch"])
+    return b, hdr.get("extra", {}), {k[2:]: np.array(v) for k, v in arr.items() if k.startswith("x_")}
+
+
 class HostState:
     """Per-run state in pinned host memory (what a host-side caller owns between calls)."""
 

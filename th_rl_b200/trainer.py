@@ -189,6 +189,16 @@ class TrainResult:
     def __init__(self, batch, rewards_log, actions_log, stats):
         self.batch, self.rewards_log, self.actions_log, self.stats = batch, rewards_log, actions_log, stats
 
+    curve_hist = None  # [epochs, bins] int64: histogram over all runs of the EWM-smoothed total reward (quantile_bins > 0)
+
+    def quantile_curves(self, qs=(0.5, 0.75, 0.25)):
+        """Per-epoch quantiles over the runs of the smoothed total reward: what th_rl/utils.py:141-143 plots as
+        median / 75th / 25th, to the histogram's bin width."""
+        from . import stats as curve_stats
+        if self.curve_hist is None:
+            raise ValueError("train_many was called without quantile_bins")
+        return curve_stats.quantiles_from_hist(self.curve_hist, qs, *self.curve_range)
+
     def mean_curves(self):
         """Cross-run mean / std of the per-epoch mean reward and action, from the exact fixed-point sums."""
         R = float(self.n_runs_total)
@@ -205,12 +215,18 @@ def shard_bounds(total_runs, rank, world):
 
 
 def train_many(config, runs, epochs=None, *, seed=0, dtype=None, device=None, log_runs=0, hp=None, chunk_epochs=None,
-               export_dir=None, export_runs=0, process_group=None):
+               export_dir=None, export_runs=0, process_group=None, quantile_bins=0, halflife=1000.0, checkpoint_to=None,
+               resume_from=None):
     """`runs` independent runs of one config as a batched device scan (the reference plays them one after another,
     th_rl/main.py:19-21).  Under torch.distributed each rank owns a contiguous shard of the global run ids; results do not
     depend on the sharding because Philox counters use global ids, and the per-epoch statistics are exact integer sums that
     are all-reduced (NCCL on GPUs).  Returns a TrainResult; with export_dir, the first `export_runs` runs are also written
-    in the reference's runs/<cfg>/<i>/ layout."""
+    in the reference's runs/<cfg>/<i>/ layout.
+    quantile_bins > 0: also the per-epoch histogram over ALL runs of the EWM-smoothed total reward (th_rl/utils.py:132-145,
+    stats.CurveHistogram) -> TrainResult.curve_hist / quantile_curves().
+    checkpoint_to: this rank's shard is written as one packed file (checkpoint.py; `{rank}` in the name is substituted) when the
+    epochs are done; resume_from: start from such a file instead of a fresh initial state -- `epochs` more epochs are played and
+    the result equals an uninterrupted run bit for bit."""
     import torch
     import torch.distributed as dist
     from . import engine
@@ -224,25 +240,55 @@ def train_many(config, runs, epochs=None, *, seed=0, dtype=None, device=None, lo
         device = "cuda:%d" % (int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0)
     dtype = dtype or torch.float32
     hp_local = None if hp is None else numpy.asarray(hp, numpy.float64)[lo:hi]
-    batch = engine.RunBatch(config, hi - lo, device=device, dtype=dtype, seed=seed, run_id0=lo, hp=hp_local).init_device()
+    from . import stats as curve_stats
+    ewm_extra = None
+    if resume_from is not None:
+        batch, extra, extra_arrays = engine.load_checkpoint(str(resume_from).format(rank=rank), device=device)
+        if batch.n_runs != hi - lo or batch.run_id0 != lo:
+            raise ValueError("checkpoint holds runs [%d, %d), this rank owns [%d, %d)" % (batch.run_id0, batch.run_id0 + batch.n_runs, lo, hi))
+        ewm_extra = dict(extra["curve_hist"], num=extra_arrays["curve_num"]) if "curve_hist" in extra else None
+    else:
+        batch = engine.RunBatch(config, hi - lo, device=device, dtype=dtype, seed=seed, run_id0=lo, hp=hp_local).init_device()
     n = batch.game.n_agents
-    n_log = max(0, min(int(max(log_runs, export_runs)) - lo, hi - lo))
+    R = hi - lo
+    n_log = max(0, min(int(max(log_runs, export_runs)) - lo, R))
     rl = numpy.zeros((n_log, epochs, n))
     al = numpy.zeros((n_log, epochs, n))
     stats = torch.zeros((epochs, n, abi.THRL_STATS_K), dtype=torch.int64, device=batch.device)
+    ch = hist = None
+    if quantile_bins:
+        ch = curve_stats.CurveHistogram(config, R, batch.device, halflife=halflife, bins=quantile_bins)
+        hist = torch.zeros((epochs, ch.bins), dtype=torch.int64, device=batch.device)
+        if ewm_extra is not None:  # resume the smoothing where the checkpoint left it
+            ch.num.copy_(torch.from_numpy(numpy.asarray(ewm_extra["num"], numpy.float64)))
+            ch.den_last, ch.epoch = float(ewm_extra["den_last"]), int(ewm_extra["epoch"])
     chunk = int(chunk_epochs or epochs or 1)
+    if ch is not None:  # every run's log row lives on the device for one chunk: keep it below ~2 GB
+        chunk = max(1, min(chunk, (1 << 31) // max(1, R * n * 16)))
     e0 = 0
     while e0 < epochs:
         E = min(chunk, epochs - e0)
-        out = batch.scan(E, n_log_runs=n_log, stats=stats[e0:e0 + E])
+        out = batch.scan(E, n_log_runs=R if ch is not None else n_log, stats=stats[e0:e0 + E])
         if n_log:
-            rl[:, e0:e0 + E] = out.rewards_log.cpu().numpy()
-            al[:, e0:e0 + E] = out.actions_log.cpu().numpy()
+            rl[:, e0:e0 + E] = out.rewards_log[:n_log].cpu().numpy()
+            al[:, e0:e0 + E] = out.actions_log[:n_log].cpu().numpy()
+        if ch is not None:
+            ch.update(out.rewards_log, hist[e0:e0 + E])
         e0 += E
     if world > 1:
         dist.all_reduce(stats, group=process_group)
+        if hist is not None:
+            dist.all_reduce(hist, group=process_group)
+    if checkpoint_to is not None:
+        extra, extra_arrays = {}, {}
+        if ch is not None:
+            extra["curve_hist"] = dict(den_last=ch.den_last, epoch=ch.epoch, halflife=ch.halflife)
+            extra_arrays["curve_num"] = ch.num.cpu().numpy()
+        engine.save_checkpoint(batch, str(checkpoint_to).format(rank=rank), extra=extra, extra_arrays=extra_arrays)
     res = TrainResult(batch, rl, al, stats.cpu().numpy())
     res.n_runs_total = int(runs)
+    if ch is not None:
+        res.curve_hist, res.curve_range, res.halflife = hist.cpu().numpy(), (ch.lo, ch.hi), ch.halflife
     if export_dir is not None:
         export_runs_to(export_dir, config, res, min(int(export_runs), hi) - lo, first_index=lo)
     return res

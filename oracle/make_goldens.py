@@ -145,6 +145,15 @@ CASES = {
     "c5_aa_bench_seed18": (dict(agents=[dict(name="ActorCritic", gamma=0.98, actions=21, states=1, action_range=[0.2, 0.4]),
                                         dict(name="ActorCritic", gamma=0.98, actions=21, states=1, action_range=[0.2, 0.4])],
                                 environment=_env(), training=dict(epochs=20, print_freq=1000)), 18),
+    # demand noise with MLP agents: the network input is a continuous price (environments.py:28-31 with agents.py:148-163):
+    # the shipped pairing QTable + Reinforce, and ActorCritic + CAC
+    "noise_qr_seed19": (dict(agents=[_agent(), dict(name="Reinforce", gamma=0.9, actions=21, states=1, action_range=[0.2, 0.4],
+                                                    min_memory=200)],
+                             environment=_env(noise_prob=0.3), training=dict(epochs=8, print_freq=1000)), 19),
+    "noise_ac_seed20": (dict(agents=[dict(name="ActorCritic", gamma=0.9, actions=7, states=1, action_range=[0.1, 0.3],
+                                          min_memory=90, capacity=120),
+                                     dict(name="CAC", gamma=0.5, states=1, action_range=[0.05, 0.2], min_memory=60)],
+                             environment=_env(noise_prob=0.2, max_steps=30), training=dict(epochs=12, print_freq=1000)), 20),
 }
 
 EVAL_ITERS = 3  # episodes of utils.play_game recorded per case (noise-free cases only)

@@ -57,3 +57,31 @@ def uses_lattice_kernel(cfg):
             return False
         joint *= g.agent[i].actions
     return joint <= 1024
+
+
+def uses_pwc_kernel(cfg):
+    """Games the library plays with the interval-table kernel (th_rl_b200/csrc/thrl_scan_pwc.cuh; mirrors plan_pwc in thrl.cu):
+    games with MLP agents that the lattice kernel does not take -- demand noise, CAC agents, QTable agents whose batches span
+    episodes -- with at most 256 hidden units and 32 head columns per MLP agent.  Same tolerance statement as the lattice
+    kernel; THRL_KERNEL=mixed selects the order-exact kernel, THRL_KERNEL=pwc forces this one on lattice games too."""
+    from oracle import oracle
+    from th_rl_b200 import abi
+    if uses_lattice_kernel(cfg):
+        return False
+    return pwc_can_play(cfg)
+
+
+def pwc_can_play(cfg):
+    from oracle import oracle
+    from th_rl_b200 import abi
+    g = oracle.layout(cfg)
+    any_mlp = False
+    for i in range(g.n_agents):
+        s = g.agent[i]
+        if s.kind == abi.THRL_AGENT_QTABLE:
+            continue
+        any_mlp = True
+        nc = 3 if s.kind == abi.THRL_AGENT_CAC else s.actions + (1 if s.kind == abi.THRL_AGENT_ACTORCRITIC else 0)
+        if s.hidden < 1 or s.hidden > 256 or nc > 32:
+            return False
+    return any_mlp

@@ -11,24 +11,29 @@ from th_rl_b200 import abi
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["auto", "generic", "lpc", "lpc16", "mixed"], autouse=True)
+@pytest.fixture(params=["auto", "generic", "lpc", "lpc16", "mixed", "pwc"], autouse=True)
 def kernel_choice(request, monkeypatch):
     """Every test runs with the default dispatch and with each alternative kernel forced, so all kernels are held to the
-    same bar.  Games of the lattice kernel (conftest.uses_lattice_kernel) run twice: default (lattice kernel, float32
-    tolerance on the MLP state) and "mixed" (order-exact kernel, bit-exact against the oracle)."""
-    from conftest import load_golden, uses_lattice_kernel
+    same bar.  Games of the lattice kernel (conftest.uses_lattice_kernel) run three times: default (lattice kernel, float32
+    tolerance on the MLP state), "pwc" (interval-table kernel forced, same tolerance) and "mixed" (order-exact kernel,
+    bit-exact against the oracle); games of the interval-table kernel (conftest.uses_pwc_kernel) twice: default and "mixed"."""
+    from conftest import load_golden, uses_lattice_kernel, uses_pwc_kernel, pwc_can_play
     monkeypatch.delenv("THRL_KERNEL", raising=False)
     monkeypatch.delenv("THRL_LPC_GL", raising=False)
     name = getattr(request.node, "callspec", None) and request.node.callspec.params.get("golden")
-    lattice = (bool(name) and uses_lattice_kernel(load_golden(name)["config"])) or request.node.get_closest_marker("lattice_game") is not None
-    if request.param == "mixed" and not lattice:
+    cfg = load_golden(name)["config"] if name else None
+    lattice = (cfg is not None and uses_lattice_kernel(cfg)) or request.node.get_closest_marker("lattice_game") is not None
+    tolerant = lattice or (cfg is not None and uses_pwc_kernel(cfg))
+    if request.param == "mixed" and not tolerant:
         pytest.skip("the order-exact MLP kernel is already the default here")
-    if lattice and request.param in ("generic", "lpc", "lpc16"):
+    if request.param == "pwc" and not (lattice and (cfg is None or pwc_can_play(cfg))):
+        pytest.skip("the interval-table kernel is the default here, or does not apply")
+    if tolerant and request.param in ("generic", "lpc", "lpc16"):
         pytest.skip("same dispatch as the default for this game")
     if request.param == "generic":
         monkeypatch.setenv("THRL_KERNEL", "generic")
-    elif request.param == "mixed":
-        monkeypatch.setenv("THRL_KERNEL", "mixed")
+    elif request.param in ("mixed", "pwc"):
+        monkeypatch.setenv("THRL_KERNEL", request.param)
     elif request.param.startswith("lpc"):
         monkeypatch.setenv("THRL_KERNEL", "lpc")  # lane-per-chain kernel where it applies (else the general kernel)
         if request.param == "lpc16":
@@ -50,12 +55,13 @@ def kernel_choice(request, monkeypatch):
 #    of the distance Adam can have moved them, 0.25 * lr * steps; measured: 1 weight in 1.5e5 at 1e-5 (lr = 2e-4).
 PWL_ATOL = 1e-6
 PWL_RTOL = 1e-6
-PWL_MOMENT_TOL = {1: 2e-5, 2: 3e-4}  # by agent kind: Reinforce, ActorCritic
+PWL_MOMENT_TOL = {1: 2e-5, 2: 3e-4, 3: 3e-4}  # by agent kind: Reinforce, ActorCritic, CAC (value head at 1000 like ActorCritic)
 
 
 def _lattice(cfg, kernel_choice):
-    from conftest import uses_lattice_kernel
-    return kernel_choice != "mixed" and uses_lattice_kernel(cfg)
+    """The game runs on one of the two re-associating MLP kernels (lattice or interval-table): tolerance instead of bits."""
+    from conftest import uses_lattice_kernel, uses_pwc_kernel
+    return kernel_choice != "mixed" and (uses_lattice_kernel(cfg) or uses_pwc_kernel(cfg))
 
 
 def _mlp_close(game, got, ref):
@@ -92,7 +98,11 @@ def _check_dispatch(cfg):
     from th_rl_b200 import _lib
     forced, got = os.environ.get("THRL_KERNEL"), _lib.last_kernel()
     if any(a["name"] != "QTable" for a in cfg["agents"]):
-        assert got == ("pwl" if uses_lattice_kernel(cfg) and forced != "mixed" else "mixed"), got
+        from conftest import uses_pwc_kernel
+        want = "mixed"
+        if forced != "mixed":
+            want = "pwl" if uses_lattice_kernel(cfg) and forced != "pwc" else ("pwc" if uses_pwc_kernel(cfg) or forced == "pwc" else "mixed")
+        assert got == want, (got, want)
     elif forced == "generic":
         assert got == "generic", got
     else:

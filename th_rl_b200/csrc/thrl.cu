@@ -25,6 +25,7 @@
 #include "thrl_scan_lpc.cuh"
 #include "thrl_scan_mixed.cuh"
 #include "thrl_scan_pwl.cuh"
+#include "thrl_scan_pwc.cuh"
 #include "thrl_aux_kernels.cuh"
 
 namespace {
@@ -866,6 +867,95 @@ int launch_pwl(thrl::PwlParams& p, int warps, bool f64, const DeviceInfo& dev, c
   return THRL_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ continuous-state MLP (pwc) launch
+// Fills p (layouts) when the interval-table kernel plays the game: at least one MLP agent, every MLP agent with at most
+// kPwcMaxHidden hidden units and at most 32 head columns.  It takes what the lattice kernel cannot: demand noise, CAC agents,
+// QTable agents whose batches span episodes.
+bool plan_pwc(thrl::PwcParams* p, bool noisy, size_t elem, int smem_optin, int* warps) {
+  const ThrlGame& G = p->game;
+  const int n = G.n_agents, T = G.max_steps;
+  p->noisy = noisy ? 1 : 0;
+  p->Hp = (G.ring_len > 0 ? G.ring_len : 1) + 1;
+  const int Hp = p->Hp;
+  int lut = 0, Hmax = 0, ncpmax = 0, Pmax = 1, capmax = 0, nm = 0;
+  long long w = 0;
+  int o = 0;
+  p->off_P = o;    o += align_up(Hp * 8, 16);
+  p->off_newa = o; o += noisy ? align_up(T * 8, 16) : 0;
+  p->off_hp = o;   o += align_up(n * 5 * 8, 16);
+  p->off_old = o;  o += align_up(Hp * (int)elem, 16);
+  p->off_pre = o;  o += align_up(T * n * 4, 16);
+  p->off_zf = o;   o += align_up(T * n * 4, 16);
+  p->off_row = o;  o += align_up((Hp + 1) * 2, 16);
+  p->off_act = o;  o += align_up(n * Hp, 16);
+  for (int i = 0; i < n; ++i) {
+    const ThrlAgentSpec& s = G.agent[i];
+    lut += s.actions;
+    p->off_th[i] = 0; p->ncp[i] = 0; p->ws_tab[i] = 0; p->ws_ord[i] = 0;
+    if (s.kind == THRL_AGENT_QTABLE) continue;
+    const int H = s.hidden;
+    const int nc = s.kind == THRL_AGENT_CAC ? 3 : s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? 1 : 0);
+    if (H < 1 || H > thrl::kPwcMaxHidden || nc > 32 || (s.kind != THRL_AGENT_CAC && s.actions < 1)) return false;
+    ++nm;
+    const int P = s.kind == THRL_AGENT_CAC ? 5 * H + 3 : 2 * H + s.actions * H + s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? H + 1 : 0);
+    p->ncp[i] = align_up(nc, 2);
+    p->off_th[i] = o; o += align_up(H * 4, 16);
+    p->ws_tab[i] = w; w += align_up((H + 1) * p->ncp[i] * 16, 256);
+    p->ws_ord[i] = w; w += align_up(H * 2, 256);
+    if (H > Hmax) Hmax = H;
+    if (p->ncp[i] > ncpmax) ncpmax = p->ncp[i];
+    if (P > Pmax) Pmax = P;
+    if (G.mlp_buffer_len[i] > capmax) capmax = G.mlp_buffer_len[i];
+  }
+  if (nm == 0) return false;
+  p->lut_total = lut;
+  p->cta_bytes = align_up(2 * lut * 8, 16);
+  p->warp_bytes = o;
+  p->ws_bkt = w;  w += align_up((Hmax + 2) * ncpmax * 16, 256);
+  p->ws_grad = w; w += align_up(Pmax * 4, 256);
+  p->ws_xs = w;   w += (long long)(capmax > 0 ? capmax : 1) * 16;
+  p->ws_warp_bytes = (w + 255) / 256 * 256;
+  const int fit = (smem_optin - p->cta_bytes) / p->warp_bytes;
+  if (fit < 1) return false;
+  *warps = fit > 16 ? 16 : fit;
+  return true;
+}
+
+template <typename QT>
+int launch_pwc(thrl::PwcParams& p, int warps, const DeviceInfo& dev, cudaStream_t stream) {
+  int grid = dev.sms;
+  {
+    const long long slots = (long long)dev.sms * warps;
+    const long long rounds = (p.n_runs + slots - 1) / slots;
+    const long long per_round = (p.n_runs + rounds - 1) / rounds;
+    warps = (int)((per_round + dev.sms - 1) / dev.sms);
+    if (warps < 1) warps = 1;
+    grid = (int)((per_round + warps - 1) / warps);
+    if (grid > dev.sms) grid = dev.sms;
+  }
+  const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
+  int device = 0;
+  CUDA_TRY(cudaGetDevice(&device));
+  if (device < 0 || device >= 64) return fail(THRL_ERR_BAD_ARGS, "device index %d", device);
+  cudaMemPool_t pool = pwl_pool(device, true);
+  if (!pool) return fail(THRL_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+  void* ws = nullptr;
+  CUDA_TRY(cudaMallocFromPoolAsync(&ws, (size_t)grid * warps * (size_t)p.ws_warp_bytes, pool, stream));
+  p.ws = (unsigned char*)ws;
+  auto kern = thrl::mlp_scan_pwc<QT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) {
+    g_last_kernel = "pwc";
+    g_last_wave = (long long)grid * warps;
+    kern<<<grid, warps * 32, smem, stream>>>(p);
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(ws, stream);
+  CUDA_TRY(e);
+  g_launches.fetch_add(1);
+  return THRL_OK;
+}
+
 // Plans (structure tables + shared-memory layouts) are functions of the laid-out game, the cell size and the noise flag only:
 // they are built once and copied per call (train_one's small chunks and the host pipeline launch the same game many times).
 template <typename P>
@@ -895,6 +985,7 @@ struct PlanCache {
 };
 PlanCache<thrl::Lut2Params> g_lut2_plans;
 PlanCache<thrl::PwlParams> g_pwl_plans;
+PlanCache<thrl::PwcParams> g_pwc_plans;
 
 int check_args(const ThrlScanArgs* a) {
   if (!a || !a->game) return fail(THRL_ERR_BAD_ARGS, "args/game is NULL");
@@ -989,7 +1080,8 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (p.game.mlp_stride > 0) {  // games with MLP agents
     const char* forced = getenv("THRL_KERNEL");
-    if (!(forced && strcmp(forced, "mixed") == 0)) {  // lattice kernel where it applies (thrl_scan_pwl.cuh)
+    const bool want_mixed = forced && strcmp(forced, "mixed") == 0, want_pwc = forced && strcmp(forced, "pwc") == 0;
+    if (!want_mixed && !want_pwc) {  // lattice kernel where it applies (thrl_scan_pwl.cuh)
       thrl::PwlParams* w = new thrl::PwlParams();
       std::unique_ptr<thrl::PwlParams> hold_w(w);
       int warps = 0;
@@ -1005,6 +1097,24 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
         w->trace_actions = p.trace_actions; w->trace_rewards = p.trace_rewards; w->trace_prices = p.trace_prices;
         w->mlp = a->mlp;
         return launch_pwl(*w, warps, a->table_dtype == THRL_F64, dev, stream);
+      }
+    }
+    if (!want_mixed) {  // continuous prices (demand noise, CAC, pending QTable batches): interval-table kernel (thrl_scan_pwc.cuh)
+      thrl::PwcParams* w = new thrl::PwcParams();
+      std::unique_ptr<thrl::PwcParams> hold_w(w);
+      int warps = 0;
+      const int elem = a->table_dtype == THRL_F64 ? 8 : 4;
+      if (g_pwc_plans.get(p.game, elem, p.noisy, dev.smem_optin, w, &warps, [&](thrl::PwcParams* q, int* wq) {
+            return plan_pwc(q, p.noisy != 0, (size_t)elem, dev.smem_optin, wq);
+          })) {
+        w->n_runs = p.n_runs; w->run_id0 = p.run_id0; w->epoch_begin = p.epoch_begin; w->E = p.E; w->rng_mode = p.rng_mode;
+        w->k0 = p.k0; w->k1 = p.k1;
+        w->q = p.q; w->counter = p.counter; w->eps = p.eps; w->price = p.price; w->hp = p.hp;
+        w->replay_u = p.replay_u; w->replay_ra = p.replay_ra; w->replay_new_a = p.replay_new_a;
+        w->rewards_log = p.rewards_log; w->actions_log = p.actions_log; w->n_log_runs = p.n_log_runs; w->stats = p.stats;
+        w->trace_actions = p.trace_actions; w->trace_rewards = p.trace_rewards; w->trace_prices = p.trace_prices;
+        w->mlp = a->mlp; w->ring = p.ring; w->ring_bytes = p.ring_bytes;
+        return a->table_dtype == THRL_F64 ? launch_pwc<double>(*w, warps, dev, stream) : launch_pwc<float>(*w, warps, dev, stream);
       }
     }
     thrl::MixedParams* m = new thrl::MixedParams();

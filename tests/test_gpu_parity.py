@@ -64,7 +64,13 @@ def _lattice(cfg, kernel_choice):
     return kernel_choice != "mixed" and (uses_lattice_kernel(cfg) or uses_pwc_kernel(cfg))
 
 
-def _mlp_close(game, got, ref):
+# Free-running games with CAC agents: the trajectories themselves differ in the last float32 bits (see _lattice_philox_case)
+CAC_TRAJ_ATOL = 2e-5
+CAC_TRAJ_RTOL = 2e-5
+CAC_TRAJ_MOMENT_SCALE = 4.0  # Adam moments of slightly different sample sets: measured 1.8e-5 of the max-norm, bar 4 x 3e-4
+
+
+def _mlp_close(game, got, ref, moment_scale=1.0):
     """MLP slabs [R, stride] agree (see the tolerance statement above); step counter and buffer header are equal."""
     from th_rl_b200 import abi as _abi
     for i in range(game.n_agents):
@@ -78,7 +84,7 @@ def _mlp_close(game, got, ref):
         for k in (1, 2):  # exp_avg, exp_avg_sq
             m, mr = got[:, o + k * P:o + (k + 1) * P].astype(np.float64), ref[:, o + k * P:o + (k + 1) * P].astype(np.float64)
             scale = np.abs(mr).max(axis=1, keepdims=True) + 1e-30
-            assert np.all(np.abs(m - mr) <= PWL_MOMENT_TOL[s.kind] * scale), (i, k, float((np.abs(m - mr) / scale).max()))
+            assert np.all(np.abs(m - mr) <= moment_scale * PWL_MOMENT_TOL[s.kind] * scale), (i, k, float((np.abs(m - mr) / scale).max()))
         w, wr = got[:, o:o + P].astype(np.float64), ref[:, o:o + P].astype(np.float64)
         err = np.abs(w - wr)
         loose = err > PWL_ATOL + PWL_RTOL * np.abs(wr)
@@ -260,18 +266,35 @@ def _lattice_philox_case(cfg, R, E, seed, run_id0=0, chunks=None):
         return res
 
     o = run([E])
-    same = (o["trace_actions"] == ref.trace_actions).reshape(R, -1).all(axis=1)
+    cac = [i for i in range(game.n_agents) if game.agent[i].kind == abi.THRL_AGENT_CAC]
+    disc = [i for i in range(game.n_agents) if i not in cac]
+    same = (o["trace_actions"][..., disc] == ref.trace_actions[..., disc]).reshape(R, -1).all(axis=1)
     # a run leaves the oracle's trajectory only when a `cdf > u` comparison falls within float32 rounding of a tie (~1e-7 per
     # draw): over R runs x E epochs x T steps x n agents draws that is at most one run in a few dozen
     assert same.sum() >= R - max(1, R // 24), "too many runs left the oracle's trajectory: %d of %d agree" % (same.sum(), R)
-    for f in ("trace_prices", "trace_rewards", "rewards_log", "actions_log"):
-        assert np.array_equal(o[f][same], getattr(ref, f)[same]), f
-    assert np.array_equal(o["price"][same], ref.price[same])
-    for f in ("q", "counter", "eps"):  # QTable agents of the same game: bit for bit
-        assert np.array_equal(o[f][same], getattr(ref, f)[same]), f
-    _mlp_close(game, o["mlp"][same], ref.mlp[same])
-    if same.all():
-        assert np.array_equal(o["stats"], ref.stats)
+    if cac:
+        # A CAC action is a float32 sigmoid(mu + std * z) of head outputs that this kernel sums in another order, so it differs
+        # from the oracle's in the last bits, and with it every later price: the trajectories stay within float32 rounding of each
+        # other instead of being equal (measured: actions within 3e-6, prices within 5e-6 over 12 epochs).
+        fa, fr = o["trace_actions"][..., cac].view(np.float32), ref.trace_actions[..., cac].view(np.float32)
+        assert np.abs(fa - fr)[same].max() <= CAC_TRAJ_ATOL, float(np.abs(fa - fr)[same].max())
+        for f in ("trace_prices", "trace_rewards", "rewards_log", "actions_log"):
+            assert np.allclose(o[f][same], getattr(ref, f)[same], rtol=CAC_TRAJ_RTOL, atol=CAC_TRAJ_ATOL), f
+        assert np.allclose(o["price"][same], ref.price[same], rtol=CAC_TRAJ_RTOL, atol=CAC_TRAJ_ATOL)
+        assert np.array_equal(o["counter"][same].sum(axis=1), ref.counter[same].sum(axis=1))
+        assert np.array_equal(o["eps"][same], ref.eps[same])
+        if game.run_stride:  # a QTable agent next to it sees rewards that differ in the last bits
+            assert np.allclose(o["q"][same], ref.q[same], rtol=1e-5, atol=1e-5)
+        _mlp_close(game, o["mlp"][same], ref.mlp[same], moment_scale=CAC_TRAJ_MOMENT_SCALE)
+    else:
+        for f in ("trace_prices", "trace_rewards", "rewards_log", "actions_log"):
+            assert np.array_equal(o[f][same], getattr(ref, f)[same]), f
+        assert np.array_equal(o["price"][same], ref.price[same])
+        for f in ("q", "counter", "eps"):  # QTable agents of the same game: bit for bit
+            assert np.array_equal(o[f][same], getattr(ref, f)[same]), f
+        _mlp_close(game, o["mlp"][same], ref.mlp[same])
+        if same.all():
+            assert np.array_equal(o["stats"], ref.stats)
     o3 = run([E], trace=False)  # the episode loop without the per-step trace stores is a separate code path
     for f in o3:
         assert np.array_equal(o[f].view(np.uint8), o3[f].view(np.uint8)), "untraced call differs in " + f
@@ -430,7 +453,7 @@ def test_c5_bench_shape_matches_oracle(kernel_choice):
     stated float32 tolerance of the oracle, chunked == single call; THRL_KERNEL=mixed bit-equal to the oracle."""
     import bench
     cfg = bench._c5_cfg(21)
-    if kernel_choice == "auto":
+    if kernel_choice in ("auto", "pwc"):  # lattice kernel; interval-table kernel forced onto the same game
         _lattice_philox_case(cfg, 24, 21, seed=77, run_id0=3, chunks=[4, 9, 8])
     elif kernel_choice == "mixed":
         _philox_case(cfg, 12, 21, np.float32, seed=77, run_id0=3)
@@ -679,7 +702,8 @@ class _GuardedArena:
 
 
 GUARD_CASES = ["c1_example_2q_seed0", "noise_2q_seed3", "hetero_3q_seed4", "overflow_2q_seed5", "c4_8q_seed7",
-               "mixed_qr_small_seed9", "mixed_arq_seed12", "mixed_cc_seed14", "mlp_aa_seed15", "mlp_raa_seed17"]
+               "mixed_qr_small_seed9", "mixed_arq_seed12", "mixed_cc_seed14", "mlp_aa_seed15", "mlp_raa_seed17", "noise_qr_seed19",
+               "noise_ac_seed20"]
 
 
 @pytest.mark.parametrize("case", GUARD_CASES)

@@ -899,7 +899,7 @@ bool plan_pwc(thrl::PwcParams* p, bool noisy, size_t elem, int smem_optin, int* 
     ++nm;
     const int P = s.kind == THRL_AGENT_CAC ? 5 * H + 3 : 2 * H + s.actions * H + s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? H + 1 : 0);
     p->ncp[i] = align_up(nc, 2);
-    p->off_th[i] = o; o += align_up(H * 4, 16);
+    p->off_th[i] = o; o += (((H + 31) / 32) * 32 + 32) * 4;  // ranked thresholds padded to whole blocks, then the 32 block maxima
     p->ws_tab[i] = w; w += align_up((H + 1) * p->ncp[i] * 16, 256);
     p->ws_ord[i] = w; w += align_up(H * 2, 256);
     if (H > Hmax) Hmax = H;
@@ -910,10 +910,12 @@ bool plan_pwc(thrl::PwcParams* p, bool noisy, size_t elem, int smem_optin, int* 
   if (nm == 0) return false;
   p->lut_total = lut;
   p->cta_bytes = align_up(2 * lut * 8, 16);
+  p->off_hist = o; o += align_up((Hmax + 2) * 4, 16);
   p->warp_bytes = o;
   p->ws_bkt = w;  w += align_up((Hmax + 2) * ncpmax * 16, 256);
   p->ws_grad = w; w += align_up(Pmax * 4, 256);
-  p->ws_xs = w;   w += (long long)(capmax > 0 ? capmax : 1) * 16;
+  p->ws_xs = w;   w += align_up((capmax > 0 ? capmax : 1) * 16, 256);
+  p->ws_evs = w;  w += (long long)(capmax > 0 ? capmax : 1) * 8;
   p->ws_warp_bytes = (w + 255) / 256 * 256;
   const int fit = (smem_optin - p->cta_bytes) / p->warp_bytes;
   if (fit < 1) return false;

@@ -74,7 +74,11 @@ __device__ __forceinline__ float det_expf(float x) {
   p = __fmul_rn(p, r);
   p = __fadd_rn(p, r);
   p = __fadd_rn(p, 1.0f);
-  return ldexpf(p, (int)kf);
+  // p * 2^k: one exact-or-correctly-rounded multiply wherever 2^k is a float (the same value ldexpf returns, subnormal
+  // results included; the library routine costs ~40 instructions)
+  const int k = (int)kf;
+  if (k >= -126 && k <= 128) return __fmul_rn(p, __int_as_float((k + 127) << 23));
+  return ldexpf(p, k);
 }
 
 // pi(x) (agents.py:148-152) with staged parameters sp = [w1 (H)] [b1 (H)] [WT (H x A)] [bp (A)].

@@ -12,9 +12,9 @@
 //     consecutive thresholds every head output is z_c(s) = S1*s + S0 (f64 running sums over the ranked units, bias folded in).
 // Acting: r = #{j: th[j] <= s} (one compare per unit, warp-wide add), one table row (lane = head column), softmax + inverse CDF
 // (Reinforce / ActorCritic) or tanh / softplus / sigmoid (CAC): O(H/32 + A) per step instead of O(H*A).
-// Updating: each buffered transition's head gradient dL/dz (the oracle's float32 per-sample coefficients) is added into the
-// bucket of its interval (f64, buffer order); one prefix sum over the H+1 buckets gives, at every unit's rank, the sums over
-// the samples the unit is active on: M0 = sum dz, M1 = sum dz*s, hence d/dW[c][j] = w1_j*M1 + b1_j*M0, d/db1_j = sum_c W[c][j]*M0,
+// Updating: the buffered transitions are put in interval order (stable counting sort) and swept once; each one's head gradient
+// dL/dz (the oracle's float32 per-sample coefficients) is added to running f64 sums that are stored whenever the interval
+// advances.  These prefix sums give, at every unit's rank, the sums over the samples the unit is active on: M0 = sum dz, M1 = sum dz*s, hence d/dW[c][j] = w1_j*M1 + b1_j*M0, d/db1_j = sum_c W[c][j]*M0,
 // d/dw1_j = sum_c W[c][j]*M1.  O(N*A + H*A) instead of O(N*H*A).  Then clip_grad_norm_ + Adam, and the tables are rebuilt.
 // The arithmetic is the reference's autograd graph summed in another order (f64 accumulation): results agree with the
 // order-exact kernel (thrl_scan_mixed.cuh, THRL_KERNEL=mixed) and the oracle to float32 rounding -- tests state the
@@ -53,11 +53,11 @@ struct PwcParams {
   float* mlp;
   unsigned char* ring;
   long long ring_bytes;
-  unsigned char* ws;  // per resident warp: interval tables, ranked units, gradient buckets, gradient, per-sample scratch
-  long long ws_warp_bytes, ws_bkt, ws_grad, ws_xs;
+  unsigned char* ws;  // per resident warp: interval tables, ranked units, prefix sums, gradient, per-sample scratch, event order
+  long long ws_warp_bytes, ws_bkt, ws_grad, ws_xs, ws_evs;
   long long ws_tab[THRL_MAX_AGENTS], ws_ord[THRL_MAX_AGENTS];
   int cta_bytes, warp_bytes;
-  int off_P, off_act, off_pre, off_zf, off_newa, off_row, off_old, off_hp;
+  int off_P, off_act, off_pre, off_zf, off_newa, off_row, off_old, off_hp, off_hist;
   int off_th[THRL_MAX_AGENTS];  // MLP agent: its thresholds (ranked) in the warp's shared memory
   int ncp[THRL_MAX_AGENTS];     // MLP agent: table row length in (S1, S0) pairs (head columns rounded up to 2)
   int lut_total, Hp, noisy;
@@ -88,11 +88,14 @@ __device__ __forceinline__ int pwc_bias(const ThrlAgentSpec& s, int c) {
 __device__ __forceinline__ double2 pwc_ld2(const double2* a) { return __ldcg(a); }
 __device__ __forceinline__ float pwc_eval(double2 t, float s) { return (float)__dadd_rn(__dmul_rn(t.x, (double)s), t.y); }
 
-// r = number of thresholds <= key, every lane the same (th need not be sorted for this)
-__device__ __forceinline__ int pwc_rank_warp(const unsigned* th, int H, unsigned key, int lane) {
-  int cnt = 0;
-  for (int j = lane; j < H; j += 32) cnt += th[j] <= key ? 1 : 0;
-  return (int)__reduce_add_sync(kFull, (unsigned)cnt);
+// r = number of thresholds <= key, every lane the same.  th: the ranked thresholds, padded with kPwcKeyNone to 32 * per
+// entries; thc[l] = th[l * per + per - 1], the last threshold of block l.  One ballot finds the blocks that lie entirely at or
+// below the key, a second one counts inside the next block.
+__device__ __forceinline__ int pwc_rank_warp(const unsigned* th, const unsigned* thc, int H, int per, unsigned key, int lane) {
+  const int full = __popc(__ballot_sync(kFull, thc[lane] <= key));
+  const unsigned m = __ballot_sync(kFull, lane < per && full < 32 && th[full * per + lane] <= key);
+  const int r = full * per + __popc(m);
+  return r < H ? r : H;
 }
 // the same for one lane's own key on the RANKED thresholds (upper bound by bisection)
 __device__ __forceinline__ int pwc_rank_lane(const unsigned* th, int H, unsigned key) {
@@ -148,14 +151,19 @@ __device__ inline void pwc_build(const float* blk, const ThrlAgentSpec& spec, un
     for (int u = 0; u < U; ++u) pos[u] += (t < myth[u] || (t == myth[u] && jp < lane + 32 * u)) ? 1 : 0;
   }
   __syncwarp();
+  const int per = (H + 31) >> 5;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int j = lane + 32 * u;
     if (j < H) {
       th[pos[u]] = myth[u];
       ord[pos[u]] = (uint16_t)(j | ((leave_bits >> u & 1u) << 15));
+    } else if (j < 32 * per) {
+      th[j] = kPwcKeyNone;
     }
   }
+  __syncwarp();
+  th[32 * per + lane] = th[lane * per + per - 1];  // thc
   __syncwarp();
   // interval table, lane = head column: S(r) = sum over the units active on interval r of W[c][j] * (w1_j, b1_j)
   const bool use = lane < NC;
@@ -200,54 +208,62 @@ __device__ __forceinline__ int pwc_sample(float z, int A, float u, int lane) {
   return m ? __ffs(m) - 1 : A - 1;
 }
 
-__device__ __forceinline__ void pwc_bucket_add(double2* b, double dl, double s) {
-  double2 v = pwc_ld2(b);
-  v.x = __dadd_rn(v.x, dl);
-  v.y = __dadd_rn(v.y, __dmul_rn(dl, s));
-  __stcg(b, v);
-}
+// ---------------------------------------------------------------------------------------------------------------- update
+// One update of one MLP agent on its N buffered transitions:
+//  1. per-transition coefficients (the oracle's float32 formulas) and interval ranks, lane = transition  -> xs[n]
+//  2. the EVENTS -- transition n at its state s_n (all heads), and for ActorCritic / CAC transition n at its next state s'_n
+//     (value head only) -- are put in interval order by a stable counting sort (hist in shared memory, evs in the workspace)
+//  3. one sweep over the ranked events, lane = head column: pi(.|s) from the interval's table row, dL/dz added to running f64
+//     sums (P0 = sum dz, P1 = sum dz * s); whenever the interval advances the sums are stored: pf[r] = sums over the intervals
+//     < r, r = 0..H, pf[H+1] = totals.  No read-modify-write, no zero fill; the next event's table row is loaded while the
+//     current one is processed, and events of one interval share the row.
+//  4. lane = rank q: unit ord[q] is active on the intervals r > q (enter) or r <= q (leave), so its sums over active
+//     transitions are totals - pf[q+1] or pf[q+1]; gradient of every parameter; clip_grad_norm_ + Adam.
 
-// buckets -> exclusive prefix sums over the intervals (row H+1: totals), the gradient of every parameter, clip + Adam
-__device__ inline void pwc_finish(float* blk, const ThrlAgentSpec& spec, const uint16_t* ord, double2* bkt, int ncp, float* g, int lane) {
-  const int H = spec.hidden, NC = pwc_ncol(spec);
-  const float *w1 = blk, *b1 = blk + H;
+// stable counting sort of the NE events by rank; afterwards evs[0..NE) lists the events in interval order
+__device__ inline void pwc_sort_events(const float4* xs, int N, int NE, int H, int* hist, uint32_t* evs, int lane) {
+  const int NB = H + 2;
+  for (int i = lane; i < NB; i += 32) hist[i] = 0;
   __syncwarp();
-  if (lane < NC) {
-    double P0 = 0.0, P1 = 0.0;
-    for (int r = 0; r <= H; ++r) {
-      double2* cell = bkt + (size_t)r * ncp + lane;
-      const double2 v = pwc_ld2(cell);
-      __stcg(cell, make_double2(P0, P1));
-      P0 = __dadd_rn(P0, v.x);
-      P1 = __dadd_rn(P1, v.y);
+  auto rank_of = [&](int e) {
+    const int rb = __float_as_int(xs[e < N ? e : e - N].x);
+    return e < N ? (rb & 0xffff) : ((rb >> 16) & 0xffff);
+  };
+  for (int e0 = 0; e0 < NE; e0 += 32) {
+    const int e = e0 + lane;
+    const unsigned kk = e < NE ? (unsigned)rank_of(e) : 0x10000u + (unsigned)lane;
+    const unsigned peers = __match_any_sync(kFull, kk);
+    if (e < NE && (peers & lanemask_lt()) == 0) hist[kk + 1] += __popc(peers);
+    __syncwarp();
+  }
+  {  // inclusive scan: afterwards hist[k] = number of events of rank < k = first position of rank k
+    const int per = (NB + 31) / 32;
+    const int beg = lane * per, end = beg + per < NB ? beg + per : NB;
+    int sum = 0;
+    for (int k = beg; k < end; ++k) sum += hist[k];
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int t = __shfl_up_sync(kFull, incl, off);
+      if (lane >= off) incl += t;
     }
-    __stcg(bkt + (size_t)(H + 1) * ncp + lane, make_double2(P0, P1));
-    g[pwc_bias(spec, lane)] = (float)P0;
+    int run = incl - sum;
+    for (int k = beg; k < end; ++k) { run += hist[k]; hist[k] = run; }
   }
   __syncwarp();
-  // lane = rank q: unit ord[q] is active on the intervals r > q (enter) or r <= q (leave); sums over the intervals <= q are row q+1
-  for (int q0 = 0; q0 < H; q0 += 32) {
-    const int q = q0 + lane;
-    if (q < H) {
-      const unsigned o = ord[q];
-      const int j = (int)(o & 0x7fffu);
-      const bool leave = (o & 0x8000u) != 0;
-      const double w = (double)w1[j], b = (double)b1[j];
-      double gw = 0.0, gb = 0.0;
-      for (int c = 0; c < NC; ++c) {
-        const double2 pre = pwc_ld2(bkt + (size_t)(q + 1) * ncp + c), tt = pwc_ld2(bkt + (size_t)(H + 1) * ncp + c);
-        const double M0 = leave ? pre.x : __dsub_rn(tt.x, pre.x), M1 = leave ? pre.y : __dsub_rn(tt.y, pre.y);
-        const int wi = pwc_wrow(spec, c) + j;
-        g[wi] = (float)__dadd_rn(__dmul_rn(w, M1), __dmul_rn(b, M0));
-        const double cw = (double)blk[wi];
-        gb = __dadd_rn(gb, __dmul_rn(cw, M0));
-        gw = __dadd_rn(gw, __dmul_rn(cw, M1));
-      }
-      g[j] = (float)gw;
-      g[H + j] = (float)gb;
+  for (int e0 = 0; e0 < NE; e0 += 32) {
+    const int e = e0 + lane;
+    const unsigned kk = e < NE ? (unsigned)rank_of(e) : 0x10000u + (unsigned)lane;
+    const unsigned peers = __match_any_sync(kFull, kk);
+    int base = 0;
+    if (e < NE) {
+      base = hist[kk];
+      evs[base + __popc(peers & lanemask_lt())] = (uint32_t)e;
     }
+    __syncwarp();
+    if (e < NE && (peers & lanemask_lt()) == 0) hist[kk] = base + __popc(peers);
+    __syncwarp();
   }
-  pwl_clip_adam(blk, spec, g, lane);
 }
 
 __device__ inline void pwc_nan_update(float* blk, const ThrlAgentSpec& spec, float* g, int lane) {
@@ -256,14 +272,15 @@ __device__ inline void pwc_nan_update(float* blk, const ThrlAgentSpec& spec, flo
   pwl_clip_adam(blk, spec, g, lane);
 }
 
-// Reinforce.train_net (agents.py:170-194) / ActorCritic.train_net (:280-305) on the N buffered transitions.  The per-sample
-// coefficients are the oracle's (mlp_train / ac_train, float32, same operation order; v(s) from the interval table).
-__device__ inline void pwc_train_discrete(float* blk, const ThrlAgentSpec& spec, int cap, int head, int N, const unsigned* th,
-                                          const uint16_t* ord, const double2* tab, double2* bkt, int ncp, float* g, float4* xs, int lane) {
-  const int H = spec.hidden, A = spec.actions, P = mlp_P(spec), EW = mlp_entry_words(spec);
-  const bool ac = spec.kind == THRL_AGENT_ACTORCRITIC;
+// Reinforce.train_net (agents.py:170-194), ActorCritic.train_net (:280-305), CAC.train_net (:391-417)
+__device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap, int head, int N, const unsigned* th, const uint16_t* ord,
+                                 const double2* tab, double2* pf, int ncp, float* g, float4* xs, uint32_t* evs, int* hist, int lane) {
+  const int H = spec.hidden, A = spec.actions, P = mlp_P(spec), EW = mlp_entry_words(spec), NC = pwc_ncol(spec);
+  const int kind = spec.kind;
+  const bool ac = kind == THRL_AGENT_ACTORCRITIC, cac = kind == THRL_AGENT_CAC;
   float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
   const float gam = (float)spec.gamma;
+  const float *w1 = blk, *b1 = blk + H;
   auto entry = [&](int nn) {
     int sl = head + nn;
     if (sl >= cap) sl -= cap;
@@ -271,9 +288,9 @@ __device__ inline void pwc_train_discrete(float* blk, const ThrlAgentSpec& spec,
   };
   __syncwarp();
   for (int i = lane * 32; i < 3 * P; i += 32 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
-  for (int i = lane; i < (H + 2) * ncp; i += 32) __stcg(bkt + i, make_double2(0.0, 0.0));
+  // ---- 1. coefficients and ranks
   bool bad = false;
-  if (!ac) {
+  if (kind == THRL_AGENT_REINFORCE) {
     // discounted returns, newest to oldest (:177-180): the float32 recurrence itself, 32 transitions per round
     float carry = 0.0f;
     bool first = true;
@@ -308,7 +325,7 @@ __device__ inline void pwc_train_discrete(float* blk, const ThrlAgentSpec& spec,
       bad |= !isfinite(ca);
       xs[nn] = make_float4(__int_as_float(pwc_rank_lane(th, H, pwc_ukey(en[0]))), ca, 0.0f, 0.0f);
     }
-  } else {
+  } else if (ac) {
     double Rp = 0.0, Dp = 0.0;
     for (int nn = lane; nn < N; nn += 32) {  // d_i = gamma * v(s'_i) - v(s_i) (:289)
       const float* en = entry(nn);
@@ -330,73 +347,25 @@ __device__ inline void pwc_train_discrete(float* blk, const ThrlAgentSpec& spec,
       bad |= !isfinite(q.y) || !isfinite(q.z);
       xs[nn] = q;
     }
-  }
-  if (__any_sync(kFull, bad)) { pwc_nan_update(blk, spec, g, lane); return; }
-  __syncwarp();
-  // lane = head column: pi(.|s_n) from the table row of the sample's interval, dL/dz into the interval's bucket
-  const bool col = lane < A, vcol = ac && lane == A;
-  for (int nn = 0; nn < N; ++nn) {
-    const float4 q = xs[nn];
-    const float* en = entry(nn);
-    const float s = en[0];
-    const int a = __float_as_int(en[1]);
-    const int rb = __float_as_int(q.x), r = rb & 0xffff;
-    const float z = (col || vcol) ? pwc_eval(pwc_ld2(tab + (size_t)r * ncp + lane), s) : 0.0f;
-    const float mx = warp_max(col ? z : NegInf<float>::v());
-    const float ex = col ? det_expf(__fsub_rn(z, mx)) : 0.0f;
-    const float sum = warp_sum(ex);
-    if (col) {
-      const float pk = __fdiv_rn(ex, sum);
-      const float dl = __fmul_rn(__fsub_rn(pk, lane == a ? 1.0f : 0.0f), q.y);
-      pwc_bucket_add(bkt + (size_t)r * ncp + lane, (double)dl, (double)s);
-    } else if (vcol) {
-      pwc_bucket_add(bkt + (size_t)r * ncp + A, (double)q.z, (double)s);
-      const int r2 = (rb >> 16) & 0xffff;
-      pwc_bucket_add(bkt + (size_t)r2 * ncp + A, (double)__fmul_rn(-gam, q.z), (double)en[3]);
-    }
-  }
-  pwc_finish(blk, spec, ord, bkt, ncp, g, lane);
-}
-
-// CAC.train_net (agents.py:391-417): closed form of the [N,N] loss via five moments (oracle cac_train); lane = sample for the
-// scalar chain, then the three head gradients of each sample are added to its buckets in buffer order.
-__device__ inline void pwc_train_cac(float* blk, const ThrlAgentSpec& spec, int cap, int head, int N, const unsigned* th,
-                                     const uint16_t* ord, const double2* tab, double2* bkt, int ncp, float* g, int lane) {
-  const int H = spec.hidden, P = mlp_P(spec), EW = mlp_entry_words(spec);
-  const float* buf = blk + 3 * (size_t)P + THRL_MLP_HEADER_WORDS;
-  const float gam = (float)spec.gamma;
-  auto entry = [&](int nn) {
-    int sl = head + nn;
-    if (sl >= cap) sl -= cap;
-    return buf + (size_t)sl * EW;
-  };
-  __syncwarp();
-  for (int i = lane * 32; i < 3 * P; i += 32 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + i));
-  for (int i = lane; i < (H + 2) * ncp; i += 32) __stcg(bkt + i, make_double2(0.0, 0.0));
-  double Sr = 0.0, Sl = 0.0, Sl2 = 0.0, Srl = 0.0, Srl2 = 0.0;
-  for (int nn = lane; nn < N; nn += 32) {
-    const float* en = entry(nn);
-    const float a_ = __fadd_rn(5e-5f, __fmul_rn(__fsub_rn(1.0f, 1e-4f), en[1]));
-    const float ratio = __fdiv_rn(a_, __fsub_rn(1.0f, a_));
-    const double l = (double)(float)det_log((double)ratio), r = (double)en[2];
-    Sr = __dadd_rn(Sr, r);
-    Sl = __dadd_rn(Sl, l);
-    Sl2 = __dadd_rn(Sl2, __dmul_rn(l, l));
-    Srl = __dadd_rn(Srl, __dmul_rn(r, l));
-    Srl2 = __dadd_rn(Srl2, __dmul_rn(__dmul_rn(r, l), l));
-  }
-  Sr = warp_sum(Sr); Sl = warp_sum(Sl); Sl2 = warp_sum(Sl2); Srl = warp_sum(Srl); Srl2 = warp_sum(Srl2);
-  const double dN = (double)N, invN2 = __ddiv_rn(1.0, __dmul_rn(dN, dN));
-  __syncwarp();
-  for (int n0 = 0; n0 < N; n0 += 32) {
-    const int nn = n0 + lane;
-    float s = 0.0f, s2 = 0.0f, dzmu = 0.0f, dzsd = 0.0f, cv = 0.0f, cvp = 0.0f;
-    int r = 0, r2 = 0;
-    if (nn < N) {
+  } else {  // CAC: closed form of the [N,N] loss via five moments (oracle cac_train); the whole scalar chain per lane
+    double Sr = 0.0, Sl = 0.0, Sl2 = 0.0, Srl = 0.0, Srl2 = 0.0;
+    for (int nn = lane; nn < N; nn += 32) {
       const float* en = entry(nn);
-      s = en[0]; s2 = en[3];
-      r = pwc_rank_lane(th, H, pwc_ukey(s));
-      r2 = pwc_rank_lane(th, H, pwc_ukey(s2));
+      const float a_ = __fadd_rn(5e-5f, __fmul_rn(__fsub_rn(1.0f, 1e-4f), en[1]));
+      const float ratio = __fdiv_rn(a_, __fsub_rn(1.0f, a_));
+      const double l = (double)(float)det_log((double)ratio), r = (double)en[2];
+      Sr = __dadd_rn(Sr, r);
+      Sl = __dadd_rn(Sl, l);
+      Sl2 = __dadd_rn(Sl2, __dmul_rn(l, l));
+      Srl = __dadd_rn(Srl, __dmul_rn(r, l));
+      Srl2 = __dadd_rn(Srl2, __dmul_rn(__dmul_rn(r, l), l));
+    }
+    Sr = warp_sum(Sr); Sl = warp_sum(Sl); Sl2 = warp_sum(Sl2); Srl = warp_sum(Srl); Srl2 = warp_sum(Srl2);
+    const double dN = (double)N, invN2 = __ddiv_rn(1.0, __dmul_rn(dN, dN));
+    for (int nn = lane; nn < N; nn += 32) {
+      const float* en = entry(nn);
+      const float s = en[0], s2 = en[3];
+      const int r = pwc_rank_lane(th, H, pwc_ukey(s)), r2 = pwc_rank_lane(th, H, pwc_ukey(s2));
       const double2* row = tab + (size_t)r * ncp;
       const float zmu = pwc_eval(pwc_ld2(row), s), zsd = pwc_eval(pwc_ld2(row + 1), s), v = pwc_eval(pwc_ld2(row + 2), s);
       const float vp = pwc_eval(pwc_ld2(tab + (size_t)r2 * ncp + 2), s2);
@@ -409,24 +378,122 @@ __device__ inline void pwc_train_cac(float* blk, const ThrlAgentSpec& spec, int 
                                   __dmul_rn(dd, __dadd_rn(__dsub_rn(Sl2, __dmul_rn(__dmul_rn(2.0, dmu), Sl)), __dmul_rn(__dmul_rn(dN, dmu), dmu))));
       const float gmu = (float)__dmul_rn(-__ddiv_rn(A1, __dmul_rn(dsd, dsd)), invN2);
       const float gsd = (float)__dmul_rn(-__dsub_rn(__ddiv_rn(A2, __dmul_rn(__dmul_rn(dsd, dsd), dsd)), __ddiv_rn(A0, dsd)), invN2);
-      cv = (float)__dmul_rn(__dmul_rn(-2.0, A0), invN2);
-      cvp = __fmul_rn(-gam, cv);
-      dzmu = __fmul_rn(gmu, __fmul_rn(4.0f, __fsub_rn(1.0f, __fmul_rn(t, t))));
-      dzsd = __fmul_rn(gsd, det_sigmoidf(zsd));
-    }
-    const int cnt = N - n0 < 32 ? N - n0 : 32;
-    for (int l = 0; l < cnt; ++l) {  // buffer order; lanes 0..2 own the columns mu, std, v
-      const int rl = __shfl_sync(kFull, r, l), r2l = __shfl_sync(kFull, r2, l);
-      const float sl_ = __shfl_sync(kFull, s, l), s2l = __shfl_sync(kFull, s2, l);
-      const float a0 = __shfl_sync(kFull, dzmu, l), a1 = __shfl_sync(kFull, dzsd, l), a2 = __shfl_sync(kFull, cv, l), a3 = __shfl_sync(kFull, cvp, l);
-      if (lane < 3) {
-        const float dz = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
-        pwc_bucket_add(bkt + (size_t)rl * ncp + lane, (double)dz, (double)sl_);
-        if (lane == 2) pwc_bucket_add(bkt + (size_t)r2l * ncp + 2, (double)a3, (double)s2l);
-      }
+      const float cv = (float)__dmul_rn(__dmul_rn(-2.0, A0), invN2);
+      const float dzmu = __fmul_rn(gmu, __fmul_rn(4.0f, __fsub_rn(1.0f, __fmul_rn(t, t))));
+      const float dzsd = __fmul_rn(gsd, det_sigmoidf(zsd));
+      xs[nn] = make_float4(__int_as_float(r | (r2 << 16)), dzmu, dzsd, cv);  // dL/dv' = -gamma * cv
     }
   }
-  pwc_finish(blk, spec, ord, bkt, ncp, g, lane);
+  if (__any_sync(kFull, bad)) { pwc_nan_update(blk, spec, g, lane); return; }
+  __syncwarp();
+  // ---- 2. events in interval order
+  const int NE = kind == THRL_AGENT_REINFORCE ? N : 2 * N;
+  pwc_sort_events(xs, N, NE, H, hist, evs, lane);
+  __syncwarp();
+  // ---- 3. the sweep
+  {
+    const bool col = !cac && lane < A, use = lane < NC;
+    const int vc = NC - 1;  // value-head column of ActorCritic / CAC
+    double P0 = 0.0, P1 = 0.0;
+    int rcur = 0;  // rows < rcur of pf are written
+    for (int i0 = 0; i0 < NE; i0 += 32) {
+      // lane l fetches event i0 + l: rank, state, coefficients
+      int my_r = 0, my_a = -1;
+      float my_s = 0.0f, my_c0 = 0.0f, my_c1 = 0.0f, my_c2 = 0.0f;
+      bool my_next = false;  // event at the transition's next state: value head only
+      if (i0 + lane < NE) {
+        const int e = (int)evs[i0 + lane];
+        my_next = e >= N;
+        const int nn = my_next ? e - N : e;
+        const float4 q = xs[nn];
+        const float* en = entry(nn);
+        const int rb = __float_as_int(q.x);
+        if (!my_next) {
+          my_r = rb & 0xffff; my_s = en[0]; my_a = __float_as_int(en[1]);
+          my_c0 = q.y; my_c1 = q.z; my_c2 = q.w;
+        } else {
+          my_r = (rb >> 16) & 0xffff; my_s = en[3];
+          my_c0 = __fmul_rn(-gam, cac ? q.w : q.z);
+        }
+      }
+      const int cnt = NE - i0 < 32 ? NE - i0 : 32;
+      int r_ld = -1;  // interval whose table row t_cur holds
+      double2 t_cur = make_double2(0.0, 0.0);
+      {
+        const int r0 = __shfl_sync(kFull, my_r, 0);
+        const bool nx0 = __shfl_sync(kFull, (int)my_next, 0) != 0;
+        if (!cac && !nx0) { r_ld = r0; if (use) t_cur = pwc_ld2(tab + (size_t)r0 * ncp + lane); }
+      }
+      for (int l = 0; l < cnt; ++l) {
+        const int r = __shfl_sync(kFull, my_r, l);
+        const bool nxt = __shfl_sync(kFull, (int)my_next, l) != 0;
+        const float s = __shfl_sync(kFull, my_s, l), c0 = __shfl_sync(kFull, my_c0, l), c1 = __shfl_sync(kFull, my_c1, l);
+        const float c2 = __shfl_sync(kFull, my_c2, l);
+        const int a = __shfl_sync(kFull, my_a, l);
+        // the row of the event after this one is requested before this one's arithmetic
+        double2 t_nx = t_cur;
+        int r_nx = r_ld;
+        if (!cac && l + 1 < cnt) {
+          const int rn = __shfl_sync(kFull, my_r, l + 1);
+          const bool nn2 = __shfl_sync(kFull, (int)my_next, l + 1) != 0;
+          if (!nn2 && rn != r_ld) { r_nx = rn; if (use) t_nx = pwc_ld2(tab + (size_t)rn * ncp + lane); }
+        }
+        while (rcur <= r) {  // the sums over the intervals < rcur are complete
+          if (use) __stcg(pf + (size_t)rcur * ncp + lane, make_double2(P0, P1));
+          ++rcur;
+        }
+        double dz = 0.0;
+        if (nxt) {
+          if (lane == vc) dz = (double)c0;
+        } else if (cac) {
+          dz = (double)(lane == 0 ? c0 : (lane == 1 ? c1 : c2));
+        } else {
+          const float z = use ? pwc_eval(t_cur, s) : 0.0f;
+          const float mx = warp_max(col ? z : NegInf<float>::v());
+          const float ex = col ? det_expf(__fsub_rn(z, mx)) : 0.0f;
+          const float sum = warp_sum(ex);
+          if (col) {
+            dz = (double)__fmul_rn(__fsub_rn(__fdiv_rn(ex, sum), lane == a ? 1.0f : 0.0f), c0);
+          } else if (ac && lane == A) {
+            dz = (double)c1;
+          }
+        }
+        P0 = __dadd_rn(P0, dz);
+        P1 = __dadd_rn(P1, __dmul_rn(dz, (double)s));
+        t_cur = t_nx;
+        r_ld = r_nx;
+      }
+    }
+    while (rcur <= H + 1) {
+      if (use) __stcg(pf + (size_t)rcur * ncp + lane, make_double2(P0, P1));
+      ++rcur;
+    }
+    if (use) g[pwc_bias(spec, lane)] = (float)P0;
+  }
+  __syncwarp();
+  // ---- 4. lane = rank q
+  for (int q0 = 0; q0 < H; q0 += 32) {
+    const int q = q0 + lane;
+    if (q < H) {
+      const unsigned o = ord[q];
+      const int j = (int)(o & 0x7fffu);
+      const bool leave = (o & 0x8000u) != 0;
+      const double w = (double)w1[j], b = (double)b1[j];
+      double gw = 0.0, gb = 0.0;
+      for (int c = 0; c < NC; ++c) {
+        const double2 pre = pwc_ld2(pf + (size_t)(q + 1) * ncp + c), tt = pwc_ld2(pf + (size_t)(H + 1) * ncp + c);
+        const double M0 = leave ? pre.x : __dsub_rn(tt.x, pre.x), M1 = leave ? pre.y : __dsub_rn(tt.y, pre.y);
+        const int wi = pwc_wrow(spec, c) + j;
+        g[wi] = (float)__dadd_rn(__dmul_rn(w, M1), __dmul_rn(b, M0));
+        const double cw = (double)blk[wi];
+        gb = __dadd_rn(gb, __dmul_rn(cw, M0));
+        gw = __dadd_rn(gw, __dmul_rn(cw, M1));
+      }
+      g[j] = (float)gw;
+      g[H + j] = (float)gb;
+    }
+  }
+  pwl_clip_adam(blk, spec, g, lane);
 }
 
 template <typename QT>
@@ -470,6 +537,8 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ P
   double2* bkt = reinterpret_cast<double2*>(wsw + p.ws_bkt);
   float* gws = reinterpret_cast<float*>(wsw + p.ws_grad);
   float4* xs = reinterpret_cast<float4*>(wsw + p.ws_xs);
+  uint32_t* evs = reinterpret_cast<uint32_t*>(wsw + p.ws_evs);
+  int* hist = reinterpret_cast<int*>(slot + p.off_hist);  // [Hmax + 2] event counts per interval (updates only)
 
   int my_cap = 0, my_minmem = 0x7fffffff, my_lut = 0, my_kind = 0, my_len = 0;
   int my_mcap = 0, my_EW = 3;  // MLP agent: buffer capacity in the slab, words per entry
@@ -621,23 +690,42 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ P
           const float sf = (float)price;
           const unsigned key = pwc_ukey(sf);
           while (samp) {
-            const int i = __ffs(samp) - 1;
-            samp &= samp - 1;
-            const ThrlAgentSpec& s = G.agent[i];
-            const int rk = pwc_rank_warp(reinterpret_cast<const unsigned*>(slot + p.off_th[i]), s.hidden, key, lane);
-            const double2* row = reinterpret_cast<const double2*>(wsw + p.ws_tab[i]) + (size_t)rk * p.ncp[i];
-            const float dev = zf[t * n + i];
-            int ks;
-            if (s.kind == THRL_AGENT_CAC) {
-              const float z = lane < 2 ? pwc_eval(pwc_ld2(row + lane), sf) : 0.0f;
-              const float zmu = __shfl_sync(kFull, z, 0), zsd = __shfl_sync(kFull, z, 1);
-              const float mu = __fmul_rn(4.0f, det_tanhf(zmu)), sd = det_softplusf(zsd);
-              ks = __float_as_int(det_sigmoidf(__fadd_rn(mu, __fmul_rn(sd, dev))));
-            } else {
-              const float z = lane < s.actions ? pwc_eval(pwc_ld2(row + lane), sf) : 0.0f;
-              ks = pwc_sample(z, s.actions, dev, lane);
+            // two agents per round: both ranks and both table-row loads are issued before either policy is evaluated
+            int ids[2];
+            double2 rows[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              ids[u] = -1;
+              rows[u] = make_double2(0.0, 0.0);
+              if (samp) {
+                const int i = __ffs(samp) - 1;
+                samp &= samp - 1;
+                ids[u] = i;
+                const ThrlAgentSpec& s = G.agent[i];
+                const int per = (s.hidden + 31) >> 5;
+                const unsigned* thi = reinterpret_cast<const unsigned*>(slot + p.off_th[i]);
+                const int rk = pwc_rank_warp(thi, thi + 32 * per, s.hidden, per, key, lane);
+                const int nc = s.kind == THRL_AGENT_CAC ? 2 : s.actions;
+                if (lane < nc) rows[u] = pwc_ld2(reinterpret_cast<const double2*>(wsw + p.ws_tab[i]) + (size_t)rk * p.ncp[i] + lane);
+              }
             }
-            if (lane == i) k = ks;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int i = ids[u];
+              if (i < 0) continue;
+              const ThrlAgentSpec& s = G.agent[i];
+              const float dev = zf[t * n + i];
+              const float z = pwc_eval(rows[u], sf);
+              int ks;
+              if (s.kind == THRL_AGENT_CAC) {
+                const float zmu = __shfl_sync(kFull, z, 0), zsd = __shfl_sync(kFull, z, 1);
+                const float mu = __fmul_rn(4.0f, det_tanhf(zmu)), sd = det_softplusf(zsd);
+                ks = __float_as_int(det_sigmoidf(__fadd_rn(mu, __fmul_rn(sd, dev))));
+              } else {
+                ks = pwc_sample(z, s.actions, dev, lane);
+              }
+              if (lane == i) k = ks;
+            }
           }
         }
         double aq = 0.0, xt = 0.0;
@@ -704,8 +792,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ P
           uint16_t* ord = reinterpret_cast<uint16_t*>(wsw + p.ws_ord[i]);
           double2* itab = reinterpret_cast<double2*>(wsw + p.ws_tab[i]);
           __syncwarp();  // the episode's buffer stores are visible to every lane
-          if (s.kind == THRL_AGENT_CAC) pwc_train_cac(blk, s, cap, hd, len, th, ord, itab, bkt, p.ncp[i], gws, lane);
-          else pwc_train_discrete(blk, s, cap, hd, len, th, ord, itab, bkt, p.ncp[i], gws, xs, lane);
+          pwc_train(blk, s, cap, hd, len, th, ord, itab, bkt, p.ncp[i], gws, xs, evs, hist, lane);
           if (lane == i) { m_len = 0; m_wr = 0; }  // :194 memory.empty()
           pwc_build(blk, s, th, ord, itab, p.ncp[i], lane);
           continue;

@@ -910,11 +910,12 @@ bool plan_pwc(thrl::PwcParams* p, bool noisy, size_t elem, int smem_optin, int* 
   if (nm == 0) return false;
   p->lut_total = lut;
   p->cta_bytes = align_up(2 * lut * 8, 16);
-  p->off_hist = o; o += align_up((Hmax + 2) * 4, 16);
+  p->off_hist = o; o += align_up((Hmax + 3) * 4, 16);
   p->warp_bytes = o;
   p->ws_bkt = w;  w += align_up((Hmax + 2) * ncpmax * 16, 256);
   p->ws_grad = w; w += align_up(Pmax * 4, 256);
   p->ws_xs = w;   w += align_up((capmax > 0 ? capmax : 1) * 16, 256);
+  p->ws_xe = w;   w += align_up((capmax > 0 ? capmax : 1) * 4, 256);
   p->ws_evs = w;  w += (long long)(capmax > 0 ? capmax : 1) * 8;
   p->ws_warp_bytes = (w + 255) / 256 * 256;
   const int fit = (smem_optin - p->cta_bytes) / p->warp_bytes;
@@ -944,7 +945,10 @@ int launch_pwc(thrl::PwcParams& p, int warps, const DeviceInfo& dev, cudaStream_
   void* ws = nullptr;
   CUDA_TRY(cudaMallocFromPoolAsync(&ws, (size_t)grid * warps * (size_t)p.ws_warp_bytes, pool, stream));
   p.ws = (unsigned char*)ws;
-  auto kern = thrl::mlp_scan_pwc<QT>;
+  const ThrlGame& G = p.game;
+  const bool two = G.n_agents == 2 && (G.agent[0].kind == THRL_AGENT_REINFORCE || G.agent[0].kind == THRL_AGENT_ACTORCRITIC) &&
+                   (G.agent[1].kind == THRL_AGENT_REINFORCE || G.agent[1].kind == THRL_AGENT_ACTORCRITIC);
+  auto kern = two ? thrl::mlp_scan_pwc<QT, true> : thrl::mlp_scan_pwc<QT, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e == cudaSuccess) {
     g_last_kernel = "pwc";

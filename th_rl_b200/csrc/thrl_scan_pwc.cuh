@@ -54,7 +54,7 @@ struct PwcParams {
   unsigned char* ring;
   long long ring_bytes;
   unsigned char* ws;  // per resident warp: interval tables, ranked units, prefix sums, gradient, per-sample scratch, event order
-  long long ws_warp_bytes, ws_bkt, ws_grad, ws_xs, ws_evs;
+  long long ws_warp_bytes, ws_bkt, ws_grad, ws_xs, ws_xe, ws_evs;
   long long ws_tab[THRL_MAX_AGENTS], ws_ord[THRL_MAX_AGENTS];
   int cta_bytes, warp_bytes;
   int off_P, off_act, off_pre, off_zf, off_newa, off_row, off_old, off_hp, off_hist;
@@ -87,6 +87,21 @@ __device__ __forceinline__ int pwc_bias(const ThrlAgentSpec& s, int c) {
 
 __device__ __forceinline__ double2 pwc_ld2(const double2* a) { return __ldcg(a); }
 __device__ __forceinline__ float pwc_eval(double2 t, float s) { return (float)__dadd_rn(__dmul_rn(t.x, (double)s), t.y); }
+
+// x / T, correctly rounded, for a constant T with y = RN(1 / T): two residual corrections by FMA (Markstein: the second one
+// starts from a faithful quotient and is then the correctly rounded quotient).  The reference divides every reward by
+// max_steps before adding it to the log (trainer.py:63); div.rn.f64 costs ~35 instructions, this 7.  Outside the range where
+// the products are free of overflow / underflow the plain division is used.  (/tmp-style check: 8e8 random operands, T = 1..400,
+// no mismatch against the hardware division.)
+__device__ __forceinline__ double pwc_div(double x, double T, double y) {
+  const double ax = fabs(x);
+  if (!(ax < 1e280) || (ax < 1e-280 && x != 0.0)) return __ddiv_rn(x, T);
+  double q = __dmul_rn(x, y);
+  double r = __fma_rn(-q, T, x);
+  q = __fma_rn(r, y, q);
+  r = __fma_rn(-q, T, x);
+  return __fma_rn(r, y, q);
+}
 
 // r = number of thresholds <= key, every lane the same.  th: the ranked thresholds, padded with kPwcKeyNone to 32 * per
 // entries; thc[l] = th[l * per + per - 1], the last threshold of block l.  One ballot finds the blocks that lie entirely at or
@@ -221,8 +236,9 @@ __device__ __forceinline__ int pwc_sample(float z, int A, float u, int lane) {
 //     transitions are totals - pf[q+1] or pf[q+1]; gradient of every parameter; clip_grad_norm_ + Adam.
 
 // stable counting sort of the NE events by rank; afterwards evs[0..NE) lists the events in interval order
-__device__ inline void pwc_sort_events(const float4* xs, int N, int NE, int H, int* hist, uint32_t* evs, int lane) {
-  const int NB = H + 2;
+// (rank H + 1 marks an event that was merged into another one: those end up behind the returned count)
+__device__ inline int pwc_sort_events(const float4* xs, int N, int NE, int H, int* hist, uint32_t* evs, int lane) {
+  const int NB = H + 3;
   for (int i = lane; i < NB; i += 32) hist[i] = 0;
   __syncwarp();
   auto rank_of = [&](int e) {
@@ -264,6 +280,7 @@ __device__ inline void pwc_sort_events(const float4* xs, int N, int NE, int H, i
     if (e < NE && (peers & lanemask_lt()) == 0) hist[kk] = base + __popc(peers);
     __syncwarp();
   }
+  return hist[H];  // end of rank H = number of events that take part in the sweep
 }
 
 __device__ inline void pwc_nan_update(float* blk, const ThrlAgentSpec& spec, float* g, int lane) {
@@ -274,7 +291,7 @@ __device__ inline void pwc_nan_update(float* blk, const ThrlAgentSpec& spec, flo
 
 // Reinforce.train_net (agents.py:170-194), ActorCritic.train_net (:280-305), CAC.train_net (:391-417)
 __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap, int head, int N, const unsigned* th, const uint16_t* ord,
-                                 const double2* tab, double2* pf, int ncp, float* g, float4* xs, uint32_t* evs, int* hist, int lane) {
+                                 const double2* tab, double2* pf, int ncp, float* g, float4* xs, float* xe, uint32_t* evs, int* hist, int lane) {
   const int H = spec.hidden, A = spec.actions, P = mlp_P(spec), EW = mlp_entry_words(spec), NC = pwc_ncol(spec);
   const int kind = spec.kind;
   const bool ac = kind == THRL_AGENT_ACTORCRITIC, cac = kind == THRL_AGENT_CAC;
@@ -386,9 +403,29 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
   }
   if (__any_sync(kFull, bad)) { pwc_nan_update(blk, spec, g, lane); return; }
   __syncwarp();
+  if (kind != THRL_AGENT_REINFORCE) {
+    // Consecutive transitions of an episode share a state: s'_n is s_(n+1), bit for bit.  The value-head event at s'_n is then
+    // carried by the event at s_(n+1) (xe = its dL/dv' = -gamma * dL/dv_n) and leaves the event list (rank H + 1).
+    for (int nn = lane; nn < N; nn += 32) {
+      const float* en = entry(nn);
+      float ex = 0.0f;
+      if (nn > 0 && __float_as_int(entry(nn - 1)[3]) == __float_as_int(en[0])) {
+        const float4 qp = xs[nn - 1];
+        ex = __fmul_rn(-gam, cac ? qp.w : qp.z);
+      }
+      xe[nn] = ex;
+    }
+    __syncwarp();
+    for (int nn = lane; nn + 1 < N; nn += 32) {
+      if (__float_as_int(entry(nn)[3]) == __float_as_int(entry(nn + 1)[0])) {
+        const int rb = __float_as_int(xs[nn].x);
+        xs[nn].x = __int_as_float((rb & 0xffff) | ((H + 1) << 16));
+      }
+    }
+    __syncwarp();
+  }
   // ---- 2. events in interval order
-  const int NE = kind == THRL_AGENT_REINFORCE ? N : 2 * N;
-  pwc_sort_events(xs, N, NE, H, hist, evs, lane);
+  const int NE = pwc_sort_events(xs, N, kind == THRL_AGENT_REINFORCE ? N : 2 * N, H, hist, evs, lane);
   __syncwarp();
   // ---- 3. the sweep
   {
@@ -399,7 +436,7 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
     for (int i0 = 0; i0 < NE; i0 += 32) {
       // lane l fetches event i0 + l: rank, state, coefficients
       int my_r = 0, my_a = -1;
-      float my_s = 0.0f, my_c0 = 0.0f, my_c1 = 0.0f, my_c2 = 0.0f;
+      float my_s = 0.0f, my_c0 = 0.0f, my_c1 = 0.0f, my_c2 = 0.0f, my_c3 = 0.0f;
       bool my_next = false;  // event at the transition's next state: value head only
       if (i0 + lane < NE) {
         const int e = (int)evs[i0 + lane];
@@ -411,6 +448,7 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
         if (!my_next) {
           my_r = rb & 0xffff; my_s = en[0]; my_a = __float_as_int(en[1]);
           my_c0 = q.y; my_c1 = q.z; my_c2 = q.w;
+          if (kind != THRL_AGENT_REINFORCE) my_c3 = xe[nn];
         } else {
           my_r = (rb >> 16) & 0xffff; my_s = en[3];
           my_c0 = __fmul_rn(-gam, cac ? q.w : q.z);
@@ -428,7 +466,7 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
         const int r = __shfl_sync(kFull, my_r, l);
         const bool nxt = __shfl_sync(kFull, (int)my_next, l) != 0;
         const float s = __shfl_sync(kFull, my_s, l), c0 = __shfl_sync(kFull, my_c0, l), c1 = __shfl_sync(kFull, my_c1, l);
-        const float c2 = __shfl_sync(kFull, my_c2, l);
+        const float c2 = __shfl_sync(kFull, my_c2, l), c3 = __shfl_sync(kFull, my_c3, l);
         const int a = __shfl_sync(kFull, my_a, l);
         // the row of the event after this one is requested before this one's arithmetic
         double2 t_nx = t_cur;
@@ -446,7 +484,7 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
         if (nxt) {
           if (lane == vc) dz = (double)c0;
         } else if (cac) {
-          dz = (double)(lane == 0 ? c0 : (lane == 1 ? c1 : c2));
+          dz = lane == 2 ? __dadd_rn((double)c2, (double)c3) : (double)(lane == 0 ? c0 : c1);
         } else {
           const float z = use ? pwc_eval(t_cur, s) : 0.0f;
           const float mx = warp_max(col ? z : NegInf<float>::v());
@@ -455,7 +493,7 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
           if (col) {
             dz = (double)__fmul_rn(__fsub_rn(__fdiv_rn(ex, sum), lane == a ? 1.0f : 0.0f), c0);
           } else if (ac && lane == A) {
-            dz = (double)c1;
+            dz = __dadd_rn((double)c1, (double)c3);
           }
         }
         P0 = __dadd_rn(P0, dz);
@@ -496,7 +534,10 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
   pwl_clip_adam(blk, spec, g, lane);
 }
 
-template <typename QT>
+// kTwo: the game is two discrete-action MLP agents (Reinforce / ActorCritic) and nothing else -- the BASELINE C5 shape with
+// demand noise.  Its episode loop keeps both agents' thresholds, tables and shapes in registers and evaluates the two policies
+// side by side; every other game takes the general loop.
+template <typename QT, bool kTwo>
 __global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ PwcParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ThrlGame& G = p.game;
@@ -537,8 +578,9 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ P
   double2* bkt = reinterpret_cast<double2*>(wsw + p.ws_bkt);
   float* gws = reinterpret_cast<float*>(wsw + p.ws_grad);
   float4* xs = reinterpret_cast<float4*>(wsw + p.ws_xs);
+  float* xe = reinterpret_cast<float*>(wsw + p.ws_xe);
   uint32_t* evs = reinterpret_cast<uint32_t*>(wsw + p.ws_evs);
-  int* hist = reinterpret_cast<int*>(slot + p.off_hist);  // [Hmax + 2] event counts per interval (updates only)
+  int* hist = reinterpret_cast<int*>(slot + p.off_hist);  // [Hmax + 3] event counts per interval (updates only)
 
   int my_cap = 0, my_minmem = 0x7fffffff, my_lut = 0, my_kind = 0, my_len = 0;
   int my_mcap = 0, my_EW = 3;  // MLP agent: buffer capacity in the slab, words per entry
@@ -558,6 +600,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ P
   const bool never_fires = my_minmem > my_cap;
   const int lead = lead_exact_floats(G);
   const bool tracing = p.trace_actions || p.trace_rewards || p.trace_prices;
+  const double dT = (double)T, rT = __ddiv_rn(1.0, dT);
 
   const long long total_warps = (long long)gridDim.x * warps_per_cta;
   for (long long r = (long long)blockIdx.x * warps_per_cta + warp; r < p.n_runs; r += total_warps) {
@@ -669,6 +712,73 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ P
 
       // ---- the episode (trainer.py:50-67)
       double rlog = 0.0, alog = 0.0;
+      if (kTwo) {
+        const int A0 = G.agent[0].actions, A1 = G.agent[1].actions, H0 = G.agent[0].hidden, H1 = G.agent[1].hidden;
+        const int per0 = (H0 + 31) >> 5, per1 = (H1 + 31) >> 5;
+        const unsigned* th0 = reinterpret_cast<const unsigned*>(slot + p.off_th[0]);
+        const unsigned* th1 = reinterpret_cast<const unsigned*>(slot + p.off_th[1]);
+        const double2* tb0 = reinterpret_cast<const double2*>(wsw + p.ws_tab[0]) + (lane < A0 ? lane : 0);
+        const double2* tb1 = reinterpret_cast<const double2*>(wsw + p.ws_tab[1]) + (lane < A1 ? lane : 0);
+        const int ncp0 = p.ncp[0], ncp1 = p.ncp[1];
+        const bool in0 = lane < A0, in1 = lane < A1;
+        const unsigned last0 = 1u << (A0 - 1), last1 = 1u << (A1 - 1);
+        const double* aq1p = lutAQ + A0;
+        const double* xtp = lutXT + (lane == 1 ? A0 : 0);
+        const bool append = is_agent && my_mcap > 0;
+        for (int t = 0; t < T; ++t) {
+          const int2 v = *reinterpret_cast<const int2*>(pre + 2 * t);  // forced action, or -2: sample
+          int k0 = v.x, k1 = v.y;
+          if ((v.x | v.y) < 0) {
+            const float2 dev = *reinterpret_cast<const float2*>(zf + 2 * t);
+            const float sf = (float)price;
+            const unsigned key = pwc_ukey(sf);
+            const int r0 = pwc_rank_warp(th0, th0 + 32 * per0, H0, per0, key, lane);
+            const int r1 = pwc_rank_warp(th1, th1 + 32 * per1, H1, per1, key, lane);
+            const double2 t0 = pwc_ld2(tb0 + (size_t)r0 * ncp0), t1 = pwc_ld2(tb1 + (size_t)r1 * ncp1);
+            const float z0 = pwc_eval(t0, sf), z1 = pwc_eval(t1, sf);
+            // both softmaxes side by side.  pi_k = e_k / sum and `cumsum(pi)[k] > u` (agents.py:160-163) are evaluated as
+            // cumsum(e)[k] > u * sum: one scan yields both the running sums and (last column) the total
+            const float m0 = warp_max(in0 ? z0 : NegInf<float>::v()), m1 = warp_max(in1 ? z1 : NegInf<float>::v());
+            float c0 = in0 ? det_expf(__fsub_rn(z0, m0)) : 0.0f, c1 = in1 ? det_expf(__fsub_rn(z1, m1)) : 0.0f;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+              const float u0 = __shfl_up_sync(kFull, c0, off), u1 = __shfl_up_sync(kFull, c1, off);
+              if (lane >= off) { c0 = __fadd_rn(c0, u0); c1 = __fadd_rn(c1, u1); }
+            }
+            const float tot0 = __shfl_sync(kFull, c0, 31), tot1 = __shfl_sync(kFull, c1, 31);
+            const unsigned b0 = __ballot_sync(kFull, in0 && c0 > __fmul_rn(dev.x, tot0)) | last0;
+            const unsigned b1 = __ballot_sync(kFull, in1 && c1 > __fmul_rn(dev.y, tot1)) | last1;
+            if (v.x < 0) k0 = __ffs(b0) - 1;
+            if (v.y < 0) k1 = __ffs(b1) - 1;
+          }
+          const int kmine = lane == 0 ? k0 : k1;
+          const double aq0 = lutAQ[k0], aq1 = aq1p[k1];  // environments.py:27 sum(A): 0 + A[0] + A[1]
+          const double Q = __dadd_rn(__dadd_rn(0.0, aq0), aq1);
+          const double na = p.noisy ? newa[t] : G.a;
+          const double pn = __dsub_rn(na, __dmul_rn(G.b, Q));
+          const double next_price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
+          const double rew = __dmul_rn(next_price, lane == 0 ? aq0 : aq1);
+          if (is_agent) {
+            rlog = __dadd_rn(rlog, pwc_div(rew, dT, rT));
+            alog = __dadd_rn(alog, xtp[kmine]);
+            if (append) {  // memory.append; replay(cast) makes state and reward float32 (buffers.py:28-38, agents.py:142)
+              float* en = m_buf + (size_t)m_wr * my_EW;
+              en[0] = (float)price;
+              en[1] = __int_as_float(kmine);
+              en[2] = (float)rew;
+              if (my_EW == 4) en[3] = (float)next_price;
+              m_wr = m_wr + 1 == my_mcap ? 0 : m_wr + 1;
+              m_len = m_len < my_mcap ? m_len + 1 : my_mcap;
+            }
+            if (tracing) {
+              if (p.trace_actions) p.trace_actions[(step0 + t) * n + lane] = kmine;
+              if (p.trace_rewards) p.trace_rewards[(step0 + t) * n + lane] = rew;
+            }
+          }
+          if (tracing && lane == 0 && p.trace_prices) p.trace_prices[step0 + t] = next_price;
+          price = next_price;
+        }
+      } else
       for (int t = 0; t < T; ++t) {
         int k = is_agent ? pre[t * n + lane] : 0;
         int arow = 0;
@@ -748,7 +858,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ P
         int nxt = pos + 1;
         if (nxt == Hp) nxt = 0;
         if (is_agent) {
-          rlog = __dadd_rn(rlog, __ddiv_rn(rew, (double)T));
+          rlog = __dadd_rn(rlog, pwc_div(rew, dT, rT));
           alog = __dadd_rn(alog, xt);
           if (my_kind == THRL_AGENT_QTABLE) {
             act[lane * Hp + pos] = (uint8_t)k;
@@ -792,7 +902,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ P
           uint16_t* ord = reinterpret_cast<uint16_t*>(wsw + p.ws_ord[i]);
           double2* itab = reinterpret_cast<double2*>(wsw + p.ws_tab[i]);
           __syncwarp();  // the episode's buffer stores are visible to every lane
-          pwc_train(blk, s, cap, hd, len, th, ord, itab, bkt, p.ncp[i], gws, xs, evs, hist, lane);
+          pwc_train(blk, s, cap, hd, len, th, ord, itab, bkt, p.ncp[i], gws, xs, xe, evs, hist, lane);
           if (lane == i) { m_len = 0; m_wr = 0; }  // :194 memory.empty()
           pwc_build(blk, s, th, ord, itab, p.ncp[i], lane);
           continue;

@@ -88,6 +88,26 @@ __device__ __forceinline__ int pwc_bias(const ThrlAgentSpec& s, int c) {
 __device__ __forceinline__ double2 pwc_ld2(const double2* a) { return __ldcg(a); }
 __device__ __forceinline__ float pwc_eval(double2 t, float s) { return (float)__dadd_rn(__dmul_rn(t.x, (double)s), t.y); }
 
+// exp(x) for the softmaxes of this kernel: Cody-Waite reduction and the Cephes polynomial evaluated with fused multiply-adds
+// (under 1 ulp; half the instructions of det_expf, whose unfused sequence exists to be bit-equal to the oracle's -- this kernel
+// is compared to float32 rounding, not bit for bit)
+__device__ __forceinline__ float pwc_expf(float x) {
+  if (x < -87.0f) return 0.0f;
+  const float kf = rintf(__fmul_rn(x, 1.44269504f));
+  float r = __fmaf_rn(kf, -0.693359375f, x);
+  r = __fmaf_rn(kf, 2.12194440e-4f, r);
+  float p = 1.9875691500e-4f;
+  p = __fmaf_rn(p, r, 1.3981999507e-3f);
+  p = __fmaf_rn(p, r, 8.3334519073e-3f);
+  p = __fmaf_rn(p, r, 4.1665795894e-2f);
+  p = __fmaf_rn(p, r, 1.6666665459e-1f);
+  p = __fmaf_rn(p, r, 5.0000001201e-1f);
+  p = __fmaf_rn(__fmul_rn(p, r), r, r);
+  p = __fadd_rn(p, 1.0f);
+  const int k = (int)kf;  // -126 <= k <= 128 here for every finite x >= -87 that does not overflow
+  return __fmul_rn(p, __int_as_float((min(max(k, -126), 128) + 127) << 23));
+}
+
 // x / T, correctly rounded, for a constant T with y = RN(1 / T): two residual corrections by FMA (Markstein: the second one
 // starts from a faithful quotient and is then the correctly rounded quotient).  The reference divides every reward by
 // max_steps before adding it to the log (trainer.py:63); div.rn.f64 costs ~35 instructions, this 7.  Outside the range where
@@ -211,7 +231,7 @@ __device__ inline void pwc_build(const float* blk, const ThrlAgentSpec& spec, un
 __device__ __forceinline__ int pwc_sample(float z, int A, float u, int lane) {
   const bool col = lane < A;
   const float mx = warp_max(col ? z : NegInf<float>::v());
-  const float ex = col ? det_expf(__fsub_rn(z, mx)) : 0.0f;
+  const float ex = col ? pwc_expf(__fsub_rn(z, mx)) : 0.0f;
   const float sum = warp_sum(ex);
   float c = col ? __fdiv_rn(ex, sum) : 0.0f;
 #pragma unroll
@@ -488,10 +508,10 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
         } else {
           const float z = use ? pwc_eval(t_cur, s) : 0.0f;
           const float mx = warp_max(col ? z : NegInf<float>::v());
-          const float ex = col ? det_expf(__fsub_rn(z, mx)) : 0.0f;
-          const float sum = warp_sum(ex);
+          const float ex = col ? pwc_expf(__fsub_rn(z, mx)) : 0.0f;
+          const float inv = __frcp_rn(warp_sum(ex));  // pi_k = e_k * (1 / sum): one reciprocal per event
           if (col) {
-            dz = (double)__fmul_rn(__fsub_rn(__fdiv_rn(ex, sum), lane == a ? 1.0f : 0.0f), c0);
+            dz = (double)__fmul_rn(__fsub_rn(__fmul_rn(ex, inv), lane == a ? 1.0f : 0.0f), c0);
           } else if (ac && lane == A) {
             dz = __dadd_rn((double)c1, (double)c3);
           }
@@ -739,7 +759,7 @@ __global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ P
             // both softmaxes side by side.  pi_k = e_k / sum and `cumsum(pi)[k] > u` (agents.py:160-163) are evaluated as
             // cumsum(e)[k] > u * sum: one scan yields both the running sums and (last column) the total
             const float m0 = warp_max(in0 ? z0 : NegInf<float>::v()), m1 = warp_max(in1 ? z1 : NegInf<float>::v());
-            float c0 = in0 ? det_expf(__fsub_rn(z0, m0)) : 0.0f, c1 = in1 ? det_expf(__fsub_rn(z1, m1)) : 0.0f;
+            float c0 = in0 ? pwc_expf(__fsub_rn(z0, m0)) : 0.0f, c1 = in1 ? pwc_expf(__fsub_rn(z1, m1)) : 0.0f;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
               const float u0 = __shfl_up_sync(kFull, c0, off), u1 = __shfl_up_sync(kFull, c1, off);

@@ -95,7 +95,7 @@ WORKLOADS = {
 }
 EXTRAS = ("c2", "c4", "c5", "c5n")
 # warp instructions per agent-step from the committed ncu captures (profiles/)
-NCU_INSTR = {"c2": 30.4, "c5": 111.0, "c5n": 543.0}
+NCU_INSTR = {"c2": 30.4, "c5": 110.5, "c5n": 354.9}
 
 
 def measured_peaks():
@@ -381,6 +381,37 @@ def measure(name, wl, R, E, steps, warmup, e2e_chunks, ctx):
     return res
 
 
+def measure_f64(wl, R, ctx, E=200, steps=2):
+    """Secondary figure: the same workload with float64 tables, the reference's own dtype (bit-exact against it under replay;
+    the headline stores float32 and updates in float64).  Half the runs: an f64 run needs twice the shared memory."""
+    torch, dist, engine, _lib = ctx["torch"], ctx["dist"], ctx["engine"], ctx["_lib"]
+    world, rank, dev = ctx["world"], ctx["rank"], ctx["dev"]
+    R = max(1, R // 2)
+    batch = engine.RunBatch(wl["config"], R, device=dev, dtype=torch.float64, seed=0, run_id0=rank * R).init_device()
+    batch.scan(E, stats=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        out = batch.scan(E, stats=True)
+        if world > 1:
+            dist.all_reduce(out.stats)
+    t1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    kern = _lib.last_kernel()
+    del batch, out
+    torch.cuda.empty_cache()
+    return {"value": R * world * wl["agents"] * E * MAX_STEPS * steps / (ms * 1e-3), "unit": "agent-steps/s", "runs_per_gpu": R,
+            "epochs_per_step": E, "steps": steps, "ms_per_step": ms / steps, "kernel_dispatched": kern,
+            "note": "float64 tables (the reference's dtype): bit-exact against the reference under replay"}
+
+
 def measure_e2e(wl, R, E, steps, n_chunks, ctx, barrier):
     """Same metric through the reference-facing boundary: thrl_qtable_scan_host on page-locked host buffers -- tables,
     counters, epsilon, price (and the MLP slab) go host -> device -> scan -> host, statistics come back, all inside the timed
@@ -455,6 +486,8 @@ def run_ours(args):
     line = base_line(args, args.workload, wl, world, _lib.game_layout)
     line.update(res)
     line["parity"] = "green: tests/ -m gpu compare this path with the oracle and the reference's recorded goldens (bit-exact)"
+    if args.workload == "c2" and not args.no_extras:
+        line["f64_tables"] = measure_f64(wl, args.runs_per_gpu, ctx)
     if not args.no_extras:
         line["workloads"] = {}
         for name in EXTRAS:

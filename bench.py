@@ -84,6 +84,13 @@ WORKLOADS = {
                     "%d runs/GPU x %d epochs per step (C5 shape)",
                kernel="thrl::mlp_scan_pwl (persistent, one launch per step; policy LUT per lattice state + sorted-breakpoint "
                       "gradient sweep, f64 accumulation; no dense contraction is left)"),
+    # the same sweep sized to the persistent grid: 3 full rounds of 12 resident runs x 148 SMs (thrl_last_wave_runs reports the
+    # round size so that a caller can do this).  4,096 runs are 2.3 rounds, i.e. three balanced rounds of 9-10 runs per SM.
+    "c4w": dict(agents=8, runs_per_gpu=5328, epochs=500, e2e_chunks=0, config=_qcfg(8, 1000, 101, 0.05, 0.15, 500), algo_bytes=824.0,
+                bound="hbm", hp=_c4_hp,
+                desc="the C4 sweep with the run count a whole multiple of the persistent grid's round (64 points x 83.25 seeds), "
+                     "8 QTable agents, 1001x101 tables left in HBM, max_steps=100, %d runs/GPU x %d epochs per step",
+                kernel="thrl::qtable_scan_hbm<float, false> (as c4)"),
     # C5 with the environment's own default demand noise (environments.py:7, noise_prob = 0.05): the network input is a continuous
     # price, so the lattice kernel does not apply and the interval-table kernel runs.  algo_bytes: one table row
     # per act (22 head columns x 16 B) + the update's share as for c5.
@@ -93,7 +100,7 @@ WORKLOADS = {
                 kernel="thrl::mlp_scan_pwc (persistent, one launch per step; exact per-unit float32 thresholds, per-interval (S1,S0) "
                        "head tables, updates by one sweep over the transitions in interval order; no dense contraction is left)"),
 }
-EXTRAS = ("c2", "c4", "c5", "c5n")
+EXTRAS = ("c2", "c4", "c4w", "c5", "c5n")
 # warp instructions per agent-step from the committed ncu captures (profiles/)
 NCU_INSTR = {"c2": 30.4, "c5": 110.5, "c5n": 354.9}
 
@@ -312,7 +319,8 @@ def measure(name, wl, R, E, steps, warmup, e2e_chunks, ctx):
     del batch, out
     torch.cuda.empty_cache()
 
-    e2e = measure_e2e(wl, R, E, min(steps, 3), e2e_chunks, ctx, barrier)
+    e2e = (measure_e2e(wl, R, E, min(steps, 3), e2e_chunks, ctx, barrier) if e2e_chunks > 0 else
+           {"value": None, "unit": "agent-steps/s", "skipped": "secondary sizing of c4: see workloads.c4.e2e"})
     res = {"value": value, "ms_per_step": total_ms / steps, "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
            "kernel_dispatched": kernel_name}
 
@@ -339,7 +347,7 @@ def measure(name, wl, R, E, steps, warmup, e2e_chunks, ctx):
             "issue_slots": {"warp_inst_per_agent_step": NCU_INSTR["c2"], "achieved": per_gpu_rate * NCU_INSTR["c2"],
                             "peak": 4 * 148 * sm_max_mhz * 1e6, "unit": "warp-inst/s",
                             "frac": per_gpu_rate * NCU_INSTR["c2"] / (4 * 148 * sm_max_mhz * 1e6)}})
-    elif name == "c4":
+    elif name in ("c4", "c4w"):
         roof["note"] = ("tables (3.2 MB per run) stay in HBM; 824 algorithmic B per agent-step = 8*A + 16 (BASELINE.md 5: act row + "
                         "bootstrap row + cell + counter); peak = measured copy bandwidth from MEASURED_PEAKS.json (%s).  The kernel "
                         "moves less than that: the act row is served by an exact greedy-action cache on chip and a row that several "
@@ -371,7 +379,7 @@ def measure(name, wl, R, E, steps, warmup, e2e_chunks, ctx):
                                "peak": 4 * 148 * sm_max_mhz * 1e6, "unit": "warp-inst/s",
                                "frac": per_gpu_rate * NCU_INSTR[name] / (4 * 148 * sm_max_mhz * 1e6)}
     try:  # DRAM traffic per launch, measured once with ncu --set full on this exact command (profiles/)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(name)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("c4" if name == "c4w" else name)
         if tr and R == wl["runs_per_gpu"]:  # per agent-step as captured x the agent-steps of this launch
             roof["traffic"] = tr["traffic_bytes_per_agent_step"] * agent_steps_rank
             roof["traffic_source"] = tr["source"]
@@ -536,7 +544,7 @@ def main():
         args.runs_per_gpu = args.global_runs // max(1, args.gpus)
     args.runs_per_gpu = args.runs_per_gpu or wl["runs_per_gpu"]
     args.epochs = args.epochs or wl["epochs"]
-    args.e2e_chunks = args.e2e_chunks or wl["e2e_chunks"]
+    args.e2e_chunks = wl["e2e_chunks"] if args.e2e_chunks is None else args.e2e_chunks
     if args.impl == "reference":
         return run_reference(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))

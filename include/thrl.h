@@ -24,7 +24,7 @@
  * cudaStream_t (passed as void*); the return value is 0 or a negative ThrlStatus, with a message in
  * thrl_last_error().  Device memory: the Q-table kernels allocate nothing.  Two paths use
  * library-owned scratch, both stream-ordered and cached (steady-state calls allocate nothing): the
- * lattice kernel for MLP agents takes its per-warp workspace from a per-device memory pool
+ * lattice and interval-table kernels for MLP agents take their per-warp workspace from a per-device memory pool
  * (cudaMallocFromPoolAsync on the caller's stream, release threshold = keep), and the `_host` entry
  * point keeps a per-device staging arena (three chunk slots) between calls; thrl_release_device_memory()
  * returns both to the driver.
@@ -219,8 +219,10 @@ int thrl_curve_hist(const double* rewards_log, int64_t n_runs, int32_t epochs, i
 /* Number of kernels this library has launched since load (bench.py reports it as gpu_launches). */
 int64_t thrl_launch_count(void);
 /* Name of the scan kernel the calling thread's latest thrl_qtable_scan / thrl_qtable_scan_host launched: "lut2", "lpc",
- * "generic" (Q-table games), "pwl" (lattice kernel for games with Reinforce / ActorCritic agents), "mixed" (order-exact MLP
- * kernel).  The dispatch is a function of the game, the inputs and THRL_KERNEL; tests use this to check it. */
+ * "hbm", "generic" (Q-table games), "pwl" (lattice kernel: Reinforce / ActorCritic agents on the noise-free demand curve),
+ * "pwc" (interval-table kernel: MLP agents on a continuous price -- demand noise, CAC, pending QTable batches), "mixed"
+ * (order-exact MLP kernel).  The dispatch is a function of the game, the inputs and THRL_KERNEL (= generic | lpc | mixed | pwc
+ * force a kernel where it applies); tests use this to check it. */
 const char* thrl_last_kernel(void);
 /* Runs the calling thread's latest scan launch kept resident at once (persistent grid x runs per CTA).  A caller that cuts a
  * batch into several launches (engine.scan_from_host overlaps them with host copies) sizes the pieces in multiples of this,

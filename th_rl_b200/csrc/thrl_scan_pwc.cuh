@@ -538,14 +538,29 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
       const bool leave = (o & 0x8000u) != 0;
       const double w = (double)w1[j], b = (double)b1[j];
       double gw = 0.0, gb = 0.0;
-      for (int c = 0; c < NC; ++c) {
-        const double2 pre = pwc_ld2(pf + (size_t)(q + 1) * ncp + c), tt = pwc_ld2(pf + (size_t)(H + 1) * ncp + c);
-        const double M0 = leave ? pre.x : __dsub_rn(tt.x, pre.x), M1 = leave ? pre.y : __dsub_rn(tt.y, pre.y);
-        const int wi = pwc_wrow(spec, c) + j;
-        g[wi] = (float)__dadd_rn(__dmul_rn(w, M1), __dmul_rn(b, M0));
-        const double cw = (double)blk[wi];
-        gb = __dadd_rn(gb, __dmul_rn(cw, M0));
-        gw = __dadd_rn(gw, __dmul_rn(cw, M1));
+      // four columns per round, every load of the round issued before its arithmetic (the prefix sums sit in L2)
+      for (int c0 = 0; c0 < NC; c0 += 4) {
+        double2 pre[4], tt[4];
+        float cwf[4];
+        int wi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u < NC ? c0 + u : NC - 1;
+          pre[u] = pwc_ld2(pf + (size_t)(q + 1) * ncp + c);
+          tt[u] = pwc_ld2(pf + (size_t)(H + 1) * ncp + c);
+          wi[u] = pwc_wrow(spec, c) + j;
+          cwf[u] = blk[wi[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c0 + u < NC) {
+            const double M0 = leave ? pre[u].x : __dsub_rn(tt[u].x, pre[u].x), M1 = leave ? pre[u].y : __dsub_rn(tt[u].y, pre[u].y);
+            g[wi[u]] = (float)__dadd_rn(__dmul_rn(w, M1), __dmul_rn(b, M0));
+            const double cw = (double)cwf[u];
+            gb = __dadd_rn(gb, __dmul_rn(cw, M0));
+            gw = __dadd_rn(gw, __dmul_rn(cw, M1));
+          }
+        }
       }
       g[j] = (float)gw;
       g[H + j] = (float)gb;

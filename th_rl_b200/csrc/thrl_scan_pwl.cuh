@@ -536,23 +536,38 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
       unsigned xm = 0;
       for (int e2 = 0; e2 < nx; ++e2) xm |= pwl_active(sv[NS + e2], w, b) ? 1u << e2 : 0u;
       double gw = 0.0, gb = 0.0;
-#pragma unroll 4
-      for (int c = 0; c < NC; ++c) {
-        const double2 pre = pf[key * CW + c], tt = pf[NS * CW + c];
-        double M0 = leave ? pre.x : __dsub_rn(tt.x, pre.x), M1 = leave ? pre.y : __dsub_rn(tt.y, pre.y);
-        for (int e2 = 0; e2 < nx; ++e2) {
-          if (xm >> e2 & 1) {
-            const double2 dx = pf[(NS + 1 + e2) * CW + c];
-            M0 = __dadd_rn(M0, dx.x);
-            M1 = __dadd_rn(M1, dx.y);
+      // four columns per round, every load of the round issued before its arithmetic (the prefix sums sit in L2: the loop is
+      // bound by their latency otherwise)
+      for (int c0 = 0; c0 < NC; c0 += 4) {
+        double2 pre[4], tt[4];
+        float cwf[4];
+        int wi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u < NC ? c0 + u : NC - 1;
+          pre[u] = pf[key * CW + c];
+          tt[u] = pf[NS * CW + c];
+          wi[u] = c < A ? 2 * H + c * H + j : 2 * H + A * H + A + j;  // fc_pi.weight[c][j] / fc_v.weight[j]
+          cwf[u] = blk[wi[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + u;
+          if (c < NC) {
+            double M0 = leave ? pre[u].x : __dsub_rn(tt[u].x, pre[u].x), M1 = leave ? pre[u].y : __dsub_rn(tt[u].y, pre[u].y);
+            for (int e2 = 0; e2 < nx; ++e2) {
+              if (xm >> e2 & 1) {
+                const double2 dx = pf[(NS + 1 + e2) * CW + c];
+                M0 = __dadd_rn(M0, dx.x);
+                M1 = __dadd_rn(M1, dx.y);
+              }
+            }
+            g[wi[u]] = (float)__dadd_rn(__dmul_rn((double)w, M1), __dmul_rn((double)b, M0));
+            const double cw = (double)cwf[u];
+            gb = __dadd_rn(gb, __dmul_rn(cw, M0));
+            gw = __dadd_rn(gw, __dmul_rn(cw, M1));
           }
         }
-        const float gc = (float)__dadd_rn(__dmul_rn((double)w, M1), __dmul_rn((double)b, M0));
-        const int wi = c < A ? 2 * H + c * H + j : 2 * H + A * H + A + j;  // fc_pi.weight[c][j] / fc_v.weight[j]
-        g[wi] = gc;
-        const double cw = (double)blk[wi];
-        gb = __dadd_rn(gb, __dmul_rn(cw, M0));
-        gw = __dadd_rn(gw, __dmul_rn(cw, M1));
       }
       g[j] = (float)gw;
       g[H + j] = (float)gb;

@@ -211,6 +211,44 @@ __device__ __forceinline__ void pwl_emit(float z, bool col, bool vcol, int A, in
   if (vcol) val[x] = z;
 }
 
+// The same for four states at a time: the four softmax / running-sum chains are independent, so their shuffle and
+// special-function latencies overlap (one chain is ~450 cycles long).  zs: the logits of state x at zs[x * A + lane] (the
+// probabilities overwrite them); states x0 .. x0+3 that are >= NX are skipped.  Per state the arithmetic is pwl_emit's.
+__device__ __forceinline__ void pwl_emit4(int x0, int NX, bool col, int A, float* cdf, float* zs, int lane) {
+  float z[4], mx[4], ex[4], sum[4], pk[4], c[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int x = x0 + u < NX ? x0 + u : NX - 1;
+    z[u] = col ? zs[x * A + lane] : 0.0f;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) mx[u] = warp_max(col ? z[u] : NegInf<float>::v());
+#pragma unroll
+  for (int u = 0; u < 4; ++u) ex[u] = col ? det_expf(__fsub_rn(z[u], mx[u])) : 0.0f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) sum[u] = ex[u];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sum[u] = __fadd_rn(sum[u], __shfl_xor_sync(kFull, sum[u], off));
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) { pk[u] = col ? __fdiv_rn(ex[u], sum[u]) : 0.0f; c[u] = pk[u]; }
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = __shfl_up_sync(kFull, c[u], off);
+      if (lane >= off) c[u] = __fadd_rn(c[u], t);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int x = x0 + u;
+    if (col && x < NX) { cdf[x * A + lane] = c[u]; zs[x * A + lane] = pk[u]; }
+  }
+}
+
 constexpr int kPwlTile = 8;  // hidden units staged per round of the forward sweep
 
 // pi(.|s) and v(s) for every lattice state (one sweep, see the header) and for the extras (direct evaluation).
@@ -271,9 +309,10 @@ __device__ inline void pwl_build_lut(const float* blk, const ThrlAgentSpec& spec
     }
   };
   int r = 0;
-  auto emit_row = [&]() {
+  auto emit_row = [&]() {  // the logits of rank r are parked (pws, val); the softmaxes follow the sweep, four states at a time
     const float z = (float)__dadd_rn(__dadd_rn(__dmul_rn(S1, (double)sv[r]), S0), bias);
-    pwl_emit(z, col, vcol, A, r, cdf, val, pws, lane);
+    if (col) pws[r * A + lane] = z;
+    if (vcol) val[r] = z;
     ++r;
   };
   gather(0);
@@ -306,8 +345,12 @@ __device__ inline void pwl_build_lut(const float* blk, const ThrlAgentSpec& spec
       const float hv = __fadd_rn(__fmul_rn(s, w1[j]), b1[j]);
       if (hv > 0.0f) acc = __dadd_rn(acc, __dmul_rn((double)hv, use ? (double)crow[j] : 0.0));
     }
-    pwl_emit((float)__dadd_rn(acc, bias), col, vcol, A, x, cdf, val, pws, lane);
+    const float z = (float)__dadd_rn(acc, bias);
+    if (col) pws[x * A + lane] = z;
+    if (vcol) val[x] = z;
   }
+  __syncwarp();
+  for (int x0 = 0; x0 < NS + nx; x0 += 4) pwl_emit4(x0, NS + nx, col, A, cdf, pws, lane);
   __syncwarp();
 }
 
@@ -339,12 +382,13 @@ __device__ inline void pwl_clip_adam(float* blk, const ThrlAgentSpec& spec, cons
   const float neg_step_size = (float)(-__ddiv_rn(spec.lr, bc1));
   const float bc2_sqrt = (float)sqrt(bc2);
   const float w1m = (float)__dsub_rn(1.0, 0.9), fb2 = (float)0.999, w2 = (float)__dsub_rn(1.0, 0.999), eps = 1e-8f;
-  // four parameters per lane and round, every load issued before the arithmetic (the moments live in HBM: the loop is
+  // eight parameters per lane and round, every load issued before the arithmetic (the moments live in HBM: the loop is
   // latency-bound otherwise; pwl_train prefetches the block into L2 while the gradient is being formed)
-  for (int i0 = lane; i0 < P; i0 += 128) {
-    float gi[4], m[4], v[4], w[4];
+  constexpr int kW = 8;  // parameters per lane and round
+  for (int i0 = lane; i0 < P; i0 += 32 * kW) {
+    float gi[kW], m[kW], v[kW], w[kW];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kW; ++u) {
       const int i = i0 + 32 * u;
       const bool in = i < P;
       gi[u] = in ? g[i] : 0.0f;
@@ -353,7 +397,7 @@ __device__ inline void pwl_clip_adam(float* blk, const ThrlAgentSpec& spec, cons
       w[u] = in ? blk[i] : 0.0f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kW; ++u) {
       const int i = i0 + 32 * u;
       if (i < P) {
         const float gc = __fmul_rn(gi[u], coef);

@@ -203,26 +203,41 @@ __device__ inline void pwc_build(const float* blk, const ThrlAgentSpec& spec, un
   // interval table, lane = head column: S(r) = sum over the units active on interval r of W[c][j] * (w1_j, b1_j)
   const bool use = lane < NC;
   const float* wrow = blk + pwc_wrow(spec, use ? lane : 0);
+  // Eight ranked units per round: their (w1, b1, W[c]) are loaded together, then applied in rank order.  First round trip: the
+  // sum over the units that are active from the lowest price on (they leave at their threshold); second: the running sums.
   double L1 = 0.0, L0 = 0.0;
-  for (int q = 0; q < H; ++q) {  // units active from the lowest price on (they leave at their threshold)
-    const unsigned o = ord[q];
-    if (o & 0x8000u) {
-      const int j = (int)(o & 0x7fffu);
-      const double cw = (double)wrow[j];
-      L1 = __dadd_rn(L1, __dmul_rn(cw, (double)w1[j]));
-      L0 = __dadd_rn(L0, __dmul_rn(cw, (double)b1[j]));
+  for (int pass = 0; pass < 2; ++pass) {
+    double S1 = L1, S0 = 0.0;
+    if (pass == 1) {
+      S0 = __dadd_rn(L0, use ? (double)blk[pwc_bias(spec, lane)] : 0.0);
+      if (use) __stcg(tab + lane, make_double2(S1, S0));
     }
-  }
-  double S1 = L1, S0 = __dadd_rn(L0, use ? (double)blk[pwc_bias(spec, lane)] : 0.0);
-  if (use) __stcg(tab + lane, make_double2(S1, S0));
-  for (int q = 0; q < H; ++q) {
-    const unsigned o = ord[q];
-    const int j = (int)(o & 0x7fffu);
-    const double cw = (double)wrow[j];
-    const double t1 = __dmul_rn(cw, (double)w1[j]), t0 = __dmul_rn(cw, (double)b1[j]);
-    if (o & 0x8000u) { S1 = __dsub_rn(S1, t1); S0 = __dsub_rn(S0, t0); }
-    else { S1 = __dadd_rn(S1, t1); S0 = __dadd_rn(S0, t0); }
-    if (use) __stcg(tab + (size_t)(q + 1) * ncp + lane, make_double2(S1, S0));
+    for (int q0 = 0; q0 < H; q0 += 8) {
+      unsigned o[8];
+      float cwf[8], wf[8], bf[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) o[u] = q0 + u < H ? (unsigned)ord[q0 + u] : 0u;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int j = (int)(o[u] & 0x7fffu);
+        cwf[u] = wrow[j]; wf[u] = w1[j]; bf[u] = b1[j];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (q0 + u < H) {
+          const double cw = (double)cwf[u];
+          const double t1 = __dmul_rn(cw, (double)wf[u]), t0 = __dmul_rn(cw, (double)bf[u]);
+          const bool leave = (o[u] & 0x8000u) != 0;
+          if (pass == 0) {
+            if (leave) { L1 = __dadd_rn(L1, t1); L0 = __dadd_rn(L0, t0); }
+          } else {
+            if (leave) { S1 = __dsub_rn(S1, t1); S0 = __dsub_rn(S0, t0); }
+            else { S1 = __dadd_rn(S1, t1); S0 = __dadd_rn(S0, t0); }
+            if (use) __stcg(tab + (size_t)(q0 + u + 1) * ncp + lane, make_double2(S1, S0));
+          }
+        }
+      }
+    }
   }
   __syncwarp();
 }

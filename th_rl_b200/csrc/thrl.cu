@@ -800,6 +800,8 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, size_t elem, int smem_optin, int* 
   const int fit = (smem_optin - p->cta_bytes) / p->warp_bytes;
   if (fit < 1) return false;
   *warps = fit > 16 ? 16 : fit;
+  if (const char* f = getenv("THRL_PWL_WARPS"))
+    if (atoi(f) >= 1 && atoi(f) < *warps) *warps = atoi(f);
   return true;
 }
 

@@ -268,27 +268,14 @@ __device__ inline void pwl_build_lut(const float* blk, const ThrlAgentSpec& spec
   __syncwarp();
   // units active from rank 0 on (they leave at their breakpoint): lane = unit, coalesced rows of the weights, one
   // butterfly sum per column; lane c keeps column c
-  // (eight units per lane and round: their weights are loaded together, a unit that does not leave contributes a zero weight)
   for (int c = 0; c < NC; ++c) {
     const float* row = c < A ? W + (size_t)c * H : wv;
     double p1 = 0.0, p0 = 0.0;
-    for (int j0 = lane; j0 < H; j0 += 256) {
-      float cwf[8], wf[8], bf[8];
-      bool lv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int j = j0 + 32 * u;
-        lv[u] = j < H && (ev[j] & 0x8000);
-        const int jj = j < H ? j : 0;
-        cwf[u] = row[jj]; wf[u] = w1[jj]; bf[u] = b1[jj];
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        if (lv[u]) {
-          const double cw = (double)cwf[u];
-          p1 = __dadd_rn(p1, __dmul_rn(cw, (double)wf[u]));
-          p0 = __dadd_rn(p0, __dmul_rn(cw, (double)bf[u]));
-        }
+    for (int j = lane; j < H; j += 32) {
+      if (ev[j] & 0x8000) {
+        const double cw = (double)row[j];
+        p1 = __dadd_rn(p1, __dmul_rn(cw, (double)w1[j]));
+        p0 = __dadd_rn(p0, __dmul_rn(cw, (double)b1[j]));
       }
     }
     p1 = warp_sum(p1);
@@ -506,28 +493,15 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
     }
     const float fN = (float)N, fR = (float)warp_sum(Rp), fD = (float)warp_sum(Dp);
     const float invN2 = __fdiv_rn(1.0f, __fmul_rn(fN, fN));
-    for (int n0 = lane; n0 < N; n0 += 128) {  // the [N,N] advantage broadcast collapsed as in oracle ac_train; four per round
-      float4 qq[4];
-      float rr[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int nn = n0 + 32 * u < N ? n0 + 32 * u : N - 1;
-        qq[u] = xs[nn];
-        rr[u] = entry(nn)[2];
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int nn = n0 + 32 * u;
-        if (nn < N) {
-          float4 q = qq[u];
-          q.y = __fmul_rn(__fadd_rn(__fmul_rn(fN, rr[u]), fD), invN2);                   // actor weight (N r_j + D) / N^2
-          q.z = __fmul_rn(-2.0f, __fmul_rn(__fadd_rn(fR, __fmul_rn(fN, q.w)), invN2));   // dL/dv_j; dL/dv'_j = -gamma * that
-          bad |= !isfinite(q.y) || !isfinite(q.z);
-          camax = fmaxf(camax, fabsf(q.y));
-          cvmax = fmaxf(cvmax, fmaxf(fabsf(q.z), fabsf(__fmul_rn(-gam, q.z))));
-          xs[nn] = q;
-        }
-      }
+    for (int nn = lane; nn < N; nn += 32) {  // the [N,N] advantage broadcast collapsed as in oracle ac_train
+      float4 q = xs[nn];
+      const float r = entry(nn)[2];
+      q.y = __fmul_rn(__fadd_rn(__fmul_rn(fN, r), fD), invN2);                       // actor weight (N r_j + D) / N^2
+      q.z = __fmul_rn(-2.0f, __fmul_rn(__fadd_rn(fR, __fmul_rn(fN, q.w)), invN2));   // dL/dv_j; dL/dv'_j = -gamma * that
+      bad |= !isfinite(q.y) || !isfinite(q.z);
+      camax = fmaxf(camax, fabsf(q.y));
+      cvmax = fmaxf(cvmax, fmaxf(fabsf(q.z), fabsf(__fmul_rn(-gam, q.z))));
+      xs[nn] = q;
     }
   }
   bad = __any_sync(kFull, bad);
@@ -542,28 +516,16 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
   __syncwarp();
   {
     unsigned long long* uacc = reinterpret_cast<unsigned long long*>(acc);
-    for (int n0 = lane; n0 < N; n0 += 128) {  // four transitions per lane and round: loads first, then the reductions
-      float4 qq[4];
-      int aa[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int nn = n0 + 32 * u < N ? n0 + 32 * u : N - 1;
-        qq[u] = xs[nn];
-        aa[u] = __float_as_int(entry(nn)[1]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (n0 + 32 * u < N) {
-          const float4 q = qq[u];
-          const int xb = __float_as_int(q.x), x = xb & 0xffff, x2 = (xb >> 16) & 0xffff;
-          const unsigned long long fa = (unsigned long long)__double2ll_rn(__dmul_rn((double)q.y, sa));
-          atomicAdd(uacc + x * C + aa[u], fa);
-          atomicAdd(uacc + x * C + A + 1, fa);
-          if (ac) {
-            atomicAdd(uacc + x * C + A, (unsigned long long)__double2ll_rn(__dmul_rn((double)q.z, sc)));
-            atomicAdd(uacc + x2 * C + A, (unsigned long long)__double2ll_rn(__dmul_rn((double)__fmul_rn(-gam, q.z), sc)));
-          }
-        }
+    for (int nn = lane; nn < N; nn += 32) {
+      const float4 q = xs[nn];
+      const int xb = __float_as_int(q.x), x = xb & 0xffff, x2 = (xb >> 16) & 0xffff;
+      const int a = __float_as_int(entry(nn)[1]);
+      const unsigned long long fa = (unsigned long long)__double2ll_rn(__dmul_rn((double)q.y, sa));
+      atomicAdd(uacc + x * C + a, fa);
+      atomicAdd(uacc + x * C + A + 1, fa);
+      if (ac) {
+        atomicAdd(uacc + x * C + A, (unsigned long long)__double2ll_rn(__dmul_rn((double)q.z, sc)));
+        atomicAdd(uacc + x2 * C + A, (unsigned long long)__double2ll_rn(__dmul_rn((double)__fmul_rn(-gam, q.z), sc)));
       }
     }
   }

@@ -88,7 +88,7 @@ typedef struct ThrlAgentSpec {
   int32_t kind;       /* ThrlAgentKind */
   int32_t hidden;     /* width of fc1 (reference: 256) */
   double lr;          /* Adam learning rate (reference: 2e-4); betas (0.9, 0.999), eps 1e-8 */
-  double entropy;     /* entropy coefficient (reference default 0; only 0 is supported) */
+  double entropy;     /* entropy coefficient c_e of loss + c_e * (-mean entropy) (agents.py:187-189, 298-300, 410-412; default 0) */
   int64_t mlp_offset; /* float offset of this agent's block inside one run's MLP slab; set by thrl_game_layout */
   /* ABI 3: elements between the starts of consecutive table rows; set by thrl_game_layout.  Equal to `actions` while one run's
    * tables are small enough to be staged in shared memory; games whose tables stay in HBM (sum_i (states_i+1)*actions_i*4 B >=

@@ -154,6 +154,15 @@ CASES = {
                                           min_memory=90, capacity=120),
                                      dict(name="CAC", gamma=0.5, states=1, action_range=[0.05, 0.2], min_memory=60)],
                              environment=_env(noise_prob=0.2, max_steps=30), training=dict(epochs=12, print_freq=1000)), 20),
+    # entropy regulariser (agents.py:187-189, 298-300, 410-412): Reinforce + ActorCritic, and QTable + CAC with demand noise
+    "ent_ra_seed21": (dict(agents=[dict(name="Reinforce", gamma=0.9, actions=7, states=1, action_range=[0.1, 0.3],
+                                        min_memory=60, entropy=0.05),
+                                   dict(name="ActorCritic", gamma=0.9, actions=5, states=1, action_range=[0.05, 0.2],
+                                        min_memory=90, capacity=120, entropy=0.02)],
+                           environment=_env(max_steps=30), training=dict(epochs=12, print_freq=1000)), 21),
+    "ent_qc_seed22": (dict(agents=[_agent(), dict(name="CAC", gamma=0.98, states=1, action_range=[0.2, 0.4], min_memory=200,
+                                                  entropy=0.05)],
+                           environment=_env(noise_prob=0.2), training=dict(epochs=8, print_freq=1000)), 22),
 }
 
 EVAL_ITERS = 3  # episodes of utils.play_game recorded per case (noise-free cases only)

@@ -62,6 +62,7 @@ static double u53(uint32_t hi, uint32_t lo) {
 /* ---------------------------------------------------------------- deterministic N(0,1) from a 53-bit uniform
  * (used by thrl_oracle_qtable_init; DESIGN.md "Device init").  Only + - * / and sqrt, in a fixed order, so the
  * CUDA version (explicit _rn intrinsics) reproduces it bit-for-bit.  log() is our own: frexp + atanh series. */
+#define THRL_ORACLE_MAX_ACTIONS 1024 /* scratch for one agent's action probabilities */
 static double det_log(double x) {
   int e;
   double m = frexp(x, &e); /* m in [0.5,1) */
@@ -327,6 +328,26 @@ static void mlp_back_fc1(int H, const float* h, const float* dh, float s, float*
   }
 }
 
+/* entropy regulariser of the discrete agents (agents.py:187-189, 298-300): loss += c_e * (-mean_n H(pi(.|s_n))), Categorical(probs):
+ * H = -sum_k p_k log p_k.  d/dlogits_k of -H_n / N is p_k (log p_k + H_n) / N (softmax Jacobian; the Categorical's renormalisation
+ * of probabilities that already sum to one has no first-order effect).  Adds ce_n = c_e / N times that to dl[k]; p = pi(.|s_n).
+ * A probability that underflowed to zero contributes nothing (torch clamps it before the log). */
+static void mlp_entropy_grad(const float* p, int A, float ce_n, float* dl) {
+  float lp[THRL_ORACLE_MAX_ACTIONS];
+  float Hn = 0.0f;
+  for (int k = 0; k < A; ++k) {
+    lp[k] = p[k] > 0.0f ? (float)det_log((double)p[k]) : 0.0f;
+    float t = p[k] * lp[k];
+    Hn = Hn - t;
+  }
+  for (int k = 0; k < A; ++k) {
+    float t = lp[k] + Hn;
+    t = p[k] * t;
+    t = ce_n * t;
+    dl[k] = dl[k] + t;
+  }
+}
+
 /* Reinforce.train_net (agents.py:170-194) on the N buffered transitions buf[(head+j) % cap] = (state, action, reward),
  * then clip_grad_norm_(1.0) and one Adam step.  blk = this agent's block of the MLP slab (include/thrl.h).
  * scratch: P + 2H + A + N floats. */
@@ -353,6 +374,7 @@ static void mlp_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, in
   for (int j = 0; j < N; ++j) { const double d = (double)disc[j] - (double)mean; ss += d * d; }
   const float sd = (float)sqrt(ss / (double)(N - 1));
   const float invN = 1.0f / (float)N;
+  const float ce = (float)sp->entropy;
   /* loss = -mean(log_prob(a) * G) (:185); d loss / d logits_k = (p_k - [k == a]) * G / N, back through fc_pi, relu, fc1 */
   for (int j = 0; j < N; ++j) {
     const float* tr = buf + (size_t)((head + j) % cap) * EW;
@@ -363,7 +385,14 @@ static void mlp_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, in
     G = G / sd;
     const float c = G * invN;
     mlp_forward(par, H, A, s, h, prob);
-    for (int k = 0; k < A; ++k) { float dl = prob[k] - (k == a ? 1.0f : 0.0f); prob[k] = dl * c; }
+    if (ce != 0.0f) {
+      float pk[THRL_ORACLE_MAX_ACTIONS];
+      for (int k = 0; k < A; ++k) pk[k] = prob[k];
+      for (int k = 0; k < A; ++k) { float dl = prob[k] - (k == a ? 1.0f : 0.0f); prob[k] = dl * c; }
+      mlp_entropy_grad(pk, A, ce * invN, prob);
+    } else {
+      for (int k = 0; k < A; ++k) { float dl = prob[k] - (k == a ? 1.0f : 0.0f); prob[k] = dl * c; }
+    }
     mlp_back_pi(par, H, A, h, prob, g, dh);
     mlp_back_fc1(H, h, dh, s, g);
   }
@@ -399,6 +428,7 @@ static void ac_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, int
   }
   const float fN = (float)N, fR = (float)R, fD = (float)D;
   const float invN2 = 1.0f / (fN * fN);
+  const float ce = (float)sp->entropy, invN = 1.0f / fN;
   for (int j = 0; j < N; ++j) {
     const float* tr = buf + (size_t)((head + j) % cap) * EW;
     const float s = tr[0], s2 = tr[3];
@@ -413,7 +443,14 @@ static void ac_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, int
     cv = -2.0f * cv; /* dL/dv_j = -2 (R + N d_j) / N^2 */
     const float cvp = (-gam) * cv; /* dL/dv'_j */
     mlp_forward(par, H, A, s, h, prob);
-    for (int k = 0; k < A; ++k) { float dl = prob[k] - (k == a ? 1.0f : 0.0f); prob[k] = dl * ca; }
+    if (ce != 0.0f) {
+      float pk[THRL_ORACLE_MAX_ACTIONS];
+      for (int k = 0; k < A; ++k) pk[k] = prob[k];
+      for (int k = 0; k < A; ++k) { float dl = prob[k] - (k == a ? 1.0f : 0.0f); prob[k] = dl * ca; }
+      mlp_entropy_grad(pk, A, ce * invN, prob);
+    } else {
+      for (int k = 0; k < A; ++k) { float dl = prob[k] - (k == a ? 1.0f : 0.0f); prob[k] = dl * ca; }
+    }
     mlp_back_pi(par, H, A, h, prob, g, dh);
     for (int jh = 0; jh < H; ++jh) { /* value head at s_j shares h with the policy head */
       float t = cv * h[jh];
@@ -524,7 +561,11 @@ static void cac_train(float* blk, const ThrlAgentSpec* sp, int cap, int head, in
     const double A1 = Srl - dmu * Sr + dd * (Sl - dN * dmu);
     const double A2 = Srl2 - 2.0 * dmu * Srl + dmu * dmu * Sr + dd * (Sl2 - 2.0 * dmu * Sl + dN * dmu * dmu);
     const float gmu = (float)(-(A1 / (dsd * dsd)) * invN2);
-    const float gsd = (float)(-(A2 / (dsd * dsd * dsd) - A0 / dsd) * invN2);
+    float gsd = (float)(-(A2 / (dsd * dsd * dsd) - A0 / dsd) * invN2);
+    if (sp->entropy != 0.0) { /* + c_e * (-mean Normal(mu, sd).entropy()) (:410-412): d/dsd = -c_e / (N sd) */
+      const float ge = (float)(-(sp->entropy / (dN * dsd)));
+      gsd = gsd + ge;
+    }
     const float cv = (float)(-2.0 * A0 * invN2); /* dL/dv_i */
     const float cvp = (-gam) * cv;               /* dL/dv'_i */
     float dzmu = 1.0f - t * t;
@@ -1014,7 +1055,7 @@ int thrl_oracle_game_layout(ThrlGame* G) {
     int64_t need = (int64_t)T * ((mm + T - 1) / T);
     if (need > s->capacity) need = s->capacity;
     if (s->kind == THRL_AGENT_REINFORCE || s->kind == THRL_AGENT_ACTORCRITIC || s->kind == THRL_AGENT_CAC) {
-      if (s->states != 1 || s->hidden < 1 || s->entropy != 0.0) return THRL_ERR_BAD_CONFIG;
+      if (s->states != 1 || s->hidden < 1) return THRL_ERR_BAD_CONFIG;
       const int64_t P = mlp_P(s);
       G->mlp_buffer_len[i] = s->min_memory <= s->capacity ? (int32_t)need : 0;
       s->mlp_offset = moff;

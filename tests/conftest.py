@@ -49,6 +49,8 @@ def uses_lattice_kernel(cfg):
     mlp = [k in (abi.THRL_AGENT_REINFORCE, abi.THRL_AGENT_ACTORCRITIC) for k in kinds]
     if not any(mlp) or any(k == abi.THRL_AGENT_CAC for k in kinds):
         return False
+    if any(g.agent[i].entropy != 0 for i in range(g.n_agents) if mlp[i]):
+        return False  # the entropy regulariser runs on the interval-table kernel
     if not all(mlp) and not g.regular:
         return False
     joint = 1

@@ -250,8 +250,10 @@ def test_c_abi_error_paths_need_no_device():
     a.game = C.pointer(gm)
     assert L.thrl_qtable_scan(C.byref(a), None) == abi.THRL_ERR_BAD_ARGS and "mlp" in err()
     ent = abi.game_from_config(mixed)
-    ent.agent[1].entropy = 0.01
-    assert L.thrl_game_layout(C.byref(ent)) == abi.THRL_ERR_UNSUPPORTED and "entropy" in err()
+    ent.agent[1].entropy = 0.01  # the entropy regulariser is part of the path (agents.py:187-189): accepted
+    assert L.thrl_game_layout(C.byref(ent)) == abi.THRL_OK
+    ent.agent[1].entropy = float("nan")
+    assert L.thrl_game_layout(C.byref(ent)) == abi.THRL_ERR_BAD_CONFIG and "entropy" in err()
     assert L.thrl_qtable_scan(C.byref(args(n_runs=0)), None) == abi.THRL_OK  # nothing to do
     import torch
     if not torch.cuda.is_available():

@@ -95,7 +95,7 @@ int validate_layout(ThrlGame* G) {
     if (s->kind == THRL_AGENT_REINFORCE || s->kind == THRL_AGENT_ACTORCRITIC || s->kind == THRL_AGENT_CAC) {
       if (s->states != 1) return fail(THRL_ERR_BAD_CONFIG, "agent %d: states=%d for an MLP agent, the environment's state is one number", i, s->states);
       if (s->hidden < 1 || s->hidden > 1024) return fail(THRL_ERR_BAD_CONFIG, "agent %d: hidden=%d outside 1..1024", i, s->hidden);
-      if (s->entropy != 0.0) return fail(THRL_ERR_UNSUPPORTED, "agent %d: entropy coefficient %g (only the reference default 0 is implemented)", i, s->entropy);
+      if (!(s->entropy == s->entropy)) return fail(THRL_ERR_BAD_CONFIG, "agent %d: entropy coefficient is NaN", i);
       const bool ac = s->kind != THRL_AGENT_REINFORCE;  // 4-word transitions (new_state kept)
       const long long P = s->kind == THRL_AGENT_CAC ? 5LL * s->hidden + 3
                                                     : 2LL * s->hidden + (long long)s->actions * s->hidden + s->actions + (s->kind == THRL_AGENT_ACTORCRITIC ? s->hidden + 1 : 0);
@@ -697,6 +697,7 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, size_t elem, int smem_optin, int* 
       if (s.states + 1 > rows_max) rows_max = s.states + 1;
     } else if (s.kind == THRL_AGENT_REINFORCE || s.kind == THRL_AGENT_ACTORCRITIC) {
       if (s.actions > 31 || s.hidden < 1) return false;
+      if (s.entropy != 0.0) return false;  // the entropy regulariser is implemented by the interval-table and order-exact kernels
       if (leading) ++lead;
       const int P = 2 * s.hidden + s.actions * s.hidden + s.actions + (s.kind == THRL_AGENT_ACTORCRITIC ? s.hidden + 1 : 0);
       if (P > Pmax) Pmax = P;

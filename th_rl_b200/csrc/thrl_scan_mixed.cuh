@@ -167,6 +167,21 @@ __device__ inline void mlp_clip_adam_warp(float* blk, const ThrlAgentSpec& spec,
   if (lane == 0) hdr[0] = step;
 }
 
+// Entropy regulariser (agents.py:187-189, 298-300; oracle mlp_entropy_grad): H_n = -sum_k p_k log p_k summed in action order
+// by every lane (the same float32 sequence as the oracle); lane k then adds ce_n * p_k * (log p_k + H_n) to its dl.
+__device__ __forceinline__ float mlp_logp(float p) { return p > 0.0f ? (float)det_log((double)p) : 0.0f; }
+__device__ __forceinline__ float mlp_entropy_warp(const float* ps, int A) {
+  float Hn = 0.0f;
+  for (int k = 0; k < A; ++k) {
+    const float pk = ps[k];
+    Hn = __fsub_rn(Hn, __fmul_rn(pk, mlp_logp(pk)));
+  }
+  return Hn;
+}
+__device__ __forceinline__ float mlp_entropy_term(float pk, float Hn, float ce_n) {
+  return __fmul_rn(ce_n, __fmul_rn(pk, __fadd_rn(mlp_logp(pk), Hn)));
+}
+
 // Reinforce.train_net (agents.py:170-194) for one agent of one run; mirrors oracle mlp_train.
 // blk: the agent's block in the global MLP slab; sp: staged parameters (updated in place); gs: gradient scratch [P] in the
 // same staged layout; hs/ps: [H] / [A + 32] scratch.
@@ -205,6 +220,7 @@ __device__ inline void mlp_train_warp(float* blk, const ThrlAgentSpec& spec, int
   mean = __shfl_sync(kFull, mean, 0);
   sd = __shfl_sync(kFull, sd, 0);
   const float invN = __fdiv_rn(1.0f, (float)N);
+  const float ce = (float)spec.entropy, cen = __fmul_rn(ce, invN);
   __syncwarp();
   for (int j = 0; j < N; ++j) {
     int sl = head + j;
@@ -214,8 +230,12 @@ __device__ inline void mlp_train_warp(float* blk, const ThrlAgentSpec& spec, int
     const float G = __fdiv_rn(__fsub_rn(buf[(size_t)sl * EW + 2], mean), sd);
     const float c = __fmul_rn(G, invN);
     mlp_forward_warp(sp, H, A, s, hs, ps, lane);
+    float Hn = 0.0f;
+    if (ce != 0.0f) { Hn = mlp_entropy_warp(ps, A); __syncwarp(); }
     for (int k = lane; k < A; k += 32) {  // d loss / d logits (:185)
-      const float dl = __fmul_rn(__fsub_rn(ps[k], k == a ? 1.0f : 0.0f), c);
+      const float pk = ps[k];
+      float dl = __fmul_rn(__fsub_rn(pk, k == a ? 1.0f : 0.0f), c);
+      if (ce != 0.0f) dl = __fadd_rn(dl, mlp_entropy_term(pk, Hn, cen));
       ps[k] = dl;
       gbp[k] = __fadd_rn(gbp[k], dl);
     }
@@ -263,6 +283,7 @@ __device__ inline void ac_train_warp(float* blk, const ThrlAgentSpec& spec, int 
   }
   const float fN = (float)N, fR = (float)R, fD = (float)D;
   const float invN2 = __fdiv_rn(1.0f, __fmul_rn(fN, fN));
+  const float ce = (float)spec.entropy, cen = __fmul_rn(ce, __fdiv_rn(1.0f, fN));
   for (int j = 0; j < N; ++j) {
     int sl = head + j;
     if (sl >= cap) sl -= cap;
@@ -276,8 +297,12 @@ __device__ inline void ac_train_warp(float* blk, const ThrlAgentSpec& spec, int 
     const float ca = __fmul_rn(__fadd_rn(__fmul_rn(fN, r), fD), invN2);                        // actor weight (N r_j + D) / N^2
     const float cv = __fmul_rn(-2.0f, __fmul_rn(__fadd_rn(fR, __fmul_rn(fN, d)), invN2));      // dL/dv_j
     const float cvp = __fmul_rn(-gam, cv);                                                     // dL/dv'_j
+    float Hn = 0.0f;
+    if (ce != 0.0f) { Hn = mlp_entropy_warp(ps, A); __syncwarp(); }
     for (int k = lane; k < A; k += 32) {
-      const float dl = __fmul_rn(__fsub_rn(ps[k], k == a ? 1.0f : 0.0f), ca);
+      const float pk = ps[k];
+      float dl = __fmul_rn(__fsub_rn(pk, k == a ? 1.0f : 0.0f), ca);
+      if (ce != 0.0f) dl = __fadd_rn(dl, mlp_entropy_term(pk, Hn, cen));
       ps[k] = dl;
       gbp[k] = __fadd_rn(gbp[k], dl);
     }
@@ -394,7 +419,9 @@ __device__ inline void cac_train_warp(float* blk, const ThrlAgentSpec& spec, int
     const double A2 = __dadd_rn(__dadd_rn(__dsub_rn(Srl2, __dmul_rn(__dmul_rn(2.0, dmu), Srl)), __dmul_rn(__dmul_rn(dmu, dmu), Sr)),
                                 __dmul_rn(dd, __dadd_rn(__dsub_rn(Sl2, __dmul_rn(__dmul_rn(2.0, dmu), Sl)), __dmul_rn(__dmul_rn(dN, dmu), dmu))));
     const float gmu = (float)__dmul_rn(-__ddiv_rn(A1, __dmul_rn(dsd, dsd)), invN2);
-    const float gsd = (float)__dmul_rn(-__dsub_rn(__ddiv_rn(A2, __dmul_rn(__dmul_rn(dsd, dsd), dsd)), __ddiv_rn(A0, dsd)), invN2);
+    float gsd = (float)__dmul_rn(-__dsub_rn(__ddiv_rn(A2, __dmul_rn(__dmul_rn(dsd, dsd), dsd)), __ddiv_rn(A0, dsd)), invN2);
+    if (spec.entropy != 0.0)  // + c_e * (-mean Normal(mu, sd).entropy()) (agents.py:410-412): d/dsd = -c_e / (N sd)
+      gsd = __fadd_rn(gsd, (float)(-__ddiv_rn(spec.entropy, __dmul_rn(dN, dsd))));
     const float cv = (float)__dmul_rn(__dmul_rn(-2.0, A0), invN2);
     const float cvp = __fmul_rn(-gam, cv);
     const float dzmu = __fmul_rn(gmu, __fmul_rn(4.0f, __fsub_rn(1.0f, __fmul_rn(t, t))));

@@ -429,7 +429,9 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
       const double A2 = __dadd_rn(__dadd_rn(__dsub_rn(Srl2, __dmul_rn(__dmul_rn(2.0, dmu), Srl)), __dmul_rn(__dmul_rn(dmu, dmu), Sr)),
                                   __dmul_rn(dd, __dadd_rn(__dsub_rn(Sl2, __dmul_rn(__dmul_rn(2.0, dmu), Sl)), __dmul_rn(__dmul_rn(dN, dmu), dmu))));
       const float gmu = (float)__dmul_rn(-__ddiv_rn(A1, __dmul_rn(dsd, dsd)), invN2);
-      const float gsd = (float)__dmul_rn(-__dsub_rn(__ddiv_rn(A2, __dmul_rn(__dmul_rn(dsd, dsd), dsd)), __ddiv_rn(A0, dsd)), invN2);
+      float gsd = (float)__dmul_rn(-__dsub_rn(__ddiv_rn(A2, __dmul_rn(__dmul_rn(dsd, dsd), dsd)), __ddiv_rn(A0, dsd)), invN2);
+      if (spec.entropy != 0.0)  // + c_e * (-mean Normal(mu, sd).entropy()) (agents.py:410-412): d/dsd = -c_e / (N sd)
+        gsd = __fadd_rn(gsd, (float)(-__ddiv_rn(spec.entropy, __dmul_rn(dN, dsd))));
       const float cv = (float)__dmul_rn(__dmul_rn(-2.0, A0), invN2);
       const float dzmu = __fmul_rn(gmu, __fmul_rn(4.0f, __fsub_rn(1.0f, __fmul_rn(t, t))));
       const float dzsd = __fmul_rn(gsd, det_sigmoidf(zsd));
@@ -466,6 +468,7 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
   {
     const bool col = !cac && lane < A, use = lane < NC;
     const int vc = NC - 1;  // value-head column of ActorCritic / CAC
+    const float cen = cac ? 0.0f : __fmul_rn((float)spec.entropy, __fdiv_rn(1.0f, (float)N));
     double P0 = 0.0, P1 = 0.0;
     int rcur = 0;  // rows < rcur of pf are written
     for (int i0 = 0; i0 < NE; i0 += 32) {
@@ -525,7 +528,14 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
           const float mx = warp_max(col ? z : NegInf<float>::v());
           const float ex = col ? pwc_expf(__fsub_rn(z, mx)) : 0.0f;
           const float inv = __frcp_rn(warp_sum(ex));  // pi_k = e_k * (1 / sum): one reciprocal per event
-          if (col) {
+          if (cen != 0.0f) {  // entropy regulariser (agents.py:187-189, 298-300): + c_e / N * p_k (log p_k + H), H = -sum p log p
+            const float pk = col ? __fmul_rn(ex, inv) : 0.0f;
+            const float lp = pk > 0.0f ? (float)det_log((double)pk) : 0.0f;
+            const float Hn = -warp_sum(__fmul_rn(pk, lp));
+            if (col) dz = (double)__fadd_rn(__fmul_rn(__fsub_rn(pk, lane == a ? 1.0f : 0.0f), c0),
+                                            __fmul_rn(cen, __fmul_rn(pk, __fadd_rn(lp, Hn))));
+            else if (ac && lane == A) dz = __dadd_rn((double)c1, (double)c3);
+          } else if (col) {
             dz = (double)__fmul_rn(__fsub_rn(__fmul_rn(ex, inv), lane == a ? 1.0f : 0.0f), c0);
           } else if (ac && lane == A) {
             dz = __dadd_rn((double)c1, (double)c3);

@@ -566,6 +566,13 @@ HBM_CASES = {
     # register landing (default): no L2 prefetch, deep prefetch; widest and narrowest rows
     "reg_pf0": (_hbm_cfg([dict(actions=128), dict(actions=33), dict(states=50, actions=3)], 40), {"THRL_HBM_PF": "0"}),
     "reg_pf9": (_hbm_cfg([dict(actions=128), dict(actions=33), dict(states=50, actions=3)], 40), {"THRL_HBM_PF": "9"}),
+    # dynamic schedule (a run played as several tasks that any warp of its CTA may take): one run per CTA, so consecutive tasks
+    # of a run land on different warps and every hand-over goes through the done-counter; then 2-3 runs per CTA, ragged batches,
+    # per-run hyper-parameters, one task per epoch
+    "dyn_handover": (_hbm_cfg([dict(), dict(actions=33), dict(states=50)], 40), {"THRL_HBM_CHUNK": "3"}),
+    "dyn_many": (_hbm_cfg([dict(capacity=37, min_memory=20), dict(min_memory=500, capacity=100), dict(capacity=80, min_memory=80),
+                           dict(states=77, actions=5)], 90), {"THRL_HBM_CHUNK": "5", "THRL_HBM_WARPS": "2"}),
+    "dyn_noisy": (_hbm_cfg([dict(states=999, actions=61)], 33, noise=0.3), {"THRL_HBM_CHUNK": "2"}),
 }
 
 
@@ -580,8 +587,9 @@ def test_hbm_kernel_edge_shapes_match_oracle(case, kernel_choice, monkeypatch):
     cfg, env = HBM_CASES[case]
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    R = 6 if case.endswith("long_wide") else 20
-    _philox_case(cfg, R, 5, np.float32, seed=61, run_id0=9, hp=(case in ("ragged", "bulk_ragged", "live_max")), chunks=[2, 3] if case in ("converged", "ragged", "bulk_ragged") else None)
+    R = 6 if case.endswith("long_wide") else (330 if case == "dyn_many" else 20)
+    _philox_case(cfg, R, 5, np.float32, seed=61, run_id0=9, hp=(case in ("ragged", "bulk_ragged", "live_max", "dyn_many")),
+                 chunks=[2, 3] if case in ("converged", "ragged", "bulk_ragged", "dyn_handover") else None)
     assert _lib.last_kernel() == "hbm", _lib.last_kernel()
     _philox_case(cfg, R, 3, np.float64, seed=62)
     assert _lib.last_kernel() == "hbm", _lib.last_kernel()

@@ -383,6 +383,43 @@ bool plan_hbm(thrl::HbmParams* p, size_t elem, const DeviceInfo& dev, int* warps
   if (const char* f = getenv("THRL_HBM_WARPS"))
     if (atoi(f) >= 1 && atoi(f) < w) w = atoi(f);
   *warps = w;
+  // Dynamic schedule (thrl_scan_hbm.cuh): only where the static rounds leave slots idle -- more than one round, not a whole
+  // number of them -- and the call is long enough for ~100-epoch tasks (a task starts with a cold greedy cache).  Register landing
+  // only.  THRL_HBM_CHUNK = number of tasks per run (0 / 1: static schedule), for tests and comparisons.
+  p->nchunk = 1;
+  p->echunk = 0;
+  p->off_q = p->cta_bytes;
+  {
+    const long long slots = (long long)dev.sms * w;
+    int nchunk = 1;
+    if (!p->staged && p->n_runs > slots && p->n_runs % slots != 0 && p->E >= 100) {
+      // Cost model fitted on the C4 shape (one round of w resident runs per SM takes ~ 0.58 + 0.035 w of a 12-run round; a task
+      // pays ~2 % of a run's chunk for its cold greedy cache): static = rounds x round time at the balanced residency; dynamic
+      // with c tasks per run = ceil(runs per CTA x c / w) / c rounds at full residency.  Dynamic only when it wins by 5 %.
+      const long long rounds = (p->n_runs + slots - 1) / slots;
+      const double wbal = (double)((p->n_runs + rounds - 1) / rounds) / dev.sms;
+      const double full = 0.58 + 0.035 * w;
+      const double stat = (double)rounds * (0.58 + 0.035 * wbal) / full;
+      const long long nloc = (p->n_runs + dev.sms - 1) / dev.sms;
+      double best = stat * 0.95;
+      for (int c = 2; c <= 8 && p->E / c >= 50; ++c) {
+        const double dyn = (double)((nloc * c + w - 1) / w) / c * (1.0 + 0.02 * c);
+        if (dyn < best) { best = dyn; nchunk = c; }
+      }
+    }
+    if (const char* f = getenv("THRL_HBM_CHUNK")) nchunk = p->staged ? 1 : atoi(f);
+    if (nchunk > p->E) nchunk = p->E;
+    if (nchunk > 1) {
+      const int grid = p->n_runs < dev.sms ? (int)p->n_runs : dev.sms;
+      const long long nloc = (p->n_runs + grid - 1) / grid;
+      const int qbytes = align_up(16 + 4 * (int)nloc, 128);
+      if (nloc * nchunk < (1LL << 30) && p->cta_bytes + qbytes + (long long)w * p->warp_bytes <= dev.smem_optin) {
+        p->nchunk = nchunk;
+        p->echunk = (p->E + nchunk - 1) / nchunk;
+        p->cta_bytes += qbytes;
+      }
+    }
+  }
   return true;
 }
 
@@ -394,13 +431,20 @@ int launch_hbm(thrl::HbmParams& p, int warps, const DeviceInfo& dev, cudaStream_
     const long long slots = (long long)dev.sms * warps;
     const long long rounds = (p.n_runs + slots - 1) / slots;
     const long long per_round = (p.n_runs + rounds - 1) / rounds;
-    warps = (int)((per_round + dev.sms - 1) / dev.sms);
-    if (warps < 1) warps = 1;
-    grid = per_round < dev.sms ? (int)per_round : dev.sms;  // partial warps of a round are spread over all SMs (slot = warp * grid + cta)
-    p.per_round = per_round;
+    if (p.nchunk > 1) {  // dynamic schedule: every CTA at full residency, tasks from the CTA's queue
+      grid = p.n_runs < dev.sms ? (int)p.n_runs : dev.sms;
+      const long long nloc = (p.n_runs + grid - 1) / grid;
+      if (nloc * p.nchunk < warps) warps = (int)(nloc * p.nchunk);
+      p.per_round = (long long)grid * warps;
+    } else {
+      warps = (int)((per_round + dev.sms - 1) / dev.sms);
+      if (warps < 1) warps = 1;
+      grid = per_round < dev.sms ? (int)per_round : dev.sms;  // partial warps of a round are spread over all SMs (slot = warp * grid + cta)
+      p.per_round = per_round;
+    }
   }
   const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
-  auto kern = p.staged ? thrl::qtable_scan_hbm<QT, true> : thrl::qtable_scan_hbm<QT, false>;
+  auto kern = p.staged ? thrl::qtable_scan_hbm<QT, true> : (p.nchunk > 1 ? thrl::qtable_scan_hbm<QT, false, true> : thrl::qtable_scan_hbm<QT, false>);
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_last_kernel = "hbm";
   g_last_wave = capacity;
@@ -1169,6 +1213,7 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
     memset(&h, 0, sizeof(h));
     h.game = p.game;
     h.n_runs = p.n_runs;
+    h.E = p.E;
     h.noisy = p.noisy;
     int warps = 0;
     if (plan_hbm(&h, a->table_dtype == THRL_F64 ? 8 : 4, dev, &warps)) {

@@ -81,6 +81,9 @@ struct HbmParams {
   int Tp, Sp;      // padded strides of the [.][T] / [.][T+1] arrays (elements)
   // shared memory (bytes): [cta_bytes][warp 0][warp 1]...
   int cta_bytes, warp_bytes;
+  // Dynamic scheduling (nchunk > 1): a run is played as nchunk tasks of echunk epochs; the warps of a CTA take the tasks of the
+  // CTA's runs from a shared-memory queue (off_q: next task, then one done-counter per local run), see the kernel.
+  int nchunk, echunk, off_q;
   int off_bar, off_g, off_P, off_hp, off_miss, off_mask, off_srow, off_rs, off_next, off_dl, off_act, off_cur, off_canon, off_nextc,
       off_bm, off_stage;
   // regions that alias the staging ring: the rollout's draws (before the update), reward / max_steps (after the gather)
@@ -210,7 +213,8 @@ template <typename QT> struct HbmReg {
 };
 __device__ __forceinline__ void hbm_prefetch_l2(const void* ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 
-template <typename QT, bool kStaged>
+// kDyn: dynamic schedule (HbmParams.nchunk > 1), compiled separately so that the static schedule keeps its code
+template <typename QT, bool kStaged, bool kDyn = false>
 __global__ void __launch_bounds__(32 * kHbmMaxWarps, 1) qtable_scan_hbm(const __grid_constant__ HbmParams p) {
   using B = HbmBits<QT>;
   using U = typename B::U;
@@ -301,9 +305,52 @@ __global__ void __launch_bounds__(32 * kHbmMaxWarps, 1) qtable_scan_hbm(const __
   const double Td = (double)T;
   const bool tracing = p.trace_actions || p.trace_rewards || p.trace_prices;
 
-  // slot w * grid + b: a round that does not fill every warp leaves the idle warps spread over all SMs
+  // Static schedule (nchunk <= 1): slot w * grid + b plays runs slot, slot + per_round, ...: a round that does not fill every
+  // warp leaves the idle warps spread over all SMs.
+  // Dynamic schedule (nchunk > 1), for launches whose run count is not a whole number of rounds (4,096 runs = 2.3 rounds of
+  // 1,776 leave two thirds of the slots idle for a third of the launch): CTA b owns the runs b, b + grid, ...; every run is cut
+  // into nchunk tasks of echunk epochs, ordered chunk by chunk; a warp that is free takes the next task of its CTA from a
+  // shared-memory counter.  A run's state between two of its tasks lives where it always does (tables in HBM, epsilon and
+  // price in their arrays); only the greedy cache starts cold.  Task (run, c) waits until (run, c - 1) is done -- a counter per
+  // local run in shared memory; the producer is a resident warp of the same CTA that never waits on a later task, so the wait
+  // terminates (and traps instead of hanging should that invariant ever be broken).
   const long long slot_id = (long long)warp * gridDim.x + blockIdx.x;
-  for (long long r = slot_id; slot_id < p.per_round && r < p.n_runs; r += p.per_round) {
+  int* qnext = reinterpret_cast<int*>(smem + p.off_q);
+  volatile int* qdone = qnext + 4;
+  const int nloc = kDyn && blockIdx.x < p.n_runs ? (int)((p.n_runs - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  if (kDyn) {
+    if (threadIdx.x == 0) *qnext = 0;
+    for (int i = threadIdx.x; i < nloc; i += blockDim.x) qdone[i] = 0;
+    __syncthreads();
+  }
+  for (long long it = 0;; ++it) {
+    long long r;
+    int e_lo = 0, e_hi = E, iloc = 0, cidx = 0;
+    if (!kDyn) {
+      r = slot_id + it * p.per_round;
+      if (!(slot_id < p.per_round && r < p.n_runs)) break;
+    } else {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(qnext, 1);
+      t = __shfl_sync(kFull, t, 0);
+      if (t >= nloc * p.nchunk) break;
+      cidx = t / nloc;
+      iloc = t - cidx * nloc;
+      r = blockIdx.x + (long long)gridDim.x * iloc;
+      e_lo = cidx * p.echunk;
+      e_hi = e_lo + p.echunk < E ? e_lo + p.echunk : E;
+      if (cidx > 0) {
+        if (lane == 0) {
+          unsigned spins = 0;
+          while (qdone[iloc] < cidx) {
+            __nanosleep(256);
+            if (++spins > (1u << 26)) __trap();
+          }
+        }
+        __syncwarp();
+        __threadfence_block();
+      }
+    }
     QT* qg = reinterpret_cast<QT*>(p.q) + r * G.run_stride;
     uint32_t* cnt = p.counter ? p.counter + r * G.run_stride : nullptr;
     const uint32_t gid = (uint32_t)(p.run_id0 + r);
@@ -323,7 +370,7 @@ __global__ void __launch_bounds__(32 * kHbmMaxWarps, 1) qtable_scan_hbm(const __
     double price = p.price[r];
     __syncwarp();
 
-    for (int e = 0; e < E; ++e) {
+    for (int e = e_lo; e < e_hi; ++e) {
       const uint32_t eabs = (uint32_t)(p.epoch_begin + e);
       const long long step0 = (r * E + e) * (long long)T;
 
@@ -803,6 +850,11 @@ __global__ void __launch_bounds__(32 * kHbmMaxWarps, 1) qtable_scan_hbm(const __
     if (is_agent) p.eps[r * n + lane] = hpw[lane * 5 + 4];
     if (lane == 0) p.price[r] = price;
     __syncwarp();
+    if (kDyn) {  // the run's next task may start: its state is in memory
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) qdone[iloc] = cidx + 1;
+    }
   }
 }
 

@@ -379,7 +379,7 @@ bool plan_hbm(thrl::HbmParams* p, size_t elem, const DeviceInfo& dev, int* warps
     }
   }
   if (w < 1) return false;
-  if (w > thrl::kHbmMaxWarps) w = thrl::kHbmMaxWarps;
+  if (w > (p->staged ? thrl::kHbmMaxWarps : thrl::kHbmRegWarps)) w = p->staged ? thrl::kHbmMaxWarps : thrl::kHbmRegWarps;
   if (const char* f = getenv("THRL_HBM_WARPS"))
     if (atoi(f) >= 1 && atoi(f) < w) w = atoi(f);
   *warps = w;

@@ -38,6 +38,7 @@ constexpr int kHbmMaxT = 254;   // transition / state indices fit one byte next 
 constexpr int kHbmMaxNb = 8;    // staging ring depth (batches)
 constexpr int kHbmAgc = 17;     // ints per agent in the CTA-shared constant block (odd: lanes that read different agents' entries hit different banks)
 constexpr int kHbmMaxWarps = 14;  // resident runs per CTA: 448 threads leave 146 registers per thread
+constexpr int kHbmRegWarps = 12;  // register landing: 12 resident runs fit the 196 KB carve-out (plan_hbm); 384 threads leave 170 registers
 
 struct HbmParams {
   ThrlGame game;
@@ -215,7 +216,7 @@ __device__ __forceinline__ void hbm_prefetch_l2(const void* ptr) { asm volatile(
 
 // kDyn: dynamic schedule (HbmParams.nchunk > 1), compiled separately so that the static schedule keeps its code
 template <typename QT, bool kStaged, bool kDyn = false>
-__global__ void __launch_bounds__(32 * kHbmMaxWarps, 1) qtable_scan_hbm(const __grid_constant__ HbmParams p) {
+__global__ void __launch_bounds__(kStaged ? 32 * kHbmMaxWarps : 32 * kHbmRegWarps, 1) qtable_scan_hbm(const __grid_constant__ HbmParams p) {
   using B = HbmBits<QT>;
   using U = typename B::U;
   using R = HbmReg<QT>;

@@ -844,7 +844,7 @@ bool plan_pwl(thrl::PwlParams* p, bool noisy, size_t elem, int smem_optin, int* 
   p->ws_warp_bytes = (w + 255) / 256 * 256;
   const int fit = (smem_optin - p->cta_bytes) / p->warp_bytes;
   if (fit < 1) return false;
-  *warps = fit > 16 ? 16 : fit;
+  *warps = fit > thrl::kPwlMaxWarps ? thrl::kPwlMaxWarps : fit;
   if (const char* f = getenv("THRL_PWL_WARPS"))
     if (atoi(f) >= 1 && atoi(f) < *warps) *warps = atoi(f);
   return true;
@@ -968,8 +968,8 @@ bool plan_pwc(thrl::PwcParams* p, bool noisy, size_t elem, int smem_optin, int* 
   const int fit = (smem_optin - p->cta_bytes) / p->warp_bytes;
   if (fit < 1) return false;
   // 16 warps x 128 registers.  (24 warps under __launch_bounds__(768, 1) = 80 registers measured 8 % slower: 300 B of spills.)
-  int cap = 16;
-  if (const char* f = getenv("THRL_PWC_WARPS")) cap = atoi(f) < 1 ? 1 : (atoi(f) > 16 ? 16 : atoi(f));
+  int cap = thrl::kPwcMaxWarps;
+  if (const char* f = getenv("THRL_PWC_WARPS")) cap = atoi(f) < 1 ? 1 : (atoi(f) > thrl::kPwcMaxWarps ? thrl::kPwcMaxWarps : atoi(f));
   *warps = fit > cap ? cap : fit;
   return true;
 }

@@ -27,6 +27,10 @@
 namespace thrl {
 
 constexpr int kPwcMaxHidden = 256;        // thresholds are ranked with 8 units per lane
+#ifndef THRL_PWC_MAXWARPS
+#define THRL_PWC_MAXWARPS 16
+#endif
+constexpr int kPwcMaxWarps = THRL_PWC_MAXWARPS;  // resident runs per CTA (launch bound: 65,536 / (32 * warps) registers per thread)
 constexpr unsigned kPwcKeyMin = 0x007fffffu;   // ukey(-inf)
 constexpr unsigned kPwcKeyNone = 0xff800001u;  // above ukey(+inf): the unit never switches
 
@@ -598,7 +602,7 @@ __device__ inline void pwc_train(float* blk, const ThrlAgentSpec& spec, int cap,
 // demand noise.  Its episode loop keeps both agents' thresholds, tables and shapes in registers and evaluates the two policies
 // side by side; every other game takes the general loop.
 template <typename QT, bool kTwo>
-__global__ void __launch_bounds__(512, 1) mlp_scan_pwc(const __grid_constant__ PwcParams p) {
+__global__ void __launch_bounds__(32 * kPwcMaxWarps, 1) mlp_scan_pwc(const __grid_constant__ PwcParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ThrlGame& G = p.game;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;

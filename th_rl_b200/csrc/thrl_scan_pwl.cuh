@@ -24,6 +24,10 @@
 
 namespace thrl {
 
+#ifndef THRL_PWL_MAXWARPS
+#define THRL_PWL_MAXWARPS 16
+#endif
+constexpr int kPwlMaxWarps = THRL_PWL_MAXWARPS;  // resident runs per CTA (launch bound)
 constexpr int kPwlMaxJoint = 1024;   // joint actions (price table in the kernel parameters)
 constexpr int kPwlMaxLattice = 1024; // distinct float32 lattice prices (<= joint actions)
 constexpr int kPwlExtras = 4;        // off-lattice states one run may hold at a time (its initial price)
@@ -630,7 +634,7 @@ __device__ inline void pwl_train(float* blk, const ThrlAgentSpec& spec, int cap,
 // of the other kernels (stale snapshot, live next_max, visit counters, epsilon decay).
 // kQ: the game has QTable agents.  kCdfG: the CDF LUT lives in the workspace (PwlParams.cdf_global).
 template <typename QT, int kN, bool kQ, bool kCdfG>
-__global__ void __launch_bounds__(512, 1) mlp_scan_pwl(const __grid_constant__ PwlParams p) {
+__global__ void __launch_bounds__(32 * kPwlMaxWarps, 1) mlp_scan_pwl(const __grid_constant__ PwlParams p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ThrlGame& G = p.game;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpc = blockDim.x >> 5;

@@ -65,15 +65,16 @@ def _c5_cfg(epochs, noise_prob=0):
 
 # name -> workload.  `algo_bytes` = algorithmic bytes per agent-step: Q-table shapes 8*A + 16; c5: the
 # update's parameter / Adam read-modify-write (6 x 4 B x 6,166 parameters per 1,000-transition batch) + 32 B of transition ring.
-# `e2e_chunks`: launches the host entry point cuts a step into (c4: two launches of one full round each -- 4,096 runs are two
-# rounds of the persistent grid, smaller launches would leave SMs idle; c5 has only 7 resident waves per step).
+# `e2e_chunks`: launches the host entry point cuts a step into (c4: the step is bound by the 27 GB that cross PCIe each way, so
+# six launches that overlap their copies beat two launches of one full round each: 2.15e9 vs 1.73e9 end to end; c5 has only 7
+# resident waves per step).
 WORKLOADS = {
     "c2": dict(agents=2, runs_per_gpu=131072, epochs=1000, e2e_chunks=12, config=_qcfg(2, 100, 21, 0.2, 0.4, 1000), algo_bytes=184.0,
                bound="smem", hp=None,
                desc="2-agent QTable iterated Cournot/PD game (example_config hyper-parameters, 101x21 tables, max_steps=100), "
                     "%d runs/GPU x %d epochs per step (C2 shape; 8 GPUs = the 1,048,576 runs of C3)",
                kernel="thrl::qtable_scan_lut2<float, true> (persistent, one launch per step)"),
-    "c4": dict(agents=8, runs_per_gpu=4096, epochs=500, e2e_chunks=2, config=_qcfg(8, 1000, 101, 0.05, 0.15, 500), algo_bytes=824.0,
+    "c4": dict(agents=8, runs_per_gpu=4096, epochs=500, e2e_chunks=6, config=_qcfg(8, 1000, 101, 0.05, 0.15, 500), algo_bytes=824.0,
                bound="hbm", hp=_c4_hp,
                desc="hyper-parameter sweep (alpha x eps_step x gamma = 64 points x 64 seeds), 8 QTable agents, 1001x101 "
                     "tables left in HBM, max_steps=100, %d runs/GPU x %d epochs per step (C4 shape)",

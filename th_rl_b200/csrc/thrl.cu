@@ -869,17 +869,11 @@ cudaMemPool_t pwl_pool(int device, bool create) {
 }
 
 int launch_pwl(thrl::PwlParams& p, int warps, bool f64, const DeviceInfo& dev, cudaStream_t stream) {
-  int grid = dev.sms;
-  {
-    const long long slots = (long long)dev.sms * warps;
-    const long long rounds = (p.n_runs + slots - 1) / slots;
-    const long long per_round = (p.n_runs + rounds - 1) / rounds;
-    warps = (int)((per_round + dev.sms - 1) / dev.sms);
-    if (warps < 1) warps = 1;
-    grid = (int)((per_round + warps - 1) / warps);
-    if (grid > dev.sms) grid = dev.sms;
-  }
-  const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
+  // A call that needs several rounds of the persistent grid is launched round by round (same stream, runs [lo, hi) each):
+  // warps that start a round together stay in step through its episodes and updates, which a single launch of seven rounds
+  // loses after the first one (C5: 4.15e9 against 3.0-4.0e9 agent-steps/s; runs are independent, so the result is the same).
+  const long long slots = (long long)dev.sms * warps;
+  const long long total = p.n_runs;
   // stream-ordered scratch from the library's own pool
   int device = 0;
   CUDA_TRY(cudaGetDevice(&device));
@@ -887,7 +881,7 @@ int launch_pwl(thrl::PwlParams& p, int warps, bool f64, const DeviceInfo& dev, c
   cudaMemPool_t pool = pwl_pool(device, true);
   if (!pool) return fail(THRL_ERR_CUDA, "cudaMemPoolCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
   void* ws = nullptr;
-  CUDA_TRY(cudaMallocFromPoolAsync(&ws, (size_t)grid * warps * (size_t)p.ws_warp_bytes, pool, stream));
+  CUDA_TRY(cudaMallocFromPoolAsync(&ws, (size_t)dev.sms * warps * (size_t)p.ws_warp_bytes, pool, stream));
   p.ws = (unsigned char*)ws;
   const bool two = p.game.n_agents == 2, g = p.cdf_global != 0;
   void (*kern)(thrl::PwlParams);
@@ -901,16 +895,24 @@ int launch_pwl(thrl::PwlParams& p, int warps, bool f64, const DeviceInfo& dev, c
     kern = two ? (g ? thrl::mlp_scan_pwl<float, 2, true, true> : thrl::mlp_scan_pwl<float, 2, true, false>)
                : (g ? thrl::mlp_scan_pwl<float, 0, true, true> : thrl::mlp_scan_pwl<float, 0, true, false>);
   }
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e == cudaSuccess) {
-    g_last_kernel = "pwl";
-    g_last_wave = (long long)grid * warps;
-    kern<<<grid, warps * 32, smem, stream>>>(p);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)p.cta_bytes + (size_t)warps * p.warp_bytes));
+  g_last_kernel = "pwl";
+  g_last_wave = slots;
+  for (long long lo = 0; lo < total && e == cudaSuccess; lo += slots) {
+    const long long n = total - lo < slots ? total - lo : slots;
+    int w = (int)((n + dev.sms - 1) / dev.sms);
+    if (w < 1) w = 1;
+    int grid = (int)((n + w - 1) / w);
+    if (grid > dev.sms) grid = dev.sms;
+    p.run_lo = lo;
+    p.n_runs = lo + n;
+    kern<<<grid, w * 32, (size_t)p.cta_bytes + (size_t)w * p.warp_bytes, stream>>>(p);
     e = cudaGetLastError();
+    g_launches.fetch_add(1);
   }
+  p.n_runs = total;
   cudaFreeAsync(ws, stream);
   CUDA_TRY(e);
-  g_launches.fetch_add(1);
   return THRL_OK;
 }
 

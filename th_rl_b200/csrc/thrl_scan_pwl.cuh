@@ -35,6 +35,7 @@ constexpr int kPwlExtras = 4;        // off-lattice states one run may hold at a
 struct PwlParams {
   ThrlGame game;
   long long n_runs, run_id0;
+  long long run_lo;      // first run of this launch (a call of several rounds is launched round by round: runs [run_lo, n_runs))
   int epoch_begin, E, rng_mode;
   uint32_t k0, k1;
   double* price;
@@ -275,11 +276,23 @@ __device__ inline void pwl_build_lut(const float* blk, const ThrlAgentSpec& spec
   for (int c = 0; c < NC; ++c) {
     const float* row = c < A ? W + (size_t)c * H : wv;
     double p1 = 0.0, p0 = 0.0;
-    for (int j = lane; j < H; j += 32) {
-      if (ev[j] & 0x8000) {
-        const double cw = (double)row[j];
-        p1 = __dadd_rn(p1, __dmul_rn(cw, (double)w1[j]));
-        p0 = __dadd_rn(p0, __dmul_rn(cw, (double)b1[j]));
+    for (int j0 = lane; j0 < H; j0 += 128) {  // four units per lane and round: the (predicated) weight loads go out together
+      float cwf[4];
+      bool lv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 32 * u;
+        lv[u] = j < H && (ev[j] & 0x8000);
+        cwf[u] = lv[u] ? row[j] : 0.0f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (lv[u]) {
+          const int j = j0 + 32 * u;
+          const double cw = (double)cwf[u];
+          p1 = __dadd_rn(p1, __dmul_rn(cw, (double)w1[j]));
+          p0 = __dadd_rn(p0, __dmul_rn(cw, (double)b1[j]));
+        }
       }
     }
     p1 = warp_sum(p1);
@@ -723,7 +736,7 @@ __global__ void __launch_bounds__(32 * kPwlMaxWarps, 1) mlp_scan_pwl(const __gri
   constexpr int kGreedy = 0x7fffffff;  // draw of a QTable agent that acts greedily (not a uniform < 1: those are < 0x3f800000)
 
   const long long total_warps = (long long)gridDim.x * wpc;
-  for (long long r = (long long)blockIdx.x * wpc + warp; r < p.n_runs; r += total_warps) {
+  for (long long r = p.run_lo + (long long)blockIdx.x * wpc + warp; r < p.n_runs; r += total_warps) {
     float* slab = p.mlp + r * G.mlp_stride;
     QT* tabg = reinterpret_cast<QT*>(p.q) + r * G.run_stride;
     uint32_t* cnt = p.counter ? p.counter + r * G.run_stride : nullptr;

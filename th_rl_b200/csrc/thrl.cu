@@ -476,9 +476,28 @@ int h_upd_row(double price, double max_state, int states) {
 // Returns true and fills p (structure + layout) when the specialised kernel applies; *warps = runs resident per CTA.
 bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int* warps) {
   const ThrlGame& G = p->game;
-  if (G.n_agents != 2 || noisy || !G.regular) return false;
+  if (G.n_agents != 2 || !G.regular) return false;
   const int A0 = G.agent[0].actions, A1 = G.agent[1].actions, T = G.max_steps;
   if (A0 > 255 || A1 > 255 || A0 * A1 > thrl::kLut2MaxJoint || T > 32767) return false;
+  // demand noise: the redrawn intercept lies in [0.7 a, a] (environments.py:28-31), so with non-negative quantities the price
+  // stays in [0, a - a * (lo_0 + lo_1)]: every row up to that price's row is staged and a compact row is its table row
+  int rmax[2] = {0, 0};
+  if (noisy) {
+    if (!(G.a > 0.0) || !(G.b > 0.0) || T > 200) return false;
+    double lo_sum = 0.0;
+    for (int a = 0; a < 2; ++a) {
+      const double lo = std::fmin(G.agent[a].action_lo, G.agent[a].action_hi);
+      if (!(lo >= 0.0)) return false;
+      lo_sum += lo;
+    }
+    double pmax = G.a - G.a * lo_sum;
+    if (!(pmax >= 0.0)) pmax = 0.0;
+    for (int a = 0; a < 2; ++a) {
+      const double r = pmax / G.agent[a].max_state * (double)G.agent[a].states + 2.5;
+      rmax[a] = r < (double)G.agent[a].states ? (int)r : G.agent[a].states;
+    }
+  }
+  p->noisy = noisy ? 1 : 0;
   const int J = A0 * A1;
   const double ab = G.a / G.b;
   std::map<std::array<int, 4>, int> ids;
@@ -508,6 +527,13 @@ bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int
   if (NS > thrl::kLut2MaxStates) return false;
   std::set<int> rows[2];
   for (auto& t : tuples) { rows[0].insert(t[0]); rows[0].insert(t[1]); rows[1].insert(t[2]); rows[1].insert(t[3]); }
+  if (noisy) {
+    if (NS + 1 + T > 255) return false;  // state ids of an episode (lattice, initial, one per noise step) fit a byte
+    for (int a = 0; a < 2; ++a) {
+      if (!rows[a].empty() && *rows[a].rbegin() > rmax[a]) return false;  // cannot happen: the lattice lies inside the bound
+      for (int r = 0; r <= rmax[a]; ++r) rows[a].insert(r);
+    }
+  }
   std::map<int, int> cidx[2];
   for (int a = 0; a < 2; ++a) {
     if ((int)rows[a].size() > thrl::kLut2MaxRows) return false;
@@ -539,8 +565,11 @@ bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int
   o = align_up((p->NR[0] + 2) * A0 * (int)elem, 16);
   p->off_tab1 = o;    o += align_up((p->NR[1] + 2) * A1 * (int)elem, 16);
   p->off_grow = o;    o += align_up(p->NR[0] + p->NR[1] + 4, 16);
-  p->off_rows = o;    o += align_up((NS + 1) * 4, 16);
-  p->off_gj = o;      o += align_up((NS + 1) * 4, 16);
+  const int nstates = NS + 1 + (noisy ? T : 0);
+  p->off_rows = o;    o += align_up(nstates * 4, 16);
+  p->off_gj = o;      o += align_up(nstates * 4, 16);
+  p->off_nt = o;      o += noisy ? align_up(T, 16) : 0;
+  p->off_nrec = o;    o += noisy ? align_up(T * 24, 16) : 0;
   p->off_seq = o;     o += align_up(T + 1, 16);
   p->off_rec = o;     o += align_up(2 * T, 16);
   p->off_scr = o;     o += thrl::kLut2Chunk * 8 + 16;            // phase D: next-row offsets of one chunk of transitions (+ read-ahead pad)
@@ -551,7 +580,8 @@ bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int
   p->warp_bytes = o;
   const int w = (smem_optin - p->cta_bytes) / p->warp_bytes;
   if (w < 2) return false;
-  const int wmax = elem == 8 ? thrl::Lut2Warps<double>::kMax : thrl::Lut2Warps<float>::kMax;
+  int wmax = elem == 8 ? thrl::Lut2Warps<double>::kMax : thrl::Lut2Warps<float>::kMax;
+  if (noisy && wmax > thrl::kLut2NoiseWarps) wmax = thrl::kLut2NoiseWarps;
   *warps = w > wmax ? wmax : w;
   return true;
 }
@@ -568,7 +598,8 @@ int launch_lut2(thrl::Lut2Params& p, int warps, const DeviceInfo& dev, cudaStrea
   }
   const size_t smem = (size_t)p.cta_bytes + (size_t)warps * p.warp_bytes;
   const bool small = p.game.agent[0].actions <= 32 && p.game.agent[1].actions <= 32;
-  auto kern = small ? thrl::qtable_scan_lut2<QT, true> : thrl::qtable_scan_lut2<QT, false>;
+  auto kern = p.noisy ? (small ? thrl::qtable_scan_lut2<QT, true, true> : thrl::qtable_scan_lut2<QT, false, true>)
+                      : (small ? thrl::qtable_scan_lut2<QT, true> : thrl::qtable_scan_lut2<QT, false>);
   CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   g_last_kernel = "lut2";
   kern<<<grid, warps * 32, smem, stream>>>(p);
@@ -1202,10 +1233,10 @@ int thrl_qtable_scan(const ThrlScanArgs* a, void* stream_) {
       l->n_runs = p.n_runs; l->run_id0 = p.run_id0; l->epoch_begin = p.epoch_begin; l->E = p.E; l->rng_mode = p.rng_mode;
       l->k0 = p.k0; l->k1 = p.k1;
       l->q = p.q; l->counter = p.counter; l->eps = p.eps; l->price = p.price; l->hp = p.hp;
-      l->replay_u = p.replay_u; l->replay_ra = p.replay_ra;
+      l->replay_u = p.replay_u; l->replay_ra = p.replay_ra; l->replay_new_a = p.replay_new_a;
       l->rewards_log = p.rewards_log; l->actions_log = p.actions_log; l->n_log_runs = p.n_log_runs; l->stats = p.stats;
       l->trace_actions = p.trace_actions; l->trace_rewards = p.trace_rewards; l->trace_prices = p.trace_prices;
-      if (force && strcmp(force, "lpc") == 0)
+      if (force && strcmp(force, "lpc") == 0 && !l->noisy)  // the lane-per-chain variant is noise-free only
         return a->table_dtype == THRL_F64 ? launch_lpc<double>(*l, dev, stream) : launch_lpc<float>(*l, dev, stream);
       return a->table_dtype == THRL_F64 ? launch_lut2<double>(*l, warps, dev, stream) : launch_lut2<float>(*l, warps, dev, stream);
     }

@@ -56,11 +56,16 @@ struct Lut2Params {
   int cta_bytes, warp_bytes;
   int off_next, off_rowlist, off_lutr, off_lutlog;  // CTA-shared
   int off_tab1, off_grow, off_rows, off_gj, off_seq, off_rec, off_scr, off_old;  // per warp (tables of agent 0 at 0)
+  // demand noise (kNoise): steps whose intercept was redrawn this episode, and what they produced
+  int noisy;                // 1: the noisy instantiation runs (state / row arrays hold max_steps more entries)
+  int off_nt, off_nrec;     // per warp: [T] step index of the k-th noise event; [T][3] f64 (reward 0, reward 1, new price; the intercept before the step)
+  const double* replay_new_a;
 };
 
 constexpr int kLut2MaxWarps = 24;  // float tables: 6 warps per scheduler at 80 registers
 template <typename QT> struct Lut2Warps { static constexpr int kMax = kLut2MaxWarps; };
 template <> struct Lut2Warps<double> { static constexpr int kMax = 16; };  // shared memory caps f64 tables at ~12 runs per SM: leave ptxas 128 registers
+constexpr int kLut2NoiseWarps = 16;  // noisy instantiation: every reachable row is staged (~16 KB per run), 13-14 runs fit: 128 registers
 constexpr int kLut2Chunk = 16;  // transitions expanded per pass of the update (16 lanes per agent)
 
 // Row max / first argmax with the column count known to be <= 32 at compile time (kSmallA): one LDS per lane.
@@ -80,8 +85,13 @@ __device__ __forceinline__ int lut2_row_argmax(const QT* row, int A, int lane, b
   return (int)__reduce_min_sync(kFull, (in && v == wm) ? (unsigned)lane : 0xffffffffu);
 }
 
-template <typename QT, bool kSmallA>
-__global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(const __grid_constant__ Lut2Params p) {
+// kNoise: demand noise (environments.py:28-31).  The intercept is redrawn in a few steps of an episode only, so the episode
+// is the noise-free rollout between those steps: a noise step computes its price, rewards and the four row encodes in f64 /
+// f32 as the reference does and opens an EXTRA state (ids NS+1.. within the episode) whose rows are the encodes themselves --
+// the host stages every row the price can reach (0 .. row of a - a * sum(min action)), so a compact row is its table row.
+// Snapshot, update and refresh see extra states like any other state; their rewards come from the event records.
+template <typename QT, bool kSmallA, bool kNoise = false>
+__global__ void __launch_bounds__(kNoise ? 32 * kLut2NoiseWarps : 32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(const __grid_constant__ Lut2Params p) {
   extern __shared__ __align__(16) unsigned char smem[];
   const ThrlGame& G = p.game;
   const int lane = threadIdx.x & 31, warps_per_cta = blockDim.x >> 5;
@@ -135,6 +145,8 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
   // phase D chunk: [kLut2Chunk] uint2 = next-row byte offsets of (agent 0, agent 1) for the transitions being applied
   unsigned char* chunk = slot + p.off_scr;
   QT* olds = reinterpret_cast<QT*>(slot + p.off_old);                // [T][2] stale old values of the batch (agents.py:67)
+  uint8_t* nT = slot + p.off_nt;                                     // kNoise: [T] step of the k-th noise event of the episode
+  double* nrec = reinterpret_cast<double*>(slot + p.off_nrec);       // kNoise: [T][3] reward 0, reward 1, price after the step
 
   const bool in0 = lane < A0, in1 = lane < A1;
   const bool hi_half = lane >= 16;
@@ -231,6 +243,7 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
 
     uint32_t sig4 = 4u * (uint32_t)NS;  // 4 * current state
     int last_k = -1;                    // k0 | k1<<8 of the most recent step (for the outgoing price)
+    double noise_price = -1.0;          // kNoise: price after the latest episode when its last step was a noise step (prices are >= 0)
 
     for (int e = 0; e < E; ++e) {
       const uint32_t eabs = (uint32_t)(p.epoch_begin + e);
@@ -256,6 +269,35 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
         }
         pre[t] = make_uint2((f0 < 0 ? 0xffu : 0u) | (f1 < 0 ? 0xff00u : 0u),
                             (uint32_t)(f0 < 0 ? 0 : f0) | ((uint32_t)(f1 < 0 ? 0 : f1) << 8));
+      }
+      int nK = 0;  // noise events of this episode
+      if (kNoise) {
+        for (int t0 = 0; t0 < T; t0 += 32) {  // environments.py:28-31, lane = step; the events in step order
+          const int t = t0 + lane;
+          bool ev = false;
+          double na = G.a;
+          if (t < T) {
+            if (rng_mode == THRL_RNG_PHILOX) {
+              uint32_t x[4];
+              philox4x32_10(gid, eabs, (uint32_t)t, kStreamEnv << 16, key0, key1, x);
+              if (u53(x[0], x[1]) < G.noise_prob) {
+                const double lo = __dmul_rn(G.a, 0.7);
+                na = __dadd_rn(lo, __dmul_rn(__dsub_rn(G.a, lo), u53(x[2], x[3])));
+                ev = true;
+              }
+            } else if (p.replay_new_a) {
+              na = p.replay_new_a[step0 + t];
+              ev = __double_as_longlong(na) != __double_as_longlong(G.a);
+            }
+          }
+          const unsigned m = __ballot_sync(kFull, ev);
+          if (ev) {
+            const int idx = nK + __popc(m & ((1u << lane) - 1u));
+            nT[idx] = (uint8_t)t;
+            nrec[3 * idx + 2] = na;  // the intercept, until the step replaces it by the price
+          }
+          nK += __popc(m);
+        }
       }
       __syncwarp();
 
@@ -286,6 +328,7 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
           asm volatile("ld.shared.u16 %0, [%1];" : "=r"(s16) : "r"(next_a + 2u * joint));
           sig4 = s16;
         };
+        if (!kNoise) {
         uint32_t pa = pre_a, ra = rec_a;
 #pragma unroll 2
         for (int n2 = T >> 1; n2 > 0; --n2, pa += 16u, ra += 4u) {  // two steps per 16-byte load of pre and per 4-byte store of rec
@@ -302,6 +345,62 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
           step(fx, fy);
           asm volatile("st.shared.u16 [%0], %1;" ::"r"(ra), "h"((uint16_t)kk) : "memory");
         }
+        } else {
+          // the noise-free rollout between the noise steps: single steps up to an even step index, pairs, a single tail step
+          auto single = [&](int t) {
+            uint32_t fx, fy;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(fx), "=r"(fy) : "r"(pre_a + 8u * (uint32_t)t));
+            step(fx, fy);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(rec_a + 2u * (uint32_t)t), "h"((uint16_t)kk) : "memory");
+          };
+          const double ab = __ddiv_rn(G.a, G.b), Td = (double)T;
+          int t = 0;
+          for (int k = 0; k <= nK; ++k) {
+            const int tn = k < nK ? (int)nT[k] : T;
+            if (t < tn && (t & 1)) { single(t); ++t; }
+            for (; t + 1 < tn; t += 2) {
+              uint32_t f0x, f0y, f1x, f1y;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(f0x), "=r"(f0y), "=r"(f1x), "=r"(f1y) : "r"(pre_a + 8u * (uint32_t)t));
+              step(f0x, f0y);
+              const uint32_t ka = kk;
+              step(f1x, f1y);
+              asm volatile("st.shared.u32 [%0], %1;" ::"r"(rec_a + 2u * (uint32_t)t), "r"(__byte_perm(ka, kk, 0x5410)) : "memory");
+            }
+            if (t < tn) { single(t); ++t; }
+            if (tn < T) {  // the noise step (environments.py:25-36 with the redrawn intercept)
+              uint32_t fx, fy, gj;
+              asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(fx), "=r"(fy) : "r"(pre_a + 8u * (uint32_t)tn));
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(gj) : "r"(gj_a + sig4));
+              kk = (gj & fx) | fy;
+              const int k0 = (int)(kk & 0xff), k1 = (int)(kk >> 8);
+              const uint32_t joint = __dp4a(kk, dp_b, 0u);
+              const double aq0 = __dmul_rn(ab, scale_action(k0, A0, G.agent[0].action_lo, G.agent[0].action_hi));
+              const double aq1 = __dmul_rn(ab, scale_action(k1, A1, G.agent[1].action_lo, G.agent[1].action_hi));
+              const double na = nrec[3 * k + 2];
+              const double pn = __dsub_rn(na, __dmul_rn(G.b, __dadd_rn(__dadd_rn(0.0, aq0), aq1)));
+              const double np = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
+              const double r0 = __dmul_rn(np, aq0), r1 = __dmul_rn(np, aq1);
+              if (lane < 2) lg = __ddiv_rn(lane == 0 ? r0 : r1, Td);                      // trainer.py:65
+              else if (lane < 4) lg = lutLog[4 * joint + lane];                           // trainer.py:66
+              acc = __dadd_rn(acc, lg);
+              const int ta0 = act_row(np, (float)G.agent[0].max_state, (float)G.agent[0].states);
+              const int tu0 = upd_row(np, G.agent[0].max_state, (double)G.agent[0].states);
+              const int ta1 = act_row(np, (float)G.agent[1].max_state, (float)G.agent[1].states);
+              const int tu1 = upd_row(np, G.agent[1].max_state, (double)G.agent[1].states);
+              const int sid = NS + 1 + k;
+              __syncwarp();
+              if (lane == 0) {
+                nrec[3 * k] = r0; nrec[3 * k + 1] = r1; nrec[3 * k + 2] = np;
+                rowsW[sid] = (uint32_t)ta0 | ((uint32_t)tu0 << 8) | ((uint32_t)ta1 << 16) | ((uint32_t)tu1 << 24);
+                GJ[sid] = (uint32_t)grow[ta0] | ((uint32_t)grow[NR0 + 2 + ta1] << 8);
+                rec[tn] = (uint16_t)kk;
+              }
+              __syncwarp();
+              sig4 = 4u * (uint32_t)sid;
+              t = tn + 1;
+            }
+          }
+        }
         last_k = (int)kk;
       }
       __syncwarp();
@@ -312,6 +411,10 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
         seq[t] = (uint8_t)(s4 >> 2);
       }
       __syncwarp();
+      if (kNoise) {  // the state after a noise step is that step's extra state
+        for (int k = lane; k < nK; k += 32) seq[nT[k] + 1] = (uint8_t)(NS + 1 + k);
+        __syncwarp();
+      }
 
       // optional per-step traces (parity runs only), lane-parallel
       if (p.trace_actions || p.trace_rewards || p.trace_prices) {
@@ -319,8 +422,14 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
         for (int t = lane; t < T; t += 32) {
           const int k0 = rec[t] & 0xff, k1 = rec[t] >> 8, joint = k0 * A1 + k1;
           if (p.trace_actions) { p.trace_actions[(step0 + t) * 2] = k0; p.trace_actions[(step0 + t) * 2 + 1] = k1; }
-          if (p.trace_rewards) { p.trace_rewards[(step0 + t) * 2] = lutR[2 * joint]; p.trace_rewards[(step0 + t) * 2 + 1] = lutR[2 * joint + 1]; }
-          if (p.trace_prices) {
+          const int ks = kNoise && seq[t + 1] > NS ? (int)seq[t + 1] - NS - 1 : -1;  // noise step: its event record
+          if (p.trace_rewards) {
+            p.trace_rewards[(step0 + t) * 2] = ks >= 0 ? nrec[3 * ks] : lutR[2 * joint];
+            p.trace_rewards[(step0 + t) * 2 + 1] = ks >= 0 ? nrec[3 * ks + 1] : lutR[2 * joint + 1];
+          }
+          if (p.trace_prices && ks >= 0) {
+            p.trace_prices[step0 + t] = nrec[3 * ks + 2];
+          } else if (p.trace_prices) {
             const double aq0 = __dmul_rn(ab, scale_action(k0, A0, G.agent[0].action_lo, G.agent[0].action_hi));
             const double aq1 = __dmul_rn(ab, scale_action(k1, A1, G.agent[1].action_lo, G.agent[1].action_hi));
             const double pn = __dsub_rn(G.a, __dmul_rn(G.b, __dadd_rn(__dadd_rn(0.0, aq0), aq1)));
@@ -359,7 +468,9 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
         const int cu = ag ? (int)(rw >> 24) : (int)((rw >> 8) & 0xff), cn = ag ? (int)(rn >> 24) : (int)((rn >> 8) & 0xff);
         row_off = (uint32_t)(cn * Aa) * (uint32_t)sizeof(QT);
         cell_addr = (ag ? tab1_off : tab0_off) + (uint32_t)(cu * Aa + k) * (uint32_t)sizeof(QT);
-        v = make_double2(lutR[2 * joint + ag], __dmul_rn(oma, (double)olds[2 * jj + ag]));
+        double rew = lutR[2 * joint + ag];
+        if (kNoise && seq[j + 1] > NS) rew = nrec[3 * ((int)seq[j + 1] - NS - 1) + ag];  // a noise step's reward
+        v = make_double2(rew, __dmul_rn(oma, (double)olds[2 * jj + ag]));
       };
 
       // ---- D: the sequential pass (agents.py:68-76).  The two agents' chains are independent: both rows are loaded
@@ -451,6 +562,14 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
         refresh(tab0, A0, NR0, grow, dirty0a, dirty0b, dirty_all0);
         refresh(tab1, A1, NR1, grow + NR0 + 2, dirty1a, dirty1b, dirty_all1);
         __syncwarp();
+        if (kNoise && sig4 > 4u * (uint32_t)NS) {  // the episode ended on an extra state: it becomes the next episode's state NS
+          if (lane == 0) rowsW[NS] = rowsW[sig4 >> 2];
+          noise_price = nrec[3 * (int)((sig4 >> 2) - NS - 1) + 2];
+          sig4 = 4u * (uint32_t)NS;
+          __syncwarp();
+        } else if (kNoise) {
+          noise_price = -1.0;
+        }
         for (int s = lane; s <= NS; s += 32) {
           const uint32_t rw = rowsW[s];
           GJ[s] = (uint32_t)grow[rw & 0xff] | ((uint32_t)grow[NR0 + 2 + ((rw >> 16) & 0xff)] << 8);
@@ -487,7 +606,9 @@ __global__ void __launch_bounds__(32 * Lut2Warps<QT>::kMax, 1) qtable_scan_lut2(
     if (lane == 0) {
       p.eps[r * 2] = eps0;
       p.eps[r * 2 + 1] = eps1;
-      if (last_k >= 0) {  // environments.py:36 self.state = price of the last step
+      if (kNoise && noise_price >= 0.0) {
+        p.price[r] = noise_price;
+      } else if (last_k >= 0) {  // environments.py:36 self.state = price of the last step
         const double ab = __ddiv_rn(G.a, G.b);
         const double aq0 = __dmul_rn(ab, scale_action(last_k & 0xff, A0, G.agent[0].action_lo, G.agent[0].action_hi));
         const double aq1 = __dmul_rn(ab, scale_action(last_k >> 8, A1, G.agent[1].action_lo, G.agent[1].action_hi));

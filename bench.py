@@ -36,11 +36,11 @@ sys.path.insert(0, ROOT)
 MAX_STEPS = 100
 
 
-def _qcfg(n, states, actions, lo, hi, epochs):
+def _qcfg(n, states, actions, lo, hi, epochs, noise_prob=0):
     return {
         "agents": [dict(name="QTable", gamma=0.95, actions=actions, states=states, alpha=0.1, eps_end=0.001, epsilon=0.5,
                         eps_step=0.9995, action_range=[lo, hi]) for _ in range(n)],
-        "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=n, max_steps=MAX_STEPS),
+        "environment": dict(name="NoisyPriceState", noise_prob=noise_prob, a=10, b=1, nplayers=n, max_steps=MAX_STEPS),
         "training": dict(print_freq=500, epochs=epochs),
     }
 
@@ -85,6 +85,12 @@ WORKLOADS = {
                     "%d runs/GPU x %d epochs per step (C5 shape)",
                kernel="thrl::mlp_scan_pwl (persistent, one launch per step; policy LUT per lattice state + sorted-breakpoint "
                       "gradient sweep, f64 accumulation; no dense contraction is left)"),
+    # C2 with the environment's own default demand noise (environments.py:7, noise_prob = 0.05): the noisy instantiation of the
+    # headline kernel (every reachable row staged, 13-14 resident runs per SM instead of 23)
+    "c2n": dict(agents=2, runs_per_gpu=131072, epochs=500, e2e_chunks=12, config=_qcfg(2, 100, 21, 0.2, 0.4, 500, noise_prob=0.05),
+                algo_bytes=184.0, bound="smem", hp=None,
+                desc="the C2 game with the environment's default demand noise (noise_prob=0.05), %d runs/GPU x %d epochs per step",
+                kernel="thrl::qtable_scan_lut2<float, true, true> (noisy instantiation of the headline kernel)"),
     # the same sweep sized to the persistent grid: 3 full rounds of 12 resident runs x 148 SMs (thrl_last_wave_runs reports the
     # round size so that a caller can do this).  4,096 runs are 2.3 rounds, i.e. three balanced rounds of 9-10 runs per SM.
     "c4w": dict(agents=8, runs_per_gpu=5328, epochs=500, e2e_chunks=0, config=_qcfg(8, 1000, 101, 0.05, 0.15, 500), algo_bytes=824.0,
@@ -101,7 +107,7 @@ WORKLOADS = {
                 kernel="thrl::mlp_scan_pwc (persistent, one launch per step; exact per-unit float32 thresholds, per-interval (S1,S0) "
                        "head tables, updates by one sweep over the transitions in interval order; no dense contraction is left)"),
 }
-EXTRAS = ("c2", "c4", "c4w", "c5", "c5n")
+EXTRAS = ("c2", "c2n", "c4", "c4w", "c5", "c5n")
 # warp instructions per agent-step from the committed ncu captures (profiles/)
 NCU_INSTR = {"c2": 30.4, "c5": 110.5, "c5n": 354.9}
 
@@ -348,6 +354,12 @@ def measure(name, wl, R, E, steps, warmup, e2e_chunks, ctx):
             "issue_slots": {"warp_inst_per_agent_step": NCU_INSTR["c2"], "achieved": per_gpu_rate * NCU_INSTR["c2"],
                             "peak": 4 * 148 * sm_max_mhz * 1e6, "unit": "warp-inst/s",
                             "frac": per_gpu_rate * NCU_INSTR["c2"] / (4 * 148 * sm_max_mhz * 1e6)}})
+    elif name == "c2n":
+        smem_peak_gbs = 128.0 * 148 * sm_max_mhz * 1e6 / 1e9
+        roof.update({"bound": "smem", "peak": smem_peak_gbs, "frac": achieved / smem_peak_gbs,
+                     "note": "as c2 (184 algorithmic B of shared-memory table traffic per agent-step against 128 B/clk/SM x 148 SMs x %.0f MHz, "
+                             "%s); the noisy instantiation stages every row the price can reach, so 13-14 runs are resident per SM instead "
+                             "of 23, and ~5 %% of the steps take the f64 noise-step path" % (sm_max_mhz, peak_src)})
     elif name in ("c4", "c4w"):
         roof["note"] = ("tables (3.2 MB per run) stay in HBM; 824 algorithmic B per agent-step = 8*A + 16 (BASELINE.md 5: act row + "
                         "bootstrap row + cell + counter); peak = measured copy bandwidth from MEASURED_PEAKS.json (%s).  The kernel "

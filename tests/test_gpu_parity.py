@@ -613,7 +613,7 @@ def _two_agent_cfg(T, a0, a1, env=None):
 
 
 @pytest.mark.parametrize("case", ["odd_T", "short_T", "partial_chunks", "unequal_batches", "one_never_fires", "unequal_actions",
-                                  "wide_actions"])
+                                  "wide_actions", "noise_all", "noise_most", "noise_rare"])
 def test_two_agent_edge_shapes_match_oracle(case, kernel_choice):
     """Shapes that exercise the corners of the specialised 2-agent kernel: odd / tiny episode lengths (rollout tail, a single
     partial update chunk), batches that are not a multiple of the 16-transition chunk, agents whose batches differ in
@@ -627,9 +627,15 @@ def test_two_agent_edge_shapes_match_oracle(case, kernel_choice):
         "one_never_fires": _two_agent_cfg(40, dict(min_memory=30, capacity=40), dict(min_memory=100, capacity=50)),
         "unequal_actions": _two_agent_cfg(50, dict(actions=5, min_memory=50, capacity=500), dict(actions=9, states=37, min_memory=50, capacity=500)),
         "wide_actions": _two_agent_cfg(30, dict(actions=40, states=60, min_memory=30), dict(actions=21, min_memory=30)),
+        # demand noise on the specialised kernel: every step a noise step (odd episode length: the rollout is single steps only),
+        # most steps (runs of consecutive noise steps, episodes that end on one), and the environment's default 5 %
+        "noise_all": _two_agent_cfg(33, dict(min_memory=33, capacity=500), dict(min_memory=20, capacity=500), env=dict(noise_prob=1.0)),
+        "noise_most": _two_agent_cfg(100, dict(min_memory=50, capacity=53), dict(min_memory=10, capacity=53), env=dict(noise_prob=0.6)),
+        "noise_rare": _two_agent_cfg(100, dict(), dict(actions=9, states=37), env=dict(noise_prob=0.05)),
     }[case]
     for dtype, seed in ((np.float32, 41), (np.float64, 42)):
-        _philox_case(cfg, 40, 4, dtype, seed=seed, run_id0=3, hp=(case == "partial_chunks"), chunks=[1, 3] if case == "odd_T" else None)
+        _philox_case(cfg, 40, 4, dtype, seed=seed, run_id0=3, hp=(case in ("partial_chunks", "noise_most")),
+                     chunks=[1, 3] if case in ("odd_T", "noise_all") else None)
     if kernel_choice == "auto":
         assert _lib.last_kernel() == "lut2", _lib.last_kernel()
 

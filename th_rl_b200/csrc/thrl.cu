@@ -567,9 +567,9 @@ bool plan_lut2(thrl::Lut2Params* p, bool noisy, size_t elem, int smem_optin, int
   p->off_grow = o;    o += align_up(p->NR[0] + p->NR[1] + 4, 16);
   const int nstates = NS + 1 + (noisy ? T : 0);
   p->off_rows = o;    o += align_up(nstates * 4, 16);
-  p->off_gj = o;      o += align_up(nstates * 4, 16);
+  p->off_gj = o;      o += align_up((NS + 2) * 4, 16);  // lattice states, the initial state, the latest noise step's state
   p->off_nt = o;      o += noisy ? align_up(T, 16) : 0;
-  p->off_nrec = o;    o += noisy ? align_up(T * 24, 16) : 0;
+  p->off_nrec = o;    o += noisy ? align_up(T * 8, 16) : 0;
   p->off_seq = o;     o += align_up(T + 1, 16);
   p->off_rec = o;     o += align_up(2 * T, 16);
   p->off_scr = o;     o += thrl::kLut2Chunk * 8 + 16;            // phase D: next-row offsets of one chunk of transitions (+ read-ahead pad)

@@ -58,7 +58,7 @@ struct Lut2Params {
   int off_tab1, off_grow, off_rows, off_gj, off_seq, off_rec, off_scr, off_old;  // per warp (tables of agent 0 at 0)
   // demand noise (kNoise): steps whose intercept was redrawn this episode, and what they produced
   int noisy;                // 1: the noisy instantiation runs (state / row arrays hold max_steps more entries)
-  int off_nt, off_nrec;     // per warp: [T] step index of the k-th noise event; [T][3] f64 (reward 0, reward 1, new price; the intercept before the step)
+  int off_nt, off_nrec;     // per warp: [T] step index of the k-th noise event; [T] f64 price after that step (the redrawn intercept before it)
   const double* replay_new_a;
 };
 
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(kNoise ? 32 * kLut2NoiseWarps : 32 * Lut2Warps
   unsigned char* chunk = slot + p.off_scr;
   QT* olds = reinterpret_cast<QT*>(slot + p.off_old);                // [T][2] stale old values of the batch (agents.py:67)
   uint8_t* nT = slot + p.off_nt;                                     // kNoise: [T] step of the k-th noise event of the episode
-  double* nrec = reinterpret_cast<double*>(slot + p.off_nrec);       // kNoise: [T][3] reward 0, reward 1, price after the step
+  double* nrec = reinterpret_cast<double*>(slot + p.off_nrec);       // kNoise: [T] price after the k-th noise step (rewards = price x quantity)
 
   const bool in0 = lane < A0, in1 = lane < A1;
   const bool hi_half = lane >= 16;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kNoise ? 32 * kLut2NoiseWarps : 32 * Lut2Warps
           if (ev) {
             const int idx = nK + __popc(m & ((1u << lane) - 1u));
             nT[idx] = (uint8_t)t;
-            nrec[3 * idx + 2] = na;  // the intercept, until the step replaces it by the price
+            nrec[idx] = na;  // the intercept, until the step replaces it by the price
           }
           nK += __popc(m);
         }
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kNoise ? 32 * kLut2NoiseWarps : 32 * Lut2Warps
               const uint32_t joint = __dp4a(kk, dp_b, 0u);
               const double aq0 = __dmul_rn(ab, scale_action(k0, A0, G.agent[0].action_lo, G.agent[0].action_hi));
               const double aq1 = __dmul_rn(ab, scale_action(k1, A1, G.agent[1].action_lo, G.agent[1].action_hi));
-              const double na = nrec[3 * k + 2];
+              const double na = nrec[k];
               const double pn = __dsub_rn(na, __dmul_rn(G.b, __dadd_rn(__dadd_rn(0.0, aq0), aq1)));
               const double np = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
               const double r0 = __dmul_rn(np, aq0), r1 = __dmul_rn(np, aq1);
@@ -387,16 +387,15 @@ __global__ void __launch_bounds__(kNoise ? 32 * kLut2NoiseWarps : 32 * Lut2Warps
               const int tu0 = upd_row(np, G.agent[0].max_state, (double)G.agent[0].states);
               const int ta1 = act_row(np, (float)G.agent[1].max_state, (float)G.agent[1].states);
               const int tu1 = upd_row(np, G.agent[1].max_state, (double)G.agent[1].states);
-              const int sid = NS + 1 + k;
               __syncwarp();
               if (lane == 0) {
-                nrec[3 * k] = r0; nrec[3 * k + 1] = r1; nrec[3 * k + 2] = np;
-                rowsW[sid] = (uint32_t)ta0 | ((uint32_t)tu0 << 8) | ((uint32_t)ta1 << 16) | ((uint32_t)tu1 << 24);
-                GJ[sid] = (uint32_t)grow[ta0] | ((uint32_t)grow[NR0 + 2 + ta1] << 8);
+                nrec[k] = np;
+                rowsW[NS + 1 + k] = (uint32_t)ta0 | ((uint32_t)tu0 << 8) | ((uint32_t)ta1 << 16) | ((uint32_t)tu1 << 24);
+                GJ[NS + 1] = (uint32_t)grow[ta0] | ((uint32_t)grow[NR0 + 2 + ta1] << 8);  // the rollout only ever stands on the latest one
                 rec[tn] = (uint16_t)kk;
               }
               __syncwarp();
-              sig4 = 4u * (uint32_t)sid;
+              sig4 = 4u * (uint32_t)(NS + 1);
               t = tn + 1;
             }
           }
@@ -423,12 +422,15 @@ __global__ void __launch_bounds__(kNoise ? 32 * kLut2NoiseWarps : 32 * Lut2Warps
           const int k0 = rec[t] & 0xff, k1 = rec[t] >> 8, joint = k0 * A1 + k1;
           if (p.trace_actions) { p.trace_actions[(step0 + t) * 2] = k0; p.trace_actions[(step0 + t) * 2 + 1] = k1; }
           const int ks = kNoise && seq[t + 1] > NS ? (int)seq[t + 1] - NS - 1 : -1;  // noise step: its event record
-          if (p.trace_rewards) {
-            p.trace_rewards[(step0 + t) * 2] = ks >= 0 ? nrec[3 * ks] : lutR[2 * joint];
-            p.trace_rewards[(step0 + t) * 2 + 1] = ks >= 0 ? nrec[3 * ks + 1] : lutR[2 * joint + 1];
+          if (p.trace_rewards && ks >= 0) {  // environments.py:34 with the noise step's price
+            p.trace_rewards[(step0 + t) * 2] = __dmul_rn(nrec[ks], __dmul_rn(ab, scale_action(k0, A0, G.agent[0].action_lo, G.agent[0].action_hi)));
+            p.trace_rewards[(step0 + t) * 2 + 1] = __dmul_rn(nrec[ks], __dmul_rn(ab, scale_action(k1, A1, G.agent[1].action_lo, G.agent[1].action_hi)));
+          } else if (p.trace_rewards) {
+            p.trace_rewards[(step0 + t) * 2] = lutR[2 * joint];
+            p.trace_rewards[(step0 + t) * 2 + 1] = lutR[2 * joint + 1];
           }
           if (p.trace_prices && ks >= 0) {
-            p.trace_prices[step0 + t] = nrec[3 * ks + 2];
+            p.trace_prices[step0 + t] = nrec[ks];
           } else if (p.trace_prices) {
             const double aq0 = __dmul_rn(ab, scale_action(k0, A0, G.agent[0].action_lo, G.agent[0].action_hi));
             const double aq1 = __dmul_rn(ab, scale_action(k1, A1, G.agent[1].action_lo, G.agent[1].action_hi));
@@ -469,7 +471,10 @@ __global__ void __launch_bounds__(kNoise ? 32 * kLut2NoiseWarps : 32 * Lut2Warps
         row_off = (uint32_t)(cn * Aa) * (uint32_t)sizeof(QT);
         cell_addr = (ag ? tab1_off : tab0_off) + (uint32_t)(cu * Aa + k) * (uint32_t)sizeof(QT);
         double rew = lutR[2 * joint + ag];
-        if (kNoise && seq[j + 1] > NS) rew = nrec[3 * ((int)seq[j + 1] - NS - 1) + ag];  // a noise step's reward
+        if (kNoise && seq[j + 1] > NS) {  // a noise step: reward = its price x the agent's quantity (environments.py:34)
+          const ThrlAgentSpec& sa = G.agent[ag];
+          rew = __dmul_rn(nrec[(int)seq[j + 1] - NS - 1], __dmul_rn(__ddiv_rn(G.a, G.b), scale_action(k, Aa, sa.action_lo, sa.action_hi)));
+        }
         v = make_double2(rew, __dmul_rn(oma, (double)olds[2 * jj + ag]));
       };
 
@@ -562,9 +567,9 @@ __global__ void __launch_bounds__(kNoise ? 32 * kLut2NoiseWarps : 32 * Lut2Warps
         refresh(tab0, A0, NR0, grow, dirty0a, dirty0b, dirty_all0);
         refresh(tab1, A1, NR1, grow + NR0 + 2, dirty1a, dirty1b, dirty_all1);
         __syncwarp();
-        if (kNoise && sig4 > 4u * (uint32_t)NS) {  // the episode ended on an extra state: it becomes the next episode's state NS
-          if (lane == 0) rowsW[NS] = rowsW[sig4 >> 2];
-          noise_price = nrec[3 * (int)((sig4 >> 2) - NS - 1) + 2];
+        if (kNoise && sig4 > 4u * (uint32_t)NS) {  // the episode ended on a noise step: its state becomes the next episode's state NS
+          if (lane == 0) rowsW[NS] = rowsW[NS + nK];
+          noise_price = nrec[nK - 1];
           sig4 = 4u * (uint32_t)NS;
           __syncwarp();
         } else if (kNoise) {

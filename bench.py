@@ -45,6 +45,14 @@ def _qcfg(n, states, actions, lo, hi, epochs, noise_prob=0):
     }
 
 
+def _example_cfg(epochs):
+    """th_rl/some_path/configs/example_config.json with `epochs` per step."""
+    q = dict(name="QTable", gamma=0.95, actions=21, states=100, alpha=0.1, eps_end=0.001, epsilon=0.5, eps_step=0.9995, action_range=[0.2, 0.4])
+    r = dict(name="Reinforce", gamma=0.995, actions=21, states=1, action_range=[0.2, 0.4])
+    return {"agents": [q, r], "environment": dict(name="NoisyPriceState", noise_prob=0, a=10, b=1, nplayers=2, max_steps=MAX_STEPS),
+            "training": dict(print_freq=500, epochs=epochs)}
+
+
 def _c4_hp(R, n):
     """BASELINE C4 sweep grid: alpha x eps_step x gamma = 64 points, repeated over the runs (64 seeds each at R = 4096)."""
     import numpy as np
@@ -85,6 +93,11 @@ WORKLOADS = {
                     "%d runs/GPU x %d epochs per step (C5 shape)",
                kernel="thrl::mlp_scan_pwl (persistent, one launch per step; policy LUT per lattice state + sorted-breakpoint "
                       "gradient sweep, f64 accumulation; no dense contraction is left)"),
+    # the configuration the reference ships (th_rl/some_path/configs/example_config.json: QTable + Reinforce, noise-free), batched:
+    # lattice kernel with the QTable agent's table staged in shared memory (last paragraph)
+    "ex": dict(agents=2, runs_per_gpu=32768, epochs=100, e2e_chunks=8, config=_example_cfg(100), algo_bytes=180.0, bound="hbm", hp=None,
+               desc="the shipped example_config.json pairing (QTable 101x21 + Reinforce 1->256->21, N=1000), %d runs/GPU x %d epochs per step",
+               kernel="thrl::mlp_scan_pwl<float, 2, true, *> (lattice kernel, QTable agent staged in shared memory)"),
     # C2 with the environment's own default demand noise (environments.py:7, noise_prob = 0.05): the noisy instantiation of the
     # headline kernel (every reachable row staged, 13-14 resident runs per SM instead of 23)
     "c2n": dict(agents=2, runs_per_gpu=131072, epochs=500, e2e_chunks=12, config=_qcfg(2, 100, 21, 0.2, 0.4, 500, noise_prob=0.05),
@@ -107,7 +120,7 @@ WORKLOADS = {
                 kernel="thrl::mlp_scan_pwc (persistent, one launch per step; exact per-unit float32 thresholds, per-interval (S1,S0) "
                        "head tables, updates by one sweep over the transitions in interval order; no dense contraction is left)"),
 }
-EXTRAS = ("c2", "c2n", "c4", "c4w", "c5", "c5n")
+EXTRAS = ("c2", "c2n", "c4", "c4w", "c5", "c5n", "ex")
 # warp instructions per agent-step from the committed ncu captures (profiles/)
 NCU_INSTR = {"c2": 30.4, "c5": 110.5, "c5n": 354.9}
 
@@ -387,6 +400,9 @@ def measure(name, wl, R, E, steps, warmup, e2e_chunks, ctx):
                         "utilisation is 0 by construction" % peak_src)
         roof["dense_formulation"] = {"flop_per_agent_step": 4.5e4, "equivalent_tflops": tf, "bf16_peak_tflops": tf_peak,
                                      "frac": tf / tf_peak}
+    if name == "ex":
+        roof["note"] = ("as c5: HBM algorithmic bytes of the MLP agent's update (148 B per agent-step of that agent) + transition ring; the "
+                        "QTable agent's table lives in shared memory for the call.  Bound by issue slots / latency like c5 (DESIGN.md 4.5)")
     if name in ("c5", "c5n"):
         roof["issue_slots"] = {"warp_inst_per_agent_step": NCU_INSTR[name], "achieved": per_gpu_rate * NCU_INSTR[name],
                                "peak": 4 * 148 * sm_max_mhz * 1e6, "unit": "warp-inst/s",

@@ -326,3 +326,17 @@ def test_hbm_update_model_equals_sequential_train_net():
     import runpy
     runpy.run_path(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "model_hbm_update.py"),
                    run_name="__main__")
+
+
+def test_bench_workloads_are_valid_games():
+    """Every workload bench.py measures is a game the library lays out (no GPU needed): catches a typo in a bench config before
+    the GPU box does."""
+    import bench
+    from th_rl_b200 import _lib
+    assert set(bench.EXTRAS) <= set(bench.WORKLOADS) and "c2" in bench.WORKLOADS
+    for name, wl in bench.WORKLOADS.items():
+        g = _lib.game_layout(wl["config"])
+        assert g.n_agents == wl["agents"] and g.max_steps == bench.MAX_STEPS, name
+        assert wl["runs_per_gpu"] > 0 and wl["epochs"] > 0 and wl["algo_bytes"] > 0, name
+        if wl["hp"] is not None:
+            assert wl["hp"](7, wl["agents"]).shape == (7, wl["agents"], 4), name

@@ -30,15 +30,12 @@ class NoisyPriceState:
         raise NotImplementedError("NoisyPriceState.step is fused into the device scan (thrl_qtable_scan / "
                                   "thrl_greedy_eval); th_rl_b200 has no host implementation of the hot path")
 
-    # environments.py:41-48
     def get_optimal(self):
-        anash = (self.a / self.b) * numpy.ones(self.nplayers,) / (self.nplayers + 1)
-        price = numpy.max([0, self.a - self.b * sum(anash)])
-        rnash = [price * a for a in anash]
-        acoll = (self.a / self.b) * 0.5 * numpy.ones(self.nplayers,) / self.nplayers
-        price = numpy.max([0, self.a - self.b * sum(acoll)])
-        rcoll = [price * a for a in acoll]
-        return sum(rnash), sum(rcoll)
+        """Total reward per step at the Cournot-Nash and at the cartel (joint monopoly) quantities (environments.py:41-48, used
+        by the plots as reference levels): with linear demand p = a - b Q every one of n symmetric players supplies
+        a / (b (n + 1)) at Nash and a / (2 b n) in the cartel, so the totals are n (a / (n + 1))^2 / b and a^2 / (4 b)."""
+        n = self.nplayers
+        return n * (self.a / (n + 1)) ** 2 / self.b, self.a ** 2 / (4 * self.b)
 
     def reset(self):
         self.episode = 0

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(kStaged ? 32 * kHbmMaxWarps : 32 * kHbmRegWarp
           unsigned spins = 0;
           while (qdone[iloc] < cidx) {
             __nanosleep(256);
-            if (++spins > (1u << 26)) __trap();
+            if (++spins > (1u << 31)) __trap();  // ~10 minutes: far beyond any predecessor task
           }
         }
         __syncwarp();

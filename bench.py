@@ -533,7 +533,14 @@ def run_ours(args):
             w2 = WORKLOADS[name]
             # the host round trip of the secondary workloads is measured on one GPU only: at N ranks their pinned host copies
             # (c4: 27 GB per rank) would have to coexist in one box's memory for a number that the N = 1 line already carries
-            r2 = measure(name, w2, w2["runs_per_gpu"], w2["epochs"], min(args.steps, 3), 3, w2["e2e_chunks"] if world == 1 else 0, ctx)
+            try:
+                r2 = measure(name, w2, w2["runs_per_gpu"], w2["epochs"], min(args.steps, 3), 3, w2["e2e_chunks"] if world == 1 else 0, ctx)
+            except Exception as exc:  # a secondary workload must not cost the headline line (one process: no collective to desynchronise)
+                if world > 1:
+                    raise
+                torch.cuda.empty_cache()
+                line["workloads"][name] = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+                continue
             r2["config"] = config_block(name, w2, w2["runs_per_gpu"], w2["epochs"], world, _lib.game_layout)
             r2["steps"], r2["warmup"], r2["unit"] = min(args.steps, 3), 3, "agent-steps/s"
             line["workloads"][name] = r2

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define THRL_ABI_VERSION 4
+#define THRL_ABI_VERSION 5
 #define THRL_MAX_AGENTS 16
 #define THRL_MAX_ACTIONS 255 /* greedy-action cache is one byte per table row, 0xFF = not cached */
 
@@ -206,6 +206,13 @@ int thrl_greedy_eval(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, 
  * the run slab of ThrlScanArgs.mlp (read only); q / mlp may be NULL when the game has no Q-tables / no MLP agents. */
 int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
                          int32_t iters, const double* price0, double* rewards, double* actions, void* stream);
+/* ABI 5: the same with demand noise (environments.py:28-31 inside utils.play_game's env.step).  new_a [R][iters][T] holds the demand
+ * intercept of every step as the environment would have drawn it -- a where no noise fires, the redrawn value in [0.7 a, a]
+ * otherwise; the Python mirror draws it from numpy's global generator in the reference's order, so a seeded evaluation equals
+ * utils.play_game's.  new_a == NULL plays the noise-free curve and is refused when game->noise_prob > 0 (as the two entry points
+ * above, which have no such argument, always do). */
+int thrl_greedy_eval_noise(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
+                           int32_t iters, const double* price0, const double* new_a, double* rewards, double* actions, void* stream);
 /* ABI 4: cross-run quantile statistics of the learning curve, th_rl/utils.py:132-145 (plot_learning_curve_conf: per run
  * pandas' ewm(halflife).mean() of the per-epoch mean rewards summed over the agents, then the median / quartiles over the runs).
  * rewards_log [n_runs][epochs][n_agents] is what thrl_qtable_scan wrote (device); ewm_num [n_runs] carries every run's EWM

@@ -204,8 +204,21 @@ def record_play_game(out, cfg, seed):
         return s
 
     environment.reset = reset
+    new_as, orig_step = [], environment.step
+
+    def step(actions):  # the demand intercept env.step draws (environments.py:28-31), re-derived from the generator state
+        st = numpy.random.get_state()
+        out_ = orig_step(actions)
+        after = numpy.random.get_state()
+        numpy.random.set_state(st)
+        un = numpy.random.uniform(0, 1)
+        new_as.append(numpy.random.uniform(environment.a * 0.7, environment.a) if un < environment.noise_prob else float(environment.a))
+        numpy.random.set_state(after)
+        return out_
+
+    environment.step = step
     acts, rwds = rutils.play_game(agents, environment, iters=EVAL_ITERS)
-    return numpy.array(p0s), numpy.asarray(acts, numpy.float64), numpy.asarray(rwds, numpy.float64)
+    return numpy.array(p0s), numpy.asarray(acts, numpy.float64), numpy.asarray(rwds, numpy.float64), numpy.array(new_as)
 
 
 
@@ -353,7 +366,7 @@ def record_case(cfg, seed):
             # play_game: noise-free games without CAC agents.  (CAC.get_action builds Normal(mu, 0), agents.py:385-389, which
             # torch's argument validation rejects -- the reference itself raises ValueError there, with the pinned torch 1.10 too.)
             evalrec = None
-            if cfg["environment"].get("noise_prob", 0.05) == 0 and all(a["name"] != "CAC" for a in cfg["agents"]):
+            if all(a["name"] != "CAC" for a in cfg["agents"]):  # with demand noise the intercepts of the steps are recorded too
                 evalrec = record_play_game(out, cfg, seed)
     finally:
         ragents.random, rtrainer.QTable, rtrainer.NoisyPriceState, rtrainer.Reinforce, rtrainer.ActorCritic, rtrainer.CAC = saved
@@ -380,7 +393,9 @@ def record_case(cfg, seed):
     )
     assert len(rec["p0"]) == 1
     if evalrec is not None:  # utils.play_game on the trained agents: [iters] initial prices, [iters*T, n] scaled actions / rewards
-        g["eval_p0"], g["eval_actions"], g["eval_rewards"] = evalrec
+        g["eval_p0"], g["eval_actions"], g["eval_rewards"] = evalrec[:3]
+        if cfg["environment"].get("noise_prob", 0.05) > 0:
+            g["eval_new_a"] = evalrec[3].reshape(EVAL_ITERS, T)  # demand intercept of every step of every episode
     qi = mi = 0
     for i in range(n):
         if kinds[i] == "QTable":

@@ -48,6 +48,9 @@ def lib():
         _lib.thrl_oracle_greedy_eval_mlp.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                                      C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.thrl_oracle_greedy_eval_mlp.restype = C.c_int
+        _lib.thrl_oracle_greedy_eval_noise.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.thrl_oracle_greedy_eval_noise.restype = C.c_int
         _lib.thrl_oracle_online_cores.restype = C.c_int
         _lib.thrl_oracle_py_sum.restype = C.c_double
         _lib.thrl_oracle_py_sum.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_int]
@@ -186,17 +189,18 @@ def init(game, n_runs, *, seed=0, run_id0=0, dtype=np.float32, hp=None, eps0=Non
     return q, counter, eps, price
 
 
-def greedy_eval(game, q, price0, mlp=None):
+def greedy_eval(game, q, price0, mlp=None, new_a=None):
     q = np.ascontiguousarray(q)
     R = q.shape[0]
     mlp = None if mlp is None else np.ascontiguousarray(mlp, np.float32)
     price0 = np.ascontiguousarray(price0, np.float64).reshape(R, -1)
     iters = price0.shape[1]
     n, T = game.n_agents, game.max_steps
+    new_a = None if new_a is None else np.ascontiguousarray(new_a, np.float64).reshape(R, iters, T)
     rewards = np.zeros((R, iters * T, n))
     actions = np.zeros((R, iters * T, n))
-    rc = lib().thrl_oracle_greedy_eval_mlp(C.byref(game), R, abi.THRL_F64 if q.dtype == np.float64 else abi.THRL_F32,
-                                           _ptr(q), _ptr(mlp), iters, _ptr(price0), _ptr(rewards), _ptr(actions))
+    rc = lib().thrl_oracle_greedy_eval_noise(C.byref(game), R, abi.THRL_F64 if q.dtype == np.float64 else abi.THRL_F32,
+                                             _ptr(q), _ptr(mlp), iters, _ptr(price0), _ptr(new_a), _ptr(rewards), _ptr(actions))
     if rc != 0:
         raise IndexError("oracle greedy_eval rc=%d" % rc)
     return actions, rewards

@@ -981,8 +981,15 @@ int thrl_oracle_game_init(const ThrlGame* G, int64_t n_runs, int64_t run_id0, ui
  * Reinforce / ActorCritic agents.py:165-168 / :275-278 (argmax of pi(float32 state)); CAC agents.py:380-384
  * (Normal(mu, 0).sample() == mu, so the action is sigmoid(4 tanh(fc_mu(h)))).  No exploration, no update.
  * price0[r][it] replaces environment.reset()'s draw.  rewards/actions: [R][iters*T][n]. */
+int thrl_oracle_greedy_eval_noise(const ThrlGame* G, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
+                                  int32_t iters, const double* price0, const double* new_a, double* rewards, double* actions);
 int thrl_oracle_greedy_eval_mlp(const ThrlGame* G, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
                                 int32_t iters, const double* price0, double* rewards, double* actions) {
+  return thrl_oracle_greedy_eval_noise(G, n_runs, table_dtype, q, mlp, iters, price0, NULL, rewards, actions);
+}
+/* new_a [R][iters][T]: the demand intercept of every step (environments.py:28-31: a, or the redrawn value); NULL = a throughout */
+int thrl_oracle_greedy_eval_noise(const ThrlGame* G, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
+                                  int32_t iters, const double* price0, const double* new_a, double* rewards, double* actions) {
   const int n = G->n_agents, T = G->max_steps;
   const size_t esz = table_dtype == THRL_F64 ? 8 : 4;
   float hbuf[1024 + 512];
@@ -1021,7 +1028,8 @@ int thrl_oracle_greedy_eval_mlp(const ThrlGame* G, int64_t n_runs, int32_t table
           Aq[i] = ab * xs[i];
         }
         const double Q = py_sum_quantities(Aq, n, lead_exact_floats(G));
-        double pn = G->a - G->b * Q; /* deterministic demand: evaluation is defined for noise_prob == 0 */
+        const double na = new_a ? new_a[((size_t)r * iters + it) * T + t] : G->a;
+        double pn = na - G->b * Q;
         double next_price = pn > 0.0 ? pn : 0.0;
         size_t o = (((size_t)r * iters + it) * T + t) * n;
         for (int i = 0; i < n; ++i) { rewards[o + i] = next_price * Aq[i]; actions[o + i] = xs[i]; }

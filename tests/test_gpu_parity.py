@@ -414,19 +414,35 @@ def test_greedy_eval_matches_oracle(golden):
     game = oracle.layout(cfg)
     q0, c0, eps0, p0, *rest = oracle.init(game, 20, seed=3, dtype=np.float64, eps0=abi.eps0_from_config(cfg))
     mlp0 = rest[0] if rest else None
-    price0 = np.random.default_rng(0).uniform(0, game.a, size=(20, 3))
-    ref_a, ref_r = oracle.greedy_eval(game, q0, price0, mlp=mlp0)
+    rng = np.random.default_rng(0)
+    price0 = rng.uniform(0, game.a, size=(20, 3))
+    new_a = None
+    if game.noise_prob > 0:  # play_game draws demand noise (environments.py:28-31): the intercept of every step is an input
+        new_a = np.where(rng.uniform(size=(20, 3, game.max_steps)) < 0.3, rng.uniform(0.7 * game.a, game.a, size=(20, 3, game.max_steps)), game.a)
+    ref_a, ref_r = oracle.greedy_eval(game, q0, price0, mlp=mlp0, new_a=new_a)
     b = engine.RunBatch(cfg, 20, dtype=torch.float64)
     b.load_state(q0, eps0, p0, mlp=mlp0)
-    if game.noise_prob > 0:  # play_game would draw demand noise (environments.py:28-31): refused, not played noise-free
-        from th_rl_b200._lib import ThrlError
-        with pytest.raises(ThrlError) as ei:
-            b.greedy_eval(price0)
-        assert ei.value.code == abi.THRL_ERR_UNSUPPORTED
-        return
-    a, r = b.greedy_eval(price0)
+    a, r = b.greedy_eval(price0, new_a=new_a)
     torch.cuda.synchronize()
     assert np.array_equal(a.cpu().numpy(), ref_a) and np.array_equal(r.cpu().numpy(), ref_r)
+    if game.noise_prob > 0:
+        # without the stream the Python mirror draws it from numpy's global generator in the environment's order ...
+        np.random.seed(5)
+        a1, r1 = b.greedy_eval(price0)
+        np.random.seed(5)
+        drawn = engine.draw_demand_intercepts(game.a, game.noise_prob, 20 * 3 * game.max_steps).reshape(20, 3, game.max_steps)
+        ref_a1, ref_r1 = oracle.greedy_eval(game, q0, price0, mlp=mlp0, new_a=drawn)
+        torch.cuda.synchronize()
+        assert np.array_equal(a1.cpu().numpy(), ref_a1) and np.array_equal(r1.cpu().numpy(), ref_r1)
+        # ... and the C entry points without the argument refuse a noisy game instead of playing it noise-free
+        import ctypes as C
+        from th_rl_b200._lib import lib
+        out = torch.zeros((20, 3 * game.max_steps, game.n_agents), dtype=torch.float64, device=b.device)
+        p0d = torch.as_tensor(price0).to(b.device)
+        rc = lib().thrl_greedy_eval_mlp(C.byref(b.game), 20, b.table_dtype, C.c_void_p(b.q.data_ptr()),
+                                        C.c_void_p(b.mlp.data_ptr()) if b.mlp is not None else None, 3, C.c_void_p(p0d.data_ptr()),
+                                        C.c_void_p(out.data_ptr()), C.c_void_p(out.data_ptr()), None)
+        assert rc == abi.THRL_ERR_UNSUPPORTED
 
 
 def test_greedy_eval_matches_play_game(golden):
@@ -435,12 +451,12 @@ def test_greedy_eval_matches_play_game(golden):
     from test_oracle_golden import final_state
     torch, oracle, engine = _mods()
     if "eval_p0" not in golden:
-        pytest.skip("no play_game record for this case (demand noise, or CAC whose get_action raises in the reference)")
+        pytest.skip("no play_game record for this case (CAC, whose get_action raises in the reference)")
     cfg = golden["config"]
     b = engine.RunBatch(cfg, 1, dtype=torch.float64)
     q, mlp = final_state(golden, b.game)
     b.load_state(q, [abi.eps0_from_config(cfg)], [golden["p0"]], mlp=mlp)
-    a, r = b.greedy_eval(golden["eval_p0"][None])
+    a, r = b.greedy_eval(golden["eval_p0"][None], new_a=golden["eval_new_a"][None] if "eval_new_a" in golden else None)
     torch.cuda.synchronize()
     assert np.array_equal(a[0].cpu().numpy(), golden["eval_actions"])
     assert np.array_equal(r[0].cpu().numpy(), golden["eval_rewards"])
@@ -736,7 +752,6 @@ def test_no_store_outside_buffers(case, kernel_choice):
     b.scan(E, stats=True, trace=True, n_log_runs=3)
     b.scan(1, run_range=(5, 30), stats=True, n_log_runs=2, advance=False)
     b.scan(1, stats=True)
-    if b.game.noise_prob == 0:
-        b.greedy_eval(np.full((R, 2), 3.0))
+    b.greedy_eval(np.full((R, 2), 3.0))  # noisy games: the intercepts are drawn by the Python mirror
     torch.cuda.synchronize()
     assert arena.damaged() == 0

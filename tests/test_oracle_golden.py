@@ -154,10 +154,12 @@ def test_greedy_eval_matches_play_game(golden):
     """oracle.greedy_eval against th_rl/utils.py:27-47 `play_game`, recorded from the unmodified reference on the agents the
     golden run saved (oracle/make_goldens.py record_play_game): scaled actions and rewards of every step, bit for bit."""
     if "eval_p0" not in golden:
-        pytest.skip("no play_game record: demand noise (the rollout would need the noise draws) or a CAC agent "
-                    "(the reference's CAC.get_action raises ValueError: Normal(mu, 0), agents.py:385-389)")
+        pytest.skip("no play_game record: a CAC agent (the reference's CAC.get_action raises ValueError: Normal(mu, 0), "
+                    "agents.py:385-389)")
     game = oracle.layout(golden["config"])
     q, mlp = final_state(golden, game)
-    acts, rews = oracle.greedy_eval(game, q, golden["eval_p0"][None], mlp=mlp)
+    new_a = golden["eval_new_a"][None] if "eval_new_a" in golden else None  # demand noise: the intercepts env.step drew
+    assert (new_a is not None) == (game.noise_prob > 0)
+    acts, rews = oracle.greedy_eval(game, q, golden["eval_p0"][None], mlp=mlp, new_a=new_a)
     assert np.array_equal(acts[0], golden["eval_actions"])
     assert np.array_equal(rews[0], golden["eval_rewards"])

@@ -50,6 +50,9 @@ def lib():
     L.thrl_greedy_eval_mlp.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.thrl_greedy_eval_mlp.restype = C.c_int
+    L.thrl_greedy_eval_noise.argtypes = [C.POINTER(abi.ThrlGame), C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.thrl_greedy_eval_noise.restype = C.c_int
     L.thrl_release_device_memory.restype = C.c_int
     L.thrl_curve_hist.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_void_p, C.c_double,
                                   C.c_double, C.c_int32, C.c_void_p, C.c_void_p]

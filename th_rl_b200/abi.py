@@ -6,7 +6,7 @@ include/thrl.h, which in turn cites the reference lines each field comes from
 """
 import ctypes as C
 
-THRL_ABI_VERSION = 4
+THRL_ABI_VERSION = 5
 THRL_MAX_AGENTS = 16
 THRL_MAX_ACTIONS = 255
 THRL_STATS_K = 4

@@ -1313,6 +1313,11 @@ int thrl_greedy_eval(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, 
 
 int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
                          int32_t iters, const double* price0, double* rewards, double* actions, void* stream) {
+  return thrl_greedy_eval_noise(game, n_runs, table_dtype, q, mlp, iters, price0, nullptr, rewards, actions, stream);
+}
+
+int thrl_greedy_eval_noise(const ThrlGame* game, int64_t n_runs, int32_t table_dtype, const void* q, const float* mlp,
+                           int32_t iters, const double* price0, const double* new_a, double* rewards, double* actions, void* stream) {
   if (!game || !price0 || !rewards || !actions) return fail(THRL_ERR_BAD_ARGS, "thrl_greedy_eval: NULL argument");
   if (table_dtype != THRL_F32 && table_dtype != THRL_F64) return fail(THRL_ERR_BAD_ARGS, "table_dtype=%d", table_dtype);
   ThrlGame G = *game;
@@ -1321,10 +1326,10 @@ int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dty
   if (G.run_stride > 0 && !q) return fail(THRL_ERR_BAD_ARGS, "q must not be NULL (the game has Q-tables)");
   if (G.mlp_stride > 0 && !mlp) return fail(THRL_ERR_BAD_ARGS, "the game has MLP agents but mlp is NULL");
   // utils.play_game steps the environment, which perturbs the demand intercept when noise_prob > 0 (environments.py:28-31);
-  // the rollout kernels evaluate the noise-free curve only, so a noisy game is refused instead of being played without noise
-  if (G.noise_prob > 0.0)
-    return fail(THRL_ERR_UNSUPPORTED, "thrl_greedy_eval: noise_prob=%g > 0 (only the noise-free demand curve is implemented; "
-                                      "evaluate with noise_prob = 0)", G.noise_prob);
+  // without the intercept stream a noisy game is refused instead of being played without noise
+  if (G.noise_prob > 0.0 && !new_a)
+    return fail(THRL_ERR_UNSUPPORTED, "thrl_greedy_eval: noise_prob=%g > 0 needs the demand intercepts of the steps "
+                                      "(thrl_greedy_eval_noise, new_a)", G.noise_prob);
   if (n_runs <= 0 || iters <= 0) return THRL_OK;
   DeviceInfo dev;
   rc = device_info(&dev);
@@ -1335,7 +1340,7 @@ int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dty
     thrl::EvalParams p;
     memset(&p, 0, sizeof(p));
     p.game = G;
-    p.n_runs = n_runs; p.iters = iters; p.q = q; p.price0 = price0; p.rewards = rewards; p.actions = actions;
+    p.n_runs = n_runs; p.iters = iters; p.q = q; p.price0 = price0; p.new_a = new_a; p.rewards = rewards; p.actions = actions;
     if (table_dtype == THRL_F64) thrl::greedy_eval<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
     else thrl::greedy_eval<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(p);
   } else {
@@ -1343,7 +1348,7 @@ int thrl_greedy_eval_mlp(const ThrlGame* game, int64_t n_runs, int32_t table_dty
     std::unique_ptr<thrl::EvalMixedParams> hold(p);
     memset(p, 0, sizeof(*p));
     p->game = G;
-    p->n_runs = n_runs; p->iters = iters; p->q = q; p->mlp = mlp; p->price0 = price0; p->rewards = rewards; p->actions = actions;
+    p->n_runs = n_runs; p->iters = iters; p->q = q; p->mlp = mlp; p->price0 = price0; p->new_a = new_a; p->rewards = rewards; p->actions = actions;
     int par = 0, hmax = 0, amax = 0;
     for (int i = 0; i < G.n_agents; ++i) {
       const ThrlAgentSpec& s = G.agent[i];

@@ -130,6 +130,7 @@ struct EvalParams {
   int iters;
   const void* q;
   const double* price0;
+  const double* new_a;  // [R][iters][T] demand intercept per step, or NULL: the noise-free curve
   double* rewards;
   double* actions;
 };
@@ -158,7 +159,8 @@ __global__ void __launch_bounds__(256) greedy_eval(const __grid_constant__ EvalP
           Q = __dadd_rn(Q, aq);
           if (lane == i) { my_x = x; my_aq = aq; }
         }
-        const double pn = __dsub_rn(G.a, __dmul_rn(G.b, Q));
+        const double na = p.new_a ? p.new_a[(r * p.iters + it) * T + t] : G.a;  // environments.py:28-31
+        const double pn = __dsub_rn(na, __dmul_rn(G.b, Q));
         const double next_price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
         if (lane < n) {
           const long long o = ((r * p.iters + it) * T + t) * n + lane;

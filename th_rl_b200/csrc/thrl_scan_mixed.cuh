@@ -812,6 +812,7 @@ struct EvalMixedParams {
   const void* q;
   const float* mlp;
   const double* price0;
+  const double* new_a;  // [R][iters][T] demand intercept per step, or NULL: the noise-free curve
   double* rewards;
   double* actions;
   int warp_bytes, off_par, off_h;
@@ -873,7 +874,8 @@ __global__ void __launch_bounds__(256) greedy_eval_mixed(const __grid_constant__
           if (lane == i) { my_x = x; my_aq = aq; }
         }
         const double Q = py_sum_quantities(n, lead_exact_floats(G), [&](int i) { return shfl_d(my_aq, i); });
-        const double pn = __dsub_rn(G.a, __dmul_rn(G.b, Q));
+        const double na = p.new_a ? p.new_a[(r * p.iters + it) * T + t] : G.a;  // environments.py:28-31
+        const double pn = __dsub_rn(na, __dmul_rn(G.b, Q));
         const double next_price = pn > 0.0 ? pn : (pn != pn ? pn : 0.0);
         if (lane < n) {
           const long long o = ((r * p.iters + it) * T + t) * n + lane;

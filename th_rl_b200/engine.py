@@ -179,17 +179,34 @@ class RunBatch:
             out.append(d)
         return out
 
-    def greedy_eval(self, price0):
-        """utils.play_game for every run: price0 [R, iters] -> (actions, rewards) [R, iters*T, n] f64 device tensors."""
+    def greedy_eval(self, price0, new_a=None):
+        """utils.play_game for every run: price0 [R, iters] -> (actions, rewards) [R, iters*T, n] f64 device tensors.
+        Games with demand noise (environments.py:28-31) need the demand intercept of every step, new_a [R, iters, T]; when it
+        is omitted it is drawn here from numpy's global generator exactly as the environment does inside play_game -- per step
+        one uniform, and a second one only when the first fell below noise_prob -- run after run, episode after episode, so a
+        seeded evaluation of one run equals the reference's."""
         g, R, n, T = self.game, self.n_runs, self.game.n_agents, self.game.max_steps
         p0 = torch.as_tensor(price0, dtype=torch.float64).reshape(R, -1).contiguous().to(self.device)
         iters = p0.shape[1]
+        if new_a is None and g.noise_prob > 0:
+            new_a = draw_demand_intercepts(g.a, g.noise_prob, R * iters * T).reshape(R, iters, T)
+        na = None if new_a is None else torch.as_tensor(np.ascontiguousarray(new_a, np.float64)).reshape(R, iters, T).to(self.device)
         rewards = self._zeros((R, iters * T, n), dtype=torch.float64, device=self.device)
         actions = self._zeros((R, iters * T, n), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            check(lib().thrl_greedy_eval_mlp(C.byref(g), R, self.table_dtype, _dp(self.q), _dp(self.mlp), iters, _dp(p0),
-                                             _dp(rewards), _dp(actions), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            check(lib().thrl_greedy_eval_noise(C.byref(g), R, self.table_dtype, _dp(self.q), _dp(self.mlp), iters, _dp(p0), _dp(na),
+                                               _dp(rewards), _dp(actions), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return actions, rewards
+
+
+def draw_demand_intercepts(a, noise_prob, steps):
+    """The demand intercepts of `steps` consecutive environment steps, drawn from numpy's global generator in the order
+    NoisyPriceState.step consumes it (environments.py:28-31): u = uniform(); new_a = uniform(0.7 a, a) if u < noise_prob else a."""
+    out = np.full(int(steps), float(a))
+    for t in range(int(steps)):
+        if np.random.uniform() < noise_prob:
+            out[t] = np.random.uniform(a * 0.7, a)
+    return out
 
 
 def save_checkpoint(batch, path, extra=None, extra_arrays=None):
